@@ -1,0 +1,220 @@
+/*
+ * rrnn.h -- C ABI of the B200-native RTE+RRTMGP-NN hot path (librrnn_b200.so).
+ *
+ * Drop-in boundary for the reference's NN gas optics + RTE flux solvers.  Every entry point cites the
+ * reference interface it replaces (paths relative to the reference tree).  The reference's own C seam
+ * is the bind(C) kernel layer (rte/kernels/mo_rte_solver_kernels.F90:125,546,1530); the type-bound
+ * Fortran procedures above it are mirrored by fortran/*.F90 (ISO_C_BINDING veneer) and by the Python
+ * host mirror in rte_rrtmgp_nn_b200/.
+ *
+ * Conventions
+ *  - All real data are fp32 (wp = sp, rte/mo_rte_kind.F90:29-33); integers are 32-bit.
+ *  - Array layout is the reference's: g-point fastest, then layer, then column:
+ *      Fortran (ngpt,nlay,ncol) == C [ncol][nlay][ngpt];  profiles (nlay,ncol) == C [ncol][nlay].
+ *  - Every function returns 0 on success, non-zero on error; rrnn_last_error() returns the message
+ *    (thread-local), the counterpart of the reference's character(len=128) error_msg.
+ *  - Pointers named *_d are DEVICE pointers valid on the context's device; work is enqueued on the
+ *    context's stream and is asynchronous w.r.t. the host.  Entry points ending in _host take HOST
+ *    pointers, stage through pinned memory and return after the results are in host memory.
+ *  - There is no CPU fallback: every compute entry point fails if no CUDA device is usable.
+ */
+#ifndef RRNN_H
+#define RRNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRNN_API __attribute__((visibility("default")))
+
+typedef struct rrnn_ctx rrnn_ctx_t;             /* device, stream, persistent workspace                 */
+typedef struct rrnn_model rrnn_model_t;         /* rrtmgp_network_type (neural/mod_network_rrtmgp.F90:34-53) */
+typedef struct rrnn_kdist rrnn_kdist_t;         /* spectral tables of ty_gas_optics_rrtmgp used on the NN path */
+typedef struct rrnn_cloud_lut rrnn_cloud_lut_t; /* ty_cloud_optics LUT state (extensions/cloud_optics/mo_cloud_optics.F90:32-70) */
+
+/* activation codes, neural/mod_layer.F90:64-95 */
+enum { RRNN_ACT_LINEAR = 0, RRNN_ACT_SOFTSIGN = 1, RRNN_ACT_RELU = 2, RRNN_ACT_SIGMOID = 3, RRNN_ACT_HARD_SIGMOID = 4 };
+
+/* One gas of ty_gas_concs (rrtmgp/mo_gas_concentrations.F90:50-88): conc is scalar, a per-layer profile
+ * or a full (nlay,ncol) field.  `conc` lives in the same memory space as the other arrays of the call
+ * (device for *_d entry points, host for *_host); scalars are passed by value in `value`. */
+typedef struct {
+  char name[32];     /* lower-case gas name, NUL- or blank-padded ("h2o", "o3", "co2", ...) */
+  const float* conc; /* ndims 1: [nlay]; ndims 2: [ncol][nlay]; ignored for ndims 0        */
+  float value;       /* ndims 0: the volume mixing ratio                                   */
+  int ndims;         /* 0, 1 or 2                                                          */
+} rrnn_gas_t;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* library / context                                                                                */
+RRNN_API const char* rrnn_last_error(void);
+RRNN_API int rrnn_version(void);
+RRNN_API int rrnn_device_count(void);
+/* stream: a cudaStream_t; NULL = the legacy default stream (the one PyTorch uses by default). */
+RRNN_API int rrnn_ctx_create(int device, void* stream, rrnn_ctx_t** out);
+RRNN_API int rrnn_ctx_destroy(rrnn_ctx_t* ctx);
+RRNN_API int rrnn_ctx_set_stream(rrnn_ctx_t* ctx, void* stream);
+RRNN_API void* rrnn_ctx_stream(rrnn_ctx_t* ctx);
+RRNN_API int rrnn_ctx_synchronize(rrnn_ctx_t* ctx);
+/* Run-time flags of rte/mo_rte_rrtmgp_config.F90:23-40.  lw_source_bug_compat = 1 (default) reproduces
+ * lw_source_noscat ignoring top_at_1 (rte/kernels/mo_rte_solver_kernels.F90:770-773); 0 orients the
+ * level sources physically for top_at_1 = false. */
+RRNN_API int rrnn_ctx_set_flag(rrnn_ctx_t* ctx, const char* name, int value);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+RRNN_API long long rrnn_ctx_launch_count(rrnn_ctx_t* ctx);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* NN models: rrtmgp_network_type%load_netcdf, neural/mod_network_rrtmgp.F90:58-122                   */
+RRNN_API int rrnn_model_load_netcdf(rrnn_ctx_t* ctx, const char* filename, rrnn_model_t** out);
+/* ASCII format of network_type%load (neural/mod_network.F90:163-209) + sidecar scaling file; see INTEGRATION.md */
+RRNN_API int rrnn_model_load_ascii(rrnn_ctx_t* ctx, const char* model_txt, const char* scaling_txt, rrnn_model_t** out);
+RRNN_API int rrnn_model_save_ascii(const rrnn_model_t* m, const char* model_txt, const char* scaling_txt);
+/* Build from host arrays: wpack = layer weights back to back, each row-major (n_in,n_out) (== the
+ * reference's column-major w_transposed(n_out,n_in)); input_names = nx*32 chars; ymean/ystd may be NULL. */
+RRNN_API int rrnn_model_create(rrnn_ctx_t* ctx, int nlayers, const int* dims, const float* wpack, const float* bpack,
+                               const int* activations, const float* xmin, const float* xmax, const float* ymean,
+                               const float* ystd, const char* input_names, rrnn_model_t** out);
+RRNN_API int rrnn_model_destroy(rrnn_model_t* m);
+RRNN_API int rrnn_model_nlayers(const rrnn_model_t* m);
+RRNN_API int rrnn_model_dims(const rrnn_model_t* m, int* dims_out /* nlayers+1 */);
+RRNN_API int rrnn_model_input_name(const rrnn_model_t* m, int i, char* buf32);
+RRNN_API int rrnn_model_activation(const rrnn_model_t* m, int layer);
+/* host copies of the parameters (for cross-checking the reader): which = 0 weights(layer), 1 bias(layer),
+ * 2 xmin, 3 xmax, 4 ymean, 5 ystd.  Returns the element count through n_out; data_out may be NULL. */
+RRNN_API int rrnn_model_get(const rrnn_model_t* m, int which, int layer, float* data_out, int* n_out);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Spectral tables (ty_gas_optics_rrtmgp%load, rrtmgp/mo_gas_optics_rrtmgp.F90:1130-1326): band->g-point
+ * limits (2,nbnd) 1-based inclusive, totplnk (nPlanckTemp,nbnd) == C [nbnd][ntemp] (may be NULL for SW),
+ * solar_source (ngpt) (may be NULL for LW). */
+RRNN_API int rrnn_kdist_create(rrnn_ctx_t* ctx, int nbnd, int ngpt, const int* band_lims_gpt, int ntemp,
+                               const float* totplnk, float temp_ref_min, float totplnk_delta,
+                               const float* solar_source, rrnn_kdist_t** out);
+RRNN_API int rrnn_kdist_destroy(rrnn_kdist_t* kd);
+/* ty_gas_optics_rrtmgp%set_tsi, rrtmgp/mo_gas_optics_rrtmgp.F90:1097-1120 */
+RRNN_API int rrnn_kdist_set_tsi(rrnn_kdist_t* kd, float tsi);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Gas optics building blocks (device pointers)                                                       */
+/* get_col_dry, rrtmgp/mo_gas_optics_rrtmgp.F90:1662-1707 (latitude absent) */
+RRNN_API int rrnn_get_col_dry(rrnn_ctx_t* ctx, int ncol, int nlay, const float* vmr_h2o_d, const float* plev_d, float* col_dry_d);
+/* level-temperature interpolation, rrtmgp/mo_gas_optics_rrtmgp.F90:326-335 */
+RRNN_API int rrnn_interp_tlev(rrnn_ctx_t* ctx, int ncol, int nlay, const float* play_d, const float* plev_d, const float* tlay_d, float* tlev_d);
+/* compute_nn_inputs, rrtmgp/mo_gas_optics_rrtmgp.F90:618-798 -> nn_inputs (ninputs,nlay,ncol) */
+RRNN_API int rrnn_compute_nn_inputs(rrnn_ctx_t* ctx, const rrnn_model_t* m, int ncol, int nlay, const float* play_d,
+                                    const float* tlay_d, const rrnn_gas_t* gases, int ngas, float* nn_inputs_d);
+/* output_sgemm_tau / _pfrac / _lw, neural/mod_network_rrtmgp.F90:125-236, 238-317, 319-409 (x: (nx,nbatch)) */
+RRNN_API int rrnn_output_sgemm_tau(rrnn_ctx_t* ctx, const rrnn_model_t* m, int nbatch, const float* x_d, const float* coldry_d,
+                                   float* output_d, float* output2_d /* NULL or tau_abs in / tau_tot out */);
+RRNN_API int rrnn_output_sgemm_pfrac(rrnn_ctx_t* ctx, const rrnn_model_t* m, int nbatch, const float* x_d, float* output_d);
+RRNN_API int rrnn_output_sgemm_lw(rrnn_ctx_t* ctx, const rrnn_model_t* m, int nbatch, const float* x_d, float* output_d);
+/* compute_Planck_source_nn, rrtmgp/kernels/mo_gas_optics_kernels.F90:615-683: pfrac_lay_source_d holds the
+ * Planck fraction on input and lay_source on output; sfc_lay is 1-based. */
+RRNN_API int rrnn_planck_source_nn(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int ncol, int nlay, const float* tlay_d,
+                                   const float* tlev_d, const float* tsfc_d, int sfc_lay, float* sfc_source_d,
+                                   float* sfc_source_Jac_d, float* pfrac_lay_source_d, float* lev_source_d);
+
+/* ty_gas_optics_rrtmgp%gas_optics with neural_nets present.
+ * LW = gas_optics_int NN branch, rrtmgp/mo_gas_optics_rrtmgp.F90:239-428 (:368-411): nmodels = 2 (tau net,
+ *      Planck-fraction net) or 1 ("both" net, 2*ngpt outputs); tlev_d may be NULL (-> interpolation :326-335).
+ *      One fused kernel: input scaling + col_dry + MLP chain + tau / Planck-source epilogues.
+ * SW = gas_optics_ext NN branch, :433-602 (:529-573, :594-599): models[0] absorption, models[1] Rayleigh;
+ *      ssa_d NULL -> 1scl request (absorption tau only); g_d NULL -> g (identically 0, :560-567) not materialised. */
+RRNN_API int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                                int ncol, int nlay, const float* play_d, const float* plev_d, const float* tlay_d,
+                                const float* tsfc_d, const rrnn_gas_t* gases, int ngas, const float* tlev_d,
+                                float* tau_d, float* lay_source_d, float* lev_source_d, float* sfc_source_d,
+                                float* sfc_source_Jac_d);
+RRNN_API int rrnn_gas_optics_sw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol,
+                                int nlay, const float* play_d, const float* plev_d, const float* tlay_d,
+                                const rrnn_gas_t* gases, int ngas, float* tau_d, float* ssa_d, float* g_d,
+                                float* toa_src_d);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* RTE solvers (device pointers)                                                                      */
+/* lw_solver_noscat_GaussQuad / lw_solver_noscat, rte/kernels/mo_rte_solver_kernels.F90:332-415, 119-330
+ * (no rescaling, no Jacobian): Ds/weights are HOST arrays of nmus entries; inc_flux_d may be NULL (= 0). */
+RRNN_API int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* Ds,
+                                   const float* weights, const float* inc_flux_d, const float* tau_d,
+                                   const float* lay_source_d, const float* lev_source_d, const float* sfc_emis_gpt_d,
+                                   const float* sfc_source_d, float* flux_up_d, float* flux_dn_d);
+/* rte_lw for ty_optical_props_1scl, rte/mo_rte_lw.F90:60-424: sfc_emis_d is (nbnd,ncol) and is expanded to
+ * g-points (:429-447); n_gauss_angles in 1..4 with the secants/weights of :113-125. */
+RRNN_API int rrnn_rte_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,
+                         const float* inc_flux_d, const float* tau_d, const float* lay_source_d,
+                         const float* lev_source_d, const float* sfc_source_d, const float* sfc_emis_d,
+                         float* flux_up_d, float* flux_dn_d);
+/* sw_solver_2stream, rte/kernels/mo_rte_solver_kernels.F90:541-692 (two-stream :1366-1480 + adding :1526-1637).
+ * inc_flux_dif_d may be NULL (= 0, rte/mo_rte_sw.F90:191-205); g_d may be NULL (g = 0). */
+RRNN_API int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux_d,
+                                    const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
+                                    const float* mu0_d, const float* sfc_alb_dir_d, const float* sfc_alb_dif_d,
+                                    float* flux_up_d, float* flux_dn_d, float* flux_dir_d);
+/* rte_sw for ty_optical_props_2str, rte/mo_rte_sw.F90:48-266 (albedos per g-point, :50-61). */
+RRNN_API int rrnn_rte_sw(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* mu0_d,
+                         const float* inc_flux_d, const float* sfc_alb_dir_gpt_d, const float* sfc_alb_dif_gpt_d,
+                         const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
+                         float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Cloud optics (LUT), delta-scaling, increments, heating rates                                        */
+/* ty_cloud_optics%load_lut, extensions/cloud_optics/mo_cloud_optics.F90:90-170: tables are
+ * (nsize,nbnd) == C [nbnd][nsize] for the chosen ice roughness. */
+RRNN_API int rrnn_cloud_lut_create(rrnn_ctx_t* ctx, int nbnd, int nsize_liq, int nsize_ice, float radliq_lwr, float radliq_upr,
+                                   float radice_lwr, float radice_upr, const float* lut_extliq, const float* lut_ssaliq,
+                                   const float* lut_asyliq, const float* lut_extice, const float* lut_ssaice,
+                                   const float* lut_asyice, rrnn_cloud_lut_t** out);
+RRNN_API int rrnn_cloud_lut_destroy(rrnn_cloud_lut_t* lut);
+/* ty_cloud_optics%cloud_optics, mo_cloud_optics.F90:354-535 (compute_all_from_table :603-645): by-band
+ * (nbnd,nlay,ncol) outputs; ssa_d = g_d = NULL -> 1scl absorption optical depth (:505-513). */
+RRNN_API int rrnn_cloud_optics(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, int ncol, int nlay, const float* clwp_d,
+                               const float* ciwp_d, const float* reliq_d, const float* reice_d, float* tau_d, float* ssa_d,
+                               float* g_d);
+/* delta_scale_2str_k, rte/kernels/mo_optical_props_kernels.F90:72-93 (n = number of elements) */
+RRNN_API int rrnn_delta_scale_2str(rrnn_ctx_t* ctx, size_t n, float* tau_d, float* ssa_d, float* g_d);
+/* inc_1scalar_by_1scalar_bybnd :358-378 and inc_2stream_by_2stream_bybnd :453-485; gpt_lims from kd.
+ */
+RRNN_API int rrnn_increment_1scl_bybnd(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, float* tau1_d, const float* tau2_d);
+RRNN_API int rrnn_increment_2str_bybnd(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, float* tau1_d, float* ssa1_d,
+                                       float* g1_d, const float* tau2_d, const float* ssa2_d, const float* g2_d);
+/* compute_heating_rate, extensions/mo_heating_rates.F90:26-54 [K/s] (this fork's (nlay+1,ncol) layout) and
+ * calc_heating_rate, examples/rrtmgp-nn-training/rrtmgp_lw_eval_nn_rfmip.F90:624-653 [K/day]. */
+RRNN_API int rrnn_heating_rate(rrnn_ctx_t* ctx, int ncol, int nlay, const float* flux_up_d, const float* flux_dn_d,
+                               const float* plev_d, float* heating_rate_d);
+RRNN_API int rrnn_calc_heating_rate(rrnn_ctx_t* ctx, int ncol, int nlay, const float* flux_up_d, const float* flux_dn_d,
+                                    const float* plev_d, float* hr_K_day_d);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Whole-path drivers with HOST buffers: what one iteration of the reference drivers' block loop does
+ * (examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:368-446, rrtmgp_rfmip_sw.F90:356-465): gas_optics -> rte_lw /
+ * rte_sw, here for all columns at once, in column chunks that fit the device workspace, H2D/D2H overlapped
+ * with compute.  sfc_emis/sfc_alb are per column (spectrally constant, as in the RFMIP drivers); mu0 <= 0
+ * marks night columns (fluxes zeroed, rrtmgp_rfmip_sw.F90:458-463).  tsi_scale may be NULL; else the
+ * per-column TSI renormalisation of :409-416 is applied.  Gas conc pointers are HOST pointers.           */
+RRNN_API int rrnn_lw_fluxes_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                                 int ncol, int nlay, int top_at_1, int n_gauss_angles, const float* play, const float* plev,
+                                 const float* tlay, const float* tlev, const float* tsfc, const float* sfc_emis,
+                                 const rrnn_gas_t* gases, int ngas, float* flux_up, float* flux_dn);
+RRNN_API int rrnn_sw_fluxes_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol,
+                                 int nlay, int top_at_1, const float* play, const float* plev, const float* tlay,
+                                 const float* mu0, const float* sfc_alb, const float* tsi, const rrnn_gas_t* gases,
+                                 int ngas, float* flux_up, float* flux_dn, float* flux_dn_dir);
+/* Same path with DEVICE buffers (inputs already resident; used for the kernel-only throughput number). */
+RRNN_API int rrnn_lw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                            int ncol, int nlay, int top_at_1, int n_gauss_angles, const float* play_d, const float* plev_d,
+                            const float* tlay_d, const float* tlev_d, const float* tsfc_d, const float* sfc_emis_d,
+                            const rrnn_gas_t* gases, int ngas, float* flux_up_d, float* flux_dn_d);
+RRNN_API int rrnn_sw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol, int nlay,
+                            int top_at_1, const float* play_d, const float* plev_d, const float* tlay_d, const float* mu0_d,
+                            const float* sfc_alb_d, const float* tsi_d, const rrnn_gas_t* gases, int ngas,
+                            float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d);
+/* Column chunk used by the drivers above (0 = automatic from free device memory). */
+RRNN_API int rrnn_ctx_set_chunk_columns(rrnn_ctx_t* ctx, int ncol_chunk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRNN_H */

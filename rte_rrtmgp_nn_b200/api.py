@@ -1,0 +1,703 @@
+"""Host-side mirror of the reference's Fortran API for the NN gas optics + RTE path.
+
+Same names, argument meaning and error behaviour as the reference (functions return the reference's
+`error_msg` string, empty on success), bodies forward to the C ABI (include/rrnn.h).  Device arrays are
+torch CUDA tensors (PyTorch is only the allocator / stream provider here); layouts are the reference's with
+the g-point fastest: tau[ncol, nlay, ngpt] == Fortran tau(ngpt, nlay, ncol).
+
+  rrtmgp_network_type      neural/mod_network_rrtmgp.F90:34-53
+  ty_gas_concs             rrtmgp/mo_gas_concentrations.F90:50-88
+  ty_gas_optics_rrtmgp     rrtmgp/mo_gas_optics_rrtmgp.F90:61-200 (gas_optics :239-243, :433-437)
+  ty_optical_props_1scl/_2str  rte/mo_optical_props.F90:98-192
+  ty_source_func_lw        rte/mo_source_functions.F90:26-43
+  ty_fluxes_broadband      rte/mo_fluxes.F90:46-67
+  rte_lw / rte_sw          rte/mo_rte_lw.F90:60-64, rte/mo_rte_sw.F90:48-52
+  ty_cloud_optics          extensions/cloud_optics/mo_cloud_optics.F90:32-70, :354-535
+  compute_heating_rate     extensions/mo_heating_rates.F90:26-54
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import RRNNError, rrnn_gas_t, vp
+
+ACT_NAMES = ["linear", "softsign", "relu", "sigmoid", "hard_sigmoid"]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Context:
+    """rrnn_ctx_t: one per GPU / host thread; calls on one context are stream-ordered."""
+
+    def __init__(self, device=0, stream=None):
+        self.h = vp()
+        _lib.check(_lib.lib().rrnn_ctx_create(int(device), vp(stream) if stream else None, C.byref(self.h)))
+        self.device = int(device)
+
+    def synchronize(self):
+        _lib.check(_lib.lib().rrnn_ctx_synchronize(self.h))
+
+    def set_flag(self, name, value):
+        _lib.check(_lib.lib().rrnn_ctx_set_flag(self.h, name.encode(), int(value)))
+
+    def set_chunk_columns(self, n):
+        _lib.check(_lib.lib().rrnn_ctx_set_chunk_columns(self.h, int(n)))
+
+    @property
+    def stream(self):
+        return _lib.lib().rrnn_ctx_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return int(_lib.lib().rrnn_ctx_launch_count(self.h))
+
+    def torch_stream(self):
+        torch = _torch()
+        return torch.cuda.ExternalStream(self.stream, device=torch.device("cuda", self.device))
+
+    def close(self):
+        if self.h:
+            _lib.lib().rrnn_ctx_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def _dev(t, ctx=None):
+    """float32 contiguous CUDA tensor from tensor / ndarray / None."""
+    if t is None:
+        return None
+    torch = _torch()
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32))
+    dev = torch.device("cuda", ctx.device if ctx else 0)
+    if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(device=dev, dtype=torch.float32).contiguous()
+    return t
+
+
+def _ptr(t):
+    return vp(t.data_ptr()) if t is not None else None
+
+
+class rrtmgp_network_type:
+    """The reference's network container; `load_netcdf` reads the shipped netCDF-4 weight files."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx
+        self.h = vp()
+
+    def load_netcdf(self, filename):
+        ctxh = self.ctx.h if self.ctx is not None else None
+        _lib.check(_lib.lib().rrnn_model_load_netcdf(ctxh, str(filename).encode(), C.byref(self.h)))
+        return self
+
+    def load(self, model_txt, scaling_txt):
+        ctxh = self.ctx.h if self.ctx is not None else None
+        _lib.check(_lib.lib().rrnn_model_load_ascii(ctxh, str(model_txt).encode(), str(scaling_txt).encode(), C.byref(self.h)))
+        return self
+
+    def save(self, model_txt, scaling_txt):
+        _lib.check(_lib.lib().rrnn_model_save_ascii(self.h, str(model_txt).encode(), str(scaling_txt).encode()))
+
+    @classmethod
+    def from_arrays(cls, ctx, model):
+        """model: dict as produced by oracle.nc4min.load_nn_model (dims, W, b, activations, ...)."""
+        self = cls(ctx)
+        dims = np.asarray(model["dims"], np.int32)
+        wpack = np.concatenate([np.ascontiguousarray(w, np.float32).ravel() for w in model["W"]])
+        bpack = np.concatenate([np.asarray(b, np.float32).ravel() for b in model["b"]])
+        act = np.asarray([ACT_NAMES.index(a) for a in model["activations"]], np.int32)
+        names = b"".join(n.encode().ljust(32) for n in model["input_names"])
+        fp = lambda a: None if a is None else np.ascontiguousarray(a, np.float32).ctypes.data_as(_lib.c_float_p)
+        keep = [np.ascontiguousarray(model[k], np.float32) if model.get(k) is not None else None
+                for k in ("xmin", "xmax", "ymean", "ystd")]
+        _lib.check(_lib.lib().rrnn_model_create(ctx.h if ctx else None, len(dims) - 1, dims.ctypes.data_as(_lib.c_int_p),
+                                                wpack.ctypes.data_as(_lib.c_float_p), bpack.ctypes.data_as(_lib.c_float_p),
+                                                act.ctypes.data_as(_lib.c_int_p), fp(keep[0]), fp(keep[1]), fp(keep[2]),
+                                                fp(keep[3]), names, C.byref(self.h)))
+        return self
+
+    @property
+    def dims(self):
+        n = _lib.lib().rrnn_model_nlayers(self.h)
+        d = (C.c_int * (n + 1))()
+        _lib.check(_lib.lib().rrnn_model_dims(self.h, d))
+        return list(d)
+
+    @property
+    def input_names(self):
+        out = []
+        for i in range(self.dims[0]):
+            b = C.create_string_buffer(32)
+            _lib.check(_lib.lib().rrnn_model_input_name(self.h, i, b))
+            out.append(b.value.decode())
+        return out
+
+    @property
+    def activations(self):
+        return [ACT_NAMES[_lib.lib().rrnn_model_activation(self.h, l)] for l in range(len(self.dims) - 1)]
+
+    def _get(self, which, layer=0):
+        n = C.c_int(0)
+        _lib.check(_lib.lib().rrnn_model_get(self.h, which, layer, None, C.byref(n)))
+        if n.value == 0:
+            return None
+        a = np.empty(n.value, np.float32)
+        _lib.check(_lib.lib().rrnn_model_get(self.h, which, layer, a.ctypes.data_as(_lib.c_float_p), C.byref(n)))
+        return a
+
+    def weights(self, layer):
+        d = self.dims
+        return self._get(0, layer).reshape(d[layer], d[layer + 1])
+
+    def bias(self, layer):
+        return self._get(1, layer)
+
+    coeffs_input_min = property(lambda self: self._get(2))
+    coeffs_input_max = property(lambda self: self._get(3))
+    coeffs_output_mean = property(lambda self: self._get(4))
+    coeffs_output_std = property(lambda self: self._get(5))
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rrnn_model_destroy(self.h)
+        except Exception:
+            pass
+
+
+class ty_gas_concs:
+    """Gas volume mixing ratios by name: scalar, per-layer profile (nlay) or full field (ncol, nlay)."""
+
+    def __init__(self, gas_names=None):
+        self.gas_name = []
+        self.concs = {}
+        if gas_names:
+            self.init(gas_names)
+
+    def init(self, gas_names):
+        self.gas_name = [g.strip().lower() for g in gas_names]
+        self.concs = {}
+        return ""
+
+    def set_vmr(self, gas, w):
+        gas = gas.strip().lower()
+        if gas not in self.gas_name:
+            self.gas_name.append(gas)
+        if np.ndim(w) == 0:
+            w = float(w)
+            if w < 0.0 or w > 1.0:
+                return "ty_gas_concs%set_vmr(): concentrations should be >= 0, <= 1"
+        self.concs[gas] = w
+        return ""
+
+    def get_vmr(self, gas):
+        return self.concs[gas.strip().lower()]
+
+    def _to_c(self, ctx, host=False):
+        """-> (array of rrnn_gas_t, keep-alive list)."""
+        items = list(self.concs.items())
+        arr = (rrnn_gas_t * max(1, len(items)))()
+        keep = []
+        for i, (name, v) in enumerate(items):
+            arr[i].name = name.encode()
+            if np.ndim(v) == 0:
+                arr[i].ndims = 0; arr[i].value = float(v); arr[i].conc = None
+            else:
+                if host:
+                    t = np.ascontiguousarray(v, np.float32)
+                    arr[i].conc = t.ctypes.data
+                else:
+                    t = _dev(v, ctx)
+                    arr[i].conc = t.data_ptr()
+                keep.append(t)
+                arr[i].ndims = t.ndim
+        return arr, len(items), keep
+
+
+class _kdist_handle:
+    def __init__(self, ctx, kd):
+        self.h = vp()
+        bl = np.ascontiguousarray(kd["band_lims_gpt"], np.int32)
+        tot = kd.get("totplnk")
+        sol = kd.get("solar_source")
+        fp = lambda a: None if a is None else np.ascontiguousarray(a, np.float32).ctypes.data_as(_lib.c_float_p)
+        tot_a = None if tot is None else np.ascontiguousarray(tot, np.float32)
+        sol_a = None if sol is None else np.ascontiguousarray(sol, np.float32)
+        ntemp = 0 if tot_a is None else tot_a.shape[1]
+        _lib.check(_lib.lib().rrnn_kdist_create(ctx.h, int(kd["nbnd"]), int(kd["ngpt"]), bl.ctypes.data_as(_lib.c_int_p), ntemp,
+                                                fp(tot_a), float(kd.get("temp_ref_min", 0.0)), float(kd.get("totplnk_delta", 1.0)),
+                                                fp(sol_a), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rrnn_kdist_destroy(self.h)
+        except Exception:
+            pass
+
+
+class ty_optical_props:
+    """Spectral discretisation base (rte/mo_optical_props.F90:62-96)."""
+
+    def __init__(self):
+        self.band2gpt = None
+        self.ngpt = 0
+        self.nband = 0
+        self.name = ""
+
+    def init(self, spectral, name=""):
+        if isinstance(spectral, ty_optical_props):
+            self.band2gpt, self.ngpt, self.nband = spectral.band2gpt, spectral.ngpt, spectral.nband
+            self._kd = getattr(spectral, "_kd", None)
+        else:
+            self.band2gpt = np.asarray(spectral["band_lims_gpt"], np.int32)
+            self.ngpt = int(spectral["ngpt"]); self.nband = int(spectral["nbnd"])
+        self.name = name
+        return ""
+
+    def get_ngpt(self): return self.ngpt
+    def get_nband(self): return self.nband
+    def get_band_lims_gpoint(self): return self.band2gpt
+    def get_name(self): return self.name
+
+
+class ty_optical_props_1scl(ty_optical_props):
+    def __init__(self):
+        super().__init__()
+        self.tau = None
+
+    def alloc_1scl(self, ncol, nlay, spectral=None, name="", by_band=False, ctx=None):
+        torch = _torch()
+        if spectral is not None:
+            self.init(spectral, name)
+        self.ctx = ctx or getattr(spectral, "ctx", None) or default_context()
+        n = self.nband if by_band else self.ngpt
+        self.by_band = by_band
+        self.tau = torch.empty((ncol, nlay, n), dtype=torch.float32, device=torch.device("cuda", self.ctx.device))
+        return ""
+
+    def get_ncol(self): return self.tau.shape[0]
+    def get_nlay(self): return self.tau.shape[1]
+
+    def increment(self, op_io):
+        """op_io := op_io + self, self given by band (inc_1scalar_by_1scalar_bybnd)."""
+        if not getattr(self, "by_band", False):
+            op_io.tau += self.tau
+            return ""
+        try:
+            _lib.check(_lib.lib().rrnn_increment_1scl_bybnd(op_io.ctx.h, op_io._kd.h, op_io.get_nlay(), op_io.get_ncol(),
+                                                            _ptr(op_io.tau), _ptr(self.tau)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+
+class ty_optical_props_2str(ty_optical_props):
+    def __init__(self):
+        super().__init__()
+        self.tau = None
+        self.ssa = None
+        self._g = None
+        self.g_is_zero = False
+
+    def alloc_2str(self, ncol, nlay, spectral=None, name="", by_band=False, ctx=None):
+        torch = _torch()
+        if spectral is not None:
+            self.init(spectral, name)
+        self.ctx = ctx or getattr(spectral, "ctx", None) or default_context()
+        n = self.nband if by_band else self.ngpt
+        self.by_band = by_band
+        dev = torch.device("cuda", self.ctx.device)
+        self.tau = torch.empty((ncol, nlay, n), dtype=torch.float32, device=dev)
+        self.ssa = torch.empty((ncol, nlay, n), dtype=torch.float32, device=dev)
+        self._g = None
+        self.g_is_zero = False
+        return ""
+
+    @property
+    def g(self):
+        """Asymmetry parameter; materialised on first use (gas optics leaves it as an implicit zero)."""
+        torch = _torch()
+        if self._g is None:
+            with torch.cuda.stream(self.ctx.torch_stream()):
+                self._g = (torch.zeros_like(self.tau) if self.g_is_zero else torch.empty_like(self.tau))
+        return self._g
+
+    @g.setter
+    def g(self, v):
+        self._g = v
+        self.g_is_zero = False
+
+    def get_ncol(self): return self.tau.shape[0]
+    def get_nlay(self): return self.tau.shape[1]
+
+    def delta_scale(self):
+        try:
+            _lib.check(_lib.lib().rrnn_delta_scale_2str(self.ctx.h, self.tau.numel(), _ptr(self.tau), _ptr(self.ssa), _ptr(self.g)))
+        except RRNNError as e:
+            return str(e)
+        self.g_is_zero = False
+        return ""
+
+    def increment(self, op_io):
+        """op_io := op_io + self, self given by band (inc_2stream_by_2stream_bybnd)."""
+        try:
+            g1 = op_io.g  # materialises zeros if needed
+            _lib.check(_lib.lib().rrnn_increment_2str_bybnd(op_io.ctx.h, op_io._kd.h, op_io.get_nlay(), op_io.get_ncol(),
+                                                            _ptr(op_io.tau), _ptr(op_io.ssa), _ptr(g1), _ptr(self.tau),
+                                                            _ptr(self.ssa), _ptr(self.g)))
+            op_io.g_is_zero = False
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+
+class ty_source_func_lw(ty_optical_props):
+    def __init__(self):
+        super().__init__()
+        self.lay_source = self.lev_source = self.sfc_source = self.sfc_source_Jac = None
+
+    def alloc(self, ncol, nlay, spectral=None, ctx=None):
+        torch = _torch()
+        if spectral is not None:
+            self.init(spectral)
+        self.ctx = ctx or getattr(spectral, "ctx", None) or default_context()
+        dev = torch.device("cuda", self.ctx.device)
+        G = self.ngpt
+        self.lay_source = torch.empty((ncol, nlay, G), dtype=torch.float32, device=dev)
+        self.lev_source = torch.empty((ncol, nlay + 1, G), dtype=torch.float32, device=dev)
+        self.sfc_source = torch.empty((ncol, G), dtype=torch.float32, device=dev)
+        self.sfc_source_Jac = torch.empty((ncol, G), dtype=torch.float32, device=dev)
+        return ""
+
+    def get_ncol(self): return self.lay_source.shape[0]
+    def get_nlay(self): return self.lay_source.shape[1]
+
+
+class ty_fluxes_broadband:
+    """Output holder: the caller associates the arrays it wants (all (ncol, nlay+1))."""
+
+    def __init__(self, flux_up=None, flux_dn=None, flux_net=None, flux_dn_dir=None):
+        self.flux_up, self.flux_dn, self.flux_net, self.flux_dn_dir = flux_up, flux_dn, flux_net, flux_dn_dir
+
+    def are_desired(self):
+        return any(v is not None for v in (self.flux_up, self.flux_dn, self.flux_net, self.flux_dn_dir))
+
+
+class ty_gas_optics_rrtmgp(ty_optical_props):
+    """The NN path of the RRTMGP gas optics.  `load` takes the spectral tables of the k-distribution
+    (rte_rrtmgp_nn_b200.spectral.make_kdist / synthetic_kdist_*)."""
+
+    def __init__(self, ctx=None):
+        super().__init__()
+        self.ctx = ctx or default_context()
+        self.kd = None
+        self._kd = None
+
+    def load(self, kd):
+        self.kd = dict(kd)
+        self.init(kd, "ty_gas_optics_rrtmgp")
+        self._kd = _kdist_handle(self.ctx, self.kd)
+        return ""
+
+    def source_is_internal(self):
+        return self.kd.get("totplnk") is not None
+
+    def source_is_external(self):
+        return self.kd.get("solar_source") is not None
+
+    def get_press_min(self): return self.kd["press_ref_min"]
+    def get_press_max(self): return self.kd["press_ref_max"]
+    def get_temp_min(self): return self.kd["temp_ref_min"]
+    def get_temp_max(self): return self.kd["temp_ref_max"]
+
+    def set_tsi(self, tsi):
+        try:
+            _lib.check(_lib.lib().rrnn_kdist_set_tsi(self._kd.h, float(tsi)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+    def gas_optics(self, play, plev, tlay, *args, col_dry=None, tlev=None, neural_nets=None):
+        """LW: gas_optics(play, plev, tlay, tsfc, gas_desc, optical_props, sources [,col_dry][,tlev][,neural_nets])
+           SW: gas_optics(play, plev, tlay, gas_desc, optical_props, toa_src [,col_dry][,neural_nets])."""
+        if neural_nets is None:
+            return "gas_optics(): only the neural-network path (neural_nets=) is implemented; the LUT path is out of scope"
+        if col_dry is not None:
+            return "gas_optics(): optional col_dry is not supported on the neural-network path (as in the reference)"
+        ctx = self.ctx
+        play, plev, tlay = _dev(play, ctx), _dev(plev, ctx), _dev(tlay, ctx)
+        ncol, nlay = play.shape
+        lib = _lib.lib()
+        models = (vp * 2)(*[n.h for n in neural_nets][:2])
+        try:
+            if self.source_is_internal():
+                tsfc, gas_desc, optical_props, sources = args
+                tsfc = _dev(tsfc, ctx)
+                tlev_d = _dev(tlev, ctx)
+                gases, ngas, keep = gas_desc._to_c(ctx)
+                if sources.get_ncol() != ncol or sources.get_nlay() != nlay or sources.ngpt != self.ngpt:
+                    return "gas_optics%gas_optics: source function arrays inconsistently sized"
+                optical_props._kd = self._kd
+                _lib.check(lib.rrnn_gas_optics_lw(ctx.h, self._kd.h, models, len(neural_nets), ncol, nlay, _ptr(play), _ptr(plev),
+                                                  _ptr(tlay), _ptr(tsfc), gases, ngas, _ptr(tlev_d), _ptr(optical_props.tau),
+                                                  _ptr(sources.lay_source), _ptr(sources.lev_source), _ptr(sources.sfc_source),
+                                                  _ptr(sources.sfc_source_Jac)))
+            else:
+                gas_desc, optical_props, toa_src = args
+                gases, ngas, keep = gas_desc._to_c(ctx)
+                optical_props._kd = self._kd
+                if isinstance(optical_props, ty_optical_props_2str):
+                    optical_props._g = None
+                    optical_props.g_is_zero = True   # g(:,:,:) = 0, mo_gas_optics_rrtmgp.F90:560-567 (kept implicit)
+                    ssa_p = _ptr(optical_props.ssa)
+                else:
+                    ssa_p = None
+                if tuple(toa_src.shape) != (ncol, self.ngpt):
+                    return "gas_optics(): array toa_src has wrong size"
+                _lib.check(lib.rrnn_gas_optics_sw(ctx.h, self._kd.h, models, ncol, nlay, _ptr(play), _ptr(plev), _ptr(tlay), gases,
+                                                  ngas, _ptr(optical_props.tau), ssa_p, None, _ptr(toa_src)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+
+def rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes, inc_flux=None, n_gauss_angles=None, use_2stream=None,
+           lw_Ds=None, flux_up_Jac=None, flux_dn_Jac=None):
+    """rte_lw (rte/mo_rte_lw.F90:60-64) for ty_optical_props_1scl; sfc_emis is (ncol, nband)."""
+    if not fluxes.are_desired():
+        return "rte_lw: no space allocated for fluxes"
+    if not isinstance(optical_props, ty_optical_props_1scl):
+        return "rte_lw: only ty_optical_props_1scl (no-scattering) is implemented"
+    if use_2stream:
+        return "rte_lw: can't use two-stream methods with only absorption optical depth"
+    if lw_Ds is not None or flux_up_Jac is not None or flux_dn_Jac is not None:
+        return "rte_lw: lw_Ds / Jacobians are not implemented"
+    ctx = optical_props.ctx
+    nang = 1 if n_gauss_angles is None else int(n_gauss_angles)
+    if nang > 4:
+        return "rte_lw: asking for too many quadrature points for no-scattering calculation"
+    if nang < 1:
+        return "rte_lw: have to ask for at least one quadrature point for no-scattering calculation"
+    ncol, nlay = optical_props.get_ncol(), optical_props.get_nlay()
+    sfc_emis = _dev(sfc_emis, ctx)
+    if tuple(sfc_emis.shape) != (ncol, optical_props.nband):
+        return "rte_lw: sfc_emis inconsistently sized"
+    inc = _dev(inc_flux, ctx)
+    try:
+        _lib.check(_lib.lib().rrnn_rte_lw(ctx.h, optical_props._kd.h, nlay, ncol, int(bool(top_at_1)), nang, _ptr(inc),
+                                          _ptr(optical_props.tau), _ptr(sources.lay_source), _ptr(sources.lev_source),
+                                          _ptr(sources.sfc_source), _ptr(sfc_emis), _ptr(fluxes.flux_up), _ptr(fluxes.flux_dn)))
+    except RRNNError as e:
+        return str(e)
+    return ""
+
+
+def rte_sw(atmos, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, fluxes, inc_flux_dif=None):
+    """rte_sw (rte/mo_rte_sw.F90:48-52) for ty_optical_props_2str; albedos are per g-point (ncol, ngpt)."""
+    if not fluxes.are_desired():
+        return "rte_sw: no space allocated for fluxes"
+    if not isinstance(atmos, ty_optical_props_2str):
+        return "rte_sw: only ty_optical_props_2str (two-stream) is implemented"
+    ctx = atmos.ctx
+    ncol, nlay, ngpt = atmos.get_ncol(), atmos.get_nlay(), atmos.ngpt
+    mu0, inc_flux = _dev(mu0, ctx), _dev(inc_flux, ctx)
+    a_dir, a_dif = _dev(sfc_alb_dir_gpt, ctx), _dev(sfc_alb_dif_gpt, ctx)
+    if tuple(mu0.shape) != (ncol,):
+        return "rte_sw: mu0 inconsistently sized"
+    if tuple(inc_flux.shape) != (ncol, ngpt):
+        return "rte_sw: inc_flux inconsistently sized"
+    if tuple(a_dir.shape) != (ncol, ngpt):
+        return "rte_sw: sfc_alb_dir inconsistently sized"
+    if tuple(a_dif.shape) != (ncol, ngpt):
+        return "rte_sw: sfc_alb_dif inconsistently sized"
+    g_p = None if atmos.g_is_zero and atmos._g is None else _ptr(atmos.g)
+    try:
+        _lib.check(_lib.lib().rrnn_rte_sw(ctx.h, ngpt, nlay, ncol, int(bool(top_at_1)), _ptr(mu0), _ptr(inc_flux), _ptr(a_dir),
+                                          _ptr(a_dif), _ptr(_dev(inc_flux_dif, ctx)), _ptr(atmos.tau), _ptr(atmos.ssa), g_p,
+                                          _ptr(fluxes.flux_up), _ptr(fluxes.flux_dn), _ptr(fluxes.flux_dn_dir)))
+    except RRNNError as e:
+        return str(e)
+    return ""
+
+
+class ty_cloud_optics(ty_optical_props):
+    def __init__(self, ctx=None):
+        super().__init__()
+        self.ctx = ctx or default_context()
+        self.h = vp()
+        self.icergh = 0
+
+    def load(self, band_lims_wvn, radliq_lwr, radliq_upr, radliq_fac, radice_lwr, radice_upr, radice_fac,
+             lut_extliq, lut_ssaliq, lut_asyliq, lut_extice, lut_ssaice, lut_asyice, ice_roughness=2):
+        """load_lut; tables as stored in the coefficient files: liq [nbnd][nsize], ice [nrough][nbnd][nsize]."""
+        self.nband = self.ngpt = int(np.shape(lut_extliq)[0])
+        self.band2gpt = np.array([[b + 1, b + 1] for b in range(self.nband)], np.int32)
+        self.icergh = int(ice_roughness)
+        r = self.icergh - 1
+        fa = lambda a: np.ascontiguousarray(a, np.float32)
+        t = [fa(lut_extliq), fa(lut_ssaliq), fa(lut_asyliq), fa(np.asarray(lut_extice)[r]), fa(np.asarray(lut_ssaice)[r]),
+             fa(np.asarray(lut_asyice)[r])]
+        self.tables = dict(extliq=t[0], ssaliq=t[1], asyliq=t[2], extice=t[3], ssaice=t[4], asyice=t[5],
+                           liq_nsteps=t[0].shape[1], ice_nsteps=t[3].shape[1], radliq_lwr=float(radliq_lwr),
+                           radice_lwr=float(radice_lwr),
+                           liq_step_size=float(np.float32(radliq_upr - radliq_lwr) / np.float32(t[0].shape[1] - 1)),
+                           ice_step_size=float(np.float32(radice_upr - radice_lwr) / np.float32(t[3].shape[1] - 1)))
+        p = [a.ctypes.data_as(_lib.c_float_p) for a in t]
+        try:
+            _lib.check(_lib.lib().rrnn_cloud_lut_create(self.ctx.h, self.nband, t[0].shape[1], t[3].shape[1], float(radliq_lwr),
+                                                        float(radliq_upr), float(radice_lwr), float(radice_upr), *p,
+                                                        C.byref(self.h)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+    def cloud_optics(self, clwp, ciwp, reliq, reice, optical_props):
+        ctx = self.ctx
+        a = [_dev(v, ctx) for v in (clwp, ciwp, reliq, reice)]
+        ncol, nlay = a[0].shape
+        if optical_props.get_ncol() != ncol or optical_props.get_nlay() != nlay:
+            return "cloud optics: optical_props have wrong extents"
+        if optical_props.tau.shape[-1] != self.nband:
+            return "cloud optics: optical properties must be requested by band not g-points"
+        two = isinstance(optical_props, ty_optical_props_2str)
+        try:
+            _lib.check(_lib.lib().rrnn_cloud_optics(ctx.h, self.h, ncol, nlay, *[_ptr(v) for v in a], _ptr(optical_props.tau),
+                                                    _ptr(optical_props.ssa) if two else None,
+                                                    _ptr(optical_props.g) if two else None))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().rrnn_cloud_lut_destroy(self.h)
+        except Exception:
+            pass
+
+
+def load_cloud_lut_file(path):
+    """Read a cloud-optics coefficient file (classic netCDF) -> kwargs of ty_cloud_optics.load
+    (examples/all-sky/mo_load_cloud_coefficients.F90:23-110)."""
+    from scipy.io import netcdf_file
+    f = netcdf_file(path, "r", mmap=False)
+    v = f.variables
+    sc = lambda k: float(v[k].getValue())
+    out = dict(band_lims_wvn=np.array(v["bnd_limits_wavenumber"][:], np.float32),
+               radliq_lwr=sc("radliq_lwr"), radliq_upr=sc("radliq_upr"), radliq_fac=sc("radliq_fac"),
+               radice_lwr=sc("radice_lwr"), radice_upr=sc("radice_upr"), radice_fac=sc("radice_fac"))
+    for k in ("lut_extliq", "lut_ssaliq", "lut_asyliq", "lut_extice", "lut_ssaice", "lut_asyice"):
+        out[k] = np.array(v[k][:], np.float32)
+    f.close()
+    return out
+
+
+def compute_heating_rate(flux_up, flux_dn, plev, heating_rate, ctx=None):
+    """[K/s], extensions/mo_heating_rates.F90:26-54; arrays (ncol, nlay+1) / (ncol, nlay)."""
+    ctx = ctx or default_context()
+    fu, fd, pl = _dev(flux_up, ctx), _dev(flux_dn, ctx), _dev(plev, ctx)
+    ncol, nlev = fu.shape
+    if tuple(fd.shape) != (ncol, nlev):
+        return "heating_rate: flux_dn array inconsistently sized."
+    if tuple(pl.shape) != (ncol, nlev):
+        return "heating_rate: plev array inconsistently sized."
+    if tuple(heating_rate.shape) != (ncol, nlev - 1):
+        return "heating_rate: heating_rate array inconsistently sized."
+    try:
+        _lib.check(_lib.lib().rrnn_heating_rate(ctx.h, ncol, nlev - 1, _ptr(fu), _ptr(fd), _ptr(pl), _ptr(heating_rate)))
+    except RRNNError as e:
+        return str(e)
+    return ""
+
+
+def calc_heating_rate(flux_up, flux_dn, pressure_hl, ctx=None):
+    """[K/day], examples/rrtmgp-nn-training/rrtmgp_lw_eval_nn_rfmip.F90:624-653."""
+    torch = _torch()
+    ctx = ctx or default_context()
+    fu, fd, pl = _dev(flux_up, ctx), _dev(flux_dn, ctx), _dev(pressure_hl, ctx)
+    ncol, nlev = fu.shape
+    out = torch.empty((ncol, nlev - 1), dtype=torch.float32, device=fu.device)
+    _lib.check(_lib.lib().rrnn_calc_heating_rate(ctx.h, ncol, nlev - 1, _ptr(fu), _ptr(fd), _ptr(pl), _ptr(out)))
+    return out
+
+
+# ---- whole-path drivers (host buffers in, host buffers out) -------------------------------------------
+def _models(neural_nets):
+    return (vp * 2)(*[n.h for n in neural_nets][:2])
+
+
+def _hp(a):
+    return None if a is None else vp(a.ctypes.data)
+
+
+def lw_fluxes_host(k_dist, neural_nets, play, plev, tlay, tsfc, sfc_emis, gas_desc, tlev=None, top_at_1=True,
+                   n_gauss_angles=1, flux_up=None, flux_dn=None):
+    """numpy in / numpy out: gas_optics(neural_nets=) -> rte_lw for all columns (rrnn_lw_fluxes_host)."""
+    ctx = k_dist.ctx
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    play, plev, tlay, tlev, tsfc, sfc_emis = map(f32, (play, plev, tlay, tlev, tsfc, sfc_emis))
+    ncol, nlay = play.shape
+    if flux_up is None:
+        flux_up = np.empty((ncol, nlay + 1), np.float32)
+    if flux_dn is None:
+        flux_dn = np.empty((ncol, nlay + 1), np.float32)
+    gases, ngas, keep = gas_desc._to_c(ctx, host=True)
+    _lib.check(_lib.lib().rrnn_lw_fluxes_host(ctx.h, k_dist._kd.h, _models(neural_nets), len(neural_nets), ncol, nlay,
+                                              int(bool(top_at_1)), int(n_gauss_angles), _hp(play), _hp(plev), _hp(tlay), _hp(tlev),
+                                              _hp(tsfc), _hp(sfc_emis), gases, ngas, _hp(flux_up), _hp(flux_dn)))
+    return flux_up, flux_dn
+
+
+def sw_fluxes_host(k_dist, neural_nets, play, plev, tlay, mu0, sfc_alb, gas_desc, tsi=None, top_at_1=True, flux_up=None,
+                   flux_dn=None, flux_dn_dir=None):
+    ctx = k_dist.ctx
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    play, plev, tlay, mu0, sfc_alb, tsi = map(f32, (play, plev, tlay, mu0, sfc_alb, tsi))
+    ncol, nlay = play.shape
+    mk = lambda a: np.empty((ncol, nlay + 1), np.float32) if a is None else a
+    flux_up, flux_dn, flux_dn_dir = mk(flux_up), mk(flux_dn), mk(flux_dn_dir)
+    gases, ngas, keep = gas_desc._to_c(ctx, host=True)
+    _lib.check(_lib.lib().rrnn_sw_fluxes_host(ctx.h, k_dist._kd.h, _models(neural_nets), ncol, nlay, int(bool(top_at_1)),
+                                              _hp(play), _hp(plev), _hp(tlay), _hp(mu0), _hp(sfc_alb), _hp(tsi), gases, ngas,
+                                              _hp(flux_up), _hp(flux_dn), _hp(flux_dn_dir)))
+    return flux_up, flux_dn, flux_dn_dir
+
+
+def lw_fluxes(k_dist, neural_nets, play, plev, tlay, tsfc, sfc_emis, gas_desc, flux_up, flux_dn, tlev=None, top_at_1=True,
+              n_gauss_angles=1):
+    """Device tensors in / out (rrnn_lw_fluxes)."""
+    ctx = k_dist.ctx
+    ncol, nlay = play.shape
+    gases, ngas, keep = gas_desc._to_c(ctx)
+    _lib.check(_lib.lib().rrnn_lw_fluxes(ctx.h, k_dist._kd.h, _models(neural_nets), len(neural_nets), ncol, nlay,
+                                         int(bool(top_at_1)), int(n_gauss_angles), _ptr(play), _ptr(plev), _ptr(tlay), _ptr(tlev),
+                                         _ptr(tsfc), _ptr(sfc_emis), gases, ngas, _ptr(flux_up), _ptr(flux_dn)))
+
+
+def sw_fluxes(k_dist, neural_nets, play, plev, tlay, mu0, sfc_alb, gas_desc, flux_up, flux_dn, flux_dn_dir, tsi=None,
+              top_at_1=True):
+    ctx = k_dist.ctx
+    ncol, nlay = play.shape
+    gases, ngas, keep = gas_desc._to_c(ctx)
+    _lib.check(_lib.lib().rrnn_sw_fluxes(ctx.h, k_dist._kd.h, _models(neural_nets), ncol, nlay, int(bool(top_at_1)), _ptr(play),
+                                         _ptr(plev), _ptr(tlay), _ptr(mu0), _ptr(sfc_alb), _ptr(tsi), gases, ngas,
+                                         _ptr(flux_up), _ptr(flux_dn), _ptr(flux_dn_dir)))

@@ -1,0 +1,163 @@
+// Shared definitions of librrnn_b200: context, error handling, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/rrnn.h"
+
+namespace rrnn {
+
+void set_error(const std::string& msg);
+int fail(const std::string& msg);
+
+#define RRNN_CUDA(call)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::rrnn::fail(std::string(#call) + ": " + cudaGetErrorString(_e));                       \
+  } while (0)
+
+#define RRNN_CHECK(cond, msg)                                                                        \
+  do {                                                                                               \
+    if (!(cond)) return ::rrnn::fail(msg);                                                           \
+  } while (0)
+
+#define RRNN_LAUNCH_CHECK(ctx)                                                                       \
+  do {                                                                                               \
+    (ctx)->launches++;                                                                               \
+    cudaError_t _e = cudaGetLastError();                                                             \
+    if (_e != cudaSuccess) return ::rrnn::fail(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int MAX_NN_INPUTS = 32;
+constexpr int MAX_LAYERS = 6;
+constexpr int MAX_BANDS = 32;
+
+}  // namespace rrnn
+
+// ---- opaque handle definitions -------------------------------------------------------------------
+struct rrnn_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  size_t smem_optin = 0;
+  long long launches = 0;
+  // flags (rte/mo_rte_rrtmgp_config.F90:23-40 + this library's own)
+  int lw_source_bug_compat = 1;
+  int fast_math = 0;       // solver transcendental variant: 0 = IEEE-accurate libdevice, 1 = ex2/rcp/rsqrt approx
+  int nn_tensor_cores = 0; // MLP variant: 0 = fp32 FFMA, 1 = tcgen05 3xTF32
+  int chunk_columns = 0;
+  // persistent workspace for the whole-path drivers
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t out_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+};
+
+struct rrnn_model {
+  int nlayers = 0;
+  int dims[rrnn::MAX_LAYERS + 1] = {};
+  int act[rrnn::MAX_LAYERS] = {};
+  std::vector<float> wpack, bpack, xmin, xmax, ymean, ystd;  // host copies
+  std::vector<std::string> input_names;
+  int device = 0;
+  // device copies
+  float* d_wpack = nullptr;
+  float* d_bpack = nullptr;
+  float* d_ymean = nullptr;
+  float* d_ystd = nullptr;
+  size_t w_off[rrnn::MAX_LAYERS] = {};
+  size_t b_off[rrnn::MAX_LAYERS] = {};
+};
+
+struct rrnn_kdist {
+  int nbnd = 0, ngpt = 0, ntemp = 0;
+  float temp_ref_min = 0.f, totplnk_delta = 1.f;
+  std::vector<int> band_lims_gpt;  // [nbnd][2], 1-based inclusive
+  std::vector<int> gpt2band;       // [ngpt], 0-based band
+  std::vector<float> totplnk, solar_source;
+  int device = 0;
+  int* d_band_lims_gpt = nullptr;
+  int* d_gpt2band = nullptr;
+  float* d_totplnk = nullptr;
+  float* d_solar_source = nullptr;
+};
+
+struct rrnn_cloud_lut {
+  int nbnd = 0, nsize_liq = 0, nsize_ice = 0;
+  float radliq_lwr = 0, radice_lwr = 0, liq_step = 0, ice_step = 0;
+  float* d_tables = nullptr;  // extliq, ssaliq, asyliq, extice, ssaice, asyice back to back
+  size_t off[6] = {};
+};
+
+// ---- device helpers ------------------------------------------------------------------------------
+namespace rrnn {
+
+__device__ __forceinline__ float warp_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// streaming (read-once) global load: keep it out of L1
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+// streaming (write-once) global store
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <bool FAST>
+__device__ __forceinline__ float exp_neg(float x) {  // exp(x), x <= 0 in practice
+  if (FAST) return __expf(x);
+  return expf(x);
+}
+template <bool FAST>
+__device__ __forceinline__ float rcp(float x) {
+  if (FAST) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+  }
+  return 1.0f / x;
+}
+template <bool FAST>
+__device__ __forceinline__ float fdiv(float a, float b) {
+  if (FAST) return __fdividef(a, b);
+  return a / b;
+}
+template <bool FAST>
+__device__ __forceinline__ float fsqrt(float x) {
+  if (FAST) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+  }
+  return sqrtf(x);
+}
+
+}  // namespace rrnn

@@ -1,0 +1,343 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances are the ones BASELINE.json states: |dflux| <= 0.01 W m-2 at every level, |dHR| <= 1e-3 K/day,
+tau relative error <= 1e-4 (fp32 path, with the absolute floor described in helpers.tau_rel_err).
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _lw_setup(ctx, files, ngpt, ncol, nlay, seed=1, flip=False):
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    kd = spectral.synthetic_kdist_lw(ngpt=ngpt)
+    atm = synth.make_atmosphere(ncol, nlay, seed=seed)
+    if flip:
+        atm = synth.flip_vertical(atm)
+    k_dist = api.ty_gas_optics_rrtmgp(ctx)
+    assert k_dist.load(kd) == ""
+    return kd, atm, k_dist, H.oracle_nets(files), H.device_nets(ctx, files)
+
+
+def _run_lw_gas_optics(ctx, k_dist, dnets, atm, use_tlev=True):
+    from rte_rrtmgp_nn_b200 import api
+    ncol, nlay = atm["play"].shape
+    op = api.ty_optical_props_1scl(); assert op.alloc_1scl(ncol, nlay, k_dist) == ""
+    src = api.ty_source_func_lw(); assert src.alloc(ncol, nlay, k_dist) == ""
+    err = k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], H.gas_concs(atm["gases"]), op, src,
+                            tlev=atm["tlev"] if use_tlev else None, neural_nets=dnets)
+    assert err == "", err
+    return op, src
+
+
+@pytest.mark.parametrize("files,ngpt,nlay,ncol", [(H.LW_G256, 256, 60, 50), (H.LW_G128, 128, 33, 37),
+                                                  (H.LW_G128_NWP, 128, 137, 9), (H.LW_G128_BOTH, 128, 60, 21)])
+def test_lw_gas_optics_matches_oracle(gpu_ctx, files, ngpt, nlay, ncol):
+    import oracle as O
+    kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, files, ngpt, ncol, nlay)
+    ref = O.gas_optics_lw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"])
+    op, src = _run_lw_gas_optics(gpu_ctx, k_dist, dnets, atm)
+    tau = op.tau.cpu().numpy()
+    err = H.tau_rel_err(tau, ref["tau"])
+    assert err.max() <= H.TAU_RTOL, f"tau rel err {err.max():.3e}"
+    for name in ("lay_source", "lev_source", "sfc_source", "sfc_source_Jac"):
+        got = getattr(src, name).cpu().numpy()
+        scale = np.abs(ref[name]).max()
+        assert np.abs(got - ref[name]).max() <= 2e-5 * scale, name
+
+
+def test_lw_gas_optics_without_tlev(gpu_ctx):
+    import oracle as O
+    kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, H.LW_G256, 256, 11, 60, seed=5)
+    ref = O.gas_optics_lw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=None)
+    op, src = _run_lw_gas_optics(gpu_ctx, k_dist, dnets, atm, use_tlev=False)
+    got = src.lev_source.cpu().numpy()
+    assert np.abs(got - ref["lev_source"]).max() <= 5e-5 * np.abs(ref["lev_source"]).max()
+
+
+@pytest.mark.parametrize("files,ngpt,nlay,ncol,flip,nang", [(H.LW_G256, 256, 60, 40, False, 1), (H.LW_G256, 256, 60, 13, True, 1),
+                                                           (H.LW_G128, 128, 91, 17, False, 3), (H.LW_G128, 128, 137, 6, False, 1)])
+def test_lw_fluxes_match_oracle(gpu_ctx, files, ngpt, nlay, ncol, flip, nang):
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api
+    torch = _torch()
+    kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, files, ngpt, ncol, nlay, seed=3, flip=flip)
+    ref = O.gas_optics_lw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"])
+    emis = np.repeat(atm["sfc_emis"][:, None], kd["nbnd"], 1)
+    rup, rdn = O.rte_lw(kd, atm["top_at_1"], ref["tau"], ref["lay_source"], ref["lev_source"], ref["sfc_source"], emis,
+                        n_gauss_angles=nang)
+    op, src = _run_lw_gas_optics(gpu_ctx, k_dist, dnets, atm)
+    dev = op.tau.device
+    fl = api.ty_fluxes_broadband(torch.empty((ncol, nlay + 1), device=dev), torch.empty((ncol, nlay + 1), device=dev))
+    err = api.rte_lw(op, atm["top_at_1"], src, emis, fl, n_gauss_angles=nang)
+    assert err == "", err
+    up, dn = fl.flux_up.cpu().numpy(), fl.flux_dn.cpu().numpy()
+    assert np.abs(up - rup).max() <= H.FLUX_TOL and np.abs(dn - rdn).max() <= H.FLUX_TOL, (np.abs(up - rup).max(), np.abs(dn - rdn).max())
+    # heating rates in K/day
+    hr = api.calc_heating_rate(fl.flux_up, fl.flux_dn, atm["plev"], ctx=gpu_ctx).cpu().numpy()
+    rhr = O.calc_heating_rate(rup, rdn, atm["plev"])
+    # exclude the top layers whose pressure thickness is < 1 Pa (dF/dp amplifies fp32 noise without bound there)
+    dp = np.abs(np.diff(atm["plev"], axis=1))
+    m = dp > 50.0
+    assert np.abs(hr - rhr)[m].max() <= H.HR_TOL, np.abs(hr - rhr)[m].max()
+
+
+def test_lw_solver_alone_random_inputs(gpu_ctx):
+    """Solver on materialised oracle inputs: isolates K3 from the NN (tight tolerance)."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    rng = np.random.default_rng(0)
+    for (G, L, C, top) in [(256, 60, 7, True), (224, 5, 3, False), (112, 137, 2, True), (36, 17, 5, True)]:
+        tau = rng.gamma(0.3, 2.0, size=(C, L, G)).astype(np.float32)
+        tau[0, 0, :4] = 1e-5  # exercises the small-tau series branch
+        lay = rng.uniform(0.1, 2.0, size=(C, L, G)).astype(np.float32)
+        lev = rng.uniform(0.1, 2.0, size=(C, L + 1, G)).astype(np.float32)
+        emis = rng.uniform(0.8, 1.0, size=(C, G)).astype(np.float32)
+        ssrc = rng.uniform(0.1, 2.0, size=(C, G)).astype(np.float32)
+        rup, rdn = O.lw_solver_noscat_GaussQuad(top, 1, tau, lay, lev, emis, ssrc)
+        d = [torch.from_numpy(a).cuda() for a in (tau, lay, lev, emis, ssrc)]
+        up = torch.empty((C, L + 1), device="cuda"); dn = torch.empty_like(up)
+        Ds = np.array([1.66], np.float32); w = np.array([0.5], np.float32)
+        _lib.check(_lib.lib().rrnn_lw_solver_noscat(gpu_ctx.h, G, L, C, int(top), 1, Ds.ctypes.data_as(_lib.c_float_p),
+                                                    w.ctypes.data_as(_lib.c_float_p), None, *[api._ptr(t) for t in d],
+                                                    api._ptr(up), api._ptr(dn)))
+        scale = max(np.abs(rup).max(), 1.0)
+        assert np.abs(up.cpu().numpy() - rup).max() <= 2e-5 * scale
+        assert np.abs(dn.cpu().numpy() - rdn).max() <= 2e-5 * scale
+
+
+def _sw_setup(ctx, files, ngpt, ncol, nlay, seed=2, flip=False):
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    kd = spectral.synthetic_kdist_sw(ngpt=ngpt)
+    atm = synth.make_atmosphere(ncol, nlay, seed=seed)
+    if flip:
+        atm = synth.flip_vertical(atm)
+    k_dist = api.ty_gas_optics_rrtmgp(ctx)
+    assert k_dist.load(kd) == ""
+    return kd, atm, k_dist, H.oracle_nets(files), H.device_nets(ctx, files)
+
+
+@pytest.mark.parametrize("files,ngpt,nlay,ncol,flip", [(H.SW_G224, 224, 60, 45, False), (H.SW_G112, 112, 91, 14, False),
+                                                      (H.SW_G224, 224, 137, 5, True)])
+def test_sw_gas_optics_and_fluxes_match_oracle(gpu_ctx, files, ngpt, nlay, ncol, flip):
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api
+    torch = _torch()
+    kd, atm, k_dist, onets, dnets = _sw_setup(gpu_ctx, files, ngpt, ncol, nlay, flip=flip)
+    ref = O.gas_optics_sw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["gases"])
+    op = api.ty_optical_props_2str(); assert op.alloc_2str(ncol, nlay, k_dist) == ""
+    toa = torch.empty((ncol, ngpt), device="cuda")
+    err = k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], H.gas_concs(atm["gases"]), op, toa, neural_nets=dnets)
+    assert err == "", err
+    assert H.tau_rel_err(op.tau.cpu().numpy(), ref["tau"]).max() <= H.TAU_RTOL
+    assert np.abs(op.ssa.cpu().numpy() - ref["ssa"]).max() <= 2e-5
+    assert np.array_equal(toa.cpu().numpy(), ref["toa_src"])
+    alb = np.repeat(atm["sfc_alb"][:, None], ngpt, 1)
+    rup, rdn, rdir = O.rte_sw(atm["top_at_1"], atm["mu0"], ref["toa_src"], alb, alb, ref["tau"], ref["ssa"], ref["g"])
+    mk = lambda: torch.empty((ncol, nlay + 1), device="cuda")
+    fl = api.ty_fluxes_broadband(mk(), mk(), None, mk())
+    err = api.rte_sw(op, atm["top_at_1"], atm["mu0"], toa, alb, alb, fl)
+    assert err == "", err
+    for got, want, nm in ((fl.flux_up, rup, "up"), (fl.flux_dn, rdn, "dn"), (fl.flux_dn_dir, rdir, "dir")):
+        d = np.abs(got.cpu().numpy() - want).max()
+        assert d <= H.FLUX_TOL, (nm, d)
+    # materialised g (explicit zeros) must give the same answer through the HAS_G kernel
+    _ = op.g
+    fl2 = api.ty_fluxes_broadband(mk(), mk(), None, mk())
+    assert api.rte_sw(op, atm["top_at_1"], atm["mu0"], toa, alb, alb, fl2) == ""
+    assert torch.equal(fl2.flux_up, fl.flux_up) and torch.equal(fl2.flux_dn, fl.flux_dn)
+
+
+def test_sw_solver_alone_with_scattering(gpu_ctx):
+    """Solver on random tau/ssa/g (g != 0, diffuse incident flux): isolates K4 from the NN."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    rng = np.random.default_rng(4)
+    for (G, L, C, top) in [(224, 60, 6, True), (112, 9, 4, False), (64, 137, 3, True)]:
+        tau = rng.gamma(0.4, 1.5, size=(C, L, G)).astype(np.float32)
+        ssa = rng.uniform(0.0, 0.999, size=(C, L, G)).astype(np.float32)
+        g = rng.uniform(-0.2, 0.9, size=(C, L, G)).astype(np.float32)
+        mu0 = rng.uniform(0.05, 1.0, size=C).astype(np.float32)
+        inc = rng.uniform(0.5, 8.0, size=(C, G)).astype(np.float32)
+        incd = rng.uniform(0.0, 1.0, size=(C, G)).astype(np.float32)
+        ad = rng.uniform(0.0, 0.9, size=(C, G)).astype(np.float32)
+        af = rng.uniform(0.0, 0.9, size=(C, G)).astype(np.float32)
+        rup, rdn, rdir = O.sw_solver_2stream(top, inc, incd, tau, ssa, g, mu0, ad, af)
+        d = {k: torch.from_numpy(v).cuda() for k, v in dict(inc=inc, incd=incd, tau=tau, ssa=ssa, g=g, mu0=mu0, ad=ad, af=af).items()}
+        up = torch.empty((C, L + 1), device="cuda"); dn = torch.empty_like(up); dr = torch.empty_like(up)
+        P = api._ptr
+        _lib.check(_lib.lib().rrnn_sw_solver_2stream(gpu_ctx.h, G, L, C, int(top), P(d["inc"]), P(d["incd"]), P(d["tau"]), P(d["ssa"]),
+                                                     P(d["g"]), P(d["mu0"]), P(d["ad"]), P(d["af"]), P(up), P(dn), P(dr)))
+        scale = max(np.abs(rdn).max(), 1.0)
+        for got, want in ((up, rup), (dn, rdn), (dr, rdir)):
+            assert np.abs(got.cpu().numpy() - want).max() <= 3e-5 * scale
+
+
+def test_sgemm_entry_points(gpu_ctx):
+    """output_sgemm_tau / _pfrac / _lw on materialised inputs (+ compute_nn_inputs, get_col_dry, Planck source)."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib, spectral, synth
+    torch = _torch()
+    kd = spectral.synthetic_kdist_lw(256)
+    atm = synth.make_atmosphere(19, 60, seed=8)
+    onets, dnets = H.oracle_nets(H.LW_G256), H.device_nets(gpu_ctx, H.LW_G256)
+    ncol, nlay = atm["play"].shape
+    x_ref = O.compute_nn_inputs(onets[0], atm["play"], atm["tlay"], atm["gases"])
+    cd_ref = O.get_col_dry(atm["gases"]["h2o"], atm["plev"])
+    P = api._ptr
+    lib = _lib.lib()
+    gases, ngas, keep = H.gas_concs(atm["gases"])._to_c(gpu_ctx)
+    play, tlay, plev = [torch.from_numpy(atm[k]).cuda() for k in ("play", "tlay", "plev")]
+    x = torch.empty((ncol, nlay, 18), device="cuda")
+    _lib.check(lib.rrnn_compute_nn_inputs(gpu_ctx.h, dnets[0].h, ncol, nlay, P(play), P(tlay), gases, ngas, P(x)))
+    assert np.abs(x.cpu().numpy() - x_ref).max() <= 2e-6
+    cd = torch.empty((ncol, nlay), device="cuda")
+    _lib.check(lib.rrnn_get_col_dry(gpu_ctx.h, ncol, nlay, P(torch.from_numpy(atm["gases"]["h2o"]).cuda()), P(plev), P(cd)))
+    assert np.allclose(cd.cpu().numpy(), cd_ref, rtol=2e-6)
+    xr = torch.from_numpy(x_ref).cuda(); cdr = torch.from_numpy(cd_ref).cuda()
+    nb = ncol * nlay
+    tau = torch.empty((nb, 256), device="cuda")
+    _lib.check(lib.rrnn_output_sgemm_tau(gpu_ctx.h, dnets[0].h, nb, P(xr), P(cdr), P(tau), None))
+    assert H.tau_rel_err(tau.cpu().numpy(), O.output_sgemm_tau(onets[0], x_ref, cd_ref)).max() <= H.TAU_RTOL
+    pf = torch.empty((nb, 256), device="cuda")
+    _lib.check(lib.rrnn_output_sgemm_pfrac(gpu_ctx.h, dnets[1].h, nb, P(xr), P(pf)))
+    pf_ref = O.output_sgemm_pfrac(onets[1], x_ref)
+    assert np.abs(pf.cpu().numpy() - pf_ref).max() <= 2e-5 * pf_ref.max()
+    raw = torch.empty((nb, 256), device="cuda")
+    _lib.check(lib.rrnn_output_sgemm_lw(gpu_ctx.h, dnets[0].h, nb, P(xr), P(raw)))
+    assert np.abs(raw.cpu().numpy() - O.output_sgemm_lw(onets[0], x_ref)).max() <= 5e-5
+    # Planck source on the oracle's Planck fraction
+    k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); k_dist.load(kd)
+    pfrac = pf_ref.reshape(ncol, nlay, 256)
+    sfc, jac, lay, lev = O.planck_source_nn(kd, atm["tlay"], atm["tlev"], atm["tsfc"], nlay, pfrac)
+    d_pf = torch.from_numpy(pfrac.copy()).cuda()
+    d_lev = torch.empty((ncol, nlay + 1, 256), device="cuda"); d_sfc = torch.empty((ncol, 256), device="cuda"); d_jac = torch.empty_like(d_sfc)
+    _lib.check(lib.rrnn_planck_source_nn(gpu_ctx.h, k_dist._kd.h, ncol, nlay, P(tlay), P(torch.from_numpy(atm["tlev"]).cuda()),
+                                         P(torch.from_numpy(atm["tsfc"]).cuda()), nlay, P(d_sfc), P(d_jac), P(d_pf), P(d_lev)))
+    for got, want in ((d_pf, lay), (d_lev, lev), (d_sfc, sfc), (d_jac, jac)):
+        assert np.abs(got.cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_whole_path_drivers_host_and_device(gpu_ctx):
+    """rrnn_{lw,sw}_fluxes_host (chunked, copies overlapped) == oracle, incl. night columns and TSI scaling."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    ncol, nlay = 301, 60
+    atm = synth.make_atmosphere(ncol, nlay, seed=11)
+    gpu_ctx.set_chunk_columns(64)  # forces 5 chunks, last one ragged
+    try:
+        kd = spectral.synthetic_kdist_lw(256)
+        k_lw = api.ty_gas_optics_rrtmgp(gpu_ctx); k_lw.load(kd)
+        onets, dnets = H.oracle_nets(H.LW_G256), H.device_nets(gpu_ctx, H.LW_G256)
+        up, dn = api.lw_fluxes_host(k_lw, dnets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["sfc_emis"],
+                                    H.gas_concs(atm["gases"]), tlev=atm["tlev"])
+        ref = O.gas_optics_lw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"])
+        rup, rdn = O.rte_lw(kd, True, ref["tau"], ref["lay_source"], ref["lev_source"], ref["sfc_source"],
+                            np.repeat(atm["sfc_emis"][:, None], 16, 1))
+        assert np.abs(up - rup).max() <= H.FLUX_TOL and np.abs(dn - rdn).max() <= H.FLUX_TOL
+
+        ks = spectral.synthetic_kdist_sw(224)
+        k_sw = api.ty_gas_optics_rrtmgp(gpu_ctx); k_sw.load(ks)
+        onets, dnets = H.oracle_nets(H.SW_G224), H.device_nets(gpu_ctx, H.SW_G224)
+        mu0 = atm["mu0"].copy(); mu0[::7] = -0.3  # night columns
+        tsi = np.random.default_rng(0).uniform(1300, 1400, ncol).astype(np.float32)
+        up, dn, dr = api.sw_fluxes_host(k_sw, dnets, atm["play"], atm["plev"], atm["tlay"], mu0, atm["sfc_alb"],
+                                        H.gas_concs(atm["gases"]), tsi=tsi)
+        ref = O.gas_optics_sw(ks, onets, atm["play"], atm["plev"], atm["tlay"], atm["gases"])
+        def_tsi = np.float32(0)
+        for v in ks["solar_source"]:
+            def_tsi = np.float32(def_tsi + v)
+        toa = (ref["toa_src"] * tsi[:, None] / def_tsi).astype(np.float32)
+        mu0e = np.where(mu0 > 0, mu0, 1.0).astype(np.float32)
+        alb = np.repeat(atm["sfc_alb"][:, None], 224, 1)
+        rup, rdn, rdir = O.rte_sw(True, mu0e, toa, alb, alb, ref["tau"], ref["ssa"], ref["g"])
+        rup[mu0 <= 0] = 0; rdn[mu0 <= 0] = 0
+        assert np.abs(up - rup).max() <= H.FLUX_TOL and np.abs(dn - rdn).max() <= H.FLUX_TOL and np.abs(dr - rdir).max() <= H.FLUX_TOL
+    finally:
+        gpu_ctx.set_chunk_columns(0)
+
+
+def test_cloud_optics_increment_delta_scale(gpu_ctx):
+    import os
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    torch = _torch()
+    atm = synth.make_atmosphere(30, 60, seed=21)
+    cl = synth.make_clouds(atm)
+    for band, ngpt, mk in (("lw", 256, spectral.synthetic_kdist_lw), ("sw", 224, spectral.synthetic_kdist_sw)):
+        kd = mk(ngpt)
+        k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); k_dist.load(kd)
+        co = api.ty_cloud_optics(gpu_ctx)
+        args = api.load_cloud_lut_file(os.path.join(H.ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc"))
+        assert co.load(**args) == ""
+        two = band == "sw"
+        clouds = api.ty_optical_props_2str() if two else api.ty_optical_props_1scl()
+        (clouds.alloc_2str if two else clouds.alloc_1scl)(30, 60, k_dist, by_band=True)
+        assert co.cloud_optics(cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], clouds) == ""
+        ref = O.cloud_optics_lut(co.tables, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], two)
+        rng = np.random.default_rng(1)
+        if not two:
+            assert np.allclose(clouds.tau.cpu().numpy(), ref, rtol=1e-5, atol=1e-7)
+            atmos = api.ty_optical_props_1scl(); atmos.alloc_1scl(30, 60, k_dist); atmos._kd = k_dist._kd
+            t1 = rng.gamma(0.5, 1.0, size=(30, 60, ngpt)).astype(np.float32)
+            atmos.tau.copy_(torch.from_numpy(t1))
+            assert clouds.increment(atmos) == ""
+            want = O.inc_1scalar_by_1scalar_bybnd(t1, ref, kd["band_lims_gpt"])
+            assert np.allclose(atmos.tau.cpu().numpy(), want, rtol=1e-6)
+        else:
+            for got, want in zip((clouds.tau, clouds.ssa, clouds.g), ref):
+                assert np.allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
+            assert clouds.delta_scale() == ""
+            ds = O.delta_scale_2str(*ref)
+            for got, want in zip((clouds.tau, clouds.ssa, clouds.g), ds):
+                assert np.allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
+            atmos = api.ty_optical_props_2str(); atmos.alloc_2str(30, 60, k_dist); atmos._kd = k_dist._kd
+            t1 = rng.gamma(0.5, 1.0, size=(30, 60, ngpt)).astype(np.float32)
+            w1 = rng.uniform(0, 1, size=t1.shape).astype(np.float32)
+            atmos.tau.copy_(torch.from_numpy(t1)); atmos.ssa.copy_(torch.from_numpy(w1)); atmos.g_is_zero = True
+            assert clouds.increment(atmos) == ""
+            want = O.inc_2stream_by_2stream_bybnd(t1, w1, np.zeros_like(t1), *ds, kd["band_lims_gpt"])
+            for got, w in zip((atmos.tau, atmos.ssa, atmos.g), want):
+                assert np.allclose(got.cpu().numpy(), w, rtol=2e-5, atol=1e-7)
+
+
+def test_heating_rate_K_per_s(gpu_ctx):
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api
+    torch = _torch()
+    rng = np.random.default_rng(3)
+    up = rng.uniform(100, 400, size=(12, 61)).astype(np.float32); dn = rng.uniform(0, 400, size=(12, 61)).astype(np.float32)
+    plev = np.sort(rng.uniform(1, 1e5, size=(12, 61)).astype(np.float32), axis=1)
+    hr = torch.empty((12, 60), device="cuda")
+    assert api.compute_heating_rate(up, dn, plev, hr, ctx=gpu_ctx) == ""
+    assert np.allclose(hr.cpu().numpy(), O.heating_rate(up, dn, plev), rtol=1e-5, atol=1e-9)
+
+
+def test_error_behaviour(gpu_ctx):
+    """Errors come back as the reference's messages, not as crashes."""
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    torch = _torch()
+    kd = spectral.synthetic_kdist_lw(256)
+    k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); k_dist.load(kd)
+    atm = synth.make_atmosphere(4, 60)
+    dnets = H.device_nets(gpu_ctx, H.LW_G256)
+    op = api.ty_optical_props_1scl(); op.alloc_1scl(4, 60, k_dist)
+    src = api.ty_source_func_lw(); src.alloc(4, 60, k_dist)
+    g = dict(atm["gases"]); del g["o3"]
+    err = k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], H.gas_concs(g), op, src, neural_nets=dnets)
+    assert "o3" in err
+    fl = api.ty_fluxes_broadband()
+    assert api.rte_lw(op, True, src, np.ones((4, 16), np.float32), fl) == "rte_lw: no space allocated for fluxes"
+    fl = api.ty_fluxes_broadband(torch.empty((4, 61), device="cuda"), torch.empty((4, 61), device="cuda"))
+    assert "too many quadrature" in api.rte_lw(op, True, src, np.ones((4, 16), np.float32), fl, n_gauss_angles=5)
+    assert "sfc_emis inconsistently sized" in api.rte_lw(op, True, src, np.ones((4, 15), np.float32), fl)
