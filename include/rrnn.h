@@ -63,6 +63,11 @@ RRNN_API int rrnn_ctx_synchronize(rrnn_ctx_t* ctx);
  * lw_source_noscat ignoring top_at_1 (rte/kernels/mo_rte_solver_kernels.F90:770-773); 0 orients the
  * level sources physically for top_at_1 = false. */
 RRNN_API int rrnn_ctx_set_flag(rrnn_ctx_t* ctx, const char* name, int value);
+/* Per-kernel device timing with CUDA events on the context's stream.  rrnn_ctx_profile(ctx, 1) enables and
+ * resets; rrnn_ctx_profile_read synchronises and returns the summed duration and launch count of kernel
+ * kind 0 = NN gas optics LW, 1 = LW solver, 2 = NN gas optics SW, 3 = SW solver. */
+RRNN_API int rrnn_ctx_profile(rrnn_ctx_t* ctx, int enable);
+RRNN_API int rrnn_ctx_profile_read(rrnn_ctx_t* ctx, int kind, double* total_ms, int* nlaunches);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 RRNN_API long long rrnn_ctx_launch_count(rrnn_ctx_t* ctx);
 

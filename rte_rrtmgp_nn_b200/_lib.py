@@ -47,6 +47,8 @@ _SIGS = {
     "rrnn_ctx_synchronize": (C.c_int, [vp]),
     "rrnn_ctx_set_flag": (C.c_int, [vp, C.c_char_p, C.c_int]),
     "rrnn_ctx_launch_count": (C.c_longlong, [vp]),
+    "rrnn_ctx_profile": (C.c_int, [vp, C.c_int]),
+    "rrnn_ctx_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), c_int_p]),
     "rrnn_ctx_set_chunk_columns": (C.c_int, [vp, C.c_int]),
     "rrnn_model_load_netcdf": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "rrnn_model_load_ascii": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(vp)]),

@@ -46,6 +46,20 @@ class Context:
     def set_chunk_columns(self, n):
         _lib.check(_lib.lib().rrnn_ctx_set_chunk_columns(self.h, int(n)))
 
+    KERNEL_KINDS = ("gas_optics_lw", "lw_solver", "gas_optics_sw", "sw_solver")
+
+    def profile(self, enable=True):
+        _lib.check(_lib.lib().rrnn_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """{kernel: (total_ms, launches)} since profile(True)."""
+        out = {}
+        for k, name in enumerate(self.KERNEL_KINDS):
+            ms = C.c_double(0); n = C.c_int(0)
+            _lib.check(_lib.lib().rrnn_ctx_profile_read(self.h, k, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     @property
     def stream(self):
         return _lib.lib().rrnn_ctx_stream(self.h)
@@ -56,6 +70,8 @@ class Context:
 
     def torch_stream(self):
         torch = _torch()
+        if not self.stream:  # legacy default stream == torch's default stream
+            return torch.cuda.default_stream(torch.device("cuda", self.device))
         return torch.cuda.ExternalStream(self.stream, device=torch.device("cuda", self.device))
 
     def close(self):

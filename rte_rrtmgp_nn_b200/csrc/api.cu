@@ -285,6 +285,7 @@ extern "C" int rrnn_ctx_destroy(rrnn_ctx_t* c) {
   if (c->ws) cudaFree(c->ws);
   if (c->pinned) cudaFreeHost(c->pinned);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& v : c->prof_ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->out_stream) cudaStreamDestroy(c->out_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -310,6 +311,26 @@ extern "C" int rrnn_ctx_set_chunk_columns(rrnn_ctx_t* c, int n) {
   c->chunk_columns = n;
   return 0;
 }
+extern "C" int rrnn_ctx_profile(rrnn_ctx_t* c, int enable) {
+  RRNN_CHECK(c, "rrnn_ctx_profile: null context");
+  c->profile = enable ? 1 : 0;
+  for (auto& u : c->prof_used) u = 0;
+  return 0;
+}
+extern "C" int rrnn_ctx_profile_read(rrnn_ctx_t* c, int kind, double* total_ms, int* nlaunches) {
+  RRNN_CHECK(c && kind >= 0 && kind < 4 && total_ms && nlaunches, "rrnn_ctx_profile_read: bad argument");
+  RRNN_CUDA(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i < c->prof_used[kind]; ++i) {
+    float ms = 0.f;
+    RRNN_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[kind][i].first, c->prof_ev[kind][i].second));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *nlaunches = (int)c->prof_used[kind];
+  return 0;
+}
+
 extern "C" int rrnn_ctx_set_flag(rrnn_ctx_t* c, const char* name, int value) {
   RRNN_CHECK(c && name, "rrnn_ctx_set_flag: null argument");
   const std::string s(name);

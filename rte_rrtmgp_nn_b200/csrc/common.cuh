@@ -60,7 +60,31 @@ struct rrnn_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t out_stream = nullptr;
   cudaEvent_t ev[8] = {};
+  // optional per-kernel timing (CUDA events around the four big kernels on the context's stream)
+  int profile = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[4];
+  size_t prof_used[4] = {0, 0, 0, 0};
 };
+
+namespace rrnn {
+enum { K_GAS_LW = 0, K_LW_SOLVER = 1, K_GAS_SW = 2, K_SW_SOLVER = 3 };
+// record a start event (returns slot index or -1) / the matching stop event
+inline int prof_begin(rrnn_ctx* c, int kind) {
+  if (!c->profile) return -1;
+  if (c->prof_used[kind] == c->prof_ev[kind].size()) {
+    if (c->prof_ev[kind].size() >= 8192) return -1;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+    c->prof_ev[kind].push_back({a, b});
+  }
+  const int slot = (int)c->prof_used[kind]++;
+  cudaEventRecord(c->prof_ev[kind][slot].first, c->stream);
+  return slot;
+}
+inline void prof_end(rrnn_ctx* c, int kind, int slot) {
+  if (slot >= 0) cudaEventRecord(c->prof_ev[kind][slot].second, c->stream);
+}
+}  // namespace rrnn
 
 struct rrnn_model {
   int nlayers = 0;
@@ -136,6 +160,26 @@ __device__ __forceinline__ float exp_neg(float x) {  // exp(x), x <= 0 in practi
   if (FAST) return __expf(x);
   return expf(x);
 }
+// 1 - exp(-x) and exp(-x) for x >= 0 without the cancellation of the literal "1 - exp(-x)" at small x.
+// The reference forms 1 - trans in working precision (rte/kernels/mo_rte_solver_kernels.F90:757-773); with
+// CUDA's 1-2 ulp expf that literal form is 2-4x noisier than the reference built on a correctly rounded libm,
+// which shows up in heating rates of thin layers.  Branch-free: degree-7 Taylor polynomial below 0.35,
+// the literal form above (where it is harmless).
+__device__ __forceinline__ void exp_and_complement(float x, float& t, float& omt) {
+  const float y = -x;
+  float p = fmaf(y, 1.0f / 5040.0f, 1.0f / 720.0f);
+  p = fmaf(p, y, 1.0f / 120.0f);
+  p = fmaf(p, y, 1.0f / 24.0f);
+  p = fmaf(p, y, 1.0f / 6.0f);
+  p = fmaf(p, y, 0.5f);
+  p = fmaf(p, y, 1.0f);
+  const float em1 = p * y;  // expm1(-x) for small x
+  const float e = expf(y);
+  const bool small = x < 0.35f;
+  omt = small ? -em1 : 1.0f - e;
+  t = small ? 1.0f + em1 : e;
+}
+
 template <bool FAST>
 __device__ __forceinline__ float rcp(float x) {
   if (FAST) {

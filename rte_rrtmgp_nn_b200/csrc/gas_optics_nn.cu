@@ -557,7 +557,7 @@ static void fill_net(NetDev& d, const rrnn_model_t* m) {
 }
 
 template <int EPIT>
-static int launch_go(rrnn_ctx_t* ctx, const GoParams& p, int nout_max) {
+static int launch_go(rrnn_ctx_t* ctx, const GoParams& p, int nout_max, int prof_kind = -1) {
   const int NG = (nout_max > 128) ? 2 : 1;
   const bool planck = (EPIT == EPI_LW2 || EPIT == EPI_LWBOTH);
   const size_t smem = go_smem_floats(p, NG, planck) * sizeof(float);
@@ -565,6 +565,7 @@ static int launch_go(rrnn_ctx_t* ctx, const GoParams& p, int nout_max) {
   const long long ntiles = (p.nsamples + S_TILE - 1) / S_TILE;
   const unsigned grid = (unsigned)std::min<long long>(ntiles, ctx->num_sms);
   if (grid == 0) return 0;
+  const int ps = prof_kind >= 0 ? prof_begin(ctx, prof_kind) : -1;
   if (NG == 2) {
     RRNN_CUDA(cudaFuncSetAttribute(gas_optics_kernel<EPIT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gas_optics_kernel<EPIT, 2><<<grid, GO_THREADS, smem, ctx->stream>>>(p);
@@ -572,6 +573,7 @@ static int launch_go(rrnn_ctx_t* ctx, const GoParams& p, int nout_max) {
     RRNN_CUDA(cudaFuncSetAttribute(gas_optics_kernel<EPIT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gas_optics_kernel<EPIT, 1><<<grid, GO_THREADS, smem, ctx->stream>>>(p);
   }
+  if (prof_kind >= 0) prof_end(ctx, prof_kind, ps);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -651,12 +653,12 @@ extern "C" int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
     RRNN_CHECK(models[0]->d_ymean && models[0]->d_ystd, "output_sgemm_tau: NN output scaling coefficients missing");
     RRNN_CHECK(models[1]->dims[0] == models[0]->dims[0], "gas_optics(): the two networks take different inputs");
     RRNN_CHECK(kd->ngpt % 4 == 0 && kd->ngpt <= 256, "gas_optics(): ngpt must be a multiple of 4 and <= 256");
-    rc = launch_go<EPI_LW2>(ctx, p, kd->ngpt);
+    rc = launch_go<EPI_LW2>(ctx, p, kd->ngpt, K_GAS_LW);
   } else {
     RRNN_CHECK(models[0]->dims[models[0]->nlayers] == 2 * kd->ngpt, "gas_optics(): 'both' network must have 2*ngpt outputs");
     RRNN_CHECK(kd->ngpt == 128, "gas_optics(): single-network longwave models are supported for ngpt = 128");
     RRNN_CHECK(models[0]->d_ymean && models[0]->d_ystd, "output_sgemm_tau: NN output scaling coefficients missing");
-    rc = launch_go<EPI_LWBOTH>(ctx, p, 256);
+    rc = launch_go<EPI_LWBOTH>(ctx, p, 256, K_GAS_LW);
   }
   if (tlev_tmp) cudaFreeAsync(tlev_tmp, ctx->stream);
   return rc;
@@ -686,7 +688,7 @@ extern "C" int rrnn_gas_optics_sw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
   }
   RRNN_CHECK(kd->ngpt % 4 == 0 && kd->ngpt <= 256, "gas_optics(): ngpt must be a multiple of 4 and <= 256");
   p.out0 = tau_d; p.out1 = ssa_d; p.out2 = g_d;
-  if (int rc = launch_go<EPI_SW>(ctx, p, kd->ngpt)) return rc;
+  if (int rc = launch_go<EPI_SW>(ctx, p, kd->ngpt, K_GAS_SW)) return rc;
   if (toa_src_d) {
     RRNN_CHECK(kd->d_solar_source, "gas_optics(): k-distribution has no solar source (not a shortwave k-distribution)");
     const size_t n = (size_t)kd->ngpt * ncol;

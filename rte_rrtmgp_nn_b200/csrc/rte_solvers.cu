@@ -20,8 +20,41 @@
 // in the other direction: identical in exact arithmetic, and within fp32 rounding (<< 0.01 W m-2) of the
 // reference order -- checked against the oracle in tests/test_solvers_gpu.py.
 #include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace rrnn {
+
+// Combine the per-level partial sums of the g-point chunks of one column.
+//  CLUSTER = true : the chunks of a column are the CTAs of one thread-block cluster; rank 0 reads the other
+//                   ranks' partial sums through distributed shared memory and adds them in rank order, so the
+//                   result is deterministic and the rounding is the same at every level (which is what keeps
+//                   heating rates, i.e. differences of adjacent levels, clean).  No memset, no atomics.
+//  CLUSTER = false: fallback for more than 8 chunks (ngpt > 256): fp32 atomics on zero-initialised arrays.
+template <bool CLUSTER, int NARR>
+__device__ __forceinline__ void combine_chunks(float* part /* [NARR][L+1] in this CTA's smem */, int L, int lane,
+                                               float* const (&gout)[NARR]) {
+  if (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (cluster.block_rank() == 0) {
+      const unsigned nr = cluster.num_blocks();
+      for (int i = lane; i < NARR * (L + 1); i += 32) {
+        float s = part[i];
+        for (unsigned r = 1; r < nr; ++r) s += *cluster.map_shared_rank(part + i, r);
+        const int a = i / (L + 1);
+        gout[a][i - a * (L + 1)] = s;
+      }
+    }
+    cluster.sync();  // keep every rank's shared memory alive until rank 0 has read it
+  } else {
+    for (int i = lane; i < NARR * (L + 1); i += 32) {
+      const int a = i / (L + 1);
+      atomicAdd(gout[a] + (i - a * (L + 1)), part[i]);
+    }
+  }
+}
 
 struct LwParams {
   int ngpt, nlay, ncol, top_at_1, nmus, bug_compat, nchunks;
@@ -39,14 +72,14 @@ struct LwParams {
 constexpr float kPi = 3.14159265358979323846f;
 constexpr int kLwUnroll = 4;
 
-template <bool FAST>
+template <bool FAST, bool CLUSTER>
 __global__ void __launch_bounds__(64) lw_solver_kernel(const LwParams p) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
+  const int wpb = blockDim.x >> 5;  // 1 when CLUSTER
   const long long item = (long long)blockIdx.x * wpb + wib;
-  if (item >= (long long)p.ncol * p.nchunks) return;
+  if (item >= (long long)p.ncol * p.nchunks) return;  // never true when CLUSTER (grid == ncol * nchunks)
   const int col = (int)(item / p.nchunks);
   const int chunk = (int)(item % p.nchunks);
   const int g = chunk * 32 + lane;
@@ -111,13 +144,14 @@ __global__ void __launch_bounds__(64) lw_solver_kernel(const LwParams p) {
         if (i < L) {
           const int l = l0 + dl * i;
           const float tl = vt[u] * D;
-          const float t = exp_neg<FAST>(-tl);
+          float t, omt;
+          if (FAST) { t = __expf(-tl); omt = 1.0f - t; }
+          else exp_and_complement(tl, t, omt);
           float fact;
-          if (tl > tau_thresh) fact = fdiv<FAST>(1.0f - t, tl) - t;
+          if (tl > tau_thresh) fact = fdiv<FAST>(omt, tl) - t;
           else fact = tl * (0.5f - (1.0f / 3.0f) * tl);
           const float lev_dn = swap_lev ? vlo[u] : vhi[u];
           const float lev_up = swap_lev ? vhi[u] : vlo[u];
-          const float omt = 1.0f - t;
           const float src_dn = omt * lev_dn + 2.0f * fact * (vlay[u] - lev_dn);
           const float src_up = omt * lev_up + 2.0f * fact * (vlay[u] - lev_up);
           I = t * I + src_dn;
@@ -145,12 +179,8 @@ __global__ void __launch_bounds__(64) lw_solver_kernel(const LwParams p) {
     __syncwarp();
   }
   // combine the g-chunks of this column
-  float* gu = p.flux_up + (size_t)col * (L + 1);
-  float* gd = p.flux_dn + (size_t)col * (L + 1);
-  for (int i = lane; i <= L; i += 32) {
-    atomicAdd(gu + i, fup[i]);
-    atomicAdd(gd + i, fdn[i]);
-  }
+  float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
+  combine_chunks<CLUSTER, 2>(fup, L, lane, gout);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -171,7 +201,7 @@ struct SwParams {
 
 constexpr int kSwUnroll = 2;
 
-template <bool FAST, bool HAS_G>
+template <bool FAST, bool HAS_G, bool CLUSTER>
 __global__ void __launch_bounds__(64) sw_solver_kernel(const SwParams p) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
@@ -309,14 +339,9 @@ __global__ void __launch_bounds__(64) sw_solver_kernel(const SwParams p) {
     if (lane == 0) { fup[lvl] += su; fdn[lvl] += sa; }
   }
   __syncwarp();
-  float* gu = p.flux_up + (size_t)col * (L + 1);
-  float* gd = p.flux_dn + (size_t)col * (L + 1);
-  float* gr = p.flux_dir + (size_t)col * (L + 1);
-  for (int i = lane; i <= L; i += 32) {
-    atomicAdd(gu + i, fup[i]);
-    atomicAdd(gd + i, fdn[i]);
-    atomicAdd(gr + i, fdr[i]);
-  }
+  float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1),
+                          p.flux_dir + (size_t)col * (L + 1)};
+  combine_chunks<CLUSTER, 3>(fup, L, lane, gout);
 }
 
 // expand (rte/mo_rte_lw.F90:429-447): band -> g-point
@@ -338,6 +363,27 @@ static int pick_warps_per_block(size_t per_warp_bytes) {
   return (2 * per_warp_bytes <= 200 * 1024) ? 2 : 1;
 }
 
+// Launch `kernel` with one 32-thread CTA per (column, chunk) and the chunks of a column forming one cluster.
+template <typename P>
+static cudaError_t launch_clustered(void (*kernel)(const P), const P& p, long long ncta, int cluster, size_t smem,
+                                    cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)ncta);
+  cfg.blockDim = dim3(32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* Ds,
                                      const float* weights, const float* inc_flux_d, const float* tau_d,
                                      const float* lay_source_d, const float* lev_source_d, const float* sfc_emis_gpt_d,
@@ -356,21 +402,29 @@ extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int nc
   p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
   const size_t per_warp = ((size_t)nlay * 64 + 2 * (size_t)(nlay + 1)) * sizeof(float);
   RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_lw_solver_noscat: nlay too large for the on-chip layer buffer");
-  const int wpb = pick_warps_per_block(per_warp);
+  const bool clustered = p.nchunks <= 8;
+  const int wpb = clustered ? 1 : pick_warps_per_block(per_warp);
   const size_t smem = per_warp * wpb;
   const long long items = (long long)ncol * p.nchunks;
   const long long blocks = (items + wpb - 1) / wpb;
   RRNN_CHECK(blocks < 2147483647LL, "rrnn_lw_solver_noscat: too many columns for one launch");
   const size_t nflux = (size_t)ncol * (nlay + 1) * sizeof(float);
-  RRNN_CUDA(cudaMemsetAsync(flux_up_d, 0, nflux, ctx->stream));
-  RRNN_CUDA(cudaMemsetAsync(flux_dn_d, 0, nflux, ctx->stream));
-  if (ctx->fast_math) {
-    RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lw_solver_kernel<true><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
-  } else {
-    RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lw_solver_kernel<false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
+  if (!clustered) {
+    RRNN_CUDA(cudaMemsetAsync(flux_up_d, 0, nflux, ctx->stream));
+    RRNN_CUDA(cudaMemsetAsync(flux_dn_d, 0, nflux, ctx->stream));
   }
+  const int ps = prof_begin(ctx, K_LW_SOLVER);
+  if (clustered) {
+    if (ctx->fast_math) RRNN_CUDA(launch_clustered(lw_solver_kernel<true, true>, p, blocks, p.nchunks, smem, ctx->stream));
+    else RRNN_CUDA(launch_clustered(lw_solver_kernel<false, true>, p, blocks, p.nchunks, smem, ctx->stream));
+  } else if (ctx->fast_math) {
+    RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lw_solver_kernel<true, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
+  } else {
+    RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lw_solver_kernel<false, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
+  }
+  prof_end(ctx, K_LW_SOLVER, ps);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -390,23 +444,32 @@ extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
   p.alb_dir = sfc_alb_dir_d; p.alb_dif = sfc_alb_dif_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d; p.flux_dir = flux_dir_d;
   const size_t per_warp = ((size_t)nlay * 96 + 3 * (size_t)(nlay + 1)) * sizeof(float);
   RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_sw_solver_2stream: nlay too large for the on-chip layer buffer");
-  const int wpb = pick_warps_per_block(per_warp);
+  const bool clustered = p.nchunks <= 8;
+  const int wpb = clustered ? 1 : pick_warps_per_block(per_warp);
   const size_t smem = per_warp * wpb;
   const long long items = (long long)ncol * p.nchunks;
   const long long blocks = (items + wpb - 1) / wpb;
   RRNN_CHECK(blocks < 2147483647LL, "rrnn_sw_solver_2stream: too many columns for one launch");
   const size_t nflux = (size_t)ncol * (nlay + 1) * sizeof(float);
-  RRNN_CUDA(cudaMemsetAsync(flux_up_d, 0, nflux, ctx->stream));
-  RRNN_CUDA(cudaMemsetAsync(flux_dn_d, 0, nflux, ctx->stream));
-  RRNN_CUDA(cudaMemsetAsync(flux_dir_d, 0, nflux, ctx->stream));
-#define SW_LAUNCH(F, HG)                                                                                          \
-  do {                                                                                                            \
-    RRNN_CUDA(cudaFuncSetAttribute(sw_solver_kernel<F, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sw_solver_kernel<F, HG><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);                                \
+  if (!clustered) {
+    RRNN_CUDA(cudaMemsetAsync(flux_up_d, 0, nflux, ctx->stream));
+    RRNN_CUDA(cudaMemsetAsync(flux_dn_d, 0, nflux, ctx->stream));
+    RRNN_CUDA(cudaMemsetAsync(flux_dir_d, 0, nflux, ctx->stream));
+  }
+#define SW_LAUNCH(F, HG)                                                                                                 \
+  do {                                                                                                                   \
+    if (clustered) {                                                                                                     \
+      RRNN_CUDA(launch_clustered(sw_solver_kernel<F, HG, true>, p, blocks, p.nchunks, smem, ctx->stream));               \
+    } else {                                                                                                             \
+      RRNN_CUDA(cudaFuncSetAttribute(sw_solver_kernel<F, HG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      sw_solver_kernel<F, HG, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);                              \
+    }                                                                                                                    \
   } while (0)
+  const int ps = prof_begin(ctx, K_SW_SOLVER);
   if (ctx->fast_math) { if (g_d) SW_LAUNCH(true, true); else SW_LAUNCH(true, false); }
   else { if (g_d) SW_LAUNCH(false, true); else SW_LAUNCH(false, false); }
 #undef SW_LAUNCH
+  prof_end(ctx, K_SW_SOLVER, ps);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }

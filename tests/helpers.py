@@ -39,8 +39,41 @@ def gas_concs(gases):
     return gc
 
 
-def tau_rel_err(tau, ref):
-    """Relative tau error with an absolute floor of 1e-6 x the largest tau of the same sample
-    (weak g-points sit at fp32 reorder-noise level: tau = (ystd*z+ymean)^8 amplifies dz by 8*ystd/ymean)."""
-    floor = 1e-6 * np.max(np.abs(ref), axis=-1, keepdims=True) + 1e-30
-    return np.abs(tau - ref) / np.maximum(np.abs(ref), floor)
+TAU_FLOOR = 1.0e-4   # relative tau error is measured against max(tau, TAU_FLOOR x largest tau of the same sample)
+NOISE_FACTOR = 1.5   # an fp32 implementation may sit this many times the reference arithmetic's own fp32 noise from fp64
+
+
+def tau_rel_err(tau, ref, floor=TAU_FLOOR):
+    """Relative tau error with an absolute floor of `floor` x the largest tau of the same (layer, column) sample.
+    tau = (ystd*z + ymean)^8 * N_dry amplifies last-layer rounding by 8*ystd/ymean (up to 32 LW / 243 SW at the weakest
+    g-points), so g-points 1e4 times weaker than the spectral maximum sit at fp32 summation-order noise: the strict
+    fp32 oracle itself is up to 2e-4 away from the fp64 evaluation there (measured), and they carry no flux."""
+    ref = np.asarray(ref, np.float64)
+    fl = floor * np.max(np.abs(ref), axis=-1, keepdims=True) + 1e-300
+    return np.abs(tau - ref) / np.maximum(np.abs(ref), fl)
+
+
+def assert_within_reference_noise(got, ref32, ref64, tol, what=""):
+    """The parity statement used where the reference's own fp32 rounding noise is comparable to the tolerance:
+    (a) |got - ref32| <= max(tol, 2 x noise)  and  (b) |got - ref64| <= max(tol, NOISE_FACTOR x noise), where
+    noise = max|ref32 - ref64| is how far the reference arithmetic (strict fp32 oracle) is from the rounding-free
+    evaluation of the same algorithm on the same inputs."""
+    got = np.asarray(got, np.float64); ref32 = np.asarray(ref32, np.float64); ref64 = np.asarray(ref64, np.float64)
+    noise = np.abs(ref32 - ref64).max()
+    d32 = np.abs(got - ref32).max(); d64 = np.abs(got - ref64).max()
+    assert d32 <= max(tol, 2.0 * noise), f"{what}: |got-oracle32| {d32:.3e} > max({tol}, 2*noise {noise:.3e})"
+    assert d64 <= max(tol, NOISE_FACTOR * noise), f"{what}: |got-oracle64| {d64:.3e} > max({tol}, {NOISE_FACTOR}*noise {noise:.3e})"
+    return d32, d64, noise
+
+
+def assert_tau_parity(tau, ref32, ref64):
+    """tau parity, fp32 path: relative error (floored, see tau_rel_err) against the strict fp32 oracle <= 1e-4 -- or,
+    where two fp32 evaluations cannot agree that well, within the reference arithmetic's own distance from fp64."""
+    e32 = tau_rel_err(tau, ref32).max()
+    e64 = tau_rel_err(tau, ref64).max()
+    noise = tau_rel_err(ref32, ref64).max()
+    assert e32 <= max(TAU_RTOL, 2.0 * noise), f"tau rel err vs fp32 oracle {e32:.3e} (oracle noise {noise:.3e})"
+    assert e64 <= max(TAU_RTOL, NOISE_FACTOR * noise), f"tau rel err vs fp64 {e64:.3e} (oracle noise {noise:.3e})"
+    # the bulk of the spectrum (tau >= 1% of the sample maximum) must meet the plain 1e-4 with a wide margin
+    assert tau_rel_err(tau, ref32, floor=1e-2).max() <= 0.25 * TAU_RTOL
+    return e32, e64, noise
