@@ -1,0 +1,171 @@
+! ISO_C_BINDING interfaces of librrnn_b200.so (include/rrnn.h).
+!
+! NOT COMPILED IN THIS REPOSITORY'S IMAGE: no Fortran compiler exists here (SURVEY.md section 0, F1).  The file is kept
+! deliberately declarative -- one interface block per C entry point, scalars by value, arrays by reference as
+! type(c_ptr) device addresses or contiguous real(c_float) host arrays -- so that a maintainer with gfortran /
+! nvfortran can build it with `make -C fortran` (guarded on `command -v gfortran`).  Every compute entry point is
+! exercised through the same C ABI from Python (tests/test_parity_gpu.py); nothing in the shim can change results.
+module mo_rrnn_c_binding
+  use, intrinsic :: iso_c_binding
+  implicit none
+  public
+
+  ! rrnn_gas_t (include/rrnn.h): one gas of ty_gas_concs
+  type, bind(C) :: rrnn_gas_t
+    character(kind=c_char) :: name(32)
+    type(c_ptr)            :: conc
+    real(c_float)          :: value
+    integer(c_int)         :: ndims
+  end type rrnn_gas_t
+
+  interface
+    function rrnn_last_error() bind(C, name="rrnn_last_error") result(msg)
+      import :: c_ptr
+      type(c_ptr) :: msg
+    end function
+    function rrnn_ctx_create(device, stream, ctx) bind(C, name="rrnn_ctx_create") result(rc)
+      import :: c_int, c_ptr
+      integer(c_int), value :: device
+      type(c_ptr),    value :: stream
+      type(c_ptr)           :: ctx
+      integer(c_int)        :: rc
+    end function
+    function rrnn_ctx_destroy(ctx) bind(C, name="rrnn_ctx_destroy") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int)     :: rc
+    end function
+    function rrnn_ctx_set_flag(ctx, name, val) bind(C, name="rrnn_ctx_set_flag") result(rc)
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char) :: name(*)
+      integer(c_int), value :: val
+      integer(c_int)     :: rc
+    end function
+    ! rrtmgp_network_type%load_netcdf  (neural/mod_network_rrtmgp.F90:58-122)
+    function rrnn_model_load_netcdf(ctx, filename, model) bind(C, name="rrnn_model_load_netcdf") result(rc)
+      import :: c_int, c_ptr, c_char
+      type(c_ptr), value     :: ctx
+      character(kind=c_char) :: filename(*)
+      type(c_ptr)            :: model
+      integer(c_int)         :: rc
+    end function
+    function rrnn_model_destroy(model) bind(C, name="rrnn_model_destroy") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: model
+      integer(c_int)     :: rc
+    end function
+    ! ty_gas_optics_rrtmgp%load subset used by the NN path  (rrtmgp/mo_gas_optics_rrtmgp.F90:1130-1326)
+    function rrnn_kdist_create(ctx, nbnd, ngpt, band_lims_gpt, ntemp, totplnk, temp_ref_min, totplnk_delta, &
+                               solar_source, kd) bind(C, name="rrnn_kdist_create") result(rc)
+      import :: c_int, c_ptr, c_float
+      type(c_ptr),    value :: ctx
+      integer(c_int), value :: nbnd, ngpt, ntemp
+      integer(c_int)        :: band_lims_gpt(2, *)
+      type(c_ptr),    value :: totplnk, solar_source     ! host real(c_float) arrays or c_null_ptr
+      real(c_float),  value :: temp_ref_min, totplnk_delta
+      type(c_ptr)           :: kd
+      integer(c_int)        :: rc
+    end function
+    function rrnn_kdist_set_tsi(kd, tsi) bind(C, name="rrnn_kdist_set_tsi") result(rc)
+      import :: c_int, c_ptr, c_float
+      type(c_ptr),   value :: kd
+      real(c_float), value :: tsi
+      integer(c_int)       :: rc
+    end function
+    ! gas_optics (LW), neural_nets present  (rrtmgp/mo_gas_optics_rrtmgp.F90:239-243, NN branch :368-411)
+    function rrnn_gas_optics_lw(ctx, kd, models, nmodels, ncol, nlay, play, plev, tlay, tsfc, gases, ngas, tlev, &
+                                tau, lay_source, lev_source, sfc_source, sfc_source_Jac) &
+                                bind(C, name="rrnn_gas_optics_lw") result(rc)
+      import :: c_int, c_ptr, rrnn_gas_t
+      type(c_ptr),    value :: ctx, kd
+      type(c_ptr)           :: models(*)
+      integer(c_int), value :: nmodels, ncol, nlay, ngas
+      type(c_ptr),    value :: play, plev, tlay, tsfc, tlev           ! device pointers
+      type(rrnn_gas_t)      :: gases(*)
+      type(c_ptr),    value :: tau, lay_source, lev_source, sfc_source, sfc_source_Jac
+      integer(c_int)        :: rc
+    end function
+    ! gas_optics (SW)  (rrtmgp/mo_gas_optics_rrtmgp.F90:433-437, NN branch :529-573)
+    function rrnn_gas_optics_sw(ctx, kd, models, ncol, nlay, play, plev, tlay, gases, ngas, tau, ssa, g, toa_src) &
+                                bind(C, name="rrnn_gas_optics_sw") result(rc)
+      import :: c_int, c_ptr, rrnn_gas_t
+      type(c_ptr),    value :: ctx, kd
+      type(c_ptr)           :: models(*)
+      integer(c_int), value :: ncol, nlay, ngas
+      type(c_ptr),    value :: play, plev, tlay
+      type(rrnn_gas_t)      :: gases(*)
+      type(c_ptr),    value :: tau, ssa, g, toa_src
+      integer(c_int)        :: rc
+    end function
+    ! rte_lw  (rte/mo_rte_lw.F90:60-64)
+    function rrnn_rte_lw(ctx, kd, nlay, ncol, top_at_1, n_gauss_angles, inc_flux, tau, lay_source, lev_source, &
+                         sfc_source, sfc_emis, flux_up, flux_dn) bind(C, name="rrnn_rte_lw") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, kd
+      integer(c_int), value :: nlay, ncol, top_at_1, n_gauss_angles
+      type(c_ptr),    value :: inc_flux, tau, lay_source, lev_source, sfc_source, sfc_emis, flux_up, flux_dn
+      integer(c_int)        :: rc
+    end function
+    ! rte_sw  (rte/mo_rte_sw.F90:48-52)
+    function rrnn_rte_sw(ctx, ngpt, nlay, ncol, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, inc_flux_dif, &
+                         tau, ssa, g, flux_up, flux_dn, flux_dn_dir) bind(C, name="rrnn_rte_sw") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx
+      integer(c_int), value :: ngpt, nlay, ncol, top_at_1
+      type(c_ptr),    value :: mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, inc_flux_dif, tau, ssa, g
+      type(c_ptr),    value :: flux_up, flux_dn, flux_dn_dir
+      integer(c_int)        :: rc
+    end function
+    ! whole block-loop body with HOST arrays (examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:368-446)
+    function rrnn_lw_fluxes_host(ctx, kd, models, nmodels, ncol, nlay, top_at_1, n_gauss_angles, play, plev, tlay, tlev, &
+                                 tsfc, sfc_emis, gases, ngas, flux_up, flux_dn) bind(C, name="rrnn_lw_fluxes_host") result(rc)
+      import :: c_int, c_ptr, c_float, rrnn_gas_t
+      type(c_ptr),    value :: ctx, kd
+      type(c_ptr)           :: models(*)
+      integer(c_int), value :: nmodels, ncol, nlay, top_at_1, n_gauss_angles, ngas
+      real(c_float)         :: play(nlay, *), plev(nlay+1, *), tlay(nlay, *), tlev(nlay+1, *), tsfc(*), sfc_emis(*)
+      type(rrnn_gas_t)      :: gases(*)
+      real(c_float)         :: flux_up(nlay+1, *), flux_dn(nlay+1, *)
+      integer(c_int)        :: rc
+    end function
+    function rrnn_sw_fluxes_host(ctx, kd, models, ncol, nlay, top_at_1, play, plev, tlay, mu0, sfc_alb, tsi, gases, ngas, &
+                                 flux_up, flux_dn, flux_dn_dir) bind(C, name="rrnn_sw_fluxes_host") result(rc)
+      import :: c_int, c_ptr, c_float, rrnn_gas_t
+      type(c_ptr),    value :: ctx, kd
+      type(c_ptr)           :: models(*)
+      integer(c_int), value :: ncol, nlay, top_at_1, ngas
+      real(c_float)         :: play(nlay, *), plev(nlay+1, *), tlay(nlay, *), mu0(*), sfc_alb(*)
+      type(c_ptr),    value :: tsi                                  ! c_loc(tsi) or c_null_ptr
+      type(rrnn_gas_t)      :: gases(*)
+      real(c_float)         :: flux_up(nlay+1, *), flux_dn(nlay+1, *), flux_dn_dir(nlay+1, *)
+      integer(c_int)        :: rc
+    end function
+    ! compute_heating_rate  (extensions/mo_heating_rates.F90:26-54)
+    function rrnn_heating_rate(ctx, ncol, nlay, flux_up, flux_dn, plev, heating_rate) bind(C, name="rrnn_heating_rate") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx
+      integer(c_int), value :: ncol, nlay
+      type(c_ptr),    value :: flux_up, flux_dn, plev, heating_rate
+      integer(c_int)        :: rc
+    end function
+  end interface
+
+contains
+
+  ! copy the thread-local C error string into the reference's character(len=128) error_msg convention
+  function rrnn_error_msg(rc) result(error_msg)
+    integer(c_int), intent(in) :: rc
+    character(len=128)         :: error_msg
+    character(kind=c_char), pointer :: s(:)
+    integer :: i
+    error_msg = ""
+    if (rc == 0) return
+    call c_f_pointer(rrnn_last_error(), s, [128])
+    do i = 1, 128
+      if (s(i) == c_null_char) exit
+      error_msg(i:i) = s(i)
+    end do
+  end function rrnn_error_msg
+
+end module mo_rrnn_c_binding

@@ -70,11 +70,49 @@ struct LwParams {
 };
 
 constexpr float kPi = 3.14159265358979323846f;
-constexpr int kLwUnroll = 4;
+constexpr int kLwU = 8;  // layers per software-pipelined group (LW)
+constexpr int kSwU = 4;  // layers per group (SW)
+
+// Sum N (power of two, <= 8) values per lane over the 32 lanes with N-1 + log2(32/N) shuffles instead of 5N:
+// a butterfly that halves the number of live values at every step.  On return v[0] of lane `lane` holds the
+// all-lane sum of the original v[multi_index(lane)].
+template <int N>
+__device__ __forceinline__ void multi_reduce(float (&v)[N], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const float send = upper ? v[k] : v[k + half];
+      const float keep = upper ? v[k + half] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+template <int N>
+__device__ __forceinline__ int multi_index(int lane) {
+  int idx = 0, off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1) {
+    if (lane & off) idx += n >> 1;
+    off >>= 1;
+  }
+  return idx;
+}
+template <int N>
+__device__ __forceinline__ bool multi_writer(int lane) {  // one lane per distinct index
+  return (lane & ((32 / N) - 1)) == 0;
+}
 
 template <bool FAST, bool CLUSTER>
 __global__ void __launch_bounds__(64) lw_solver_kernel(const LwParams p) {
   extern __shared__ float smem[];
+  constexpr int U = kLwU;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;  // 1 when CLUSTER
@@ -95,86 +133,114 @@ __global__ void __launch_bounds__(64) lw_solver_kernel(const LwParams p) {
   for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
   __syncwarp();
 
-  const size_t gl_off = (size_t)col * L * G + g;         // + l*G
-  const size_t gv_off = (size_t)col * (L + 1) * G + g;   // + lev*G
-  const size_t gc_off = (size_t)col * G + g;
-  const float* tau = p.tau + gl_off;
-  const float* lay = p.lay_source + gl_off;
-  const float* lev = p.lev_source + gv_off;
+  // inactive lanes (ngpt not a multiple of 32) read lane 0's g-point and contribute zero
+  const int gs = act ? g : chunk * 32;
+  const float* tau = p.tau + (size_t)col * L * G + gs;
+  const float* lay = p.lay_source + (size_t)col * L * G + gs;
+  const float* lev = p.lev_source + (size_t)col * (L + 1) * G + gs;
+  const size_t gc_off = (size_t)col * G + gs;
   const float tau_thresh = 3.4526698e-4f;  // sqrt(epsilon(1._sp)), mo_rte_solver_kernels.F90:754
-  const float emis = act ? p.sfc_emis[gc_off] : 0.0f;
-  const float ssrc = act ? p.sfc_source[gc_off] : 0.0f;
-  const float inc = (act && p.inc_flux) ? p.inc_flux[gc_off] : 0.0f;
+  const float emis = p.sfc_emis[gc_off];
+  const float ssrc = p.sfc_source[gc_off];
+  const float inc = p.inc_flux ? p.inc_flux[gc_off] : 0.0f;
+  const float live = act ? 1.0f : 0.0f;
 
-  // sweep direction in memory: top_at_1 -> down sweep walks l = 0..L-1, else L-1..0
-  const int l0 = p.top_at_1 ? 0 : L - 1;
-  const int dl = p.top_at_1 ? 1 : -1;
-  // which level row feeds source_dn / source_up for layer l (array indices):
-  //   reference (bug-compatible, Q1): dn <- lev[l+1], up <- lev[l] whatever the orientation.
-  //   physical for top_at_1=false:     dn <- lev[l],   up <- lev[l+1].
-  const bool swap_lev = (!p.top_at_1) && (!p.bug_compat);
+  // Sweep order i = 0..L-1 runs from the top of the atmosphere down: layer l(i) = l0 + dl*i.  In sweep order
+  // layer i is bounded by level rows ent(i) (towards the top) and ext(i) = ent(i+1) (towards the surface).
+  const int top = p.top_at_1;
+  const int l0 = top ? 0 : L - 1;
+  const int dl = top ? 1 : -1;
+  // lw_source_noscat (:770-773) takes source_dn from lev(l+1) and source_up from lev(l) whatever the orientation
+  // (quirk Q1).  In sweep terms: top_at_1 -> dn uses ext, up uses ent (physical).  Otherwise the reference uses
+  // dn <- lev(l+1) = ent, up <- lev(l) = ext; the physical choice is again dn <- ext, up <- ent.
+  const bool dn_uses_ext = top || !p.bug_compat;
 
   for (int imu = 0; imu < p.nmus; ++imu) {
     const float D = p.Ds[imu];
-    const float fac = 2.0f * kPi * p.wts[imu];
-    float I = inc / fac;  // radn_dn(top) = inc_flux/(2 pi w), :196-201
+    const float fac = 2.0f * kPi * p.wts[imu] * live;
+    float I = inc / (2.0f * kPi * p.wts[imu]);  // radn_dn(top) = inc_flux/(2 pi w), :196-201
     {
-      float s = warp_sum(fac * I);
-      if (lane == 0) fdn[p.top_at_1 ? 0 : L] += s;
+      const float s = warp_sum(fac * I);
+      if (lane == 0) fdn[top ? 0 : L] += s;
     }
-    // ---------------- downward sweep ----------------
-    for (int i0 = 0; i0 < L; i0 += kLwUnroll) {
-      float vt[kLwUnroll], vlay[kLwUnroll], vlo[kLwUnroll], vhi[kLwUnroll];
+    // ---------------- downward sweep, software pipelined in groups of U layers ----------------
+    float n_tau[U], n_lay[U], n_ext[U];
+    float carry = ld_stream(lev + (size_t)(top ? 0 : L) * G);  // ent(0)
+    auto load_group = [&](int i0) {
 #pragma unroll
-      for (int u = 0; u < kLwUnroll; ++u) {
-        const int i = i0 + u;
-        if (i < L && act) {
-          const int l = l0 + dl * i;
-          vt[u] = ld_stream(tau + (size_t)l * G);
-          vlay[u] = ld_stream(lay + (size_t)l * G);
-          vlo[u] = ld_stream(lev + (size_t)l * G);
-          vhi[u] = ld_stream(lev + (size_t)(l + 1) * G);
-        } else {
-          vt[u] = 0.f; vlay[u] = 0.f; vlo[u] = 0.f; vhi[u] = 0.f;
-        }
+      for (int u = 0; u < U; ++u) {
+        const int i = min(i0 + u, L - 1);
+        const int l = l0 + dl * i;
+        n_tau[u] = ld_stream(tau + (size_t)l * G);
+        n_lay[u] = ld_stream(lay + (size_t)l * G);
+        n_ext[u] = ld_stream(lev + (size_t)(top ? l + 1 : l) * G);
       }
+    };
+    load_group(0);
+    for (int i0 = 0; i0 < L; i0 += U) {
+      float c_tau[U], c_lay[U], c_ext[U];
 #pragma unroll
-      for (int u = 0; u < kLwUnroll; ++u) {
-        const int i = i0 + u;
-        if (i < L) {
-          const int l = l0 + dl * i;
-          const float tl = vt[u] * D;
-          float t, omt;
-          if (FAST) { t = __expf(-tl); omt = 1.0f - t; }
-          else exp_and_complement(tl, t, omt);
-          float fact;
-          if (tl > tau_thresh) fact = fdiv<FAST>(omt, tl) - t;
-          else fact = tl * (0.5f - (1.0f / 3.0f) * tl);
-          const float lev_dn = swap_lev ? vlo[u] : vhi[u];
-          const float lev_up = swap_lev ? vhi[u] : vlo[u];
-          const float src_dn = omt * lev_dn + 2.0f * fact * (vlay[u] - lev_dn);
-          const float src_up = omt * lev_up + 2.0f * fact * (vlay[u] - lev_up);
-          I = t * I + src_dn;
-          buf[(size_t)l * 32 + lane] = make_float2(t, src_up);
-          const float s = warp_sum(fac * I);
-          if (lane == 0) fdn[p.top_at_1 ? l + 1 : l] += s;
-        }
+      for (int u = 0; u < U; ++u) { c_tau[u] = n_tau[u]; c_lay[u] = n_lay[u]; c_ext[u] = n_ext[u]; }
+      if (i0 + U < L) load_group(i0 + U);
+      float tv[U], sdn[U], sup[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float ent = (u == 0) ? carry : c_ext[u - 1];
+        const float ext = c_ext[u];
+        const float tl = c_tau[u] * D;
+        float t, omt;
+        if (FAST) { t = __expf(-tl); omt = 1.0f - t; }
+        else exp_and_complement(tl, t, omt);
+        float fact;
+        if (tl > tau_thresh) fact = fdiv<FAST>(omt, tl) - t;
+        else fact = tl * (0.5f - (1.0f / 3.0f) * tl);
+        const float lev_dn = dn_uses_ext ? ext : ent;
+        const float lev_up = dn_uses_ext ? ent : ext;
+        tv[u] = t;
+        sdn[u] = omt * lev_dn + 2.0f * fact * (c_lay[u] - lev_dn);
+        sup[u] = omt * lev_up + 2.0f * fact * (c_lay[u] - lev_up);
       }
+      carry = c_ext[U - 1];
+      float red[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u;
+        if (i < L) {  // warp-uniform; the ragged tail of the last group is computed on clamped loads and dropped
+          I = tv[u] * I + sdn[u];
+          buf[(size_t)(l0 + dl * i) * 32 + lane] = make_float2(tv[u], sup[u]);
+        }
+        red[u] = fac * I;
+      }
+      multi_reduce<U>(red, lane);
+      const int i = i0 + multi_index<U>(lane);
+      if (multi_writer<U>(lane) && i < L) fdn[top ? (l0 + dl * i) + 1 : (l0 + dl * i)] += red[0];
     }
     // ---------------- surface ----------------
-    float U = I * (1.0f - emis) + emis * ssrc;  // :269
+    float U0 = I;
+    U0 = U0 * (1.0f - emis) + emis * ssrc;  // :269
     {
-      const float s = warp_sum(fac * U);
-      if (lane == 0) fup[p.top_at_1 ? L : 0] += s;
+      const float s = warp_sum(fac * U0);
+      if (lane == 0) fup[top ? L : 0] += s;
     }
     __syncwarp();
-    // ---------------- upward sweep (reverse memory order) ----------------
-    for (int i = L - 1; i >= 0; --i) {
-      const int l = l0 + dl * i;
-      const float2 b = buf[(size_t)l * 32 + lane];
-      U = b.x * U + b.y;
-      const float s = warp_sum(fac * U);
-      if (lane == 0) fup[p.top_at_1 ? l : l + 1] += s;
+    // ---------------- upward sweep (reverse order) from the on-chip buffer ----------------
+    float Uu = U0;
+    for (int i1 = L - 1; i1 >= 0; i1 -= U) {
+      float2 b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = max(i1 - u, 0);
+        b[u] = buf[(size_t)(l0 + dl * i) * 32 + lane];
+      }
+      float red[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i1 - u >= 0) Uu = b[u].x * Uu + b[u].y;
+        red[u] = fac * Uu;
+      }
+      multi_reduce<U>(red, lane);
+      const int i = i1 - multi_index<U>(lane);
+      if (multi_writer<U>(lane) && i >= 0) fup[top ? (l0 + dl * i) : (l0 + dl * i) + 1] += red[0];
     }
     __syncwarp();
   }
@@ -194,16 +260,15 @@ struct SwParams {
   const float* mu0;
   const float* alb_dir;
   const float* alb_dif;
-  float* flux_up;  // zero-initialised
+  float* flux_up;
   float* flux_dn;
   float* flux_dir;
 };
 
-constexpr int kSwUnroll = 2;
-
 template <bool FAST, bool HAS_G, bool CLUSTER>
 __global__ void __launch_bounds__(64) sw_solver_kernel(const SwParams p) {
   extern __shared__ float smem[];
+  constexpr int U = kSwU;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -227,116 +292,153 @@ __global__ void __launch_bounds__(64) sw_solver_kernel(const SwParams p) {
   for (int i = lane; i < 3 * (L + 1); i += 32) fup[i] = 0.0f;
   __syncwarp();
 
-  const size_t gl_off = (size_t)col * L * G + gp;
-  const size_t gc_off = (size_t)col * G + gp;
-  const float* tau = p.tau + gl_off;
-  const float* ssa = p.ssa + gl_off;
-  const float* gas = HAS_G ? p.g + gl_off : nullptr;
+  const int gs = act ? gp : chunk * 32;  // inactive lanes shadow lane 0 and contribute zero
+  const float live = act ? 1.0f : 0.0f;
+  const float* tau = p.tau + (size_t)col * L * G + gs;
+  const float* ssa = p.ssa + (size_t)col * L * G + gs;
+  const float* gas = HAS_G ? p.g + (size_t)col * L * G + gs : nullptr;
+  const size_t gc_off = (size_t)col * G + gs;
   const float mu0 = p.mu0[col];
   const float mu0_inv = 1.0f / mu0;
   const float k_min = 1.e-4f;       // mo_rte_solver_kernels.F90:76-82 (single precision)
   const float eps = 1.1920929e-7f;  // epsilon(1._sp)
 
-  const int l0 = p.top_at_1 ? 0 : L - 1;
-  const int dl = p.top_at_1 ? 1 : -1;
-  const int top_level = p.top_at_1 ? 0 : L;
+  const int top = p.top_at_1;
+  const int l0 = top ? 0 : L - 1;
+  const int dl = top ? 1 : -1;
+  const int top_level = top ? 0 : L;
 
-  float dir = act ? p.inc_flux[gc_off] * mu0 : 0.0f;                      // :589
-  float beta = (act && p.inc_flux_dif) ? p.inc_flux_dif[gc_off] : 0.0f;   // :590
+  float dir = live * p.inc_flux[gc_off] * mu0;                         // :589
+  float beta = p.inc_flux_dif ? live * p.inc_flux_dif[gc_off] : 0.0f;  // :590
   float alpha = 0.0f;
   {
     const float sd = warp_sum(dir), sb = warp_sum(beta + dir);
     if (lane == 0) { fdr[top_level] += sd; fdn[top_level] += sb; }
   }
-  // ---------------- sweep 1: top -> surface ----------------
-  for (int i0 = 0; i0 < L; i0 += kSwUnroll) {
-    float vt[kSwUnroll], vw[kSwUnroll], vg[kSwUnroll];
+  // ---------------- sweep 1: top -> surface, software pipelined in groups of U layers ----------------
+  float n_t[U], n_w[U], n_g[U];
+  auto load_group = [&](int i0) {
 #pragma unroll
-    for (int u = 0; u < kSwUnroll; ++u) {
-      const int i = i0 + u;
-      if (i < L && act) {
-        const int l = l0 + dl * i;
-        vt[u] = ld_stream(tau + (size_t)l * G);
-        vw[u] = ld_stream(ssa + (size_t)l * G);
-        vg[u] = HAS_G ? ld_stream(gas + (size_t)l * G) : 0.0f;
-      } else {
-        vt[u] = 0.f; vw[u] = 0.f; vg[u] = 0.f;
-      }
+    for (int u = 0; u < U; ++u) {
+      const int l = l0 + dl * min(i0 + u, L - 1);
+      n_t[u] = ld_stream(tau + (size_t)l * G);
+      n_w[u] = ld_stream(ssa + (size_t)l * G);
+      n_g[u] = HAS_G ? ld_stream(gas + (size_t)l * G) : 0.0f;
     }
+  };
+  load_group(0);
+  for (int i0 = 0; i0 < L; i0 += U) {
+    float c_t[U], c_w[U], c_g[U];
 #pragma unroll
-    for (int u = 0; u < kSwUnroll; ++u) {
+    for (int u = 0; u < U; ++u) { c_t[u] = n_t[u]; c_w[u] = n_w[u]; c_g[u] = n_g[u]; }
+    if (i0 + U < L) load_group(i0 + U);
+    // layer coefficients: independent across the U layers (instruction-level parallelism)
+    float Rdif[U], Tdif[U], Rdir[U], Tdir[U], Tnos[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float tauv = c_t[u], w0 = c_w[u], gg = c_g[u];
+      // ---- sw_two_stream_source :1405-1475 ----
+      const float Tnoscat = exp_neg<FAST>(-tauv * mu0_inv);
+      const float gamma1 = (8.0f - w0 * (5.0f + 3.0f * gg)) * 0.25f;
+      const float gamma2 = 3.0f * (w0 * (1.0f - gg)) * 0.25f;
+      const float gamma3 = (2.0f - 3.0f * mu0 * gg) * 0.25f;
+      const float gamma4 = 1.0f - gamma3;
+      const float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
+      const float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
+      const float k = fsqrt<FAST>(fmaxf((gamma1 - gamma2) * (gamma1 + gamma2), k_min));
+      const float ekt = exp_neg<FAST>(-tauv * k);
+      const float e2kt = ekt * ekt;
+      const float k2e = 2.0f * k * ekt;
+      float RT = rcp<FAST>(k * (1.0f + e2kt) + gamma1 * (1.0f - e2kt));
+      Rdif[u] = RT * gamma2 * (1.0f - e2kt);
+      Tdif[u] = RT * 2.0f * k * ekt;
+      const float k_mu = k * mu0;
+      const float k_mu2 = k_mu * k_mu;
+      const float k_gamma3 = k * gamma3;
+      const float k_gamma4 = k * gamma4;
+      const float om = 1.0f - k_mu2;
+      const float dd = (fabsf(om) >= eps) ? om : eps;
+      RT = fdiv<FAST>(w0 * RT, dd);
+      float rd = RT * ((1.0f - k_mu) * (alpha2 + k_gamma3) - (1.0f + k_mu) * (alpha2 - k_gamma3) * e2kt -
+                       k2e * (gamma3 - alpha2 * mu0) * Tnoscat);
+      float td = RT * (k2e * (gamma4 + alpha1 * mu0) -
+                       Tnoscat * ((1.0f + k_mu) * (alpha1 + k_gamma4) - (1.0f - k_mu) * (alpha1 - k_gamma4) * e2kt));
+      rd = fmaxf(0.0f, fminf(rd, 1.0f - Tnoscat));
+      td = fmaxf(0.0f, fminf(td, 1.0f - Tnoscat - rd));
+      Rdir[u] = rd; Tdir[u] = td; Tnos[u] = Tnoscat;
+    }
+    // the sequential part: direct beam and the adding recurrences, eliminated from the top
+    float red[2 * U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       const int i = i0 + u;
-      if (i < L) {
+      if (i < L) {  // warp-uniform
         const int l = l0 + dl * i;
-        const float tauv = vt[u], w0 = vw[u], gg = vg[u];
-        // ---- sw_two_stream_source :1405-1475 ----
-        const float Tnoscat = exp_neg<FAST>(-tauv * mu0_inv);
-        const float gamma1 = (8.0f - w0 * (5.0f + 3.0f * gg)) * 0.25f;
-        const float gamma2 = 3.0f * (w0 * (1.0f - gg)) * 0.25f;
-        const float gamma3 = (2.0f - 3.0f * mu0 * gg) * 0.25f;
-        const float gamma4 = 1.0f - gamma3;
-        const float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
-        const float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
-        const float k = fsqrt<FAST>(fmaxf((gamma1 - gamma2) * (gamma1 + gamma2), k_min));
-        const float ekt = exp_neg<FAST>(-tauv * k);
-        const float e2kt = ekt * ekt;
-        const float k2e = 2.0f * k * ekt;
-        float RT = rcp<FAST>(k * (1.0f + e2kt) + gamma1 * (1.0f - e2kt));
-        const float Rdif = RT * gamma2 * (1.0f - e2kt);
-        const float Tdif = RT * 2.0f * k * ekt;
-        const float k_mu = k * mu0;
-        const float k_mu2 = k_mu * k_mu;
-        const float k_gamma3 = k * gamma3;
-        const float k_gamma4 = k * gamma4;
-        const float om = 1.0f - k_mu2;
-        const float dd = (fabsf(om) >= eps) ? om : eps;
-        RT = fdiv<FAST>(w0 * RT, dd);
-        float Rdir = RT * ((1.0f - k_mu) * (alpha2 + k_gamma3) - (1.0f + k_mu) * (alpha2 - k_gamma3) * e2kt -
-                           k2e * (gamma3 - alpha2 * mu0) * Tnoscat);
-        float Tdir = RT * (k2e * (gamma4 + alpha1 * mu0) -
-                           Tnoscat * ((1.0f + k_mu) * (alpha1 + k_gamma4) - (1.0f - k_mu) * (alpha1 - k_gamma4) * e2kt));
-        Rdir = fmaxf(0.0f, fminf(Rdir, 1.0f - Tnoscat));
-        Tdir = fmaxf(0.0f, fminf(Tdir, 1.0f - Tnoscat - Rdir));
-        const float s_up = Rdir * dir;
-        const float s_dn = Tdir * dir;
-        dir = Tnoscat * dir;
-        // ---- adding, eliminated from the top (mirror image of :1560-1577) ----
-        const float d = rcp<FAST>(1.0f - Rdif * alpha);
-        const float e = d * Tdif;
-        const float f = d * (Rdif * beta + s_up);
+        const float s_up = Rdir[u] * dir;
+        const float s_dn = Tdir[u] * dir;
+        dir = Tnos[u] * dir;
+        const float d = rcp<FAST>(1.0f - Rdif[u] * alpha);
+        const float e = d * Tdif[u];
+        const float f = d * (Rdif[u] * beta + s_up);
         beta = s_dn + e * (beta + alpha * s_up);
-        alpha = Rdif + Tdif * e * alpha;
+        alpha = Rdif[u] + Tdif[u] * e * alpha;
         be[(size_t)l * 32 + lane] = e;
         bf[(size_t)l * 32 + lane] = f;
         ba[(size_t)l * 32 + lane] = alpha;  // reflectance seen from the level BELOW layer l
-        const float sd = warp_sum(dir), sb = warp_sum(beta + dir);
-        const int lvl = p.top_at_1 ? l + 1 : l;
-        if (lane == 0) { fdr[lvl] += sd; fdn[lvl] += sb; }
+      }
+      red[u] = dir;
+      red[U + u] = beta + dir;
+    }
+    multi_reduce<2 * U>(red, lane);
+    {
+      const int idx = multi_index<2 * U>(lane);
+      const int i = i0 + (idx & (U - 1));
+      if (multi_writer<2 * U>(lane) && i < L) {
+        const int l = l0 + dl * i;
+        const int lvl = top ? l + 1 : l;
+        if (idx < U) fdr[lvl] += red[0]; else fdn[lvl] += red[0];
       }
     }
   }
   // ---------------- surface ----------------
-  const float a_s = act ? p.alb_dif[gc_off] : 0.0f;
-  const float S_s = act ? dir * p.alb_dir[gc_off] : 0.0f;  // source_sfc :1477
-  float U = fdiv<FAST>(a_s * beta + S_s, 1.0f - a_s * alpha);
+  const float a_s = p.alb_dif[gc_off];
+  const float S_s = dir * p.alb_dir[gc_off];  // source_sfc :1477
+  float Uu = fdiv<FAST>(a_s * beta + S_s, 1.0f - a_s * alpha) * live;
   {
-    const int sfc = p.top_at_1 ? L : 0;
-    const float su = warp_sum(U), sa = warp_sum(alpha * U);
+    const int sfc = top ? L : 0;
+    const float su = warp_sum(Uu), sa = warp_sum(alpha * Uu);
     if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
   }
   __syncwarp();
   // ---------------- sweep 2: surface -> top (back substitution) ----------------
-  for (int i = L - 1; i >= 0; --i) {
-    const int l = l0 + dl * i;
-    U = be[(size_t)l * 32 + lane] * U + bf[(size_t)l * 32 + lane];
-    const int lvl = p.top_at_1 ? l : l + 1;  // level at the top of layer l
-    const float su = warp_sum(U);
-    float sa = 0.0f;
-    if (i > 0) {
-      const int labove = l - dl;
-      sa = warp_sum(ba[(size_t)labove * 32 + lane] * U);
+  for (int i1 = L - 1; i1 >= 0; i1 -= U) {
+    float ce[U], cf[U], ca[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = max(i1 - u, 0);
+      const int l = l0 + dl * i;
+      ce[u] = be[(size_t)l * 32 + lane];
+      cf[u] = bf[(size_t)l * 32 + lane];
+      // reflectance of the atmosphere above the level at the top of layer i (0 at the top of the domain)
+      ca[u] = (i > 0) ? ba[(size_t)(l - dl) * 32 + lane] : 0.0f;
     }
-    if (lane == 0) { fup[lvl] += su; fdn[lvl] += sa; }
+    float red[2 * U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i1 - u >= 0) Uu = ce[u] * Uu + cf[u];
+      red[u] = Uu;
+      red[U + u] = ca[u] * Uu;
+    }
+    multi_reduce<2 * U>(red, lane);
+    {
+      const int idx = multi_index<2 * U>(lane);
+      const int i = i1 - (idx & (U - 1));
+      if (multi_writer<2 * U>(lane) && i >= 0) {
+        const int l = l0 + dl * i;
+        const int lvl = top ? l : l + 1;  // level at the top of layer i
+        if (idx < U) fup[lvl] += red[0]; else fdn[lvl] += red[0];
+      }
+    }
   }
   __syncwarp();
   float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1),

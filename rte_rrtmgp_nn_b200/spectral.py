@@ -34,7 +34,7 @@ def _planck_band_radiance(T, lo_cm, hi_cm, n=400):
 
 
 def make_kdist(band_lims_wvn, band_lims_gpt, totplnk=None, temp_ref_min=160.0, totplnk_delta=1.0,
-               solar_source=None, press_ref_min=1.0, press_ref_max=109663.3, temp_ref_max=355.0):
+               solar_source=None, press_ref_min=1.00518357, press_ref_max=109663.31, temp_ref_max=355.0):
     band_lims_gpt = np.ascontiguousarray(band_lims_gpt, np.int32)
     ngpt = int(band_lims_gpt[-1, 1])
     kd = dict(nbnd=len(band_lims_gpt), ngpt=ngpt, band_lims_wvn=np.asarray(band_lims_wvn, np.float32),

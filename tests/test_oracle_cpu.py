@@ -1,0 +1,235 @@
+"""CPU tests of the oracle (oracle/oracle.c): golden fixtures, analytic known answers, the reference's invariance
+ideas (tests/clear_sky_regression.F90: subsets, vertical reversal, block-size independence), fp64 cross-checks."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import oracle as O
+from rte_rrtmgp_nn_b200 import rfmip, spectral, synth
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    return dict(kd=spectral.synthetic_kdist_lw(256), ks=spectral.synthetic_kdist_sw(224), lw=H.oracle_nets(H.LW_G256),
+                sw=H.oracle_nets(H.SW_G224))
+
+
+def _lw(cfg, atm, fast=False, nang=1):
+    go = O.gas_optics_lw(cfg["kd"], cfg["lw"], atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"], fast=fast)
+    emis = np.repeat(atm["sfc_emis"][:, None], 16, 1)
+    up, dn = O.rte_lw(cfg["kd"], atm["top_at_1"], go["tau"], go["lay_source"], go["lev_source"], go["sfc_source"], emis, n_gauss_angles=nang, fast=fast)
+    return go, up, dn
+
+
+def _sw(cfg, atm, fast=False, tsi=None):
+    gs = O.gas_optics_sw(cfg["ks"], cfg["sw"], atm["play"], atm["plev"], atm["tlay"], atm["gases"], fast=fast)
+    toa = gs["toa_src"]
+    if tsi is not None:
+        d = np.float32(0)
+        for v in cfg["ks"]["solar_source"]:
+            d = np.float32(d + v)
+        toa = (toa * tsi[:, None] / d).astype(np.float32)
+    alb = np.repeat(atm["sfc_alb"][:, None], 224, 1)
+    return gs, O.rte_sw(atm["top_at_1"], atm["mu0"], toa, alb, alb, gs["tau"], gs["ssa"], gs["g"], fast=fast)
+
+
+@pytest.mark.parametrize("tag,maker", [("tiny", lambda: synth.make_atmosphere(4, 5, seed=1)), ("synth60", lambda: synth.make_atmosphere(6, 60, seed=2)),
+                                       ("rfmip", None)])
+def test_oracle_matches_golden(cfg, tag, maker):
+    gold = np.load(os.path.join(H.GOLDEN, "oracle_golden.npz"))
+    if tag == "rfmip":
+        atm = rfmip.load(columns=gold["rfmip_columns"]); tsi = atm["tsi"]
+    else:
+        atm = maker(); tsi = None
+    go, up, dn = _lw(cfg, atm)
+    gs, (su, sd, sr) = _sw(cfg, atm, tsi=tsi)
+    for name, got in (("lw_up", up), ("lw_dn", dn), ("sw_up", su), ("sw_dn", sd), ("sw_dir", sr)):
+        want = gold[f"{tag}_{name}"]
+        assert np.allclose(got, want, rtol=2e-6, atol=2e-4), (tag, name, np.abs(got - want).max())
+    assert np.allclose(go["tau"][:2, ::7, ::5], gold[f"{tag}_lw_tau_slice"], rtol=1e-5)
+    assert np.allclose(gs["ssa"][:2, ::7, ::5], gold[f"{tag}_sw_ssa_slice"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(go["tau"].sum(-1, dtype=np.float64), gold[f"{tag}_lw_tau_sum"], rtol=1e-5)
+
+
+def test_rfmip_fixture_is_the_reference_problem():
+    atm = rfmip.load()
+    assert atm["play"].shape == (1800, 60) and atm["plev"].shape == (1800, 61)
+    assert atm["top_at_1"] and abs(atm["play"][0, 0] - 10.0) < 1e-3       # p_lay(1) = 10 Pa
+    assert atm["plev"][0, 0] == pytest.approx(1.00518357, rel=1e-6)       # top level := press_min + eps
+    assert 180 < atm["tlay"].min() and atm["tlay"].max() < 313
+    assert 0 < atm["gases"]["h2o"].min() and atm["gases"]["h2o"].max() < 0.05
+    assert abs(atm["gases"]["co2"][0, 0] - 397.547e-6) < 1e-9              # experiment 1 = present day
+    assert (~atm["usecol"]).sum() > 0 and np.all(atm["mu0"][~atm["usecol"]] == 1.0)
+
+
+def test_mlp_against_float64_numpy(cfg):
+    """The oracle's fp32 MLP against an independent float64 numpy evaluation of the same weights."""
+    import nc4min
+    rng = np.random.default_rng(0)
+    for f in (H.LW_G256[0], H.LW_G256[1], H.SW_G224[1], H.LW_G128_BOTH[0]):
+        m = nc4min.load_nn_model(os.path.join(H.NN_DIR, f))
+        net = O.Net(m)
+        x = rng.uniform(0, 1, size=(50, m["dims"][0])).astype(np.float32)
+        a = x.astype(np.float64)
+        for l in range(3):
+            a = a @ m["W"][l].astype(np.float64) + m["b"][l].astype(np.float64)
+            if l < 2:
+                a = a / (np.abs(a) + 1)
+        raw = O.output_sgemm_lw(net, x)
+        assert np.abs(raw - a).max() <= 2e-5
+        raw64 = O.output_sgemm_lw(net, x, fast="f64")
+        assert np.abs(raw64 - a).max() <= 1e-12
+        pf = O.output_sgemm_pfrac(net, x)
+        assert np.allclose(pf, a * a, rtol=2e-4, atol=1e-6)
+
+
+def test_lw_isothermal_known_answer():
+    """Isothermal, black surface: upward radiance is B everywhere -> flux_up = pi * sum_g B_g at every level, and
+    flux_dn(l) = pi * sum_g B_g (1 - prod_{k above l} exp(-1.66 tau_k))."""
+    rng = np.random.default_rng(1)
+    C, L, G = 3, 11, 16
+    tau = rng.gamma(0.5, 1.0, size=(C, L, G)).astype(np.float32)
+    B = rng.uniform(0.5, 2.0, size=(C, 1, G)).astype(np.float32)
+    lay = np.broadcast_to(B, (C, L, G)).copy(); lev = np.broadcast_to(B, (C, L + 1, G)).copy()
+    emis = np.ones((C, G), np.float32); ssrc = B[:, 0].copy()
+    up, dn = O.lw_solver_noscat_GaussQuad(True, 1, tau, lay, lev, emis, ssrc)
+    want_up = np.pi * B[:, 0].sum(-1, dtype=np.float64)
+    assert np.allclose(up, want_up[:, None], rtol=2e-6)
+    trans = np.exp(-1.66 * np.cumsum(tau.astype(np.float64), axis=1))
+    want_dn = np.pi * (B.astype(np.float64) * (1 - trans)).sum(-1)
+    assert np.allclose(dn[:, 1:], want_dn, rtol=5e-6)
+    assert np.all(dn[:, 0] == 0)
+    # same physical column given bottom-up (flux arrays flip with it): isothermal -> the Q1 quirk is invisible
+    up2, dn2 = O.lw_solver_noscat_GaussQuad(False, 1, tau[:, ::-1].copy(), lay, lev, emis, ssrc)
+    assert np.allclose(up2[:, ::-1], up, rtol=1e-6) and np.allclose(dn2[:, ::-1], dn, rtol=2e-6, atol=1e-6)
+
+
+def test_sw_pure_absorption_known_answer():
+    """ssa = 0: direct beam = inc*mu0*exp(-sum tau/mu0); the surface reflects it diffusely and the PIFM two-stream
+    transmits diffuse light as exp(-2 tau) (gamma1 = k = 2, no reflection)."""
+    rng = np.random.default_rng(2)
+    C, L, G = 4, 9, 8
+    tau = rng.gamma(0.5, 0.4, size=(C, L, G)).astype(np.float32)
+    z = np.zeros_like(tau)
+    mu0 = rng.uniform(0.2, 1.0, size=C).astype(np.float32)
+    inc = rng.uniform(1, 5, size=(C, G)).astype(np.float32)
+    alb = rng.uniform(0.1, 0.8, size=(C, G)).astype(np.float32)
+    up, dn, dr = O.sw_solver_2stream(True, inc, np.zeros_like(inc), tau, z, z, mu0, alb, alb)
+    t64 = tau.astype(np.float64)
+    cum = np.concatenate([np.zeros((C, 1, G)), np.cumsum(t64, axis=1)], axis=1)
+    dir64 = inc[:, None] * mu0[:, None, None] * np.exp(-cum / mu0[:, None, None])
+    assert np.allclose(dr, dir64.sum(-1), rtol=5e-6)
+    assert np.allclose(dn, dr, rtol=1e-6)                      # no diffuse downward flux at all
+    below = cum[:, -1:, :] - cum                               # optical depth between a level and the surface
+    up64 = (dir64[:, -1:, :] * alb[:, None] * np.exp(-2.0 * below)).sum(-1)
+    assert np.allclose(up, up64, rtol=2e-5)
+
+
+def test_column_subset_and_block_size_independence(cfg):
+    """clear_sky_regression.F90's 'two half-subsets' idea: any split of the columns gives the same fluxes."""
+    atm = synth.make_atmosphere(10, 60, seed=4)
+    _, up, dn = _lw(cfg, atm)
+    _, (su, sd, sr) = _sw(cfg, atm)
+    for sl in (slice(0, 5), slice(5, 10), slice(3, 4)):
+        sub = {k: (v[sl] if isinstance(v, np.ndarray) else v) for k, v in atm.items()}
+        sub["gases"] = {k: (v[sl] if np.ndim(v) == 2 else v) for k, v in atm["gases"].items()}
+        _, u2, d2 = _lw(cfg, sub)
+        _, (a, b, c) = _sw(cfg, sub)
+        assert np.array_equal(u2, up[sl]) and np.array_equal(d2, dn[sl])
+        assert np.array_equal(a, su[sl]) and np.array_equal(b, sd[sl]) and np.array_equal(c, sr[sl])
+
+
+def test_vertical_reversal(cfg):
+    """'vertically reversed' invariance.  SW has no orientation quirk: bottom-up input gives the flipped fluxes.
+    LW reproduces the reference's lw_source_noscat, which ignores top_at_1 (quirk Q1): the flipped
+    problem differs (by ~10 W m-2 here: the level sources are swapped) -- assert the difference is there, so the quirk
+    stays restated; the CUDA path reproduces it by default and offers lw_source_bug_compat = 0 (tests/test_parity_gpu.py)."""
+    atm = synth.make_atmosphere(5, 60, seed=6)
+    flip = synth.flip_vertical(atm)
+    _, (su, sd, sr) = _sw(cfg, atm)
+    _, (fu, fd, fr) = _sw(cfg, flip)
+    assert np.allclose(fu[:, ::-1], su, rtol=3e-5, atol=2e-2) and np.allclose(fd[:, ::-1], sd, rtol=3e-5, atol=2e-2)
+    _, up, dn = _lw(cfg, atm)
+    _, up2, dn2 = _lw(cfg, flip)
+    d = max(np.abs(up2[:, ::-1] - up).max(), np.abs(dn2[:, ::-1] - dn).max())
+    assert 1e-3 < d < 50.0, d
+
+
+def test_three_angle_quadrature_close_to_one_angle(cfg):
+    atm = synth.make_atmosphere(4, 60, seed=7)
+    _, up1, dn1 = _lw(cfg, atm, nang=1)
+    _, up3, dn3 = _lw(cfg, atm, nang=3)
+    assert 0 < np.abs(up3 - up1).max() < 2.0 and np.abs(dn3 - dn1).max() < 2.0
+
+
+def test_fast_build_and_f64_build_agree_with_strict(cfg):
+    atm = synth.make_atmosphere(8, 60, seed=9)
+    _, up, dn = _lw(cfg, atm)
+    _, upf, dnf = _lw(cfg, atm, fast=True)
+    _, up64, dn64 = _lw(cfg, atm, fast="f64")
+    assert np.abs(upf - up).max() < 5e-3 and np.abs(up64 - up).max() < 5e-3 and np.abs(dn64 - dn).max() < 5e-3
+
+
+def test_zero_cloud_increment_is_clear_sky():
+    """'incrementing by zero-valued optical properties' (clear_sky_regression.F90)."""
+    rng = np.random.default_rng(3)
+    kd = spectral.synthetic_kdist_lw(256)
+    t1 = rng.gamma(0.5, 1.0, size=(3, 7, 256)).astype(np.float32)
+    w1 = rng.uniform(0, 1, size=t1.shape).astype(np.float32); g1 = rng.uniform(0, 0.9, size=t1.shape).astype(np.float32)
+    zb = np.zeros((3, 7, 16), np.float32)
+    assert np.array_equal(O.inc_1scalar_by_1scalar_bybnd(t1, zb, kd["band_lims_gpt"]), t1)
+    t, w, g = O.inc_2stream_by_2stream_bybnd(t1, w1, g1, zb, zb, zb, kd["band_lims_gpt"])
+    assert np.array_equal(t, t1) and np.allclose(w, w1, rtol=2e-7) and np.allclose(g, g1, rtol=3e-7)
+
+
+def test_cloud_optics_lut_and_delta_scale_properties():
+    from rte_rrtmgp_nn_b200.api import load_cloud_lut_file
+    args = load_cloud_lut_file(os.path.join(H.ROOT, "data", "cloud_optics", "rrtmgp-cloud-optics-coeffs-sw.nc"))
+    r = 1  # ice roughness 2 (examples/all-sky/rrtmgp_allsky.F90:219)
+    co = dict(extliq=args["lut_extliq"], ssaliq=args["lut_ssaliq"], asyliq=args["lut_asyliq"], extice=args["lut_extice"][r],
+              ssaice=args["lut_ssaice"][r], asyice=args["lut_asyice"][r], liq_nsteps=20, ice_nsteps=18, radliq_lwr=2.5, radice_lwr=10.0,
+              liq_step_size=(21.5 - 2.5) / 19, ice_step_size=(180.0 - 10.0) / 17)
+    atm = synth.make_atmosphere(6, 60, seed=5)
+    cl = synth.make_clouds(atm)
+    tau, ssa, g = O.cloud_optics_lut(co, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], True)
+    cloudy = cl["lwp"] > 0
+    assert np.all(tau[~cloudy] == 0) and np.all(tau[cloudy] > 0)
+    assert np.all((ssa >= 0) & (ssa <= 1)) and np.all((g >= 0) & (g < 1))
+    # node values of the table are reproduced exactly at a tabulated radius
+    re0 = np.full_like(cl["rel"], 2.5 + 3 * co["liq_step_size"])
+    t0 = O.cloud_optics_lut(co, np.where(cloudy, 10.0, 0).astype(np.float32), np.zeros_like(cl["iwp"]), re0, cl["rei"], False)
+    want = 10.0 * args["lut_extliq"][:, 3] * (1 - args["lut_ssaliq"][:, 3])
+    assert np.allclose(t0[cloudy][0], want, rtol=2e-4, atol=1e-6)
+    ts, ws, gs = O.delta_scale_2str(tau, ssa, g)
+    assert np.all(ts <= tau + 1e-6) and np.all(gs <= g + 1e-6)
+    # tau*(1-ssa) (absorption optical depth) is invariant under delta scaling
+    assert np.allclose(ts * (1 - ws), tau * (1 - ssa), rtol=3e-4, atol=1e-5)
+
+
+def test_heating_rates_formulas():
+    rng = np.random.default_rng(8)
+    up = rng.uniform(100, 400, size=(5, 21)).astype(np.float32); dn = rng.uniform(0, 400, size=(5, 21)).astype(np.float32)
+    plev = np.sort(rng.uniform(1, 1e5, size=(5, 21)).astype(np.float32), axis=1)
+    net = dn.astype(np.float64) - up.astype(np.float64)
+    want_day = -(86400 * 9.80665 / 1004.0) * np.diff(net, axis=1) / np.diff(plev.astype(np.float64), axis=1)
+    assert np.allclose(O.calc_heating_rate(up, dn, plev), want_day, rtol=1e-4, atol=1e-3)
+    want_s = -np.diff(net, axis=1) * 9.80665 / (1004.64 * np.diff(plev.astype(np.float64), axis=1))
+    assert np.allclose(O.heating_rate(up, dn, plev), want_s, rtol=1e-4, atol=1e-8)
+
+
+def test_gas_missing_and_profile_modes(cfg):
+    """compute_nn_inputs: scalar / per-layer / full concentrations; a missing minor gas counts as zero (:757-759)."""
+    atm = synth.make_atmosphere(3, 60, seed=10)
+    net = cfg["lw"][0]
+    g = dict(atm["gases"])
+    x0 = O.compute_nn_inputs(net, atm["play"], atm["tlay"], g)
+    g1 = dict(g); g1["co2"] = np.full(60, g["co2"], np.float32)
+    g2 = dict(g); g2["co2"] = np.full((3, 60), g["co2"], np.float32)
+    assert np.array_equal(O.compute_nn_inputs(net, atm["play"], atm["tlay"], g1), x0)
+    assert np.array_equal(O.compute_nn_inputs(net, atm["play"], atm["tlay"], g2), x0)
+    g3 = dict(g); del g3["cf4"]
+    x3 = O.compute_nn_inputs(net, atm["play"], atm["tlay"], g3)
+    i = net.input_names.index("cf4")
+    assert np.allclose(x3[..., i], (0.0 - net.xmin[i]) / (net.xmax[i] - net.xmin[i])) and np.array_equal(np.delete(x3, i, -1), np.delete(x0, i, -1))

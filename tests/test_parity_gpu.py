@@ -97,6 +97,31 @@ def test_lw_fluxes_match_oracle(gpu_ctx, files, ngpt, nlay, ncol, flip, nang):
     H.assert_within_reference_noise(hr[m], rhr[m], hr64[m], H.HR_TOL, "LW heating rate")
 
 
+def test_lw_physical_orientation_flag(gpu_ctx):
+    """lw_source_bug_compat = 0: a bottom-up column gives exactly the flipped fluxes of the same column top-down
+    (the reference's lw_source_noscat ignores top_at_1 -- quirk Q1 -- which the default reproduces)."""
+    from rte_rrtmgp_nn_b200 import api, synth
+    torch = _torch()
+    kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, H.LW_G256, 256, 9, 60, seed=12)
+    flip = synth.flip_vertical(atm)
+    emis = np.repeat(atm["sfc_emis"][:, None], 16, 1)
+    res = {}
+    try:
+        for compat in (1, 0):
+            gpu_ctx.set_flag("lw_source_bug_compat", compat)
+            for name, a in (("down", atm), ("up", flip)):
+                op, src = _run_lw_gas_optics(gpu_ctx, k_dist, dnets, a)
+                fl = api.ty_fluxes_broadband(torch.empty((9, 61), device="cuda"), torch.empty((9, 61), device="cuda"))
+                assert api.rte_lw(op, a["top_at_1"], src, emis, fl) == ""
+                res[(compat, name)] = (fl.flux_up.cpu().numpy(), fl.flux_dn.cpu().numpy())
+    finally:
+        gpu_ctx.set_flag("lw_source_bug_compat", 1)
+    u0, d0 = res[(0, "down")]; u1, d1 = res[(0, "up")]
+    assert np.abs(u1[:, ::-1] - u0).max() <= 2e-3 and np.abs(d1[:, ::-1] - d0).max() <= 2e-3
+    assert np.array_equal(res[(1, "down")][0], u0)                      # the flag only matters bottom-up
+    assert np.abs(res[(1, "up")][0][:, ::-1] - u0).max() > 1e-2         # and the default keeps the quirk
+
+
 def test_lw_solver_alone_random_inputs(gpu_ctx):
     """Solver on materialised oracle inputs: isolates K3 from the NN (tight tolerance)."""
     import oracle as O
