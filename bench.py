@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fast-math", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--solver-buffer", type=int, default=0, help="0 auto, 1 shared memory, 2 L2-resident global scratch")
+    ap.add_argument("--sw-fast-math", type=int, default=0)
     args = ap.parse_args()
     args.steps = max(1, args.steps)
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
@@ -219,6 +221,8 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
     ctx.set_flag("fast_math", args.fast_math)
+    ctx.set_flag("solver_buffer", args.solver_buffer)
+    ctx.set_flag("sw_fast_math", args.sw_fast_math)
     if args.chunk:
         ctx.set_chunk_columns(args.chunk)
     k_lw = api.ty_gas_optics_rrtmgp(ctx); k_lw.load(spectral.synthetic_kdist_lw(NGPT_LW))

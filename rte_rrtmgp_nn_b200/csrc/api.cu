@@ -274,6 +274,10 @@ extern "C" int rrnn_ctx_create(int device, void* stream, rrnn_ctx_t** out) {
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("rrnn_ctx_create: cannot create copy streams"); }
   for (auto& ev : c->ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  // defaults of the tuning flags can be overridden from the environment (used by the test matrix)
+  if (const char* e = getenv("RRNN_FAST_MATH")) c->fast_math = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("RRNN_SW_FAST_MATH")) c->sw_fast_math = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("RRNN_SOLVER_BUFFER")) c->solver_buffer = atoi(e);
   *out = c;
   return 0;
 }
@@ -283,6 +287,7 @@ extern "C" int rrnn_ctx_destroy(rrnn_ctx_t* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->ws) cudaFree(c->ws);
+  if (c->scratch) cudaFree(c->scratch);
   if (c->pinned) cudaFreeHost(c->pinned);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& v : c->prof_ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -336,6 +341,8 @@ extern "C" int rrnn_ctx_set_flag(rrnn_ctx_t* c, const char* name, int value) {
   const std::string s(name);
   if (s == "lw_source_bug_compat") c->lw_source_bug_compat = value ? 1 : 0;
   else if (s == "fast_math") c->fast_math = value ? 1 : 0;
+  else if (s == "sw_fast_math") c->sw_fast_math = value ? 1 : 0;
+  else if (s == "solver_buffer") c->solver_buffer = value;
   else if (s == "nn_tensor_cores") c->nn_tensor_cores = value ? 1 : 0;
   else return fail("rrnn_ctx_set_flag: unknown flag " + s);
   return 0;

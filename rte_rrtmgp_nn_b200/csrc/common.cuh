@@ -50,6 +50,10 @@ struct rrnn_ctx {
   // flags (rte/mo_rte_rrtmgp_config.F90:23-40 + this library's own)
   int lw_source_bug_compat = 1;
   int fast_math = 0;       // solver transcendental variant: 0 = IEEE-accurate libdevice, 1 = ex2/rcp/rsqrt approx
+  int sw_fast_math = 0;    // the same for the SW solver only
+  int solver_buffer = 0;   // reverse-sweep buffer: 0 auto, 1 shared memory, 2 L2-resident global scratch
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
   int nn_tensor_cores = 0; // MLP variant: 0 = fp32 FFMA, 1 = tcgen05 3xTF32
   int chunk_columns = 0;
   // persistent workspace for the whole-path drivers
@@ -180,28 +184,39 @@ __device__ __forceinline__ void exp_and_complement(float x, float& t, float& omt
   t = small ? 1.0f + em1 : e;
 }
 
+// Division / reciprocal / square root.  FAST = raw MUFU approximations (1-2 ulp, denormals flushed).
+// Otherwise: MUFU seed + one Newton-Raphson step in FMA arithmetic -- branch-free, within ~1 ulp of the IEEE result
+// (the IEEE-exact CUDA sequences carry slow-path branches that split the unrolled layer groups into small basic
+// blocks and stop the scheduler from interleaving independent layers).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 template <bool FAST>
 __device__ __forceinline__ float rcp(float x) {
-  if (FAST) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-  }
-  return 1.0f / x;
+  const float r = rcp_approx(x);
+  if (FAST) return r;
+  return fmaf(fmaf(-x, r, 1.0f), r, r);
 }
 template <bool FAST>
 __device__ __forceinline__ float fdiv(float a, float b) {
   if (FAST) return __fdividef(a, b);
-  return a / b;
+  const float r = rcp<false>(b);
+  const float q = a * r;
+  return fmaf(fmaf(-b, q, a), r, q);
 }
 template <bool FAST>
-__device__ __forceinline__ float fsqrt(float x) {
+__device__ __forceinline__ float fsqrt(float x) {  // x > 0
   if (FAST) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
   }
-  return sqrtf(x);
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  const float sq = x * y;
+  return fmaf(fmaf(-sq, sq, x), 0.5f * y, sq);
 }
 
 }  // namespace rrnn

@@ -65,8 +65,9 @@ struct LwParams {
   const float* lev_source;  // (ngpt,nlay+1,ncol)
   const float* sfc_emis;    // (ngpt,ncol)
   const float* sfc_source;  // (ngpt,ncol)
-  float* flux_up;           // (nlay+1,ncol), zero-initialised
+  float* flux_up;           // (nlay+1,ncol)
   float* flux_dn;
+  float* scratch;           // GBUF: nCTA * 2 * L * 32 floats
 };
 
 constexpr float kPi = 3.14159265358979323846f;
@@ -109,144 +110,220 @@ __device__ __forceinline__ bool multi_writer(int lane) {  // one lane per distin
   return (lane & ((32 / N) - 1)) == 0;
 }
 
-template <bool FAST, bool CLUSTER>
+// L2 cache policies: the optical-property arrays are read exactly once (evict first); the reverse-sweep buffer,
+// when it lives in global memory, is written and read back in LIFO order within microseconds (evict last: it should
+// never reach HBM).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float ld_once(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+// reverse-sweep buffer accessors: shared memory or (GBUF) L2-resident global scratch
+template <bool GBUF>
+__device__ __forceinline__ void buf_st2(float2* p, float2 v, uint64_t pol) {
+  if (GBUF) asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+  else *p = v;
+}
+template <bool GBUF>
+__device__ __forceinline__ float2 buf_ld2(const float2* p, uint64_t pol) {
+  if (GBUF) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
+  }
+  return *p;
+}
+template <bool GBUF>
+__device__ __forceinline__ void buf_st1(float* p, float v, uint64_t pol) {
+  if (GBUF) asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+  else *p = v;
+}
+template <bool GBUF>
+__device__ __forceinline__ float buf_ld1(const float* p, uint64_t pol) {
+  if (GBUF) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+  }
+  return *p;
+}
+
+// Work distribution.  CLUSTER: persistent clusters, cluster c handles columns c, c+nclusters, ...; the CTA's rank in
+// the cluster is its g-point chunk.  Otherwise one (column, chunk) item per warp, no loop.
+template <bool CLUSTER>
+struct ItemLoop {
+  int col, chunk, ncol, step;
+  __device__ ItemLoop(int ncol_, int nchunks) : ncol(ncol_) {
+    if (CLUSTER) {
+      cg::cluster_group cl = cg::this_cluster();
+      const int csize = cl.num_blocks();
+      col = blockIdx.x / csize;
+      chunk = cl.block_rank();
+      step = gridDim.x / csize;
+    } else {
+      const int wpb = blockDim.x >> 5;
+      const long long item = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+      col = (item < (long long)ncol_ * nchunks) ? (int)(item / nchunks) : ncol_;
+      chunk = (int)(item % nchunks);
+      step = ncol_;  // single pass
+    }
+  }
+  __device__ bool valid() const { return col < ncol; }
+  __device__ void next() { col += step; }
+};
+
+template <bool FAST, bool CLUSTER, bool GBUF>
 __global__ void __launch_bounds__(64) lw_solver_kernel(const LwParams p) {
   extern __shared__ float smem[];
   constexpr int U = kLwU;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;  // 1 when CLUSTER
-  const long long item = (long long)blockIdx.x * wpb + wib;
-  if (item >= (long long)p.ncol * p.nchunks) return;  // never true when CLUSTER (grid == ncol * nchunks)
-  const int col = (int)(item / p.nchunks);
-  const int chunk = (int)(item % p.nchunks);
-  const int g = chunk * 32 + lane;
-  const bool act = g < p.ngpt;
   const int G = p.ngpt, L = p.nlay;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t pol_buf = policy_evict_last();
 
-  // per-warp shared memory: [L][32] float2 (t, src_up), then flux partials [2][L+1]
-  const size_t per_warp = (size_t)L * 64 + 2 * (size_t)(L + 1);
+  // per-warp shared memory: [L][32] float2 (t, src_up) unless GBUF, then flux partials [2][L+1]
+  const int buf_floats = GBUF ? 0 : L * 64;
+  const int per_warp = buf_floats + 2 * (L + 1);
   float* wbase = smem + (size_t)wib * per_warp;
-  float2* buf = reinterpret_cast<float2*>(wbase);
-  float* fup = wbase + (size_t)L * 64;
+  float2* buf = GBUF ? reinterpret_cast<float2*>(p.scratch) + (size_t)blockIdx.x * L * 32 : reinterpret_cast<float2*>(wbase);
+  float* fup = wbase + buf_floats;
   float* fdn = fup + (L + 1);
-  for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
-  __syncwarp();
 
-  // inactive lanes (ngpt not a multiple of 32) read lane 0's g-point and contribute zero
-  const int gs = act ? g : chunk * 32;
-  const float* tau = p.tau + (size_t)col * L * G + gs;
-  const float* lay = p.lay_source + (size_t)col * L * G + gs;
-  const float* lev = p.lev_source + (size_t)col * (L + 1) * G + gs;
-  const size_t gc_off = (size_t)col * G + gs;
   const float tau_thresh = 3.4526698e-4f;  // sqrt(epsilon(1._sp)), mo_rte_solver_kernels.F90:754
-  const float emis = p.sfc_emis[gc_off];
-  const float ssrc = p.sfc_source[gc_off];
-  const float inc = p.inc_flux ? p.inc_flux[gc_off] : 0.0f;
-  const float live = act ? 1.0f : 0.0f;
-
   // Sweep order i = 0..L-1 runs from the top of the atmosphere down: layer l(i) = l0 + dl*i.  In sweep order
   // layer i is bounded by level rows ent(i) (towards the top) and ext(i) = ent(i+1) (towards the surface).
   const int top = p.top_at_1;
   const int l0 = top ? 0 : L - 1;
   const int dl = top ? 1 : -1;
+  const int sG = dl * G;  // element stride between consecutive layers in sweep order
   // lw_source_noscat (:770-773) takes source_dn from lev(l+1) and source_up from lev(l) whatever the orientation
   // (quirk Q1).  In sweep terms: top_at_1 -> dn uses ext, up uses ent (physical).  Otherwise the reference uses
   // dn <- lev(l+1) = ent, up <- lev(l) = ext; the physical choice is again dn <- ext, up <- ent.
   const bool dn_uses_ext = top || !p.bug_compat;
 
-  for (int imu = 0; imu < p.nmus; ++imu) {
-    const float D = p.Ds[imu];
-    const float fac = 2.0f * kPi * p.wts[imu] * live;
-    float I = inc / (2.0f * kPi * p.wts[imu]);  // radn_dn(top) = inc_flux/(2 pi w), :196-201
-    {
-      const float s = warp_sum(fac * I);
-      if (lane == 0) fdn[top ? 0 : L] += s;
-    }
-    // ---------------- downward sweep, software pipelined in groups of U layers ----------------
-    float n_tau[U], n_lay[U], n_ext[U];
-    float carry = ld_stream(lev + (size_t)(top ? 0 : L) * G);  // ent(0)
-    auto load_group = [&](int i0) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = min(i0 + u, L - 1);
-        const int l = l0 + dl * i;
-        n_tau[u] = ld_stream(tau + (size_t)l * G);
-        n_lay[u] = ld_stream(lay + (size_t)l * G);
-        n_ext[u] = ld_stream(lev + (size_t)(top ? l + 1 : l) * G);
+  for (ItemLoop<CLUSTER> it(p.ncol, p.nchunks); it.valid(); it.next()) {
+    const int col = it.col, chunk = it.chunk;
+    const int g = chunk * 32 + lane;
+    const bool act = g < G;
+    for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
+    __syncwarp();
+    // inactive lanes (ngpt not a multiple of 32) shadow the chunk's first g-point and contribute zero
+    const int gs = act ? g : chunk * 32;
+    const float* tau = p.tau + (size_t)col * L * G + (size_t)l0 * G + gs;          // layer i at tau[i*sG]
+    const float* lay = p.lay_source + (size_t)col * L * G + (size_t)l0 * G + gs;
+    const float* lev = p.lev_source + (size_t)col * (L + 1) * G + gs;
+    const float* lext = lev + (size_t)(top ? 1 : L - 1) * G;                       // ext(i) at lext[i*sG]
+    const size_t gc_off = (size_t)col * G + gs;
+    const float emis = p.sfc_emis[gc_off];
+    const float ssrc = p.sfc_source[gc_off];
+    const float inc = p.inc_flux ? p.inc_flux[gc_off] : 0.0f;
+    const float live = act ? 1.0f : 0.0f;
+
+    for (int imu = 0; imu < p.nmus; ++imu) {
+      const float D = p.Ds[imu];
+      const float fac = 2.0f * kPi * p.wts[imu] * live;
+      float I = inc / (2.0f * kPi * p.wts[imu]);  // radn_dn(top) = inc_flux/(2 pi w), :196-201
+      {
+        const float s = warp_sum(fac * I);
+        if (lane == 0) fdn[top ? 0 : L] += s;
       }
-    };
-    load_group(0);
-    for (int i0 = 0; i0 < L; i0 += U) {
-      float c_tau[U], c_lay[U], c_ext[U];
+      // ---------------- downward sweep, software pipelined in groups of U layers ----------------
+      float n_tau[U], n_lay[U], n_ext[U];
+      float carry = ld_once(lev + (size_t)(top ? 0 : L) * G, pol_in);  // ent(0)
+      auto load_group = [&](int i0) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) { c_tau[u] = n_tau[u]; c_lay[u] = n_lay[u]; c_ext[u] = n_ext[u]; }
-      if (i0 + U < L) load_group(i0 + U);
-      float tv[U], sdn[U], sup[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float ent = (u == 0) ? carry : c_ext[u - 1];
-        const float ext = c_ext[u];
-        const float tl = c_tau[u] * D;
-        float t, omt;
-        if (FAST) { t = __expf(-tl); omt = 1.0f - t; }
-        else exp_and_complement(tl, t, omt);
-        float fact;
-        if (tl > tau_thresh) fact = fdiv<FAST>(omt, tl) - t;
-        else fact = tl * (0.5f - (1.0f / 3.0f) * tl);
-        const float lev_dn = dn_uses_ext ? ext : ent;
-        const float lev_up = dn_uses_ext ? ent : ext;
-        tv[u] = t;
-        sdn[u] = omt * lev_dn + 2.0f * fact * (c_lay[u] - lev_dn);
-        sup[u] = omt * lev_up + 2.0f * fact * (c_lay[u] - lev_up);
-      }
-      carry = c_ext[U - 1];
-      float red[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u;
-        if (i < L) {  // warp-uniform; the ragged tail of the last group is computed on clamped loads and dropped
-          I = tv[u] * I + sdn[u];
-          buf[(size_t)(l0 + dl * i) * 32 + lane] = make_float2(tv[u], sup[u]);
+        for (int u = 0; u < U; ++u) {
+          const int o = min(i0 + u, L - 1) * sG;
+          n_tau[u] = ld_once(tau + o, pol_in);
+          n_lay[u] = ld_once(lay + o, pol_in);
+          n_ext[u] = ld_once(lext + o, pol_in);
         }
-        red[u] = fac * I;
-      }
-      multi_reduce<U>(red, lane);
-      const int i = i0 + multi_index<U>(lane);
-      if (multi_writer<U>(lane) && i < L) fdn[top ? (l0 + dl * i) + 1 : (l0 + dl * i)] += red[0];
-    }
-    // ---------------- surface ----------------
-    float U0 = I;
-    U0 = U0 * (1.0f - emis) + emis * ssrc;  // :269
-    {
-      const float s = warp_sum(fac * U0);
-      if (lane == 0) fup[top ? L : 0] += s;
-    }
-    __syncwarp();
-    // ---------------- upward sweep (reverse order) from the on-chip buffer ----------------
-    float Uu = U0;
-    for (int i1 = L - 1; i1 >= 0; i1 -= U) {
-      float2 b[U];
+      };
+      load_group(0);
+      for (int i0 = 0; i0 < L; i0 += U) {
+        float c_tau[U], c_lay[U], c_ext[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = max(i1 - u, 0);
-        b[u] = buf[(size_t)(l0 + dl * i) * 32 + lane];
-      }
-      float red[U];
+        for (int u = 0; u < U; ++u) { c_tau[u] = n_tau[u]; c_lay[u] = n_lay[u]; c_ext[u] = n_ext[u]; }
+        if (i0 + U < L) load_group(i0 + U);
+        float tv[U], sdn[U], sup[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (i1 - u >= 0) Uu = b[u].x * Uu + b[u].y;
-        red[u] = fac * Uu;
+        for (int u = 0; u < U; ++u) {
+          const float ent = (u == 0) ? carry : c_ext[u - 1];
+          const float ext = c_ext[u];
+          const float tl = c_tau[u] * D;
+          float t, omt;
+          if (FAST) { t = __expf(-tl); omt = 1.0f - t; }
+          else exp_and_complement(tl, t, omt);
+          float fact;
+          if (tl > tau_thresh) fact = __fdividef(omt, tl) - t;
+          else fact = tl * (0.5f - (1.0f / 3.0f) * tl);
+          const float lev_dn = dn_uses_ext ? ext : ent;
+          const float lev_up = dn_uses_ext ? ent : ext;
+          tv[u] = t;
+          sdn[u] = omt * lev_dn + 2.0f * fact * (c_lay[u] - lev_dn);
+          sup[u] = omt * lev_up + 2.0f * fact * (c_lay[u] - lev_up);
+        }
+        carry = c_ext[U - 1];
+        float red[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u;
+          if (i < L) {  // warp-uniform; the ragged tail of the last group is computed on clamped loads and dropped
+            I = tv[u] * I + sdn[u];
+            buf_st2<GBUF>(buf + i * 32 + lane, make_float2(tv[u], sup[u]), pol_buf);
+          }
+          red[u] = fac * I;
+        }
+        multi_reduce<U>(red, lane);
+        const int i = i0 + multi_index<U>(lane);
+        if (multi_writer<U>(lane) && i < L) fdn[top ? i + 1 : L - 1 - i] += red[0];
       }
-      multi_reduce<U>(red, lane);
-      const int i = i1 - multi_index<U>(lane);
-      if (multi_writer<U>(lane) && i >= 0) fup[top ? (l0 + dl * i) : (l0 + dl * i) + 1] += red[0];
+      // ---------------- surface ----------------
+      float Uu = I * (1.0f - emis) + emis * ssrc;  // :269
+      {
+        const float s = warp_sum(fac * Uu);
+        if (lane == 0) fup[top ? L : 0] += s;
+      }
+      __syncwarp();
+      // ---------------- upward sweep (reverse order) from the buffer, software pipelined ----------------
+      float2 nb[U];
+      auto load_back = [&](int i1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) nb[u] = buf_ld2<GBUF>(buf + max(i1 - u, 0) * 32 + lane, pol_buf);
+      };
+      load_back(L - 1);
+      for (int i1 = L - 1; i1 >= 0; i1 -= U) {
+        float2 b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) b[u] = nb[u];
+        if (i1 - U >= 0) load_back(i1 - U);
+        float red[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (i1 - u >= 0) Uu = b[u].x * Uu + b[u].y;
+          red[u] = fac * Uu;
+        }
+        multi_reduce<U>(red, lane);
+        const int i = i1 - multi_index<U>(lane);
+        if (multi_writer<U>(lane) && i >= 0) fup[top ? i : L - i] += red[0];
+      }
+      __syncwarp();
     }
-    __syncwarp();
+    // combine the g-chunks of this column
+    float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
+    combine_chunks<CLUSTER, 2>(fup, L, lane, gout);
   }
-  // combine the g-chunks of this column
-  float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
-  combine_chunks<CLUSTER, 2>(fup, L, lane, gout);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -263,187 +340,192 @@ struct SwParams {
   float* flux_up;
   float* flux_dn;
   float* flux_dir;
+  float* scratch;  // GBUF: nCTA * 3 * L * 32 floats
 };
 
-template <bool FAST, bool HAS_G, bool CLUSTER>
+template <bool FAST, bool HAS_G, bool CLUSTER, bool GBUF>
 __global__ void __launch_bounds__(64) sw_solver_kernel(const SwParams p) {
   extern __shared__ float smem[];
   constexpr int U = kSwU;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  const long long item = (long long)blockIdx.x * wpb + wib;
-  if (item >= (long long)p.ncol * p.nchunks) return;
-  const int col = (int)(item / p.nchunks);
-  const int chunk = (int)(item % p.nchunks);
-  const int gp = chunk * 32 + lane;
-  const bool act = gp < p.ngpt;
   const int G = p.ngpt, L = p.nlay;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t pol_buf = policy_evict_last();
 
-  // per-warp shared memory: e[L][32], f[L][32], alpha_below[L][32], then flux partials [3][L+1]
-  const size_t per_warp = (size_t)L * 96 + 3 * (size_t)(L + 1);
+  // per-warp: e[L][32], f[L][32], alpha_below[L][32] (shared memory unless GBUF), then flux partials [3][L+1]
+  const int buf_floats = GBUF ? 0 : L * 96;
+  const int per_warp = buf_floats + 3 * (L + 1);
   float* wbase = smem + (size_t)wib * per_warp;
-  float* be = wbase;
-  float* bf = be + (size_t)L * 32;
-  float* ba = bf + (size_t)L * 32;
-  float* fup = ba + (size_t)L * 32;
+  float* be = GBUF ? p.scratch + (size_t)blockIdx.x * L * 96 : wbase;
+  float* bf = be + L * 32;
+  float* ba = bf + L * 32;
+  float* fup = wbase + buf_floats;
   float* fdn = fup + (L + 1);
   float* fdr = fdn + (L + 1);
-  for (int i = lane; i < 3 * (L + 1); i += 32) fup[i] = 0.0f;
-  __syncwarp();
 
-  const int gs = act ? gp : chunk * 32;  // inactive lanes shadow lane 0 and contribute zero
-  const float live = act ? 1.0f : 0.0f;
-  const float* tau = p.tau + (size_t)col * L * G + gs;
-  const float* ssa = p.ssa + (size_t)col * L * G + gs;
-  const float* gas = HAS_G ? p.g + (size_t)col * L * G + gs : nullptr;
-  const size_t gc_off = (size_t)col * G + gs;
-  const float mu0 = p.mu0[col];
-  const float mu0_inv = 1.0f / mu0;
   const float k_min = 1.e-4f;       // mo_rte_solver_kernels.F90:76-82 (single precision)
   const float eps = 1.1920929e-7f;  // epsilon(1._sp)
-
   const int top = p.top_at_1;
   const int l0 = top ? 0 : L - 1;
-  const int dl = top ? 1 : -1;
+  const int sG = (top ? 1 : -1) * G;
   const int top_level = top ? 0 : L;
 
-  float dir = live * p.inc_flux[gc_off] * mu0;                         // :589
-  float beta = p.inc_flux_dif ? live * p.inc_flux_dif[gc_off] : 0.0f;  // :590
-  float alpha = 0.0f;
-  {
-    const float sd = warp_sum(dir), sb = warp_sum(beta + dir);
-    if (lane == 0) { fdr[top_level] += sd; fdn[top_level] += sb; }
-  }
-  // ---------------- sweep 1: top -> surface, software pipelined in groups of U layers ----------------
-  float n_t[U], n_w[U], n_g[U];
-  auto load_group = [&](int i0) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int l = l0 + dl * min(i0 + u, L - 1);
-      n_t[u] = ld_stream(tau + (size_t)l * G);
-      n_w[u] = ld_stream(ssa + (size_t)l * G);
-      n_g[u] = HAS_G ? ld_stream(gas + (size_t)l * G) : 0.0f;
-    }
-  };
-  load_group(0);
-  for (int i0 = 0; i0 < L; i0 += U) {
-    float c_t[U], c_w[U], c_g[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) { c_t[u] = n_t[u]; c_w[u] = n_w[u]; c_g[u] = n_g[u]; }
-    if (i0 + U < L) load_group(i0 + U);
-    // layer coefficients: independent across the U layers (instruction-level parallelism)
-    float Rdif[U], Tdif[U], Rdir[U], Tdir[U], Tnos[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float tauv = c_t[u], w0 = c_w[u], gg = c_g[u];
-      // ---- sw_two_stream_source :1405-1475 ----
-      const float Tnoscat = exp_neg<FAST>(-tauv * mu0_inv);
-      const float gamma1 = (8.0f - w0 * (5.0f + 3.0f * gg)) * 0.25f;
-      const float gamma2 = 3.0f * (w0 * (1.0f - gg)) * 0.25f;
-      const float gamma3 = (2.0f - 3.0f * mu0 * gg) * 0.25f;
-      const float gamma4 = 1.0f - gamma3;
-      const float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
-      const float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
-      const float k = fsqrt<FAST>(fmaxf((gamma1 - gamma2) * (gamma1 + gamma2), k_min));
-      const float ekt = exp_neg<FAST>(-tauv * k);
-      const float e2kt = ekt * ekt;
-      const float k2e = 2.0f * k * ekt;
-      float RT = rcp<FAST>(k * (1.0f + e2kt) + gamma1 * (1.0f - e2kt));
-      Rdif[u] = RT * gamma2 * (1.0f - e2kt);
-      Tdif[u] = RT * 2.0f * k * ekt;
-      const float k_mu = k * mu0;
-      const float k_mu2 = k_mu * k_mu;
-      const float k_gamma3 = k * gamma3;
-      const float k_gamma4 = k * gamma4;
-      const float om = 1.0f - k_mu2;
-      const float dd = (fabsf(om) >= eps) ? om : eps;
-      RT = fdiv<FAST>(w0 * RT, dd);
-      float rd = RT * ((1.0f - k_mu) * (alpha2 + k_gamma3) - (1.0f + k_mu) * (alpha2 - k_gamma3) * e2kt -
-                       k2e * (gamma3 - alpha2 * mu0) * Tnoscat);
-      float td = RT * (k2e * (gamma4 + alpha1 * mu0) -
-                       Tnoscat * ((1.0f + k_mu) * (alpha1 + k_gamma4) - (1.0f - k_mu) * (alpha1 - k_gamma4) * e2kt));
-      rd = fmaxf(0.0f, fminf(rd, 1.0f - Tnoscat));
-      td = fmaxf(0.0f, fminf(td, 1.0f - Tnoscat - rd));
-      Rdir[u] = rd; Tdir[u] = td; Tnos[u] = Tnoscat;
-    }
-    // the sequential part: direct beam and the adding recurrences, eliminated from the top
-    float red[2 * U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u;
-      if (i < L) {  // warp-uniform
-        const int l = l0 + dl * i;
-        const float s_up = Rdir[u] * dir;
-        const float s_dn = Tdir[u] * dir;
-        dir = Tnos[u] * dir;
-        const float d = rcp<FAST>(1.0f - Rdif[u] * alpha);
-        const float e = d * Tdif[u];
-        const float f = d * (Rdif[u] * beta + s_up);
-        beta = s_dn + e * (beta + alpha * s_up);
-        alpha = Rdif[u] + Tdif[u] * e * alpha;
-        be[(size_t)l * 32 + lane] = e;
-        bf[(size_t)l * 32 + lane] = f;
-        ba[(size_t)l * 32 + lane] = alpha;  // reflectance seen from the level BELOW layer l
-      }
-      red[u] = dir;
-      red[U + u] = beta + dir;
-    }
-    multi_reduce<2 * U>(red, lane);
+  for (ItemLoop<CLUSTER> it(p.ncol, p.nchunks); it.valid(); it.next()) {
+    const int col = it.col, chunk = it.chunk;
+    const int gp = chunk * 32 + lane;
+    const bool act = gp < G;
+    for (int i = lane; i < 3 * (L + 1); i += 32) fup[i] = 0.0f;
+    __syncwarp();
+    const int gs = act ? gp : chunk * 32;  // inactive lanes shadow the chunk's first g-point and contribute zero
+    const float live = act ? 1.0f : 0.0f;
+    const float* tau = p.tau + (size_t)col * L * G + (size_t)l0 * G + gs;  // layer i (sweep order) at [i*sG]
+    const float* ssa = p.ssa + (size_t)col * L * G + (size_t)l0 * G + gs;
+    const float* gas = HAS_G ? p.g + (size_t)col * L * G + (size_t)l0 * G + gs : nullptr;
+    const size_t gc_off = (size_t)col * G + gs;
+    const float mu0 = p.mu0[col];
+    const float mu0_inv = 1.0f / mu0;
+
+    float dir = live * p.inc_flux[gc_off] * mu0;                         // :589
+    float beta = p.inc_flux_dif ? live * p.inc_flux_dif[gc_off] : 0.0f;  // :590
+    float alpha = 0.0f;
     {
-      const int idx = multi_index<2 * U>(lane);
-      const int i = i0 + (idx & (U - 1));
-      if (multi_writer<2 * U>(lane) && i < L) {
-        const int l = l0 + dl * i;
-        const int lvl = top ? l + 1 : l;
-        if (idx < U) fdr[lvl] += red[0]; else fdn[lvl] += red[0];
+      const float sd = warp_sum(dir), sb = warp_sum(beta + dir);
+      if (lane == 0) { fdr[top_level] += sd; fdn[top_level] += sb; }
+    }
+    // ---------------- sweep 1: top -> surface, software pipelined in groups of U layers ----------------
+    float n_t[U], n_w[U], n_g[U];
+    auto load_group = [&](int i0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int o = min(i0 + u, L - 1) * sG;
+        n_t[u] = ld_once(tau + o, pol_in);
+        n_w[u] = ld_once(ssa + o, pol_in);
+        n_g[u] = HAS_G ? ld_once(gas + o, pol_in) : 0.0f;
+      }
+    };
+    load_group(0);
+    for (int i0 = 0; i0 < L; i0 += U) {
+      float c_t[U], c_w[U], c_g[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { c_t[u] = n_t[u]; c_w[u] = n_w[u]; c_g[u] = n_g[u]; }
+      if (i0 + U < L) load_group(i0 + U);
+      // layer coefficients: independent across the U layers (instruction-level parallelism)
+      float Rdif[U], Tdif[U], Rdir[U], Tdir[U], Tnos[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float tauv = c_t[u], w0 = c_w[u], gg = c_g[u];
+        // ---- sw_two_stream_source :1405-1475 ----
+        const float Tnoscat = exp_neg<FAST>(-tauv * mu0_inv);
+        const float gamma1 = (8.0f - w0 * (5.0f + 3.0f * gg)) * 0.25f;
+        const float gamma2 = 3.0f * (w0 * (1.0f - gg)) * 0.25f;
+        const float gamma3 = (2.0f - 3.0f * mu0 * gg) * 0.25f;
+        const float gamma4 = 1.0f - gamma3;
+        const float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
+        const float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
+        const float k = fsqrt<FAST>(fmaxf((gamma1 - gamma2) * (gamma1 + gamma2), k_min));
+        const float ekt = exp_neg<FAST>(-tauv * k);
+        const float e2kt = ekt * ekt;
+        const float k2e = 2.0f * k * ekt;
+        float RT = rcp<FAST>(k * (1.0f + e2kt) + gamma1 * (1.0f - e2kt));
+        Rdif[u] = RT * gamma2 * (1.0f - e2kt);
+        Tdif[u] = RT * 2.0f * k * ekt;
+        const float k_mu = k * mu0;
+        const float k_mu2 = k_mu * k_mu;
+        const float k_gamma3 = k * gamma3;
+        const float k_gamma4 = k * gamma4;
+        const float om = 1.0f - k_mu2;
+        const float dd = (fabsf(om) >= eps) ? om : eps;
+        RT = fdiv<FAST>(w0 * RT, dd);
+        float rd = RT * ((1.0f - k_mu) * (alpha2 + k_gamma3) - (1.0f + k_mu) * (alpha2 - k_gamma3) * e2kt -
+                         k2e * (gamma3 - alpha2 * mu0) * Tnoscat);
+        float td = RT * (k2e * (gamma4 + alpha1 * mu0) -
+                         Tnoscat * ((1.0f + k_mu) * (alpha1 + k_gamma4) - (1.0f - k_mu) * (alpha1 - k_gamma4) * e2kt));
+        rd = fmaxf(0.0f, fminf(rd, 1.0f - Tnoscat));
+        td = fmaxf(0.0f, fminf(td, 1.0f - Tnoscat - rd));
+        Rdir[u] = rd; Tdir[u] = td; Tnos[u] = Tnoscat;
+      }
+      // the sequential part: direct beam and the adding recurrences, eliminated from the top
+      float red[2 * U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u;
+        if (i < L) {  // warp-uniform
+          const float s_up = Rdir[u] * dir;
+          const float s_dn = Tdir[u] * dir;
+          dir = Tnos[u] * dir;
+          const float d = rcp<FAST>(1.0f - Rdif[u] * alpha);
+          const float e = d * Tdif[u];
+          const float f = d * (Rdif[u] * beta + s_up);
+          beta = s_dn + e * (beta + alpha * s_up);
+          alpha = Rdif[u] + Tdif[u] * e * alpha;
+          buf_st1<GBUF>(be + i * 32 + lane, e, pol_buf);
+          buf_st1<GBUF>(bf + i * 32 + lane, f, pol_buf);
+          buf_st1<GBUF>(ba + i * 32 + lane, alpha, pol_buf);  // reflectance seen from the level BELOW layer i
+        }
+        red[u] = dir;
+        red[U + u] = beta + dir;
+      }
+      multi_reduce<2 * U>(red, lane);
+      {
+        const int idx = multi_index<2 * U>(lane);
+        const int i = i0 + (idx & (U - 1));
+        if (multi_writer<2 * U>(lane) && i < L) {
+          const int lvl = top ? i + 1 : L - 1 - i;
+          if (idx < U) fdr[lvl] += red[0]; else fdn[lvl] += red[0];
+        }
       }
     }
-  }
-  // ---------------- surface ----------------
-  const float a_s = p.alb_dif[gc_off];
-  const float S_s = dir * p.alb_dir[gc_off];  // source_sfc :1477
-  float Uu = fdiv<FAST>(a_s * beta + S_s, 1.0f - a_s * alpha) * live;
-  {
-    const int sfc = top ? L : 0;
-    const float su = warp_sum(Uu), sa = warp_sum(alpha * Uu);
-    if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
-  }
-  __syncwarp();
-  // ---------------- sweep 2: surface -> top (back substitution) ----------------
-  for (int i1 = L - 1; i1 >= 0; i1 -= U) {
-    float ce[U], cf[U], ca[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = max(i1 - u, 0);
-      const int l = l0 + dl * i;
-      ce[u] = be[(size_t)l * 32 + lane];
-      cf[u] = bf[(size_t)l * 32 + lane];
-      // reflectance of the atmosphere above the level at the top of layer i (0 at the top of the domain)
-      ca[u] = (i > 0) ? ba[(size_t)(l - dl) * 32 + lane] : 0.0f;
-    }
-    float red[2 * U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i1 - u >= 0) Uu = ce[u] * Uu + cf[u];
-      red[u] = Uu;
-      red[U + u] = ca[u] * Uu;
-    }
-    multi_reduce<2 * U>(red, lane);
+    // ---------------- surface ----------------
+    const float a_s = p.alb_dif[gc_off];
+    const float S_s = dir * p.alb_dir[gc_off];  // source_sfc :1477
+    float Uu = fdiv<FAST>(a_s * beta + S_s, 1.0f - a_s * alpha) * live;
     {
-      const int idx = multi_index<2 * U>(lane);
-      const int i = i1 - (idx & (U - 1));
-      if (multi_writer<2 * U>(lane) && i >= 0) {
-        const int l = l0 + dl * i;
-        const int lvl = top ? l : l + 1;  // level at the top of layer i
-        if (idx < U) fup[lvl] += red[0]; else fdn[lvl] += red[0];
+      const int sfc = top ? L : 0;
+      const float su = warp_sum(Uu), sa = warp_sum(alpha * Uu);
+      if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
+    }
+    __syncwarp();
+    // ---------------- sweep 2: surface -> top (back substitution), software pipelined ----------------
+    float ne[U], nf[U], na[U];
+    auto load_back = [&](int i1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = max(i1 - u, 0);
+        ne[u] = buf_ld1<GBUF>(be + i * 32 + lane, pol_buf);
+        nf[u] = buf_ld1<GBUF>(bf + i * 32 + lane, pol_buf);
+        // reflectance of the atmosphere above the level at the top of layer i (0 at the top of the domain)
+        na[u] = (i > 0) ? buf_ld1<GBUF>(ba + (i - 1) * 32 + lane, pol_buf) : 0.0f;
+      }
+    };
+    load_back(L - 1);
+    for (int i1 = L - 1; i1 >= 0; i1 -= U) {
+      float ce[U], cf[U], ca[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { ce[u] = ne[u]; cf[u] = nf[u]; ca[u] = na[u]; }
+      if (i1 - U >= 0) load_back(i1 - U);
+      float red[2 * U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i1 - u >= 0) Uu = ce[u] * Uu + cf[u];
+        red[u] = Uu;
+        red[U + u] = ca[u] * Uu;
+      }
+      multi_reduce<2 * U>(red, lane);
+      {
+        const int idx = multi_index<2 * U>(lane);
+        const int i = i1 - (idx & (U - 1));
+        if (multi_writer<2 * U>(lane) && i >= 0) {
+          const int lvl = top ? i : L - i;  // level at the top of layer i
+          if (idx < U) fup[lvl] += red[0]; else fdn[lvl] += red[0];
+        }
       }
     }
+    __syncwarp();
+    float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1),
+                            p.flux_dir + (size_t)col * (L + 1)};
+    combine_chunks<CLUSTER, 3>(fup, L, lane, gout);
   }
-  __syncwarp();
-  float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1),
-                          p.flux_dir + (size_t)col * (L + 1)};
-  combine_chunks<CLUSTER, 3>(fup, L, lane, gout);
 }
 
 // expand (rte/mo_rte_lw.F90:429-447): band -> g-point
@@ -465,25 +547,49 @@ static int pick_warps_per_block(size_t per_warp_bytes) {
   return (2 * per_warp_bytes <= 200 * 1024) ? 2 : 1;
 }
 
-// Launch `kernel` with one 32-thread CTA per (column, chunk) and the chunks of a column forming one cluster.
+static int ensure_scratch(rrnn_ctx_t* ctx, size_t bytes) {
+  if (ctx->scratch_bytes >= bytes) return 0;
+  if (ctx->scratch) { RRNN_CUDA(cudaStreamSynchronize(ctx->stream)); RRNN_CUDA(cudaFree(ctx->scratch)); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
+  RRNN_CUDA(cudaMalloc(&ctx->scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return 0;
+}
+
+// Persistent clustered launch: one 32-thread CTA per g-point chunk, the chunks of a column form one cluster, and as
+// many clusters as can be co-resident loop over the columns.  Returns the grid size through ncta_out.
 template <typename P>
-static cudaError_t launch_clustered(void (*kernel)(const P), const P& p, long long ncta, int cluster, size_t smem,
-                                    cudaStream_t stream) {
+static cudaError_t cluster_config(void (*kernel)(const P), int cluster, size_t smem, int ncol, cudaStream_t stream,
+                                  cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int& ncta_out) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)ncta);
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3((unsigned)cluster);
   cfg.blockDim = dim3(32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, p);
+  int nclusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg);
+  if (e != cudaSuccess) return e;
+  if (nclusters < 1) nclusters = 1;
+  if (nclusters > ncol) nclusters = ncol;
+  ncta_out = nclusters * cluster;
+  cfg.gridDim = dim3((unsigned)ncta_out);
+  return cudaSuccess;
+}
+
+// Where does the reverse-sweep buffer live?  Shared memory when enough warps fit per SM to hide latency, otherwise
+// an L2-resident global scratch ring (ctx flag solver_buffer: 0 auto, 1 shared memory, 2 global).
+static bool use_global_buffer(const rrnn_ctx_t* ctx, size_t smem_per_warp) {
+  if (ctx->solver_buffer == 1) return false;
+  if (ctx->solver_buffer == 2) return true;
+  const size_t warps_by_smem = (size_t)220 * 1024 / smem_per_warp;
+  return warps_by_smem < 12;
 }
 
 extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* Ds,
@@ -502,29 +608,39 @@ extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int nc
   for (int i = 0; i < nmus; ++i) { p.Ds[i] = Ds[i]; p.wts[i] = weights[i]; }
   p.inc_flux = inc_flux_d; p.tau = tau_d; p.lay_source = lay_source_d; p.lev_source = lev_source_d;
   p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
-  const size_t per_warp = ((size_t)nlay * 64 + 2 * (size_t)(nlay + 1)) * sizeof(float);
-  RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_lw_solver_noscat: nlay too large for the on-chip layer buffer");
+  const size_t part = 2 * (size_t)(nlay + 1) * sizeof(float);
+  const size_t bufb = (size_t)nlay * 64 * sizeof(float);
   const bool clustered = p.nchunks <= 8;
-  const int wpb = clustered ? 1 : pick_warps_per_block(per_warp);
-  const size_t smem = per_warp * wpb;
-  const long long items = (long long)ncol * p.nchunks;
-  const long long blocks = (items + wpb - 1) / wpb;
-  RRNN_CHECK(blocks < 2147483647LL, "rrnn_lw_solver_noscat: too many columns for one launch");
-  const size_t nflux = (size_t)ncol * (nlay + 1) * sizeof(float);
-  if (!clustered) {
-    RRNN_CUDA(cudaMemsetAsync(flux_up_d, 0, nflux, ctx->stream));
-    RRNN_CUDA(cudaMemsetAsync(flux_dn_d, 0, nflux, ctx->stream));
-  }
+  const bool gbuf = clustered && use_global_buffer(ctx, bufb + part);
+  const size_t per_warp = part + (gbuf ? 0 : bufb);
+  RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_lw_solver_noscat: nlay too large for the on-chip layer buffer");
   const int ps = prof_begin(ctx, K_LW_SOLVER);
   if (clustered) {
-    if (ctx->fast_math) RRNN_CUDA(launch_clustered(lw_solver_kernel<true, true>, p, blocks, p.nchunks, smem, ctx->stream));
-    else RRNN_CUDA(launch_clustered(lw_solver_kernel<false, true>, p, blocks, p.nchunks, smem, ctx->stream));
-  } else if (ctx->fast_math) {
-    RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lw_solver_kernel<true, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1]; int ncta = 0;
+#define LW_CL(F, GB)                                                                                              \
+    do {                                                                                                          \
+      RRNN_CUDA(cluster_config(lw_solver_kernel<F, true, GB>, p.nchunks, per_warp, ncol, ctx->stream, cfg, attr, ncta)); \
+      if (GB) { if (int rc = ensure_scratch(ctx, (size_t)ncta * bufb)) return rc; p.scratch = (float*)ctx->scratch; } \
+      RRNN_CUDA(cudaLaunchKernelEx(&cfg, lw_solver_kernel<F, true, GB>, p));                                      \
+    } while (0)
+    if (ctx->fast_math) { if (gbuf) LW_CL(true, true); else LW_CL(true, false); }
+    else { if (gbuf) LW_CL(false, true); else LW_CL(false, false); }
+#undef LW_CL
   } else {
-    RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lw_solver_kernel<false, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
+    const int wpb = pick_warps_per_block(per_warp);
+    const size_t smem = per_warp * wpb;
+    const long long blocks = ((long long)ncol * p.nchunks + wpb - 1) / wpb;
+    RRNN_CHECK(blocks < 2147483647LL, "rrnn_lw_solver_noscat: too many columns for one launch");
+    const size_t nflux = (size_t)ncol * (nlay + 1) * sizeof(float);
+    RRNN_CUDA(cudaMemsetAsync(flux_up_d, 0, nflux, ctx->stream));
+    RRNN_CUDA(cudaMemsetAsync(flux_dn_d, 0, nflux, ctx->stream));
+    if (ctx->fast_math) {
+      RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lw_solver_kernel<true, false, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
+    } else {
+      RRNN_CUDA(cudaFuncSetAttribute(lw_solver_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      lw_solver_kernel<false, false, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);
+    }
   }
   prof_end(ctx, K_LW_SOLVER, ps);
   RRNN_LAUNCH_CHECK(ctx);
@@ -544,33 +660,45 @@ extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
   p.nchunks = (ngpt + 31) / 32;
   p.inc_flux = inc_flux_d; p.inc_flux_dif = inc_flux_dif_d; p.tau = tau_d; p.ssa = ssa_d; p.g = g_d; p.mu0 = mu0_d;
   p.alb_dir = sfc_alb_dir_d; p.alb_dif = sfc_alb_dif_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d; p.flux_dir = flux_dir_d;
-  const size_t per_warp = ((size_t)nlay * 96 + 3 * (size_t)(nlay + 1)) * sizeof(float);
-  RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_sw_solver_2stream: nlay too large for the on-chip layer buffer");
+  const size_t part = 3 * (size_t)(nlay + 1) * sizeof(float);
+  const size_t bufb = (size_t)nlay * 96 * sizeof(float);
   const bool clustered = p.nchunks <= 8;
-  const int wpb = clustered ? 1 : pick_warps_per_block(per_warp);
-  const size_t smem = per_warp * wpb;
-  const long long items = (long long)ncol * p.nchunks;
-  const long long blocks = (items + wpb - 1) / wpb;
-  RRNN_CHECK(blocks < 2147483647LL, "rrnn_sw_solver_2stream: too many columns for one launch");
-  const size_t nflux = (size_t)ncol * (nlay + 1) * sizeof(float);
-  if (!clustered) {
+  const bool gbuf = clustered && use_global_buffer(ctx, bufb + part);
+  const size_t per_warp = part + (gbuf ? 0 : bufb);
+  RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_sw_solver_2stream: nlay too large for the on-chip layer buffer");
+  const bool fast = ctx->fast_math || ctx->sw_fast_math;
+  const int ps = prof_begin(ctx, K_SW_SOLVER);
+  if (clustered) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1]; int ncta = 0;
+#define SW_CL(F, HG, GB)                                                                                              \
+    do {                                                                                                              \
+      RRNN_CUDA(cluster_config(sw_solver_kernel<F, HG, true, GB>, p.nchunks, per_warp, ncol, ctx->stream, cfg, attr, ncta)); \
+      if (GB) { if (int rc = ensure_scratch(ctx, (size_t)ncta * bufb)) return rc; p.scratch = (float*)ctx->scratch; } \
+      RRNN_CUDA(cudaLaunchKernelEx(&cfg, sw_solver_kernel<F, HG, true, GB>, p));                                      \
+    } while (0)
+#define SW_CL2(F, HG) do { if (gbuf) SW_CL(F, HG, true); else SW_CL(F, HG, false); } while (0)
+    if (fast) { if (g_d) SW_CL2(true, true); else SW_CL2(true, false); }
+    else { if (g_d) SW_CL2(false, true); else SW_CL2(false, false); }
+#undef SW_CL2
+#undef SW_CL
+  } else {
+    const int wpb = pick_warps_per_block(per_warp);
+    const size_t smem = per_warp * wpb;
+    const long long blocks = ((long long)ncol * p.nchunks + wpb - 1) / wpb;
+    RRNN_CHECK(blocks < 2147483647LL, "rrnn_sw_solver_2stream: too many columns for one launch");
+    const size_t nflux = (size_t)ncol * (nlay + 1) * sizeof(float);
     RRNN_CUDA(cudaMemsetAsync(flux_up_d, 0, nflux, ctx->stream));
     RRNN_CUDA(cudaMemsetAsync(flux_dn_d, 0, nflux, ctx->stream));
     RRNN_CUDA(cudaMemsetAsync(flux_dir_d, 0, nflux, ctx->stream));
+#define SW_PL(F, HG)                                                                                                       \
+    do {                                                                                                                   \
+      RRNN_CUDA(cudaFuncSetAttribute(sw_solver_kernel<F, HG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      sw_solver_kernel<F, HG, false, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);                         \
+    } while (0)
+    if (fast) { if (g_d) SW_PL(true, true); else SW_PL(true, false); }
+    else { if (g_d) SW_PL(false, true); else SW_PL(false, false); }
+#undef SW_PL
   }
-#define SW_LAUNCH(F, HG)                                                                                                 \
-  do {                                                                                                                   \
-    if (clustered) {                                                                                                     \
-      RRNN_CUDA(launch_clustered(sw_solver_kernel<F, HG, true>, p, blocks, p.nchunks, smem, ctx->stream));               \
-    } else {                                                                                                             \
-      RRNN_CUDA(cudaFuncSetAttribute(sw_solver_kernel<F, HG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      sw_solver_kernel<F, HG, false><<<(unsigned)blocks, wpb * 32, smem, ctx->stream>>>(p);                              \
-    }                                                                                                                    \
-  } while (0)
-  const int ps = prof_begin(ctx, K_SW_SOLVER);
-  if (ctx->fast_math) { if (g_d) SW_LAUNCH(true, true); else SW_LAUNCH(true, false); }
-  else { if (g_d) SW_LAUNCH(false, true); else SW_LAUNCH(false, false); }
-#undef SW_LAUNCH
   prof_end(ctx, K_SW_SOLVER, ps);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;

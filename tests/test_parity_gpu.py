@@ -98,8 +98,11 @@ def test_lw_fluxes_match_oracle(gpu_ctx, files, ngpt, nlay, ncol, flip, nang):
 
 
 def test_lw_physical_orientation_flag(gpu_ctx):
-    """lw_source_bug_compat = 0: a bottom-up column gives exactly the flipped fluxes of the same column top-down
-    (the reference's lw_source_noscat ignores top_at_1 -- quirk Q1 -- which the default reproduces)."""
+    """lw_source_bug_compat = 0 orients the level sources physically for bottom-up columns (the reference's
+    lw_source_noscat ignores top_at_1 -- quirk Q1 -- which the default reproduces).  The flipped problem then agrees
+    with the top-down one up to the part that is a property of the reference's gas optics, not of the solver:
+    lev_source(l) = pfrac(l) * B(tlev(l)) takes the Planck fraction of the layer with the same INDEX as the level,
+    i.e. the layer below the level top-down but above it bottom-up (mo_gas_optics_kernels.F90:663-672)."""
     from rte_rrtmgp_nn_b200 import api, synth
     torch = _torch()
     kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, H.LW_G256, 256, 9, 60, seed=12)
@@ -117,9 +120,11 @@ def test_lw_physical_orientation_flag(gpu_ctx):
     finally:
         gpu_ctx.set_flag("lw_source_bug_compat", 1)
     u0, d0 = res[(0, "down")]; u1, d1 = res[(0, "up")]
-    assert np.abs(u1[:, ::-1] - u0).max() <= 2e-3 and np.abs(d1[:, ::-1] - d0).max() <= 2e-3
+    phys = max(np.abs(u1[:, ::-1] - u0).max(), np.abs(d1[:, ::-1] - d0).max())
+    quirk = max(np.abs(res[(1, "up")][0][:, ::-1] - u0).max(), np.abs(res[(1, "up")][1][:, ::-1] - d0).max())
+    assert phys <= 0.5, phys
+    assert quirk > 10 * phys, (quirk, phys)                             # the default keeps the quirk
     assert np.array_equal(res[(1, "down")][0], u0)                      # the flag only matters bottom-up
-    assert np.abs(res[(1, "up")][0][:, ::-1] - u0).max() > 1e-2         # and the default keeps the quirk
 
 
 def test_lw_solver_alone_random_inputs(gpu_ctx):
