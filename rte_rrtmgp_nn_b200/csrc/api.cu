@@ -278,6 +278,7 @@ extern "C" int rrnn_ctx_create(int device, void* stream, rrnn_ctx_t** out) {
   if (const char* e = getenv("RRNN_FAST_MATH")) c->fast_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("RRNN_SW_FAST_MATH")) c->sw_fast_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("RRNN_SOLVER_BUFFER")) c->solver_buffer = atoi(e);
+  if (const char* e = getenv("RRNN_NN_TENSOR_CORES")) c->nn_tensor_cores = atoi(e) ? 1 : 0;
   *out = c;
   return 0;
 }
@@ -406,6 +407,7 @@ extern "C" int rrnn_model_destroy(rrnn_model_t* m) {
   if (!m) return 0;
   if (m->device >= 0) cudaSetDevice(m->device);
   cudaFree(m->d_wpack); cudaFree(m->d_bpack); cudaFree(m->d_ymean); cudaFree(m->d_ystd);
+  cudaFree(m->d_tc_w); cudaFree(m->d_tc_b);
   delete m;
   return 0;
 }

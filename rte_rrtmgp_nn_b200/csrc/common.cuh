@@ -104,6 +104,10 @@ struct rrnn_model {
   float* d_ystd = nullptr;
   size_t w_off[rrnn::MAX_LAYERS] = {};
   size_t b_off[rrnn::MAX_LAYERS] = {};
+  // tensor-core pack (built lazily by gas_optics_tc.cu): fp16 hi/lo weights in the canonical UMMA layout
+  void* d_tc_w = nullptr;
+  float* d_tc_b = nullptr;
+  int tc_w_bytes = 0, tc_H = 0;
 };
 
 struct rrnn_kdist {

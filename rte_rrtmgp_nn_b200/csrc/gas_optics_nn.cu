@@ -617,6 +617,11 @@ int map_gases(const rrnn_model_t* m, const rrnn_gas_t* gases, int ngas, GoParams
 
 using namespace rrnn;
 
+int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol, int nlay,
+                       const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
+                       const rrnn_gas_t* gases, int ngas, float* out0, float* out1, float* out2, float* sfc_source,
+                       float* sfc_jac, int prof_kind);  // gas_optics_tc.cu; -1 = configuration not supported
+
 extern "C" int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
                                   int ncol, int nlay, const float* play_d, const float* plev_d, const float* tlay_d,
                                   const float* tsfc_d, const rrnn_gas_t* gases, int ngas, const float* tlev_d,
@@ -646,8 +651,14 @@ extern "C" int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
   p.nbnd = kd->nbnd; p.ntemp = kd->ntemp; p.gpt2band = kd->d_gpt2band; p.totplnk = kd->d_totplnk;
   p.temp_ref_min = kd->temp_ref_min; p.totplnk_delta = kd->totplnk_delta;
   p.out0 = tau_d; p.out1 = lay_source_d; p.out2 = lev_source_d; p.sfc_source = sfc_source_d; p.sfc_jac = sfc_source_Jac_d;
-  int rc;
-  if (nmodels == 2) {
+  int rc = -1;
+  if (nmodels == 2 && ctx->nn_tensor_cores) {
+    rc = rrnn_gas_optics_tc(ctx, 0, kd, models, ncol, nlay, play_d, plev_d, tlay_d, p.tlev, tsfc_d, gases, ngas, tau_d,
+                            lay_source_d, lev_source_d, sfc_source_d, sfc_source_Jac_d, K_GAS_LW);
+  }
+  if (rc >= 0) {
+    // done on the tensor cores (or failed with an error)
+  } else if (nmodels == 2) {
     RRNN_CHECK(models[0]->dims[models[0]->nlayers] == kd->ngpt && models[1]->dims[models[1]->nlayers] == kd->ngpt,
                "gas_optics(): network output size differs from the number of g-points");
     RRNN_CHECK(models[0]->d_ymean && models[0]->d_ystd, "output_sgemm_tau: NN output scaling coefficients missing");
@@ -688,7 +699,12 @@ extern "C" int rrnn_gas_optics_sw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
   }
   RRNN_CHECK(kd->ngpt % 4 == 0 && kd->ngpt <= 256, "gas_optics(): ngpt must be a multiple of 4 and <= 256");
   p.out0 = tau_d; p.out1 = ssa_d; p.out2 = g_d;
-  if (int rc = launch_go<EPI_SW>(ctx, p, kd->ngpt, K_GAS_SW)) return rc;
+  int rc = -1;
+  if (two_stream && ctx->nn_tensor_cores)
+    rc = rrnn_gas_optics_tc(ctx, 1, kd, models, ncol, nlay, play_d, plev_d, tlay_d, nullptr, nullptr, gases, ngas, tau_d, ssa_d,
+                            g_d, nullptr, nullptr, K_GAS_SW);
+  if (rc < 0) rc = launch_go<EPI_SW>(ctx, p, kd->ngpt, K_GAS_SW);
+  if (rc) return rc;
   if (toa_src_d) {
     RRNN_CHECK(kd->d_solar_source, "gas_optics(): k-distribution has no solar source (not a shortwave k-distribution)");
     const size_t n = (size_t)kd->ngpt * ncol;
