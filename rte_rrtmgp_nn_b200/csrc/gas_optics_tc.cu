@@ -55,6 +55,8 @@ struct Params {
   const float *play, *plev, *tlay, *tlev, *tsfc;
   GasIn gas[KIN];
   float xmin[KIN], xmax[KIN];
+  float xconst[KIN];  // scaled value of inputs that do not vary per sample (scalar gases, missing gases, padding)
+  int xvar[KIN];      // 1 = varies per sample (tlay, play, 1-D / 2-D gas fields)
   Net net[2];
   int nbnd, ntemp;
   const int* gpt2band;
@@ -139,18 +141,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // canonical K-major no-swizzle layout of an operand with R rows: byte offset of the 16-byte unit (row r, k-unit ku)
 __device__ __forceinline__ uint32_t unit_off(int R, int r, int ku) { return (uint32_t)ku * (R * 16) + (r >> 3) * 128 + (r & 7) * 16; }
 
-// split 8 fp32 values into fp16 hi / lo and store the two 16-byte units
+// split 8 fp32 values into fp16 hi / lo (packed conversions) and store the two 16-byte units
 __device__ __forceinline__ void store_split8(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float* v) {
   __half2 h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-    const __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-    h[i] = __halves2half2(h0, h1);
-    l[i] = __halves2half2(l0, l1);
+    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
   }
   *reinterpret_cast<uint4*>(hi_base + off) = *reinterpret_cast<uint4*>(h);
   *reinterpret_cast<uint4*>(lo_base + off) = *reinterpret_cast<uint4*>(l);
+}
+// softsign x/(|x|+1) with a Newton-refined reciprocal (branch-free, ~1 ulp)
+__device__ __forceinline__ float softsign(float x) {
+  const float d = fabsf(x) + 1.0f;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  r = fmaf(fmaf(-d, r, 1.0f), r, r);
+  return x * r;
 }
 
 __device__ __forceinline__ float act_apply(int code, float x) {
