@@ -1,6 +1,7 @@
 // Context / handle management and the small column-parallel kernels of librrnn_b200.
 #include "common.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cfloat>
 
@@ -11,6 +12,10 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(const std::string& msg) {
   g_last_error = msg;
   return 1;
+}
+unsigned long long next_uid() {
+  static std::atomic<unsigned long long> counter{1};
+  return counter.fetch_add(1);
 }
 
 // ---- small kernels -------------------------------------------------------------------------------
@@ -407,7 +412,6 @@ extern "C" int rrnn_model_destroy(rrnn_model_t* m) {
   if (!m) return 0;
   if (m->device >= 0) cudaSetDevice(m->device);
   cudaFree(m->d_wpack); cudaFree(m->d_bpack); cudaFree(m->d_ymean); cudaFree(m->d_ystd);
-  cudaFree(m->d_tc_w); cudaFree(m->d_tc_b);
   delete m;
   return 0;
 }

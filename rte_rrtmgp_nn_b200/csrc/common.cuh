@@ -90,7 +90,10 @@ inline void prof_end(rrnn_ctx* c, int kind, int slot) {
 }
 }  // namespace rrnn
 
+namespace rrnn { unsigned long long next_uid(); }
+
 struct rrnn_model {
+  unsigned long long uid = rrnn::next_uid();  // never reused: keys caches safely across destroy / create
   int nlayers = 0;
   int dims[rrnn::MAX_LAYERS + 1] = {};
   int act[rrnn::MAX_LAYERS] = {};
@@ -104,13 +107,10 @@ struct rrnn_model {
   float* d_ystd = nullptr;
   size_t w_off[rrnn::MAX_LAYERS] = {};
   size_t b_off[rrnn::MAX_LAYERS] = {};
-  // tensor-core pack (built lazily by gas_optics_tc.cu): fp16 hi/lo weights in the canonical UMMA layout
-  void* d_tc_w = nullptr;
-  float* d_tc_b = nullptr;
-  int tc_w_bytes = 0, tc_H = 0;
 };
 
 struct rrnn_kdist {
+  unsigned long long uid = rrnn::next_uid();
   int nbnd = 0, ngpt = 0, ntemp = 0;
   float temp_ref_min = 0.f, totplnk_delta = 1.f;
   std::vector<int> band_lims_gpt;  // [nbnd][2], 1-based inclusive

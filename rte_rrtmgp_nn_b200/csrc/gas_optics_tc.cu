@@ -1,68 +1,83 @@
-// NN gas optics on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+// NN gas optics on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
 //
-// Same fused path as gas_optics_nn.cu (inputs -> MLP chain -> tau / Planck-source / ssa epilogues, every output
-// written once) with the three GEMMs of each network on tcgen05.mma:
-//   * one CTA per SM (256 threads) walks tiles of 128 samples = the 128 TMEM lanes;
-//   * operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8 x 16-byte core matrices);
-//     weights are staged once per CTA, activations are written by the epilogue threads of the previous layer;
-//   * precision: every fp32 value v is split v = hi + lo with hi = fp16(v), lo = fp16(v - hi) (22 mantissa bits
-//     together) and each GEMM is issued as hi*Whi + lo*Whi + hi*Wlo on kind::f16 with fp32 accumulation in TMEM --
-//     fp32-class accuracy at fp16 tensor rate (the dropped lo*lo term is < 2^-22 relative);
-//   * accumulators: 256 TMEM columns for the output layer, 64 for the hidden layers; tcgen05.ld (32x32b) brings one
-//     sample row x 32 g-points per thread into registers; bias, softsign, (ystd*z+ymean)^8*N_dry, pfrac^2 * Planck,
-//     tau_abs+tau_ray / ssa are applied there;
-//   * stores: each warp transposes its 32 rows x 32 g-points through a private padded shared-memory tile so that
-//     every st.global.v4 covers full 128-byte lines (4 rows x 128 B per instruction).
-// One elected thread issues the MMAs and commits them to an mbarrier; the 8 warps are the epilogue (two warps per
-// TMEM lane quarter, each taking half of the columns).
+// Same fused path as gas_optics_nn.cu (compute_nn_inputs + get_col_dry -> MLP chain -> tau / Planck-source / ssa
+// epilogues; every output float written exactly once, neural/mod_network_rrtmgp.F90:125-317,
+// rrtmgp/kernels/mo_gas_optics_kernels.F90:615-683) as a warp-specialised, persistent, software-pipelined kernel:
 //
-// Supported: 2 hidden layers, hidden width <= 64, <= 32 inputs, ngpt a multiple of 32 and <= 256 (all g256/g224/g128
-// two-network models of the reference); anything else falls back to the fp32 FFMA kernel.
+//   one CTA per SM, 288 threads, walking tiles of 128 rows (= the 128 TMEM lanes);
+//     warps 0-3  FRONT     thread = row: scaled inputs (log p, h2o^1/4, o3^1/4, min-max scaling) -> A operand of
+//                          layer 1; hidden epilogues (tcgen05.ld, bias, softsign, fp16 hi/lo split) -> A operand of
+//                          the next layer.  Runs about one tile ahead of the output epilogue.
+//     warps 4-7  EPILOGUE  thread = row: tcgen05.ld of 32 g-points of both networks at a time from a ring of TMEM
+//                          slots; (.)^8 * N_dry | pfrac^2 * Planck(T_lay), Planck(T_lev) | tau_abs+tau_ray, ssa in
+//                          registers; rows are staged in 128B-swizzled shared memory and written with TMA tensor stores
+//                          (cp.async.bulk.tensor.3d): no load/store instruction is spent on the 3 KB/row of output,
+//                          column boundaries inside a tile are handled by the tensor map's bounds (negative start
+//                          coordinates and rows beyond nlay are clipped by the TMA unit).
+//     warp 8     MMA       one thread issues every tcgen05.mma and commits to mbarriers.
+//   LW rows run over (level, column) with nlay+1 rows per column: the extra row repeats the bottom layer and produces
+//   lev_source(nlay+1) (and the surface source when the surface is at layer nlay), so lev_source needs no special case.
+//   precision: every fp32 operand v is split v = hi + lo, hi = fp16(v), lo = fp16(v - hi) (22 mantissa bits) and each
+//   GEMM is issued as hi*Whi + lo*Whi + hi*Wlo + lo*Wlo on kind::f16 with fp32 accumulation in TMEM.  The output scaling
+//   ystd*(z+b)+ymean is folded into the last layer's weights (times 2^10 so that the fp16 lo parts stay normal; the
+//   2^-80 comes back with N_dry) and, where the padded K has a spare column, the bias rides on a column of ones.
+//
+// Supported: two networks with 2 hidden layers of equal width <= 64, linear output, <= 32 inputs, ngpt a multiple of
+// 32 and <= 256, nbnd <= 16 (all g256 / g224 / g128 two-network models of the reference with hidden width <= 64);
+// anything else returns -1 and the caller uses the fp32 FFMA kernel.
 #include "common.cuh"
+#include <cuda.h>
 #include <cuda_fp16.h>
+#include <algorithm>
+#include <mutex>
 
 namespace rrnn {
-
-int map_gases(const rrnn_model_t* m, const rrnn_gas_t* gases, int ngas, struct GoParams& p);  // gas_optics_nn.cu
-
 namespace tc {
 
-constexpr int TM = 128;  // samples per tile (TMEM lanes)
-constexpr int THREADS = 256;
-constexpr int KIN = 32;  // padded number of network inputs
-constexpr int STAGE_LD = 36;  // floats per staging row (32 + 4 pad): conflict-free 16-byte accesses
+constexpr int TM = 128;          // rows per tile (TMEM lanes)
+constexpr int THREADS = 416;     // 4 front warps + 2 x 4 epilogue warps + 1 MMA warp
+constexpr int MMA_WARP = 12;
+constexpr int KIN_MAX = 32;      // padded number of network inputs
+constexpr int NSLOT = 6;         // ring of output accumulators: 6 x 64 TMEM columns (32 of net 0 | 32 of net 1)
+constexpr int RING_COL0 = 128;   // TMEM columns 0..63 / 64..127: hidden accumulators of net 0 / 1
+constexpr int STAGE_BYTES = 4096;  // one staged output tile: 32 rows x 32 g-points
+constexpr float OUT_SCALE = 1024.0f;            // folded into the last layer of the tau-type networks
+constexpr float OUT_UNSCALE = 8.271806125530277e-25f;  // 2^-80 = OUT_SCALE^-8
 
-struct Net {
-  int H, N;            // padded hidden width (16..64, multiple of 16), outputs (multiple of 32)
-  int act[3];
-  int w_bytes;         // bytes of the packed weights (hi/lo blocks of the three layers)
-  const uint8_t* w;    // device: [W1hi][W1lo][W2hi][W2lo][W3hi][W3lo], canonical layout, fp16
-  const float* b;      // device: b1[H] b2[H] b3[N]
-  const float* ymean;  // device, N (or null)
-  const float* ystd;
+enum { BAR_AIN = 0, BAR_HID = 1, BAR_ACT = 3, BAR_ACTFREE = 5, BAR_SLOT_FULL = 7, BAR_SLOT_EMPTY = 7 + NSLOT, NBAR = 7 + 2 * NSLOT };
+
+struct NetP {
+  int H, K3, Hraw, fold, act0, act1, ntot;
+  uint32_t w[3][2];          // shared-memory byte offsets of W{1,2,3}{hi,lo} (canonical K-major layout, fp16)
+  uint32_t b[3];             // byte offsets of b1[H], b2[H], b3''[N] (fp32)
+  uint32_t act_hi, act_lo;   // activation operand (A of layers 2 and 3)
 };
 
 struct GasIn {
   const float* ptr;
-  float value;
-  int mode;
+  int mode;  // 1 = per-layer profile, 2 = (nlay,ncol) field
 };
 
 struct Params {
-  int mode;  // 0 = LW (tau net + Planck-fraction net), 1 = SW (absorption net + Rayleigh net)
-  int ncol, nlay, ngpt, nx;
-  long long nsamples;
+  int ncol, nlay, ngpt, nx, kin, nbnd, ntemp, period, nchunks;
+  int nstage;  // staging tiles per epilogue warp (2 when shared memory allows, else 1)
+  int nrec;  // depth of the per-row record ring (how many tiles the front warps may run ahead of the output epilogue)
+  unsigned nrows;
   const float *play, *plev, *tlay, *tlev, *tsfc;
-  GasIn gas[KIN];
-  float xmin[KIN], xmax[KIN];
-  float xconst[KIN];  // scaled value of inputs that do not vary per sample (scalar gases, missing gases, padding)
-  int xvar[KIN];      // 1 = varies per sample (tlay, play, 1-D / 2-D gas fields)
-  Net net[2];
-  int nbnd, ntemp;
-  const int* gpt2band;
+  GasIn gas[KIN_MAX];
+  float xmin[KIN_MAX], xmax[KIN_MAX];
+  float xconst[KIN_MAX];  // scaled value of inputs that do not vary per sample (scalar gases, missing gases, padding)
+  int xvar[KIN_MAX];      // 1 = varies per sample (tlay, play, 1-D / 2-D gas fields)
+  float h2o_const;        // h2o vmr when it is a scalar
+  NetP net[2];
+  const uint8_t* blob;    // weights, biases, band tables exactly as they sit in shared memory
+  uint32_t blob_bytes;
+  uint32_t off_band4, off_totplnk, off_ain_hi, off_ain_lo, off_stage, off_rec, off_bar;
   const float* totplnk;
   float temp_ref_min, totplnk_delta;
-  float *out0, *out1, *out2, *sfc_source, *sfc_jac;
+  float *sfc_source, *sfc_jac;
+  unsigned* dbg;   // debug only (RRNN_TC_DEBUG): host-mapped progress words, else null
+  int dbg_flags;   // 2 = issue no TMA store, 4 = first box only
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -94,6 +109,9 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -103,43 +121,104 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifndef RRNN_TC_TRACE
+#define RRNN_TC_TRACE 0  // 1: compile the progress marks / timeline stamps into the hot loops (debug builds only)
+#endif
+__device__ unsigned* g_dbg = nullptr;
+__device__ __forceinline__ void dbg_mark(unsigned* dbg, int role, unsigned code) {
+#if RRNN_TC_TRACE
+  if (dbg && blockIdx.x == 0) { volatile unsigned* d = dbg; d[role] = code; }
+#endif
+}
+// debug timeline: SM clock at event `idx` of one steady-state tile of block 0
+__device__ __forceinline__ void dbg_ts(unsigned* dbg, int it, int idx) {
+#if RRNN_TC_TRACE
+  if (dbg && blockIdx.x == 0 && it == 5) { volatile unsigned* d = dbg; d[32 + idx] = (unsigned)clock64(); }
+#endif
+}
+// Spin on an mbarrier phase.  A wait that lasts ~seconds can only be a protocol bug: trap (the launch then fails with
+// an error) rather than hang the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      if (g_dbg) {
+        volatile unsigned* d = g_dbg;
+        d[16] = 0xdead0000u | (unsigned)threadIdx.x; d[17] = bar; d[18] = parity; d[19] = blockIdx.x;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+// one lane of a converged warp (elect.sync): lets ptxas issue the uniform-datapath tcgen05 instructions straight,
+// without the per-lane retry loop it wraps around them under an ordinary `lane == 0` branch
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(smem)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// packed fp32x2 arithmetic (sm_100): one instruction for two lanes of a register pair
+__device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a, b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(r));
+}
+__device__ __forceinline__ void mul2to(float& d0, float& d1, float a0, float a1, float b) {  // (d0,d1) = (a0,a1) * b
+  uint64_t a, bb, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b), "f"(b));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(bb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(r));
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+#define RRNN_R8(a, o) "=r"(a[o]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3]), "=r"(a[o + 4]), "=r"(a[o + 5]), "=r"(a[o + 6]), "=r"(a[o + 7])
+// one TMEM lane (= row) x 64 columns per thread
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n\t"
       "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : RRNN_R8(r, 0), RRNN_R8(r, 8), RRNN_R8(r, 16), RRNN_R8(r, 24), RRNN_R8(r, 32), RRNN_R8(r, 40), RRNN_R8(r, 48), RRNN_R8(r, 56)
       : "r"(taddr)
       : "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
       "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : RRNN_R8(r, 0), RRNN_R8(r, 8)
       : "r"(taddr)
       : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+#undef RRNN_R8
 
 // canonical K-major no-swizzle layout of an operand with R rows: byte offset of the 16-byte unit (row r, k-unit ku)
-__device__ __forceinline__ uint32_t unit_off(int R, int r, int ku) { return (uint32_t)ku * (R * 16) + (r >> 3) * 128 + (r & 7) * 16; }
+__host__ __device__ __forceinline__ uint32_t unit_off(int R, int r, int ku) { return (uint32_t)ku * (R * 16) + (r >> 3) * 128 + (r & 7) * 16; }
 
 // split 8 fp32 values into fp16 hi / lo (packed conversions) and store the two 16-byte units
 __device__ __forceinline__ void store_split8(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float* v) {
@@ -156,15 +235,14 @@ __device__ __forceinline__ void store_split8(uint8_t* hi_base, uint8_t* lo_base,
 // softsign x/(|x|+1) with a Newton-refined reciprocal (branch-free, ~1 ulp)
 __device__ __forceinline__ float softsign(float x) {
   const float d = fabsf(x) + 1.0f;
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  float r = rcp_approx(d);
   r = fmaf(fmaf(-d, r, 1.0f), r, r);
   return x * r;
 }
-
-__device__ __forceinline__ float act_apply(int code, float x) {
+// generic activations (neural/mod_activation.F90): kept out of line, the shipped models only use softsign
+__device__ __noinline__ float act_apply(int code, float x) {
   switch (code) {
-    case RRNN_ACT_SOFTSIGN: return x / (fabsf(x) + 1.0f);
+    case RRNN_ACT_SOFTSIGN: return softsign(x);
     case RRNN_ACT_RELU: return fmaxf(0.0f, x);
     case RRNN_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
     case RRNN_ACT_HARD_SIGMOID: return fmaxf(0.0f, fminf(1.0f, 0.2f * x + 0.5f));
@@ -172,369 +250,549 @@ __device__ __forceinline__ float act_apply(int code, float x) {
   }
 }
 
-__device__ __forceinline__ float planck_interp(float T, float tmin, float delta, const float* __restrict__ tab, int ntemp) {
+// interpolate1D of compute_Planck_source_nn (mo_gas_optics_kernels.F90:1024-1043): index clamped, fraction not (quirk Q4)
+struct PlanckPos {
+  int idx;
+  float frac;
+};
+__device__ __forceinline__ PlanckPos planck_pos(float T, float tmin, float delta, int ntemp) {
   const float val0 = (T - tmin) / delta;
   const int iv = (int)val0;
-  const float frac = val0 - (float)iv;
-  const int idx = min(ntemp - 1, max(1, iv + 1));
-  const float t0 = __ldg(tab + idx - 1);
-  return t0 + frac * (__ldg(tab + idx) - t0);
+  PlanckPos pp;
+  pp.frac = val0 - (float)iv;
+  pp.idx = min(ntemp - 1, max(1, iv + 1));
+  return pp;
+}
+__device__ __forceinline__ float planck_at(const PlanckPos pp, const float* __restrict__ tab /* band row */) {
+  const float t0 = __ldg(tab + pp.idx - 1);
+  return t0 + pp.frac * (__ldg(tab + pp.idx) - t0);
 }
 
-// Issue D[128 x N] (+)= A[128 x K] * W[N x K]^T as the three split products; A hi/lo and W hi/lo in canonical layout.
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, int K, int N) {
-  const uint32_t idesc = make_idesc(TM, N);
-  const int ksteps = K >> 4;
-  uint32_t acc = 0;
-  for (int s = 0; s < ksteps; ++s) {
-    // one k-step = 16 fp16 = two 16-byte k-units; operands advance by two units
-    const uint32_t ao = (uint32_t)(2 * s) * (TM * 16), wo = (uint32_t)(2 * s) * (N * 16);
-    const uint64_t dah = make_desc(a_hi + ao, TM * 16, 128), dal = make_desc(a_lo + ao, TM * 16, 128);
-    const uint64_t dwh = make_desc(w_hi + wo, N * 16, 128), dwl = make_desc(w_lo + wo, N * 16, 128);
-    mma_f16(tmem_d, dah, dwh, idesc, acc);
-    acc = 1;
-    mma_f16(tmem_d, dal, dwh, idesc, 1);
-    mma_f16(tmem_d, dah, dwl, idesc, 1);
-  }
-}
-
-struct NetPlan {
-  uint32_t w[3][2];  // shared-memory byte offsets of W{1,2,3}{hi,lo}
-  uint32_t b[3];     // float offsets of b1, b2, b3 in the bias area
-  uint32_t ystd, ymean;
+// Issue D[128 x N] = A[128 x K] * W[N x K]^T as the four split products hi*hi + lo*hi + hi*lo + lo*lo.
+// Operands are given as ready-made shared-memory descriptors of their first k-step (the address field is the low 14
+// bits, in 16-byte units, so advancing an operand is one integer add): A advances 2 k-units x 2048 B = 256 units per
+// k-step, W advances `wstep` units.  The issuing thread is a serial resource -- ~200 MMAs per tile -- so nothing but
+// the adds and the MMA itself is left in these loops.
+// Order matters: the tensor core truncates (does not round) when it adds a product block to the accumulator, one
+// accumulator-ulp per tcgen05.mma, always in the same direction.  The three correction products are 2^-11 of the main
+// one, so they are accumulated FIRST, while the accumulator is still small (their truncations are then negligible),
+// and the hi*hi blocks last: K/16 full-size truncations instead of 4K/16 (measured: the systematic relative tau offset
+// of the interleaved order, -4e-4 at the most amplified g-point, drops accordingly).
+struct OperandDesc {
+  uint64_t hi, lo;
 };
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const OperandDesc a, const OperandDesc w, uint32_t wstep, int ksteps,
+                                           uint32_t idesc) {
+  mma_f16(tmem_d, a.lo, w.lo, idesc, 0);
+  mma_f16(tmem_d, a.lo, w.hi, idesc, 1);
+  mma_f16(tmem_d, a.hi, w.lo, idesc, 1);
+  for (int s = 1; s < ksteps; ++s) {
+    const uint64_t ao = (uint64_t)(256u * s), wo = (uint64_t)(wstep * s);
+    mma_f16(tmem_d, a.lo + ao, w.lo + wo, idesc, 1);
+    mma_f16(tmem_d, a.lo + ao, w.hi + wo, idesc, 1);
+    mma_f16(tmem_d, a.hi + ao, w.lo + wo, idesc, 1);
+  }
+  for (int s = 0; s < ksteps; ++s) mma_f16(tmem_d, a.hi + (uint64_t)(256u * s), w.hi + (uint64_t)(wstep * s), idesc, 1);
+}
 
+// get_col_dry for one layer (rrtmgp/mo_gas_optics_rrtmgp.F90:1697-1703)
+__device__ __forceinline__ float col_dry_of(float h2o, float p0, float p1) {
+  const float dp = fabsf(p0 - p1);
+  const float fact = 1.0f / (1.0f + h2o);
+  const float m_air = (0.028964f + 0.018016f * h2o) * fact;
+  return 10.0f * dp * 6.02214076e23f * fact / (1000.0f * m_air * 100.0f * 9.80665f);
+}
+
+// MODE 0 = LW (net 0: absorption -> tau; net 1: Planck fraction -> lay_source, lev_source, sfc_source[_Jac])
+// MODE 1 = SW (net 0: absorption, net 1: Rayleigh -> tau = abs + ray, ssa = ray / tau)
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1) gas_optics_tc_kernel(const Params p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+__global__ void __launch_bounds__(THREADS, 1)
+gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap tm0,
+                     const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+                     const __grid_constant__ CUtensorMap tm0s, const __grid_constant__ CUtensorMap tm1s) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the dynamic shared memory window is at least 16-byte aligned; the swizzled staging tiles want 1024
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int quarter = warp & 3;    // TMEM lane quarter this warp may access
-  const int half = warp >> 2;      // which half of the columns this warp handles
-  const int row = 32 * quarter + lane;
-  const int L = p.nlay, G = p.ngpt;
+  const int L = p.nlay, G = p.ngpt, P = p.period;
 
-  // ---------------------------------------------------------------------------------- shared-memory carve-up
-  uint32_t off = 0;
-  NetPlan plan[2];
-  uint32_t woff[2];
-  for (int n = 0; n < 2; ++n) {
-    const int H = p.net[n].H, N = p.net[n].N;
-    woff[n] = off;
-    uint32_t o = off;
-    plan[n].w[0][0] = o; o += H * KIN * 2; plan[n].w[0][1] = o; o += H * KIN * 2;
-    plan[n].w[1][0] = o; o += H * H * 2;   plan[n].w[1][1] = o; o += H * H * 2;
-    plan[n].w[2][0] = o; o += N * H * 2;   plan[n].w[2][1] = o; o += N * H * 2;
-    off = o;
-  }
-  float* fl = reinterpret_cast<float*>(smem + off);
-  uint32_t fo = 0;
-  for (int n = 0; n < 2; ++n) {
-    const int H = p.net[n].H, N = p.net[n].N;
-    plan[n].b[0] = fo; fo += H; plan[n].b[1] = fo; fo += H; plan[n].b[2] = fo; fo += N;
-    plan[n].ystd = fo; fo += N; plan[n].ymean = fo; fo += N;
-  }
-  off += fo * 4;
-  uint8_t* ain_hi = smem + off; off += TM * KIN * 2;
-  uint8_t* ain_lo = smem + off; off += TM * KIN * 2;
-  uint8_t* act_hi = smem + off; off += TM * 64 * 2;
-  uint8_t* act_lo = smem + off; off += TM * 64 * 2;
-  float* stage = reinterpret_cast<float*>(smem + off) + warp * (32 * STAGE_LD); off += 8 * 32 * STAGE_LD * 4;
-  float* coldry_s = reinterpret_cast<float*>(smem + off); off += TM * 4;
-  int* levrow_s = reinterpret_cast<int*>(smem + off); off += TM * 4;   // row index into lev_source; -1 = sample beyond the end
-  int* flag_s = reinterpret_cast<int*>(smem + off); off += TM * 4;
-  int* band_s = reinterpret_cast<int*>(smem + off); off += 256 * 4;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + off); off += 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off); off += 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   // ---------------------------------------------------------------------------------- one-time set-up
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.blob);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = tid; i < p.blob_bytes / 16; i += THREADS) dst[i] = __ldg(src + i);
+    // activation operands start from zero (padding k-units are never written again); a folded bias that lives in an
+    // extension k-unit (Hraw == H) gets its column of ones here, once
+    for (int n = 0; n < 2; ++n) {
+      const NetP& nt = p.net[n];
+      uint4* a = reinterpret_cast<uint4*>(smem + nt.act_hi);
+      const uint32_t units = (uint32_t)(2 * TM * nt.K3 * 2) / 16;  // hi and lo are contiguous
+      for (uint32_t i = tid; i < units; i += THREADS) a[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint4* ain = reinterpret_cast<uint4*>(smem + p.off_ain_hi);
+    for (uint32_t i = tid; i < (uint32_t)(2 * TM * p.kin * 2) / 16; i += THREADS) ain[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
   for (int n = 0; n < 2; ++n) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.net[n].w);
-    uint4* dst = reinterpret_cast<uint4*>(smem + woff[n]);
-    for (int i = tid; i < p.net[n].w_bytes / 16; i += THREADS) dst[i] = src[i];
-    const int H = p.net[n].H, N = p.net[n].N;
-    for (int i = tid; i < 2 * H + N; i += THREADS) fl[plan[n].b[0] + i] = p.net[n].b[i];
-    for (int i = tid; i < N; i += THREADS) {
-      fl[plan[n].ystd + i] = p.net[n].ystd ? p.net[n].ystd[i] : 0.0f;
-      fl[plan[n].ymean + i] = p.net[n].ymean ? p.net[n].ymean[i] : 0.0f;
+    const NetP& nt = p.net[n];
+    if (nt.fold && nt.Hraw >= nt.H && tid < TM) {
+      __half* a = reinterpret_cast<__half*>(smem + nt.act_hi + unit_off(TM, tid, nt.Hraw >> 3));
+      a[nt.Hraw & 7] = __float2half_rn(1.0f);
     }
   }
-  for (int i = tid; i < 256; i += THREADS) band_s[i] = (MODE == 0 && i < G) ? p.gpt2band[i] : 0;
-  if (tid == 0) mbar_init(smem_u32(bar), 1);
+  if (tid == 0) {
+    mbar_init(BAR(BAR_AIN), 128);
+    for (int n = 0; n < 2; ++n) {
+      mbar_init(BAR(BAR_HID + n), 1);
+      mbar_init(BAR(BAR_ACT + n), 128);
+      mbar_init(BAR(BAR_ACTFREE + n), 1);
+    }
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(BAR(BAR_SLOT_FULL + s), 1);
+      mbar_init(BAR(BAR_SLOT_EMPTY + s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_async_smem();
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * quarter) << 16);  // this warp's lanes
-  uint32_t phase = 0;
-  const uint32_t bar_a = smem_u32(bar);
 
-  int sfc_lay0 = -1;
-  if (MODE == 0) sfc_lay0 = (p.play[0] > p.play[L - 1]) ? 0 : L - 1;  // merge(1,nlay,play(1,1) > play(nlay,1))
+  const unsigned ntiles = (p.nrows + TM - 1) / TM;
+  if (p.dbg && tid == 0) { g_dbg = p.dbg; dbg_mark(p.dbg, 15, 0x1000u + (bar0 & 0xffffu)); }
 
-  const long long ntiles = (p.nsamples + TM - 1) / TM;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long s0 = tile * TM;
-    // ------------------------------------------------------------------------------ prologue: inputs, col_dry
-    {
-      const int r = tid & 127, part = tid >> 7;  // two threads per sample: inputs [0,16) and [16,32)
-      const long long smp = s0 + r;
-      const bool ok = smp < p.nsamples;
-      const long long col = ok ? smp / L : 0;
-      const int lay = ok ? (int)(smp - col * L) : 0;
-      float v[16];
+  if (warp < 4) {
+    // =================================================================================== FRONT: thread = row
+    const int r = tid;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * warp) << 16);
+    uint8_t* ain_hi = smem + p.off_ain_hi;
+    uint8_t* ain_lo = smem + p.off_ain_lo;
+    uint32_t ph_hid[2] = {0u, 0u}, ph_free[2] = {0u, 0u};
+    int sfc_lev = -1;
+    if (MODE == 0) sfc_lev = (__ldg(p.play) > __ldg(p.play + L - 1)) ? 0 : L;  // merge(1,nlay,play(1,1) > play(nlay,1)); layer nlay <-> extra row
+    int it = 0;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      // ---- compute_nn_inputs (mo_gas_optics_rrtmgp.F90:713-782) for this row
+      if (tid == 0) dbg_ts(p.dbg, it, 0);
+      const unsigned s = tile * TM + r;
+      const bool valid = s < p.nrows;
+      const unsigned col = valid ? s / (unsigned)P : 0u;
+      const int lev = valid ? (int)(s - col * (unsigned)P) : 0;
+      const int lay = min(lev, L - 1);
+      const size_t smp = (size_t)col * L + lay;
+#pragma unroll 1
+      for (int ku = 0; ku < (p.kin >> 3); ++ku) {
+        float v[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int k = 16 * part + j;
-        float x = 0.0f;
-        if (ok && k < p.nx) {
-          float raw;
-          if (k == 0) raw = p.tlay[smp];
-          else if (k == 1) raw = logf(p.play[smp]);
-          else {
-            const GasIn gi = p.gas[k];
-            raw = (gi.mode == 2) ? gi.ptr[smp] : (gi.mode == 1 ? gi.ptr[lay] : (gi.mode == 0 ? gi.value : 0.0f));
-            if (k == 2 || k == 3) raw = sqrtf(sqrtf(raw));
+        for (int j = 0; j < 8; ++j) {
+          const int k = 8 * ku + j;
+          float x = p.xconst[k];
+          if (p.xvar[k]) {
+            float raw;
+            if (k == 0) raw = __ldg(p.tlay + smp);
+            else if (k == 1) raw = logf(__ldg(p.play + smp));
+            else {
+              raw = (p.gas[k].mode == 2) ? __ldg(p.gas[k].ptr + smp) : __ldg(p.gas[k].ptr + lay);
+              if (k == 2 || k == 3) raw = sqrtf(sqrtf(raw));
+            }
+            x = (raw - p.xmin[k]) / (p.xmax[k] - p.xmin[k]);
           }
-          x = (raw - p.xmin[k]) / (p.xmax[k] - p.xmin[k]);
+          v[j] = valid ? x : 0.0f;
         }
-        v[j] = x;
+        store_split8(ain_hi, ain_lo, unit_off(TM, r, ku), v);
       }
-      store_split8(ain_hi, ain_lo, unit_off(TM, r, 2 * part), v);
-      store_split8(ain_hi, ain_lo, unit_off(TM, r, 2 * part + 1), v + 8);
-      if (part == 0) {
-        float cd = 0.0f;
-        int fl_ = 0, lr = -1;
-        if (ok) {
-          const GasIn gh = p.gas[2];
-          const float h = (gh.mode == 2) ? gh.ptr[smp] : (gh.mode == 1 ? gh.ptr[lay] : gh.value);
-          const float dp = fabsf(p.plev[col * (L + 1) + lay] - p.plev[col * (L + 1) + lay + 1]);
-          const float fact = 1.0f / (1.0f + h);
-          const float m_air = (0.028964f + 0.018016f * h) * fact;
-          cd = 10.0f * dp * 6.02214076e23f * fact / (1000.0f * m_air * 100.0f * 9.80665f);
-          if (lay == L - 1) fl_ |= 1;
-          if (lay == sfc_lay0) fl_ |= 2;
-          lr = (int)(col * (L + 1) + lay);
+      // ---- per-row record for the output epilogue of this tile (a ring of nrec tiles; ordered by the
+      //      AIN -> ... -> SLOT_FULL barrier chain): N_dry * 2^-80 and where T_lay, T_lev, T_sfc fall in the Planck table
+      {
+        float* rec = reinterpret_cast<float*>(smem + p.off_rec) + (it % p.nrec) * (8 * TM) + r;
+        float cdp = 0.0f;
+        if (valid) {
+          const float h = p.xvar[2] ? ((p.gas[2].mode == 2) ? __ldg(p.gas[2].ptr + smp) : __ldg(p.gas[2].ptr + lay)) : p.h2o_const;
+          const float* pl = p.plev + (size_t)col * (L + 1) + lay;
+          cdp = col_dry_of(h, __ldg(pl), __ldg(pl + 1)) * OUT_UNSCALE;
         }
-        coldry_s[r] = cd; flag_s[r] = fl_; levrow_s[r] = lr;
+        rec[0] = cdp;
+        if (MODE == 0) {
+          const float Tl = valid ? __ldg(p.tlay + smp) : 200.0f;
+          const float Tv = valid ? __ldg(p.tlev + (size_t)col * (L + 1) + lev) : 200.0f;
+          const PlanckPos pl_ = planck_pos(Tl, p.temp_ref_min, p.totplnk_delta, p.ntemp);
+          const PlanckPos pv_ = planck_pos(Tv, p.temp_ref_min, p.totplnk_delta, p.ntemp);
+          rec[1 * TM] = pl_.frac; rec[2 * TM] = __int_as_float(pl_.idx);
+          rec[3 * TM] = pv_.frac; rec[4 * TM] = __int_as_float(pv_.idx);
+          if (valid && lev == sfc_lev) rec[5 * TM] = __ldg(p.tsfc + col);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(BAR(BAR_AIN));
+      if (tid == 0) { dbg_mark(p.dbg, 0, (it << 8) | 1); dbg_ts(p.dbg, it, 1); }
+      // ---- pull the next tile's inputs towards L2 while this tile's chain runs
+      {
+        const unsigned sn = (tile + gridDim.x) * TM + r;
+        if (tile + gridDim.x < ntiles && sn < p.nrows) {
+          const unsigned coln = sn / (unsigned)P;
+          const int layn = min((int)(sn - coln * (unsigned)P), L - 1);
+          const size_t smpn = (size_t)coln * L + layn;
+          prefetch_l2(p.tlay + smpn); prefetch_l2(p.play + smpn);
+          prefetch_l2(p.plev + (size_t)coln * (L + 1) + layn);
+          if (MODE == 0) prefetch_l2(p.tlev + (size_t)coln * (L + 1) + layn);
+#pragma unroll 1
+          for (int k = 2; k < p.nx; ++k)
+            if (p.xvar[k] && p.gas[k].mode == 2) prefetch_l2(p.gas[k].ptr + smpn);
+        }
+      }
+      // ---- hidden epilogues: layer 1 of net 0, net 1; layer 2 of net 0, net 1
+#pragma unroll 1
+      for (int l = 0; l < 2; ++l) {
+#pragma unroll 1
+        for (int n = 0; n < 2; ++n) {
+          const NetP& nt = p.net[n];
+          uint8_t* act_hi = smem + nt.act_hi;
+          uint8_t* act_lo = smem + nt.act_lo;
+          // the previous tile's output-layer MMAs read this buffer: wait until they are done
+          if (l == 0 && it > 0) { mbar_wait(BAR(BAR_ACTFREE + n), ph_free[n]); ph_free[n] ^= 1u; }
+          if (tid == 0) dbg_ts(p.dbg, it, 2 + 3 * (2 * l + n));
+          mbar_wait(BAR(BAR_HID + n), ph_hid[n]); ph_hid[n] ^= 1u;
+          fence_after();
+          if (tid == 0) dbg_ts(p.dbg, it, 3 + 3 * (2 * l + n));
+          const float* bb = reinterpret_cast<const float*>(smem + nt.b[l]);
+          const int act = l ? nt.act1 : nt.act0;
+          const bool ones = (l == 1) && nt.fold && nt.Hraw < nt.H;
+          for (int c0 = 0; c0 < nt.H; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_row + 64u * n + c0, v);
+            if (act == RRNN_ACT_SOFTSIGN) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = softsign(v[j] + bb[c0 + j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = act_apply(act, v[j] + bb[c0 + j]);
+            }
+            if (ones && (nt.Hraw >> 4) == (c0 >> 4)) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = ((nt.Hraw & 15) == j) ? 1.0f : v[j];
+            }
+            store_split8(act_hi, act_lo, unit_off(TM, r, c0 >> 3), v);
+            store_split8(act_hi, act_lo, unit_off(TM, r, (c0 >> 3) + 1), v + 8);
+          }
+          fence_before();
+          fence_async_smem();
+          mbar_arrive(BAR(BAR_ACT + n));
+          if (tid == 0) { dbg_mark(p.dbg, 0, (it << 8) | (0x10 + 2 * l + n)); dbg_ts(p.dbg, it, 4 + 3 * (2 * l + n)); }
+        }
       }
     }
-
-    for (int n = 0; n < 2; ++n) {
-      const Net& net = p.net[n];
-      const int H = net.H, N = net.N;
-      // TMEM columns: output-layer accumulator at 0 (LW, SW net 0) or 256 (SW net 1); hidden accumulator beside it
-      const uint32_t col_out = (MODE == 1 && n == 1) ? 256u : 0u;
-      const uint32_t col_hid = (MODE == 1 && n == 1) ? (uint32_t)p.net[0].N : 256u;
-      // ---------------------------------------------------------------------------- two hidden layers
-      for (int l = 0; l < 2; ++l) {
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        if (tid == 0) {
+  } else if (warp == MMA_WARP) {
+    // =================================================================================== MMA issuer
+    // The whole warp walks the loop and waits on the barriers (it stays converged); one elected lane issues.
+    {
+      uint32_t ph_ain = 0u, ph_act[2] = {0u, 0u};
+      unsigned jc = 0;
+      const uint32_t sb = smem_u32(smem);
+      // every operand descriptor is tile-invariant: build them once
+      const OperandDesc d_ain = {make_desc(sb + p.off_ain_hi, TM * 16, 128), make_desc(sb + p.off_ain_lo, TM * 16, 128)};
+      OperandDesc d_act[2], d_w[2][3];
+      uint32_t wstep12[2], idesc_h[2];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const NetP& nt = p.net[n];
+        d_act[n] = {make_desc(sb + nt.act_hi, TM * 16, 128), make_desc(sb + nt.act_lo, TM * 16, 128)};
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          const uint32_t lbo = (uint32_t)(l == 2 ? nt.ntot : nt.H) * 16u;
+          d_w[n][l] = {make_desc(sb + nt.w[l][0], lbo, 128), make_desc(sb + nt.w[l][1], lbo, 128)};
+        }
+        wstep12[n] = 2u * (uint32_t)nt.H;  // two k-units of H rows x 16 B, in 16-byte units
+        idesc_h[n] = make_idesc(TM, nt.H);
+      }
+      const uint32_t wstep3 = 2u * (uint32_t)p.ngpt;
+      const uint32_t idesc_o = make_idesc(TM, 32);
+      int mit = 0;
+      for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++mit) {
+        if (lane == 0) dbg_ts(p.dbg, mit, 20);
+        mbar_wait(BAR(BAR_AIN), ph_ain); ph_ain ^= 1u;
+        fence_after();
+        if (lane == 0) dbg_ts(p.dbg, mit, 21);
+        if (elect_one()) {
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            issue_gemm(tmem_base + 64u * n, d_ain, d_w[n][0], wstep12[n], p.kin >> 4, idesc_h[n]);
+            mma_commit(BAR(BAR_HID + n));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) dbg_ts(p.dbg, mit, 22);
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          mbar_wait(BAR(BAR_ACT + n), ph_act[n]); ph_act[n] ^= 1u;
           fence_after();
-          if (l == 0) issue_gemm(tmem_base + col_hid, smem_u32(ain_hi), smem_u32(ain_lo), smem_u32(smem + plan[n].w[0][0]), smem_u32(smem + plan[n].w[0][1]), KIN, H);
-          else issue_gemm(tmem_base + col_hid, smem_u32(act_hi), smem_u32(act_lo), smem_u32(smem + plan[n].w[1][0]), smem_u32(smem + plan[n].w[1][1]), H, H);
-          mma_commit(bar_a);
-        }
-        mbar_wait(bar_a, phase); phase ^= 1;
-        fence_after();
-        // epilogue: bias + activation, split, write the next A operand (16 columns per step)
-        const float* bb = fl + plan[n].b[l];
-        const int cols_per_half = (H >= 32) ? H / 2 : H;
-        if (H >= 32 || half == 0) {
-          for (int c0 = half * cols_per_half; c0 < (half + 1) * cols_per_half && c0 < H; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_row + col_hid + c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = act_apply(net.act[l], v[j] + bb[c0 + j]);
-            store_split8(act_hi, act_lo, unit_off(TM, row, c0 >> 3), v);
-            store_split8(act_hi, act_lo, unit_off(TM, row, (c0 >> 3) + 1), v + 8);
+          if (lane == 0) dbg_ts(p.dbg, mit, 23 + 2 * n);
+          if (elect_one()) {
+            issue_gemm(tmem_base + 64u * n, d_act[n], d_w[n][1], wstep12[n], p.net[n].H >> 4, idesc_h[n]);
+            mma_commit(BAR(BAR_HID + n));
           }
+          __syncwarp();
+          if (lane == 0) dbg_ts(p.dbg, mit, 24 + 2 * n);
         }
-      }
-      // ---------------------------------------------------------------------------- output layer
-      fence_async_smem();
-      fence_before();
-      __syncthreads();
-      if (tid == 0) {
+#pragma unroll
+        for (int n = 0; n < 2; ++n) { mbar_wait(BAR(BAR_ACT + n), ph_act[n]); ph_act[n] ^= 1u; }
         fence_after();
-        issue_gemm(tmem_base + col_out, smem_u32(act_hi), smem_u32(act_lo), smem_u32(smem + plan[n].w[2][0]), smem_u32(smem + plan[n].w[2][1]), H, N);
-        mma_commit(bar_a);
+        if (lane == 0) dbg_ts(p.dbg, mit, 27);
+        for (int c = 0; c < p.nchunks; ++c, ++jc) {
+          const unsigned slot = jc % NSLOT, round = jc / NSLOT;
+          if (round > 0) { mbar_wait(BAR(BAR_SLOT_EMPTY + slot), (round - 1u) & 1u); fence_after(); }
+          if (elect_one()) {
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              // rows [32c, 32c+32) of W3: 8-row groups are 128 B apart -> 512 B = 32 descriptor units per chunk
+              const OperandDesc w3 = {d_w[n][2].hi + (uint64_t)(32u * c), d_w[n][2].lo + (uint64_t)(32u * c)};
+              issue_gemm(tmem_base + RING_COL0 + 64u * slot + 32u * n, d_act[n], w3, wstep3, p.net[n].K3 >> 4, idesc_o);
+            }
+            mma_commit(BAR(BAR_SLOT_FULL + slot));
+          }
+          __syncwarp();
+          if (lane == 0) dbg_ts(p.dbg, mit, 28 + c);
+        }
+        if (elect_one()) {
+          mma_commit(BAR(BAR_ACTFREE + 0));
+          mma_commit(BAR(BAR_ACTFREE + 1));
+        }
+        __syncwarp();
       }
-      mbar_wait(bar_a, phase); phase ^= 1;
-      fence_after();
-      if (MODE == 1 && n == 0) continue;  // SW: the absorption accumulator waits in TMEM for the Rayleigh network
+    }
+  } else {
+    // =================================================================================== EPILOGUE: thread = row
+    // Two groups of four warps (warps 4-7 and 8-11): a warp may only touch the TMEM lanes of quarter warp % 4, so the
+    // groups share the rows and take alternate jobs -- two instruction streams per scheduler to hide each other's stalls.
+    const int q = warp & 3;            // TMEM lane quarter
+    const int eg = (warp - 4) >> 2;    // epilogue group: handles the jobs with jc % 2 == eg
+    const int r = 32 * q + lane;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * q) << 16);
+    uint8_t* stage = smem + p.off_stage + (uint32_t)(warp - 4) * (uint32_t)(p.nstage * STAGE_BYTES);
+    const uint32_t stage_a = smem_u32(stage);
+    const int* band4_s = reinterpret_cast<const int*>(smem + p.off_band4);  // band of each group of 4 g-points
+    const float* tp_s = reinterpret_cast<const float*>(smem + p.off_totplnk);  // totplnk [band][ntemp]
+    const float* b3_0 = reinterpret_cast<const float*>(smem + p.net[0].b[2]);
+    const float* b3_1 = reinterpret_cast<const float*>(smem + p.net[1].b[2]);
+    const bool fold0 = p.net[0].fold != 0, fold1 = p.net[1].fold != 0;
+    int sfc_lev = -1;
+    if (MODE == 0) sfc_lev = (__ldg(p.play) > __ldg(p.play + L - 1)) ? 0 : L;
+    int it = 0;
+    unsigned jc = 0;
+    int sbuf = 0;
+    const unsigned nrows_lay = (unsigned)p.ncol * (unsigned)L;  // rows of tau / lay_source / ssa
 
-      // ---------------------------------------------------------------------------- output epilogue
-      const int nchunks = N >> 5;
-      const int c_begin = half ? (nchunks + 1) / 2 : 0;
-      const int c_end = half ? nchunks : (nchunks + 1) / 2;
-      const long long smp = s0 + row;
-      const bool ok = smp < p.nsamples;
-      const float cd = coldry_s[row];
-      const int fl_ = flag_s[row];
-      const long long col = ok ? smp / L : 0;
-      const int lay = ok ? (int)(smp - col * L) : 0;
-      const float* b3 = fl + plan[n].b[2];
-      for (int ch = c_begin; ch < c_end; ++ch) {
-        const int g0 = 32 * ch;
-        float z[32];
-        tmem_ld32(tmem_row + col_out + g0, z);
-        if (MODE == 1) {
-          // ---- SW: tau_abs (net 0, TMEM columns 0..) and tau_ray (net 1): tau_tot, ssa (mod_network_rrtmgp.F90:209-231)
-          float za[32];
-          tmem_ld32(tmem_row + g0, za);
-          const float* b3a = fl + plan[0].b[2];
-          const float *ysa = fl + plan[0].ystd, *yma = fl + plan[0].ymean, *ysr = fl + plan[1].ystd, *ymr = fl + plan[1].ymean;
+    // Stage one tile of up to 32 rows x 32 g-points and write it with one TMA store.  Every array is a 2-D tensor
+    // [rows][ngpt] whose rows are contiguous across columns, so a tile is one box starting at row `dest`; `slot_row` is
+    // this thread's row inside the staged tile (-1: this row is not part of the array) -- see the LW row numbering.
+    auto stage_and_store = [&](const CUtensorMap* tm, const float (&o)[32], int g0, int slot_row, unsigned dest, unsigned nrows_arr) {
+      if (lane == 0) {  // the staging tile about to be overwritten has been read by its TMA store
+        if (p.nstage == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+      }
+      __syncwarp();
+      if (slot_row >= 0) {
+        uint8_t* row = stage + sbuf * STAGE_BYTES + slot_row * 128;
+        const uint32_t swz = (uint32_t)(slot_row & 7);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = ysa[g0 + j] * (za[j] + b3a[g0 + j]) + yma[g0 + j];
-            a = a * a; a = a * a; a = a * a;
-            a = a * cd;
-            float r = ysr[g0 + j] * (z[j] + b3[g0 + j]) + ymr[g0 + j];
-            r = r * r; r = r * r; r = r * r;
-            r = r * cd;
-            const float tot = a + r;
-            za[j] = tot;
-            z[j] = r / tot;
-          }
-          // tau_tot
-#pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * j) = make_float4(za[4 * j], za[4 * j + 1], za[4 * j + 2], za[4 * j + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + (lane >> 3), cc = (lane & 7) * 4;
-            const long long s2 = s0 + 32 * quarter + rr;
-            if (s2 < p.nsamples) st_stream4(reinterpret_cast<float4*>(p.out0 + s2 * G + g0 + cc), *reinterpret_cast<const float4*>(stage + rr * STAGE_LD + cc));
-          }
-          __syncwarp();
-          // ssa
-#pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * j) = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + (lane >> 3), cc = (lane & 7) * 4;
-            const long long s2 = s0 + 32 * quarter + rr;
-            if (s2 < p.nsamples) {
-              st_stream4(reinterpret_cast<float4*>(p.out1 + s2 * G + g0 + cc), *reinterpret_cast<const float4*>(stage + rr * STAGE_LD + cc));
-              if (p.out2) st_stream4(reinterpret_cast<float4*>(p.out2 + s2 * G + g0 + cc), make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(row + (((uint32_t)j4 ^ swz) << 4)) = make_float4(o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        // a box that starts inside the tensor may hang over its end: those rows are clipped by the TMA unit
+        if (dest < nrows_arr && !(p.dbg_flags & 2)) tma_store_2d(tm, stage_a + sbuf * STAGE_BYTES, g0, (int)dest);
+        bulk_commit();
+      }
+      sbuf = (p.nstage == 2) ? (sbuf ^ 1) : 0;
+    };
+
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const unsigned s0 = tile * TM;
+      const unsigned s = s0 + r;
+      const bool valid = s < p.nrows;
+      const unsigned col = valid ? s / (unsigned)P : 0u;
+      const int lev = valid ? (int)(s - col * (unsigned)P) : 0;
+      // Destination rows of this warp's 32 rows.  SW: row s of the tile is row s of tau / ssa.  LW: rows are numbered
+      // over nlay+1 levels per column, which IS the row number of lev_source; tau and lay_source have nlay rows per
+      // column, so the extra row (lev == nlay; at most one per warp since nlay >= 31) is squeezed out of the staged tile:
+      // rows after it move up by one and the box is 31 rows high (tensor maps tm0s / tm1s).
+      const unsigned w0 = s0 + 32u * q;
+      const unsigned wcol = w0 / (unsigned)P;
+      const int wlev = (int)(w0 - wcol * (unsigned)P);
+      int slot_row = lane;
+      bool squeezed = false;
+      unsigned dest_lay = w0;
+      if (MODE == 0) {
+        const int ph = L - wlev;  // position of the extra row in this warp's 32 rows, if 0 <= ph < 32
+        squeezed = ph < 32 && w0 + (unsigned)ph < p.nrows;
+        if (squeezed) slot_row = (lane == ph) ? -1 : (lane > ph ? lane - 1 : lane);
+        dest_lay = w0 - wcol;
+      }
+      const bool is_sfc = (MODE == 0) && valid && lev == sfc_lev;
+      const float* rec = reinterpret_cast<const float*>(smem + p.off_rec) + (it % p.nrec) * (8 * TM) + r;
+      float cdp = 0.0f, frac_l = 0.0f, frac_v = 0.0f;
+      const float *tp_l = tp_s, *tp_v = tp_s;   // &totplnk[0][idx-1] for T_lay and T_lev of this row
+      PlanckPos ps0{1, 0.0f}, ps1{1, 0.0f};      // T_sfc, T_sfc + 1 (surface row only)
+      bool have_rec = false;
+      for (int c = 0; c < p.nchunks; ++c, ++jc) {
+        if ((int)(jc & 1u) != eg) continue;
+        const unsigned slot = jc % NSLOT, round = jc / NSLOT;
+        const int g0 = 32 * c;
+        if (tid == 128) dbg_ts(p.dbg, it, 40 + 2 * c);
+        mbar_wait(BAR(BAR_SLOT_FULL + slot), round & 1u);
+        fence_after();
+        if (tid == 128) dbg_ts(p.dbg, it, 41 + 2 * c);
+        if (!have_rec) {
+          // the record of this tile was written by the front warps before the MMAs this barrier tracks were issued
+          have_rec = true;
+          cdp = rec[0];
+          if (MODE == 0) {
+            frac_l = rec[1 * TM]; tp_l = tp_s + __float_as_int(rec[2 * TM]) - 1;
+            frac_v = rec[3 * TM]; tp_v = tp_s + __float_as_int(rec[4 * TM]) - 1;
+            if (is_sfc) {
+              const float Ts = rec[5 * TM];
+              ps0 = planck_pos(Ts, p.temp_ref_min, p.totplnk_delta, p.ntemp);
+              ps1 = planck_pos(Ts + 1.0f, p.temp_ref_min, p.totplnk_delta, p.ntemp);
             }
           }
-          __syncwarp();
-        } else if (n == 0) {
-          // ---- LW tau: ((ystd*(z+b)+ymean)**8)*col_dry
-          const float *ys = fl + plan[0].ystd, *ym = fl + plan[0].ymean;
+        }
+        if (tid == 128) dbg_mark(p.dbg, 2, (jc << 8) | 1);
+        float z[64];
+        tmem_ld64(tmem_row + RING_COL0 + 64u * slot, z);
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(BAR_SLOT_EMPTY + slot));
+        if (!fold0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = ys[g0 + j] * (z[j] + b3[g0 + j]) + ym[g0 + j];
-            t = t * t; t = t * t; t = t * t;
-            z[j] = t * cd;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3_0 + g0 + 4 * j4);
+            z[4 * j4] += b.x; z[4 * j4 + 1] += b.y; z[4 * j4 + 2] += b.z; z[4 * j4 + 3] += b.w;
           }
+        }
+        if (!fold1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * j) = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + (lane >> 3), cc = (lane & 7) * 4;
-            const long long s2 = s0 + 32 * quarter + rr;
-            if (s2 < p.nsamples) st_stream4(reinterpret_cast<float4*>(p.out0 + s2 * G + g0 + cc), *reinterpret_cast<const float4*>(stage + rr * STAGE_LD + cc));
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(b3_1 + g0 + 4 * j4);
+            z[32 + 4 * j4] += b.x; z[32 + 4 * j4 + 1] += b.y; z[32 + 4 * j4 + 2] += b.z; z[32 + 4 * j4 + 3] += b.w;
           }
-          __syncwarp();
-        } else {
-          // ---- LW Planck fraction -> lay_source, lev_source (+ bottom level, surface source) : compute_Planck_source_nn
-          const int lact = net.act[2];
+        }
+        float o[32];
+        if (MODE == 0) {
+          // ---- tau = ((ystd*(z+b)+ymean)**8)*col_dry (mod_network_rrtmgp.F90:209-222); z here is 2^10 x that bracket
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float zz = act_apply(lact, z[j] + b3[g0 + j]);
-            z[j] = zz * zz;  // Planck fraction (:309-312)
+          for (int j = 0; j < 32; j += 2) {
+            float t0 = z[j], t1 = z[j + 1];
+            mul2(t0, t1, t0, t1); mul2(t0, t1, t0, t1); mul2(t0, t1, t0, t1);
+            mul2(t0, t1, cdp, cdp);
+            o[j] = t0; o[j + 1] = t1;
           }
-          // stage z[j] * B_band(T) for this thread's row; band changes are warp-uniform (same column for all lanes)
-          auto stage_scaled = [&](float T, float dT) {
-            int cur_band = -1;
-            float bv = 0.0f;
+          stage_and_store(squeezed ? &tm0s : &tm0, o, g0, slot_row, dest_lay, nrows_lay);
+          // ---- Planck fraction (:309-312) -> lay_source, lev_source (compute_Planck_source_nn, interpolate1D); every
+          //      group of 4 g-points lies in one band (checked on the host), bands change rarely along g
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) mul2(z[32 + j], z[33 + j], z[32 + j], z[33 + j]);
+          int b4[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) b4[j4] = band4_s[(g0 >> 2) + j4];
+          float bl = 0.0f, bv = 0.0f;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (j4 == 0 || b4[j4] != b4[j4 - 1]) {  // warp-uniform
+              const float* t = tp_l + b4[j4] * p.ntemp;
+              const float t0 = t[0];
+              bl = t0 + frac_l * (t[1] - t0);
+            }
+            mul2to(o[4 * j4], o[4 * j4 + 1], z[32 + 4 * j4], z[33 + 4 * j4], bl);
+            mul2to(o[4 * j4 + 2], o[4 * j4 + 3], z[34 + 4 * j4], z[35 + 4 * j4], bl);
+          }
+          stage_and_store(squeezed ? &tm1s : &tm1, o, g0, slot_row, dest_lay, nrows_lay);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (j4 == 0 || b4[j4] != b4[j4 - 1]) {
+              const float* t = tp_v + b4[j4] * p.ntemp;
+              const float t0 = t[0];
+              bv = t0 + frac_v * (t[1] - t0);
+            }
+            mul2to(o[4 * j4], o[4 * j4 + 1], z[32 + 4 * j4], z[33 + 4 * j4], bv);
+            mul2to(o[4 * j4 + 2], o[4 * j4 + 3], z[34 + 4 * j4], z[35 + 4 * j4], bv);
+          }
+          stage_and_store(&tm2, o, g0, lane, w0, p.nrows);
+          if (is_sfc) {  // surface source and its Jacobian: one row per column, written by the owning lane
+            float* ss = p.sfc_source + (size_t)col * G + g0;
+            float* sj = p.sfc_jac + (size_t)col * G + g0;
+            float b0 = 0.0f, bj = 0.0f;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              float o[4];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int bnd = band_s[g0 + 4 * j4 + c];
-                if (bnd != cur_band) {
-                  cur_band = bnd;
-                  const float* tab = p.totplnk + (size_t)bnd * p.ntemp;
-                  bv = planck_interp(T, p.temp_ref_min, p.totplnk_delta, tab, p.ntemp);
-                  if (dT != 0.0f) bv = planck_interp(T + dT, p.temp_ref_min, p.totplnk_delta, tab, p.ntemp) - bv;
-                }
-                o[c] = z[4 * j4 + c] * bv;
+              if (j4 == 0 || b4[j4] != b4[j4 - 1]) {
+                const float* t = tp_s + b4[j4] * p.ntemp;
+                const float u0 = t[ps0.idx - 1], u1 = t[ps1.idx - 1];
+                b0 = u0 + ps0.frac * (t[ps0.idx] - u0);
+                bj = (u1 + ps1.frac * (t[ps1.idx] - u1)) - b0;
               }
-              *reinterpret_cast<float4*>(stage + lane * STAGE_LD + 4 * j4) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(ss + 4 * j4) = make_float4(z[32 + 4 * j4] * b0, z[33 + 4 * j4] * b0, z[34 + 4 * j4] * b0, z[35 + 4 * j4] * b0);
+              *reinterpret_cast<float4*>(sj + 4 * j4) = make_float4(z[32 + 4 * j4] * bj, z[33 + 4 * j4] * bj, z[34 + 4 * j4] * bj, z[35 + 4 * j4] * bj);
             }
-          };
-          auto copy_own_row = [&](float* dst) {  // rare rows (bottom level, surface): this thread's staged row -> dst
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(dst + 4 * j4) = *reinterpret_cast<const float4*>(stage + lane * STAGE_LD + 4 * j4);
-          };
-          const float t_lay = ok ? p.tlay[smp] : 200.0f;
-          const float t_lev = ok ? p.tlev[col * (L + 1) + lay] : 200.0f;
-          // lay_source
-          stage_scaled(t_lay, 0.0f);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + (lane >> 3), cc = (lane & 7) * 4;
-            const long long s2 = s0 + 32 * quarter + rr;
-            if (s2 < p.nsamples) st_stream4(reinterpret_cast<float4*>(p.out1 + s2 * G + g0 + cc), *reinterpret_cast<const float4*>(stage + rr * STAGE_LD + cc));
           }
-          __syncwarp();
-          // lev_source (rows col*(L+1)+lay)
-          stage_scaled(t_lev, 0.0f);
-          __syncwarp();
+        } else {
+          // ---- SW: tau_abs (net 0), tau_ray (net 1): tau = abs + ray, ssa = ray / tau (mod_network_rrtmgp.F90:209-231)
+          float w[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = 4 * j + (lane >> 3), cc = (lane & 7) * 4;
-            const int lr = levrow_s[32 * quarter + rr];
-            if (lr >= 0) st_stream4(reinterpret_cast<float4*>(p.out2 + (size_t)lr * G + g0 + cc), *reinterpret_cast<const float4*>(stage + rr * STAGE_LD + cc));
+          for (int j = 0; j < 32; j += 2) {
+            float a0 = z[j], a1 = z[j + 1], r0 = z[32 + j], r1 = z[33 + j];
+            mul2(a0, a1, a0, a1); mul2(a0, a1, a0, a1); mul2(a0, a1, a0, a1); mul2(a0, a1, cdp, cdp);
+            mul2(r0, r1, r0, r1); mul2(r0, r1, r0, r1); mul2(r0, r1, r0, r1); mul2(r0, r1, cdp, cdp);
+            z[j] = a0; z[j + 1] = a1; z[32 + j] = r0; z[33 + j] = r1;
           }
-          __syncwarp();
-          // the bottom level and the surface terms belong to one sample per column: handled by the owning lane
-          if (__any_sync(0xffffffffu, ok && fl_ != 0)) {
-            if (ok && (fl_ & 1)) { stage_scaled(p.tlev[col * (L + 1) + L], 0.0f); copy_own_row(p.out2 + ((size_t)col * (L + 1) + L) * G + g0); }
-            __syncwarp();
-            if (ok && (fl_ & 2)) { stage_scaled(p.tsfc[col], 0.0f); copy_own_row(p.sfc_source + (size_t)col * G + g0); }
-            __syncwarp();
-            if (ok && (fl_ & 2)) { stage_scaled(p.tsfc[col], 1.0f); copy_own_row(p.sfc_jac + (size_t)col * G + g0); }
-            __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float ry = z[32 + j];
+            const float tot = z[j] + ry;
+            o[j] = tot;
+            // ray / tot: reciprocal seed + two residual corrections (correctly rounded but for rare ties; no branches);
+            // no zero guard, as the reference (quirk Q2): 0/0 gives NaN here too
+            const float rc = rcp_approx(tot);
+            float qd = ry * rc;
+            qd = fmaf(fmaf(-tot, qd, ry), rc, qd);
+            w[j] = fmaf(fmaf(-tot, qd, ry), rc, qd);
           }
+          stage_and_store(&tm0, o, g0, lane, w0, nrows_lay);
+          stage_and_store(&tm1, w, g0, lane, w0, nrows_lay);
         }
       }
     }
-    // all TMEM reads and operand buffers of this tile are done before the next tile's prologue overwrites them
-    fence_before();
-    __syncthreads();
-    fence_after();
+    if (lane == 0) bulk_wait_all();
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// pack one layer W (row-major [K][O] fp32) into the canonical K-major layout of the B operand: rows = outputs
-// (padded to OP), K padded to KP; hi block then lo block.
-static void pack_layer(const float* W, int K, int O, int KP, int OP, std::vector<uint8_t>& out) {
+// pack one layer W (row-major [K][O] fp32, scaled per output) into the canonical K-major layout of the B operand:
+// rows = outputs (padded to OP), K padded to KP; hi block then lo block.  bias_k >= 0 puts bias[o] on that k.
+static void pack_layer(const float* W, int K, int O, int KP, int OP, const double* oscale, int bias_k, const double* bias,
+                       std::vector<uint8_t>& out, uint32_t& off_hi, uint32_t& off_lo) {
   const size_t base = out.size();
   out.resize(base + (size_t)2 * OP * KP * 2, 0);
-  __half* hi = reinterpret_cast<__half*>(out.data() + base);
-  __half* lo = hi + (size_t)OP * KP;
+  off_hi = (uint32_t)base;
+  off_lo = (uint32_t)(base + (size_t)OP * KP * 2);
+  __half* hi = reinterpret_cast<__half*>(out.data() + off_hi);
+  __half* lo = reinterpret_cast<__half*>(out.data() + off_lo);
   for (int o = 0; o < OP; ++o)
     for (int k = 0; k < KP; ++k) {
-      const float w = (o < O && k < K) ? W[(size_t)k * O + o] : 0.0f;
+      double wd = 0.0;
+      if (o < O && k < K) wd = (double)W[(size_t)k * O + o] * (oscale ? oscale[o] : 1.0);
+      else if (o < O && k == bias_k) wd = bias[o];
+      const float w = (float)wd;
       const __half h = __float2half_rn(w);
       const __half l = __float2half_rn(w - __half2float(h));
       const size_t idx = ((size_t)(k >> 3) * (OP * 16) + (o >> 3) * 128 + (o & 7) * 16 + (k & 7) * 2) / 2;
@@ -543,41 +801,181 @@ static void pack_layer(const float* W, int K, int O, int KP, int OP, std::vector
     }
 }
 
+struct HostPlan {
+  Params p;
+  std::vector<uint8_t> blob;
+  size_t smem = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(f);
+  return fn;
+}
+// [rows][ngpt] fp32 tensor, box 32 g-points x box_rows rows, 128-byte swizzle
+static int make_map(CUtensorMap* tm, float* base, int G, unsigned long long rows, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail("gas_optics (tensor cores): cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)G * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("gas_optics (tensor cores): cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
 }  // namespace tc
 }  // namespace rrnn
 
 using namespace rrnn;
 
+static int pad16(int n) { return (n + 15) & ~15; }
+
 // Is this pair of networks supported by the tensor-core kernel?
-static bool tc_supported(const rrnn_model_t* const* models, int nmodels, int ngpt) {
-  if (nmodels != 2) return false;
+static bool tc_supported(const rrnn_model_t* const* models, const rrnn_kdist_t* kd, int mode) {
+  const int ngpt = kd->ngpt;
   if (ngpt % 32 != 0 || ngpt > 256) return false;
+  if (mode == 0 && (kd->nbnd > 16 || kd->nbnd < 1)) return false;
   for (int n = 0; n < 2; ++n) {
     const rrnn_model_t* m = models[n];
     if (!m || m->nlayers != 3) return false;
-    if (m->dims[0] > tc::KIN || m->dims[1] > 64 || m->dims[2] != m->dims[1] || m->dims[3] != ngpt) return false;
+    if (m->dims[0] > tc::KIN_MAX || m->dims[0] < 4 || m->dims[1] > 64 || m->dims[2] != m->dims[1] || m->dims[3] != ngpt) return false;
+    if (m->act[2] != RRNN_ACT_LINEAR) return false;
   }
-  return models[0]->dims[0] == models[1]->dims[0];
+  if (models[0]->dims[0] != models[1]->dims[0]) return false;
+  if (models[0]->ymean.empty() || models[0]->ystd.empty()) return false;
+  if (mode == 1 && (models[1]->ymean.empty() || models[1]->ystd.empty())) return false;
+  return true;
 }
 
-static int tc_prepare(rrnn_model_t* m) {
-  if (m->d_tc_w) return 0;
-  const int nx = m->dims[0], Hraw = m->dims[1], N = m->dims[3];
-  const int H = Hraw <= 16 ? 16 : (Hraw <= 32 ? 32 : 64);
-  std::vector<uint8_t> pack;
-  tc::pack_layer(m->wpack.data() + m->w_off[0], nx, Hraw, tc::KIN, H, pack);
-  tc::pack_layer(m->wpack.data() + m->w_off[1], Hraw, Hraw, H, H, pack);
-  tc::pack_layer(m->wpack.data() + m->w_off[2], Hraw, N, H, N, pack);
-  std::vector<float> b((size_t)2 * H + N, 0.0f);
-  for (int i = 0; i < Hraw; ++i) { b[i] = m->bpack[m->b_off[0] + i]; b[H + i] = m->bpack[m->b_off[1] + i]; }
-  for (int i = 0; i < N; ++i) b[2 * H + i] = m->bpack[m->b_off[2] + i];
-  RRNN_CUDA(cudaMalloc((void**)&m->d_tc_w, pack.size()));
-  RRNN_CUDA(cudaMemcpy(m->d_tc_w, pack.data(), pack.size(), cudaMemcpyHostToDevice));
-  RRNN_CUDA(cudaMalloc((void**)&m->d_tc_b, b.size() * sizeof(float)));
-  RRNN_CUDA(cudaMemcpy(m->d_tc_b, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
-  m->tc_w_bytes = (int)pack.size();
-  m->tc_H = H;
-  return 0;
+// Build the shared-memory image (weights, biases, band tables) and the layout; cached per (model pair, kdist, mode).
+struct TcCache {
+  unsigned long long m0 = 0, m1 = 0, kd = 0;  // uids
+  int mode = -1, device = -1;
+  tc::Params p{};
+  size_t smem = 0;
+  uint8_t* d_blob = nullptr;
+};
+static std::vector<TcCache> g_tc_cache;
+static std::mutex g_tc_mutex;
+
+// returns 0 and a copy of the plan, -1 if the pair does not fit the kernel's shared-memory design, > 0 on error
+static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, TcCache* out) {
+  std::lock_guard<std::mutex> lock(g_tc_mutex);
+  for (auto& c : g_tc_cache)
+    if (c.m0 == models[0]->uid && c.m1 == models[1]->uid && c.kd == kd->uid && c.mode == mode && c.device == ctx->device) { *out = c; return 0; }
+  const int G = kd->ngpt;
+  const int nx = models[0]->dims[0];
+  const int kin = pad16(nx);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    TcCache c;
+    c.m0 = models[0]->uid; c.m1 = models[1]->uid; c.kd = kd->uid; c.mode = mode; c.device = ctx->device;
+    tc::Params& p = c.p;
+    std::vector<uint8_t> blob;
+    for (int n = 0; n < 2; ++n) {
+      const rrnn_model_t* m = models[n];
+      tc::NetP& nt = p.net[n];
+      const int Hraw = m->dims[1];
+      nt.Hraw = Hraw; nt.H = pad16(Hraw); nt.ntot = G;
+      nt.act0 = m->act[0]; nt.act1 = m->act[1];
+      // bias of the output layer on a column of ones: free when the padded K has a spare column, otherwise one more
+      // k-step (first attempt) or not at all (second attempt, when shared memory is short)
+      nt.fold = (Hraw < nt.H) ? 1 : (attempt == 0 ? 1 : 0);
+      nt.K3 = (nt.fold && Hraw >= nt.H) ? nt.H + 16 : nt.H;
+      const bool tau_type = (mode == 1) || (n == 0);
+      std::vector<double> oscale(G, 1.0), bias(G, 0.0);
+      for (int o = 0; o < G; ++o) {
+        const double b3 = m->bpack[m->b_off[2] + o];
+        if (tau_type) {
+          oscale[o] = (double)m->ystd[o] * tc::OUT_SCALE;
+          bias[o] = ((double)m->ystd[o] * b3 + (double)m->ymean[o]) * tc::OUT_SCALE;
+        } else {
+          bias[o] = b3;
+        }
+      }
+      tc::pack_layer(m->wpack.data() + m->w_off[0], nx, Hraw, kin, nt.H, nullptr, -1, nullptr, blob, nt.w[0][0], nt.w[0][1]);
+      tc::pack_layer(m->wpack.data() + m->w_off[1], Hraw, Hraw, nt.H, nt.H, nullptr, -1, nullptr, blob, nt.w[1][0], nt.w[1][1]);
+      tc::pack_layer(m->wpack.data() + m->w_off[2], Hraw, G, nt.K3, G, oscale.data(), nt.fold ? Hraw : -1, bias.data(), blob,
+                     nt.w[2][0], nt.w[2][1]);
+      // fp32 biases: b1[H], b2[H], b3''[G]
+      const size_t fb = blob.size();
+      blob.resize(fb + (size_t)(2 * nt.H + G) * 4, 0);
+      float* f = reinterpret_cast<float*>(blob.data() + fb);
+      for (int i = 0; i < Hraw; ++i) { f[i] = m->bpack[m->b_off[0] + i]; f[nt.H + i] = m->bpack[m->b_off[1] + i]; }
+      for (int o = 0; o < G; ++o) f[2 * nt.H + o] = (float)bias[o];
+      nt.b[0] = (uint32_t)fb; nt.b[1] = (uint32_t)(fb + nt.H * 4); nt.b[2] = (uint32_t)(fb + 2 * nt.H * 4);
+    }
+    // band of every group of 4 g-points (the kernel multiplies 4 g-points by one Planck value: mixed groups -> fallback)
+    p.off_band4 = (uint32_t)blob.size();
+    blob.resize(blob.size() + 64 * 4, 0);
+    {
+      int* band4 = reinterpret_cast<int*>(blob.data() + p.off_band4);
+      for (int g4 = 0; g4 < G / 4; ++g4) {
+        const int b = kd->gpt2band.empty() ? 0 : kd->gpt2band[4 * g4];
+        if (mode == 0)
+          for (int e = 1; e < 4; ++e)
+            if (kd->gpt2band[4 * g4 + e] != b) return -1;
+        band4[g4] = b;
+      }
+    }
+    // LW: the Planck table totplnk [band][ntemp] rides in the image too
+    p.off_totplnk = (uint32_t)blob.size();
+    if (mode == 0) {
+      blob.resize(blob.size() + (((size_t)kd->nbnd * kd->ntemp * 4 + 15) & ~(size_t)15), 0);
+      memcpy(blob.data() + p.off_totplnk, kd->totplnk.data(), (size_t)kd->nbnd * kd->ntemp * 4);
+    }
+    p.blob_bytes = (uint32_t)blob.size();
+    uint32_t off = (p.blob_bytes + 127u) & ~127u;
+    p.off_ain_hi = off; off += tc::TM * kin * 2;
+    p.off_ain_lo = off; off += tc::TM * kin * 2;
+    for (int n = 0; n < 2; ++n) {
+      p.net[n].act_hi = off; off += tc::TM * p.net[n].K3 * 2;
+      p.net[n].act_lo = off; off += tc::TM * p.net[n].K3 * 2;
+    }
+    off = (off + 1023u) & ~1023u;
+    p.off_stage = off;
+    const uint32_t off_stage_end2 = off + 8 * 2 * tc::STAGE_BYTES;  // 8 epilogue warps x 2 staging tiles, if they fit
+    p.nstage = 2; off = off_stage_end2;
+    // Per-row records, a ring over tiles.  The front warps start tile t+2 only after every output-layer MMA of tile t
+    // has been issued, i.e. when the epilogue (either group) is at most NSLOT jobs short of the end of tile t, which is
+    // at most ceil(NSLOT/nchunks) tiles back.
+    const int nchunks = G / 32;
+    p.nrec = (tc::NSLOT + nchunks - 1) / nchunks + 2;
+    p.off_rec = off; off += (uint32_t)p.nrec * 8 * tc::TM * 4;
+    p.off_bar = off; off += tc::NBAR * 8 + 16;
+    c.smem = (size_t)off + 1024;  // alignment slack
+    if (c.smem > ctx->smem_optin) {  // one staging tile per warp instead of two
+      const uint32_t shrink = 8 * tc::STAGE_BYTES;
+      p.nstage = 1; p.off_rec -= shrink; p.off_bar -= shrink; c.smem -= shrink;
+    }
+    if (c.smem > ctx->smem_optin) {
+      if (attempt == 0) continue;
+      return -1;
+    }
+    p.kin = kin; p.nx = nx; p.ngpt = G; p.nchunks = G / 32;
+    p.nbnd = kd->nbnd; p.ntemp = kd->ntemp;
+    RRNN_CUDA(cudaMalloc((void**)&c.d_blob, blob.size()));
+    RRNN_CUDA(cudaMemcpy(c.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    p.blob = c.d_blob;
+    if (g_tc_cache.size() >= 32) {  // bounded: drop the oldest plan
+      cudaFree(g_tc_cache.front().d_blob);
+      g_tc_cache.erase(g_tc_cache.begin());
+    }
+    g_tc_cache.push_back(c);
+    *out = c;
+    return 0;
+  }
+  return -1;
 }
 
 // Launch the tensor-core gas optics; returns -1 if the configuration is not supported (caller falls back).
@@ -585,60 +983,106 @@ int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const 
                        const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
                        const rrnn_gas_t* gases, int ngas, float* out0, float* out1, float* out2, float* sfc_source,
                        float* sfc_jac, int prof_kind) {
-  if (!tc_supported(models, 2, kd->ngpt)) return -1;
-  if (mode == 1 && models[0]->dims[3] + (models[1]->dims[1] <= 16 ? 16 : (models[1]->dims[1] <= 32 ? 32 : 64)) > 256) return -1;
-  tc::Params p{};
+  if (!tc_supported(models, kd, mode)) return -1;
+  const int period = (mode == 0) ? nlay + 1 : nlay;
+  if (mode == 0 && nlay < 31) return -1;  // at most one extra (bottom-level) row per warp of 32 rows
+  if ((long long)ncol * period >= (1LL << 31) - tc::TM) return -1;
+  TcCache cache;
   {
-    // reuse the by-name gas mapping of the FFMA path through a scratch GoParams-compatible view
-    const rrnn_model_t* m = models[0];
-    const int nx = m->dims[0];
-    p.nx = nx;
-    for (int i = 0; i < tc::KIN; ++i) { p.gas[i].ptr = nullptr; p.gas[i].value = 0.f; p.gas[i].mode = -1; p.xmin[i] = 0.f; p.xmax[i] = 1.f; }
-    for (int i = 0; i < nx; ++i) {
-      p.xmin[i] = m->xmin[i]; p.xmax[i] = m->xmax[i];
-      if (i < 2) continue;
-      for (int g = 0; g < ngas; ++g) {
-        std::string nm(gases[g].name, strnlen(gases[g].name, 32));
-        while (!nm.empty() && (nm.back() == ' ' || nm.back() == '\0')) nm.pop_back();
-        if (nm == m->input_names[i]) {
-          if (gases[g].ndims < 0 || gases[g].ndims > 2) return fail("gas_concs: ndims must be 0, 1 or 2");
-          if (gases[g].ndims > 0 && !gases[g].conc) return fail("gas_concs: null concentration pointer");
-          p.gas[i].ptr = gases[g].conc; p.gas[i].value = gases[g].value; p.gas[i].mode = gases[g].ndims;
-          break;
-        }
-      }
-      if (i < 4 && p.gas[i].mode < 0) return fail(std::string("compute_nn_inputs: gas ") + m->input_names[i] + " is required but was not provided");
+    const int rc = tc_plan(ctx, mode, kd, models, &cache);
+    if (rc != 0) return rc;
+  }
+  tc::Params p = cache.p;
+  const rrnn_model_t* m = models[0];
+  const int nx = m->dims[0];
+  // map ty_gas_concs entries onto the network's inputs BY NAME (compute_nn_inputs :708-760)
+  for (int i = 0; i < tc::KIN_MAX; ++i) { p.gas[i].ptr = nullptr; p.gas[i].mode = 0; p.xmin[i] = 0.f; p.xmax[i] = 1.f; p.xconst[i] = 0.f; p.xvar[i] = 0; }
+  p.h2o_const = 0.0f;
+  for (int i = 0; i < nx; ++i) {
+    p.xmin[i] = m->xmin[i]; p.xmax[i] = m->xmax[i];
+    if (i < 2) { p.xvar[i] = 1; continue; }
+    int found = -1;
+    for (int g = 0; g < ngas; ++g) {
+      std::string nm(gases[g].name, strnlen(gases[g].name, 32));
+      while (!nm.empty() && (nm.back() == ' ' || nm.back() == '\0')) nm.pop_back();
+      size_t b = 0;
+      while (b < nm.size() && nm[b] == ' ') ++b;
+      if (nm.substr(b) == m->input_names[i]) { found = g; break; }
+    }
+    if (found < 0) {
+      if (i < 4) return fail(std::string("compute_nn_inputs: gas ") + m->input_names[i] + " is required but was not provided");
+      p.xconst[i] = (0.0f - p.xmin[i]) / (p.xmax[i] - p.xmin[i]);  // missing gas: vmr 0 (:757-759)
+      continue;
+    }
+    const rrnn_gas_t& gs = gases[found];
+    if (gs.ndims < 0 || gs.ndims > 2) return fail("gas_concs: ndims must be 0, 1 or 2");
+    if (gs.ndims > 0 && !gs.conc) return fail("gas_concs: null concentration pointer");
+    if (gs.ndims == 0) {
+      float raw = gs.value;
+      if (i == 2) p.h2o_const = raw;
+      if (i == 2 || i == 3) raw = sqrtf(sqrtf(raw));
+      p.xconst[i] = (raw - p.xmin[i]) / (p.xmax[i] - p.xmin[i]);
+    } else {
+      p.xvar[i] = 1; p.gas[i].ptr = gs.conc; p.gas[i].mode = gs.ndims;
     }
   }
-  size_t smem = 0;
-  for (int n = 0; n < 2; ++n) {
-    rrnn_model_t* m = const_cast<rrnn_model_t*>(models[n]);
-    if (int rc = tc_prepare(m)) return rc;
-    p.net[n].H = m->tc_H; p.net[n].N = m->dims[3];
-    for (int l = 0; l < 3; ++l) p.net[n].act[l] = m->act[l];
-    p.net[n].w_bytes = m->tc_w_bytes; p.net[n].w = (const uint8_t*)m->d_tc_w; p.net[n].b = m->d_tc_b;
-    p.net[n].ymean = m->d_ymean; p.net[n].ystd = m->d_ystd;
-    smem += m->tc_w_bytes + (size_t)(2 * m->tc_H + 3 * m->dims[3]) * 4;
-  }
-  smem += 2 * tc::TM * tc::KIN * 2 + 2 * tc::TM * 64 * 2 + 8 * 32 * tc::STAGE_LD * 4 + 3 * tc::TM * 4 + 256 * 4 + 16;
-  smem += 1024;  // alignment slack
-  if (smem > ctx->smem_optin) return -1;
-  p.mode = mode; p.ncol = ncol; p.nlay = nlay; p.ngpt = kd->ngpt; p.nsamples = (long long)ncol * nlay;
+  p.ncol = ncol; p.nlay = nlay; p.period = period; p.nrows = (unsigned)((long long)ncol * period);
   p.play = play; p.plev = plev; p.tlay = tlay; p.tlev = tlev; p.tsfc = tsfc;
-  p.nbnd = kd->nbnd; p.ntemp = kd->ntemp; p.gpt2band = kd->d_gpt2band; p.totplnk = kd->d_totplnk;
-  p.temp_ref_min = kd->temp_ref_min; p.totplnk_delta = kd->totplnk_delta;
-  p.out0 = out0; p.out1 = out1; p.out2 = out2; p.sfc_source = sfc_source; p.sfc_jac = sfc_jac;
-  const long long ntiles = (p.nsamples + tc::TM - 1) / tc::TM;
-  const unsigned grid = (unsigned)std::min<long long>(ntiles, ctx->num_sms);
+  p.totplnk = kd->d_totplnk; p.temp_ref_min = kd->temp_ref_min; p.totplnk_delta = kd->totplnk_delta;
+  p.sfc_source = sfc_source; p.sfc_jac = sfc_jac;
+  CUtensorMap tm0, tm1, tm2, tm0s, tm1s;
+  const unsigned long long nrows_lay = (unsigned long long)ncol * nlay;
+  if (int rc = tc::make_map(&tm0, out0, kd->ngpt, nrows_lay, 32)) return rc;
+  if (int rc = tc::make_map(&tm1, out1, kd->ngpt, nrows_lay, 32)) return rc;
+  if (mode == 0) {
+    if (int rc = tc::make_map(&tm2, out2, kd->ngpt, (unsigned long long)ncol * (nlay + 1), 32)) return rc;
+    if (int rc = tc::make_map(&tm0s, out0, kd->ngpt, nrows_lay, 31)) return rc;
+    if (int rc = tc::make_map(&tm1s, out1, kd->ngpt, nrows_lay, 31)) return rc;
+  } else {
+    tm2 = tm1; tm0s = tm0; tm1s = tm1;
+  }
+  if (mode == 1 && out2)  // g is identically zero on the NN path (mo_gas_optics_rrtmgp.F90:560-567)
+    RRNN_CUDA(cudaMemsetAsync(out2, 0, (size_t)ncol * nlay * kd->ngpt * sizeof(float), ctx->stream));
+  const unsigned ntiles = (p.nrows + tc::TM - 1) / tc::TM;
+  const unsigned grid = std::min<unsigned>(ntiles, (unsigned)ctx->num_sms);
+  static unsigned* dbg_host = nullptr;
+  const char* dbg_env = getenv("RRNN_TC_DEBUG");
+  const int dbg_flags = dbg_env ? atoi(dbg_env) : 0;
+  p.dbg = nullptr; p.dbg_flags = dbg_flags;
+  if (dbg_flags) {
+    if (!dbg_host) RRNN_CUDA(cudaHostAlloc((void**)&dbg_host, 128 * sizeof(unsigned), cudaHostAllocMapped));
+    memset(dbg_host, 0, 128 * sizeof(unsigned));
+    unsigned* dptr = nullptr;
+    RRNN_CUDA(cudaHostGetDevicePointer((void**)&dptr, dbg_host, 0));
+    p.dbg = dptr;
+  }
   const int ps = prof_begin(ctx, prof_kind);
   if (mode == 0) {
-    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::gas_optics_tc_kernel<0><<<grid, tc::THREADS, smem, ctx->stream>>>(p);
+    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache.smem));
+    tc::gas_optics_tc_kernel<0><<<grid, tc::THREADS, cache.smem, ctx->stream>>>(p, tm0, tm1, tm2, tm0s, tm1s);
   } else {
-    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::gas_optics_tc_kernel<1><<<grid, tc::THREADS, smem, ctx->stream>>>(p);
+    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache.smem));
+    tc::gas_optics_tc_kernel<1><<<grid, tc::THREADS, cache.smem, ctx->stream>>>(p, tm0, tm1, tm2, tm0s, tm1s);
   }
   prof_end(ctx, prof_kind, ps);
   RRNN_LAUNCH_CHECK(ctx);
+  if (dbg_flags) {
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    fprintf(stderr, "[tc debug] mode %d ncol %d nlay %d grid %u smem %zu -> %s | front %08x mma %08x epi %08x store %08x | wd %08x bar %08x par %u blk %u | init %08x\n",
+            mode, ncol, nlay, grid, cache.smem, cudaGetErrorString(e), dbg_host[0], dbg_host[1], dbg_host[2], dbg_host[3], dbg_host[16],
+            dbg_host[17], dbg_host[18], dbg_host[19], dbg_host[15]);
+    if (dbg_flags & 8) {  // timeline of tile 5 of block 0, SM cycles relative to the front warps' start of that tile
+      const unsigned t0 = dbg_host[32];
+      static const char* names[60] = {"F prologue start", "F AIN arrive", "F L1n0 free ok", "F L1n0 hid ok", "F L1n0 act arrive", "F L1n1 free ok",
+        "F L1n1 hid ok", "F L1n1 act arrive", "F L2n0 -", "F L2n0 hid ok", "F L2n0 act arrive", "F L2n1 -", "F L2n1 hid ok", "F L2n1 act arrive",
+        "", "", "", "", "", "", "M loop top", "M AIN ok", "M L1 issued", "M act0 ok", "M L2n0 issued", "M act1 ok", "M L2n1 issued", "M act(2) ok",
+        "M job0 issued", "M job1 issued", "M job2 issued", "M job3 issued", "M job4 issued", "M job5 issued", "M job6 issued", "M job7 issued",
+        "", "", "", "", "E job0 wait", "E job0 go", "E job1 wait", "E job1 go", "E job2 wait", "E job2 go", "E job3 wait", "E job3 go", "E job4 wait",
+        "E job4 go", "E job5 wait", "E job5 go", "E job6 wait", "E job6 go", "E job7 wait", "E job7 go", "", "", "", ""};
+      for (int i = 0; i < 60; ++i)
+        if (dbg_host[32 + i]) fprintf(stderr, "  [tl] %-20s %8d\n", names[i], (int)(dbg_host[32 + i] - t0));
+    }
+    if (e != cudaSuccess) return fail(std::string("gas_optics (tensor cores): ") + cudaGetErrorString(e));
+  }
   return 0;
 }
