@@ -54,7 +54,7 @@ struct rrnn_ctx {
   int solver_buffer = 0;   // reverse-sweep buffer: 0 auto, 1 shared memory, 2 L2-resident global scratch
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
-  int nn_tensor_cores = 0; // MLP variant: 0 = fp32 FFMA, 1 = tcgen05 3xTF32
+  int nn_tensor_cores = 1; // MLP variant: 1 = tcgen05 (fp16 hi/lo split operands, fp32 accumulation; default), 0 = fp32 FFMA
   int chunk_columns = 0;
   // persistent workspace for the whole-path drivers
   void* ws = nullptr;

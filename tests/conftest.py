@@ -20,3 +20,13 @@ def gpu_ctx():
         pytest.skip("no CUDA device")
     from rte_rrtmgp_nn_b200 import api
     return api.default_context(0)
+
+
+@pytest.fixture(params=[1, 0], ids=["tensor_cores", "fp32_ffma"])
+def nn_variant(request, gpu_ctx):
+    """Both MLP variants of the NN gas optics: tcgen05 tensor cores (the default) and the fp32 FFMA kernel, each with
+    the tau tolerance stated for it (helpers.TAU_RTOL_*)."""
+    import helpers as H
+    gpu_ctx.set_flag("nn_tensor_cores", request.param)
+    yield (H.TAU_RTOL_TC if request.param else H.TAU_RTOL_FP32)
+    gpu_ctx.set_flag("nn_tensor_cores", 1)

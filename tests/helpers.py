@@ -17,11 +17,13 @@ SW_G112 = ("sw-g112-210809_absorption_BEST.nc", "sw-g112-210809_rayleigh_BEST.nc
 # tolerances stated by BASELINE.json north_star
 FLUX_TOL = 0.01      # W m-2, every level
 HR_TOL = 1.0e-3      # K day-1
-# tau: 1e-4 relative on the fp32 path (north_star); the tensor-core path (fp16 hi/lo split operands, fp32 accumulation in
-# TMEM, RRNN_NN_TENSOR_CORES=1) is stated separately, as north_star allows: 5e-4 with the same floor -- the fluxes and
-# heating rates must still meet the same tolerances as the fp32 path.
-TENSOR_CORES = os.environ.get("RRNN_NN_TENSOR_CORES", "0") == "1"
-TAU_RTOL = 5.0e-4 if TENSOR_CORES else 1.0e-4
+# tau: 1e-4 relative on the fp32 path (north_star; context flag nn_tensor_cores = 0, the FFMA kernel).  The tensor-core
+# path (the default: fp16 hi/lo split operands, fp32 accumulation in TMEM) is stated separately, as north_star allows:
+# 4e-4 with the same floor (measured: 1.5e-4 against the oracle, 3e-4 against the FFMA kernel at the most amplified
+# g-point; the tensor core truncates when it accumulates) -- fluxes and heating rates must meet the SAME tolerances.
+TAU_RTOL_FP32 = 1.0e-4
+TAU_RTOL_TC = 4.0e-4
+TAU_RTOL = TAU_RTOL_FP32
 
 
 def oracle_nets(files):
@@ -70,16 +72,17 @@ def assert_within_reference_noise(got, ref32, ref64, tol, what=""):
     return d32, d64, noise
 
 
-def assert_tau_parity(tau, ref32, ref64):
+def assert_tau_parity(tau, ref32, ref64, rtol=None):
     """tau parity, fp32 path: relative error (floored, see tau_rel_err) against the strict fp32 oracle <= 1e-4 -- or,
     where two fp32 evaluations cannot agree that well, within the reference arithmetic's own distance from fp64."""
+    rtol = TAU_RTOL if rtol is None else rtol
     e32 = tau_rel_err(tau, ref32).max()
     e64 = tau_rel_err(tau, ref64).max()
     noise = tau_rel_err(ref32, ref64).max()
-    assert e32 <= max(TAU_RTOL, 2.0 * noise), f"tau rel err vs fp32 oracle {e32:.3e} (oracle noise {noise:.3e})"
-    assert e64 <= max(TAU_RTOL, NOISE_FACTOR * noise), f"tau rel err vs fp64 {e64:.3e} (oracle noise {noise:.3e})"
+    assert e32 <= max(rtol, 2.0 * noise), f"tau rel err vs fp32 oracle {e32:.3e} (oracle noise {noise:.3e})"
+    assert e64 <= max(rtol, NOISE_FACTOR * noise), f"tau rel err vs fp64 {e64:.3e} (oracle noise {noise:.3e})"
     # the bulk of the spectrum (tau >= 1% of the sample maximum) must meet the plain 1e-4 with a wide margin
     bulk = tau_rel_err(tau, ref32, floor=1e-2).max()
     print(f"tau parity: vs fp32 oracle {e32:.2e}, vs fp64 {e64:.2e}, oracle noise {noise:.2e}, bulk (tau >= 1% of max) {bulk:.2e}")
-    assert bulk <= 0.25 * TAU_RTOL
+    assert bulk <= 0.25 * rtol
     return e32, e64, noise
