@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--solver-buffer", type=int, default=0, help="0 auto, 1 shared memory, 2 L2-resident global scratch")
     ap.add_argument("--sw-fast-math", type=int, default=0)
+    ap.add_argument("--solver-variant", type=int, default=0, help="0 packed two-g-points-per-lane solvers, 1 one g-point per lane")
+    ap.add_argument("--solver-scratch-mb", type=int, default=0, help="L2 budget of the packed solvers' reverse-sweep scratch (0 = default)")
     args = ap.parse_args()
     args.steps = max(1, args.steps)
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
@@ -223,6 +225,8 @@ def main():
     ctx.set_flag("fast_math", args.fast_math)
     ctx.set_flag("solver_buffer", args.solver_buffer)
     ctx.set_flag("sw_fast_math", args.sw_fast_math)
+    ctx.set_flag("solver_variant", args.solver_variant)
+    ctx.set_flag("solver_scratch_mb", args.solver_scratch_mb)
     if args.chunk:
         ctx.set_chunk_columns(args.chunk)
     k_lw = api.ty_gas_optics_rrtmgp(ctx); k_lw.load(spectral.synthetic_kdist_lw(NGPT_LW))

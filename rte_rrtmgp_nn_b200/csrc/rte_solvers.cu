@@ -19,144 +19,12 @@
 // by one back-substitution from the surface up.  It is the same linear two-point boundary-value problem solved
 // in the other direction: identical in exact arithmetic, and within fp32 rounding (<< 0.01 W m-2) of the
 // reference order -- checked against the oracle in tests/test_solvers_gpu.py.
-#include "common.cuh"
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
+#include "solver_common.cuh"
 
 namespace rrnn {
 
-// Combine the per-level partial sums of the g-point chunks of one column.
-//  CLUSTER = true : the chunks of a column are the CTAs of one thread-block cluster; rank 0 reads the other
-//                   ranks' partial sums through distributed shared memory and adds them in rank order, so the
-//                   result is deterministic and the rounding is the same at every level (which is what keeps
-//                   heating rates, i.e. differences of adjacent levels, clean).  No memset, no atomics.
-//  CLUSTER = false: fallback for more than 8 chunks (ngpt > 256): fp32 atomics on zero-initialised arrays.
-template <bool CLUSTER, int NARR>
-__device__ __forceinline__ void combine_chunks(float* part /* [NARR][L+1] in this CTA's smem */, int L, int lane,
-                                               float* const (&gout)[NARR]) {
-  if (CLUSTER) {
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();
-    if (cluster.block_rank() == 0) {
-      const unsigned nr = cluster.num_blocks();
-      for (int i = lane; i < NARR * (L + 1); i += 32) {
-        float s = part[i];
-        for (unsigned r = 1; r < nr; ++r) s += *cluster.map_shared_rank(part + i, r);
-        const int a = i / (L + 1);
-        gout[a][i - a * (L + 1)] = s;
-      }
-    }
-    cluster.sync();  // keep every rank's shared memory alive until rank 0 has read it
-  } else {
-    for (int i = lane; i < NARR * (L + 1); i += 32) {
-      const int a = i / (L + 1);
-      atomicAdd(gout[a] + (i - a * (L + 1)), part[i]);
-    }
-  }
-}
-
-struct LwParams {
-  int ngpt, nlay, ncol, top_at_1, nmus, bug_compat, nchunks;
-  float Ds[4], wts[4];
-  const float* inc_flux;  // (ngpt,ncol) or null
-  const float* tau;       // (ngpt,nlay,ncol)
-  const float* lay_source;
-  const float* lev_source;  // (ngpt,nlay+1,ncol)
-  const float* sfc_emis;    // (ngpt,ncol)
-  const float* sfc_source;  // (ngpt,ncol)
-  float* flux_up;           // (nlay+1,ncol)
-  float* flux_dn;
-  float* scratch;           // GBUF: nCTA * 2 * L * 32 floats
-};
-
-constexpr float kPi = 3.14159265358979323846f;
 constexpr int kLwU = 8;  // layers per software-pipelined group (LW)
 constexpr int kSwU = 4;  // layers per group (SW)
-
-// Sum N (power of two, <= 8) values per lane over the 32 lanes with N-1 + log2(32/N) shuffles instead of 5N:
-// a butterfly that halves the number of live values at every step.  On return v[0] of lane `lane` holds the
-// all-lane sum of the original v[multi_index(lane)].
-template <int N>
-__device__ __forceinline__ void multi_reduce(float (&v)[N], int lane) {
-  int off = 16;
-#pragma unroll
-  for (int n = N; n > 1; n >>= 1) {
-    const int half = n >> 1;
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < half; ++k) {
-      const float send = upper ? v[k] : v[k + half];
-      const float keep = upper ? v[k + half] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-    off >>= 1;
-  }
-#pragma unroll
-  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-}
-template <int N>
-__device__ __forceinline__ int multi_index(int lane) {
-  int idx = 0, off = 16;
-#pragma unroll
-  for (int n = N; n > 1; n >>= 1) {
-    if (lane & off) idx += n >> 1;
-    off >>= 1;
-  }
-  return idx;
-}
-template <int N>
-__device__ __forceinline__ bool multi_writer(int lane) {  // one lane per distinct index
-  return (lane & ((32 / N) - 1)) == 0;
-}
-
-// L2 cache policies: the optical-property arrays are read exactly once (evict first); the reverse-sweep buffer,
-// when it lives in global memory, is written and read back in LIFO order within microseconds (evict last: it should
-// never reach HBM).
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float ld_once(const float* p, uint64_t pol) {
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-  return v;
-}
-// reverse-sweep buffer accessors: shared memory or (GBUF) L2-resident global scratch
-template <bool GBUF>
-__device__ __forceinline__ void buf_st2(float2* p, float2 v, uint64_t pol) {
-  if (GBUF) asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
-  else *p = v;
-}
-template <bool GBUF>
-__device__ __forceinline__ float2 buf_ld2(const float2* p, uint64_t pol) {
-  if (GBUF) {
-    float2 v;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol) : "memory");
-    return v;
-  }
-  return *p;
-}
-template <bool GBUF>
-__device__ __forceinline__ void buf_st1(float* p, float v, uint64_t pol) {
-  if (GBUF) asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
-  else *p = v;
-}
-template <bool GBUF>
-__device__ __forceinline__ float buf_ld1(const float* p, uint64_t pol) {
-  if (GBUF) {
-    float v;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-  }
-  return *p;
-}
 
 // Work distribution.  CLUSTER: persistent clusters, cluster c handles columns c, c+nclusters, ...; the CTA's rank in
 // the cluster is its g-point chunk.  Otherwise one (column, chunk) item per warp, no loop.
@@ -327,22 +195,6 @@ __global__ void __launch_bounds__(64) lw_solver_kernel(const LwParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct SwParams {
-  int ngpt, nlay, ncol, top_at_1, nchunks;
-  const float* inc_flux;      // (ngpt,ncol)
-  const float* inc_flux_dif;  // (ngpt,ncol) or null
-  const float* tau;
-  const float* ssa;
-  const float* g;  // or null (g = 0)
-  const float* mu0;
-  const float* alb_dir;
-  const float* alb_dif;
-  float* flux_up;
-  float* flux_dn;
-  float* flux_dir;
-  float* scratch;  // GBUF: nCTA * 3 * L * 32 floats
-};
-
 template <bool FAST, bool HAS_G, bool CLUSTER, bool GBUF>
 __global__ void __launch_bounds__(64) sw_solver_kernel(const SwParams p) {
   extern __shared__ float smem[];
@@ -542,45 +394,15 @@ __global__ void expand_kernel(int nbnd, int ngpt, int ncol, const int* __restric
 
 using namespace rrnn;
 
+namespace rrnn {
+int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v5.cu (TMA-staged, packed); -1 = shape not supported
+int launch_lw_v4(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v4.cu (packed, per-lane loads)
+int launch_sw_v4(rrnn_ctx_t* ctx, SwParams& p, bool fast);
+}
+
 static int pick_warps_per_block(size_t per_warp_bytes) {
   // two warps per CTA unless that does not fit
   return (2 * per_warp_bytes <= 200 * 1024) ? 2 : 1;
-}
-
-static int ensure_scratch(rrnn_ctx_t* ctx, size_t bytes) {
-  if (ctx->scratch_bytes >= bytes) return 0;
-  if (ctx->scratch) { RRNN_CUDA(cudaStreamSynchronize(ctx->stream)); RRNN_CUDA(cudaFree(ctx->scratch)); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
-  RRNN_CUDA(cudaMalloc(&ctx->scratch, bytes));
-  ctx->scratch_bytes = bytes;
-  return 0;
-}
-
-// Persistent clustered launch: one 32-thread CTA per g-point chunk, the chunks of a column form one cluster, and as
-// many clusters as can be co-resident loop over the columns.  Returns the grid size through ncta_out.
-template <typename P>
-static cudaError_t cluster_config(void (*kernel)(const P), int cluster, size_t smem, int ncol, cudaStream_t stream,
-                                  cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int& ncta_out) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  cfg = cudaLaunchConfig_t{};
-  cfg.gridDim = dim3((unsigned)cluster);
-  cfg.blockDim = dim3(32);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int nclusters = 0;
-  e = cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg);
-  if (e != cudaSuccess) return e;
-  if (nclusters < 1) nclusters = 1;
-  if (nclusters > ncol) nclusters = ncol;
-  ncta_out = nclusters * cluster;
-  cfg.gridDim = dim3((unsigned)ncta_out);
-  return cudaSuccess;
 }
 
 // Where does the reverse-sweep buffer live?  Shared memory when enough warps fit per SM to hide latency, otherwise
@@ -615,7 +437,18 @@ extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int nc
   const size_t per_warp = part + (gbuf ? 0 : bufb);
   RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_lw_solver_noscat: nlay too large for the on-chip layer buffer");
   const int ps = prof_begin(ctx, K_LW_SOLVER);
-  if (clustered) {
+  int rc4 = -1;
+  if (ctx->solver_variant == 0) {
+    rc4 = launch_lw_v5(ctx, p);
+    if (rc4 > 0) return rc4;
+  }
+  if (rc4 < 0 && (ctx->solver_variant == 0 || ctx->solver_variant == 2)) {
+    rc4 = launch_lw_v4(ctx, p);
+    if (rc4 > 0) return rc4;
+  }
+  if (rc4 == 0) {
+    // done by the packed kernel
+  } else if (clustered) {
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1]; int ncta = 0;
 #define LW_CL(F, GB)                                                                                              \
     do {                                                                                                          \
@@ -668,7 +501,14 @@ extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
   RRNN_CHECK(per_warp <= ctx->smem_optin, "rrnn_sw_solver_2stream: nlay too large for the on-chip layer buffer");
   const bool fast = ctx->fast_math || ctx->sw_fast_math;
   const int ps = prof_begin(ctx, K_SW_SOLVER);
-  if (clustered) {
+  int rc4 = -1;
+  if (ctx->solver_variant == 0 || ctx->solver_variant == 2) {
+    rc4 = launch_sw_v4(ctx, p, fast);
+    if (rc4 > 0) return rc4;
+  }
+  if (rc4 == 0) {
+    // done by the packed kernel
+  } else if (clustered) {
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1]; int ncta = 0;
 #define SW_CL(F, HG, GB)                                                                                              \
     do {                                                                                                              \

@@ -1,0 +1,465 @@
+// RTE flux solvers, TMA-staged packed variant (the default): two g-points per lane, fp32x2 arithmetic, and every
+// global <-> on-chip transfer done by the TMA unit instead of per-lane loads and stores.
+//
+//  lw_solver_v5  <- lw_solver_noscat + lw_source_noscat + lw_transport_noscat_dn/_up + inlined broadband sums
+//                   (rte/kernels/mo_rte_solver_kernels.F90:119-330, 742-776, 950-1009, 301-314), angle loop :332-415
+//  sw_solver_v5  <- sw_solver_2stream + sw_two_stream_source + adding (:541-692, 1366-1480, 1526-1637)
+//
+// Why: ncu on the per-lane-load kernels (rte_solvers.cu, rte_solvers_v4.cu) shows them bound by instruction issue and
+// load latency, not by HBM -- ~40 % of the issued instructions were 64-bit address arithmetic for the loads, and with the
+// few warps the reverse-sweep buffer allows, one group of register prefetch could not cover the memory latency.  Here
+//   * one elected lane issues ONE cp.async.bulk.tensor.2d per input array per group of U layers (box 64 g-points x U rows of
+//     the [rows][ngpt] tensor) into a ring of S shared-memory stages, S-1 groups ahead, signalled by mbarriers; lanes read
+//     their two g-points with LDS.64 at immediate offsets -- no per-lane address arithmetic, no prefetch registers;
+//   * the reverse-sweep coefficients (LW: t, source_up -- 16 B per lane and layer; SW: e, f, alpha_above -- 24 B) are staged
+//     in shared memory and moved to / from an L2-resident scratch ring with 1-D bulk copies (cp.async.bulk), evict_last;
+//   * arithmetic as in rte_solvers_v4.cu (f32x2.cuh); orientation and the level-source convention are template parameters.
+// One warp per CTA, the ceil(ngpt/64) chunk-warps of a column form a cluster, partial fluxes are combined through DSMEM
+// in rank order (deterministic), clusters are persistent over columns.
+#include "solver_common.cuh"
+#include "f32x2.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <type_traits>
+
+namespace rrnn {
+namespace v5 {
+
+constexpr int U = 4;   // layers per group (one TMA box)
+constexpr int S = 3;   // stages of the input and back-sweep rings
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  unsigned spins = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // a wait of seconds is a protocol bug: fail the launch instead of hanging
+  }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ f2 lds2(const void* p) { f2 v; v.v = *reinterpret_cast<const unsigned long long*>(p); return v; }
+__device__ __forceinline__ void lds22(const void* p, f2& a, f2& b) {
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+  a.v = v.x; b.v = v.y;
+}
+__device__ __forceinline__ void sts22(void* p, f2 a, f2 b) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a.v, b.v); }
+__device__ __forceinline__ void sts2(void* p, f2 a) { *reinterpret_cast<unsigned long long*>(p) = a.v; }
+__device__ __forceinline__ f2 ldg2(const float* p) { f2 v; asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v.v) : "l"(p)); return v; }
+__device__ __forceinline__ f2 sel2(bool mx, bool my, f2 a, f2 b) {
+  float ax, ay, bx, by;
+  unpack2(a, ax, ay);
+  unpack2(b, bx, by);
+  return mk2(mx ? ax : bx, my ? ay : by);
+}
+
+// exp(-x) and 1 - exp(-x) for x >= 0 without the cancellation of the literal 1 - exp(-x) at small x (common.cuh,
+// exp_and_complement): degree-7 Taylor polynomial of expm1 below 0.35, the literal form above.
+template <bool FAST>
+__device__ __forceinline__ void exp_and_complement2(f2 x, f2& t, f2& omt) {
+  const f2 y = neg2(x);
+  const f2 e = exp2x<FAST>(y);
+  if (FAST) { t = e; omt = splat2(1.0f) - e; return; }
+  f2 p = fma2(y, splat2(1.0f / 5040.0f), splat2(1.0f / 720.0f));
+  p = fma2(p, y, splat2(1.0f / 120.0f));
+  p = fma2(p, y, splat2(1.0f / 24.0f));
+  p = fma2(p, y, splat2(1.0f / 6.0f));
+  p = fma2(p, y, splat2(0.5f));
+  p = fma2(p, y, splat2(1.0f));
+  const f2 em1 = p * y;  // expm1(-x)
+  float xx, xy;
+  unpack2(x, xx, xy);
+  const bool sx = xx < 0.35f, sy = xy < 0.35f;
+  omt = sel2(sx, sy, neg2(em1), splat2(1.0f) - e);
+  t = sel2(sx, sy, splat2(1.0f) + em1, e);
+}
+
+// one lane of a converged warp (elect.sync): ptxas then issues the uniform-datapath TMA instructions straight, without
+// the per-lane retry loop it wraps around them under an ordinary `lane == 0` branch
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// Rows of a group of U layers in a [rows][ngpt] tensor.  Sweep order i = k*U + u runs from the top of the atmosphere
+// down; the tensor row of sweep layer i is r0 + i (TOP) or r0 - i (bottom-up arrays), r0 = row of sweep layer 0.
+// The TMA box is [start, start + U): start = r0 + k*U (TOP) or r0 - k*U - (U-1); sweep layer k*U + u then sits in
+// shared-memory row u (TOP) or U-1-u.  Two boxes can leave the tensor: the last box of the last column (TOP; rows past
+// the end are zero-filled by the TMA unit and belong to layers >= nlay, never used) and the ragged last box of column 0
+// bottom-up, whose start would be negative: that one is moved to row 0 and `shift` says by how much.
+template <bool TOP>
+__device__ __forceinline__ int box_start(int r0, int k, int& shift) {
+  if (TOP) { shift = 0; return r0 + k * U; }
+  const int start = r0 - k * U - (U - 1);
+  shift = min(start, 0);  // <= 0
+  return start - shift;
+}
+template <bool TOP>
+__device__ __forceinline__ int box_row(int u, int shift) { return TOP ? u : max(U - 1 - u + shift, 0); }
+
+struct LwV5Params {
+  LwParams b;
+  int ngroups;
+};
+
+// ---------------------------------------------------------------------------------------------------- LW
+template <bool FAST, bool TOP, bool DN_EXT>
+__global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
+                                                   const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const LwParams& p = pp.b;
+  const int lane = threadIdx.x;
+  const int G = p.ngpt, L = p.nlay;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t pol_buf = policy_evict_last();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int chunk = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+
+  // ---- shared memory: input ring, reverse-buffer staging (out: 2 tiles, back: S tiles), partial fluxes (2 sets), barriers
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* in_ring = smem;                                   // [S][3][U][256 B]: tau, lay_source, lev_source(ext rows)
+  uint8_t* ob = in_ring + S * 3 * U * 256;                   // [2][U][512 B]
+  uint8_t* bb = ob + 2 * U * 512;                            // [S][U][512 B]
+  float* part = reinterpret_cast<float*>(bb + S * U * 512);  // [2 sets][2][L+1]
+  const int part_set = 2 * (L + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
+  const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
+  const uint32_t in_a = smem_u32(in_ring), ob_a = smem_u32(ob), bb_a = smem_u32(bb);
+  if (lane == 0) {
+    for (int s = 0; s < 2 * S; ++s) mbar_init(bar_in + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t n_in = 0, n_bb = 0;  // groups consumed so far from each ring (stage = n % S, parity = (n / S) & 1)
+
+  const float tau_thresh = 3.4526698e-4f;  // sqrt(epsilon(1._sp)), mo_rte_solver_kernels.F90:754
+  const int g = chunk * 64 + 2 * lane;
+  const bool act = g < G;                // ngpt is even: a pair is live or not as a whole
+  const int gs = act ? g : chunk * 64;   // idle lanes shadow the chunk's first pair and contribute zero
+  const float live = act ? 1.0f : 0.0f;
+  const int NG = pp.ngroups;
+  const int NGF = L / U;                 // full groups; the ragged one (if any) is group NGF
+  // reverse-sweep scratch of this CTA in global memory (L2-resident): [L][32 lanes x 16 B]
+  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * L * 512;
+  const uint32_t lane_in = (uint32_t)lane * 8u;   // byte offset of this lane's pair in a 256-byte row
+  const uint32_t lane_bf = (uint32_t)lane * 16u;  // ... in a 512-byte reverse-buffer row
+
+  int ncols_done = 0;
+  for (int col = blockIdx.x / csize; col < p.ncol; col += gridDim.x / csize, ++ncols_done) {
+    float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
+    float* fdn = fup + (L + 1);
+    for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
+    const size_t gc_off = (size_t)col * G + gs;
+    const f2 emis = ldg2(p.sfc_emis + gc_off);
+    const f2 ssrc = ldg2(p.sfc_source + gc_off);
+    const f2 inc = p.inc_flux ? ldg2(p.inc_flux + gc_off) : splat2(0.0f);
+    // tensor rows of sweep layer 0: layers (tau, lay_source) and the level towards the surface (lev_source)
+    const int lay0 = col * L + (TOP ? 0 : L - 1);
+    const int ext0 = col * (L + 1) + (TOP ? 1 : L - 1);
+    const float* lev_ent0 = p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs;
+    __syncwarp();
+
+    for (int imu = 0; imu < p.nmus; ++imu) {
+      const f2 D = splat2(p.Ds[imu]);
+      const f2 fac = splat2(2.0f * kPi * p.wts[imu] * live);
+      const float rad_norm = 2.0f * kPi * p.wts[imu];
+      f2 I = map2(inc, [&](float v) { return v / rad_norm; });  // radn_dn(top) = inc_flux/(2 pi w), :196-201
+      {
+        const float s = warp_sum(hsum2(fac * I));
+        if (lane == 0) fdn[TOP ? 0 : L] += s;
+      }
+      // one elected lane feeds the input ring: group k -> stage (n_in + k) % S
+      auto issue_in = [&](int k) {
+        if (k < NG) {
+          const uint32_t st = (n_in + (uint32_t)k) % S;
+          int sh;
+          const int rl = box_start<TOP>(lay0, k, sh), rv = box_start<TOP>(ext0, k, sh);
+          if (elect_one()) {
+            const uint32_t bar = bar_in + 8 * st;
+            const uint32_t dst = in_a + st * (3 * U * 256);
+            mbar_expect_tx(bar, 3 * U * 256);
+            tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
+            tma_load_2d(dst + U * 256, &tm_lay, chunk * 64, rl, bar, pol_in);
+            tma_load_2d(dst + 2 * U * 256, &tm_lev, chunk * 64, rv, bar, pol_in);
+          }
+          __syncwarp();
+        }
+      };
+      f2 carry = ldg2(lev_ent0);  // ent(0)
+#pragma unroll
+      for (int k = 0; k < S - 1; ++k) issue_in(k);
+      // ---------------- downward sweep: one group of U layers ----------------
+      // TAIL = false: a full group whose boxes sit where box_start put them (immediate shared-memory offsets);
+      // TAIL = true: the ragged last group (nvalid < U) and/or a box that was moved (column 0, bottom-up)
+      auto forward_group = [&](int k, auto tail_c) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        __syncwarp();                 // every lane is done with the stage that group k+S-1 overwrites
+        issue_in(k + S - 1);
+        const uint32_t nk = n_in + (uint32_t)k;
+        const uint32_t st = nk % S;
+        mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
+        const uint8_t* base = in_ring + st * (3 * U * 256) + lane_in;
+        int shl = 0, shv = 0, nvalid = U;
+        if (TAIL) {
+          box_start<TOP>(lay0, k, shl);
+          box_start<TOP>(ext0, k, shv);
+          nvalid = min(U, L - k * U);
+        }
+        f2 tau[U], lay[U], ext[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int rl = TAIL ? box_row<TOP>(u, shl) : (TOP ? u : U - 1 - u);
+          const int rv = TAIL ? box_row<TOP>(u, shv) : (TOP ? u : U - 1 - u);
+          tau[u] = lds2(base + rl * 256);
+          lay[u] = lds2(base + U * 256 + rl * 256);
+          ext[u] = lds2(base + 2 * U * 256 + rv * 256);
+        }
+        f2 tv[U], sdn[U], sup[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const f2 ent = (u == 0) ? carry : ext[u - 1];
+          const f2 tl = tau[u] * D;
+          f2 t, omt;
+          exp_and_complement2<FAST>(tl, t, omt);
+          // fact = (1-t)/tau' - t, or its series where tau' is tiny (:757-768)
+          const f2 fa = div2<true>(omt, tl) - t;
+          const f2 fb = tl * fnma2(tl, splat2(1.0f / 3.0f), splat2(0.5f));
+          float tx, ty;
+          unpack2(tl, tx, ty);
+          const f2 fact = sel2(tx > tau_thresh, ty > tau_thresh, fa, fb);
+          const f2 f2x = fact + fact;
+          // lw_source_noscat (:770-773): source_dn from lev(l+1), source_up from lev(l) whatever the orientation (quirk Q1)
+          const f2 lev_dn = DN_EXT ? ext[u] : ent;
+          const f2 lev_up = DN_EXT ? ent : ext[u];
+          tv[u] = t;
+          sdn[u] = fma2(f2x, lay[u] - lev_dn, omt * lev_dn);
+          sup[u] = fma2(f2x, lay[u] - lev_up, omt * lev_up);
+        }
+        carry = ext[U - 1];
+        // reverse-buffer staging tile k&1: free once the bulk store of group k-2 has read it
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        uint8_t* ot = ob + (k & 1) * (U * 512) + lane_bf;
+        float red[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!TAIL || u < nvalid) {  // warp-uniform
+            I = fma2(tv[u], I, sdn[u]);
+            sts22(ot + u * 512, tv[u], sup[u]);
+          }
+          red[u] = hsum2(fac * I);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          bulk_store(scratch + (size_t)k * (U * 512), ob_a + (k & 1) * (U * 512), (uint32_t)nvalid * 512u, pol_buf);
+          bulk_commit();
+        }
+        __syncwarp();
+        multi_reduce<U>(red, lane);
+        const int i = k * U + multi_index<U>(lane);
+        if (multi_writer<U>(lane) && (!TAIL || i < L)) fdn[TOP ? i + 1 : L - 1 - i] += red[0];
+      };
+      {
+        // bottom-up, column 0: the boxes of the last groups may have been moved -> generic path for those
+        const int nfast = (TOP || col > 0) ? NGF : max(NGF - 1, 0);
+        for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
+        for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
+      }
+      n_in += (uint32_t)NG;
+      // ---------------- surface ----------------
+      f2 Uu = fma2(I, splat2(1.0f) - emis, emis * ssrc);  // :269
+      {
+        const float s = warp_sum(hsum2(fac * Uu));
+        if (lane == 0) fup[TOP ? L : 0] += s;
+      }
+      // ---------------- upward sweep (reverse order) from the scratch ring ----------------
+      if (lane == 0) bulk_wait_all();  // all reverse-buffer stores have landed
+      __syncwarp();
+      auto issue_bb = [&](int j) {  // j-th group of the upward sweep = forward group NG-1-j
+        if (j < NG) {
+          const int k = NG - 1 - j;
+          const uint32_t st = (n_bb + (uint32_t)j) % S;
+          const uint32_t bytes = (uint32_t)min(U, L - k * U) * 512u;
+          if (elect_one()) {
+            mbar_expect_tx(bar_bb + 8 * st, bytes);
+            bulk_load(bb_a + st * (U * 512), scratch + (size_t)k * (U * 512), bytes, bar_bb + 8 * st, pol_buf);
+          }
+          __syncwarp();
+        }
+      };
+#pragma unroll
+      for (int j = 0; j < S - 1; ++j) issue_bb(j);
+      auto backward_group = [&](int j, auto tail_c) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        __syncwarp();
+        issue_bb(j + S - 1);
+        const int k = NG - 1 - j;
+        const uint32_t nj = n_bb + (uint32_t)j;
+        const uint32_t st = nj % S;
+        mbar_wait(bar_bb + 8 * st, (nj / S) & 1u);
+        const uint8_t* bt = bb + st * (U * 512) + lane_bf;
+        const int nvalid = TAIL ? min(U, L - k * U) : U;
+        f2 t[U], s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) lds22(bt + (TAIL ? min(u, nvalid - 1) : u) * 512, t[u], s[u]);
+        float red[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
+          const int uu = U - 1 - u;
+          if (!TAIL || uu < nvalid) Uu = fma2(t[uu], Uu, s[uu]);
+          red[u] = hsum2(fac * Uu);
+        }
+        multi_reduce<U>(red, lane);
+        const int i = k * U + (U - 1 - multi_index<U>(lane));
+        if (multi_writer<U>(lane) && (!TAIL || i < L)) fup[TOP ? i : L - i] += red[0];
+      };
+      {
+        int j = 0;
+        if (NG > NGF) backward_group(j++, std::true_type{});  // the ragged group comes first on the way up
+        for (; j < NG; ++j) backward_group(j, std::false_type{});
+      }
+      n_bb += (uint32_t)NG;
+      __syncwarp();
+    }
+    // ---- combine the chunks of this column: rank 0 adds the ranks' partial sums in rank order through distributed
+    //      shared memory (deterministic).  Partial sums are double-buffered by column, so one cluster barrier per column
+    //      is enough: the other ranks only need it before they reuse this set, two columns later.
+    cluster.sync();
+    if (chunk == 0) {
+      float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
+      for (int i = lane; i < 2 * (L + 1); i += 32) {
+        float sacc = fup[i];
+        for (int r = 1; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
+        const int a = i / (L + 1);
+        gout[a][i - a * (L + 1)] = sacc;
+      }
+    }
+  }
+  cluster.sync();  // nobody leaves while rank 0 may still read its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(f);
+  return fn;
+}
+// [rows][ngpt] fp32 tensor, box 64 g-points x U rows, no swizzle (rows of 256 B, read with 8-byte LDS per lane)
+static int make_map(CUtensorMap* tm, const float* base, int G, long long rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail("rte solvers: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)G * 4};
+  const cuuint32_t box[2] = {64, (cuuint32_t)U};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("rte solvers: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
+}  // namespace v5
+
+// Resident clusters are capped so that the reverse-sweep scratch of all of them stays L2-sized.
+static int resident_clusters5(const rrnn_ctx_t* ctx, int occ_clusters, int csize, size_t per_cta_bytes, int ncol) {
+  const size_t budget = (size_t)(ctx->solver_scratch_mb > 0 ? ctx->solver_scratch_mb : 96) << 20;
+  long long n = (long long)(budget / (per_cta_bytes * (size_t)csize));
+  n = std::max<long long>(n, ctx->num_sms / 2);  // never starve the GPU outright
+  n = std::min<long long>(n, occ_clusters);
+  n = std::min<long long>(n, ncol);
+  return (int)std::max<long long>(n, 1);
+}
+
+template <typename K, typename P>
+static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t smem, size_t per_cta_scratch, int ncol, P& pp, float** scratch_slot,
+                            const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2) {
+  RRNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3((unsigned)csize);
+  cfg.blockDim = dim3(32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int occ = 0;
+  RRNN_CUDA(cudaOccupancyMaxActiveClusters(&occ, kernel, &cfg));
+  const int ncl = resident_clusters5(ctx, std::max(occ, 1), csize, per_cta_scratch, ncol);
+  const int ncta = ncl * csize;
+  cfg.gridDim = dim3((unsigned)ncta);
+  if (int rc = ensure_scratch(ctx, (size_t)ncta * per_cta_scratch)) return rc;
+  *scratch_slot = (float*)ctx->scratch;
+  RRNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, pp, t0, t1, t2));
+  return 0;
+}
+
+// returns -1 when the shape does not fit (the caller falls back to the per-lane-load kernels)
+int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
+  const int G = p.ngpt, L = p.nlay;
+  const int csize = (G + 63) / 64;
+  if ((G & 3) || csize > 8 || L < v5::U) return -1;  // TMA: row pitch a multiple of 16 B
+  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source})
+    if ((uintptr_t)q & 15) return -1;
+  for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
+    if ((uintptr_t)q & 7) return -1;
+  v5::LwV5Params pp;
+  pp.b = p;
+  pp.ngroups = (L + v5::U - 1) / v5::U;
+  const long long rows_lay = (long long)p.ncol * L, rows_lev = (long long)p.ncol * (L + 1);
+  if (rows_lev >= (1LL << 31) - 8) return -1;
+  CUtensorMap tm_tau, tm_lay, tm_lev;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay)) return rc;
+  if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay)) return rc;
+  if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev)) return rc;
+  const size_t smem = 128 + (size_t)v5::S * 3 * v5::U * 256 + 2 * v5::U * 512 + (size_t)v5::S * v5::U * 512 + 4 * (size_t)(L + 1) * 4 + 2 * v5::S * 8;
+  const size_t per_cta = (size_t)L * 512;
+  const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
+#define LW5(F, T, D) launch_clustered(ctx, v5::lw_solver_v5<F, T, D>, csize, smem, per_cta, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev)
+  if (fast) {
+    if (top) return LW5(true, true, true);
+    return dn_ext ? LW5(true, false, true) : LW5(true, false, false);
+  }
+  if (top) return LW5(false, true, true);
+  return dn_ext ? LW5(false, false, true) : LW5(false, false, false);
+#undef LW5
+}
+
+}  // namespace rrnn
