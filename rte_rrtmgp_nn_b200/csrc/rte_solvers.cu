@@ -397,6 +397,7 @@ using namespace rrnn;
 namespace rrnn {
 int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v5.cu (TMA-staged, packed); -1 = shape not supported
 int launch_lw_v4(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v4.cu (packed, per-lane loads)
+int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast);
 int launch_sw_v4(rrnn_ctx_t* ctx, SwParams& p, bool fast);
 }
 
@@ -502,7 +503,11 @@ extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
   const bool fast = ctx->fast_math || ctx->sw_fast_math;
   const int ps = prof_begin(ctx, K_SW_SOLVER);
   int rc4 = -1;
-  if (ctx->solver_variant == 0 || ctx->solver_variant == 2) {
+  if (ctx->solver_variant == 0) {
+    rc4 = launch_sw_v5(ctx, p, fast);
+    if (rc4 > 0) return rc4;
+  }
+  if (rc4 < 0 && (ctx->solver_variant == 0 || ctx->solver_variant == 2)) {
     rc4 = launch_sw_v4(ctx, p, fast);
     if (rc4 > 0) return rc4;
   }

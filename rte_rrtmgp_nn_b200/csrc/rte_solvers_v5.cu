@@ -212,6 +212,24 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
       f2 carry = ldg2(lev_ent0);  // ent(0)
 #pragma unroll
       for (int k = 0; k < S - 1; ++k) issue_in(k);
+      // The per-level broadband sums (butterfly shuffles: long dependent latencies, nothing downstream waits for them)
+      // are deferred by one group, so that they overlap the next group's arithmetic instead of stalling the warp.
+      float pend[U];
+      int pend_k = -1;
+      auto flush_dn = [&]() {
+        if (pend_k >= 0) {
+          multi_reduce<U>(pend, lane);
+          const int i = pend_k * U + multi_index<U>(lane);
+          if (multi_writer<U>(lane) && i < L) fdn[TOP ? i + 1 : L - 1 - i] += pend[0];
+        }
+      };
+      auto flush_up = [&]() {
+        if (pend_k >= 0) {
+          multi_reduce<U>(pend, lane);
+          const int i = pend_k * U + (U - 1 - multi_index<U>(lane));
+          if (multi_writer<U>(lane) && i < L) fup[TOP ? i : L - i] += pend[0];
+        }
+      };
       // ---------------- downward sweep: one group of U layers ----------------
       // TAIL = false: a full group whose boxes sit where box_start put them (immediate shared-memory offsets);
       // TAIL = true: the ragged last group (nvalid < U) and/or a box that was moved (column 0, bottom-up)
@@ -238,6 +256,7 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
           lay[u] = lds2(base + U * 256 + rl * 256);
           ext[u] = lds2(base + 2 * U * 256 + rv * 256);
         }
+        flush_dn();
         f2 tv[U], sdn[U], sup[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -280,9 +299,9 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
           bulk_commit();
         }
         __syncwarp();
-        multi_reduce<U>(red, lane);
-        const int i = k * U + multi_index<U>(lane);
-        if (multi_writer<U>(lane) && (!TAIL || i < L)) fdn[TOP ? i + 1 : L - 1 - i] += red[0];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pend[u] = red[u];
+        pend_k = k;
       };
       {
         // bottom-up, column 0: the boxes of the last groups may have been moved -> generic path for those
@@ -290,6 +309,8 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
         for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
         for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
       }
+      flush_dn();
+      pend_k = -1;
       n_in += (uint32_t)NG;
       // ---------------- surface ----------------
       f2 Uu = fma2(I, splat2(1.0f) - emis, emis * ssrc);  // :269
@@ -327,6 +348,7 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
         f2 t[U], s[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) lds22(bt + (TAIL ? min(u, nvalid - 1) : u) * 512, t[u], s[u]);
+        flush_up();
         float red[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
@@ -334,33 +356,351 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
           if (!TAIL || uu < nvalid) Uu = fma2(t[uu], Uu, s[uu]);
           red[u] = hsum2(fac * Uu);
         }
-        multi_reduce<U>(red, lane);
-        const int i = k * U + (U - 1 - multi_index<U>(lane));
-        if (multi_writer<U>(lane) && (!TAIL || i < L)) fup[TOP ? i : L - i] += red[0];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pend[u] = red[u];
+        pend_k = k;
       };
       {
         int j = 0;
         if (NG > NGF) backward_group(j++, std::true_type{});  // the ragged group comes first on the way up
         for (; j < NG; ++j) backward_group(j, std::false_type{});
       }
+      flush_up();
+      pend_k = -1;
       n_bb += (uint32_t)NG;
       __syncwarp();
     }
-    // ---- combine the chunks of this column: rank 0 adds the ranks' partial sums in rank order through distributed
-    //      shared memory (deterministic).  Partial sums are double-buffered by column, so one cluster barrier per column
+    // ---- combine the chunks of this column: the ranks' partial sums are added in rank order through distributed
+    //      shared memory (deterministic), each rank doing its share of the levels.  Partial sums are double-buffered by column, so one cluster barrier per column
     //      is enough: the other ranks only need it before they reuse this set, two columns later.
     cluster.sync();
-    if (chunk == 0) {
+    {
+      // every rank combines its share of the levels, adding the ranks' partial sums in rank order
       float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
-      for (int i = lane; i < 2 * (L + 1); i += 32) {
-        float sacc = fup[i];
-        for (int r = 1; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
+      const int n = 2 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
+      for (int i = lo + lane; i < hi; i += 32) {
+        float sacc = 0.0f;
+        for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
         const int a = i / (L + 1);
         gout[a][i - a * (L + 1)] = sacc;
       }
     }
   }
-  cluster.sync();  // nobody leaves while rank 0 may still read its shared memory
+  cluster.sync();  // nobody leaves while another rank may still read its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------- SW
+// Two-stream coefficients of one layer for a pair of g-points (sw_two_stream_source :1405-1475; PIFM, Zdunkowski).
+template <bool FAST, bool HAS_G>
+__device__ __forceinline__ void two_stream2(f2 tau, f2 w0, f2 gg, float mu0, float mu0_inv, f2& Rdif, f2& Tdif, f2& Rdir, f2& Tdir,
+                                            f2& Tnos) {
+  const float k_min = 1.e-4f;       // mo_rte_solver_kernels.F90:76-82 (single precision)
+  const float eps = 1.1920929e-7f;  // epsilon(1._sp)
+  const f2 one = splat2(1.0f), quarter = splat2(0.25f);
+  Tnos = exp2x<FAST>(tau * splat2(-mu0_inv));
+  f2 gamma1, gamma2, gamma3, gamma4, alpha1, alpha2;
+  if (HAS_G) {
+    gamma1 = fnma2(w0, fma2(gg, splat2(3.0f), splat2(5.0f)), splat2(8.0f)) * quarter;
+    gamma2 = (splat2(3.0f) * (w0 * (one - gg))) * quarter;
+    gamma3 = fnma2(splat2(3.0f * mu0), gg, splat2(2.0f)) * quarter;
+    gamma4 = one - gamma3;
+    alpha1 = fma2(gamma1, gamma4, gamma2 * gamma3);
+    alpha2 = fma2(gamma1, gamma3, gamma2 * gamma4);
+  } else {
+    // g = 0 (always, on the NN path): gamma3 = gamma4 = 1/2 exactly, alpha1 = alpha2 = (gamma1 + gamma2)/2
+    gamma1 = fnma2(w0, splat2(5.0f), splat2(8.0f)) * quarter;
+    gamma2 = (splat2(3.0f) * w0) * quarter;
+    gamma3 = splat2(0.5f);
+    gamma4 = gamma3;
+    alpha1 = (gamma1 + gamma2) * gamma3;
+    alpha2 = alpha1;
+  }
+  const f2 k = sqrt2<FAST>(max2((gamma1 - gamma2) * (gamma1 + gamma2), splat2(k_min)));
+  const f2 ekt = exp2x<FAST>(neg2(tau) * k);
+  const f2 e2kt = ekt * ekt;
+  const f2 k2e = (k + k) * ekt;
+  const f2 ome2 = one - e2kt;
+  f2 RT = rcp2<FAST>(fma2(gamma1, ome2, k * (one + e2kt)));
+  Rdif = (RT * gamma2) * ome2;
+  Tdif = RT * k2e;
+  const f2 k_mu = k * splat2(mu0);
+  const f2 k_g3 = k * gamma3, k_g4 = k * gamma4;
+  const f2 om = fnma2(k_mu, k_mu, one);
+  float ox, oy;
+  unpack2(om, ox, oy);
+  const f2 dd = mk2(fabsf(ox) >= eps ? ox : eps, fabsf(oy) >= eps ? oy : eps);
+  RT = div2<FAST>(w0 * RT, dd);
+  const f2 a_m = one - k_mu, a_p = one + k_mu;
+  // the brackets cancel heavily near k*mu0 = 1: every difference is closed by an FMA (one rounding less per term)
+  f2 rd = fnma2(a_p * (alpha2 - k_g3), e2kt, a_m * (alpha2 + k_g3));
+  rd = RT * fnma2(k2e * fnma2(alpha2, splat2(mu0), gamma3), Tnos, rd);
+  f2 td = fnma2(a_m * (alpha1 - k_g4), e2kt, a_p * (alpha1 + k_g4));
+  td = RT * fnma2(Tnos, td, k2e * fma2(alpha1, splat2(mu0), gamma4));
+  const f2 lim = one - Tnos;
+  rd = max2(splat2(0.0f), min2(rd, lim));
+  td = max2(splat2(0.0f), min2(td, lim - rd));
+  Rdir = rd;
+  Tdir = td;
+}
+
+struct SwV5Params {
+  SwParams b;
+  int ngroups;
+};
+
+// Reverse-buffer row of one layer: 32 lanes x (e, f) 16 B, then 32 lanes x alpha_above 8 B = 768 B
+constexpr int SWROW = 768;
+
+template <bool FAST, bool HAS_G, bool TOP>
+__global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
+                                                   const __grid_constant__ CUtensorMap tm_ssa, const __grid_constant__ CUtensorMap tm_g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const SwParams& p = pp.b;
+  constexpr int NIN = HAS_G ? 3 : 2;
+  const int lane = threadIdx.x;
+  const int G = p.ngpt, L = p.nlay;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t pol_buf = policy_evict_last();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int chunk = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* in_ring = smem;                                     // [S][NIN][U][256 B]: tau, ssa (, g)
+  uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][U][768 B]
+  uint8_t* bb = ob + 2 * U * SWROW;                            // [S][U][768 B]
+  float* part = reinterpret_cast<float*>(bb + S * U * SWROW);  // [2 sets][3][L+1]
+  const int part_set = 3 * (L + 1) + ((L + 1) & 1);            // keep the barriers 8-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
+  const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
+  const uint32_t in_a = smem_u32(in_ring), ob_a = smem_u32(ob), bb_a = smem_u32(bb);
+  if (lane == 0) {
+    for (int s = 0; s < 2 * S; ++s) mbar_init(bar_in + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t n_in = 0, n_bb = 0;
+
+  const int g = chunk * 64 + 2 * lane;
+  const bool act = g < G;
+  const int gs = act ? g : chunk * 64;
+  const f2 live = splat2(act ? 1.0f : 0.0f);
+  const int NG = pp.ngroups;
+  const int NGF = L / U;
+  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * L * SWROW;
+  const uint32_t lane_in = (uint32_t)lane * 8u;
+  const uint32_t lane_ef = (uint32_t)lane * 16u, lane_al = 512u + (uint32_t)lane * 8u;
+  const int top_level = TOP ? 0 : L;
+
+  int ncols_done = 0;
+  for (int col = blockIdx.x / csize; col < p.ncol; col += gridDim.x / csize, ++ncols_done) {
+    float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [3][L+1]
+    float* fdn = fup + (L + 1);
+    float* fdr = fdn + (L + 1);
+    for (int i = lane; i < 3 * (L + 1); i += 32) fup[i] = 0.0f;
+    const size_t gc_off = (size_t)col * G + gs;
+    const float mu0 = __ldg(p.mu0 + col);
+    const float mu0_inv = 1.0f / mu0;
+    const int lay0 = col * L + (TOP ? 0 : L - 1);
+    f2 dir = (live * ldg2(p.inc_flux + gc_off)) * splat2(mu0);                        // :589
+    f2 beta = p.inc_flux_dif ? live * ldg2(p.inc_flux_dif + gc_off) : splat2(0.0f);   // :590
+    f2 alpha = splat2(0.0f);
+    const f2 a_s = ldg2(p.alb_dif + gc_off);
+    const f2 a_d = ldg2(p.alb_dir + gc_off);
+    __syncwarp();
+    {
+      const float sd = warp_sum(hsum2(dir)), sb = warp_sum(hsum2(beta + dir));
+      if (lane == 0) { fdr[top_level] += sd; fdn[top_level] += sb; }
+    }
+    auto issue_in = [&](int k) {
+      if (k < NG) {
+        const uint32_t st = (n_in + (uint32_t)k) % S;
+        int sh;
+        const int rl = box_start<TOP>(lay0, k, sh);
+        if (elect_one()) {
+          const uint32_t bar = bar_in + 8 * st;
+          const uint32_t dst = in_a + st * (NIN * U * 256);
+          mbar_expect_tx(bar, NIN * U * 256);
+          tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
+          tma_load_2d(dst + U * 256, &tm_ssa, chunk * 64, rl, bar, pol_in);
+          if (HAS_G) tma_load_2d(dst + 2 * U * 256, &tm_g, chunk * 64, rl, bar, pol_in);
+        }
+        __syncwarp();
+      }
+    };
+#pragma unroll
+    for (int k = 0; k < S - 1; ++k) issue_in(k);
+    // per-level broadband sums deferred by one group (see lw_solver_v5)
+    float pend[2 * U];
+    int pend_k = -1;
+    auto flush_fwd = [&]() {
+      if (pend_k >= 0) {
+        multi_reduce<2 * U>(pend, lane);
+        const int idx = multi_index<2 * U>(lane);
+        const int i = pend_k * U + (idx & (U - 1));
+        if (multi_writer<2 * U>(lane) && i < L) {
+          const int lvl = TOP ? i + 1 : L - 1 - i;
+          if (idx < U) fdr[lvl] += pend[0]; else fdn[lvl] += pend[0];
+        }
+      }
+    };
+    auto flush_bwd = [&]() {
+      if (pend_k >= 0) {
+        multi_reduce<2 * U>(pend, lane);
+        const int idx = multi_index<2 * U>(lane);
+        const int i = pend_k * U + (U - 1 - (idx & (U - 1)));
+        if (multi_writer<2 * U>(lane) && i < L) {
+          const int lvl = TOP ? i : L - i;  // level at the top of layer i
+          if (idx < U) fup[lvl] += pend[0]; else fdn[lvl] += pend[0];
+        }
+      }
+    };
+    // ---------------- sweep 1: top -> surface ----------------
+    auto forward_group = [&](int k, auto tail_c) {
+      constexpr bool TAIL = decltype(tail_c)::value;
+      __syncwarp();
+      issue_in(k + S - 1);
+      const uint32_t nk = n_in + (uint32_t)k;
+      const uint32_t st = nk % S;
+      mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
+      const uint8_t* base = in_ring + st * (NIN * U * 256) + lane_in;
+      int shl = 0, nvalid = U;
+      if (TAIL) {
+        box_start<TOP>(lay0, k, shl);
+        nvalid = min(U, L - k * U);
+      }
+      f2 tau[U], w0[U], gg[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rl = TAIL ? box_row<TOP>(u, shl) : (TOP ? u : U - 1 - u);
+        tau[u] = lds2(base + rl * 256);
+        w0[u] = lds2(base + U * 256 + rl * 256);
+        gg[u] = HAS_G ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
+      }
+      flush_fwd();
+      // layer coefficients: independent across the U layers (instruction-level parallelism)
+      f2 Rdif[U], Tdif[U], Rdir[U], Tdir[U], Tnos[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) two_stream2<FAST, HAS_G>(tau[u], w0[u], gg[u], mu0, mu0_inv, Rdif[u], Tdif[u], Rdir[u], Tdir[u], Tnos[u]);
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      uint8_t* ot = ob + (k & 1) * (U * SWROW);
+      // the sequential part: direct beam and the adding recurrences, eliminated from the top
+      float red[2 * U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!TAIL || u < nvalid) {  // warp-uniform
+          const f2 s_up = Rdir[u] * dir;
+          const f2 s_dn = Tdir[u] * dir;
+          dir = Tnos[u] * dir;
+          const f2 d = rcp2<FAST>(fnma2(Rdif[u], alpha, splat2(1.0f)));
+          const f2 e = d * Tdif[u];
+          const f2 f = d * fma2(Rdif[u], beta, s_up);
+          sts2(ot + u * SWROW + lane_al, alpha);  // reflectance of the atmosphere ABOVE this layer: what sweep 2 needs
+          sts22(ot + u * SWROW + lane_ef, e, f);
+          beta = fma2(e, fma2(alpha, s_up, beta), s_dn);
+          alpha = fma2(Tdif[u] * e, alpha, Rdif[u]);
+        }
+        red[u] = hsum2(dir);
+        red[U + u] = hsum2(beta + dir);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        bulk_store(scratch + (size_t)k * (U * SWROW), ob_a + (k & 1) * (U * SWROW), (uint32_t)nvalid * SWROW, pol_buf);
+        bulk_commit();
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
+      pend_k = k;
+    };
+    {
+      const int nfast = (TOP || col > 0) ? NGF : max(NGF - 1, 0);
+      for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
+      for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
+    }
+    flush_fwd();
+    pend_k = -1;
+    n_in += (uint32_t)NG;
+    // ---------------- surface ----------------
+    const f2 S_s = dir * a_d;  // source_sfc :1477
+    f2 Uu = div2<FAST>(fma2(a_s, beta, S_s), fnma2(a_s, alpha, splat2(1.0f))) * live;
+    {
+      const int sfc = TOP ? L : 0;
+      const float su = warp_sum(hsum2(Uu)), sa = warp_sum(hsum2(alpha * Uu));
+      if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
+    }
+    // ---------------- sweep 2: surface -> top (back substitution) ----------------
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+    auto issue_bb = [&](int j) {
+      if (j < NG) {
+        const int k = NG - 1 - j;
+        const uint32_t st = (n_bb + (uint32_t)j) % S;
+        const uint32_t bytes = (uint32_t)min(U, L - k * U) * SWROW;
+        if (elect_one()) {
+          mbar_expect_tx(bar_bb + 8 * st, bytes);
+          bulk_load(bb_a + st * (U * SWROW), scratch + (size_t)k * (U * SWROW), bytes, bar_bb + 8 * st, pol_buf);
+        }
+        __syncwarp();
+      }
+    };
+#pragma unroll
+    for (int j = 0; j < S - 1; ++j) issue_bb(j);
+    auto backward_group = [&](int j, auto tail_c) {
+      constexpr bool TAIL = decltype(tail_c)::value;
+      __syncwarp();
+      issue_bb(j + S - 1);
+      const int k = NG - 1 - j;
+      const uint32_t nj = n_bb + (uint32_t)j;
+      const uint32_t st = nj % S;
+      mbar_wait(bar_bb + 8 * st, (nj / S) & 1u);
+      const uint8_t* bt = bb + st * (U * SWROW);
+      const int nvalid = TAIL ? min(U, L - k * U) : U;
+      f2 e[U], f[U], a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ru = TAIL ? min(u, nvalid - 1) : u;
+        lds22(bt + ru * SWROW + lane_ef, e[u], f[u]);
+        a[u] = lds2(bt + ru * SWROW + lane_al);
+      }
+      flush_bwd();
+      float red[2 * U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
+        const int uu = U - 1 - u;
+        if (!TAIL || uu < nvalid) Uu = fma2(e[uu], Uu, f[uu]);
+        red[u] = hsum2(Uu);               // upward flux at the level on top of that layer
+        red[U + u] = hsum2(a[uu] * Uu);   // diffuse downward flux there: alpha_above * U (+ beta, added in sweep 1)
+      }
+#pragma unroll
+      for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
+      pend_k = k;
+    };
+    {
+      int j = 0;
+      if (NG > NGF) backward_group(j++, std::true_type{});
+      for (; j < NG; ++j) backward_group(j, std::false_type{});
+    }
+    flush_bwd();
+    pend_k = -1;
+    n_bb += (uint32_t)NG;
+    __syncwarp();
+    // ---- combine the chunks of this column (see lw_solver_v5)
+    cluster.sync();
+    {
+      float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1), p.flux_dir + (size_t)col * (L + 1)};
+      const int n = 3 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
+      for (int i = lo + lane; i < hi; i += 32) {
+        float sacc = 0.0f;
+        for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
+        const int a = i / (L + 1);
+        gout[a][i - a * (L + 1)] = sacc;
+      }
+    }
+  }
+  cluster.sync();
 }
 
 // ---------------------------------------------------------------------------------------------------- host side
@@ -395,8 +735,8 @@ static int make_map(CUtensorMap* tm, const float* base, int G, long long rows) {
 }  // namespace v5
 
 // Resident clusters are capped so that the reverse-sweep scratch of all of them stays L2-sized.
-static int resident_clusters5(const rrnn_ctx_t* ctx, int occ_clusters, int csize, size_t per_cta_bytes, int ncol) {
-  const size_t budget = (size_t)(ctx->solver_scratch_mb > 0 ? ctx->solver_scratch_mb : 96) << 20;
+static int resident_clusters5(const rrnn_ctx_t* ctx, int occ_clusters, int csize, size_t per_cta_bytes, int ncol, int default_mb) {
+  const size_t budget = (size_t)(ctx->solver_scratch_mb > 0 ? ctx->solver_scratch_mb : default_mb) << 20;
   long long n = (long long)(budget / (per_cta_bytes * (size_t)csize));
   n = std::max<long long>(n, ctx->num_sms / 2);  // never starve the GPU outright
   n = std::min<long long>(n, occ_clusters);
@@ -405,8 +745,8 @@ static int resident_clusters5(const rrnn_ctx_t* ctx, int occ_clusters, int csize
 }
 
 template <typename K, typename P>
-static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t smem, size_t per_cta_scratch, int ncol, P& pp, float** scratch_slot,
-                            const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2) {
+static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t smem, size_t per_cta_scratch, int default_mb, int ncol, P& pp,
+                            float** scratch_slot, const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2) {
   RRNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
@@ -422,7 +762,7 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t smem, s
   cfg.numAttrs = 1;
   int occ = 0;
   RRNN_CUDA(cudaOccupancyMaxActiveClusters(&occ, kernel, &cfg));
-  const int ncl = resident_clusters5(ctx, std::max(occ, 1), csize, per_cta_scratch, ncol);
+  const int ncl = resident_clusters5(ctx, std::max(occ, 1), csize, per_cta_scratch, ncol, default_mb);
   const int ncta = ncl * csize;
   cfg.gridDim = dim3((unsigned)ncta);
   if (int rc = ensure_scratch(ctx, (size_t)ncta * per_cta_scratch)) return rc;
@@ -452,7 +792,7 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
   const size_t smem = 128 + (size_t)v5::S * 3 * v5::U * 256 + 2 * v5::U * 512 + (size_t)v5::S * v5::U * 512 + 4 * (size_t)(L + 1) * 4 + 2 * v5::S * 8;
   const size_t per_cta = (size_t)L * 512;
   const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
-#define LW5(F, T, D) launch_clustered(ctx, v5::lw_solver_v5<F, T, D>, csize, smem, per_cta, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev)
+#define LW5(F, T, D) launch_clustered(ctx, v5::lw_solver_v5<F, T, D>, csize, smem, per_cta, 96, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev)
   if (fast) {
     if (top) return LW5(true, true, true);
     return dn_ext ? LW5(true, false, true) : LW5(true, false, false);
@@ -460,6 +800,40 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
   if (top) return LW5(false, true, true);
   return dn_ext ? LW5(false, false, true) : LW5(false, false, false);
 #undef LW5
+}
+
+
+int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
+  const int G = p.ngpt, L = p.nlay;
+  const int csize = (G + 63) / 64;
+  if ((G & 3) || csize > 8 || L < v5::U) return -1;
+  for (const void* q : {(const void*)p.tau, (const void*)p.ssa, (const void*)p.g})
+    if ((uintptr_t)q & 15) return -1;
+  for (const void* q : {(const void*)p.inc_flux, (const void*)p.inc_flux_dif, (const void*)p.alb_dir, (const void*)p.alb_dif})
+    if ((uintptr_t)q & 7) return -1;
+  v5::SwV5Params pp;
+  pp.b = p;
+  pp.ngroups = (L + v5::U - 1) / v5::U;
+  const long long rows = (long long)p.ncol * L;
+  if (rows >= (1LL << 31) - 8) return -1;
+  CUtensorMap tm_tau, tm_ssa, tm_g;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows)) return rc;
+  if (int rc = v5::make_map(&tm_ssa, p.ssa, G, rows)) return rc;
+  if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows)) return rc; }
+  else tm_g = tm_ssa;
+  const int nin = p.g ? 3 : 2;
+  const size_t smem = 128 + (size_t)v5::S * nin * v5::U * 256 + 2 * v5::U * v5::SWROW + (size_t)v5::S * v5::U * v5::SWROW +
+                      2 * (size_t)(3 * (L + 1) + 1) * 4 + 2 * v5::S * 8;
+  const size_t per_cta = (size_t)L * v5::SWROW;
+  const bool top = p.top_at_1 != 0;
+#define SW5(F, HG, T) launch_clustered(ctx, v5::sw_solver_v5<F, HG, T>, csize, smem, per_cta, 256, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
+  if (fast) {
+    if (p.g) return top ? SW5(true, true, true) : SW5(true, true, false);
+    return top ? SW5(true, false, true) : SW5(true, false, false);
+  }
+  if (p.g) return top ? SW5(false, true, true) : SW5(false, true, false);
+  return top ? SW5(false, false, true) : SW5(false, false, false);
+#undef SW5
 }
 
 }  // namespace rrnn
