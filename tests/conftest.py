@@ -30,3 +30,12 @@ def nn_variant(request, gpu_ctx):
     gpu_ctx.set_flag("nn_tensor_cores", request.param)
     yield (H.TAU_RTOL_TC if request.param else H.TAU_RTOL_FP32)
     gpu_ctx.set_flag("nn_tensor_cores", 1)
+
+
+@pytest.fixture(params=[0, 2, 1], ids=["v5_tma_packed", "v4_packed", "v3_scalar"])
+def solver_variant(request, gpu_ctx):
+    """The three generations of RTE solver kernels behind rrnn_lw_solver_noscat / rrnn_sw_solver_2stream: TMA-staged
+    packed fp32x2 (default), packed with per-lane loads, one g-point per lane."""
+    gpu_ctx.set_flag("solver_variant", request.param)
+    yield request.param
+    gpu_ctx.set_flag("solver_variant", 0)

@@ -127,13 +127,16 @@ def test_lw_physical_orientation_flag(gpu_ctx):
     assert np.array_equal(res[(1, "down")][0], u0)                      # the flag only matters bottom-up
 
 
-def test_lw_solver_alone_random_inputs(gpu_ctx):
-    """Solver on materialised oracle inputs: isolates K3 from the NN (tight tolerance)."""
+def test_lw_solver_alone_random_inputs(gpu_ctx, solver_variant):
+    """Solver on materialised oracle inputs: isolates K3 from the NN (tight tolerance).  Shapes: ragged layer groups,
+    bottom-up columns (incl. column 0, whose last TMA box is moved), g-point counts that leave idle lanes, and more
+    columns than resident clusters (the persistent loop and the double-buffered partial fluxes)."""
     import oracle as O
     from rte_rrtmgp_nn_b200 import api, _lib
     torch = _torch()
     rng = np.random.default_rng(0)
-    for (G, L, C, top) in [(256, 60, 7, True), (224, 5, 3, False), (112, 137, 2, True), (36, 17, 5, True)]:
+    for (G, L, C, top) in [(256, 60, 7, True), (224, 5, 3, False), (112, 137, 2, True), (36, 17, 5, True), (128, 33, 2100, False),
+                           (256, 4, 3, False), (64, 7, 1, False)]:
         tau = rng.gamma(0.3, 2.0, size=(C, L, G)).astype(np.float32)
         tau[0, 0, :4] = 1e-5  # exercises the small-tau series branch
         lay = rng.uniform(0.1, 2.0, size=(C, L, G)).astype(np.float32)
@@ -198,13 +201,13 @@ def test_sw_gas_optics_and_fluxes_match_oracle(gpu_ctx, nn_variant, files, ngpt,
     assert torch.allclose(fl2.flux_up, fl.flux_up, rtol=2e-6, atol=1e-4) and torch.allclose(fl2.flux_dn, fl.flux_dn, rtol=2e-6, atol=1e-4)
 
 
-def test_sw_solver_alone_with_scattering(gpu_ctx):
+def test_sw_solver_alone_with_scattering(gpu_ctx, solver_variant):
     """Solver on random tau/ssa/g (g != 0, diffuse incident flux): isolates K4 from the NN."""
     import oracle as O
     from rte_rrtmgp_nn_b200 import api, _lib
     torch = _torch()
     rng = np.random.default_rng(4)
-    for (G, L, C, top) in [(224, 60, 6, True), (112, 9, 4, False), (64, 137, 3, True)]:
+    for (G, L, C, top) in [(224, 60, 6, True), (112, 9, 4, False), (64, 137, 3, True), (224, 30, 1500, False), (32, 6, 2, False)]:
         tau = rng.gamma(0.4, 1.5, size=(C, L, G)).astype(np.float32)
         ssa = rng.uniform(0.0, 0.999, size=(C, L, G)).astype(np.float32)
         g = rng.uniform(-0.2, 0.9, size=(C, L, G)).astype(np.float32)
