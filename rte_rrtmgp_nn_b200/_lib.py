@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librrnn_b200.so")
+# RRNN_LIB_PATH: load another build of the same library (kernel-variant experiments); never a different implementation
+LIB_PATH = os.environ.get("RRNN_LIB_PATH") or os.path.join(_HERE, "lib", "librrnn_b200.so")
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)

@@ -25,8 +25,22 @@
 namespace rrnn {
 namespace v5 {
 
-constexpr int U = 4;   // layers per group (one TMA box)
-constexpr int S = 3;   // stages of the input and back-sweep rings
+// Layers per group (one TMA box) and stages of the input / back-sweep rings, tuned per kernel on B200 (1 M x 137):
+// LW 8 x 2 (146 -> 124 ms against 4 x 3: more independent layers per warp), SW 4 x 3 (8 x 2: 238 ms, 4 x 3: 224 ms --
+// the two-stream arithmetic already fills the registers at 4 layers).
+#ifndef RRNN_V5_LW_U
+#define RRNN_V5_LW_U 8
+#endif
+#ifndef RRNN_V5_LW_S
+#define RRNN_V5_LW_S 2
+#endif
+#ifndef RRNN_V5_SW_U
+#define RRNN_V5_SW_U 4
+#endif
+#ifndef RRNN_V5_SW_S
+#define RRNN_V5_SW_S 3
+#endif
+constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -110,14 +124,14 @@ __device__ __forceinline__ bool elect_one() {
 // shared-memory row u (TOP) or U-1-u.  Two boxes can leave the tensor: the last box of the last column (TOP; rows past
 // the end are zero-filled by the TMA unit and belong to layers >= nlay, never used) and the ragged last box of column 0
 // bottom-up, whose start would be negative: that one is moved to row 0 and `shift` says by how much.
-template <bool TOP>
+template <bool TOP, int U>
 __device__ __forceinline__ int box_start(int r0, int k, int& shift) {
   if (TOP) { shift = 0; return r0 + k * U; }
   const int start = r0 - k * U - (U - 1);
   shift = min(start, 0);  // <= 0
   return start - shift;
 }
-template <bool TOP>
+template <bool TOP, int U>
 __device__ __forceinline__ int box_row(int u, int shift) { return TOP ? u : max(U - 1 - u + shift, 0); }
 
 struct LwV5Params {
@@ -130,6 +144,7 @@ template <bool FAST, bool TOP, bool DN_EXT>
 __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int U = LW_U, S = LW_S;
   const LwParams& p = pp.b;
   const int lane = threadIdx.x;
   const int G = p.ngpt, L = p.nlay;
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
         if (k < NG) {
           const uint32_t st = (n_in + (uint32_t)k) % S;
           int sh;
-          const int rl = box_start<TOP>(lay0, k, sh), rv = box_start<TOP>(ext0, k, sh);
+          const int rl = box_start<TOP, U>(lay0, k, sh), rv = box_start<TOP, U>(ext0, k, sh);
           if (elect_one()) {
             const uint32_t bar = bar_in + 8 * st;
             const uint32_t dst = in_a + st * (3 * U * 256);
@@ -243,15 +258,15 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
         const uint8_t* base = in_ring + st * (3 * U * 256) + lane_in;
         int shl = 0, shv = 0, nvalid = U;
         if (TAIL) {
-          box_start<TOP>(lay0, k, shl);
-          box_start<TOP>(ext0, k, shv);
+          box_start<TOP, U>(lay0, k, shl);
+          box_start<TOP, U>(ext0, k, shv);
           nvalid = min(U, L - k * U);
         }
         f2 tau[U], lay[U], ext[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int rl = TAIL ? box_row<TOP>(u, shl) : (TOP ? u : U - 1 - u);
-          const int rv = TAIL ? box_row<TOP>(u, shv) : (TOP ? u : U - 1 - u);
+          const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
+          const int rv = TAIL ? box_row<TOP, U>(u, shv) : (TOP ? u : U - 1 - u);
           tau[u] = lds2(base + rl * 256);
           lay[u] = lds2(base + U * 256 + rl * 256);
           ext[u] = lds2(base + 2 * U * 256 + rv * 256);
@@ -455,6 +470,7 @@ template <bool FAST, bool HAS_G, bool TOP>
 __global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_ssa, const __grid_constant__ CUtensorMap tm_g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int U = SW_U, S = SW_S;
   const SwParams& p = pp.b;
   constexpr int NIN = HAS_G ? 3 : 2;
   const int lane = threadIdx.x;
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5P
       if (k < NG) {
         const uint32_t st = (n_in + (uint32_t)k) % S;
         int sh;
-        const int rl = box_start<TOP>(lay0, k, sh);
+        const int rl = box_start<TOP, U>(lay0, k, sh);
         if (elect_one()) {
           const uint32_t bar = bar_in + 8 * st;
           const uint32_t dst = in_a + st * (NIN * U * 256);
@@ -566,13 +582,13 @@ __global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5P
       const uint8_t* base = in_ring + st * (NIN * U * 256) + lane_in;
       int shl = 0, nvalid = U;
       if (TAIL) {
-        box_start<TOP>(lay0, k, shl);
+        box_start<TOP, U>(lay0, k, shl);
         nvalid = min(U, L - k * U);
       }
       f2 tau[U], w0[U], gg[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int rl = TAIL ? box_row<TOP>(u, shl) : (TOP ? u : U - 1 - u);
+        const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
         tau[u] = lds2(base + rl * 256);
         w0[u] = lds2(base + U * 256 + rl * 256);
         gg[u] = HAS_G ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
@@ -717,13 +733,13 @@ static EncodeTiledFn encode_fn() {
   fn = reinterpret_cast<EncodeTiledFn>(f);
   return fn;
 }
-// [rows][ngpt] fp32 tensor, box 64 g-points x U rows, no swizzle (rows of 256 B, read with 8-byte LDS per lane)
-static int make_map(CUtensorMap* tm, const float* base, int G, long long rows) {
+// [rows][ngpt] fp32 tensor, box 64 g-points x box_rows rows, no swizzle (rows of 256 B, read with 8-byte LDS per lane)
+static int make_map(CUtensorMap* tm, const float* base, int G, long long rows, int box_rows) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail("rte solvers: cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)G * 4};
-  const cuuint32_t box[2] = {64, (cuuint32_t)U};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -775,21 +791,21 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t smem, s
 int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 63) / 64;
-  if ((G & 3) || csize > 8 || L < v5::U) return -1;  // TMA: row pitch a multiple of 16 B
+  if ((G & 3) || csize > 8 || L < v5::LW_U) return -1;  // TMA: row pitch a multiple of 16 B
   for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source})
     if ((uintptr_t)q & 15) return -1;
   for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
     if ((uintptr_t)q & 7) return -1;
   v5::LwV5Params pp;
   pp.b = p;
-  pp.ngroups = (L + v5::U - 1) / v5::U;
+  pp.ngroups = (L + v5::LW_U - 1) / v5::LW_U;
   const long long rows_lay = (long long)p.ncol * L, rows_lev = (long long)p.ncol * (L + 1);
   if (rows_lev >= (1LL << 31) - 8) return -1;
   CUtensorMap tm_tau, tm_lay, tm_lev;
-  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay)) return rc;
-  if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay)) return rc;
-  if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev)) return rc;
-  const size_t smem = 128 + (size_t)v5::S * 3 * v5::U * 256 + 2 * v5::U * 512 + (size_t)v5::S * v5::U * 512 + 4 * (size_t)(L + 1) * 4 + 2 * v5::S * 8;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, v5::LW_U)) return rc;
+  if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, v5::LW_U)) return rc;
+  if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev, v5::LW_U)) return rc;
+  const size_t smem = 128 + (size_t)v5::LW_S * 3 * v5::LW_U * 256 + 2 * v5::LW_U * 512 + (size_t)v5::LW_S * v5::LW_U * 512 + 4 * (size_t)(L + 1) * 4 + 2 * v5::LW_S * 8;
   const size_t per_cta = (size_t)L * 512;
   const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
 #define LW5(F, T, D) launch_clustered(ctx, v5::lw_solver_v5<F, T, D>, csize, smem, per_cta, 96, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev)
@@ -806,27 +822,27 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
 int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 63) / 64;
-  if ((G & 3) || csize > 8 || L < v5::U) return -1;
+  if ((G & 3) || csize > 8 || L < v5::SW_U) return -1;
   for (const void* q : {(const void*)p.tau, (const void*)p.ssa, (const void*)p.g})
     if ((uintptr_t)q & 15) return -1;
   for (const void* q : {(const void*)p.inc_flux, (const void*)p.inc_flux_dif, (const void*)p.alb_dir, (const void*)p.alb_dif})
     if ((uintptr_t)q & 7) return -1;
   v5::SwV5Params pp;
   pp.b = p;
-  pp.ngroups = (L + v5::U - 1) / v5::U;
+  pp.ngroups = (L + v5::SW_U - 1) / v5::SW_U;
   const long long rows = (long long)p.ncol * L;
   if (rows >= (1LL << 31) - 8) return -1;
   CUtensorMap tm_tau, tm_ssa, tm_g;
-  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows)) return rc;
-  if (int rc = v5::make_map(&tm_ssa, p.ssa, G, rows)) return rc;
-  if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows)) return rc; }
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows, v5::SW_U)) return rc;
+  if (int rc = v5::make_map(&tm_ssa, p.ssa, G, rows, v5::SW_U)) return rc;
+  if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, v5::SW_U)) return rc; }
   else tm_g = tm_ssa;
   const int nin = p.g ? 3 : 2;
-  const size_t smem = 128 + (size_t)v5::S * nin * v5::U * 256 + 2 * v5::U * v5::SWROW + (size_t)v5::S * v5::U * v5::SWROW +
-                      2 * (size_t)(3 * (L + 1) + 1) * 4 + 2 * v5::S * 8;
+  const size_t smem = 128 + (size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_U * v5::SWROW + (size_t)v5::SW_S * v5::SW_U * v5::SWROW +
+                      2 * (size_t)(3 * (L + 1) + 1) * 4 + 2 * v5::SW_S * 8;
   const size_t per_cta = (size_t)L * v5::SWROW;
   const bool top = p.top_at_1 != 0;
-#define SW5(F, HG, T) launch_clustered(ctx, v5::sw_solver_v5<F, HG, T>, csize, smem, per_cta, 256, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
+#define SW5(F, HG, T) launch_clustered(ctx, v5::sw_solver_v5<F, HG, T>, csize, smem, per_cta, 160, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
   if (fast) {
     if (p.g) return top ? SW5(true, true, true) : SW5(true, true, false);
     return top ? SW5(true, false, true) : SW5(true, false, false);

@@ -223,8 +223,11 @@ def test_sw_solver_alone_with_scattering(gpu_ctx, solver_variant):
         _lib.check(_lib.lib().rrnn_sw_solver_2stream(gpu_ctx.h, G, L, C, int(top), P(d["inc"]), P(d["incd"]), P(d["tau"]), P(d["ssa"]),
                                                      P(d["g"]), P(d["mu0"]), P(d["ad"]), P(d["af"]), P(up), P(dn), P(dr)))
         scale = max(np.abs(rdn).max(), 1.0)
+        # random ssa up to 0.999 and g up to 0.9 are harsher than any clear-sky column: two fp32 evaluations of the
+        # two-stream coefficients differ by a few 1e-5 of the flux in the tail of 1500 columns (see tools/sw_noise.py)
         for got, want in ((up, rup), (dn, rdn), (dr, rdir)):
-            assert np.abs(got.cpu().numpy() - want).max() <= 3e-5 * scale
+            d = np.abs(got.cpu().numpy() - want)
+            assert d.max() <= 6e-5 * scale and np.sqrt((d ** 2).mean()) <= 6e-6 * scale, (G, L, C, top, d.max() / scale)
 
 
 def test_sgemm_entry_points(gpu_ctx):
