@@ -26,6 +26,7 @@
 // 32 and <= 256, nbnd <= 16 (all g256 / g224 / g128 two-network models of the reference with hidden width <= 64);
 // anything else returns -1 and the caller uses the fp32 FFMA kernel.
 #include "common.cuh"
+#include "f32x2.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <algorithm>
@@ -239,6 +240,32 @@ __device__ __forceinline__ float softsign(float x) {
   r = fmaf(fmaf(-d, r, 1.0f), r, r);
   return x * r;
 }
+// packed variants for the hidden-layer epilogue: two columns per instruction
+__device__ __forceinline__ f2 softsign2(f2 x) {
+  float a, b;
+  unpack2(x, a, b);
+  const float da = fabsf(a) + 1.0f, db = fabsf(b) + 1.0f;
+  const f2 d = mk2(da, db);
+  f2 r = mk2(rcp_approx(da), rcp_approx(db));
+  r = fma2(fnma2(d, r, splat2(1.0f)), r, r);
+  return x * r;
+}
+// split 4 pairs (8 fp32 values) into fp16 hi / lo and store the two 16-byte units
+__device__ __forceinline__ void store_split8p(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const f2* y) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a, b;
+    unpack2(y[i], a, b);
+    h[i] = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h[i]);
+    const f2 lo = y[i] - mk2(hf.x, hf.y);
+    unpack2(lo, a, b);
+    l[i] = __floats2half2_rn(a, b);
+  }
+  *reinterpret_cast<uint4*>(hi_base + off) = *reinterpret_cast<uint4*>(h);
+  *reinterpret_cast<uint4*>(lo_base + off) = *reinterpret_cast<uint4*>(l);
+}
 // generic activations (neural/mod_activation.F90): kept out of line, the shipped models only use softsign
 __device__ __noinline__ float act_apply(int code, float x) {
   switch (code) {
@@ -380,16 +407,48 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     uint32_t ph_hid[2] = {0u, 0u}, ph_free[2] = {0u, 0u};
     int sfc_lev = -1;
     if (MODE == 0) sfc_lev = (__ldg(p.play) > __ldg(p.play + L - 1)) ? 0 : L;  // merge(1,nlay,play(1,1) > play(nlay,1)); layer nlay <-> extra row
+    // Raw per-row values of the NEXT tile are loaded while this tile's hidden layers run, so the prologue never waits on
+    // global memory: T_lay, p_lay, the first two gases (h2o, o3), the two bounding p_lev, T_lev, T_sfc.
+    struct RowIn {
+      unsigned col;
+      int lev, lay;
+      size_t smp;
+      bool valid;
+      float x0, x1, x2, x3, p0, p1, tv, ts;
+    };
+    auto load_row = [&](unsigned tile) {
+      RowIn q;
+      const unsigned s = tile * TM + r;
+      q.valid = tile < ntiles && s < p.nrows;
+      q.col = q.valid ? s / (unsigned)P : 0u;
+      q.lev = q.valid ? (int)(s - q.col * (unsigned)P) : 0;
+      q.lay = min(q.lev, L - 1);
+      q.smp = (size_t)q.col * L + q.lay;
+      q.x0 = q.x1 = 200.0f; q.x2 = q.x3 = 0.0f; q.p0 = q.p1 = 0.0f; q.tv = q.ts = 200.0f;
+      if (q.valid) {
+        q.x0 = __ldg(p.tlay + q.smp);
+        q.x1 = __ldg(p.play + q.smp);
+        if (p.xvar[2]) q.x2 = (p.gas[2].mode == 2) ? __ldg(p.gas[2].ptr + q.smp) : __ldg(p.gas[2].ptr + q.lay);
+        if (p.xvar[3]) q.x3 = (p.gas[3].mode == 2) ? __ldg(p.gas[3].ptr + q.smp) : __ldg(p.gas[3].ptr + q.lay);
+        const float* pl = p.plev + (size_t)q.col * (L + 1) + q.lay;
+        q.p0 = __ldg(pl); q.p1 = __ldg(pl + 1);
+        if (MODE == 0) {
+          q.tv = __ldg(p.tlev + (size_t)q.col * (L + 1) + q.lev);
+          if (q.lev == sfc_lev) q.ts = __ldg(p.tsfc + q.col);
+        }
+      }
+      return q;
+    };
+    RowIn nxt = load_row(blockIdx.x);
     int it = 0;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       // ---- compute_nn_inputs (mo_gas_optics_rrtmgp.F90:713-782) for this row
       if (tid == 0) dbg_ts(p.dbg, it, 0);
-      const unsigned s = tile * TM + r;
-      const bool valid = s < p.nrows;
-      const unsigned col = valid ? s / (unsigned)P : 0u;
-      const int lev = valid ? (int)(s - col * (unsigned)P) : 0;
-      const int lay = min(lev, L - 1);
-      const size_t smp = (size_t)col * L + lay;
+      const RowIn cur = nxt;
+      const bool valid = cur.valid;
+      const unsigned col = cur.col;
+      const int lev = cur.lev, lay = cur.lay;
+      const size_t smp = cur.smp;
 #pragma unroll 1
       for (int ku = 0; ku < (p.kin >> 3); ++ku) {
         float v[8];
@@ -399,12 +458,11 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
           float x = p.xconst[k];
           if (p.xvar[k]) {
             float raw;
-            if (k == 0) raw = __ldg(p.tlay + smp);
-            else if (k == 1) raw = logf(__ldg(p.play + smp));
-            else {
-              raw = (p.gas[k].mode == 2) ? __ldg(p.gas[k].ptr + smp) : __ldg(p.gas[k].ptr + lay);
-              if (k == 2 || k == 3) raw = sqrtf(sqrtf(raw));
-            }
+            if (k == 0) raw = cur.x0;
+            else if (k == 1) raw = logf(cur.x1);
+            else if (k == 2) raw = sqrtf(sqrtf(cur.x2));
+            else if (k == 3) raw = sqrtf(sqrtf(cur.x3));
+            else raw = (p.gas[k].mode == 2) ? __ldg(p.gas[k].ptr + smp) : __ldg(p.gas[k].ptr + lay);
             x = (raw - p.xmin[k]) / (p.xmax[k] - p.xmin[k]);
           }
           v[j] = valid ? x : 0.0f;
@@ -417,39 +475,24 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         float* rec = reinterpret_cast<float*>(smem + p.off_rec) + (it % p.nrec) * (8 * TM) + r;
         float cdp = 0.0f;
         if (valid) {
-          const float h = p.xvar[2] ? ((p.gas[2].mode == 2) ? __ldg(p.gas[2].ptr + smp) : __ldg(p.gas[2].ptr + lay)) : p.h2o_const;
-          const float* pl = p.plev + (size_t)col * (L + 1) + lay;
-          cdp = col_dry_of(h, __ldg(pl), __ldg(pl + 1)) * OUT_UNSCALE;
+          const float h = p.xvar[2] ? cur.x2 : p.h2o_const;
+          cdp = col_dry_of(h, cur.p0, cur.p1) * OUT_UNSCALE;
         }
         rec[0] = cdp;
         if (MODE == 0) {
-          const float Tl = valid ? __ldg(p.tlay + smp) : 200.0f;
-          const float Tv = valid ? __ldg(p.tlev + (size_t)col * (L + 1) + lev) : 200.0f;
-          const PlanckPos pl_ = planck_pos(Tl, p.temp_ref_min, p.totplnk_delta, p.ntemp);
-          const PlanckPos pv_ = planck_pos(Tv, p.temp_ref_min, p.totplnk_delta, p.ntemp);
+          const PlanckPos pl_ = planck_pos(cur.x0, p.temp_ref_min, p.totplnk_delta, p.ntemp);
+          const PlanckPos pv_ = planck_pos(cur.tv, p.temp_ref_min, p.totplnk_delta, p.ntemp);
           rec[1 * TM] = pl_.frac; rec[2 * TM] = __int_as_float(pl_.idx);
           rec[3 * TM] = pv_.frac; rec[4 * TM] = __int_as_float(pv_.idx);
-          if (valid && lev == sfc_lev) rec[5 * TM] = __ldg(p.tsfc + col);
+          if (valid && lev == sfc_lev) rec[5 * TM] = cur.ts;
         }
       }
       fence_async_smem();
       mbar_arrive(BAR(BAR_AIN));
       if (tid == 0) { dbg_mark(p.dbg, 0, (it << 8) | 1); dbg_ts(p.dbg, it, 1); }
-      // ---- pull the next tile's inputs towards L2 while this tile's chain runs
-      {
-        const unsigned sn = (tile + gridDim.x) * TM + r;
-        if (tile + gridDim.x < ntiles && sn < p.nrows) {
-          const unsigned coln = sn / (unsigned)P;
-          const int layn = min((int)(sn - coln * (unsigned)P), L - 1);
-          const size_t smpn = (size_t)coln * L + layn;
-          prefetch_l2(p.tlay + smpn); prefetch_l2(p.play + smpn);
-          prefetch_l2(p.plev + (size_t)coln * (L + 1) + layn);
-          if (MODE == 0) prefetch_l2(p.tlev + (size_t)coln * (L + 1) + layn);
-#pragma unroll 1
-          for (int k = 2; k < p.nx; ++k)
-            if (p.xvar[k] && p.gas[k].mode == 2) prefetch_l2(p.gas[k].ptr + smpn);
-        }
-      }
+      // ---- the next tile's raw inputs start their way to registers now
+      nxt = load_row(tile + gridDim.x);
+      (void)col;
       // ---- hidden epilogues: layer 1 of net 0, net 1; layer 2 of net 0, net 1
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
@@ -470,19 +513,32 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
           for (int c0 = 0; c0 < nt.H; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_row + 64u * n + c0, v);
-            if (act == RRNN_ACT_SOFTSIGN) {
+            const bool has_one = ones && (nt.Hraw >> 4) == (c0 >> 4);
+            if (act == RRNN_ACT_SOFTSIGN && !has_one) {
+              // the common case, in packed arithmetic: bias, softsign, fp16 hi/lo split of two columns at a time
+              f2 y[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = softsign(v[j] + bb[c0 + j]);
+              for (int j = 0; j < 8; ++j) {
+                const float2 b = *reinterpret_cast<const float2*>(bb + c0 + 2 * j);
+                y[j] = softsign2(mk2(v[2 * j], v[2 * j + 1]) + mk2(b.x, b.y));
+              }
+              store_split8p(act_hi, act_lo, unit_off(TM, r, c0 >> 3), y);
+              store_split8p(act_hi, act_lo, unit_off(TM, r, (c0 >> 3) + 1), y + 4);
             } else {
+              if (act == RRNN_ACT_SOFTSIGN) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = act_apply(act, v[j] + bb[c0 + j]);
-            }
-            if (ones && (nt.Hraw >> 4) == (c0 >> 4)) {
+                for (int j = 0; j < 16; ++j) v[j] = softsign(v[j] + bb[c0 + j]);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = ((nt.Hraw & 15) == j) ? 1.0f : v[j];
+                for (int j = 0; j < 16; ++j) v[j] = act_apply(act, v[j] + bb[c0 + j]);
+              }
+              if (has_one) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = ((nt.Hraw & 15) == j) ? 1.0f : v[j];
+              }
+              store_split8(act_hi, act_lo, unit_off(TM, r, c0 >> 3), v);
+              store_split8(act_hi, act_lo, unit_off(TM, r, (c0 >> 3) + 1), v + 8);
             }
-            store_split8(act_hi, act_lo, unit_off(TM, r, c0 >> 3), v);
-            store_split8(act_hi, act_lo, unit_off(TM, r, (c0 >> 3) + 1), v + 8);
           }
           fence_before();
           fence_async_smem();
