@@ -163,6 +163,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is entitled to every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     ncol_sample = args.cpu_columns
     vals = []
     for i in range(args.warmup + args.steps):
@@ -199,7 +201,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--columns", type=int, default=NCOL_TOTAL, help="total columns (all ranks)")
-    ap.add_argument("--cpu-columns", type=int, default=16384, help="columns in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-columns", type=int, default=65536, help="columns in the bounded CPU-baseline sample (~12 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fast-math", type=int, default=0)
@@ -397,7 +399,7 @@ def main():
                 "per_kernel": kern}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, threads, dt = cpu_baseline(args.cpu_columns, NLAY)
         cpu = {"value": v, "unit": "columns/s", "cores": threads, "kind": "port",
                "sample": f"{args.cpu_columns} columns x {NLAY} layers of the same synthetic workload, LW+SW, {dt:.1f} s; oracle/oracle.c "
