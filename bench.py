@@ -195,12 +195,14 @@ def workload_config(ngpus, ncol_total):
 
 
 def main():
+    global NLAY
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--columns", type=int, default=NCOL_TOTAL, help="total columns (all ranks)")
+    ap.add_argument("--nlay", type=int, default=NLAY, help="layers (137 = the headline configuration; 91 = the size sweep, configs[4])")
     ap.add_argument("--cpu-columns", type=int, default=65536, help="columns in the bounded CPU-baseline sample (~12 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -211,6 +213,7 @@ def main():
     ap.add_argument("--solver-variant", type=int, default=0, help="0 packed two-g-points-per-lane solvers, 1 one g-point per lane")
     ap.add_argument("--solver-scratch-mb", type=int, default=0, help="L2 budget of the packed solvers' reverse-sweep scratch (0 = default)")
     args = ap.parse_args()
+    NLAY = args.nlay
     args.steps = max(1, args.steps)
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
 

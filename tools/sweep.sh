@@ -1,0 +1,15 @@
+#!/bin/bash
+# Column-count sweep (BASELINE configs[4]): LW+SW at 91 layers, 1e3 ... 1e6 columns on one GPU -> profiles/<tag>_sweep_L91.jsonl
+tag=${1:-r1}
+out=gpurun_out/${tag}_sweep_L91.jsonl
+: > $out
+for n in 1000 3000 10000 30000 100000 300000 1000000; do
+  timeout 300 python bench.py --columns $n --nlay 91 --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | grep '^{' >> $out
+done
+python - <<'PY' $out
+import json, sys
+for l in open(sys.argv[1]):
+    d = json.loads(l); k = d["roofline"]["per_kernel"]
+    print(f'{d["config"]["ncol_total"]:>8d} cols: {d["value"]:>10.0f} col/s device, {d["e2e"]["value"]:>10.0f} col/s e2e | ' +
+          " ".join(f'{n}={v["frac_of_hbm_peak"]:.2f}' for n, v in k.items()))
+PY
