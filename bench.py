@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--sw-fast-math", type=int, default=0)
     ap.add_argument("--solver-variant", type=int, default=0, help="0 packed two-g-points-per-lane solvers, 1 one g-point per lane")
     ap.add_argument("--solver-scratch-mb", type=int, default=0, help="L2 budget of the packed solvers' reverse-sweep scratch (0 = default)")
+    ap.add_argument("--solver-warps", type=int, default=0, help="solvers (warps) per CTA in the v5 solver kernels (0 = default)")
     args = ap.parse_args()
     NLAY = args.nlay
     args.steps = max(1, args.steps)
@@ -248,6 +249,7 @@ def main():
     ctx.set_flag("sw_fast_math", args.sw_fast_math)
     ctx.set_flag("solver_variant", args.solver_variant)
     ctx.set_flag("solver_scratch_mb", args.solver_scratch_mb)
+    ctx.set_flag("solver_warps", args.solver_warps)
     if args.chunk:
         ctx.set_chunk_columns(args.chunk)
     k_lw = api.ty_gas_optics_rrtmgp(ctx); k_lw.load(spectral.synthetic_kdist_lw(NGPT_LW))

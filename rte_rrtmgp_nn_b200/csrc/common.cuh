@@ -54,6 +54,7 @@ struct rrnn_ctx {
   int solver_buffer = 0;   // reverse-sweep buffer: 0 auto, 1 shared memory, 2 L2-resident global scratch
   int solver_variant = 0;  // 0 = TMA-staged packed kernels (rte_solvers_v5.cu), 2 = packed with per-lane loads (v4), 1 = one g-point per lane (rte_solvers.cu)
   int solver_scratch_mb = 0;  // L2 budget of the packed kernels' reverse-sweep scratch (0 = default)
+  int solver_warps = 0;       // solvers per CTA in the v5 kernels (0 = default)
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   int nn_tensor_cores = 1; // MLP variant: 1 = tcgen05 (fp16 hi/lo split operands, fp32 accumulation; default), 0 = fp32 FFMA

@@ -17,6 +17,8 @@
 // One warp per CTA, the ceil(ngpt/64) chunk-warps of a column form a cluster, partial fluxes are combined through DSMEM
 // in rank order (deterministic), clusters are persistent over columns.
 #include "solver_common.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include "f32x2.cuh"
 #include <cuda.h>
 #include <algorithm>
@@ -40,6 +42,7 @@ namespace v5 {
 #ifndef RRNN_V5_SW_S
 #define RRNN_V5_SW_S 3
 #endif
+constexpr int MAX_WARPS = 4;  // solvers (warps) per CTA
 constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,16 +140,17 @@ __device__ __forceinline__ int box_row(int u, int shift) { return TOP ? u : max(
 struct LwV5Params {
   LwParams b;
   int ngroups;
+  int warp_smem;  // bytes of shared memory per warp
 };
 
 // ---------------------------------------------------------------------------------------------------- LW
 template <bool FAST, bool TOP, bool DN_EXT>
-__global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
+__global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int U = LW_U, S = LW_S;
   const LwParams& p = pp.b;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
   const int G = p.ngpt, L = p.nlay;
   const uint64_t pol_in = policy_evict_first();
   const uint64_t pol_buf = policy_evict_last();
@@ -155,11 +159,14 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
   const int csize = (int)cluster.num_blocks();
 
   // ---- shared memory: input ring, reverse-buffer staging (out: 2 tiles, back: S tiles), partial fluxes (2 sets), barriers
-  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
+  // The input ring and the store staging are only live during the downward sweep, the back ring only during the upward
+  // sweep (bulk_wait_all separates them): they share their shared memory, which is what bounds the CTAs per SM.
   uint8_t* in_ring = smem;                                   // [S][3][U][256 B]: tau, lay_source, lev_source(ext rows)
   uint8_t* ob = in_ring + S * 3 * U * 256;                   // [2][U][512 B]
-  uint8_t* bb = ob + 2 * U * 512;                            // [S][U][512 B]
-  float* part = reinterpret_cast<float*>(bb + S * U * 512);  // [2 sets][2][L+1]
+  uint8_t* bb = smem;                                        // [S][U][512 B]  (aliases in_ring / ob)
+  constexpr int FWD_BYTES = S * 3 * U * 256 + 2 * U * 512, BWD_BYTES = S * U * 512;
+  float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][2][L+1]
   const int part_set = 2 * (L + 1);
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
   const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
@@ -179,12 +186,16 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
   const int NG = pp.ngroups;
   const int NGF = L / U;                 // full groups; the ragged one (if any) is group NGF
   // reverse-sweep scratch of this CTA in global memory (L2-resident): [L][32 lanes x 16 B]
-  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * L * 512;
+  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * 512;
   const uint32_t lane_in = (uint32_t)lane * 8u;   // byte offset of this lane's pair in a 256-byte row
   const uint32_t lane_bf = (uint32_t)lane * 16u;  // ... in a 512-byte reverse-buffer row
 
   int ncols_done = 0;
-  for (int col = blockIdx.x / csize; col < p.ncol; col += gridDim.x / csize, ++ncols_done) {
+  // The warps of a CTA take adjacent columns; all warps of a cluster make the same number of trips (one cluster barrier
+  // each), a warp past the last column recomputes it and does not write.
+  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
+    const bool owner = cb + warp < p.ncol;
+    const int col = owner ? cb + warp : p.ncol - 1;
     float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
     float* fdn = fup + (L + 1);
     for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(32) lw_solver_v5(const __grid_constant__ LwV5P
       // every rank combines its share of the levels, adding the ranks' partial sums in rank order
       float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
       const int n = 2 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
-      for (int i = lo + lane; i < hi; i += 32) {
+      for (int i = lo + lane; i < hi && owner; i += 32) {
         float sacc = 0.0f;
         for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
         const int a = i / (L + 1);
@@ -458,22 +469,103 @@ __device__ __forceinline__ void two_stream2(f2 tau, f2 w0, f2 gg, float mu0, flo
   Tdir = td;
 }
 
+// The same coefficients for U layers at once, written step by step across the layers: the U evaluations are independent,
+// and presenting them to the compiler already interleaved is what lets one warp cover its own MUFU / FMA latencies
+// (each warp runs alone on its scheduler slot most of the time).
+template <bool FAST, bool HAS_G, int U>
+__device__ __forceinline__ void two_stream2_batch(const f2 (&tau)[U], const f2 (&w0)[U], const f2 (&gg)[U], float mu0, float mu0_inv,
+                                                  f2 (&Rdif)[U], f2 (&Tdif)[U], f2 (&Rdir)[U], f2 (&Tdir)[U], f2 (&Tnos)[U]) {
+  const float k_min = 1.e-4f;       // mo_rte_solver_kernels.F90:76-82 (single precision)
+  const float eps = 1.1920929e-7f;  // epsilon(1._sp)
+  const f2 one = splat2(1.0f), quarter = splat2(0.25f), half = splat2(0.5f);
+  const f2 mu = splat2(mu0), nmi = splat2(-mu0_inv);
+  f2 gamma1[U], gamma2[U], gamma3[U], gamma4[U], alpha1[U], alpha2[U], k[U], ekt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) Tnos[u] = tau[u] * nmi;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (HAS_G) {
+      gamma1[u] = fnma2(w0[u], fma2(gg[u], splat2(3.0f), splat2(5.0f)), splat2(8.0f)) * quarter;
+      gamma2[u] = (splat2(3.0f) * (w0[u] * (one - gg[u]))) * quarter;
+      gamma3[u] = fnma2(splat2(3.0f * mu0), gg[u], splat2(2.0f)) * quarter;
+      gamma4[u] = one - gamma3[u];
+      alpha1[u] = fma2(gamma1[u], gamma4[u], gamma2[u] * gamma3[u]);
+      alpha2[u] = fma2(gamma1[u], gamma3[u], gamma2[u] * gamma4[u]);
+    } else {
+      // g = 0 (always, on the NN path): gamma3 = gamma4 = 1/2 exactly, alpha1 = alpha2 = (gamma1 + gamma2)/2
+      gamma1[u] = fnma2(w0[u], splat2(5.0f), splat2(8.0f)) * quarter;
+      gamma2[u] = (splat2(3.0f) * w0[u]) * quarter;
+      gamma3[u] = half;
+      gamma4[u] = half;
+      alpha1[u] = (gamma1[u] + gamma2[u]) * half;
+      alpha2[u] = alpha1[u];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) Tnos[u] = exp2x<FAST>(Tnos[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) k[u] = max2((gamma1[u] - gamma2[u]) * (gamma1[u] + gamma2[u]), splat2(k_min));
+#pragma unroll
+  for (int u = 0; u < U; ++u) k[u] = sqrt2<FAST>(k[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) ekt[u] = exp2x<FAST>(neg2(tau[u]) * k[u]);
+  f2 e2kt[U], k2e[U], ome2[U], RT[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    e2kt[u] = ekt[u] * ekt[u];
+    k2e[u] = (k[u] + k[u]) * ekt[u];
+    ome2[u] = one - e2kt[u];
+    RT[u] = fma2(gamma1[u], ome2[u], k[u] * (one + e2kt[u]));
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) RT[u] = rcp2<FAST>(RT[u]);
+  f2 k_mu[U], dd[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    Rdif[u] = (RT[u] * gamma2[u]) * ome2[u];
+    Tdif[u] = RT[u] * k2e[u];
+    k_mu[u] = k[u] * mu;
+    const f2 om = fnma2(k_mu[u], k_mu[u], one);
+    float ox, oy;
+    unpack2(om, ox, oy);
+    dd[u] = mk2(fabsf(ox) >= eps ? ox : eps, fabsf(oy) >= eps ? oy : eps);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) RT[u] = div2<FAST>(w0[u] * RT[u], dd[u]);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const f2 k_g3 = k[u] * gamma3[u], k_g4 = k[u] * gamma4[u];
+    const f2 a_m = one - k_mu[u], a_p = one + k_mu[u];
+    // the brackets cancel heavily near k*mu0 = 1: every difference is closed by an FMA (one rounding less per term)
+    f2 rd = fnma2(a_p * (alpha2[u] - k_g3), e2kt[u], a_m * (alpha2[u] + k_g3));
+    rd = RT[u] * fnma2(k2e[u] * fnma2(alpha2[u], mu, gamma3[u]), Tnos[u], rd);
+    f2 td = fnma2(a_m * (alpha1[u] - k_g4), e2kt[u], a_p * (alpha1[u] + k_g4));
+    td = RT[u] * fnma2(Tnos[u], td, k2e[u] * fma2(alpha1[u], mu, gamma4[u]));
+    const f2 lim = one - Tnos[u];
+    rd = max2(splat2(0.0f), min2(rd, lim));
+    td = max2(splat2(0.0f), min2(td, lim - rd));
+    Rdir[u] = rd;
+    Tdir[u] = td;
+  }
+}
+
 struct SwV5Params {
   SwParams b;
   int ngroups;
+  int warp_smem;
 };
 
 // Reverse-buffer row of one layer: 32 lanes x (e, f) 16 B, then 32 lanes x alpha_above 8 B = 768 B
 constexpr int SWROW = 768;
 
 template <bool FAST, bool HAS_G, bool TOP>
-__global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
+__global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_ssa, const __grid_constant__ CUtensorMap tm_g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int U = SW_U, S = SW_S;
   const SwParams& p = pp.b;
   constexpr int NIN = HAS_G ? 3 : 2;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
   const int G = p.ngpt, L = p.nlay;
   const uint64_t pol_in = policy_evict_first();
   const uint64_t pol_buf = policy_evict_last();
@@ -481,11 +573,12 @@ __global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5P
   const int chunk = (int)cluster.block_rank();
   const int csize = (int)cluster.num_blocks();
 
-  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
   uint8_t* in_ring = smem;                                     // [S][NIN][U][256 B]: tau, ssa (, g)
   uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][U][768 B]
-  uint8_t* bb = ob + 2 * U * SWROW;                            // [S][U][768 B]
-  float* part = reinterpret_cast<float*>(bb + S * U * SWROW);  // [2 sets][3][L+1]
+  uint8_t* bb = smem;                                          // [S][U][768 B]  (aliases in_ring / ob, see lw_solver_v5)
+  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * U * SWROW, BWD_BYTES = S * U * SWROW;
+  float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][3][L+1]
   const int part_set = 3 * (L + 1) + ((L + 1) & 1);            // keep the barriers 8-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
   const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
@@ -503,13 +596,17 @@ __global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5P
   const f2 live = splat2(act ? 1.0f : 0.0f);
   const int NG = pp.ngroups;
   const int NGF = L / U;
-  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + (size_t)blockIdx.x * L * SWROW;
+  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * SWROW;
   const uint32_t lane_in = (uint32_t)lane * 8u;
   const uint32_t lane_ef = (uint32_t)lane * 16u, lane_al = 512u + (uint32_t)lane * 8u;
   const int top_level = TOP ? 0 : L;
 
   int ncols_done = 0;
-  for (int col = blockIdx.x / csize; col < p.ncol; col += gridDim.x / csize, ++ncols_done) {
+  // The warps of a CTA take adjacent columns; all warps of a cluster make the same number of trips (one cluster barrier
+  // each), a warp past the last column recomputes it and does not write.
+  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
+    const bool owner = cb + warp < p.ncol;
+    const int col = owner ? cb + warp : p.ncol - 1;
     float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [3][L+1]
     float* fdn = fup + (L + 1);
     float* fdr = fdn + (L + 1);
@@ -596,8 +693,7 @@ __global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5P
       flush_fwd();
       // layer coefficients: independent across the U layers (instruction-level parallelism)
       f2 Rdif[U], Tdif[U], Rdir[U], Tdir[U], Tnos[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) two_stream2<FAST, HAS_G>(tau[u], w0[u], gg[u], mu0, mu0_inv, Rdif[u], Tdif[u], Rdir[u], Tdir[u], Tnos[u]);
+      two_stream2_batch<FAST, HAS_G, U>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
       if (lane == 0) bulk_wait_read<1>();
       __syncwarp();
       uint8_t* ot = ob + (k & 1) * (U * SWROW);
@@ -708,7 +804,7 @@ __global__ void __launch_bounds__(32) sw_solver_v5(const __grid_constant__ SwV5P
     {
       float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1), p.flux_dir + (size_t)col * (L + 1)};
       const int n = 3 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
-      for (int i = lo + lane; i < hi; i += 32) {
+      for (int i = lo + lane; i < hi && owner; i += 32) {
         float sacc = 0.0f;
         for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
         const int a = i / (L + 1);
@@ -760,15 +856,17 @@ static int resident_clusters5(const rrnn_ctx_t* ctx, int occ_clusters, int csize
   return (int)std::max<long long>(n, 1);
 }
 
+// One warp is one solver (a 64-g-point chunk of one column); a CTA carries `solver_warps` of them on adjacent columns
+// because a cluster launch keeps at most 8 CTAs per SM resident (cudaOccupancyMaxActiveClusters: 284 clusters of 4 on
+// 148 SMs whatever the shared memory).  Measured at 137 layers: the SW sweeps gain 12-15 % from 13 warps per SM
+// (2 per CTA, scratch beyond L2 notwithstanding); the LW sweeps are DRAM-limited by then and stay at 1 per CTA.
 template <typename K, typename P>
-static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t smem, size_t per_cta_scratch, int default_mb, int ncol, P& pp,
+static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_smem, size_t warp_scratch, int default_mb, int default_warps, int ncol, P& pp,
                             float** scratch_slot, const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2) {
-  RRNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  warp_smem = (warp_smem + 127) & ~(size_t)127;
+  pp.warp_smem = (int)warp_smem;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
-  cfg.gridDim = dim3((unsigned)csize);
-  cfg.blockDim = dim3(32);
-  cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)csize;
@@ -776,12 +874,26 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t smem, s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int occ = 0;
-  RRNN_CUDA(cudaOccupancyMaxActiveClusters(&occ, kernel, &cfg));
-  const int ncl = resident_clusters5(ctx, std::max(occ, 1), csize, per_cta_scratch, ncol, default_mb);
+  int W = std::min(std::max(ctx->solver_warps > 0 ? ctx->solver_warps : default_warps, 1), v5::MAX_WARPS);
+  int occ = 0, ncl = 1;
+  size_t smem = 0;
+  for (;; --W) {
+    smem = 128 + (size_t)W * warp_smem;
+    RRNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.gridDim = dim3((unsigned)csize);
+    cfg.blockDim = dim3(32u * (unsigned)W);
+    cfg.dynamicSmemBytes = smem;
+    RRNN_CUDA(cudaOccupancyMaxActiveClusters(&occ, kernel, &cfg));
+    ncl = resident_clusters5(ctx, std::max(occ, 1), csize, warp_scratch * W, (ncol + W - 1) / W, default_mb);
+    // few columns: spread them over more CTAs instead of stacking them in one
+    if (W == 1 || ctx->solver_warps > 0 || (long long)ncl * W <= ncol) break;
+  }
   const int ncta = ncl * csize;
+  static const bool dbg = getenv("RRNN_SOLVER_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "[rrnn] solver v5: csize %d warps %d smem %zu occ_clusters %d -> resident %d (%.1f warps/SM, scratch %.1f MB)\n", csize, W, smem,
+                   occ, ncl, (double)ncta * W / ctx->num_sms, (double)ncta * W * warp_scratch / 1048576.0);
   cfg.gridDim = dim3((unsigned)ncta);
-  if (int rc = ensure_scratch(ctx, (size_t)ncta * per_cta_scratch)) return rc;
+  if (int rc = ensure_scratch(ctx, (size_t)ncta * W * warp_scratch)) return rc;
   *scratch_slot = (float*)ctx->scratch;
   RRNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, pp, t0, t1, t2));
   return 0;
@@ -805,10 +917,10 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
   if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, v5::LW_U)) return rc;
   if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, v5::LW_U)) return rc;
   if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev, v5::LW_U)) return rc;
-  const size_t smem = 128 + (size_t)v5::LW_S * 3 * v5::LW_U * 256 + 2 * v5::LW_U * 512 + (size_t)v5::LW_S * v5::LW_U * 512 + 4 * (size_t)(L + 1) * 4 + 2 * v5::LW_S * 8;
+  const size_t smem = std::max<size_t>((size_t)v5::LW_S * 3 * v5::LW_U * 256 + 2 * v5::LW_U * 512, (size_t)v5::LW_S * v5::LW_U * 512) + 4 * (size_t)(L + 1) * 4 + 2 * v5::LW_S * 8;
   const size_t per_cta = (size_t)L * 512;
   const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
-#define LW5(F, T, D) launch_clustered(ctx, v5::lw_solver_v5<F, T, D>, csize, smem, per_cta, 96, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev)
+#define LW5(F, T, D) launch_clustered(ctx, v5::lw_solver_v5<F, T, D>, csize, smem, per_cta, 96, 1, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev)
   if (fast) {
     if (top) return LW5(true, true, true);
     return dn_ext ? LW5(true, false, true) : LW5(true, false, false);
@@ -838,11 +950,11 @@ int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, v5::SW_U)) return rc; }
   else tm_g = tm_ssa;
   const int nin = p.g ? 3 : 2;
-  const size_t smem = 128 + (size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_U * v5::SWROW + (size_t)v5::SW_S * v5::SW_U * v5::SWROW +
+  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_U * v5::SWROW, (size_t)v5::SW_S * v5::SW_U * v5::SWROW) +
                       2 * (size_t)(3 * (L + 1) + 1) * 4 + 2 * v5::SW_S * 8;
   const size_t per_cta = (size_t)L * v5::SWROW;
   const bool top = p.top_at_1 != 0;
-#define SW5(F, HG, T) launch_clustered(ctx, v5::sw_solver_v5<F, HG, T>, csize, smem, per_cta, 160, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
+#define SW5(F, HG, T) launch_clustered(ctx, v5::sw_solver_v5<F, HG, T>, csize, smem, per_cta, 250, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
   if (fast) {
     if (p.g) return top ? SW5(true, true, true) : SW5(true, true, false);
     return top ? SW5(true, false, true) : SW5(true, false, false);

@@ -230,6 +230,40 @@ def test_sw_solver_alone_with_scattering(gpu_ctx, solver_variant):
             assert d.max() <= 6e-5 * scale and np.sqrt((d ** 2).mean()) <= 6e-6 * scale, (G, L, C, top, d.max() / scale)
 
 
+@pytest.mark.parametrize("warps", [2, 3, 4])
+def test_solvers_per_cta_do_not_change_the_fluxes(gpu_ctx, warps):
+    """`solver_warps` only changes which warp of which CTA takes a column: every setting must give bit-identical
+    fluxes (the g-point chunks are combined in a fixed order), also when the column count is not a multiple of it
+    and when there are more columns than resident solvers."""
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    rng = np.random.default_rng(11)
+    P = api._ptr
+    try:
+        for (G, L, C, top) in [(256, 21, 7, True), (224, 60, 1, False), (224, 17, 3001, True)]:
+            tau = torch.from_numpy(rng.gamma(0.4, 1.5, size=(C, L, G)).astype(np.float32)).cuda()
+            a = torch.from_numpy(rng.uniform(0.05, 0.95, size=(C, L, G)).astype(np.float32)).cuda()
+            lev = torch.from_numpy(rng.uniform(0.1, 2.0, size=(C, L + 1, G)).astype(np.float32)).cuda()
+            sfc = torch.from_numpy(rng.uniform(0.1, 0.9, size=(C, G)).astype(np.float32)).cuda()
+            mu0 = torch.from_numpy(rng.uniform(0.05, 1.0, size=C).astype(np.float32)).cuda()
+            Ds = np.array([1.66], np.float32); w = np.array([0.5], np.float32)
+            res = {}
+            for W in (1, warps):
+                gpu_ctx.set_flag("solver_warps", W)
+                fl = [torch.zeros((C, L + 1), device="cuda") for _ in range(5)]
+                _lib.check(_lib.lib().rrnn_lw_solver_noscat(gpu_ctx.h, G, L, C, int(top), 1, Ds.ctypes.data_as(_lib.c_float_p),
+                                                            w.ctypes.data_as(_lib.c_float_p), None, P(tau), P(a), P(lev), P(sfc), P(sfc),
+                                                            P(fl[0]), P(fl[1])))
+                _lib.check(_lib.lib().rrnn_sw_solver_2stream(gpu_ctx.h, G, L, C, int(top), P(sfc), None, P(tau), P(a), None, P(mu0),
+                                                             P(sfc), P(sfc), P(fl[2]), P(fl[3]), P(fl[4])))
+                res[W] = [f.cpu().numpy() for f in fl]
+            for x, y in zip(res[1], res[warps]):
+                assert np.isfinite(x).all() and np.abs(x).max() > 0
+                assert np.array_equal(x, y), (G, L, C, top, np.abs(x - y).max())
+    finally:
+        gpu_ctx.set_flag("solver_warps", 0)
+
+
 def test_sgemm_entry_points(gpu_ctx):
     """output_sgemm_tau / _pfrac / _lw on materialised inputs (+ compute_nn_inputs, get_col_dry, Planck source)."""
     import oracle as O

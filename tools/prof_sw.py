@@ -1,4 +1,4 @@
-"""One SW (or LW) solver launch on synthetic optical properties for ncu: python tools/prof_sw.py sw|lw ncol nlay scratch_mb"""
+"""One SW (or LW) solver launch on synthetic optical properties for ncu: python tools/prof_sw.py sw|lw ncol nlay scratch_mb [warps]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT]
@@ -7,6 +7,8 @@ from rte_rrtmgp_nn_b200 import api, _lib
 which, ncol, nlay, mb = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 ctx = api.default_context(0)
 ctx.set_flag("solver_scratch_mb", mb)
+if len(sys.argv) > 5:
+    ctx.set_flag("solver_warps", int(sys.argv[5]))
 P = api._ptr
 g = torch.Generator(device="cuda").manual_seed(1)
 mk = lambda *s: torch.rand(*s, device="cuda", generator=g)
