@@ -399,6 +399,71 @@ def test_cloud_optics_increment_delta_scale(gpu_ctx):
                 assert np.allclose(got.cpu().numpy(), w, rtol=2e-5, atol=1e-7)
 
 
+def test_all_sky_fluxes_match_oracle(gpu_ctx):
+    """BASELINE config 3 at test size, the body of examples/all-sky/rrtmgp_allsky.F90:366-446: NN gas optics -> LUT cloud
+    optics (-> delta_scale, SW) -> clouds%increment(atmos) -> rte_lw / rte_sw (g != 0 in cloudy layers) -> broadband fluxes,
+    against the same chain of oracle functions."""
+    import os
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    torch = _torch()
+    ncol, nlay = 48, 60
+    atm = synth.make_atmosphere(ncol, nlay, seed=33)
+    cl = synth.make_clouds(atm)
+    assert (cl["lwp"] > 0).any()
+    mk = lambda: torch.empty((ncol, nlay + 1), device="cuda")
+    lut = lambda band: api.load_cloud_lut_file(os.path.join(H.ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc"))
+    # ---- LW
+    kd = spectral.synthetic_kdist_lw(256)
+    k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_dist.load(kd) == ""
+    onets, dnets = H.oracle_nets(H.LW_G256), H.device_nets(gpu_ctx, H.LW_G256)
+    co = api.ty_cloud_optics(gpu_ctx); assert co.load(**lut("lw")) == ""
+    atmos = api.ty_optical_props_1scl(); assert atmos.alloc_1scl(ncol, nlay, k_dist) == ""
+    src = api.ty_source_func_lw(); assert src.alloc(ncol, nlay, k_dist) == ""
+    clouds = api.ty_optical_props_1scl(); assert clouds.alloc_1scl(ncol, nlay, k_dist, by_band=True) == ""
+    assert k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], H.gas_concs(atm["gases"]), atmos, src,
+                             tlev=atm["tlev"], neural_nets=dnets) == ""
+    assert co.cloud_optics(cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], clouds) == ""
+    assert clouds.increment(atmos) == ""
+    emis = np.repeat(atm["sfc_emis"][:, None], 16, 1)
+    fl = api.ty_fluxes_broadband(mk(), mk())
+    assert api.rte_lw(atmos, atm["top_at_1"], src, emis, fl) == ""
+    ref = O.gas_optics_lw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"])
+    ctau = O.cloud_optics_lut(co.tables, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], False)
+    tau = O.inc_1scalar_by_1scalar_bybnd(ref["tau"], ctau, kd["band_lims_gpt"])
+    rup, rdn = O.rte_lw(kd, atm["top_at_1"], tau, ref["lay_source"], ref["lev_source"], ref["sfc_source"], emis)
+    assert np.abs(fl.flux_up.cpu().numpy() - rup).max() <= H.FLUX_TOL
+    assert np.abs(fl.flux_dn.cpu().numpy() - rdn).max() <= H.FLUX_TOL
+    clear_up, _ = O.rte_lw(kd, atm["top_at_1"], ref["tau"], ref["lay_source"], ref["lev_source"], ref["sfc_source"], emis)
+    assert np.abs(clear_up - rup).max() > 1.0  # the clouds matter
+    # ---- SW
+    kd = spectral.synthetic_kdist_sw(224)
+    k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_dist.load(kd) == ""
+    onets, dnets = H.oracle_nets(H.SW_G224), H.device_nets(gpu_ctx, H.SW_G224)
+    co = api.ty_cloud_optics(gpu_ctx); assert co.load(**lut("sw")) == ""
+    atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(ncol, nlay, k_dist) == ""
+    clouds = api.ty_optical_props_2str(); assert clouds.alloc_2str(ncol, nlay, k_dist, by_band=True) == ""
+    toa = torch.empty((ncol, 224), device="cuda")
+    assert k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], H.gas_concs(atm["gases"]), atmos, toa, neural_nets=dnets) == ""
+    assert co.cloud_optics(cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], clouds) == ""
+    assert clouds.delta_scale() == ""
+    assert clouds.increment(atmos) == ""
+    alb = np.repeat(atm["sfc_alb"][:, None], 224, 1)
+    fl = api.ty_fluxes_broadband(mk(), mk(), None, mk())
+    assert api.rte_sw(atmos, atm["top_at_1"], atm["mu0"], toa, alb, alb, fl) == ""
+
+    def chain(fast):
+        r = O.gas_optics_sw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["gases"], fast=fast)
+        c = O.delta_scale_2str(*O.cloud_optics_lut(co.tables, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], True, fast=fast), fast=fast)
+        t, w, g = O.inc_2stream_by_2stream_bybnd(r["tau"], r["ssa"], r["g"], *c, kd["band_lims_gpt"], fast=fast)
+        assert np.abs(g).max() > 0.1
+        return O.rte_sw(atm["top_at_1"], atm["mu0"], r["toa_src"], alb, alb, t, w, g, fast=fast)
+
+    want, w64 = chain(False), chain("f64")
+    for got, a, b, nm in zip((fl.flux_up, fl.flux_dn, fl.flux_dn_dir), want, w64, ("up", "dn", "dir")):
+        H.assert_within_reference_noise(got.cpu().numpy(), a, b, H.FLUX_TOL, "all-sky SW flux_" + nm)
+
+
 def test_heating_rate_K_per_s(gpu_ctx):
     import oracle as O
     from rte_rrtmgp_nn_b200 import api
