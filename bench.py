@@ -91,12 +91,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def algorithmic_bytes_per_column(nlay, nx_lw=18, nx_sw=7):
-    """bytes each kernel must move per column (fp32), every array touched once."""
+def algorithmic_bytes_per_column(nlay, nx_lw=18, nx_sw=7, lw_compact=True):
+    """bytes each kernel must move per column (fp32), every array touched once.
+    lw_compact: the LW sources cross HBM factored -- tau, pfrac (G,L) and two band tables (16,L), (16,L+1) instead of
+    tau, lay_source (G,L) and lev_source (G,L+1); the denominators shrink with the traffic (8 instead of 12 B per g-point
+    and layer), so `frac` stays a statement about the bytes that really have to move."""
     L, G, H = nlay, NGPT_LW, NGPT_SW
+    lw_arrays = 4 * G * (2 * L) + 4 * 16 * (2 * L + 1) if lw_compact else 4 * G * (2 * L + (L + 1))
     return {
-        "gas_optics_lw": 4 * ((nx_lw + 1) * L + 2 * (L + 1) + 1) + 4 * G * (L + L + (L + 1) + 2),
-        "lw_solver": 4 * G * (2 * L + (L + 1) + 2) + 8 * (L + 1),
+        "gas_optics_lw": 4 * ((nx_lw + 1) * L + 2 * (L + 1) + 1) + lw_arrays + 4 * G * 2,
+        "lw_solver": lw_arrays + 4 * G * 2 + 8 * (L + 1),
         # g is identically zero on the NN path and is neither written nor read (2 arrays instead of 3)
         "gas_optics_sw": 4 * (nx_sw + 1) * L + 4 * H * (2 * L),
         "sw_solver": 4 * H * (2 * L + 3) + 4 + 12 * (L + 1),
@@ -212,6 +216,7 @@ def main():
     ap.add_argument("--sw-fast-math", type=int, default=0)
     ap.add_argument("--solver-variant", type=int, default=0, help="0 packed two-g-points-per-lane solvers, 1 one g-point per lane")
     ap.add_argument("--solver-scratch-mb", type=int, default=0, help="L2 budget of the packed solvers' reverse-sweep scratch (0 = default)")
+    ap.add_argument("--lw-compact-source", type=int, default=1, help="1 = LW sources stay factored between gas optics and solver (default), 0 = materialised lay/lev_source")
     ap.add_argument("--solver-warps", type=int, default=0, help="solvers (warps) per CTA in the v5 solver kernels (0 = default)")
     args = ap.parse_args()
     NLAY = args.nlay
@@ -250,6 +255,7 @@ def main():
     ctx.set_flag("solver_variant", args.solver_variant)
     ctx.set_flag("solver_scratch_mb", args.solver_scratch_mb)
     ctx.set_flag("solver_warps", args.solver_warps)
+    ctx.set_flag("lw_compact_source", args.lw_compact_source)
     if args.chunk:
         ctx.set_chunk_columns(args.chunk)
     k_lw = api.ty_gas_optics_rrtmgp(ctx); k_lw.load(spectral.synthetic_kdist_lw(NGPT_LW))
@@ -380,7 +386,7 @@ def main():
 
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peaks()
-    abytes = algorithmic_bytes_per_column(NLAY)
+    abytes = algorithmic_bytes_per_column(NLAY, lw_compact=bool(args.lw_compact_source) and args.solver_variant == 0)
     shares = {k: v[0] for k, v in prof.items()}
     tot = sum(shares.values()) or 1.0
     dom = max(shares, key=shares.get)
@@ -415,7 +421,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, ncol_total),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
-        "fast_math": int(args.fast_math), "nn_variant": "tcgen05 (fp16 hi/lo split operands, fp32 accumulation in TMEM)",
+        "fast_math": int(args.fast_math), "lw_compact_source": int(bool(args.lw_compact_source) and args.solver_variant == 0), "nn_variant": "tcgen05 (fp16 hi/lo split operands, fp32 accumulation in TMEM)",
         "solver_variant": {0: "v5 TMA-staged packed fp32x2", 2: "v4 packed fp32x2", 1: "v3 one g-point per lane"}[args.solver_variant],
     }
     print(json.dumps(line))

@@ -138,6 +138,18 @@ RRNN_API int rrnn_gas_optics_sw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const r
                                 const rrnn_gas_t* gases, int ngas, float* tau_d, float* ssa_d, float* g_d,
                                 float* toa_src_d);
 
+/* The same longwave gas optics with the sources left FACTORED (no reference counterpart; this library's fused path
+ * rrnn_lw_fluxes uses it): instead of lay_source(g,l) = pfrac(g,l) B_b(T_lay(l)) and lev_source (g,l) = pfrac(g,min(l,nlay))
+ * B_b(T_lev(l)) (compute_Planck_source_nn, rrtmgp/kernels/mo_gas_optics_kernels.F90:654-672) it returns their factors:
+ * pfrac_d (ngpt,nlay,ncol) and the band Planck functions planck_lay_d (16,nlay,ncol), planck_lev_d (16,nlay+1,ncol) (rows
+ * of 16 floats, bands >= nbnd repeat the last band).  8 instead of 12 bytes per (g-point, layer) cross HBM.  Two networks,
+ * tensor-core kernel only (an error otherwise); rrnn_lw_solver_noscat_compact consumes it with bit-identical fluxes. */
+RRNN_API int rrnn_gas_optics_lw_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models,
+                                        int nmodels, int ncol, int nlay, const float* play_d, const float* plev_d,
+                                        const float* tlay_d, const float* tsfc_d, const rrnn_gas_t* gases, int ngas,
+                                        const float* tlev_d, float* tau_d, float* pfrac_d, float* planck_lay_d,
+                                        float* planck_lev_d, float* sfc_source_d, float* sfc_source_Jac_d);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* RTE solvers (device pointers)                                                                      */
 /* lw_solver_noscat_GaussQuad / lw_solver_noscat, rte/kernels/mo_rte_solver_kernels.F90:332-415, 119-330
@@ -146,6 +158,14 @@ RRNN_API int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol
                                    const float* weights, const float* inc_flux_d, const float* tau_d,
                                    const float* lay_source_d, const float* lev_source_d, const float* sfc_emis_gpt_d,
                                    const float* sfc_source_d, float* flux_up_d, float* flux_dn_d);
+/* lw_solver_noscat_GaussQuad (mo_rte_solver_kernels.F90:332-415) on the factored sources of rrnn_gas_optics_lw_compact:
+ * the solver forms lay_source / lev_source itself (one fp32 product, as mo_gas_optics_kernels.F90:654-672).  kd supplies
+ * the g-point -> band map.  Needs ngpt % 4 == 0, ngpt <= 512, nlay >= 8. */
+RRNN_API int rrnn_lw_solver_noscat_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int nmus,
+                                           const float* Ds, const float* weights, const float* tau_d, const float* pfrac_d,
+                                           const float* planck_lay_d, const float* planck_lev_d,
+                                           const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d,
+                                           float* flux_dn_d);
 /* rte_lw for ty_optical_props_1scl, rte/mo_rte_lw.F90:60-424: sfc_emis_d is (nbnd,ncol) and is expanded to
  * g-points (:429-447); n_gauss_angles in 1..4 with the secants/weights of :113-125. */
 RRNN_API int rrnn_rte_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,

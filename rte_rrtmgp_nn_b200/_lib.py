@@ -75,6 +75,10 @@ _SIGS = {
     "rrnn_planck_source_nn": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, vp]),
     "rrnn_gas_optics_lw": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
                                      C.POINTER(rrnn_gas_t), C.c_int, vp, vp, vp, vp, vp, vp]),
+    "rrnn_gas_optics_lw_compact": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
+                                             C.POINTER(rrnn_gas_t), C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "rrnn_lw_solver_noscat_compact": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, vp, vp, vp, vp,
+                                                vp, vp, vp, vp]),
     "rrnn_gas_optics_sw": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, vp, vp, vp, C.POINTER(rrnn_gas_t), C.c_int,
                                      vp, vp, vp, vp]),
     "rrnn_lw_solver_noscat": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, vp, vp, vp,

@@ -495,6 +495,24 @@ class ty_gas_optics_rrtmgp(ty_optical_props):
             return str(e)
         return ""
 
+    def gas_optics_compact(self, play, plev, tlay, tsfc, gas_desc, tau, pfrac, planck_lay, planck_lev, sfc_source, sfc_source_Jac,
+                           tlev=None, neural_nets=None):
+        """LW gas optics with the sources left factored (rrnn_gas_optics_lw_compact, no reference counterpart): device
+        tensors tau, pfrac (ncol,nlay,ngpt), planck_lay (ncol,nlay,16), planck_lev (ncol,nlay+1,16), sfc_source[_Jac] (ncol,ngpt)."""
+        ctx = self.ctx
+        play, plev, tlay, tsfc = _dev(play, ctx), _dev(plev, ctx), _dev(tlay, ctx), _dev(tsfc, ctx)
+        ncol, nlay = play.shape
+        models = (vp * 2)(*[n.h for n in neural_nets][:2])
+        try:
+            tlev_d = _dev(tlev, ctx)
+            gases, ngas, keep = gas_desc._to_c(ctx)
+            _lib.check(_lib.lib().rrnn_gas_optics_lw_compact(ctx.h, self._kd.h, models, len(neural_nets), ncol, nlay, _ptr(play), _ptr(plev),
+                                                             _ptr(tlay), _ptr(tsfc), gases, ngas, _ptr(tlev_d), _ptr(tau), _ptr(pfrac),
+                                                             _ptr(planck_lay), _ptr(planck_lev), _ptr(sfc_source), _ptr(sfc_source_Jac)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
 
 def rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes, inc_flux=None, n_gauss_angles=None, use_2stream=None,
            lw_Ds=None, flux_up_Jac=None, flux_dn_Jac=None):

@@ -350,6 +350,7 @@ extern "C" int rrnn_ctx_set_flag(rrnn_ctx_t* c, const char* name, int value) {
   else if (s == "sw_fast_math") c->sw_fast_math = value ? 1 : 0;
   else if (s == "solver_buffer") c->solver_buffer = value;
   else if (s == "nn_tensor_cores") c->nn_tensor_cores = value ? 1 : 0;
+  else if (s == "lw_compact_source") c->lw_compact_source = value ? 1 : 0;
   else if (s == "solver_variant") c->solver_variant = value;
   else if (s == "solver_scratch_mb") c->solver_scratch_mb = value;
   else if (s == "solver_warps") c->solver_warps = value;

@@ -620,7 +620,8 @@ using namespace rrnn;
 int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol, int nlay,
                        const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
                        const rrnn_gas_t* gases, int ngas, float* out0, float* out1, float* out2, float* sfc_source,
-                       float* sfc_jac, int prof_kind);  // gas_optics_tc.cu; -1 = configuration not supported
+                       float* sfc_jac, int prof_kind, float* planck_lay = nullptr,
+                       float* planck_lev = nullptr);  // gas_optics_tc.cu; -1 = configuration not supported
 
 extern "C" int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
                                   int ncol, int nlay, const float* play_d, const float* plev_d, const float* tlay_d,
@@ -672,6 +673,32 @@ extern "C" int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
     rc = launch_go<EPI_LWBOTH>(ctx, p, 256, K_GAS_LW);
   }
   if (tlev_tmp) cudaFreeAsync(tlev_tmp, ctx->stream);
+  return rc;
+}
+
+// Longwave gas optics with the sources left factored (see include/rrnn.h): tensor-core kernel only.
+extern "C" int rrnn_gas_optics_lw_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                                          int ncol, int nlay, const float* play_d, const float* plev_d, const float* tlay_d,
+                                          const float* tsfc_d, const rrnn_gas_t* gases, int ngas, const float* tlev_d,
+                                          float* tau_d, float* pfrac_d, float* planck_lay_d, float* planck_lev_d,
+                                          float* sfc_source_d, float* sfc_source_Jac_d) {
+  RRNN_CHECK(ctx && kd && models, "gas_optics(): null handle");
+  RRNN_CHECK(nmodels == 2, "gas_optics (compact sources): needs the absorption and the Planck-fraction network");
+  RRNN_CHECK(kd->d_totplnk, "gas_optics(): k-distribution has no Planck table (not a longwave k-distribution)");
+  RRNN_CHECK(nlay >= 2 && ncol >= 0, "gas_optics(): bad extents");
+  RRNN_CHECK(tau_d && pfrac_d && planck_lay_d && planck_lev_d && sfc_source_d && sfc_source_Jac_d, "gas_optics (compact sources): null output");
+  for (int n = 0; n < nmodels; ++n) RRNN_CHECK(on_device(models[n]), "gas_optics(): network was loaded without a device context");
+  if (ncol == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  float* tlev_tmp = nullptr;
+  if (!tlev_d) {
+    RRNN_CUDA(cudaMallocAsync((void**)&tlev_tmp, (size_t)ncol * (nlay + 1) * sizeof(float), ctx->stream));
+    if (int rc = rrnn_interp_tlev(ctx, ncol, nlay, play_d, plev_d, tlay_d, tlev_tmp)) return rc;
+  }
+  const int rc = rrnn_gas_optics_tc(ctx, 0, kd, models, ncol, nlay, play_d, plev_d, tlay_d, tlev_d ? tlev_d : tlev_tmp, tsfc_d, gases,
+                                    ngas, tau_d, pfrac_d, nullptr, sfc_source_d, sfc_source_Jac_d, K_GAS_LW, planck_lay_d, planck_lev_d);
+  if (tlev_tmp) RRNN_CUDA(cudaFreeAsync(tlev_tmp, ctx->stream));
+  if (rc < 0) return fail("gas_optics (compact sources): configuration not supported by the tensor-core kernel");
   return rc;
 }
 

@@ -77,6 +77,7 @@ struct Params {
   const float* totplnk;
   float temp_ref_min, totplnk_delta;
   float *sfc_source, *sfc_jac;
+  float *planck_lay, *planck_lev;  // COMPACT only: band Planck functions, rows of 16 floats per layer / level
   unsigned* dbg;   // debug only (RRNN_TC_DEBUG): host-mapped progress words, else null
   int dbg_flags;   // 2 = issue no TMA store, 4 = first box only
 };
@@ -332,7 +333,7 @@ __device__ __forceinline__ float col_dry_of(float h2o, float p0, float p1) {
 
 // MODE 0 = LW (net 0: absorption -> tau; net 1: Planck fraction -> lay_source, lev_source, sfc_source[_Jac])
 // MODE 1 = SW (net 0: absorption, net 1: Rayleigh -> tau = abs + ray, ssa = ray / tau)
-template <int MODE>
+template <int MODE, bool COMPACT>
 __global__ void __launch_bounds__(THREADS, 1)
 gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap tm0,
                      const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
@@ -760,6 +761,33 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
           int b4[8];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) b4[j4] = band4_s[(g0 >> 2) + j4];
+          if (COMPACT) {
+            // The sources stay factored: the Planck fraction goes out as it is, and the band Planck functions of this
+            // row (16 floats for T_lay, 16 for T_lev; written once per row, by the job of the first g-points) are
+            // multiplied in by lw_solver_v5<COMPACT> -- the same single fp32 product, 8 instead of 12 bytes per g-point.
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = z[32 + j];
+            stage_and_store(squeezed ? &tm1s : &tm1, o, g0, slot_row, dest_lay, nrows_lay);
+            if (c == 0 && valid) {
+              float4* bv_out = reinterpret_cast<float4*>(p.planck_lev + (size_t)s * 16);
+              float4* bl_out = reinterpret_cast<float4*>(p.planck_lay + ((size_t)col * L + lev) * 16);
+#pragma unroll 1
+              for (int q4 = 0; q4 < 4; ++q4) {
+                float vl[4], vv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int b = min(4 * q4 + e, p.nbnd - 1);
+                  const float* tl = tp_l + b * p.ntemp;
+                  const float* tv = tp_v + b * p.ntemp;
+                  const float l0 = tl[0], v0 = tv[0];
+                  vl[e] = l0 + frac_l * (tl[1] - l0);
+                  vv[e] = v0 + frac_v * (tv[1] - v0);
+                }
+                bv_out[q4] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                if (lev < L) bl_out[q4] = make_float4(vl[0], vl[1], vl[2], vl[3]);
+              }
+            }
+          } else {
           float bl = 0.0f, bv = 0.0f;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -783,6 +811,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
             mul2to(o[4 * j4 + 2], o[4 * j4 + 3], z[34 + 4 * j4], z[35 + 4 * j4], bv);
           }
           stage_and_store(&tm2, o, g0, lane, w0, p.nrows);
+          }
           if (is_sfc) {  // surface source and its Jacobian: one row per column, written by the owning lane
             float* ss = p.sfc_source + (size_t)col * G + g0;
             float* sj = p.sfc_jac + (size_t)col * G + g0;
@@ -1034,12 +1063,24 @@ static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn
   return -1;
 }
 
+// Does the tensor-core kernel take this configuration?  (pipeline.cu decides the workspace layout with it)
+bool rrnn_gas_optics_tc_can(const rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int nlay,
+                            bool compact) {
+  if (!ctx->nn_tensor_cores || nmodels != 2 || !models[0] || !models[1]) return false;
+  if (!tc_supported(models, kd, mode)) return false;
+  if (mode == 0 && nlay < 31) return false;
+  if (compact && (mode != 0 || kd->nbnd > 16)) return false;
+  return true;
+}
+
 // Launch the tensor-core gas optics; returns -1 if the configuration is not supported (caller falls back).
 int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol, int nlay,
                        const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
                        const rrnn_gas_t* gases, int ngas, float* out0, float* out1, float* out2, float* sfc_source,
-                       float* sfc_jac, int prof_kind) {
+                       float* sfc_jac, int prof_kind, float* planck_lay, float* planck_lev) {
   if (!tc_supported(models, kd, mode)) return -1;
+  const bool compact = planck_lay != nullptr;  // LW only: out1 receives the Planck fraction, out2 is not written
+  if (compact && (mode != 0 || !planck_lev || kd->nbnd > 16)) return -1;
   const int period = (mode == 0) ? nlay + 1 : nlay;
   if (mode == 0 && nlay < 31) return -1;  // at most one extra (bottom-level) row per warp of 32 rows
   if ((long long)ncol * period >= (1LL << 31) - tc::TM) return -1;
@@ -1086,12 +1127,14 @@ int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const 
   p.play = play; p.plev = plev; p.tlay = tlay; p.tlev = tlev; p.tsfc = tsfc;
   p.totplnk = kd->d_totplnk; p.temp_ref_min = kd->temp_ref_min; p.totplnk_delta = kd->totplnk_delta;
   p.sfc_source = sfc_source; p.sfc_jac = sfc_jac;
+  p.planck_lay = planck_lay; p.planck_lev = planck_lev;
   CUtensorMap tm0, tm1, tm2, tm0s, tm1s;
   const unsigned long long nrows_lay = (unsigned long long)ncol * nlay;
   if (int rc = tc::make_map(&tm0, out0, kd->ngpt, nrows_lay, 32)) return rc;
   if (int rc = tc::make_map(&tm1, out1, kd->ngpt, nrows_lay, 32)) return rc;
   if (mode == 0) {
-    if (int rc = tc::make_map(&tm2, out2, kd->ngpt, (unsigned long long)ncol * (nlay + 1), 32)) return rc;
+    if (compact) tm2 = tm1;
+    else if (int rc = tc::make_map(&tm2, out2, kd->ngpt, (unsigned long long)ncol * (nlay + 1), 32)) return rc;
     if (int rc = tc::make_map(&tm0s, out0, kd->ngpt, nrows_lay, 31)) return rc;
     if (int rc = tc::make_map(&tm1s, out1, kd->ngpt, nrows_lay, 31)) return rc;
   } else {
@@ -1113,12 +1156,15 @@ int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const 
     p.dbg = dptr;
   }
   const int ps = prof_begin(ctx, prof_kind);
-  if (mode == 0) {
-    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache.smem));
-    tc::gas_optics_tc_kernel<0><<<grid, tc::THREADS, cache.smem, ctx->stream>>>(p, tm0, tm1, tm2, tm0s, tm1s);
+  if (mode == 0 && compact) {
+    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache.smem));
+    tc::gas_optics_tc_kernel<0, true><<<grid, tc::THREADS, cache.smem, ctx->stream>>>(p, tm0, tm1, tm2, tm0s, tm1s);
+  } else if (mode == 0) {
+    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache.smem));
+    tc::gas_optics_tc_kernel<0, false><<<grid, tc::THREADS, cache.smem, ctx->stream>>>(p, tm0, tm1, tm2, tm0s, tm1s);
   } else {
-    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache.smem));
-    tc::gas_optics_tc_kernel<1><<<grid, tc::THREADS, cache.smem, ctx->stream>>>(p, tm0, tm1, tm2, tm0s, tm1s);
+    RRNN_CUDA(cudaFuncSetAttribute(tc::gas_optics_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache.smem));
+    tc::gas_optics_tc_kernel<1, false><<<grid, tc::THREADS, cache.smem, ctx->stream>>>(p, tm0, tm1, tm2, tm0s, tm1s);
   }
   prof_end(ctx, prof_kind, ps);
   RRNN_LAUNCH_CHECK(ctx);

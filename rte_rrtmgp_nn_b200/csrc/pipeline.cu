@@ -8,6 +8,12 @@
 #include <algorithm>
 
 namespace rrnn {
+bool lw_v5_supports(int G, int L);  // rte_solvers_v5.cu
+}
+bool rrnn_gas_optics_tc_can(const rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int nlay,
+                            bool compact);  // gas_optics_tc.cu
+
+namespace rrnn {
 
 __global__ void bcast_col_kernel(int ngpt, int ncol, const float* __restrict__ percol, float* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,8 +53,17 @@ static int ensure_ws(rrnn_ctx_t* ctx, size_t bytes) {
 
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
-static size_t lw_ws_bytes(int G, int L, int nc) {
+static size_t lw_ws_bytes(int G, int L, int nc, bool compact) {
+  if (compact)  // tau, pfrac, planck_lay, planck_lev, sfc_source, sfc_source_Jac, sfc_emis_gpt
+    return 4 * (align256((size_t)nc * L * G) * 2 + align256((size_t)nc * L * 16) + align256((size_t)nc * (L + 1) * 16) + 3 * align256((size_t)nc * G));
   return 4 * (align256((size_t)nc * L * G) * 2 + align256((size_t)nc * (L + 1) * G) + 3 * align256((size_t)nc * G));
+}
+
+// rrnn_lw_fluxes keeps the sources factored between its two kernels when both take that form (gas_optics_tc.cu,
+// rte_solvers_v5.cu); the fluxes are bit-identical either way (tested).
+static bool lw_compact(const rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int L) {
+  return ctx->lw_compact_source && ctx->solver_variant == 0 && lw_v5_supports(kd->ngpt, L) &&
+         rrnn_gas_optics_tc_can(ctx, 0, kd, models, nmodels, L, true);
 }
 static size_t sw_ws_bytes(int G, int L, int nc) {
   return 4 * (align256((size_t)nc * L * G) * 2 + 2 * align256((size_t)nc * G) + align256((size_t)nc));
@@ -82,15 +97,28 @@ static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
                                         {0.2009319137f, 0.2292411064f, 0.0698269799f, 0.f},
                                         {0.1355069134f, 0.2034645680f, 0.1298475476f, 0.0311809710f}};
   const int G = kd->ngpt;
+  const size_t n = (size_t)G * nc;
   float* tau = ws;
   float* lay = tau + align256((size_t)nc * L * G);
+  if (lw_compact(ctx, kd, models, nmodels, L)) {
+    float* bl = lay + align256((size_t)nc * L * G);
+    float* bv = bl + align256((size_t)nc * L * 16);
+    float* ssrc = bv + align256((size_t)nc * (L + 1) * 16);
+    float* sjac = ssrc + align256((size_t)nc * G);
+    float* egpt = sjac + align256((size_t)nc * G);
+    if (int rc = rrnn_gas_optics_lw_compact(ctx, kd, models, nmodels, nc, L, play, plev, tlay, tsfc, gases, ngas, tlev, tau, lay, bl, bv, ssrc, sjac))
+      return rc;
+    bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
+    RRNN_LAUNCH_CHECK(ctx);
+    return rrnn_lw_solver_noscat_compact(ctx, kd, L, nc, top_at_1, nang, gauss_Ds[nang - 1], gauss_wts[nang - 1], tau, lay, bl, bv, egpt,
+                                         ssrc, fup, fdn);
+  }
   float* lev = lay + align256((size_t)nc * L * G);
   float* ssrc = lev + align256((size_t)nc * (L + 1) * G);
   float* sjac = ssrc + align256((size_t)nc * G);
   float* egpt = sjac + align256((size_t)nc * G);
   if (int rc = rrnn_gas_optics_lw(ctx, kd, models, nmodels, nc, L, play, plev, tlay, tsfc, gases, ngas, tlev, tau, lay, lev, ssrc, sjac))
     return rc;
-  const size_t n = (size_t)G * nc;
   bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
   RRNN_LAUNCH_CHECK(ctx);
   return rrnn_lw_solver_noscat(ctx, G, L, nc, top_at_1, nang, gauss_Ds[nang - 1], gauss_wts[nang - 1], nullptr, tau, lay, lev,
@@ -133,8 +161,9 @@ extern "C" int rrnn_lw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrn
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const int G = kd->ngpt, L = nlay;
-  const int chunk = pick_chunk(ctx, ncol, lw_ws_bytes(G, L, 1));
-  if (int rc = ensure_ws(ctx, lw_ws_bytes(G, L, chunk))) return rc;
+  const bool compact = lw_compact(ctx, kd, models, nmodels, L);
+  const int chunk = pick_chunk(ctx, ncol, lw_ws_bytes(G, L, 1, compact));
+  if (int rc = ensure_ws(ctx, lw_ws_bytes(G, L, chunk, compact))) return rc;
   std::vector<rrnn_gas_t> gs;
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int nc = std::min(chunk, ncol - c0);
@@ -203,9 +232,10 @@ static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, c
   size_t in_per_col = 0;
   for (auto& f : fields) if (f.host) in_per_col += f.per_col;
   const size_t out_per_col = (size_t)nout * (L + 1);
-  const size_t opt_per_col = lw ? lw_ws_bytes(G, L, 1) : sw_ws_bytes(G, L, 1);
+  const bool compact = lw && lw_compact(ctx, kd, models, nmodels, L);
+  const size_t opt_per_col = lw ? lw_ws_bytes(G, L, 1, compact) : sw_ws_bytes(G, L, 1);
   const int chunk = pick_chunk(ctx, ncol, opt_per_col + 8 * (in_per_col + out_per_col));
-  const size_t opt_bytes = lw ? lw_ws_bytes(G, L, chunk) : sw_ws_bytes(G, L, chunk);
+  const size_t opt_bytes = lw ? lw_ws_bytes(G, L, chunk, compact) : sw_ws_bytes(G, L, chunk);
   size_t stage_floats = 0;
   for (auto& f : fields) if (f.host) stage_floats += 2 * align256(f.per_col * chunk);
   stage_floats += 2 * (size_t)nout * align256((size_t)(L + 1) * chunk);

@@ -481,6 +481,45 @@ extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int nc
   return 0;
 }
 
+namespace rrnn {
+// rrnn_lw_solver_noscat on compact sources (pipeline.cu, rrnn_lw_fluxes): lay_source = pfrac * planck_lay and
+// lev_source = pfrac * planck_lev are formed inside lw_solver_v5 (see there).  Only the default solver variant has it.
+int lw_solver_noscat_compact(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* Ds, const float* weights,
+                             const float* tau_d, const float* pfrac_d, const float* planck_lay_d, const float* planck_lev_d,
+                             const int* gpt2band_d, const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d,
+                             float* flux_dn_d) {
+  if (ncol == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  LwParams p{};
+  p.ngpt = ngpt; p.nlay = nlay; p.ncol = ncol; p.top_at_1 = top_at_1 ? 1 : 0; p.nmus = nmus;
+  p.bug_compat = ctx->lw_source_bug_compat;
+  p.nchunks = (ngpt + 31) / 32;
+  for (int i = 0; i < nmus; ++i) { p.Ds[i] = Ds[i]; p.wts[i] = weights[i]; }
+  p.tau = tau_d; p.lay_source = pfrac_d; p.planck_lay = planck_lay_d; p.planck_lev = planck_lev_d; p.gpt2band = gpt2band_d;
+  p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
+  const int ps = prof_begin(ctx, K_LW_SOLVER);
+  const int rc = launch_lw_v5(ctx, p);
+  if (rc < 0) return fail("lw_solver (compact sources): shape not supported by the packed kernel");
+  if (rc > 0) return rc;
+  prof_end(ctx, K_LW_SOLVER, ps);
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+}  // namespace rrnn
+
+extern "C" int rrnn_lw_solver_noscat_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int nmus,
+                                             const float* Ds, const float* weights, const float* tau_d, const float* pfrac_d,
+                                             const float* planck_lay_d, const float* planck_lev_d, const float* sfc_emis_gpt_d,
+                                             const float* sfc_source_d, float* flux_up_d, float* flux_dn_d) {
+  RRNN_CHECK(ctx && kd, "rrnn_lw_solver_noscat_compact: null handle");
+  RRNN_CHECK(nlay > 0 && ncol >= 0, "rrnn_lw_solver_noscat_compact: bad extents");
+  RRNN_CHECK(nmus >= 1 && nmus <= 4, "rte_lw: have to ask for between 1 and 4 quadrature points for no-scattering calculation");
+  RRNN_CHECK(tau_d && pfrac_d && planck_lay_d && planck_lev_d && sfc_emis_gpt_d && sfc_source_d && flux_up_d && flux_dn_d,
+             "rrnn_lw_solver_noscat_compact: null argument");
+  return lw_solver_noscat_compact(ctx, kd->ngpt, nlay, ncol, top_at_1, nmus, Ds, weights, tau_d, pfrac_d, planck_lay_d, planck_lev_d,
+                                  kd->d_gpt2band, sfc_emis_gpt_d, sfc_source_d, flux_up_d, flux_dn_d);
+}
+
 extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux_d,
                                       const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
                                       const float* mu0_d, const float* sfc_alb_dir_d, const float* sfc_alb_dif_d,

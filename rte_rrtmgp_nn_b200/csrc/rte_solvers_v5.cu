@@ -144,11 +144,22 @@ struct LwV5Params {
 };
 
 // ---------------------------------------------------------------------------------------------------- LW
-template <bool FAST, bool TOP, bool DN_EXT>
+// COMPACT: the sources are not materialised per g-point.  `lay_source` holds the Planck fraction pfrac (G,L,C) and the two
+// small tables planck_lay (16,L,C) / planck_lev (16,L+1,C) the band Planck functions B_b(T_lay), B_b(T_lev); the kernel
+// forms lay_source = pfrac(l) B(T_lay(l)) and lev_source(l) = pfrac(min(l, L)) B(T_lev(l)) itself with the same single
+// fp32 multiplication compute_Planck_source_nn does (mo_gas_optics_kernels.F90:654-672): 8 instead of 12 bytes per
+// (g-point, layer) cross HBM, on both sides of the interface.
+template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT>
 __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
-                                                   const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev) {
+                                                   const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev,
+                                                   const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int U = LW_U, S = LW_S;
+  // one stage of the input ring.  Materialised: tau | lay_source | lev_source(ext rows), U rows of 256 B each.
+  // COMPACT: tau (U rows) | pfrac (PFR rows: top-down sweeps also need the next layer's) | B_lay | B_lev(ext) (U rows of 64 B)
+  constexpr int PFR = COMPACT ? (TOP ? U + 1 : U) : U;
+  constexpr int OFF_PF = U * 256, OFF_3 = OFF_PF + PFR * 256, OFF_BV = OFF_3 + U * 64;
+  constexpr int STAGE = COMPACT ? OFF_BV + U * 64 : 3 * U * 256;
   const LwParams& p = pp.b;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
   const int G = p.ngpt, L = p.nlay;
@@ -162,10 +173,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
   // The input ring and the store staging are only live during the downward sweep, the back ring only during the upward
   // sweep (bulk_wait_all separates them): they share their shared memory, which is what bounds the CTAs per SM.
-  uint8_t* in_ring = smem;                                   // [S][3][U][256 B]: tau, lay_source, lev_source(ext rows)
-  uint8_t* ob = in_ring + S * 3 * U * 256;                   // [2][U][512 B]
+  uint8_t* in_ring = smem;                                   // [S][STAGE]
+  uint8_t* ob = in_ring + S * STAGE;                         // [2][U][512 B]
   uint8_t* bb = smem;                                        // [S][U][512 B]  (aliases in_ring / ob)
-  constexpr int FWD_BYTES = S * 3 * U * 256 + 2 * U * 512, BWD_BYTES = S * U * 512;
+  constexpr int FWD_BYTES = S * STAGE + 2 * U * 512, BWD_BYTES = S * U * 512;
   float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][2][L+1]
   const int part_set = 2 * (L + 1);
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
@@ -189,6 +200,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
   uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * 512;
   const uint32_t lane_in = (uint32_t)lane * 8u;   // byte offset of this lane's pair in a 256-byte row
   const uint32_t lane_bf = (uint32_t)lane * 16u;  // ... in a 512-byte reverse-buffer row
+  // COMPACT: byte offsets of the bands of this lane's two g-points in a 64-byte row of the Planck tables
+  uint32_t bo0 = 0, bo1 = 0;
+  if (COMPACT) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
+  auto band_pair = [&](const uint8_t* row) { return mk2(*reinterpret_cast<const float*>(row + bo0), *reinterpret_cast<const float*>(row + bo1)); };
 
   int ncols_done = 0;
   // The warps of a CTA take adjacent columns; all warps of a cluster make the same number of trips (one cluster barrier
@@ -206,7 +221,14 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
     // tensor rows of sweep layer 0: layers (tau, lay_source) and the level towards the surface (lev_source)
     const int lay0 = col * L + (TOP ? 0 : L - 1);
     const int ext0 = col * (L + 1) + (TOP ? 1 : L - 1);
-    const float* lev_ent0 = p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs;
+    // lev_source at the level where the sweep enters the atmosphere
+    f2 ent0;
+    if (COMPACT) {
+      const float* bv0 = p.planck_lev + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * 16;
+      ent0 = ldg2(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs) * mk2(__ldg(bv0 + (bo0 >> 2)), __ldg(bv0 + (bo1 >> 2)));
+    } else {
+      ent0 = ldg2(p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs);
+    }
     __syncwarp();
 
     for (int imu = 0; imu < p.nmus; ++imu) {
@@ -226,16 +248,21 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
           const int rl = box_start<TOP, U>(lay0, k, sh), rv = box_start<TOP, U>(ext0, k, sh);
           if (elect_one()) {
             const uint32_t bar = bar_in + 8 * st;
-            const uint32_t dst = in_a + st * (3 * U * 256);
-            mbar_expect_tx(bar, 3 * U * 256);
+            const uint32_t dst = in_a + st * STAGE;
+            mbar_expect_tx(bar, STAGE);
             tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
-            tma_load_2d(dst + U * 256, &tm_lay, chunk * 64, rl, bar, pol_in);
-            tma_load_2d(dst + 2 * U * 256, &tm_lev, chunk * 64, rv, bar, pol_in);
+            tma_load_2d(dst + OFF_PF, &tm_lay, chunk * 64, rl, bar, pol_in);
+            if (COMPACT) {
+              tma_load_2d(dst + OFF_3, &tm_bl, 0, rl, bar, pol_in);
+              tma_load_2d(dst + OFF_BV, &tm_bv, 0, rv, bar, pol_in);
+            } else {
+              tma_load_2d(dst + OFF_3, &tm_lev, chunk * 64, rv, bar, pol_in);
+            }
           }
           __syncwarp();
         }
       };
-      f2 carry = ldg2(lev_ent0);  // ent(0)
+      f2 carry = ent0;  // ent(0)
 #pragma unroll
       for (int k = 0; k < S - 1; ++k) issue_in(k);
       // The per-level broadband sums (butterfly shuffles: long dependent latencies, nothing downstream waits for them)
@@ -266,7 +293,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
         const uint32_t nk = n_in + (uint32_t)k;
         const uint32_t st = nk % S;
         mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
-        const uint8_t* base = in_ring + st * (3 * U * 256) + lane_in;
+        const uint8_t* stg = in_ring + st * STAGE;
+        const uint8_t* base = stg + lane_in;
         int shl = 0, shv = 0, nvalid = U;
         if (TAIL) {
           box_start<TOP, U>(lay0, k, shl);
@@ -279,8 +307,17 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
           const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
           const int rv = TAIL ? box_row<TOP, U>(u, shv) : (TOP ? u : U - 1 - u);
           tau[u] = lds2(base + rl * 256);
-          lay[u] = lds2(base + U * 256 + rl * 256);
-          ext[u] = lds2(base + 2 * U * 256 + rv * 256);
+          if (COMPACT) {
+            const f2 pf = lds2(base + OFF_PF + rl * 256);
+            lay[u] = pf * band_pair(stg + OFF_3 + rl * 64);
+            // the level below the bottom layer takes that layer's fraction (:667-669); bottom-up sweeps leave through
+            // the layer's own level
+            const f2 pfx = (TOP && k * U + u != L - 1) ? lds2(base + OFF_PF + (rl + 1) * 256) : pf;
+            ext[u] = pfx * band_pair(stg + OFF_BV + rv * 64);
+          } else {
+            lay[u] = lds2(base + OFF_PF + rl * 256);
+            ext[u] = lds2(base + OFF_3 + rv * 256);
+          }
         }
         flush_dn();
         f2 tv[U], sdn[U], sup[U];
@@ -830,12 +867,12 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 // [rows][ngpt] fp32 tensor, box 64 g-points x box_rows rows, no swizzle (rows of 256 B, read with 8-byte LDS per lane)
-static int make_map(CUtensorMap* tm, const float* base, int G, long long rows, int box_rows) {
+static int make_map(CUtensorMap* tm, const float* base, int G, long long rows, int box_rows, int box_cols = 64) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail("rte solvers: cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)G * 4};
-  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -860,9 +897,9 @@ static int resident_clusters5(const rrnn_ctx_t* ctx, int occ_clusters, int csize
 // because a cluster launch keeps at most 8 CTAs per SM resident (cudaOccupancyMaxActiveClusters: 284 clusters of 4 on
 // 148 SMs whatever the shared memory).  Measured at 137 layers: the SW sweeps gain 12-15 % from 13 warps per SM
 // (2 per CTA, scratch beyond L2 notwithstanding); the LW sweeps are DRAM-limited by then and stay at 1 per CTA.
-template <typename K, typename P>
+template <typename K, typename P, typename... Maps>
 static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_smem, size_t warp_scratch, int default_mb, int default_warps, int ncol, P& pp,
-                            float** scratch_slot, const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2) {
+                            float** scratch_slot, const Maps&... maps) {
   warp_smem = (warp_smem + 127) & ~(size_t)127;
   pp.warp_smem = (int)warp_smem;
   cudaLaunchConfig_t cfg{};
@@ -895,16 +932,20 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_sm
   cfg.gridDim = dim3((unsigned)ncta);
   if (int rc = ensure_scratch(ctx, (size_t)ncta * W * warp_scratch)) return rc;
   *scratch_slot = (float*)ctx->scratch;
-  RRNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, pp, t0, t1, t2));
+  RRNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, pp, maps...));
   return 0;
 }
+
+// The shapes the v5 kernels take (TMA: row pitch a multiple of 16 B; one cluster per column)
+bool lw_v5_supports(int G, int L) { return !(G & 3) && (G + 63) / 64 <= 8 && L >= v5::LW_U; }
 
 // returns -1 when the shape does not fit (the caller falls back to the per-lane-load kernels)
 int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 63) / 64;
-  if ((G & 3) || csize > 8 || L < v5::LW_U) return -1;  // TMA: row pitch a multiple of 16 B
-  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source})
+  const bool compact = p.planck_lay != nullptr;
+  if (!lw_v5_supports(G, L)) return -1;
+  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source, (const void*)p.planck_lay, (const void*)p.planck_lev})
     if ((uintptr_t)q & 15) return -1;
   for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
     if ((uintptr_t)q & 7) return -1;
@@ -913,20 +954,36 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
   pp.ngroups = (L + v5::LW_U - 1) / v5::LW_U;
   const long long rows_lay = (long long)p.ncol * L, rows_lev = (long long)p.ncol * (L + 1);
   if (rows_lev >= (1LL << 31) - 8) return -1;
-  CUtensorMap tm_tau, tm_lay, tm_lev;
-  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, v5::LW_U)) return rc;
-  if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, v5::LW_U)) return rc;
-  if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev, v5::LW_U)) return rc;
-  const size_t smem = std::max<size_t>((size_t)v5::LW_S * 3 * v5::LW_U * 256 + 2 * v5::LW_U * 512, (size_t)v5::LW_S * v5::LW_U * 512) + 4 * (size_t)(L + 1) * 4 + 2 * v5::LW_S * 8;
-  const size_t per_cta = (size_t)L * 512;
   const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
-#define LW5(F, T, D) launch_clustered(ctx, v5::lw_solver_v5<F, T, D>, csize, smem, per_cta, 96, 1, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev)
-  if (fast) {
-    if (top) return LW5(true, true, true);
-    return dn_ext ? LW5(true, false, true) : LW5(true, false, false);
+  constexpr int U = v5::LW_U, S = v5::LW_S;
+  CUtensorMap tm_tau, tm_lay, tm_lev, tm_bl, tm_bv;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, U)) return rc;
+  size_t stage;
+  if (compact) {
+    if (!p.planck_lev || !p.gpt2band) return fail("lw_solver: incomplete compact source description");
+    const int pfr = top ? U + 1 : U;
+    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, pfr)) return rc;
+    if (int rc = v5::make_map(&tm_bl, p.planck_lay, 16, rows_lay, U, 16)) return rc;
+    if (int rc = v5::make_map(&tm_bv, p.planck_lev, 16, rows_lev, U, 16)) return rc;
+    tm_lev = tm_tau;
+    stage = (size_t)U * 256 + (size_t)pfr * 256 + 2 * U * 64;
+  } else {
+    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, U)) return rc;
+    if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev, U)) return rc;
+    tm_bl = tm_tau; tm_bv = tm_tau;
+    stage = (size_t)3 * U * 256;
   }
-  if (top) return LW5(false, true, true);
-  return dn_ext ? LW5(false, false, true) : LW5(false, false, false);
+  const size_t smem = std::max<size_t>((size_t)S * stage + 2 * U * 512, (size_t)S * U * 512) + 4 * (size_t)(L + 1) * 4 + 2 * S * 8;
+  const size_t per_cta = (size_t)L * 512;
+#define LW5(F, T, D, C) launch_clustered(ctx, v5::lw_solver_v5<F, T, D, C>, csize, smem, per_cta, 96, 1, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv)
+#define LW5C(F, T, D) (compact ? LW5(F, T, D, true) : LW5(F, T, D, false))
+  if (fast) {
+    if (top) return LW5C(true, true, true);
+    return dn_ext ? LW5C(true, false, true) : LW5C(true, false, false);
+  }
+  if (top) return LW5C(false, true, true);
+  return dn_ext ? LW5C(false, false, true) : LW5C(false, false, false);
+#undef LW5C
 #undef LW5
 }
 

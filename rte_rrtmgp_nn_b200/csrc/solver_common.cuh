@@ -138,6 +138,10 @@ struct LwParams {
   float* flux_up;           // (nlay+1,ncol)
   float* flux_dn;
   float* scratch;           // GBUF: nCTA * 2 * L * 32 floats
+  // compact sources (lw_solver_v5 only; null otherwise): lay_source then holds the Planck fraction, lev_source is null
+  const float* planck_lay = nullptr;  // (16,nlay,ncol)   band Planck function at T_lay
+  const float* planck_lev = nullptr;  // (16,nlay+1,ncol) ... at T_lev
+  const int* gpt2band = nullptr;      // (ngpt) 0-based band of each g-point
 };
 
 

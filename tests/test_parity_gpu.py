@@ -264,6 +264,67 @@ def test_solvers_per_cta_do_not_change_the_fluxes(gpu_ctx, warps):
         gpu_ctx.set_flag("solver_warps", 0)
 
 
+def test_lw_compact_sources_give_identical_fluxes(gpu_ctx):
+    """rrnn_gas_optics_lw_compact + rrnn_lw_solver_noscat_compact (sources left factored, what rrnn_lw_fluxes runs) against the
+    materialised pair: pfrac * planck tables must reproduce lay_source / lev_source bit for bit, and the fluxes must be
+    bit-identical -- top-down and bottom-up columns, ragged layer groups, the level-source quirk on and off, 1-3 angles."""
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    P = api._ptr
+    L_ = _lib.lib()
+    ran = 0
+    for (files, G, nlay, ncol, flip, nang, compat) in [(H.LW_G256, 256, 60, 37, False, 1, 1), (H.LW_G256, 256, 137, 5, True, 1, 1),
+                                                      (H.LW_G256, 256, 64, 9, True, 2, 0), (H.LW_G128, 128, 33, 300, False, 3, 1),
+                                                      (H.LW_G128_NWP, 128, 72, 11, False, 1, 0)]:
+        kd, atm, k_dist, _, dnets = _lw_setup(gpu_ctx, files, G, ncol, nlay, seed=5, flip=flip)
+        op, src = _run_lw_gas_optics(gpu_ctx, k_dist, dnets, atm)
+        gc = H.gas_concs(atm["gases"])
+        tau = torch.empty((ncol, nlay, G), device="cuda"); pf = torch.empty_like(tau)
+        bl = torch.empty((ncol, nlay, 16), device="cuda"); bv = torch.empty((ncol, nlay + 1, 16), device="cuda")
+        ss = torch.empty((ncol, G), device="cuda"); sj = torch.empty_like(ss)
+        err = k_dist.gas_optics_compact(atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], gc, tau, pf, bl, bv, ss, sj,
+                                        tlev=atm["tlev"], neural_nets=dnets)
+        if "not supported" in err:  # networks the tensor-core kernel does not take (hidden width > 64)
+            continue
+        assert err == "", err
+        ran += 1
+        assert torch.equal(tau, op.tau) and torch.equal(ss, src.sfc_source)
+        lims = np.asarray(kd["band_lims_gpt"])
+        band = torch.from_numpy(np.repeat(np.arange(lims.shape[0]), lims[:, 1] - lims[:, 0] + 1)).cuda().long()
+        lay = pf * bl[:, :, band]
+        pfx = torch.cat([pf, pf[:, -1:, :]], dim=1)
+        lev = pfx * bv[:, :, band]
+        assert torch.equal(lay, src.lay_source), (lay - src.lay_source).abs().max()
+        assert torch.equal(lev, src.lev_source), (lev - src.lev_source).abs().max()
+        emis = torch.from_numpy(np.repeat(atm["sfc_emis"][:, None], G, 1).astype(np.float32)).cuda()
+        Ds = {1: [1.66], 2: [1.18350343, 2.81649655], 3: [1.09719858, 1.69338507, 4.70941630]}[nang]
+        ws = {1: [0.5], 2: [0.3180413817, 0.1819586183], 3: [0.2009319137, 0.2292411064, 0.0698269799]}[nang]
+        Ds = np.array(Ds, np.float32); ws = np.array(ws, np.float32)
+        fp = lambda a: a.ctypes.data_as(_lib.c_float_p)
+        gpu_ctx.set_flag("lw_source_bug_compat", compat)
+        try:
+            f = [torch.zeros((ncol, nlay + 1), device="cuda") for _ in range(4)]
+            _lib.check(L_.rrnn_lw_solver_noscat(gpu_ctx.h, G, nlay, ncol, int(atm["top_at_1"]), nang, fp(Ds), fp(ws), None, P(op.tau),
+                                                P(src.lay_source), P(src.lev_source), P(emis), P(src.sfc_source), P(f[0]), P(f[1])))
+            _lib.check(L_.rrnn_lw_solver_noscat_compact(gpu_ctx.h, k_dist._kd.h, nlay, ncol, int(atm["top_at_1"]), nang, fp(Ds), fp(ws),
+                                                        P(tau), P(pf), P(bl), P(bv), P(emis), P(ss), P(f[2]), P(f[3])))
+            del fp
+        finally:
+            gpu_ctx.set_flag("lw_source_bug_compat", 1)
+        assert f[0].abs().max() > 1.0
+        assert torch.equal(f[0], f[2]) and torch.equal(f[1], f[3]), ((f[0] - f[2]).abs().max(), (f[1] - f[3]).abs().max())
+    assert ran >= 3
+    # and through the fused driver: the flag must not change a bit
+    kd, atm, k_dist, _, dnets = _lw_setup(gpu_ctx, H.LW_G256, 256, 70, 60, seed=8)
+    res = {}
+    for flag in (1, 0):
+        gpu_ctx.set_flag("lw_compact_source", flag)
+        res[flag] = api.lw_fluxes_host(k_dist, dnets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["sfc_emis"],
+                                       H.gas_concs(atm["gases"]), tlev=atm["tlev"])
+    gpu_ctx.set_flag("lw_compact_source", 1)
+    assert np.array_equal(res[1][0], res[0][0]) and np.array_equal(res[1][1], res[0][1])
+
+
 def test_sgemm_entry_points(gpu_ctx):
     """output_sgemm_tau / _pfrac / _lw on materialised inputs (+ compute_nn_inputs, get_col_dry, Planck source)."""
     import oracle as O
