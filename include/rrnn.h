@@ -166,6 +166,25 @@ RRNN_API int rrnn_lw_solver_noscat_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* 
                                            const float* planck_lay_d, const float* planck_lev_d,
                                            const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d,
                                            float* flux_dn_d);
+/* lw_solver_noscat_GaussQuad with every option rte_lw can pass it (rte/kernels/mo_rte_solver_kernels.F90:332-415, 119-330):
+ * re-scaled scattering (do_rescaling: ssa_d, g_d, lw_transport_1rescl :1729-1795; both NULL = none), per-g-point secants
+ * lw_Ds_gpt_d (ngpt,ncol; one angle, NULL = Ds[]), g-point fluxes gpt_flux_{up,dn}_d (ngpt,nlay+1,ncol; NULL = not wanted;
+ * with one angle they hold radiances NOT multiplied by 2 pi w, as in the reference :287-291), and the surface-temperature
+ * Jacobian flux_up_Jac_d (nlay+1,ncol) from sfc_source_Jac_d (compute_Jac, rte/mo_rte_rrtmgp_config.F90:29; with one
+ * angle the sum of the un-scaled Jacobian radiances, :319).  A general kernel, not the tuned benchmark path. */
+RRNN_API int rrnn_lw_solver_noscat_ext(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* Ds,
+                                       const float* weights, const float* lw_Ds_gpt_d, const float* inc_flux_d,
+                                       const float* tau_d, const float* ssa_d, const float* g_d, const float* lay_source_d,
+                                       const float* lev_source_d, const float* sfc_emis_gpt_d, const float* sfc_source_d,
+                                       const float* sfc_source_Jac_d, float* flux_up_d, float* flux_dn_d,
+                                       float* flux_up_Jac_d, float* gpt_flux_up_d, float* gpt_flux_dn_d);
+/* rte_lw with its optional arguments and for ty_optical_props_2str (re-scaled solution, rte/mo_rte_lw.F90:363-384):
+ * ssa_d/g_d NULL = _1scl; lw_Ds_d (ngpt,ncol) only for _1scl and one angle (:239-249); sfc_emis_d is (nbnd,ncol). */
+RRNN_API int rrnn_rte_lw_ext(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,
+                             const float* inc_flux_d, const float* tau_d, const float* ssa_d, const float* g_d,
+                             const float* lay_source_d, const float* lev_source_d, const float* sfc_source_d,
+                             const float* sfc_emis_d, const float* lw_Ds_d, const float* sfc_source_Jac_d, float* flux_up_d,
+                             float* flux_dn_d, float* flux_up_Jac_d, float* gpt_flux_up_d, float* gpt_flux_dn_d);
 /* rte_lw for ty_optical_props_1scl, rte/mo_rte_lw.F90:60-424: sfc_emis_d is (nbnd,ncol) and is expanded to
  * g-points (:429-447); n_gauss_angles in 1..4 with the secants/weights of :113-125. */
 RRNN_API int rrnn_rte_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,

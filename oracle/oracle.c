@@ -364,20 +364,24 @@ ORC_API void orc_expand(int nband, int ngpt, int ncol, const int* band_limits, c
 }
 
 /* ------------------------------------------------------------------------------------------
- * lw_solver_noscat: rte/kernels/mo_rte_solver_kernels.F90:119-330 (do_rescaling = false,
- * compute_Jac = false as in rte/mo_rte_rrtmgp_config.F90:30-40) with
+ * lw_solver_noscat: rte/kernels/mo_rte_solver_kernels.F90:119-330 with
  *   lw_source_noscat :742-776 (ignores top_at_1: quirk Q1),
  *   lw_transport_noscat_dn :982-1009, lw_transport_noscat_up :950-980,
+ *   do_rescaling (:179-181, :211-233, :275-277) with lw_transport_1rescl :1729-1795,
+ *   the surface-temperature Jacobian (compute_Jac, a compile-time constant .false. in this fork,
+ *   rte/mo_rte_rrtmgp_config.F90:29; :186, :270, :290, :319, :967, :975, :1761, :1782),
  *   broadband sums in four interleaved partial sums :301-314.
  * D is (ngpt,ncol).  When nmus != 1 the radiances are scaled by fac and left in
  * radn_up_out/radn_dn_out (ngpt,nlay+1,ncol) and flux_up/flux_dn are NOT written (:287-317).
  * When save_gpt && nmus == 1 the g-point arrays hold un-scaled radiances (quirk Q3).
  * ------------------------------------------------------------------------------------------ */
-ORC_API void orc_lw_solver_noscat(int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* D,
+static void lw_solver_noscat_core(int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* D,
                                   float weight, const float* inc_flux, const float* tau,
                                   const float* lay_source, const float* lev_source, const float* sfc_emis,
                                   const float* sfc_source, float* flux_up, float* flux_dn, int save_gpt,
-                                  float* radn_up_out, float* radn_dn_out) {
+                                  float* radn_up_out, float* radn_dn_out, int compute_Jac,
+                                  const float* sfc_source_Jac, float* flux_up_Jac, float* radn_up_Jac_out,
+                                  int do_rescaling, const float* ssa, const float* gasym) {
   const float pi = acosf(-1.0f);
   const float tau_thresh = 3.4526698e-4f; /* sqrt(epsilon(1._sp)) */
   const int top_level = top_at_1 ? 0 : nlay;
@@ -385,20 +389,25 @@ ORC_API void orc_lw_solver_noscat(int ngpt, int nlay, int ncol, int top_at_1, in
 #pragma omp parallel
   {
     size_t nl = (size_t)ngpt * nlay;
-    float* wk = (float*)malloc(sizeof(float) * (4 * nl + 2 * (size_t)ngpt * (nlay + 1)));
+    size_t nv = (size_t)ngpt * (nlay + 1);
+    float* wk = (float*)malloc(sizeof(float) * (6 * nl + 3 * nv));
     float* tau_loc = wk;
     float* trans = tau_loc + nl;
     float* source_up = trans + nl;
     float* source_dn = source_up + nl;
-    float* radn_dn_arr = source_dn + nl;
-    float* radn_up_arr = radn_dn_arr + (size_t)ngpt * (nlay + 1);
+    float* An = source_dn + nl;
+    float* Cn = An + nl;
+    float* radn_dn_arr = Cn + nl;
+    float* radn_up_arr = radn_dn_arr + nv;
+    float* radn_jac_arr = radn_up_arr + nv;
 #pragma omp for schedule(static)
     for (int icol = 0; icol < ncol; ++icol) {
-      float* radn_dn = save_gpt ? radn_dn_out + (size_t)icol * (nlay + 1) * ngpt : radn_dn_arr;
-      float* radn_up = save_gpt ? radn_up_out + (size_t)icol * (nlay + 1) * ngpt : radn_up_arr;
+      float* radn_dn = save_gpt ? radn_dn_out + (size_t)icol * nv : radn_dn_arr;
+      float* radn_up = save_gpt ? radn_up_out + (size_t)icol * nv : radn_up_arr;
+      float* radn_jac = (save_gpt && radn_up_Jac_out) ? radn_up_Jac_out + (size_t)icol * nv : radn_jac_arr;
       const float* tauc = tau + (size_t)icol * nl;
       const float* layc = lay_source + (size_t)icol * nl;
-      const float* levc = lev_source + (size_t)icol * (nlay + 1) * ngpt;
+      const float* levc = lev_source + (size_t)icol * nv;
       const float* Dc = D + (size_t)icol * ngpt;
       const float* emis = sfc_emis + (size_t)icol * ngpt;
       const float* ssrc = sfc_source + (size_t)icol * ngpt;
@@ -407,13 +416,30 @@ ORC_API void orc_lw_solver_noscat(int ngpt, int nlay, int ncol, int top_at_1, in
         float v = inc_flux[(size_t)icol * ngpt + g];
         radn_dn[(size_t)top_level * ngpt + g] = v / (2.0f * pi * weight);
       }
-      /* optical path and transmission :234-239 */
-      for (int l = 0; l < nlay; ++l)
-        for (int g = 0; g < ngpt; ++g) {
-          float tl = tauc[(size_t)l * ngpt + g] * Dc[g];
-          tau_loc[(size_t)l * ngpt + g] = tl;
-          trans[(size_t)l * ngpt + g] = expf(-tl);
-        }
+      /* optical path and transmission :211-239 */
+      if (do_rescaling) {
+        const float* ssac = ssa + (size_t)icol * nl;
+        const float* gc = gasym + (size_t)icol * nl;
+        for (int l = 0; l < nlay; ++l)
+          for (int g = 0; g < ngpt; ++g) {
+            size_t i = (size_t)l * ngpt + g;
+            float ssal = ssac[i];
+            float wb = ssal * (1.0f - gc[i]) * 0.5f;
+            float scaleTau = (1.0f - ssal + wb);
+            Cn[i] = 0.4f * wb / scaleTau;
+            float tl = tauc[i] * Dc[g] * scaleTau;
+            tau_loc[i] = tl;
+            trans[i] = expf(-tl);
+            An[i] = (1.0f - trans[i] * trans[i]);
+          }
+      } else {
+        for (int l = 0; l < nlay; ++l)
+          for (int g = 0; g < ngpt; ++g) {
+            float tl = tauc[(size_t)l * ngpt + g] * Dc[g];
+            tau_loc[(size_t)l * ngpt + g] = tl;
+            trans[(size_t)l * ngpt + g] = expf(-tl);
+          }
+      }
       /* lw_source_noscat :742-776 */
       for (int l = 0; l < nlay; ++l)
         for (int g = 0; g < ngpt; ++g) {
@@ -437,25 +463,68 @@ ORC_API void orc_lw_solver_noscat(int ngpt, int nlay, int ncol, int top_at_1, in
             radn_dn[(size_t)lev * ngpt + g] = trans[(size_t)lev * ngpt + g] * radn_dn[(size_t)(lev + 1) * ngpt + g] +
                                               source_dn[(size_t)lev * ngpt + g];
       }
-      /* surface reflection and emission :269 */
-      for (int g = 0; g < ngpt; ++g)
+      /* surface reflection and emission :269-270 */
+      for (int g = 0; g < ngpt; ++g) {
         radn_up[(size_t)sfc_level * ngpt + g] =
             radn_dn[(size_t)sfc_level * ngpt + g] * (1 - emis[g]) + emis[g] * ssrc[g];
-      /* lw_transport_noscat_up :950-980 */
-      if (top_at_1) {
-        for (int l = nlay - 1; l >= 0; --l)
-          for (int g = 0; g < ngpt; ++g)
-            radn_up[(size_t)l * ngpt + g] = trans[(size_t)l * ngpt + g] * radn_up[(size_t)(l + 1) * ngpt + g] +
-                                            source_up[(size_t)l * ngpt + g];
+        if (compute_Jac) radn_jac[(size_t)sfc_level * ngpt + g] = emis[g] * sfc_source_Jac[(size_t)icol * ngpt + g];
+      }
+      if (do_rescaling) {
+        /* lw_transport_1rescl :1729-1795: up with the adjustment, then down again */
+        if (top_at_1) {
+          for (int l = nlay - 1; l >= 0; --l)
+            for (int g = 0; g < ngpt; ++g) {
+              size_t i = (size_t)l * ngpt + g;
+              float adj = Cn[i] * (An[i] * radn_dn[i] - trans[i] * source_dn[i] - source_up[i]);
+              radn_up[i] = trans[i] * radn_up[i + ngpt] + source_up[i] + adj;
+              if (compute_Jac) radn_jac[i] = trans[i] * radn_jac[i + ngpt];
+            }
+          for (int l = 0; l < nlay; ++l)
+            for (int g = 0; g < ngpt; ++g) {
+              size_t i = (size_t)l * ngpt + g;
+              float adj = Cn[i] * (An[i] * radn_up[i] - trans[i] * source_up[i] - source_dn[i]);
+              radn_dn[i + ngpt] = trans[i] * radn_dn[i] + source_dn[i] + adj;
+            }
+        } else {
+          for (int l = 0; l < nlay; ++l)
+            for (int g = 0; g < ngpt; ++g) {
+              size_t i = (size_t)l * ngpt + g;
+              float adj = Cn[i] * (An[i] * radn_dn[i + ngpt] - trans[i] * source_dn[i] - source_up[i]);
+              radn_up[i + ngpt] = trans[i] * radn_up[i] + source_up[i] + adj;
+              if (compute_Jac) radn_jac[i + ngpt] = trans[i] * radn_jac[i];
+            }
+          for (int l = nlay - 1; l >= 0; --l)
+            for (int g = 0; g < ngpt; ++g) {
+              size_t i = (size_t)l * ngpt + g;
+              float adj = Cn[i] * (An[i] * radn_up[i] - trans[i] * source_up[i] - source_dn[i]);
+              radn_dn[i] = trans[i] * radn_dn[i + ngpt] + source_dn[i] + adj;
+            }
+        }
       } else {
-        for (int lev = 1; lev <= nlay; ++lev)
-          for (int g = 0; g < ngpt; ++g)
-            radn_up[(size_t)lev * ngpt + g] = trans[(size_t)(lev - 1) * ngpt + g] * radn_up[(size_t)(lev - 1) * ngpt + g] +
-                                              source_up[(size_t)(lev - 1) * ngpt + g];
+        /* lw_transport_noscat_up :950-980 */
+        if (top_at_1) {
+          for (int l = nlay - 1; l >= 0; --l)
+            for (int g = 0; g < ngpt; ++g) {
+              radn_up[(size_t)l * ngpt + g] = trans[(size_t)l * ngpt + g] * radn_up[(size_t)(l + 1) * ngpt + g] +
+                                              source_up[(size_t)l * ngpt + g];
+              if (compute_Jac) radn_jac[(size_t)l * ngpt + g] = trans[(size_t)l * ngpt + g] * radn_jac[(size_t)(l + 1) * ngpt + g];
+            }
+        } else {
+          for (int lev = 1; lev <= nlay; ++lev)
+            for (int g = 0; g < ngpt; ++g) {
+              radn_up[(size_t)lev * ngpt + g] = trans[(size_t)(lev - 1) * ngpt + g] * radn_up[(size_t)(lev - 1) * ngpt + g] +
+                                                source_up[(size_t)(lev - 1) * ngpt + g];
+              if (compute_Jac)
+                radn_jac[(size_t)lev * ngpt + g] = trans[(size_t)(lev - 1) * ngpt + g] * radn_jac[(size_t)(lev - 1) * ngpt + g];
+            }
+        }
       }
       float fac = 2.0f * pi * weight;
       if (nmus != 1) {
-        for (size_t i = 0; i < (size_t)ngpt * (nlay + 1); ++i) { radn_dn[i] = fac * radn_dn[i]; radn_up[i] = fac * radn_up[i]; }
+        for (size_t i = 0; i < nv; ++i) {
+          radn_dn[i] = fac * radn_dn[i]; radn_up[i] = fac * radn_up[i];
+          if (compute_Jac) radn_jac[i] = fac * radn_jac[i];
+        }
       } else {
         if (ngpt % 4 == 0) {
           for (int lev = 0; lev <= nlay; ++lev) {
@@ -477,10 +546,25 @@ ORC_API void orc_lw_solver_noscat(int ngpt, int nlay, int ncol, int top_at_1, in
             flux_dn[(size_t)icol * (nlay + 1) + lev] = sd;
           }
         }
+        if (compute_Jac) /* :319 -- sum() of the un-scaled Jacobian radiances, as written */
+          for (int lev = 0; lev <= nlay; ++lev) {
+            float sj = 0;
+            for (int g = 0; g < ngpt; ++g) sj += radn_jac[(size_t)lev * ngpt + g];
+            flux_up_Jac[(size_t)icol * (nlay + 1) + lev] = sj;
+          }
       }
     }
     free(wk);
   }
+}
+
+ORC_API void orc_lw_solver_noscat(int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* D,
+                                  float weight, const float* inc_flux, const float* tau,
+                                  const float* lay_source, const float* lev_source, const float* sfc_emis,
+                                  const float* sfc_source, float* flux_up, float* flux_dn, int save_gpt,
+                                  float* radn_up_out, float* radn_dn_out) {
+  lw_solver_noscat_core(ngpt, nlay, ncol, top_at_1, nmus, D, weight, inc_flux, tau, lay_source, lev_source, sfc_emis,
+                        sfc_source, flux_up, flux_dn, save_gpt, radn_up_out, radn_dn_out, 0, NULL, NULL, NULL, 0, NULL, NULL);
 }
 
 /* sum_broadband: rte/kernels/mo_fluxes_broadband_kernels.F90:31-74 */
@@ -523,6 +607,49 @@ ORC_API void orc_lw_solver_noscat_GaussQuad(int ngpt, int nlay, int ncol, int to
     sum_broadband(ngpt, nlay + 1, ncol, gup, flux_up);
     sum_broadband(ngpt, nlay + 1, ncol, gdn, flux_dn);
     free(gup);
+  }
+  free(Dg);
+}
+
+/* lw_solver_noscat_GaussQuad with everything rte_lw can ask of it (rte/mo_rte_lw.F90:324-384, kernels :332-415):
+ * per-g-point secants lw_Ds (one angle, :329-340; Ds_gpt (ngpt,ncol) or NULL), re-scaled scattering for _2str clouds
+ * (ssa, g or NULL), the surface-temperature Jacobian (sfc_source_Jac, flux_up_Jac or NULL) and the g-point fluxes
+ * (gpt_up, gpt_dn (ngpt,nlay+1,ncol) or NULL; quirk Q3 for one angle). */
+ORC_API void orc_lw_solver_noscat_GaussQuad_ext(int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* Ds,
+                                                const float* weights, const float* Ds_gpt, const float* inc_flux,
+                                                const float* tau, const float* ssa, const float* g,
+                                                const float* lay_source, const float* lev_source, const float* sfc_emis,
+                                                const float* sfc_source, const float* sfc_source_Jac, float* flux_up,
+                                                float* flux_dn, float* flux_up_Jac, float* gpt_up, float* gpt_dn) {
+  size_t ngc = (size_t)ngpt * ncol;
+  size_t n3 = ngc * (nlay + 1);
+  const int jac = flux_up_Jac != NULL, resc = ssa != NULL, save = gpt_up != NULL;
+  float* Dg = (float*)malloc(sizeof(float) * ngc);
+  for (size_t i = 0; i < ngc; ++i) Dg[i] = Ds_gpt ? Ds_gpt[i] : Ds[0];
+  if (nmus == 1) {
+    float* gj = (save && jac) ? (float*)malloc(sizeof(float) * n3) : NULL;
+    lw_solver_noscat_core(ngpt, nlay, ncol, top_at_1, nmus, Dg, weights[0], inc_flux, tau, lay_source, lev_source, sfc_emis,
+                          sfc_source, flux_up, flux_dn, save, gpt_up, gpt_dn, jac, sfc_source_Jac, flux_up_Jac, gj, resc, ssa, g);
+    free(gj);
+  } else {
+    float* own = save ? NULL : (float*)malloc(sizeof(float) * n3 * 2);
+    float* gup = save ? gpt_up : own;
+    float* gdn = save ? gpt_dn : own + n3;
+    float* tmp = (float*)malloc(sizeof(float) * n3 * 4);
+    float *rup = tmp, *rdn = tmp + n3, *gjac = tmp + 2 * n3, *rjac = tmp + 3 * n3;
+    lw_solver_noscat_core(ngpt, nlay, ncol, top_at_1, nmus, Dg, weights[0], inc_flux, tau, lay_source, lev_source, sfc_emis,
+                          sfc_source, flux_up, flux_dn, 1, gup, gdn, jac, sfc_source_Jac, flux_up_Jac, gjac, resc, ssa, g);
+    for (int imu = 1; imu < nmus; ++imu) {
+      for (size_t i = 0; i < ngc; ++i) Dg[i] = Ds[imu];
+      lw_solver_noscat_core(ngpt, nlay, ncol, top_at_1, nmus, Dg, weights[imu], inc_flux, tau, lay_source, lev_source,
+                            sfc_emis, sfc_source, flux_up, flux_dn, 1, rup, rdn, jac, sfc_source_Jac, flux_up_Jac, rjac, resc, ssa, g);
+      for (size_t i = 0; i < n3; ++i) { gup[i] = gup[i] + rup[i]; gdn[i] = gdn[i] + rdn[i]; if (jac) gjac[i] = gjac[i] + rjac[i]; }
+    }
+    sum_broadband(ngpt, nlay + 1, ncol, gup, flux_up);
+    sum_broadband(ngpt, nlay + 1, ncol, gdn, flux_dn);
+    if (jac) sum_broadband(ngpt, nlay + 1, ncol, gjac, flux_up_Jac);
+    free(tmp);
+    free(own);
   }
   free(Dg);
 }

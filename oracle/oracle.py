@@ -286,6 +286,35 @@ def rte_lw(kd, top_at_1, tau, lay_source, lev_source, sfc_source, sfc_emis, n_ga
                                       inc_flux, fast)
 
 
+def lw_solver_noscat_GaussQuad_ext(top_at_1, nmus, tau, lay_source, lev_source, sfc_emis_gpt, sfc_source, inc_flux=None,
+                                   ssa=None, g=None, lw_Ds=None, sfc_source_Jac=None, want_gpt=False, fast=False):
+    """Everything rte_lw can ask of lw_solver_noscat_GaussQuad (rte/mo_rte_lw.F90:324-384): re-scaled scattering (ssa, g),
+    per-g-point secants lw_Ds (ncol, ngpt; one angle), the surface-temperature Jacobian, g-point fluxes.
+    Returns a dict with flux_up, flux_dn [, flux_up_Jac][, gpt_flux_up, gpt_flux_dn]."""
+    ncol, nlay, ngpt = tau.shape
+    dt = _dt(fast)
+    if inc_flux is None:
+        inc_flux = np.zeros((ncol, ngpt), dt)
+    Ds = _a(GAUSS_DS[nmus - 1, :nmus], fast); wts = _a(GAUSS_WTS[nmus - 1, :nmus], fast)
+    opt = lambda v: None if v is None else _a(v, fast)
+    ssa_a, g_a, dsg, sj = opt(ssa), opt(g), opt(lw_Ds), opt(sfc_source_Jac)
+    inc, tau_a, lay, lev, emis, ssrc = [_a(v, fast) for v in (inc_flux, tau, lay_source, lev_source, sfc_emis_gpt, sfc_source)]
+    up = np.empty((ncol, nlay + 1), dt); dn = np.empty_like(up)
+    jac = np.empty_like(up) if sj is not None else None
+    gup = np.empty((ncol, nlay + 1, ngpt), dt) if want_gpt else None
+    gdn = np.empty_like(gup) if want_gpt else None
+    pn = lambda v: None if v is None else _p(v)
+    lib(fast).orc_lw_solver_noscat_GaussQuad_ext(ngpt, nlay, ncol, int(bool(top_at_1)), nmus, _p(Ds), _p(wts), pn(dsg), _p(inc),
+                                                 _p(tau_a), pn(ssa_a), pn(g_a), _p(lay), _p(lev), _p(emis), _p(ssrc), pn(sj),
+                                                 _p(up), _p(dn), pn(jac), pn(gup), pn(gdn))
+    out = dict(flux_up=up, flux_dn=dn)
+    if jac is not None:
+        out["flux_up_Jac"] = jac
+    if want_gpt:
+        out["gpt_flux_up"], out["gpt_flux_dn"] = gup, gdn
+    return out
+
+
 def sw_solver_2stream(top_at_1, inc_flux, inc_flux_dif, tau, ssa, g, mu0, alb_dir, alb_dif, fast=False):
     ncol, nlay, ngpt = tau.shape
     dt = _dt(fast)

@@ -418,6 +418,15 @@ class ty_fluxes_broadband:
         return any(v is not None for v in (self.flux_up, self.flux_dn, self.flux_net, self.flux_dn_dir))
 
 
+class ty_fluxes_flexible(ty_fluxes_broadband):
+    """ty_fluxes_flexible (rte/mo_fluxes.F90:52-67): broadband fluxes plus, when associated, the g-point fluxes
+    gpt_flux_up / gpt_flux_dn (ncol, nlay+1, ngpt)."""
+
+    def __init__(self, flux_up=None, flux_dn=None, flux_net=None, flux_dn_dir=None, gpt_flux_up=None, gpt_flux_dn=None):
+        super().__init__(flux_up, flux_dn, flux_net, flux_dn_dir)
+        self.gpt_flux_up, self.gpt_flux_dn = gpt_flux_up, gpt_flux_dn
+
+
 class ty_gas_optics_rrtmgp(ty_optical_props):
     """The NN path of the RRTMGP gas optics.  `load` takes the spectral tables of the k-distribution
     (rte_rrtmgp_nn_b200.spectral.make_kdist / synthetic_kdist_*)."""
@@ -516,16 +525,51 @@ class ty_gas_optics_rrtmgp(ty_optical_props):
 
 def rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes, inc_flux=None, n_gauss_angles=None, use_2stream=None,
            lw_Ds=None, flux_up_Jac=None, flux_dn_Jac=None):
-    """rte_lw (rte/mo_rte_lw.F90:60-64) for ty_optical_props_1scl; sfc_emis is (ncol, nband)."""
+    """rte_lw (rte/mo_rte_lw.F90:60-64); sfc_emis is (ncol, nband).  ty_optical_props_1scl: no-scattering solution (the tuned
+    kernels; the general kernel when lw_Ds, flux_up_Jac or g-point fluxes are asked for).  ty_optical_props_2str: the
+    re-scaled solution (:363-384); use_2stream (lw_solver_2stream) is not implemented."""
     if not fluxes.are_desired():
         return "rte_lw: no space allocated for fluxes"
-    if not isinstance(optical_props, ty_optical_props_1scl):
-        return "rte_lw: only ty_optical_props_1scl (no-scattering) is implemented"
+    two = isinstance(optical_props, ty_optical_props_2str)
+    if not two and not isinstance(optical_props, ty_optical_props_1scl):
+        return "rte_lw: lw_solver(...ty_optical_props_nstr...) not yet implemented"
     if use_2stream:
-        return "rte_lw: can't use two-stream methods with only absorption optical depth"
-    if lw_Ds is not None or flux_up_Jac is not None or flux_dn_Jac is not None:
-        return "rte_lw: lw_Ds / Jacobians are not implemented"
+        return ("rte_lw: the two-stream longwave solver (lw_solver_2stream) is not implemented" if two else
+                "rte_lw: can't use two-stream methods with only absorption optical depth")
+    if flux_dn_Jac is not None:
+        return "rte_lw: flux_dn_Jac is not computed (as in the reference)"
+    if lw_Ds is not None and two:
+        return "rte_lw: lw_Ds not valid input for _2str class"
+    if lw_Ds is not None and n_gauss_angles is not None:
+        return "rte_lw: providing lw_Ds incompatible with specifying n_gauss_angles"
     ctx = optical_props.ctx
+    gpt_up, gpt_dn = getattr(fluxes, "gpt_flux_up", None), getattr(fluxes, "gpt_flux_dn", None)
+    if two or lw_Ds is not None or flux_up_Jac is not None or gpt_up is not None:
+        nang = 1 if n_gauss_angles is None else int(n_gauss_angles)
+        ncol, nlay = optical_props.get_ncol(), optical_props.get_nlay()
+        sfc_emis = _dev(sfc_emis, ctx)
+        if tuple(sfc_emis.shape) != (ncol, optical_props.nband):
+            return "rte_lw: sfc_emis inconsistently sized"
+        if lw_Ds is not None:
+            lw_Ds = _dev(lw_Ds, ctx)
+            if tuple(lw_Ds.shape) != (ncol, optical_props.ngpt):
+                return "rte_lw: lw_Ds inconsistently sized"
+            if bool((lw_Ds < 1.0).any()):
+                return "rte_lw: one or more values of lw_Ds < 1."
+        if flux_up_Jac is not None and tuple(flux_up_Jac.shape) != (ncol, nlay + 1):
+            return "rte_lw: flux Jacobian inconsistently sized"
+        if two:
+            g = optical_props.g  # materialises zeros when g is implicit
+        try:
+            _lib.check(_lib.lib().rrnn_rte_lw_ext(
+                ctx.h, optical_props._kd.h, nlay, ncol, int(bool(top_at_1)), nang, _ptr(_dev(inc_flux, ctx)), _ptr(optical_props.tau),
+                _ptr(optical_props.ssa) if two else None, _ptr(g) if two else None, _ptr(sources.lay_source),
+                _ptr(sources.lev_source), _ptr(sources.sfc_source), _ptr(sfc_emis), _ptr(lw_Ds),
+                _ptr(sources.sfc_source_Jac) if flux_up_Jac is not None else None, _ptr(fluxes.flux_up), _ptr(fluxes.flux_dn),
+                _ptr(flux_up_Jac), _ptr(gpt_up), _ptr(gpt_dn)))
+        except RRNNError as e:
+            return str(e)
+        return ""
     nang = 1 if n_gauss_angles is None else int(n_gauss_angles)
     if nang > 4:
         return "rte_lw: asking for too many quadrature points for no-scattering calculation"

@@ -325,6 +325,124 @@ def test_lw_compact_sources_give_identical_fluxes(gpu_ctx):
     assert np.array_equal(res[1][0], res[0][0]) and np.array_equal(res[1][1], res[0][1])
 
 
+@pytest.mark.parametrize("G,L,C,top,nang", [(256, 60, 9, True, 1), (224, 33, 5, False, 1), (128, 137, 3, True, 3), (36, 7, 4, False, 2)])
+def test_lw_rescaled_jacobian_gpt_fluxes_match_oracle(gpu_ctx, G, L, C, top, nang):
+    """rte_lw's remaining dispatch rows through rrnn_lw_solver_noscat_ext: re-scaled scattering
+    (lw_transport_1rescl), surface-temperature Jacobian, g-point fluxes (quirk Q3 for one angle), per-g-point lw_Ds --
+    against the oracle's restatement of mo_rte_solver_kernels.F90:119-415, 1729-1795."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    rng = np.random.default_rng(G + L)
+    tau = rng.gamma(0.4, 1.5, size=(C, L, G)).astype(np.float32)
+    tau[0, 0, :4] = 1e-5
+    ssa = rng.uniform(0.0, 0.95, size=(C, L, G)).astype(np.float32)
+    g = rng.uniform(-0.2, 0.9, size=(C, L, G)).astype(np.float32)
+    lay = rng.uniform(0.1, 2.0, size=(C, L, G)).astype(np.float32)
+    lev = rng.uniform(0.1, 2.0, size=(C, L + 1, G)).astype(np.float32)
+    emis = rng.uniform(0.8, 1.0, size=(C, G)).astype(np.float32)
+    ssrc = rng.uniform(0.1, 2.0, size=(C, G)).astype(np.float32)
+    sjac = rng.uniform(0.001, 0.02, size=(C, G)).astype(np.float32)
+    inc = rng.uniform(0.0, 0.5, size=(C, G)).astype(np.float32)
+    lwds = rng.uniform(1.0, 2.0, size=(C, G)).astype(np.float32)
+    Ds = np.ascontiguousarray(O.GAUSS_DS[nang - 1, :nang], np.float32); ws = np.ascontiguousarray(O.GAUSS_WTS[nang - 1, :nang], np.float32)
+    fp = lambda a: a.ctypes.data_as(_lib.c_float_p)
+    P = api._ptr
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(tau=tau, ssa=ssa, g=g, lay=lay, lev=lev, emis=emis, ssrc=ssrc, sjac=sjac,
+                                                        inc=inc, lwds=lwds).items()}
+    cases = [dict(resc=True, jac=True, gpt=True, ds=False), dict(resc=False, jac=True, gpt=False, ds=False),
+             dict(resc=True, jac=False, gpt=False, ds=False)]
+    if nang == 1:
+        cases.append(dict(resc=False, jac=False, gpt=True, ds=True))
+    for c in cases:
+        ref = O.lw_solver_noscat_GaussQuad_ext(top, nang, tau, lay, lev, emis, ssrc, inc_flux=inc, ssa=ssa if c["resc"] else None,
+                                               g=g if c["resc"] else None, lw_Ds=lwds if c["ds"] else None,
+                                               sfc_source_Jac=sjac if c["jac"] else None, want_gpt=c["gpt"])
+        up = torch.zeros((C, L + 1), device="cuda"); dn = torch.zeros_like(up)
+        jac = torch.zeros_like(up) if c["jac"] else None
+        gup = torch.zeros((C, L + 1, G), device="cuda") if c["gpt"] else None
+        gdn = torch.zeros_like(gup) if c["gpt"] else None
+        _lib.check(_lib.lib().rrnn_lw_solver_noscat_ext(
+            gpu_ctx.h, G, L, C, int(top), nang, fp(Ds), fp(ws), P(d["lwds"]) if c["ds"] else None, P(d["inc"]), P(d["tau"]),
+            P(d["ssa"]) if c["resc"] else None, P(d["g"]) if c["resc"] else None, P(d["lay"]), P(d["lev"]), P(d["emis"]), P(d["ssrc"]),
+            P(d["sjac"]) if c["jac"] else None, P(up), P(dn), P(jac), P(gup), P(gdn)))
+        scale = max(np.abs(ref["flux_up"]).max(), 1.0)
+        assert np.abs(up.cpu().numpy() - ref["flux_up"]).max() <= 2e-5 * scale, c
+        assert np.abs(dn.cpu().numpy() - ref["flux_dn"]).max() <= 2e-5 * scale, c
+        if c["jac"]:
+            assert np.abs(jac.cpu().numpy() - ref["flux_up_Jac"]).max() <= 2e-5 * max(np.abs(ref["flux_up_Jac"]).max(), 1e-3), c
+        if c["gpt"]:
+            # single g-points see the cancellation in the re-scaling adjustment (An*I - t*s_dn - s_up) unaveraged: measured
+            # against the fp64 evaluation, and no further from it than twice the strict fp32 oracle is
+            r64 = O.lw_solver_noscat_GaussQuad_ext(top, nang, tau, lay, lev, emis, ssrc, inc_flux=inc, ssa=ssa if c["resc"] else None,
+                                                   g=g if c["resc"] else None, lw_Ds=lwds if c["ds"] else None, want_gpt=True, fast="f64")
+            for got, k in ((gup, "gpt_flux_up"), (gdn, "gpt_flux_dn")):
+                gs = max(np.abs(ref[k]).max(), 1e-3)
+                noise = np.abs(ref[k] - r64[k]).max()
+                err = np.abs(got.cpu().numpy() - r64[k]).max()
+                assert err <= max(2e-5 * gs, 2.0 * noise), (c, k, err, noise)
+    # without any option the general kernel agrees with the tuned one
+    a = [torch.zeros((C, L + 1), device="cuda") for _ in range(4)]
+    _lib.check(_lib.lib().rrnn_lw_solver_noscat_ext(gpu_ctx.h, G, L, C, int(top), nang, fp(Ds), fp(ws), None, P(d["inc"]), P(d["tau"]), None,
+                                                    None, P(d["lay"]), P(d["lev"]), P(d["emis"]), P(d["ssrc"]), None, P(a[0]), P(a[1]),
+                                                    None, None, None))
+    _lib.check(_lib.lib().rrnn_lw_solver_noscat(gpu_ctx.h, G, L, C, int(top), nang, fp(Ds), fp(ws), P(d["inc"]), P(d["tau"]), P(d["lay"]),
+                                                P(d["lev"]), P(d["emis"]), P(d["ssrc"]), P(a[2]), P(a[3])))
+    assert torch.allclose(a[0], a[2], rtol=2e-5, atol=1e-4) and torch.allclose(a[1], a[3], rtol=2e-5, atol=1e-4)
+
+
+def test_rte_lw_with_2str_clouds_and_optional_arguments(gpu_ctx):
+    """The host mirror of rte_lw (rte/mo_rte_lw.F90:60-64, 324-384): _2str cloudy atmosphere -> re-scaled solution, lw_Ds,
+    flux_up_Jac, ty_fluxes_flexible, and the reference's error messages for the invalid combinations."""
+    import os
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    torch = _torch()
+    ncol, nlay, G = 24, 60, 256
+    kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, H.LW_G256, G, ncol, nlay, seed=41)
+    cl = synth.make_clouds(atm)
+    op, src = _run_lw_gas_optics(gpu_ctx, k_dist, dnets, atm)
+    ref = O.gas_optics_lw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"])
+    # SW-style 2str cloud optics on the LW bands: LUT with ssa / g, delta-scaled, added to a 2str copy of the gas optics
+    co = api.ty_cloud_optics(gpu_ctx)
+    assert co.load(**api.load_cloud_lut_file(os.path.join(H.ROOT, "data", "cloud_optics", "rrtmgp-cloud-optics-coeffs-lw.nc"))) == ""
+    clouds = api.ty_optical_props_2str(); assert clouds.alloc_2str(ncol, nlay, k_dist, by_band=True) == ""
+    assert co.cloud_optics(cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], clouds) == ""
+    atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(ncol, nlay, k_dist) == ""
+    atmos._kd = k_dist._kd
+    atmos.tau.copy_(op.tau); atmos.ssa.zero_(); atmos.g_is_zero = True
+    assert clouds.increment(atmos) == ""
+    c_ref = O.cloud_optics_lut(co.tables, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], True)
+    t, w, g = O.inc_2stream_by_2stream_bybnd(ref["tau"], np.zeros_like(ref["tau"]), np.zeros_like(ref["tau"]), *c_ref, kd["band_lims_gpt"])
+    assert w.max() > 0.1
+    emis = np.repeat(atm["sfc_emis"][:, None], 16, 1)
+    emis_gpt = O.expand(kd["band_lims_gpt"], G, emis)
+    mk = lambda *s: torch.zeros(s, device="cuda")
+    fl = api.ty_fluxes_flexible(mk(ncol, nlay + 1), mk(ncol, nlay + 1), gpt_flux_up=mk(ncol, nlay + 1, G), gpt_flux_dn=mk(ncol, nlay + 1, G))
+    jac = mk(ncol, nlay + 1)
+    assert api.rte_lw(atmos, atm["top_at_1"], src, emis, fl, n_gauss_angles=2, flux_up_Jac=jac) == ""
+    want = O.lw_solver_noscat_GaussQuad_ext(atm["top_at_1"], 2, t, ref["lay_source"], ref["lev_source"], emis_gpt, ref["sfc_source"],
+                                            ssa=w, g=g, sfc_source_Jac=ref["sfc_source_Jac"], want_gpt=True)
+    assert np.abs(fl.flux_up.cpu().numpy() - want["flux_up"]).max() <= H.FLUX_TOL
+    assert np.abs(fl.flux_dn.cpu().numpy() - want["flux_dn"]).max() <= H.FLUX_TOL
+    assert np.abs(jac.cpu().numpy() - want["flux_up_Jac"]).max() <= 1e-4
+    assert np.abs(fl.gpt_flux_up.cpu().numpy() - want["gpt_flux_up"]).max() <= 1e-4
+    noscat = O.lw_solver_noscat_GaussQuad_ext(atm["top_at_1"], 2, t, ref["lay_source"], ref["lev_source"], emis_gpt, ref["sfc_source"])
+    assert np.abs(noscat["flux_up"] - want["flux_up"]).max() > 0.05  # the re-scaling matters
+    # lw_Ds on the clear-sky _1scl atmosphere
+    lw_Ds = np.full((ncol, G), 1.5, np.float32)
+    fl1 = api.ty_fluxes_broadband(mk(ncol, nlay + 1), mk(ncol, nlay + 1))
+    assert api.rte_lw(op, atm["top_at_1"], src, emis, fl1, lw_Ds=lw_Ds) == ""
+    w1 = O.lw_solver_noscat_GaussQuad_ext(atm["top_at_1"], 1, ref["tau"], ref["lay_source"], ref["lev_source"], emis_gpt,
+                                          ref["sfc_source"], lw_Ds=lw_Ds)
+    assert np.abs(fl1.flux_up.cpu().numpy() - w1["flux_up"]).max() <= H.FLUX_TOL
+    # error behaviour (mo_rte_lw.F90:239-252)
+    assert api.rte_lw(atmos, True, src, emis, fl, lw_Ds=lw_Ds) == "rte_lw: lw_Ds not valid input for _2str class"
+    assert api.rte_lw(op, True, src, emis, fl1, lw_Ds=lw_Ds, n_gauss_angles=1) == "rte_lw: providing lw_Ds incompatible with specifying n_gauss_angles"
+    assert api.rte_lw(op, True, src, emis, fl1, lw_Ds=lw_Ds * 0.5) == "rte_lw: one or more values of lw_Ds < 1."
+    assert "two-stream" in api.rte_lw(op, True, src, emis, fl1, use_2stream=True)
+
+
 def test_sgemm_entry_points(gpu_ctx):
     """output_sgemm_tau / _pfrac / _lw on materialised inputs (+ compute_nn_inputs, get_col_dry, Planck source)."""
     import oracle as O
