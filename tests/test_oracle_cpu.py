@@ -233,3 +233,31 @@ def test_gas_missing_and_profile_modes(cfg):
     x3 = O.compute_nn_inputs(net, atm["play"], atm["tlay"], g3)
     i = net.input_names.index("cf4")
     assert np.allclose(x3[..., i], (0.0 - net.xmin[i]) / (net.xmax[i] - net.xmin[i])) and np.array_equal(np.delete(x3, i, -1), np.delete(x0, i, -1))
+
+
+def test_lw_solver_ext_rescaling_jacobian_gpt_fluxes():
+    """The oracle's restatement of lw_solver_noscat's optional branches (mo_rte_solver_kernels.F90:179-319, 1729-1795) against
+    properties the reference's formulas imply: no single-scattering albedo -> the plain solution (bit for bit); g-point fluxes sum
+    to the broadband ones; the Jacobian is the derivative with respect to the surface source (the problem is linear in it),
+    short of the 2 pi w the reference leaves out for one angle (:319)."""
+    import oracle as O
+    rng = np.random.default_rng(5)
+    C, L, G = 3, 14, 16
+    tau = rng.gamma(0.5, 1.0, size=(C, L, G)).astype(np.float32)
+    ssa = rng.uniform(0, 0.9, size=tau.shape).astype(np.float32); g = rng.uniform(-0.1, 0.9, size=tau.shape).astype(np.float32)
+    lay = rng.uniform(1, 2, size=(C, L, G)).astype(np.float32); lev = rng.uniform(1, 2, size=(C, L + 1, G)).astype(np.float32)
+    em = rng.uniform(0.8, 1, size=(C, G)).astype(np.float32); ss = rng.uniform(1, 2, size=(C, G)).astype(np.float32)
+    sj = rng.uniform(0.01, 0.02, size=(C, G)).astype(np.float32)
+    for top in (True, False):
+        for nm in (1, 3):
+            plain = O.lw_solver_noscat_GaussQuad(top, nm, tau, lay, lev, em, ss)
+            z = O.lw_solver_noscat_GaussQuad_ext(top, nm, tau, lay, lev, em, ss, ssa=np.zeros_like(ssa), g=g)
+            assert np.array_equal(z["flux_up"], plain[0]) and np.array_equal(z["flux_dn"], plain[1])
+            r = O.lw_solver_noscat_GaussQuad_ext(top, nm, tau, lay, lev, em, ss, ssa=ssa, g=g, sfc_source_Jac=sj, want_gpt=True, fast="f64")
+            assert np.abs(r["flux_up"] - plain[0]).max() > 1e-3  # the re-scaling does something
+            fac = 2 * np.pi * 0.5 if nm == 1 else 1.0            # quirk Q3: un-scaled radiances for one angle
+            assert np.allclose(r["gpt_flux_up"].sum(-1) * fac, r["flux_up"], rtol=1e-12)
+            assert np.allclose(r["gpt_flux_dn"].sum(-1) * fac, r["flux_dn"], rtol=1e-12)
+            r2 = O.lw_solver_noscat_GaussQuad_ext(top, nm, tau, lay, lev, em, ss.astype(np.float64) + 0.5 * sj, ssa=ssa, g=g, fast="f64")
+            deriv = (r2["flux_up"] - r["flux_up"]) / 0.5
+            assert np.allclose(r["flux_up_Jac"] * fac, deriv, rtol=1e-9, atol=1e-12)
