@@ -211,6 +211,15 @@ RRNN_API int rrnn_cloud_lut_create(rrnn_ctx_t* ctx, int nbnd, int nsize_liq, int
                                    float radice_lwr, float radice_upr, const float* lut_extliq, const float* lut_ssaliq,
                                    const float* lut_asyliq, const float* lut_extice, const float* lut_ssaice,
                                    const float* lut_asyice, rrnn_cloud_lut_t** out);
+/* load_pade (extensions/cloud_optics/mo_cloud_optics.F90:178-262): Pade coefficients as stored in the coefficient files,
+ * (ncoeff, nsizereg, nbnd) with ncoeff_ext = 6 ([2/3]), ncoeff_ssa_g = 5 ([2/2]), nsizereg = 3, nbound = 4; the ice arrays for
+ * the chosen roughness.  The handle is used with rrnn_cloud_optics like a LUT handle (compute_all_from_pade :650-714). */
+RRNN_API int rrnn_cloud_pade_create(rrnn_ctx_t* ctx, int nbnd, int nsizereg, int ncoeff_ext, int ncoeff_ssa_g, int nbound,
+                                    const float* pade_extliq, const float* pade_ssaliq, const float* pade_asyliq,
+                                    const float* pade_extice, const float* pade_ssaice, const float* pade_asyice,
+                                    const float* sizreg_extliq, const float* sizreg_ssaliq, const float* sizreg_asyliq,
+                                    const float* sizreg_extice, const float* sizreg_ssaice, const float* sizreg_asyice,
+                                    rrnn_cloud_lut_t** out);
 RRNN_API int rrnn_cloud_lut_destroy(rrnn_cloud_lut_t* lut);
 /* ty_cloud_optics%cloud_optics, mo_cloud_optics.F90:354-535 (compute_all_from_table :603-645): by-band
  * (nbnd,nlay,ncol) outputs; ssa_d = g_d = NULL -> 1scl absorption optical depth (:505-513). */

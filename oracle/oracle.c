@@ -890,6 +890,67 @@ ORC_API void orc_inc_2stream_by_2stream_bybnd(int ngpt, int nlay, int ncol, floa
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Cloud optics from Pade approximants: extensions/cloud_optics/mo_cloud_optics.F90:476-493 (orders [2/3] for the
+ * extinction, [2/2] for the co-albedo and the asymmetry, three size regimes), compute_all_from_pade :650-714,
+ * pade_eval_1 :757-781, combination of liquid and ice :500-528.  Coefficients as stored in the files:
+ * (ncoeff, nsizereg, nbnd) in C order = the reference's (nbnd, nsizereg, 0:m+n); the ice arrays for ONE roughness.
+ * ------------------------------------------------------------------------------------------ */
+static float pade_eval_1(int iband, int nbnd, int nrads, int m, int n, int irad, float re, const float* c) {
+#define PC(i) c[((size_t)(i) * nrads + (irad - 1)) * nbnd + iband]
+  float denom = PC(n + m);
+  for (int i = n - 1 + m; i >= 1 + m; --i) denom = PC(i) + re * denom;
+  denom = 1.0f + re * denom;
+  float numer = PC(m);
+  for (int i = m - 1; i >= 1; --i) numer = PC(i) + re * numer;
+  numer = PC(0) + re * numer;
+#undef PC
+  return numer / denom;
+}
+
+static void pade_all(int nbnd, float wp, float re, const float* b_ext, const float* c_ext, const float* b_ssa,
+                     const float* c_ssa, const float* b_asy, const float* c_asy, float* t, float* ts, float* tsg) {
+  for (int ib = 0; ib < nbnd; ++ib) {
+    int irad = (int)floorf((re - b_ext[1]) / b_ext[2]) + 2;
+    if (irad > 3) irad = 3;
+    float tt = wp * pade_eval_1(ib, nbnd, 3, 2, 3, irad, re, c_ext);
+    irad = (int)floorf((re - b_ssa[1]) / b_ssa[2]) + 2;
+    if (irad > 3) irad = 3;
+    float tts = tt * (1.0f - fmaxf(0.0f, pade_eval_1(ib, nbnd, 3, 2, 2, irad, re, c_ssa)));
+    irad = (int)floorf((re - b_asy[1]) / b_asy[2]) + 2;
+    if (irad > 3) irad = 3;
+    tsg[ib] = tts * pade_eval_1(ib, nbnd, 3, 2, 2, irad, re, c_asy);
+    ts[ib] = tts;
+    t[ib] = tt;
+  }
+}
+
+ORC_API void orc_cloud_optics_pade(int ncol, int nlay, int nbnd, const float* clwp, const float* ciwp, const float* reliq,
+                                   const float* reice, const float* extliq, const float* ssaliq, const float* asyliq,
+                                   const float* extice, const float* ssaice, const float* asyice, const float* sizreg,
+                                   int two_stream, float* tau, float* ssa, float* g) {
+  /* sizreg: the six bound arrays of 4 back to back: extliq, ssaliq, asyliq, extice, ssaice, asyice */
+  const float eps = FLT_EPSILON;
+  float lt[64], lts[64], ltsg[64], it[64], its[64], itsg[64];
+  for (size_t s = 0; s < (size_t)ncol * nlay; ++s) {
+    if (clwp[s] > 0.0f) pade_all(nbnd, clwp[s], reliq[s], sizreg, extliq, sizreg + 4, ssaliq, sizreg + 8, asyliq, lt, lts, ltsg);
+    else for (int b = 0; b < nbnd; ++b) lt[b] = lts[b] = ltsg[b] = 0.0f;
+    if (ciwp[s] > 0.0f) pade_all(nbnd, ciwp[s], reice[s], sizreg + 12, extice, sizreg + 16, ssaice, sizreg + 20, asyice, it, its, itsg);
+    else for (int b = 0; b < nbnd; ++b) it[b] = its[b] = itsg[b] = 0.0f;
+    for (int b = 0; b < nbnd; ++b) {
+      size_t i = s * nbnd + b;
+      if (!two_stream) {
+        tau[i] = (lt[b] - lts[b]) + (it[b] - its[b]);
+      } else {
+        float t = lt[b] + it[b], ts = lts[b] + its[b];
+        g[i] = (ltsg[b] + itsg[b]) / fmaxf(eps, ts);
+        ssa[i] = ts / fmaxf(eps, t);
+        tau[i] = t;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Heating rates.
  *  orc_heating_rate      : extensions/mo_heating_rates.F90:26-54 semantics [K/s], cp_dry = 1004.64,
  *                          restated in this fork's (nlay+1,ncol) layout.

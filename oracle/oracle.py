@@ -348,6 +348,23 @@ def cloud_optics_lut(co, clwp, ciwp, reliq, reice, two_stream, fast=False):
     return tau
 
 
+def cloud_optics_pade(co, clwp, ciwp, reliq, reice, two_stream, fast=False):
+    """co: dict with pade_{ext,ssa,asy}{liq,ice} (ncoeff, 3, nbnd; ice for one roughness) and sizreg (6, 4)
+    (extensions/cloud_optics/mo_cloud_optics.F90:476-528, 650-781)."""
+    ncol, nlay = clwp.shape
+    dt = _dt(fast)
+    nbnd = co["pade_extliq"].shape[-1]
+    a = [_a(v, fast) for v in (clwp, ciwp, reliq, reice)]
+    t = [_a(co[k], fast) for k in ("pade_extliq", "pade_ssaliq", "pade_asyliq", "pade_extice", "pade_ssaice", "pade_asyice")]
+    sz = _a(co["sizreg"], fast)
+    tau = np.empty((ncol, nlay, nbnd), dt); ssa = np.empty_like(tau); g = np.empty_like(tau)
+    lib(fast).orc_cloud_optics_pade(ncol, nlay, nbnd, *[_p(v) for v in a], *[_p(v) for v in t], _p(sz), int(two_stream),
+                                    _p(tau), _p(ssa), _p(g))
+    if two_stream:
+        return tau, ssa, g
+    return tau
+
+
 def delta_scale_2str(tau, ssa, g, fast=False):
     dt = _dt(fast)
     tau = np.array(tau, dt, copy=True); ssa = np.array(ssa, dt, copy=True); g = np.array(g, dt, copy=True)

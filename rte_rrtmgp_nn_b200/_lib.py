@@ -90,6 +90,7 @@ _SIGS = {
     "rrnn_rte_sw": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_cloud_lut_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                         c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.POINTER(vp)]),
+    "rrnn_cloud_pade_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [c_float_p] * 12 + [C.POINTER(vp)]),
     "rrnn_cloud_lut_destroy": (C.c_int, [vp]),
     "rrnn_cloud_optics": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_delta_scale_2str": (C.c_int, [vp, C.c_size_t, vp, vp, vp]),

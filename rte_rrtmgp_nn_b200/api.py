@@ -648,6 +648,46 @@ class ty_cloud_optics(ty_optical_props):
             return str(e)
         return ""
 
+    def load_pade(self, band_lims_wvn, pade_extliq, pade_ssaliq, pade_asyliq, pade_extice, pade_ssaice, pade_asyice,
+                  pade_sizreg_extliq, pade_sizreg_ssaliq, pade_sizreg_asyliq, pade_sizreg_extice, pade_sizreg_ssaice,
+                  pade_sizreg_asyice, ice_roughness=2):
+        """load_pade (extensions/cloud_optics/mo_cloud_optics.F90:178-262); arrays as stored in the coefficient files: liq
+        (ncoeff, nsizereg, nbnd), ice (nrough, ncoeff, nsizereg, nbnd), size-regime bounds (nbound)."""
+        fa = lambda a: np.ascontiguousarray(a, np.float32)
+        self.icergh = int(ice_roughness)
+        r = self.icergh - 1
+        t = [fa(pade_extliq), fa(pade_ssaliq), fa(pade_asyliq), fa(np.asarray(pade_extice)[r]), fa(np.asarray(pade_ssaice)[r]),
+             fa(np.asarray(pade_asyice)[r])]
+        z = [fa(v) for v in (pade_sizreg_extliq, pade_sizreg_ssaliq, pade_sizreg_asyliq, pade_sizreg_extice, pade_sizreg_ssaice,
+                             pade_sizreg_asyice)]
+        if t[0].ndim != 3 or any(a.ndim != 3 for a in t):
+            return "cloud_optics%init(): Pade coefficient arrays must be (ncoeff, nsizereg, nband)"
+        ncoeff_ext, nsizereg, nbnd = t[0].shape
+        ncoeff_ssa_g = t[1].shape[0]
+        if t[1].shape != (ncoeff_ssa_g, nsizereg, nbnd):
+            return "cloud_optics%init(): array pade_ssaliq isn't consistently sized"
+        if t[2].shape != (ncoeff_ssa_g, nsizereg, nbnd):
+            return "cloud_optics%init(): array pade_asyliq isn't consistently sized"
+        if t[3].shape != (ncoeff_ext, nsizereg, nbnd):
+            return "cloud_optics%init(): array pade_extice isn't consistently sized"
+        if t[4].shape != (ncoeff_ssa_g, nsizereg, nbnd):
+            return "cloud_optics%init(): array pade_ssaice isn't consistently sized"
+        if t[5].shape != (ncoeff_ssa_g, nsizereg, nbnd):
+            return "cloud_optics%init(): array pade_asyice isn't consistently sized"
+        if any(v.shape != z[0].shape for v in z):
+            return "cloud_optics%init(): one or more Pade size regime arrays are inconsistently sized"
+        self.nband = self.ngpt = int(nbnd)
+        self.band2gpt = np.array([[b + 1, b + 1] for b in range(self.nband)], np.int32)
+        self.tables = dict(pade_extliq=t[0], pade_ssaliq=t[1], pade_asyliq=t[2], pade_extice=t[3], pade_ssaice=t[4], pade_asyice=t[5],
+                           sizreg=np.stack(z))
+        try:
+            _lib.check(_lib.lib().rrnn_cloud_pade_create(self.ctx.h, nbnd, nsizereg, ncoeff_ext, ncoeff_ssa_g, z[0].shape[0],
+                                                         *[a.ctypes.data_as(_lib.c_float_p) for a in t],
+                                                         *[a.ctypes.data_as(_lib.c_float_p) for a in z], C.byref(self.h)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
     def cloud_optics(self, clwp, ciwp, reliq, reice, optical_props):
         ctx = self.ctx
         a = [_dev(v, ctx) for v in (clwp, ciwp, reliq, reice)]
@@ -684,6 +724,20 @@ def load_cloud_lut_file(path):
                radliq_lwr=sc("radliq_lwr"), radliq_upr=sc("radliq_upr"), radliq_fac=sc("radliq_fac"),
                radice_lwr=sc("radice_lwr"), radice_upr=sc("radice_upr"), radice_fac=sc("radice_fac"))
     for k in ("lut_extliq", "lut_ssaliq", "lut_asyliq", "lut_extice", "lut_ssaice", "lut_asyice"):
+        out[k] = np.array(v[k][:], np.float32)
+    f.close()
+    return out
+
+
+def load_cloud_pade_file(path):
+    """Read the Pade part of a cloud-optics coefficient file -> kwargs of ty_cloud_optics.load_pade
+    (examples/all-sky/mo_load_cloud_coefficients.F90:113-200)."""
+    from scipy.io import netcdf_file
+    f = netcdf_file(path, "r", mmap=False)
+    v = f.variables
+    out = dict(band_lims_wvn=np.array(v["bnd_limits_wavenumber"][:], np.float32))
+    for k in ("pade_extliq", "pade_ssaliq", "pade_asyliq", "pade_extice", "pade_ssaice", "pade_asyice", "pade_sizreg_extliq",
+              "pade_sizreg_ssaliq", "pade_sizreg_asyliq", "pade_sizreg_extice", "pade_sizreg_ssaice", "pade_sizreg_asyice"):
         out[k] = np.array(v[k][:], np.float32)
     f.close()
     return out

@@ -170,6 +170,61 @@ __global__ void cloud_optics_kernel(const CloudParams p) {
   }
 }
 
+// compute_all_from_pade + pade_eval_1 + combine, extensions/cloud_optics/mo_cloud_optics.F90:650-714, 757-781, 500-528:
+// orders [2/3] (extinction) and [2/2] (co-albedo, asymmetry), three size regimes (:476-493)
+struct PadeParams {
+  int ncol, nlay, nbnd, two_stream;
+  float sizreg[24];  // bounds of extliq, ssaliq, asyliq, extice, ssaice, asyice (4 each)
+  const float *extliq, *ssaliq, *asyliq, *extice, *ssaice, *asyice;
+  const float *clwp, *ciwp, *reliq, *reice;
+  float *tau, *ssa, *g;
+};
+
+template <int M, int N>
+__device__ __forceinline__ float pade_eval(int iband, int nbnd, const float* bounds, float re, const float* __restrict__ c) {
+  // index into the size-regime table, as written (:683): works for exactly three regimes
+  const int irad = min((int)floorf((re - bounds[1]) / bounds[2]) + 2, 3);
+  const float* cc = c + (size_t)(irad - 1) * nbnd + iband;
+  const size_t st = (size_t)3 * nbnd;  // stride between coefficients
+  float denom = cc[(N + M) * st];
+#pragma unroll
+  for (int i = N - 1 + M; i >= 1 + M; --i) denom = cc[i * st] + re * denom;
+  denom = 1.0f + re * denom;
+  float numer = cc[M * st];
+#pragma unroll
+  for (int i = M - 1; i >= 1; --i) numer = cc[i * st] + re * numer;
+  numer = cc[0] + re * numer;
+  return numer / denom;
+}
+
+__device__ __forceinline__ void pade3(float wp, float re, bool mask, int b, int nbnd, const float* bounds, const float* e, const float* s,
+                                      const float* a, float& t, float& ts, float& tsg) {
+  if (!mask) { t = 0.f; ts = 0.f; tsg = 0.f; return; }
+  t = wp * pade_eval<2, 3>(b, nbnd, bounds, re, e);
+  ts = t * (1.0f - fmaxf(0.0f, pade_eval<2, 2>(b, nbnd, bounds + 4, re, s)));  // the co-albedo approximant can be negative
+  tsg = ts * pade_eval<2, 2>(b, nbnd, bounds + 8, re, a);
+}
+
+__global__ void cloud_optics_pade_kernel(const PadeParams p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)p.ncol * p.nlay * p.nbnd;
+  if (i >= n) return;
+  const int b = (int)(i % p.nbnd);
+  const size_t s = i / p.nbnd;
+  float lt, lts, ltsg, it, its, itsg;
+  const float lw = p.clwp[s], iw = p.ciwp[s];
+  pade3(lw, p.reliq[s], lw > 0.f, b, p.nbnd, p.sizreg, p.extliq, p.ssaliq, p.asyliq, lt, lts, ltsg);
+  pade3(iw, p.reice[s], iw > 0.f, b, p.nbnd, p.sizreg + 12, p.extice, p.ssaice, p.asyice, it, its, itsg);
+  if (!p.two_stream) {
+    p.tau[i] = (lt - lts) + (it - its);
+  } else {
+    const float t = lt + it, ts = lts + its;
+    p.g[i] = (ltsg + itsg) / fmaxf(FLT_EPSILON, ts);
+    p.ssa[i] = ts / fmaxf(FLT_EPSILON, t);
+    p.tau[i] = t;
+  }
+}
+
 // delta_scale_2str_k, rte/kernels/mo_optical_props_kernels.F90:72-93
 __global__ void delta_scale_kernel(size_t n, float* __restrict__ tau, float* __restrict__ ssa, float* __restrict__ g) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -597,6 +652,45 @@ extern "C" int rrnn_cloud_lut_create(rrnn_ctx_t* ctx, int nbnd, int nsize_liq, i
   *out = l;
   return 0;
 }
+// load_pade, extensions/cloud_optics/mo_cloud_optics.F90:178-262: coefficient arrays (ncoeff, nsizereg, nbnd) as in the files
+// (ice: one roughness), six arrays of nbound = 4 size-regime bounds
+extern "C" int rrnn_cloud_pade_create(rrnn_ctx_t* ctx, int nbnd, int nsizereg, int ncoeff_ext, int ncoeff_ssa_g, int nbound,
+                                      const float* pade_extliq, const float* pade_ssaliq, const float* pade_asyliq,
+                                      const float* pade_extice, const float* pade_ssaice, const float* pade_asyice,
+                                      const float* sizreg_extliq, const float* sizreg_ssaliq, const float* sizreg_asyliq,
+                                      const float* sizreg_extice, const float* sizreg_ssaice, const float* sizreg_asyice,
+                                      rrnn_cloud_lut_t** out) {
+  RRNN_CHECK(ctx && out && pade_extliq && pade_ssaliq && pade_asyliq && pade_extice && pade_ssaice && pade_asyice && sizreg_extliq &&
+             sizreg_ssaliq && sizreg_asyliq && sizreg_extice && sizreg_ssaice && sizreg_asyice, "cloud_optics%init(): null argument");
+  *out = nullptr;
+  RRNN_CHECK(nbound == nsizereg + 1, "cloud_optics%init(): one or more Pade size regime arrays are inconsistently sized");
+  RRNN_CHECK(nsizereg == 3, "cloud_optics%init(): Expecting precisely three size regimes for Pade approximants");
+  RRNN_CHECK(ncoeff_ext == 6 && ncoeff_ssa_g == 5, "cloud optics: code assumes Pade orders [2/3] and [2/2] but data is otherwise");
+  RRNN_CHECK(nbnd > 0, "cloud_optics%init(): number of bands inconsistent between lookup tables, spectral discretization");
+  const float* sz[6] = {sizreg_extliq, sizreg_ssaliq, sizreg_asyliq, sizreg_extice, sizreg_ssaice, sizreg_asyice};
+  // :247-256
+  RRNN_CHECK(!(sz[1][0] < sz[0][0] || sz[2][0] < sz[0][0]), "cloud_optics%init(): one or more Pade size regimes have inconsistent lowest values");
+  RRNN_CHECK(!(sz[4][0] < sz[3][0] || sz[5][0] < sz[3][0]), "cloud_optics%init(): one or more Pade size regimes have inconsistent lower values");
+  RRNN_CHECK(!(sz[1][3] > sz[0][3] || sz[2][3] > sz[0][3]), "cloud_optics%init(): one or more Pade size regimes have lowest value less than radliq_upr");
+  RRNN_CHECK(!(sz[4][3] > sz[3][3] || sz[5][3] > sz[3][3]), "cloud_optics%init(): one or more Pade size regimes have lowest value less than radice_upr");
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  rrnn_cloud_lut_t* l = new rrnn_cloud_lut_t();
+  l->nbnd = nbnd; l->is_pade = 1;
+  l->radliq_lwr = sz[0][0]; l->radice_lwr = sz[3][0];
+  for (int a = 0; a < 6; ++a)
+    for (int i = 0; i < 4; ++i) l->sizreg[4 * a + i] = sz[a][i];
+  std::vector<float> pack;
+  const float* srcs[6] = {pade_extliq, pade_ssaliq, pade_asyliq, pade_extice, pade_ssaice, pade_asyice};
+  for (int i = 0; i < 6; ++i) {
+    l->off[i] = pack.size();
+    const size_t n = (size_t)((i % 3 == 0) ? ncoeff_ext : ncoeff_ssa_g) * nsizereg * nbnd;
+    pack.insert(pack.end(), srcs[i], srcs[i] + n);
+  }
+  int rc = to_device(&l->d_tables, pack.data(), pack.size());
+  if (rc) { delete l; return rc; }
+  *out = l;
+  return 0;
+}
 extern "C" int rrnn_cloud_lut_destroy(rrnn_cloud_lut_t* l) {
   if (!l) return 0;
   cudaFree(l->d_tables);
@@ -611,6 +705,18 @@ extern "C" int rrnn_cloud_optics(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, i
   RRNN_CHECK((ssa_d == nullptr) == (g_d == nullptr), "cloud optics: ssa and g must both be given or both be absent");
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
+  if (lut->is_pade) {
+    PadeParams q{};
+    q.ncol = ncol; q.nlay = nlay; q.nbnd = lut->nbnd; q.two_stream = ssa_d ? 1 : 0;
+    for (int i = 0; i < 24; ++i) q.sizreg[i] = lut->sizreg[i];
+    q.extliq = lut->d_tables + lut->off[0]; q.ssaliq = lut->d_tables + lut->off[1]; q.asyliq = lut->d_tables + lut->off[2];
+    q.extice = lut->d_tables + lut->off[3]; q.ssaice = lut->d_tables + lut->off[4]; q.asyice = lut->d_tables + lut->off[5];
+    q.clwp = clwp_d; q.ciwp = ciwp_d; q.reliq = reliq_d; q.reice = reice_d; q.tau = tau_d; q.ssa = ssa_d; q.g = g_d;
+    const size_t nq = (size_t)ncol * nlay * lut->nbnd;
+    cloud_optics_pade_kernel<<<nblk(nq), 256, 0, ctx->stream>>>(q);
+    RRNN_LAUNCH_CHECK(ctx);
+    return 0;
+  }
   CloudParams p{};
   p.ncol = ncol; p.nlay = nlay; p.nbnd = lut->nbnd; p.nliq = lut->nsize_liq; p.nice = lut->nsize_ice;
   p.two_stream = ssa_d ? 1 : 0;

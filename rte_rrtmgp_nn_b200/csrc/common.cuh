@@ -132,6 +132,8 @@ struct rrnn_cloud_lut {
   float radliq_lwr = 0, radice_lwr = 0, liq_step = 0, ice_step = 0;
   float* d_tables = nullptr;  // extliq, ssaliq, asyliq, extice, ssaice, asyice back to back
   size_t off[6] = {};
+  int is_pade = 0;            // 1: the tables are Pade coefficients (ncoeff, 3, nbnd) and sizreg holds the 6 x 4 size-regime bounds
+  float sizreg[24] = {};
 };
 
 // ---- device helpers ------------------------------------------------------------------------------

@@ -261,3 +261,67 @@ def test_lw_solver_ext_rescaling_jacobian_gpt_fluxes():
             r2 = O.lw_solver_noscat_GaussQuad_ext(top, nm, tau, lay, lev, em, ss.astype(np.float64) + 0.5 * sj, ssa=ssa, g=g, fast="f64")
             deriv = (r2["flux_up"] - r["flux_up"]) / 0.5
             assert np.allclose(r["flux_up_Jac"] * fac, deriv, rtol=1e-9, atol=1e-12)
+
+
+def test_cloud_optics_pade_against_lut():
+    """The oracle's Pade branch (mo_cloud_optics.F90:650-781) on the shipped coefficient files: against an independent float64
+    numpy evaluation of the approximants (including the reference's regime index :683, which -- written for bounds the files
+    do not have -- keeps the middle regime until bound(2)+bound(3)), and against the LUT branch inside the LUT's radius range,
+    where the two parameterisations of the same particles agree to a few per cent (a fraction of a per cent in the median)."""
+    import oracle as O
+    from scipy.io import netcdf_file
+
+    def pade_np(c, m, n, irad, re):  # c (ncoeff, 3, nbnd); returns (nbnd,)
+        cc = c[:, irad - 1, :].astype(np.float64)
+        denom = cc[n + m]
+        for i in range(n - 1 + m, m, -1):
+            denom = cc[i] + re * denom
+        denom = 1.0 + re * denom
+        numer = cc[m]
+        for i in range(m - 1, 0, -1):
+            numer = cc[i] + re * numer
+        return (cc[0] + re * numer) / denom
+
+    for band in ("lw", "sw"):
+        f = netcdf_file(os.path.join(H.ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc"), "r", mmap=False)
+        v = {k: np.array(f.variables[k][:], np.float32) if f.variables[k].shape else np.float32(f.variables[k].getValue()) for k in f.variables}
+        f.close()
+        r = 1
+        pade = dict(pade_extliq=v["pade_extliq"], pade_ssaliq=v["pade_ssaliq"], pade_asyliq=v["pade_asyliq"], pade_extice=v["pade_extice"][r],
+                    pade_ssaice=v["pade_ssaice"][r], pade_asyice=v["pade_asyice"][r],
+                    sizreg=np.stack([v["pade_sizreg_" + k] for k in ("extliq", "ssaliq", "asyliq", "extice", "ssaice", "asyice")]))
+        nl, ni = v["lut_extliq"].shape[1], v["lut_extice"].shape[2]
+        lut = dict(extliq=v["lut_extliq"], ssaliq=v["lut_ssaliq"], asyliq=v["lut_asyliq"], extice=np.ascontiguousarray(v["lut_extice"][r]),
+                   ssaice=np.ascontiguousarray(v["lut_ssaice"][r]), asyice=np.ascontiguousarray(v["lut_asyice"][r]), liq_nsteps=nl, ice_nsteps=ni,
+                   radliq_lwr=float(v["radliq_lwr"]), radice_lwr=float(v["radice_lwr"]),
+                   liq_step_size=float((v["radliq_upr"] - v["radliq_lwr"]) / np.float32(nl - 1)),
+                   ice_step_size=float((v["radice_upr"] - v["radice_lwr"]) / np.float32(ni - 1)))
+        rng = np.random.default_rng(3)
+        n = (8, 50)
+        lwp = rng.uniform(1, 20, n).astype(np.float32); iwp = np.zeros(n, np.float32)
+        rel = rng.uniform(float(v["radliq_lwr"]), float(v["radliq_upr"]), n).astype(np.float32); rei = np.full(n, 50.0, np.float32)
+        tp, sp, gp = O.cloud_optics_pade(pade, lwp, iwp, rel, rei, True)
+        tl, sl, gl = O.cloud_optics_lut(lut, lwp, iwp, rel, rei, True)
+        rel_t = np.abs(tp - tl) / tl  # a sanity check of two fits to the same particles, not a pin: medians, not maxima
+        assert np.median(rel_t) < 0.01 and np.quantile(rel_t, 0.9) < 0.05
+        assert np.median(np.abs(sp - sl)) < 0.01 and np.median(np.abs(gp - gl)) < 0.01
+        one = O.cloud_optics_pade(pade, lwp, iwp, rel, rei, False)
+        assert np.allclose(one, tp * (1 - sp), rtol=2e-4, atol=1e-5)                              # 1scl = absorption optical depth
+        z = O.cloud_optics_pade(pade, np.zeros(n, np.float32), iwp, rel, rei, True)
+        assert not z[0].any() and not z[1].any() and not z[2].any()                               # masks
+        # liquid and ice radii across all regimes, one sample each, against the numpy evaluation
+        for re_l, re_i in ((3.0, 12.0), (9.9, 19.0), (20.0, 25.0), (40.0, 45.0), (44.9, 49.0), (50.0, 120.0)):
+            o = O.cloud_optics_pade(pade, np.array([[2.0]], np.float32), np.array([[3.0]], np.float32), np.array([[re_l]], np.float32),
+                                    np.array([[re_i]], np.float32), True, fast="f64")
+            tot = np.zeros((3, pade["pade_extliq"].shape[-1]))
+            for wp, re, k0 in ((2.0, float(np.float32(re_l)), 0), (3.0, float(np.float32(re_i)), 3)):
+                names = ("liq", "ice")[k0 // 3]
+                b = pade["sizreg"][k0:k0 + 3].astype(np.float64)
+                ir = [min(int(np.floor((re - b[j, 1]) / b[j, 2])) + 2, 3) for j in range(3)]
+                t = wp * pade_np(pade["pade_ext" + names], 2, 3, ir[0], re)
+                ts = t * (1.0 - np.maximum(0.0, pade_np(pade["pade_ssa" + names], 2, 2, ir[1], re)))
+                tot += np.stack([t, ts, ts * pade_np(pade["pade_asy" + names], 2, 2, ir[2], re)])
+            assert np.allclose(o[0][0, 0], tot[0], rtol=1e-12) and np.allclose(o[1][0, 0], tot[1] / tot[0], rtol=1e-12)
+            assert np.allclose(o[2][0, 0], tot[2] / tot[1], rtol=1e-12)
+        b = pade["sizreg"][0]
+        assert min(int(np.floor((40.0 - b[1]) / b[2])) + 2, 3) == 2 and 40.0 > b[2]               # the quirk: 40 um is past regime 2

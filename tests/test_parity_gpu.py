@@ -643,6 +643,45 @@ def test_all_sky_fluxes_match_oracle(gpu_ctx):
         H.assert_within_reference_noise(got.cpu().numpy(), a, b, H.FLUX_TOL, "all-sky SW flux_" + nm)
 
 
+def test_cloud_optics_pade_matches_oracle(gpu_ctx):
+    """ty_cloud_optics%load_pade + cloud_optics (extensions/cloud_optics/mo_cloud_optics.F90:178-262, 476-528, 650-781), both
+    bands, 1scl and 2str, all three ice roughnesses, radii across the three size regimes (including the stretch where the
+    reference's regime index, as written, stays in the middle regime past its upper bound)."""
+    import os
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral
+    torch = _torch()
+    rng = np.random.default_rng(12)
+    ncol, nlay = 17, 23
+    for band, ngpt, mk in (("lw", 256, spectral.synthetic_kdist_lw), ("sw", 224, spectral.synthetic_kdist_sw)):
+        path = os.path.join(H.ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc")
+        args = api.load_cloud_pade_file(path)
+        k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); k_dist.load(mk(ngpt))
+        for rough in (1, 2, 3):
+            co = api.ty_cloud_optics(gpu_ctx)
+            assert co.load_pade(**args, ice_roughness=rough) == ""
+            z = co.tables["sizreg"]
+            lwp = rng.uniform(0, 30, (ncol, nlay)).astype(np.float32); iwp = rng.uniform(0, 30, (ncol, nlay)).astype(np.float32)
+            lwp[rng.uniform(size=lwp.shape) < 0.3] = 0; iwp[rng.uniform(size=iwp.shape) < 0.3] = 0
+            rel = rng.uniform(z[0, 0], z[0, 3], (ncol, nlay)).astype(np.float32)
+            rei = rng.uniform(z[3, 0], z[3, 3], (ncol, nlay)).astype(np.float32)
+            for two in (False, True):
+                clouds = api.ty_optical_props_2str() if two else api.ty_optical_props_1scl()
+                (clouds.alloc_2str if two else clouds.alloc_1scl)(ncol, nlay, k_dist, by_band=True)
+                assert co.cloud_optics(lwp, iwp, rel, rei, clouds) == ""
+                ref = O.cloud_optics_pade(co.tables, lwp, iwp, rel, rei, two)
+                r64 = O.cloud_optics_pade(co.tables, lwp, iwp, rel, rei, two, fast="f64")
+                # rational functions evaluated outside their fitted range have small denominators here and there: the
+                # statement is "as close to the fp64 evaluation as the strict fp32 oracle is" (x3), 2e-5 elsewhere
+                gots = (clouds.tau, clouds.ssa, clouds.g) if two else (clouds.tau,)
+                for got, want, w64 in zip(gots, ref if two else (ref,), r64 if two else (r64,)):
+                    err = np.abs(got.cpu().numpy() - w64)
+                    lim = np.maximum(2e-5 * np.abs(w64) + 2e-6 * np.abs(w64).max(), 3.0 * np.abs(want - w64))
+                    assert (err <= lim).all(), (band, rough, two, float((err / lim).max()))
+    bad = dict(args); bad["pade_ssaliq"] = args["pade_ssaliq"][:4]
+    assert "isn't consistently sized" in api.ty_cloud_optics(gpu_ctx).load_pade(**bad)
+
+
 def test_heating_rate_K_per_s(gpu_ctx):
     import oracle as O
     from rte_rrtmgp_nn_b200 import api
