@@ -404,8 +404,8 @@ def main():
                 "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_column": abytes[dom],
                 "algorithmic_bytes_per_launch": abytes[dom] * cols_per_launch, "columns_per_launch": cols_per_launch,
                 "ms_per_launch": kern[dom]["ms_per_step"] / max(nl, 1.0),
-                "note": "the RTE solvers are bound by instruction issue and latency, not by HBM (ncu: issue slots ~43 % busy, fp32x2 + MUFU "
-                        "arithmetic); their DRAM traffic exceeds the algorithmic bytes because the reverse-sweep scratch of all resident "
+                "note": "the RTE solvers are bound by instruction issue and latency, not by HBM (ncu, sw_solver: 209 warp instructions per "
+                        "64 g-points and layer, issue slots 56 % busy at 12 warps/SM, fp32x2 + MUFU arithmetic); their DRAM traffic exceeds the algorithmic bytes because the reverse-sweep scratch of all resident "
                         "warps is larger than the L2 and partly spills (DESIGN.md section 3)",
                 "per_kernel": kern}
 
