@@ -197,6 +197,14 @@ RRNN_API int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int nco
                                     const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
                                     const float* mu0_d, const float* sfc_alb_dir_d, const float* sfc_alb_dif_d,
                                     float* flux_up_d, float* flux_dn_d, float* flux_dir_d);
+/* sw_solver_2stream with its optional g-point fluxes (rte/kernels/mo_rte_solver_kernels.F90:541-692, save_gpt_flux):
+ * gpt_flux_{up,dn,dir}_d (ngpt,nlay+1,ncol), all three or none; gpt_flux_dn is the TOTAL downward flux (:660-663).  The
+ * reference's own three sweeps (sw_two_stream_source :1366-1480, adding :1526-1637), a general kernel, not the tuned one. */
+RRNN_API int rrnn_sw_solver_2stream_ext(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux_d,
+                                        const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
+                                        const float* mu0_d, const float* sfc_alb_dir_d, const float* sfc_alb_dif_d,
+                                        float* flux_up_d, float* flux_dn_d, float* flux_dir_d, float* gpt_flux_up_d,
+                                        float* gpt_flux_dn_d, float* gpt_flux_dir_d);
 /* rte_sw for ty_optical_props_2str, rte/mo_rte_sw.F90:48-266 (albedos per g-point, :50-61). */
 RRNN_API int rrnn_rte_sw(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* mu0_d,
                          const float* inc_flux_d, const float* sfc_alb_dir_gpt_d, const float* sfc_alb_dif_gpt_d,

@@ -659,10 +659,12 @@ ORC_API void orc_lw_solver_noscat_GaussQuad_ext(int ngpt, int nlay, int ncol, in
  *   sw_two_stream_source :1366-1480, adding :1526-1637, k_min = 1e-4 (:76-82),
  *   broadband sums :643-680.
  * ------------------------------------------------------------------------------------------ */
-ORC_API void orc_sw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux,
+static void sw_solver_2stream_core(int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux,
                                    const float* inc_flux_dif, const float* tau, const float* ssa,
                                    const float* gasym, const float* mu0v, const float* sfc_alb_dir,
-                                   const float* sfc_alb_dif, float* flux_up, float* flux_dn, float* flux_dir) {
+                                   const float* sfc_alb_dif, float* flux_up, float* flux_dn, float* flux_dir,
+                                   float* gpt_up, float* gpt_dn, float* gpt_dir) {
+  /* gpt_*: optional g-point fluxes (ngpt,nlay+1,ncol), save_gpt_flux :557-587; flux_dn_gpt is the TOTAL downward flux :660-663 */
   const float k_min = 1.e-4f;
   const int top_level = top_at_1 ? 0 : nlay;
 #pragma omp parallel
@@ -674,10 +676,10 @@ ORC_API void orc_sw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, c
     float* source_up = Tdif + nl;
     float* source_dn = source_up + nl;
     float* denom = source_dn + nl;
-    float* radn_up = denom + nl;
-    float* radn_dn = radn_up + nv;
-    float* radn_dir = radn_dn + nv;
-    float* albedo = radn_dir + nv;
+    float* radn_up_arr = denom + nl;
+    float* radn_dn_arr = radn_up_arr + nv;
+    float* radn_dir_arr = radn_dn_arr + nv;
+    float* albedo = radn_dir_arr + nv;
     float* src = albedo + nv;
     float* source_sfc = src + nv;
 #pragma omp for schedule(static)
@@ -686,6 +688,9 @@ ORC_API void orc_sw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, c
       const float* w0c = ssa + (size_t)icol * nl;
       const float* gc = gasym + (size_t)icol * nl;
       const float mu0 = mu0v[icol];
+      float* radn_up = gpt_up ? gpt_up + (size_t)icol * nv : radn_up_arr;
+      float* radn_dn = gpt_up ? gpt_dn + (size_t)icol * nv : radn_dn_arr;
+      float* radn_dir = gpt_up ? gpt_dir + (size_t)icol * nv : radn_dir_arr;
       for (int g = 0; g < ngpt; ++g) {
         radn_dir[(size_t)top_level * ngpt + g] = inc_flux[(size_t)icol * ngpt + g] * mu0;
         radn_dn[(size_t)top_level * ngpt + g] = inc_flux_dif[(size_t)icol * ngpt + g];
@@ -781,7 +786,12 @@ ORC_API void orc_sw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, c
               size_t i = (size_t)lev * ngpt + g + j;
               su[j] = su[j] + radn_up[i];
               sr[j] = sr[j] + radn_dir[i];
-              sd[j] = sd[j] + radn_dn[i] + radn_dir[i];
+              if (gpt_up) {
+                radn_dn[i] = radn_dn[i] + radn_dir[i];
+                sd[j] = sd[j] + radn_dn[i];
+              } else {
+                sd[j] = sd[j] + radn_dn[i] + radn_dir[i];
+              }
             }
           flux_up[(size_t)icol * (nlay + 1) + lev] = su[0] + su[1] + su[2] + su[3];
           flux_dn[(size_t)icol * (nlay + 1) + lev] = sd[0] + sd[1] + sd[2] + sd[3];
@@ -792,7 +802,8 @@ ORC_API void orc_sw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, c
           float su = 0, sd = 0, sr = 0;
           for (int g = 0; g < ngpt; ++g) {
             size_t i = (size_t)lev * ngpt + g;
-            su += radn_up[i]; sr += radn_dir[i]; sd += (radn_dn[i] + radn_dir[i]);
+            if (gpt_up) radn_dn[i] = radn_dn[i] + radn_dir[i];
+            su += radn_up[i]; sr += radn_dir[i]; sd += gpt_up ? radn_dn[i] : (radn_dn[i] + radn_dir[i]);
           }
           flux_up[(size_t)icol * (nlay + 1) + lev] = su;
           flux_dn[(size_t)icol * (nlay + 1) + lev] = sd;
@@ -802,6 +813,23 @@ ORC_API void orc_sw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, c
     }
     free(wk);
   }
+}
+
+ORC_API void orc_sw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux,
+                                   const float* inc_flux_dif, const float* tau, const float* ssa,
+                                   const float* gasym, const float* mu0v, const float* sfc_alb_dir,
+                                   const float* sfc_alb_dif, float* flux_up, float* flux_dn, float* flux_dir) {
+  sw_solver_2stream_core(ngpt, nlay, ncol, top_at_1, inc_flux, inc_flux_dif, tau, ssa, gasym, mu0v, sfc_alb_dir, sfc_alb_dif, flux_up,
+                         flux_dn, flux_dir, NULL, NULL, NULL);
+}
+
+ORC_API void orc_sw_solver_2stream_gpt(int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux,
+                                       const float* inc_flux_dif, const float* tau, const float* ssa,
+                                       const float* gasym, const float* mu0v, const float* sfc_alb_dir,
+                                       const float* sfc_alb_dif, float* flux_up, float* flux_dn, float* flux_dir,
+                                       float* gpt_up, float* gpt_dn, float* gpt_dir) {
+  sw_solver_2stream_core(ngpt, nlay, ncol, top_at_1, inc_flux, inc_flux_dif, tau, ssa, gasym, mu0v, sfc_alb_dir, sfc_alb_dif, flux_up,
+                         flux_dn, flux_dir, gpt_up, gpt_dn, gpt_dir);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -324,6 +324,19 @@ def sw_solver_2stream(top_at_1, inc_flux, inc_flux_dif, tau, ssa, g, mu0, alb_di
     return up, dn, dr
 
 
+def sw_solver_2stream_gpt(top_at_1, inc_flux, inc_flux_dif, tau, ssa, g, mu0, alb_dir, alb_dif, fast=False):
+    """sw_solver_2stream with the optional g-point fluxes (mo_rte_solver_kernels.F90:541-692, save_gpt_flux): returns
+    flux_up, flux_dn, flux_dir, gpt_flux_up, gpt_flux_dn (total), gpt_flux_dn_dir."""
+    ncol, nlay, ngpt = tau.shape
+    dt = _dt(fast)
+    a = [_a(v, fast) for v in (inc_flux, inc_flux_dif, tau, ssa, g, mu0, alb_dir, alb_dif)]
+    up = np.empty((ncol, nlay + 1), dt); dn = np.empty_like(up); dr = np.empty_like(up)
+    gu = np.empty((ncol, nlay + 1, ngpt), dt); gd = np.empty_like(gu); gr = np.empty_like(gu)
+    lib(fast).orc_sw_solver_2stream_gpt(ngpt, nlay, ncol, int(bool(top_at_1)), *[_p(v) for v in a], _p(up), _p(dn), _p(dr),
+                                        _p(gu), _p(gd), _p(gr))
+    return up, dn, dr, gu, gd, gr
+
+
 def rte_sw(top_at_1, mu0, inc_flux, alb_dir_gpt, alb_dif_gpt, tau, ssa, g, inc_flux_dif=None, fast=False):
     if inc_flux_dif is None:
         inc_flux_dif = np.zeros_like(inc_flux)

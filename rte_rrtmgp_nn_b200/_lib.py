@@ -87,6 +87,7 @@ _SIGS = {
     "rrnn_rte_lw_ext": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 15),
     "rrnn_rte_lw": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_sw_solver_2stream": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rrnn_sw_solver_2stream_ext": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 14),
     "rrnn_rte_sw": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_cloud_lut_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                         c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.POINTER(vp)]),

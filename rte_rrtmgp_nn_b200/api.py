@@ -422,9 +422,10 @@ class ty_fluxes_flexible(ty_fluxes_broadband):
     """ty_fluxes_flexible (rte/mo_fluxes.F90:52-67): broadband fluxes plus, when associated, the g-point fluxes
     gpt_flux_up / gpt_flux_dn (ncol, nlay+1, ngpt)."""
 
-    def __init__(self, flux_up=None, flux_dn=None, flux_net=None, flux_dn_dir=None, gpt_flux_up=None, gpt_flux_dn=None):
+    def __init__(self, flux_up=None, flux_dn=None, flux_net=None, flux_dn_dir=None, gpt_flux_up=None, gpt_flux_dn=None,
+                 gpt_flux_dn_dir=None):
         super().__init__(flux_up, flux_dn, flux_net, flux_dn_dir)
-        self.gpt_flux_up, self.gpt_flux_dn = gpt_flux_up, gpt_flux_dn
+        self.gpt_flux_up, self.gpt_flux_dn, self.gpt_flux_dn_dir = gpt_flux_up, gpt_flux_dn, gpt_flux_dn_dir
 
 
 class ty_gas_optics_rrtmgp(ty_optical_props):
@@ -608,6 +609,20 @@ def rte_sw(atmos, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, flu
     if tuple(a_dif.shape) != (ncol, ngpt):
         return "rte_sw: sfc_alb_dif inconsistently sized"
     g_p = None if atmos.g_is_zero and atmos._g is None else _ptr(atmos.g)
+    gpt = [getattr(fluxes, k, None) for k in ("gpt_flux_up", "gpt_flux_dn", "gpt_flux_dn_dir")]
+    if any(v is not None for v in gpt):  # ty_fluxes_flexible with g-point fluxes: the general kernel
+        if any(v is None for v in gpt):
+            return "rte_sw: gpt_flux_up, gpt_flux_dn and gpt_flux_dn_dir must all be associated"
+        if any(tuple(v.shape) != (ncol, nlay + 1, ngpt) for v in gpt):
+            return "rte_sw: g-point flux arrays inconsistently sized"
+        try:
+            _lib.check(_lib.lib().rrnn_sw_solver_2stream_ext(ctx.h, ngpt, nlay, ncol, int(bool(top_at_1)), _ptr(inc_flux),
+                                                             _ptr(_dev(inc_flux_dif, ctx)), _ptr(atmos.tau), _ptr(atmos.ssa), g_p, _ptr(mu0),
+                                                             _ptr(a_dir), _ptr(a_dif), _ptr(fluxes.flux_up), _ptr(fluxes.flux_dn),
+                                                             _ptr(fluxes.flux_dn_dir), *[_ptr(v) for v in gpt]))
+        except RRNNError as e:
+            return str(e)
+        return ""
     try:
         _lib.check(_lib.lib().rrnn_rte_sw(ctx.h, ngpt, nlay, ncol, int(bool(top_at_1)), _ptr(mu0), _ptr(inc_flux), _ptr(a_dir),
                                           _ptr(a_dif), _ptr(_dev(inc_flux_dif, ctx)), _ptr(atmos.tau), _ptr(atmos.ssa), g_p,

@@ -443,6 +443,66 @@ def test_rte_lw_with_2str_clouds_and_optional_arguments(gpu_ctx):
     assert "two-stream" in api.rte_lw(op, True, src, emis, fl1, use_2stream=True)
 
 
+@pytest.mark.parametrize("G,L,C,top,has_g", [(224, 60, 7, True, True), (112, 33, 5, False, True), (224, 137, 3, True, False), (36, 6, 4, False, True)])
+def test_sw_gpt_fluxes_and_three_sweep_kernel(gpu_ctx, G, L, C, top, has_g):
+    """rrnn_sw_solver_2stream_ext (the reference's three sweeps, g-point fluxes) against the oracle, and as an
+    independent cross-check of the reformulated production kernel sw_solver_v5 on the same inputs."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    rng = np.random.default_rng(G * L)
+    tau = rng.gamma(0.4, 1.5, size=(C, L, G)).astype(np.float32)
+    ssa = rng.uniform(0.0, 0.999, size=(C, L, G)).astype(np.float32)
+    g = rng.uniform(-0.2, 0.9, size=(C, L, G)).astype(np.float32) if has_g else np.zeros((C, L, G), np.float32)
+    mu0 = rng.uniform(0.05, 1.0, size=C).astype(np.float32)
+    inc = rng.uniform(0.5, 8.0, size=(C, G)).astype(np.float32); incd = rng.uniform(0.0, 1.0, size=(C, G)).astype(np.float32)
+    ad = rng.uniform(0.0, 0.9, size=(C, G)).astype(np.float32); af = rng.uniform(0.0, 0.9, size=(C, G)).astype(np.float32)
+    ref = O.sw_solver_2stream_gpt(top, inc, incd, tau, ssa, g, mu0, ad, af)
+    r64 = O.sw_solver_2stream_gpt(top, inc, incd, tau, ssa, g, mu0, ad, af, fast="f64")
+    d = {k: torch.from_numpy(v).cuda() for k, v in dict(inc=inc, incd=incd, tau=tau, ssa=ssa, g=g, mu0=mu0, ad=ad, af=af).items()}
+    P = api._ptr
+    fl = [torch.zeros((C, L + 1), device="cuda") for _ in range(6)]
+    gp = [torch.zeros((C, L + 1, G), device="cuda") for _ in range(3)]
+    lib = _lib.lib()
+    gptr = P(d["g"]) if has_g else None
+    _lib.check(lib.rrnn_sw_solver_2stream_ext(gpu_ctx.h, G, L, C, int(top), P(d["inc"]), P(d["incd"]), P(d["tau"]), P(d["ssa"]), gptr,
+                                              P(d["mu0"]), P(d["ad"]), P(d["af"]), P(fl[0]), P(fl[1]), P(fl[2]), P(gp[0]), P(gp[1]), P(gp[2])))
+    _lib.check(lib.rrnn_sw_solver_2stream(gpu_ctx.h, G, L, C, int(top), P(d["inc"]), P(d["incd"]), P(d["tau"]), P(d["ssa"]), gptr,
+                                          P(d["mu0"]), P(d["ad"]), P(d["af"]), P(fl[3]), P(fl[4]), P(fl[5])))
+    scale = max(np.abs(ref[1]).max(), 1.0)
+    for k in range(3):
+        for got in (fl[k], fl[3 + k]):   # the three-sweep kernel and the production kernel
+            e = np.abs(got.cpu().numpy() - r64[k])
+            noise = np.abs(ref[k] - r64[k])
+            assert e.max() <= max(6e-5 * scale, 2.0 * noise.max()), (k, e.max(), noise.max())
+        gs = max(np.abs(ref[3 + k]).max(), 1e-3)
+        e = np.abs(gp[k].cpu().numpy() - r64[3 + k]).max()
+        noise = np.abs(ref[3 + k] - r64[3 + k]).max()
+        assert e <= max(2e-5 * gs, 2.0 * noise), (k, e, noise)
+    # the g-point fluxes add up to the broadband ones, and the saved downward flux is the total one
+    assert torch.allclose(gp[0].sum(-1), fl[0], rtol=1e-5, atol=1e-4) and torch.allclose(gp[1].sum(-1), fl[1], rtol=1e-5, atol=1e-4)
+    assert bool((gp[1] >= gp[2] - 1e-6).all())
+    # without g-point outputs the same kernel gives the same broadband fluxes
+    f2 = [torch.zeros((C, L + 1), device="cuda") for _ in range(3)]
+    _lib.check(lib.rrnn_sw_solver_2stream_ext(gpu_ctx.h, G, L, C, int(top), P(d["inc"]), P(d["incd"]), P(d["tau"]), P(d["ssa"]), gptr,
+                                              P(d["mu0"]), P(d["ad"]), P(d["af"]), P(f2[0]), P(f2[1]), P(f2[2]), None, None, None))
+    assert torch.allclose(f2[0], fl[0], rtol=1e-6, atol=1e-5) and torch.allclose(f2[1], fl[1], rtol=1e-6, atol=1e-5)
+    # host mirror: rte_sw with ty_fluxes_flexible
+    from rte_rrtmgp_nn_b200 import spectral
+    if G == 224:
+        k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); k_dist.load(spectral.synthetic_kdist_sw(224))
+        atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(C, L, k_dist) == ""
+        atmos.tau.copy_(d["tau"]); atmos.ssa.copy_(d["ssa"])
+        if has_g:
+            atmos.g = d["g"].clone()
+        else:
+            atmos.g_is_zero = True
+        mk = lambda *s: torch.zeros(s, device="cuda")
+        flx = api.ty_fluxes_flexible(mk(C, L + 1), mk(C, L + 1), None, mk(C, L + 1), mk(C, L + 1, G), mk(C, L + 1, G), mk(C, L + 1, G))
+        assert api.rte_sw(atmos, top, mu0, inc, ad, af, flx, inc_flux_dif=incd) == ""
+        assert torch.equal(flx.gpt_flux_up, gp[0]) and torch.equal(flx.flux_dn, fl[1])
+
+
 def test_sgemm_entry_points(gpu_ctx):
     """output_sgemm_tau / _pfrac / _lw on materialised inputs (+ compute_nn_inputs, get_col_dry, Planck source)."""
     import oracle as O
