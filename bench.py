@@ -187,7 +187,7 @@ def run_reference(args):
                                    "(C restatement of the reference kernels, -O3 AVX2 OpenMP) -- the Fortran reference cannot be built here"},
         "e2e": {"value": value, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(ngpus, ncol_total):
@@ -198,7 +198,28 @@ def workload_config(ngpus, ncol_total):
             "l2": "per-step working set (optical properties, ~1.6 MB/column) is far larger than the 126 MB L2; no explicit flush"}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG is set in the environment): from here on file descriptor 1 goes to stderr and the JSON line is written to
+    the real stdout kept aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     global NLAY
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,7 +445,7 @@ def main():
         "fast_math": int(args.fast_math), "lw_compact_source": int(bool(args.lw_compact_source) and args.solver_variant == 0), "nn_variant": "tcgen05 (fp16 hi/lo split operands, fp32 accumulation in TMEM)",
         "solver_variant": {0: "v5 TMA-staged packed fp32x2", 2: "v4 packed fp32x2", 1: "v3 one g-point per lane"}[args.solver_variant],
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
