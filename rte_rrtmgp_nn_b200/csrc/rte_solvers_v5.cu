@@ -37,13 +37,14 @@ namespace v5 {
 #define RRNN_V5_LW_S 2
 #endif
 #ifndef RRNN_V5_SW_U
-#define RRNN_V5_SW_U 4
+#define RRNN_V5_SW_U 8
 #endif
 #ifndef RRNN_V5_SW_S
-#define RRNN_V5_SW_S 3
+#define RRNN_V5_SW_S 2
 #endif
 constexpr int MAX_WARPS = 4;  // solvers (warps) per CTA
 constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
+constexpr int SW_OBR = (SW_U > 4) ? SW_U / 2 : SW_U;  // layers per store-staging tile of the SW solver
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -612,9 +613,11 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
 
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
   uint8_t* in_ring = smem;                                     // [S][NIN][U][256 B]: tau, ssa (, g)
-  uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][U][768 B]
+  // store staging: two tiles of OBR layers (groups of 8 layers are staged and stored in two halves: 6 KB less per solver)
+  constexpr int OBR = SW_OBR, NOB = U / OBR;
+  uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][OBR][768 B]
   uint8_t* bb = smem;                                          // [S][U][768 B]  (aliases in_ring / ob, see lw_solver_v5)
-  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * U * SWROW, BWD_BYTES = S * U * SWROW;
+  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * OBR * SWROW, BWD_BYTES = S * U * SWROW;
   float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][3][L+1]
   const int part_set = 3 * (L + 1) + ((L + 1) & 1);            // keep the barriers 8-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
@@ -719,47 +722,57 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
         box_start<TOP, U>(lay0, k, shl);
         nvalid = min(U, L - k * U);
       }
-      f2 tau[U], w0[U], gg[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
-        tau[u] = lds2(base + rl * 256);
-        w0[u] = lds2(base + U * 256 + rl * 256);
-        gg[u] = HAS_G ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
-      }
       flush_fwd();
-      // layer coefficients: independent across the U layers (instruction-level parallelism)
-      f2 Rdif[U], Tdif[U], Rdir[U], Tdir[U], Tnos[U];
-      two_stream2_batch<FAST, HAS_G, U>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-      uint8_t* ot = ob + (k & 1) * (U * SWROW);
       // the sequential part: direct beam and the adding recurrences, eliminated from the top
       float red[2 * U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!TAIL || u < nvalid) {  // warp-uniform
-          const f2 s_up = Rdir[u] * dir;
-          const f2 s_dn = Tdir[u] * dir;
-          dir = Tnos[u] * dir;
-          const f2 d = rcp2<FAST>(fnma2(Rdif[u], alpha, splat2(1.0f)));
-          const f2 e = d * Tdif[u];
-          const f2 f = d * fma2(Rdif[u], beta, s_up);
-          sts2(ot + u * SWROW + lane_al, alpha);  // reflectance of the atmosphere ABOVE this layer: what sweep 2 needs
-          sts22(ot + u * SWROW + lane_ef, e, f);
-          beta = fma2(e, fma2(alpha, s_up, beta), s_dn);
-          alpha = fma2(Tdif[u] * e, alpha, Rdif[u]);
+      for (int h = 0; h < NOB; ++h) {
+        // layer coefficients of this half: independent across its OBR layers (instruction-level parallelism); a group of
+        // 8 layers is done in two halves so that the register footprint stays that of 4 layers
+        f2 tau[OBR], w0[OBR], gg[OBR];
+#pragma unroll
+        for (int uu = 0; uu < OBR; ++uu) {
+          const int u = h * OBR + uu;
+          const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
+          tau[uu] = lds2(base + rl * 256);
+          w0[uu] = lds2(base + U * 256 + rl * 256);
+          gg[uu] = HAS_G ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
         }
-        red[u] = hsum2(dir);
-        red[U + u] = hsum2(beta + dir);
+        f2 Rdif[OBR], Tdif[OBR], Rdir[OBR], Tdir[OBR], Tnos[OBR];
+        two_stream2_batch<FAST, HAS_G, OBR>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+        // staging tile (k*NOB + h) & 1: free once the bulk store issued two tiles ago has read it
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const int slot = (k * NOB + h) & 1;
+        uint8_t* ot = ob + slot * (OBR * SWROW);
+#pragma unroll
+        for (int uu = 0; uu < OBR; ++uu) {
+          const int u = h * OBR + uu;
+          if (!TAIL || u < nvalid) {  // warp-uniform
+            const f2 s_up = Rdir[uu] * dir;
+            const f2 s_dn = Tdir[uu] * dir;
+            dir = Tnos[uu] * dir;
+            const f2 d = rcp2<FAST>(fnma2(Rdif[uu], alpha, splat2(1.0f)));
+            const f2 e = d * Tdif[uu];
+            const f2 f = d * fma2(Rdif[uu], beta, s_up);
+            sts2(ot + uu * SWROW + lane_al, alpha);  // reflectance of the atmosphere ABOVE this layer: what sweep 2 needs
+            sts22(ot + uu * SWROW + lane_ef, e, f);
+            beta = fma2(e, fma2(alpha, s_up, beta), s_dn);
+            alpha = fma2(Tdif[uu] * e, alpha, Rdif[uu]);
+          }
+          red[u] = hsum2(dir);
+          red[U + u] = hsum2(beta + dir);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          const int nrows = min(max(nvalid - h * OBR, 0), OBR);
+          if (nrows > 0)
+            bulk_store(scratch + ((size_t)k * U + h * OBR) * SWROW, ob_a + slot * (OBR * SWROW), (uint32_t)nrows * SWROW, pol_buf);
+          bulk_commit();
+        }
+        __syncwarp();
       }
-      fence_async_smem();
-      __syncwarp();
-      if (elect_one()) {
-        bulk_store(scratch + (size_t)k * (U * SWROW), ob_a + (k & 1) * (U * SWROW), (uint32_t)nvalid * SWROW, pol_buf);
-        bulk_commit();
-      }
-      __syncwarp();
 #pragma unroll
       for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
       pend_k = k;
@@ -1007,7 +1020,7 @@ int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, v5::SW_U)) return rc; }
   else tm_g = tm_ssa;
   const int nin = p.g ? 3 : 2;
-  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_U * v5::SWROW, (size_t)v5::SW_S * v5::SW_U * v5::SWROW) +
+  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_OBR * v5::SWROW, (size_t)v5::SW_S * v5::SW_U * v5::SWROW) +
                       2 * (size_t)(3 * (L + 1) + 1) * 4 + 2 * v5::SW_S * 8;
   const size_t per_cta = (size_t)L * v5::SWROW;
   const bool top = p.top_at_1 != 0;
