@@ -36,6 +36,9 @@ namespace v5 {
 #ifndef RRNN_V5_LW_S
 #define RRNN_V5_LW_S 2
 #endif
+#ifndef RRNN_V5_DISCARD
+#define RRNN_V5_DISCARD 1
+#endif
 #ifndef RRNN_V5_SW_U
 #define RRNN_V5_SW_U 8
 #endif
@@ -112,6 +115,14 @@ __device__ __forceinline__ void exp_and_complement2(f2 x, f2& t, f2& omt) {
   const bool sx = xx < 0.35f, sy = xy < 0.35f;
   omt = sel2(sx, sy, neg2(em1), splat2(1.0f) - e);
   t = sel2(sx, sy, splat2(1.0f) + em1, e);
+}
+
+// The reverse-sweep scratch is dead once the upward sweep has pulled a group back into shared memory: discarding its L2
+// lines (no write-back; the contents become undefined until the next column's downward sweep rewrites them in full) saves
+// the DRAM write of every line that was still resident -- the L2 only writes dirty lines back when it evicts them.
+__device__ __forceinline__ void discard_scratch(const uint8_t* base, uint32_t bytes, int lane) {
+  if (RRNN_V5_DISCARD)
+    for (uint32_t o = (uint32_t)lane * 128u; o < bytes; o += 32u * 128u) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + o) : "memory");
 }
 
 // one lane of a converged warp (elect.sync): ptxas then issues the uniform-datapath TMA instructions straight, without
@@ -409,6 +420,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
         mbar_wait(bar_bb + 8 * st, (nj / S) & 1u);
         const uint8_t* bt = bb + st * (U * 512) + lane_bf;
         const int nvalid = TAIL ? min(U, L - k * U) : U;
+        discard_scratch(scratch + (size_t)k * (U * 512), (uint32_t)nvalid * 512u, lane);
         f2 t[U], s[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) lds22(bt + (TAIL ? min(u, nvalid - 1) : u) * 512, t[u], s[u]);
@@ -820,6 +832,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
       mbar_wait(bar_bb + 8 * st, (nj / S) & 1u);
       const uint8_t* bt = bb + st * (U * SWROW);
       const int nvalid = TAIL ? min(U, L - k * U) : U;
+      discard_scratch(scratch + (size_t)k * (U * SWROW), (uint32_t)nvalid * SWROW, lane);
       f2 e[U], f[U], a[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
