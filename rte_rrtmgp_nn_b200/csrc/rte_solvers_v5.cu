@@ -47,7 +47,8 @@ namespace v5 {
 #endif
 constexpr int MAX_WARPS = 4;  // solvers (warps) per CTA
 constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
-constexpr int SW_OBR = (SW_U > 4) ? SW_U / 2 : SW_U;  // layers per store-staging tile of the SW solver
+constexpr int SW_OBR = (SW_U > 4) ? SW_U / 2 : SW_U;
+constexpr int LW_OBR = (LW_U > 4) ? LW_U / 2 : LW_U;  // layers per store-staging tile of the SW solver
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -186,9 +187,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
   // The input ring and the store staging are only live during the downward sweep, the back ring only during the upward
   // sweep (bulk_wait_all separates them): they share their shared memory, which is what bounds the CTAs per SM.
   uint8_t* in_ring = smem;                                   // [S][STAGE]
-  uint8_t* ob = in_ring + S * STAGE;                         // [2][U][512 B]
+  constexpr int OBR = LW_OBR, NOB = U / OBR;                 // store staging in tiles of OBR layers (see sw_solver_v5)
+  uint8_t* ob = in_ring + S * STAGE;                         // [2][OBR][512 B]
   uint8_t* bb = smem;                                        // [S][U][512 B]  (aliases in_ring / ob)
-  constexpr int FWD_BYTES = S * STAGE + 2 * U * 512, BWD_BYTES = S * U * 512;
+  constexpr int FWD_BYTES = S * STAGE + 2 * OBR * 512, BWD_BYTES = S * U * 512;
   float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][2][L+1]
   const int part_set = 2 * (L + 1);
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
@@ -354,26 +356,33 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
           sup[u] = fma2(f2x, lay[u] - lev_up, omt * lev_up);
         }
         carry = ext[U - 1];
-        // reverse-buffer staging tile k&1: free once the bulk store of group k-2 has read it
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
-        uint8_t* ot = ob + (k & 1) * (U * 512) + lane_bf;
         float red[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (!TAIL || u < nvalid) {  // warp-uniform
-            I = fma2(tv[u], I, sdn[u]);
-            sts22(ot + u * 512, tv[u], sup[u]);
+        for (int h = 0; h < NOB; ++h) {
+          // reverse-buffer staging tile (k*NOB + h) & 1 (OBR layers): free once the bulk store issued two tiles ago has read it
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const int slot = (k * NOB + h) & 1;
+          uint8_t* ot = ob + slot * (OBR * 512) + lane_bf;
+#pragma unroll
+          for (int uu = 0; uu < OBR; ++uu) {
+            const int u = h * OBR + uu;
+            if (!TAIL || u < nvalid) {  // warp-uniform
+              I = fma2(tv[u], I, sdn[u]);
+              sts22(ot + uu * 512, tv[u], sup[u]);
+            }
+            red[u] = hsum2(fac * I);
           }
-          red[u] = hsum2(fac * I);
+          fence_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            const int nrows = min(max(nvalid - h * OBR, 0), OBR);
+            if (nrows > 0)
+              bulk_store(scratch + ((size_t)k * U + h * OBR) * 512, ob_a + slot * (OBR * 512), (uint32_t)nrows * 512u, pol_buf);
+            bulk_commit();
+          }
+          __syncwarp();
         }
-        fence_async_smem();
-        __syncwarp();
-        if (elect_one()) {
-          bulk_store(scratch + (size_t)k * (U * 512), ob_a + (k & 1) * (U * 512), (uint32_t)nvalid * 512u, pol_buf);
-          bulk_commit();
-        }
-        __syncwarp();
 #pragma unroll
         for (int u = 0; u < U; ++u) pend[u] = red[u];
         pend_k = k;
@@ -999,9 +1008,9 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
     tm_bl = tm_tau; tm_bv = tm_tau;
     stage = (size_t)3 * U * 256;
   }
-  const size_t smem = std::max<size_t>((size_t)S * stage + 2 * U * 512, (size_t)S * U * 512) + 4 * (size_t)(L + 1) * 4 + 2 * S * 8;
+  const size_t smem = std::max<size_t>((size_t)S * stage + 2 * v5::LW_OBR * 512, (size_t)S * U * 512) + 4 * (size_t)(L + 1) * 4 + 2 * S * 8;
   const size_t per_cta = (size_t)L * 512;
-#define LW5(F, T, D, C) launch_clustered(ctx, v5::lw_solver_v5<F, T, D, C>, csize, smem, per_cta, 96, 1, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv)
+#define LW5(F, T, D, C) launch_clustered(ctx, v5::lw_solver_v5<F, T, D, C>, csize, smem, per_cta, 160, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv)
 #define LW5C(F, T, D) (compact ? LW5(F, T, D, true) : LW5(F, T, D, false))
   if (fast) {
     if (top) return LW5C(true, true, true);
