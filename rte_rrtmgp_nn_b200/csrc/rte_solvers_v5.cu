@@ -39,6 +39,9 @@ namespace v5 {
 #ifndef RRNN_V5_DISCARD
 #define RRNN_V5_DISCARD 1
 #endif
+#ifndef RRNN_V5_SW_NOB
+#define RRNN_V5_SW_NOB 2
+#endif
 #ifndef RRNN_V5_SW_U
 #define RRNN_V5_SW_U 8
 #endif
@@ -47,7 +50,7 @@ namespace v5 {
 #endif
 constexpr int MAX_WARPS = 4;  // solvers (warps) per CTA
 constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
-constexpr int SW_OBR = (SW_U > 4) ? SW_U / 2 : SW_U;
+constexpr int SW_OBR = (SW_U > 4) ? SW_U / RRNN_V5_SW_NOB : SW_U;
 constexpr int LW_OBR = (LW_U > 4) ? LW_U / 2 : LW_U;  // layers per store-staging tile of the SW solver
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -228,6 +231,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
     float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
     float* fdn = fup + (L + 1);
     for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
+    // the previous column's discards (generic proxy) are ordered before this column's bulk stores (async proxy) to the same lines
+    if (RRNN_V5_DISCARD) asm volatile("fence.proxy.async.global;" ::: "memory");
     const size_t gc_off = (size_t)col * G + gs;
     const f2 emis = ldg2(p.sfc_emis + gc_off);
     const f2 ssrc = ldg2(p.sfc_source + gc_off);
@@ -672,6 +677,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
     float* fdn = fup + (L + 1);
     float* fdr = fdn + (L + 1);
     for (int i = lane; i < 3 * (L + 1); i += 32) fup[i] = 0.0f;
+    // the previous column's discards (generic proxy) are ordered before this column's bulk stores (async proxy) to the same lines
+    if (RRNN_V5_DISCARD) asm volatile("fence.proxy.async.global;" ::: "memory");
     const size_t gc_off = (size_t)col * G + gs;
     const float mu0 = __ldg(p.mu0 + col);
     const float mu0_inv = 1.0f / mu0;
