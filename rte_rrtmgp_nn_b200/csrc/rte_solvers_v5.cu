@@ -937,8 +937,8 @@ static int resident_clusters5(const rrnn_ctx_t* ctx, int occ_clusters, int csize
 
 // One warp is one solver (a 64-g-point chunk of one column); a CTA carries `solver_warps` of them on adjacent columns
 // because a cluster launch keeps at most 8 CTAs per SM resident (cudaOccupancyMaxActiveClusters: 284 clusters of 4 on
-// 148 SMs whatever the shared memory).  Measured at 137 layers: the SW sweeps gain 12-15 % from 13 warps per SM
-// (2 per CTA, scratch beyond L2 notwithstanding); the LW sweeps are DRAM-limited by then and stay at 1 per CTA.
+// 148 SMs whatever the shared memory).  Measured at 137 layers: both sweeps keep gaining from resident warps up to the
+// 11.5 per SM that their shared memory allows (2 per CTA, 6 CTAs), now that consumed scratch is discarded from the L2.
 template <typename K, typename P, typename... Maps>
 static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_smem, size_t warp_scratch, int default_mb, int default_warps, int ncol, P& pp,
                             float** scratch_slot, const Maps&... maps) {
