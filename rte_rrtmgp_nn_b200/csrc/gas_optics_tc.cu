@@ -652,9 +652,33 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     // [rows][ngpt] whose rows are contiguous across columns, so a tile is one box starting at row `dest`; `slot_row` is
     // this thread's row inside the staged tile (-1: this row is not part of the array) -- see the LW row numbering.
     auto stage_and_store = [&](const CUtensorMap* tm, const float (&o)[32], int g0, int slot_row, unsigned dest, unsigned nrows_arr) {
-      if (lane == 0) {  // the staging tile about to be overwritten has been read by its TMA store
-        if (p.nstage == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+      if (p.nstage == 1) {
+        // Shared memory holds ONE 4 KB staging tile per warp (the g256 LW networks): it is used as two half tiles of
+        // 32 rows x 16 g-points (64-byte rows, 64-byte swizzle; the tensor maps are encoded to match), so that a half is
+        // refilled while the TMA store of the other is still reading -- no blocking wait, twice the stores.
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (lane == 0) bulk_wait_read<1>();  // the store issued two halves ago has read this half
+          __syncwarp();
+          if (slot_row >= 0) {
+            uint8_t* row = stage + sbuf * (STAGE_BYTES / 2) + slot_row * 64;
+            const uint32_t swz = (uint32_t)((slot_row >> 1) & 3);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              *reinterpret_cast<float4*>(row + (((uint32_t)j4 ^ swz) << 4)) =
+                  make_float4(o[16 * hf + 4 * j4], o[16 * hf + 4 * j4 + 1], o[16 * hf + 4 * j4 + 2], o[16 * hf + 4 * j4 + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (dest < nrows_arr && !(p.dbg_flags & 2)) tma_store_2d(tm, stage_a + sbuf * (STAGE_BYTES / 2), g0 + 16 * hf, (int)dest);
+            bulk_commit();
+          }
+          sbuf ^= 1;
+        }
+        return;
       }
+      if (lane == 0) bulk_wait_read<1>();  // the staging tile about to be overwritten has been read by its TMA store
       __syncwarp();
       if (slot_row >= 0) {
         uint8_t* row = stage + sbuf * STAGE_BYTES + slot_row * 128;
@@ -670,7 +694,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         if (dest < nrows_arr && !(p.dbg_flags & 2)) tma_store_2d(tm, stage_a + sbuf * STAGE_BYTES, g0, (int)dest);
         bulk_commit();
       }
-      sbuf = (p.nstage == 2) ? (sbuf ^ 1) : 0;
+      sbuf ^= 1;
     };
 
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -905,16 +929,17 @@ static EncodeTiledFn encode_fn() {
   fn = reinterpret_cast<EncodeTiledFn>(f);
   return fn;
 }
-// [rows][ngpt] fp32 tensor, box 32 g-points x box_rows rows, 128-byte swizzle
-static int make_map(CUtensorMap* tm, float* base, int G, unsigned long long rows, int box_rows) {
+// [rows][ngpt] fp32 tensor, box 32 g-points x box_rows rows, 128-byte swizzle (half = true: 16 g-points, 64-byte swizzle)
+static int make_map(CUtensorMap* tm, float* base, int G, unsigned long long rows, int box_rows, bool half = false) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail("gas_optics (tensor cores): cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)G * 4};
-  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {half ? 16u : 32u, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("gas_optics (tensor cores): cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return 0;
 }
@@ -1130,13 +1155,14 @@ int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const 
   p.planck_lay = planck_lay; p.planck_lev = planck_lev;
   CUtensorMap tm0, tm1, tm2, tm0s, tm1s;
   const unsigned long long nrows_lay = (unsigned long long)ncol * nlay;
-  if (int rc = tc::make_map(&tm0, out0, kd->ngpt, nrows_lay, 32)) return rc;
-  if (int rc = tc::make_map(&tm1, out1, kd->ngpt, nrows_lay, 32)) return rc;
+  const bool half = p.nstage == 1;  // one staging tile per warp: stored as two half tiles (see stage_and_store)
+  if (int rc = tc::make_map(&tm0, out0, kd->ngpt, nrows_lay, 32, half)) return rc;
+  if (int rc = tc::make_map(&tm1, out1, kd->ngpt, nrows_lay, 32, half)) return rc;
   if (mode == 0) {
     if (compact) tm2 = tm1;
-    else if (int rc = tc::make_map(&tm2, out2, kd->ngpt, (unsigned long long)ncol * (nlay + 1), 32)) return rc;
-    if (int rc = tc::make_map(&tm0s, out0, kd->ngpt, nrows_lay, 31)) return rc;
-    if (int rc = tc::make_map(&tm1s, out1, kd->ngpt, nrows_lay, 31)) return rc;
+    else if (int rc = tc::make_map(&tm2, out2, kd->ngpt, (unsigned long long)ncol * (nlay + 1), 32, half)) return rc;
+    if (int rc = tc::make_map(&tm0s, out0, kd->ngpt, nrows_lay, 31, half)) return rc;
+    if (int rc = tc::make_map(&tm1s, out1, kd->ngpt, nrows_lay, 31, half)) return rc;
   } else {
     tm2 = tm1; tm0s = tm0; tm1s = tm1;
   }
