@@ -39,7 +39,10 @@ constexpr int TM = 128;          // rows per tile (TMEM lanes)
 constexpr int THREADS = 416;     // 4 front warps + 2 x 4 epilogue warps + 1 MMA warp
 constexpr int MMA_WARP = 12;
 constexpr int KIN_MAX = 32;      // padded number of network inputs
-constexpr int NSLOT = 6;         // ring of output accumulators: 6 x 64 TMEM columns (32 of net 0 | 32 of net 1)
+constexpr int NSLOT = 6;         // ring of output accumulators: 6 jobs of 32 g-points x 2 networks = 384 TMEM columns, laid out as
+                                 // 3 pairs of 128 columns [net 0: 64 | net 1: 64] so that ONE N = 64 MMA per network and k-step
+                                 // feeds two jobs (an SS-mode MMA re-reads its 4 KB A operand from shared memory whatever N is:
+                                 // measured ~60 cycles per N = 32 MMA against a 16-cycle tensor floor)
 constexpr int RING_COL0 = 128;   // TMEM columns 0..63 / 64..127: hidden accumulators of net 0 / 1
 constexpr int STAGE_BYTES = 4096;  // one staged output tile: 32 rows x 32 g-points
 constexpr float OUT_SCALE = 1024.0f;            // folded into the last layer of the tau-type networks
@@ -202,6 +205,21 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
       "tcgen05.wait::ld.sync.aligned;"
       : RRNN_R8(r, 0), RRNN_R8(r, 8), RRNN_R8(r, 16), RRNN_R8(r, 24), RRNN_R8(r, 32), RRNN_R8(r, 40), RRNN_R8(r, 48), RRNN_R8(r, 56)
       : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+// two runs of 32 columns of this thread's lane (net 0 -> v[0..31], net 1 -> v[32..63]), one wait for both
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr0, uint32_t taddr1, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : RRNN_R8(r, 0), RRNN_R8(r, 8), RRNN_R8(r, 16), RRNN_R8(r, 24), RRNN_R8(r, 32), RRNN_R8(r, 40), RRNN_R8(r, 48), RRNN_R8(r, 56)
+      : "r"(taddr0), "r"(taddr1)
       : "memory");
 #pragma unroll
   for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
@@ -572,7 +590,8 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         idesc_h[n] = make_idesc(TM, nt.H);
       }
       const uint32_t wstep3 = 2u * (uint32_t)p.ngpt;
-      const uint32_t idesc_o = make_idesc(TM, 32);
+      const uint32_t idesc_o = make_idesc(TM, 32), idesc_o2 = make_idesc(TM, 64);
+      const int nch_pad = (p.nchunks + 1) & ~1;
       int mit = 0;
       for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++mit) {
         if (lane == 0) dbg_ts(p.dbg, mit, 20);
@@ -604,17 +623,26 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         for (int n = 0; n < 2; ++n) { mbar_wait(BAR(BAR_ACT + n), ph_act[n]); ph_act[n] ^= 1u; }
         fence_after();
         if (lane == 0) dbg_ts(p.dbg, mit, 27);
-        for (int c = 0; c < p.nchunks; ++c, ++jc) {
-          const unsigned slot = jc % NSLOT, round = jc / NSLOT;
-          if (round > 0) { mbar_wait(BAR(BAR_SLOT_EMPTY + slot), (round - 1u) & 1u); fence_after(); }
+        // two jobs (64 g-points) per set of MMAs; an odd last job (ngpt = 224) is padded with an empty one so that job
+        // pairs and slot pairs stay aligned across tiles
+        for (int c = 0; c < nch_pad; c += 2, jc += 2) {
+          const unsigned slot = jc % NSLOT, round = jc / NSLOT;  // slot is even: the pair (slot, slot + 1)
+          if (round > 0) {
+            mbar_wait(BAR(BAR_SLOT_EMPTY + slot), (round - 1u) & 1u);
+            mbar_wait(BAR(BAR_SLOT_EMPTY + slot + 1), (round - 1u) & 1u);
+            fence_after();
+          }
           if (elect_one()) {
+            const bool both = c + 1 < p.nchunks;
 #pragma unroll
             for (int n = 0; n < 2; ++n) {
-              // rows [32c, 32c+32) of W3: 8-row groups are 128 B apart -> 512 B = 32 descriptor units per chunk
+              // rows [32c, 32c+64) of W3: 8-row groups are 128 B apart -> 512 B = 32 descriptor units per 32 rows
               const OperandDesc w3 = {d_w[n][2].hi + (uint64_t)(32u * c), d_w[n][2].lo + (uint64_t)(32u * c)};
-              issue_gemm(tmem_base + RING_COL0 + 64u * slot + 32u * n, d_act[n], w3, wstep3, p.net[n].K3 >> 4, idesc_o);
+              issue_gemm(tmem_base + RING_COL0 + 128u * (slot >> 1) + 64u * n, d_act[n], w3, wstep3, p.net[n].K3 >> 4,
+                         both ? idesc_o2 : idesc_o);
             }
             mma_commit(BAR(BAR_SLOT_FULL + slot));
+            mma_commit(BAR(BAR_SLOT_FULL + slot + 1));
           }
           __syncwarp();
           if (lane == 0) dbg_ts(p.dbg, mit, 28 + c);
@@ -645,6 +673,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     if (MODE == 0) sfc_lev = (__ldg(p.play) > __ldg(p.play + L - 1)) ? 0 : L;
     int it = 0;
     unsigned jc = 0;
+    const int nch_pad = (p.nchunks + 1) & ~1;  // jobs per tile incl. the padding job of an odd count (see the MMA warp)
     int sbuf = 0;
     const unsigned nrows_lay = (unsigned)p.ncol * (unsigned)L;  // rows of tau / lay_source / ssa
 
@@ -725,13 +754,18 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
       const float *tp_l = tp_s, *tp_v = tp_s;   // &totplnk[0][idx-1] for T_lay and T_lev of this row
       PlanckPos ps0{1, 0.0f}, ps1{1, 0.0f};      // T_sfc, T_sfc + 1 (surface row only)
       bool have_rec = false;
-      for (int c = 0; c < p.nchunks; ++c, ++jc) {
+      for (int c = 0; c < nch_pad; ++c, ++jc) {
         if ((int)(jc & 1u) != eg) continue;
         const unsigned slot = jc % NSLOT, round = jc / NSLOT;
         const int g0 = 32 * c;
         if (tid == 128) dbg_ts(p.dbg, it, 40 + 2 * c);
         mbar_wait(BAR(BAR_SLOT_FULL + slot), round & 1u);
         fence_after();
+        if (c >= p.nchunks) {  // the padding job of an odd job count: keep the slot protocol going, nothing to do
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(BAR_SLOT_EMPTY + slot));
+          continue;
+        }
         if (tid == 128) dbg_ts(p.dbg, it, 41 + 2 * c);
         if (!have_rec) {
           // the record of this tile was written by the front warps before the MMAs this barrier tracks were issued
@@ -749,7 +783,10 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         if (tid == 128) dbg_mark(p.dbg, 2, (jc << 8) | 1);
         float z[64];
-        tmem_ld64(tmem_row + RING_COL0 + 64u * slot, z);
+        {
+          const uint32_t pair_col = tmem_row + RING_COL0 + 128u * (slot >> 1) + 32u * (slot & 1u);
+          tmem_ld32x2(pair_col, pair_col + 64u, z);
+        }
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(BAR_SLOT_EMPTY + slot));
@@ -1060,7 +1097,7 @@ static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn
     // has been issued, i.e. when the epilogue (either group) is at most NSLOT jobs short of the end of tile t, which is
     // at most ceil(NSLOT/nchunks) tiles back.
     const int nchunks = G / 32;
-    p.nrec = (tc::NSLOT + nchunks - 1) / nchunks + 2;
+    p.nrec = (tc::NSLOT + nchunks - 1) / nchunks + 2;  // (the padded job count of the kernel is >= nchunks: this stays an upper bound)
     p.off_rec = off; off += (uint32_t)p.nrec * 8 * tc::TM * 4;
     p.off_bar = off; off += tc::NBAR * 8 + 16;
     c.smem = (size_t)off + 1024;  // alignment slack
