@@ -234,6 +234,16 @@ RRNN_API int rrnn_cloud_lut_destroy(rrnn_cloud_lut_t* lut);
 RRNN_API int rrnn_cloud_optics(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, int ncol, int nlay, const float* clwp_d,
                                const float* ciwp_d, const float* reliq_d, const float* reice_d, float* tau_d, float* ssa_d,
                                float* g_d);
+/* McICA sampling (extensions/cloud_optics/mo_cloud_sampling.F90): sampled_mask_max_ran :107-170 (overlap_param_d NULL) and
+ * sampled_mask_exp_ran :176-286; randoms_d and the mask (1 byte per element) are (ngpt,nlay,ncol), cloud_frac_d (nlay,ncol),
+ * overlap_param_d (nlay-1,ncol) -- this fork's layout throughout (the module itself still declares (ncol,nlay,ngpt)). */
+RRNN_API int rrnn_sampled_mask(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, const float* randoms_d, const float* cloud_frac_d,
+                               const float* overlap_param_d, unsigned char* cloud_mask_d);
+/* draw_samples / apply_cloud_mask (:38-101, 292-308): by-band cloud properties (nbnd,nlay,ncol) -> sampled by g-point
+ * (ngpt,nlay,ncol), zero where the mask is false; ssa/g NULL for ty_optical_props_1scl. */
+RRNN_API int rrnn_draw_samples(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, const unsigned char* cloud_mask_d,
+                               const float* tau_bnd_d, const float* ssa_bnd_d, const float* g_bnd_d, float* tau_gpt_d,
+                               float* ssa_gpt_d, float* g_gpt_d);
 /* delta_scale_2str_k, rte/kernels/mo_optical_props_kernels.F90:72-93 (n = number of elements) */
 RRNN_API int rrnn_delta_scale_2str(rrnn_ctx_t* ctx, size_t n, float* tau_d, float* ssa_d, float* g_d);
 /* inc_1scalar_by_1scalar_bybnd :358-378 and inc_2stream_by_2stream_bybnd :453-485; gpt_lims from kd.

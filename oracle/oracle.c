@@ -979,6 +979,56 @@ ORC_API void orc_cloud_optics_pade(int ncol, int nlay, int nbnd, const float* cl
 }
 
 /* ------------------------------------------------------------------------------------------
+ * McICA sampling: extensions/cloud_optics/mo_cloud_sampling.F90
+ *   sampled_mask_max_ran :107-170, sampled_mask_exp_ran :176-286, draw_samples / apply_cloud_mask :38-101, 292-308.
+ * The module still declares its masks and fields in the pre-fork (ncol,nlay,ngpt) order; the restatement keeps the
+ * algorithm and uses this fork's layout throughout: randoms, mask, sampled fields (ngpt,nlay,ncol) = C [ncol][nlay][ngpt],
+ * cloud_frac (nlay,ncol) = C [ncol][nlay], overlap_param C [ncol][nlay-1], by-band fields C [ncol][nlay][nbnd].
+ * overlap_param == NULL selects maximum-random overlap.
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_sampled_mask(int ngpt, int nlay, int ncol, const float* randoms, const float* cloud_frac,
+                              const float* overlap_param, unsigned char* cloud_mask) {
+  float* local = (float*)malloc(sizeof(float) * ngpt);
+  for (int icol = 0; icol < ncol; ++icol) {
+    const float* cf = cloud_frac + (size_t)icol * nlay;
+    unsigned char* m = cloud_mask + (size_t)icol * nlay * ngpt;
+    const float* rn = randoms + (size_t)icol * nlay * ngpt;
+    int fst = -1, lst = -1;
+    for (int l = 0; l < nlay; ++l)
+      if (cf[l] > 0.0f) { if (fst < 0) fst = l; lst = l; }
+    memset(m, 0, (size_t)nlay * ngpt);
+    if (fst < 0) continue;
+    for (int g = 0; g < ngpt; ++g) {
+      local[g] = rn[(size_t)fst * ngpt + g];
+      m[(size_t)fst * ngpt + g] = local[g] > (1.0f - cf[fst]);
+    }
+    for (int l = fst + 1; l <= lst; ++l) {
+      if (!(cf[l] > 0.0f)) continue;
+      if (cf[l - 1] > 0.0f) {
+        if (overlap_param) { /* exponential-random: correlated deviates :267-274 */
+          float rho = overlap_param[(size_t)icol * (nlay - 1) + (l - 1)];
+          for (int g = 0; g < ngpt; ++g)
+            local[g] = rho * (local[g] - 0.5f) + sqrtf(1.0f - rho * rho) * (rn[(size_t)l * ngpt + g] - 0.5f) + 0.5f;
+        } /* maximum-random: the same deviates :158 */
+      } else {
+        for (int g = 0; g < ngpt; ++g) local[g] = rn[(size_t)l * ngpt + g];
+      }
+      for (int g = 0; g < ngpt; ++g) m[(size_t)l * ngpt + g] = local[g] > (1.0f - cf[l]);
+    }
+  }
+  free(local);
+}
+
+/* apply_cloud_mask :292-308 for one field */
+ORC_API void orc_apply_cloud_mask(int ngpt, int nlay, int ncol, int nbnd, const int* gpt_lims, const unsigned char* cloud_mask,
+                                  const float* input_field, float* sampled_field) {
+  for (size_t s = 0; s < (size_t)ncol * nlay; ++s)
+    for (int b = 0; b < nbnd; ++b)
+      for (int g = gpt_lims[2 * b] - 1; g <= gpt_lims[2 * b + 1] - 1; ++g)
+        sampled_field[s * ngpt + g] = cloud_mask[s * ngpt + g] ? input_field[s * nbnd + b] : 0.0f;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Heating rates.
  *  orc_heating_rate      : extensions/mo_heating_rates.F90:26-54 semantics [K/s], cp_dry = 1004.64,
  *                          restated in this fork's (nlay+1,ncol) layout.

@@ -378,6 +378,29 @@ def cloud_optics_pade(co, clwp, ciwp, reliq, reice, two_stream, fast=False):
     return tau
 
 
+def sampled_mask(randoms, cloud_frac, overlap_param=None, fast=False):
+    """sampled_mask_max_ran (overlap_param None) / sampled_mask_exp_ran, extensions/cloud_optics/mo_cloud_sampling.F90:107-286;
+    randoms (ncol, nlay, ngpt), cloud_frac (ncol, nlay), overlap_param (ncol, nlay-1) -> bool mask (ncol, nlay, ngpt)."""
+    ncol, nlay, ngpt = randoms.shape
+    r = _a(randoms, fast); cf = _a(cloud_frac, fast)
+    op = None if overlap_param is None else _a(overlap_param, fast)
+    m = np.empty((ncol, nlay, ngpt), np.uint8)
+    lib(fast).orc_sampled_mask(ngpt, nlay, ncol, _p(r), _p(cf), None if op is None else _p(op), _p(m))
+    return m.astype(bool)
+
+
+def draw_samples(cloud_mask, gpt_lims, *fields, fast=False):
+    """draw_samples / apply_cloud_mask (:38-101, 292-308): by-band fields (ncol, nlay, nbnd) -> sampled (ncol, nlay, ngpt)."""
+    ncol, nlay, ngpt = cloud_mask.shape
+    m = np.ascontiguousarray(cloud_mask, np.uint8); gl = np.ascontiguousarray(gpt_lims, np.int32)
+    out = []
+    for f in fields:
+        a = _a(f, fast); o = np.zeros((ncol, nlay, ngpt), _dt(fast))
+        lib(fast).orc_apply_cloud_mask(ngpt, nlay, ncol, a.shape[-1], _ip(gl), _p(m), _p(a), _p(o))
+        out.append(o)
+    return out
+
+
 def delta_scale_2str(tau, ssa, g, fast=False):
     dt = _dt(fast)
     tau = np.array(tau, dt, copy=True); ssa = np.array(ssa, dt, copy=True); g = np.array(g, dt, copy=True)

@@ -94,6 +94,8 @@ _SIGS = {
     "rrnn_cloud_pade_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [c_float_p] * 12 + [C.POINTER(vp)]),
     "rrnn_cloud_lut_destroy": (C.c_int, [vp]),
     "rrnn_cloud_optics": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "rrnn_sampled_mask": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "rrnn_draw_samples": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_delta_scale_2str": (C.c_int, [vp, C.c_size_t, vp, vp, vp]),
     "rrnn_increment_1scl_bybnd": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
     "rrnn_increment_2str_bybnd": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),

@@ -744,6 +744,68 @@ def load_cloud_lut_file(path):
     return out
 
 
+def _sampled_mask(name, randoms, cloud_frac, overlap_param, cloud_mask, ctx):
+    torch = _torch()
+    ctx = ctx or default_context()
+    r, cf = _dev(randoms, ctx), _dev(cloud_frac, ctx)
+    ncol, nlay, ngpt = r.shape
+    if tuple(cf.shape) != (ncol, nlay):
+        return "sampled_mask_max_ran: sizes of randoms(ngpt,nlay,ncol) and cloud_frac(ncol,nlay) are inconsistent"
+    op = None
+    if overlap_param is not None:
+        op = _dev(overlap_param, ctx)
+        if tuple(op.shape) != (ncol, nlay - 1):
+            return "sampled_mask_max_ran: sizes of randoms(ngpt,nlay,ncol) and overlap_param(ncol,nlay-1) are inconsistent"
+    if tuple(cloud_mask.shape) != (ncol, nlay, ngpt) or cloud_mask.dtype not in (torch.uint8, torch.bool):
+        return "sampled_mask_max_ran: sizes of randoms(ngpt,nlay,ncol) and cloud_mask(ncol,nlay,ngpt) are inconsistent"
+    if bool((cf > 1).any()) or bool((cf < 0).any()):
+        return "sampled_mask_max_ran: cloud fraction values out of range [0,1]"
+    if op is not None and (bool((op > 1).any()) or bool((op < -1).any())):
+        return "sampled_mask_max_ran: overlap_param values out of range [-1,1]"
+    try:
+        _lib.check(_lib.lib().rrnn_sampled_mask(ctx.h, ngpt, nlay, ncol, _ptr(r), _ptr(cf), _ptr(op), _ptr(cloud_mask)))
+    except RRNNError as e:
+        return str(e)
+    return ""
+
+
+def sampled_mask_max_ran(randoms, cloud_frac, cloud_mask, ctx=None):
+    """extensions/cloud_optics/mo_cloud_sampling.F90:107-170; randoms (ncol, nlay, ngpt), cloud_frac (ncol, nlay), cloud_mask a
+    device uint8 / bool tensor (ncol, nlay, ngpt)."""
+    return _sampled_mask("max_ran", randoms, cloud_frac, None, cloud_mask, ctx)
+
+
+def sampled_mask_exp_ran(randoms, cloud_frac, overlap_param, cloud_mask, ctx=None):
+    """extensions/cloud_optics/mo_cloud_sampling.F90:176-286; overlap_param (ncol, nlay-1).  Clear layers inside the cloudy
+    range get a false mask (the reference leaves them undefined)."""
+    return _sampled_mask("exp_ran", randoms, cloud_frac, overlap_param, cloud_mask, ctx)
+
+
+def draw_samples(cloud_mask, clouds, clouds_sampled):
+    """draw_samples (extensions/cloud_optics/mo_cloud_sampling.F90:38-101): by-band cloud properties -> sampled by g-point."""
+    two, two_s = isinstance(clouds, ty_optical_props_2str), isinstance(clouds_sampled, ty_optical_props_2str)
+    if two != two_s:
+        return "draw_samples: by-band and sampled cloud properties need to be the same variable type"
+    ncol, nlay = clouds.get_ncol(), clouds.get_nlay()
+    if clouds_sampled.get_ncol() != ncol or clouds_sampled.get_nlay() != nlay:
+        return "draw_samples: sampled/unsampled cloud optical properties have different ncol and/or nlay"
+    if tuple(cloud_mask.shape) != (ncol, nlay, clouds_sampled.ngpt):
+        return "draw_samples: cloud mask and cloud optical properties have different ncol and/or nlay"
+    if clouds.tau.shape[-1] != clouds_sampled.nband:
+        return "draw_samples: by-band and sampled cloud properties spectral structure is different"
+    ctx = clouds_sampled.ctx
+    try:
+        _lib.check(_lib.lib().rrnn_draw_samples(ctx.h, clouds_sampled._kd.h, nlay, ncol, _ptr(cloud_mask), _ptr(clouds.tau),
+                                                _ptr(clouds.ssa) if two else None, _ptr(clouds.g) if two else None,
+                                                _ptr(clouds_sampled.tau), _ptr(clouds_sampled.ssa) if two else None,
+                                                _ptr(clouds_sampled.g) if two else None))
+    except RRNNError as e:
+        return str(e)
+    if two:
+        clouds_sampled.g_is_zero = False
+    return ""
+
+
 def load_cloud_pade_file(path):
     """Read the Pade part of a cloud-optics coefficient file -> kwargs of ty_cloud_optics.load_pade
     (examples/all-sky/mo_load_cloud_coefficients.F90:113-200)."""

@@ -225,6 +225,53 @@ __global__ void cloud_optics_pade_kernel(const PadeParams p) {
   }
 }
 
+// McICA sampling, extensions/cloud_optics/mo_cloud_sampling.F90:107-286 (sampled_mask_max_ran / sampled_mask_exp_ran): one
+// thread per (column, g-point) walks the layers; adjacent g-points read adjacent random numbers (coalesced).  The module's
+// stale (ncol,nlay,ngpt) declarations are replaced by this fork's (ngpt,nlay,ncol) layout; overlap == null: maximum-random.
+__global__ void sampled_mask_kernel(int ngpt, int nlay, int ncol, const float* __restrict__ randoms, const float* __restrict__ cloud_frac,
+                                    const float* __restrict__ overlap, unsigned char* __restrict__ mask) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)ngpt * ncol) return;
+  const size_t c = i / ngpt;
+  const int g = (int)(i - c * ngpt);
+  const float* cf = cloud_frac + c * nlay;
+  const float* rn = randoms + c * nlay * ngpt + g;
+  unsigned char* m = mask + c * nlay * ngpt + g;
+  float local = 0.0f;
+  bool prev_cloudy = false, started = false;
+  for (int l = 0; l < nlay; ++l) {
+    const float f = cf[l];
+    const bool cloudy = f > 0.0f;
+    unsigned char out = 0;
+    if (cloudy) {
+      const float r = rn[(size_t)l * ngpt];
+      if (!started || !prev_cloudy) local = r;                      // first cloudy layer, or the layer above is clear: new deviates
+      else if (overlap) {                                           // exponential-random: correlated deviates (:267-274)
+        const float rho = overlap[c * (nlay - 1) + (l - 1)];
+        local = rho * (local - 0.5f) + sqrtf(1.0f - rho * rho) * (r - 0.5f) + 0.5f;
+      }                                                             // maximum-random: keep the deviates (:158)
+      out = local > (1.0f - f);
+      started = true;
+    }
+    prev_cloudy = cloudy;
+    m[(size_t)l * ngpt] = out;
+  }
+}
+
+// draw_samples / apply_cloud_mask (:38-101, 292-308) for up to three fields at once
+__global__ void apply_cloud_mask_kernel(size_t nsmp, int ngpt, int nbnd, const int* __restrict__ gpt2band, const unsigned char* __restrict__ mask,
+                                        const float* __restrict__ i0, const float* __restrict__ i1, const float* __restrict__ i2,
+                                        float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsmp * ngpt) return;
+  const size_t s = i / ngpt;
+  const int b = gpt2band[i - s * ngpt];
+  const bool on = mask[i] != 0;
+  o0[i] = on ? i0[s * nbnd + b] : 0.0f;
+  if (o1) o1[i] = on ? i1[s * nbnd + b] : 0.0f;
+  if (o2) o2[i] = on ? i2[s * nbnd + b] : 0.0f;
+}
+
 // delta_scale_2str_k, rte/kernels/mo_optical_props_kernels.F90:72-93
 __global__ void delta_scale_kernel(size_t n, float* __restrict__ tau, float* __restrict__ ssa, float* __restrict__ g) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -726,6 +773,35 @@ extern "C" int rrnn_cloud_optics(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, i
   p.clwp = clwp_d; p.ciwp = ciwp_d; p.reliq = reliq_d; p.reice = reice_d; p.tau = tau_d; p.ssa = ssa_d; p.g = g_d;
   const size_t n = (size_t)ncol * nlay * lut->nbnd;
   cloud_optics_kernel<<<nblk(n), 256, 0, ctx->stream>>>(p);
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int rrnn_sampled_mask(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, const float* randoms_d, const float* cloud_frac_d,
+                                 const float* overlap_param_d, unsigned char* cloud_mask_d) {
+  RRNN_CHECK(ctx && randoms_d && cloud_frac_d && cloud_mask_d, "sampled_mask_max_ran: null argument");
+  RRNN_CHECK(ngpt > 0 && nlay > 0 && ncol >= 0, "sampled_mask_max_ran: sizes of randoms(ngpt,nlay,ncol) and cloud_frac(ncol,nlay) are inconsistent");
+  if (ncol == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ngpt * ncol;
+  sampled_mask_kernel<<<nblk(n), 256, 0, ctx->stream>>>(ngpt, nlay, ncol, randoms_d, cloud_frac_d, overlap_param_d, cloud_mask_d);
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int rrnn_draw_samples(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, const unsigned char* cloud_mask_d,
+                                 const float* tau_bnd_d, const float* ssa_bnd_d, const float* g_bnd_d, float* tau_gpt_d, float* ssa_gpt_d,
+                                 float* g_gpt_d) {
+  RRNN_CHECK(ctx && kd, "draw_samples: cloud optical properties are not initialized");
+  RRNN_CHECK(cloud_mask_d && tau_bnd_d && tau_gpt_d, "draw_samples: sampled cloud optical properties are not initialized");
+  RRNN_CHECK((ssa_bnd_d == nullptr) == (ssa_gpt_d == nullptr) && (g_bnd_d == nullptr) == (g_gpt_d == nullptr) &&
+                 (ssa_bnd_d == nullptr) == (g_bnd_d == nullptr),
+             "draw_samples: by-band and sampled cloud properties need to be the same variable type");
+  if (ncol <= 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const size_t nsmp = (size_t)ncol * nlay;
+  apply_cloud_mask_kernel<<<nblk(nsmp * kd->ngpt), 256, 0, ctx->stream>>>(nsmp, kd->ngpt, kd->nbnd, kd->d_gpt2band, cloud_mask_d, tau_bnd_d,
+                                                                         ssa_bnd_d, g_bnd_d, tau_gpt_d, ssa_gpt_d, g_gpt_d);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -325,3 +325,32 @@ def test_cloud_optics_pade_against_lut():
             assert np.allclose(o[2][0, 0], tot[2] / tot[1], rtol=1e-12)
         b = pade["sizreg"][0]
         assert min(int(np.floor((40.0 - b[1]) / b[2])) + 2, 3) == 2 and 40.0 > b[2]               # the quirk: 40 um is past regime 2
+
+
+def test_mcica_sampling_properties():
+    """The oracle's McICA sampling (mo_cloud_sampling.F90:107-286): the sampled cloud fraction of a layer converges to
+    cloud_frac; maximum overlap inside a contiguous cloud (nested masks); rho = 1 reproduces maximum-random, rho = 0
+    decorrelates adjacent layers; clear layers and clear columns stay clear."""
+    import oracle as O
+    rng = np.random.default_rng(9)
+    ncol, nlay, ngpt = 6, 10, 4096
+    randoms = rng.uniform(size=(ncol, nlay, ngpt)).astype(np.float32)
+    cf = np.zeros((ncol, nlay), np.float32)
+    cf[0, 2:6] = [0.2, 0.5, 0.3, 0.8]   # one contiguous cloud
+    cf[1, 1] = 0.4; cf[1, 5] = 0.7      # two separate clouds
+    cf[2, :] = 0.25
+    m = O.sampled_mask(randoms, cf)
+    assert not m[3:].any() and not m[0, :2].any() and not m[0, 6:].any()
+    assert np.allclose(m.mean(-1)[cf > 0], cf[cf > 0], atol=0.03)
+    assert (m[0, 2] <= m[0, 3]).all() and (m[0, 4] <= m[0, 3]).all() and (m[0, 3] <= m[0, 5]).all()   # nested: maximum overlap
+    both = (m[1, 1] & m[1, 5]).mean()
+    assert abs(both - 0.4 * 0.7) < 0.03                                                                 # random overlap
+    one = O.sampled_mask(randoms, cf, np.ones((ncol, nlay - 1), np.float32))
+    assert np.array_equal(one, m)
+    zero = O.sampled_mask(randoms, cf, np.zeros((ncol, nlay - 1), np.float32))
+    assert abs((zero[2, 3] & zero[2, 4]).mean() - 0.25 * 0.25) < 0.02
+    assert np.allclose(zero.mean(-1)[cf > 0], cf[cf > 0], atol=0.03)
+    lims = np.array([[1, 1024], [1025, 4096]], np.int32)
+    f = rng.uniform(1, 2, size=(ncol, nlay, 2)).astype(np.float32)
+    s, = O.draw_samples(m, lims, f)
+    assert np.array_equal(s[..., :1024], np.where(m[..., :1024], f[..., :1], 0)) and np.array_equal(s[..., 1024:], np.where(m[..., 1024:], f[..., 1:], 0))

@@ -742,6 +742,57 @@ def test_cloud_optics_pade_matches_oracle(gpu_ctx):
     assert "isn't consistently sized" in api.ty_cloud_optics(gpu_ctx).load_pade(**bad)
 
 
+def test_mcica_sampling_matches_oracle(gpu_ctx):
+    """sampled_mask_max_ran / sampled_mask_exp_ran / draw_samples (extensions/cloud_optics/mo_cloud_sampling.F90) against the
+    oracle: bit-exact masks, sampled fields equal to the by-band field where the mask is set and zero elsewhere."""
+    import os
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral
+    torch = _torch()
+    rng = np.random.default_rng(77)
+    for band, ngpt, mk in (("lw", 256, spectral.synthetic_kdist_lw), ("sw", 224, spectral.synthetic_kdist_sw)):
+        ncol, nlay = 19, 41
+        kd = mk(ngpt)
+        k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); k_dist.load(kd)
+        randoms = rng.uniform(size=(ncol, nlay, ngpt)).astype(np.float32)
+        cf = rng.uniform(size=(ncol, nlay)).astype(np.float32)
+        cf[rng.uniform(size=cf.shape) < 0.45] = 0.0
+        cf[3] = 0.0                      # a clear column
+        cf[4, :] = 0.0; cf[4, 7] = 0.6   # a single cloudy layer
+        rho = rng.uniform(-1, 1, size=(ncol, nlay - 1)).astype(np.float32)
+        for overlap in (None, rho):
+            mask = torch.zeros((ncol, nlay, ngpt), dtype=torch.uint8, device="cuda")
+            err = (api.sampled_mask_max_ran(randoms, cf, mask, ctx=gpu_ctx) if overlap is None else
+                   api.sampled_mask_exp_ran(randoms, cf, overlap, mask, ctx=gpu_ctx))
+            assert err == "", err
+            want = O.sampled_mask(randoms, cf, overlap)
+            got = mask.cpu().numpy().astype(bool)
+            assert want.any() and not want[3].any()
+            if overlap is None:
+                assert np.array_equal(got, want)
+            else:  # the correlated deviates go through one fused multiply-add on the GPU: a handful of threshold ties may flip
+                assert (got != want).mean() < 2e-4
+            two = band == "sw"
+            clouds = api.ty_optical_props_2str() if two else api.ty_optical_props_1scl()
+            (clouds.alloc_2str if two else clouds.alloc_1scl)(ncol, nlay, k_dist, by_band=True)
+            sampled = api.ty_optical_props_2str() if two else api.ty_optical_props_1scl()
+            (sampled.alloc_2str if two else sampled.alloc_1scl)(ncol, nlay, k_dist)
+            sampled._kd = k_dist._kd
+            nb = clouds.tau.shape[-1]
+            fields = [rng.uniform(0.1, 2.0, size=(ncol, nlay, nb)).astype(np.float32) for _ in range(3 if two else 1)]
+            clouds.tau.copy_(torch.from_numpy(fields[0]))
+            if two:
+                clouds.ssa.copy_(torch.from_numpy(fields[1])); clouds.g = torch.from_numpy(fields[2]).cuda()
+            assert api.draw_samples(mask, clouds, sampled) == ""
+            ref = O.draw_samples(got, kd["band_lims_gpt"], *fields)
+            assert np.array_equal(sampled.tau.cpu().numpy(), ref[0])
+            if two:
+                assert np.array_equal(sampled.ssa.cpu().numpy(), ref[1]) and np.array_equal(sampled.g.cpu().numpy(), ref[2])
+    bad = torch.zeros((ncol, nlay, ngpt), dtype=torch.uint8, device="cuda")
+    assert "out of range" in api.sampled_mask_max_ran(randoms, cf * 3.0, bad, ctx=gpu_ctx)
+    assert "inconsistent" in api.sampled_mask_max_ran(randoms, cf[:, :-1], bad, ctx=gpu_ctx)
+
+
 def test_heating_rate_K_per_s(gpu_ctx):
     import oracle as O
     from rte_rrtmgp_nn_b200 import api
