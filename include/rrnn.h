@@ -178,6 +178,18 @@ RRNN_API int rrnn_lw_solver_noscat_ext(rrnn_ctx_t* ctx, int ngpt, int nlay, int 
                                        const float* lev_source_d, const float* sfc_emis_gpt_d, const float* sfc_source_d,
                                        const float* sfc_source_Jac_d, float* flux_up_d, float* flux_dn_d,
                                        float* flux_up_Jac_d, float* gpt_flux_up_d, float* gpt_flux_dn_d);
+/* lw_solver_2stream (rte/kernels/mo_rte_solver_kernels.F90:426-486: lw_two_stream :1018-1069, lw_source_2str :1112-1162, adding
+ * :1526-1637): two-stream longwave with scattering; lay_source is not used by the reference and is not an argument here;
+ * gpt_flux_{up,dn}_d (ngpt,nlay+1,ncol) optional.  General kernel. */
+RRNN_API int rrnn_lw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux_d,
+                                    const float* tau_d, const float* ssa_d, const float* g_d, const float* lev_source_d,
+                                    const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d,
+                                    float* flux_dn_d, float* gpt_flux_up_d, float* gpt_flux_dn_d);
+/* rte_lw(..., use_2stream = .true.) for ty_optical_props_2str (rte/mo_rte_lw.F90:346-361); sfc_emis_d is (nbnd,ncol). */
+RRNN_API int rrnn_rte_lw_2stream(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1,
+                                 const float* inc_flux_d, const float* tau_d, const float* ssa_d, const float* g_d,
+                                 const float* lev_source_d, const float* sfc_source_d, const float* sfc_emis_d,
+                                 float* flux_up_d, float* flux_dn_d, float* gpt_flux_up_d, float* gpt_flux_dn_d);
 /* rte_lw with its optional arguments and for ty_optical_props_2str (re-scaled solution, rte/mo_rte_lw.F90:363-384):
  * ssa_d/g_d NULL = _1scl; lw_Ds_d (ngpt,ncol) only for _1scl and one angle (:239-249); sfc_emis_d is (nbnd,ncol). */
 RRNN_API int rrnn_rte_lw_ext(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,

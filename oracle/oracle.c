@@ -655,6 +655,113 @@ ORC_API void orc_lw_solver_noscat_GaussQuad_ext(int ngpt, int nlay, int ncol, in
 }
 
 /* ------------------------------------------------------------------------------------------
+ * lw_solver_2stream: rte/kernels/mo_rte_solver_kernels.F90:426-486 with lw_two_stream :1018-1069 (LW_diff_sec = 1.66,
+ * k_min), lw_source_2str :1112-1162 (lev_source used as it is; lay_source unused; tau <= 1e-8 -> no source),
+ * adding :1526-1637 with sfc_albedo = 1 - sfc_emis and source_sfc = pi * sfc_emis * sfc_source, plain sums over
+ * g-points (sum_broadband_nocol, mo_fluxes_broadband_kernels.F90:40-47).  gpt_up / gpt_dn (ngpt,nlay+1,ncol) optional.
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_lw_solver_2stream(int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux, const float* tau,
+                                   const float* ssa, const float* gasym, const float* lev_source, const float* sfc_emis,
+                                   const float* sfc_source, float* flux_up, float* flux_dn, float* gpt_up, float* gpt_dn) {
+  const float k_min = 1.e-4f;
+  const float LW_diff_sec = 1.66f;
+  const float pi = acosf(-1.0f);
+  const int top_level = top_at_1 ? 0 : nlay;
+#pragma omp parallel
+  {
+    size_t nl = (size_t)ngpt * nlay, nv = (size_t)ngpt * (nlay + 1);
+    float* wk = (float*)malloc(sizeof(float) * (5 * nl + 4 * nv));
+    float* Rdif = wk;
+    float* Tdif = Rdif + nl;
+    float* source_up = Tdif + nl;
+    float* source_dn = source_up + nl;
+    float* denom = source_dn + nl;
+    float* radn_up_arr = denom + nl;
+    float* radn_dn_arr = radn_up_arr + nv;
+    float* albedo = radn_dn_arr + nv;
+    float* src = albedo + nv;
+#pragma omp for schedule(static)
+    for (int icol = 0; icol < ncol; ++icol) {
+      float* radn_up = gpt_up ? gpt_up + (size_t)icol * nv : radn_up_arr;
+      float* radn_dn = gpt_up ? gpt_dn + (size_t)icol * nv : radn_dn_arr;
+      const float* tauc = tau + (size_t)icol * nl;
+      const float* w0c = ssa + (size_t)icol * nl;
+      const float* gc = gasym + (size_t)icol * nl;
+      const float* levc = lev_source + (size_t)icol * nv;
+      for (int g = 0; g < ngpt; ++g) radn_dn[(size_t)top_level * ngpt + g] = inc_flux ? inc_flux[(size_t)icol * ngpt + g] : 0.0f;
+      for (int l = 0; l < nlay; ++l)
+        for (int g = 0; g < ngpt; ++g) {
+          size_t i = (size_t)l * ngpt + g;
+          float gamma1 = LW_diff_sec * (1.0f - 0.5f * w0c[i] * (1.0f + gc[i]));
+          float gamma2 = LW_diff_sec * 0.5f * w0c[i] * (1.0f - gc[i]);
+          float k = sqrtf(fmaxf((gamma1 - gamma2) * (gamma1 + gamma2), k_min));
+          float e1 = expf(-tauc[i] * k);
+          float e2 = e1 * e1;
+          float RT = 1.0f / (k * (1.0f + e2) + gamma1 * (1.0f - e2));
+          Rdif[i] = RT * gamma2 * (1.0f - e2);
+          Tdif[i] = RT * 2.0f * k * e1;
+          float top = top_at_1 ? levc[i] : levc[i + ngpt], bot = top_at_1 ? levc[i + ngpt] : levc[i];
+          if (tauc[i] > 1.0e-8f) {
+            float Z = (bot - top) / (tauc[i] * (gamma1 + gamma2));
+            float Zup_top = Z + top, Zup_bottom = Z + bot, Zdn_top = -Z + top, Zdn_bottom = -Z + bot;
+            source_up[i] = pi * (Zup_top - Rdif[i] * Zdn_top - Tdif[i] * Zup_bottom);
+            source_dn[i] = pi * (Zdn_bottom - Rdif[i] * Zup_bottom - Tdif[i] * Zdn_top);
+          } else {
+            source_up[i] = 0.0f;
+            source_dn[i] = 0.0f;
+          }
+        }
+      /* adding :1526-1637 */
+      const float* em = sfc_emis + (size_t)icol * ngpt;
+      const float* ss = sfc_source + (size_t)icol * ngpt;
+      if (top_at_1) {
+        for (int g = 0; g < ngpt; ++g) { albedo[(size_t)nlay * ngpt + g] = 1.0f - em[g]; src[(size_t)nlay * ngpt + g] = pi * em[g] * ss[g]; }
+        for (int l = nlay - 1; l >= 0; --l)
+          for (int g = 0; g < ngpt; ++g) {
+            size_t i = (size_t)l * ngpt + g, ip = (size_t)(l + 1) * ngpt + g;
+            denom[i] = 1.0f / (1.0f - Rdif[i] * albedo[ip]);
+            albedo[i] = Rdif[i] + Tdif[i] * Tdif[i] * albedo[ip] * denom[i];
+            src[i] = source_up[i] + Tdif[i] * denom[i] * (src[ip] + albedo[ip] * source_dn[i]);
+          }
+        for (int g = 0; g < ngpt; ++g) radn_up[g] = radn_dn[g] * albedo[g] + src[g];
+        for (int lev = 1; lev <= nlay; ++lev)
+          for (int g = 0; g < ngpt; ++g) {
+            size_t i = (size_t)lev * ngpt + g, im = (size_t)(lev - 1) * ngpt + g;
+            radn_dn[i] = (Tdif[im] * radn_dn[im] + Rdif[im] * src[i] + source_dn[im]) * denom[im];
+            radn_up[i] = radn_dn[i] * albedo[i] + src[i];
+          }
+      } else {
+        for (int g = 0; g < ngpt; ++g) { albedo[g] = 1.0f - em[g]; src[g] = pi * em[g] * ss[g]; }
+        for (int l = 0; l < nlay; ++l)
+          for (int g = 0; g < ngpt; ++g) {
+            size_t i = (size_t)l * ngpt + g, ip = (size_t)(l + 1) * ngpt + g;
+            denom[i] = 1.0f / (1.0f - Rdif[i] * albedo[i]);
+            albedo[ip] = Rdif[i] + Tdif[i] * Tdif[i] * albedo[i] * denom[i];
+            src[ip] = source_up[i] + Tdif[i] * denom[i] * (src[i] + albedo[i] * source_dn[i]);
+          }
+        {
+          size_t t = (size_t)nlay * ngpt;
+          for (int g = 0; g < ngpt; ++g) radn_up[t + g] = radn_dn[t + g] * albedo[t + g] + src[t + g];
+        }
+        for (int l = nlay - 1; l >= 0; --l)
+          for (int g = 0; g < ngpt; ++g) {
+            size_t i = (size_t)l * ngpt + g, ip = (size_t)(l + 1) * ngpt + g;
+            radn_dn[i] = (Tdif[i] * radn_dn[ip] + Rdif[i] * src[i] + source_dn[i]) * denom[i];
+            radn_up[i] = radn_dn[i] * albedo[i] + src[i];
+          }
+      }
+      for (int lev = 0; lev <= nlay; ++lev) {
+        float su = 0, sd = 0;
+        for (int g = 0; g < ngpt; ++g) { su += radn_up[(size_t)lev * ngpt + g]; sd += radn_dn[(size_t)lev * ngpt + g]; }
+        flux_up[(size_t)icol * (nlay + 1) + lev] = su;
+        flux_dn[(size_t)icol * (nlay + 1) + lev] = sd;
+      }
+    }
+    free(wk);
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
  * sw_solver_2stream: rte/kernels/mo_rte_solver_kernels.F90:541-692 with
  *   sw_two_stream_source :1366-1480, adding :1526-1637, k_min = 1e-4 (:76-82),
  *   broadband sums :643-680.

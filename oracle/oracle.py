@@ -315,6 +315,21 @@ def lw_solver_noscat_GaussQuad_ext(top_at_1, nmus, tau, lay_source, lev_source, 
     return out
 
 
+def lw_solver_2stream(top_at_1, tau, ssa, g, lev_source, sfc_emis_gpt, sfc_source, inc_flux=None, want_gpt=False, fast=False):
+    """lw_solver_2stream (rte/kernels/mo_rte_solver_kernels.F90:426-486): flux_up, flux_dn [, gpt_flux_up, gpt_flux_dn]."""
+    ncol, nlay, ngpt = tau.shape
+    dt = _dt(fast)
+    if inc_flux is None:
+        inc_flux = np.zeros((ncol, ngpt), dt)
+    a = [_a(v, fast) for v in (inc_flux, tau, ssa, g, lev_source, sfc_emis_gpt, sfc_source)]
+    up = np.empty((ncol, nlay + 1), dt); dn = np.empty_like(up)
+    gu = np.empty((ncol, nlay + 1, ngpt), dt) if want_gpt else None
+    gd = np.empty_like(gu) if want_gpt else None
+    lib(fast).orc_lw_solver_2stream(ngpt, nlay, ncol, int(bool(top_at_1)), *[_p(v) for v in a], _p(up), _p(dn),
+                                    None if gu is None else _p(gu), None if gd is None else _p(gd))
+    return (up, dn, gu, gd) if want_gpt else (up, dn)
+
+
 def sw_solver_2stream(top_at_1, inc_flux, inc_flux_dif, tau, ssa, g, mu0, alb_dir, alb_dif, fast=False):
     ncol, nlay, ngpt = tau.shape
     dt = _dt(fast)

@@ -84,6 +84,8 @@ _SIGS = {
     "rrnn_lw_solver_noscat": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, vp, vp, vp,
                                         vp, vp, vp, vp, vp]),
     "rrnn_lw_solver_noscat_ext": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p] + [vp] * 15),
+    "rrnn_lw_solver_2stream": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 11),
+    "rrnn_rte_lw_2stream": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int] + [vp] * 11),
     "rrnn_rte_lw_ext": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int] + [vp] * 15),
     "rrnn_rte_lw": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_sw_solver_2stream": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

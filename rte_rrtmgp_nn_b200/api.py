@@ -528,15 +528,35 @@ def rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes, inc_flux=None, n_
            lw_Ds=None, flux_up_Jac=None, flux_dn_Jac=None):
     """rte_lw (rte/mo_rte_lw.F90:60-64); sfc_emis is (ncol, nband).  ty_optical_props_1scl: no-scattering solution (the tuned
     kernels; the general kernel when lw_Ds, flux_up_Jac or g-point fluxes are asked for).  ty_optical_props_2str: the
-    re-scaled solution (:363-384); use_2stream (lw_solver_2stream) is not implemented."""
+    re-scaled solution (:363-384), or lw_solver_2stream with use_2stream=True (:346-361)."""
     if not fluxes.are_desired():
         return "rte_lw: no space allocated for fluxes"
     two = isinstance(optical_props, ty_optical_props_2str)
     if not two and not isinstance(optical_props, ty_optical_props_1scl):
         return "rte_lw: lw_solver(...ty_optical_props_nstr...) not yet implemented"
+    if use_2stream and not two:
+        return "rte_lw: can't use two-stream methods with only absorption optical depth"
+    if use_2stream and (flux_up_Jac is not None or flux_dn_Jac is not None):
+        return "rte_lw: can't provide Jacobian of fluxes w.r.t surface temperature with 2-stream"
     if use_2stream:
-        return ("rte_lw: the two-stream longwave solver (lw_solver_2stream) is not implemented" if two else
-                "rte_lw: can't use two-stream methods with only absorption optical depth")
+        if n_gauss_angles is not None:
+            return "rte_lw: n_gauss_angles not compatible with use_2stream"
+        if lw_Ds is not None:
+            return "rte_lw: lw_Ds not valid input for _2str class"
+        ctx = optical_props.ctx
+        ncol, nlay = optical_props.get_ncol(), optical_props.get_nlay()
+        sfc_emis = _dev(sfc_emis, ctx)
+        if tuple(sfc_emis.shape) != (ncol, optical_props.nband):
+            return "rte_lw: sfc_emis inconsistently sized"
+        try:
+            _lib.check(_lib.lib().rrnn_rte_lw_2stream(
+                ctx.h, optical_props._kd.h, nlay, ncol, int(bool(top_at_1)), _ptr(_dev(inc_flux, ctx)), _ptr(optical_props.tau),
+                _ptr(optical_props.ssa), _ptr(optical_props.g), _ptr(sources.lev_source), _ptr(sources.sfc_source), _ptr(sfc_emis),
+                _ptr(fluxes.flux_up), _ptr(fluxes.flux_dn), _ptr(getattr(fluxes, "gpt_flux_up", None)),
+                _ptr(getattr(fluxes, "gpt_flux_dn", None))))
+        except RRNNError as e:
+            return str(e)
+        return ""
     if flux_dn_Jac is not None:
         return "rte_lw: flux_dn_Jac is not computed (as in the reference)"
     if lw_Ds is not None and two:

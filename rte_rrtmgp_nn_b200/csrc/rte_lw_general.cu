@@ -182,6 +182,110 @@ __global__ void __launch_bounds__(256) lw_general_kernel(const LwGenParams p) {
   }
 }
 
+// lw_solver_2stream (:426-486): lw_two_stream :1018-1069 (LW_diff_sec = 1.66), lw_source_2str :1112-1162, adding :1526-1637 with
+// sfc_albedo = 1 - sfc_emis and source_sfc = pi * sfc_emis * sfc_source; plain sums over g-points.  Same layout of the work
+// as lw_general_kernel (thread = g-point, array order, coalesced scratch); reuses LwGenParams (Ds / wts / Jacobian unused).
+__global__ void __launch_bounds__(256) lw_2stream_kernel(const LwGenParams p) {
+  const int G = p.ngpt, L = p.nlay, GP = p.gp;
+  const bool top = p.top_at_1 != 0;
+  const float k_min = 1.e-4f, LW_diff_sec = 1.66f;
+  float* sc = p.scratch + (size_t)blockIdx.x * p.scratch_per_block;
+  float* Rdif = sc;
+  float* Tdif = Rdif + (size_t)L * GP;
+  float* sup = Tdif + (size_t)L * GP;
+  float* sdn = sup + (size_t)L * GP;
+  float* den = sdn + (size_t)L * GP;
+  float* alb = den + (size_t)L * GP;
+  float* src = alb + (size_t)(L + 1) * GP;
+  float* rup_s = src + (size_t)(L + 1) * GP;
+  float* rdn_s = rup_s + (size_t)(L + 1) * GP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int col = blockIdx.x; col < p.ncol; col += gridDim.x) {
+    const size_t nl = (size_t)col * L * G, nv = (size_t)col * (L + 1) * G;
+    float* rup = p.gpt_up ? p.gpt_up + nv : rup_s;
+    float* rdn = p.gpt_dn ? p.gpt_dn + nv : rdn_s;
+    const int rp = p.gpt_up ? G : GP;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      for (int l = 0; l < L; ++l) {
+        const size_t i = nl + (size_t)l * G + g, k_ = (size_t)l * GP + g;
+        const float tau = p.tau[i], w0 = p.ssa[i], gg = p.g[i];
+        const float gamma1 = LW_diff_sec * (1.0f - 0.5f * w0 * (1.0f + gg));  // Fu et al. Eq 2.9
+        const float gamma2 = LW_diff_sec * 0.5f * w0 * (1.0f - gg);           // Eq 2.10
+        const float k = sqrtf(fmaxf((gamma1 - gamma2) * (gamma1 + gamma2), k_min));
+        const float e1 = expf(-tau * k);
+        const float e2 = e1 * e1;
+        const float RT = 1.0f / (k * (1.0f + e2) + gamma1 * (1.0f - e2));
+        const float R = RT * gamma2 * (1.0f - e2), T = RT * 2.0f * k * e1;
+        Rdif[k_] = R; Tdif[k_] = T;
+        const float la = p.lev_source[nv + (size_t)l * G + g], lb = p.lev_source[nv + (size_t)(l + 1) * G + g];
+        const float ltop = top ? la : lb, lbot = top ? lb : la;
+        float su = 0.0f, sd = 0.0f;
+        if (tau > 1.0e-8f) {
+          const float Z = (lbot - ltop) / (tau * (gamma1 + gamma2));
+          const float Zup_top = Z + ltop, Zup_bottom = Z + lbot, Zdn_top = -Z + ltop, Zdn_bottom = -Z + lbot;
+          su = kPi * (Zup_top - R * Zdn_top - T * Zup_bottom);
+          sd = kPi * (Zdn_bottom - R * Zup_bottom - T * Zdn_top);
+        }
+        sup[k_] = su; sdn[k_] = sd;
+      }
+      const float em = p.sfc_emis[(size_t)col * G + g];
+      float a = 1.0f - em, s = kPi * em * p.sfc_source[(size_t)col * G + g];
+      const float inc = p.inc_flux ? p.inc_flux[(size_t)col * G + g] : 0.0f;
+      if (top) {
+        alb[(size_t)L * GP + g] = a; src[(size_t)L * GP + g] = s;
+        for (int l = L - 1; l >= 0; --l) {
+          const size_t i = (size_t)l * GP + g;
+          const float R = Rdif[i], T = Tdif[i];
+          const float d = 1.0f / (1.0f - R * a);
+          den[i] = d;
+          const float a_new = R + T * T * a * d;
+          s = sup[i] + T * d * (s + a * sdn[i]);
+          a = a_new;
+          alb[i] = a; src[i] = s;
+        }
+        float dn = inc;
+        rdn[g] = dn;
+        rup[g] = dn * a + s;
+        for (int lev = 1; lev <= L; ++lev) {
+          const size_t im = (size_t)(lev - 1) * GP + g, i = (size_t)lev * GP + g;
+          dn = (Tdif[im] * dn + Rdif[im] * src[i] + sdn[im]) * den[im];
+          rdn[(size_t)lev * rp + g] = dn;
+          rup[(size_t)lev * rp + g] = dn * alb[i] + src[i];
+        }
+      } else {
+        alb[g] = a; src[g] = s;
+        for (int l = 0; l < L; ++l) {
+          const size_t i = (size_t)l * GP + g;
+          const float R = Rdif[i], T = Tdif[i];
+          const float d = 1.0f / (1.0f - R * a);
+          den[i] = d;
+          const float a_new = R + T * T * a * d;
+          s = sup[i] + T * d * (s + a * sdn[i]);
+          a = a_new;
+          alb[i + GP] = a; src[i + GP] = s;
+        }
+        float dn = inc;
+        rdn[(size_t)L * rp + g] = dn;
+        rup[(size_t)L * rp + g] = dn * a + s;
+        for (int l = L - 1; l >= 0; --l) {
+          const size_t i = (size_t)l * GP + g;
+          dn = (Tdif[i] * dn + Rdif[i] * src[i] + sdn[i]) * den[i];
+          rdn[(size_t)l * rp + g] = dn;
+          rup[(size_t)l * rp + g] = dn * alb[i] + src[i];
+        }
+      }
+    }
+    __syncthreads();
+    for (int lev = warp; lev <= L; lev += nwarps) {
+      float su = 0.0f, sd = 0.0f;
+      for (int g = lane; g < G; g += 32) { su += rup[(size_t)lev * rp + g]; sd += rdn[(size_t)lev * rp + g]; }
+      su = warp_sum(su); sd = warp_sum(sd);
+      if (lane == 0) { p.flux_up[(size_t)col * (L + 1) + lev] = su; p.flux_dn[(size_t)col * (L + 1) + lev] = sd; }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void expand_emis_kernel(int nbnd, int ngpt, int ncol, const int* __restrict__ gpt2band, const float* __restrict__ in,
                                    float* __restrict__ out) {  // expand, rte/mo_rte_lw.F90:429-447
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,6 +369,56 @@ extern "C" int rrnn_rte_lw_ext(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay
                                            gauss_wts[n_gauss_angles - 1], lw_Ds_d, inc_flux_d, tau_d, ssa_d, g_d, lay_source_d,
                                            lev_source_d, emis_gpt, sfc_source_d, sfc_source_Jac_d, flux_up_d, flux_dn_d, flux_up_Jac_d,
                                            gpt_flux_up_d, gpt_flux_dn_d);
+  cudaFreeAsync(emis_gpt, ctx->stream);
+  return rc;
+}
+
+extern "C" int rrnn_lw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux_d,
+                                      const float* tau_d, const float* ssa_d, const float* g_d, const float* lev_source_d,
+                                      const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d, float* flux_dn_d,
+                                      float* gpt_flux_up_d, float* gpt_flux_dn_d) {
+  RRNN_CHECK(ctx, "rrnn_lw_solver_2stream: null context");
+  RRNN_CHECK(ngpt > 0 && nlay > 0 && ncol >= 0, "rrnn_lw_solver_2stream: bad extents");
+  RRNN_CHECK(tau_d && ssa_d && g_d && lev_source_d && sfc_emis_gpt_d && sfc_source_d && flux_up_d && flux_dn_d,
+             "rrnn_lw_solver_2stream: null argument");
+  RRNN_CHECK((gpt_flux_up_d == nullptr) == (gpt_flux_dn_d == nullptr), "rrnn_lw_solver_2stream: gpt_flux_up and gpt_flux_dn come together");
+  if (ncol == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  LwGenParams p{};
+  p.ngpt = ngpt; p.nlay = nlay; p.ncol = ncol; p.top_at_1 = top_at_1 ? 1 : 0;
+  p.gp = (ngpt + 31) & ~31;
+  p.inc_flux = inc_flux_d; p.tau = tau_d; p.ssa = ssa_d; p.g = g_d; p.lev_source = lev_source_d;
+  p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
+  p.gpt_up = gpt_flux_up_d; p.gpt_dn = gpt_flux_dn_d;
+  p.scratch_per_block = ((size_t)5 * nlay + (size_t)4 * (nlay + 1)) * p.gp;
+  const int threads = std::min(p.gp, 256);
+  const int blocks = std::min(ncol, ctx->num_sms * 4);
+  if (int rc = ensure_scratch(ctx, (size_t)blocks * p.scratch_per_block * sizeof(float))) return rc;
+  p.scratch = (float*)ctx->scratch;
+  const int ps = prof_begin(ctx, K_LW_SOLVER);
+  lw_2stream_kernel<<<blocks, threads, 0, ctx->stream>>>(p);
+  prof_end(ctx, K_LW_SOLVER, ps);
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// rte_lw(..., use_2stream = .true.) for ty_optical_props_2str (rte/mo_rte_lw.F90:346-361); sfc_emis_d is (nbnd,ncol)
+extern "C" int rrnn_rte_lw_2stream(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, const float* inc_flux_d,
+                                   const float* tau_d, const float* ssa_d, const float* g_d, const float* lev_source_d,
+                                   const float* sfc_source_d, const float* sfc_emis_d, float* flux_up_d, float* flux_dn_d,
+                                   float* gpt_flux_up_d, float* gpt_flux_dn_d) {
+  RRNN_CHECK(ctx && kd, "rte_lw: null handle");
+  RRNN_CHECK(flux_up_d && flux_dn_d, "rte_lw: no space allocated for fluxes");
+  if (ncol == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const int ngpt = kd->ngpt;
+  float* emis_gpt = nullptr;
+  RRNN_CUDA(cudaMallocAsync((void**)&emis_gpt, (size_t)ngpt * ncol * sizeof(float), ctx->stream));
+  const size_t n = (size_t)ngpt * ncol;
+  expand_emis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(kd->nbnd, ngpt, ncol, kd->d_gpt2band, sfc_emis_d, emis_gpt);
+  RRNN_LAUNCH_CHECK(ctx);
+  const int rc = rrnn_lw_solver_2stream(ctx, ngpt, nlay, ncol, top_at_1, inc_flux_d, tau_d, ssa_d, g_d, lev_source_d, emis_gpt, sfc_source_d,
+                                        flux_up_d, flux_dn_d, gpt_flux_up_d, gpt_flux_dn_d);
   cudaFreeAsync(emis_gpt, ctx->stream);
   return rc;
 }

@@ -354,3 +354,31 @@ def test_mcica_sampling_properties():
     f = rng.uniform(1, 2, size=(ncol, nlay, 2)).astype(np.float32)
     s, = O.draw_samples(m, lims, f)
     assert np.array_equal(s[..., :1024], np.where(m[..., :1024], f[..., :1], 0)) and np.array_equal(s[..., 1024:], np.where(m[..., 1024:], f[..., 1:], 0))
+
+
+def test_lw_solver_2stream_known_answers():
+    """The oracle's lw_solver_2stream (mo_rte_solver_kernels.F90:426-486): an isothermal atmosphere over a black surface at the
+    same temperature radiates pi*B upward at every level without scattering (with scattering: deep inside only), and pi*B
+    downward where it is optically thick; both orientations agree under a vertical flip; without scattering the fluxes are close to the 1-angle no-scattering
+    solution (the two-stream diffusivity factor is the same 1.66)."""
+    import oracle as O
+    rng = np.random.default_rng(2)
+    C, L, G = 3, 24, 16
+    tau = rng.gamma(2.0, 1.0, (C, L, G)).astype(np.float32)
+    ssa = rng.uniform(0, 0.9, (C, L, G)).astype(np.float32); g = rng.uniform(0, 0.8, (C, L, G)).astype(np.float32)
+    B = 1.5
+    lev = np.full((C, L + 1, G), B, np.float32); em = np.ones((C, G), np.float32); ss = np.full((C, G), B, np.float32)
+    up, dn = O.lw_solver_2stream(True, tau, np.zeros_like(ssa), g, lev, em, ss, fast="f64")
+    assert np.allclose(up, np.pi * B * G, rtol=1e-10) and np.allclose(dn[:, -1], np.pi * B * G, rtol=1e-6)
+    up, dn = O.lw_solver_2stream(True, tau, ssa, g, lev, em, ss, fast="f64")   # scattering: still pi*B deep inside, less at the top
+    assert np.allclose(up[:, L // 2:], np.pi * B * G, rtol=1e-4) and np.allclose(dn[:, -1], np.pi * B * G, rtol=1e-4)
+    assert (up[:, 0] < 0.99 * np.pi * B * G).all()
+    lev2 = np.sort(rng.uniform(0.5, 2.0, (C, L + 1, G)), axis=1).astype(np.float32)
+    a = O.lw_solver_2stream(True, tau, ssa, g, lev2, em * 0.9, ss, fast="f64")
+    b = O.lw_solver_2stream(False, tau[:, ::-1], ssa[:, ::-1], g[:, ::-1], lev2[:, ::-1], em * 0.9, ss, fast="f64")
+    assert np.allclose(a[0], b[0][:, ::-1], rtol=1e-12) and np.allclose(a[1], b[1][:, ::-1], rtol=1e-12)
+    z = np.zeros_like(tau)
+    lay2 = np.sqrt(lev2[:, 1:] * lev2[:, :-1]).astype(np.float32)
+    two = O.lw_solver_2stream(True, tau, z, z, lev2, em, ss, fast="f64")
+    one = O.lw_solver_noscat_GaussQuad(True, 1, tau, lay2, lev2, em, ss, fast="f64")
+    assert np.abs(two[0] - one[0]).max() / one[0].max() < 0.05

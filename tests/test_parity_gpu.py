@@ -503,6 +503,56 @@ def test_sw_gpt_fluxes_and_three_sweep_kernel(gpu_ctx, G, L, C, top, has_g):
         assert torch.equal(flx.gpt_flux_up, gp[0]) and torch.equal(flx.flux_dn, fl[1])
 
 
+@pytest.mark.parametrize("G,L,C,top", [(256, 60, 6, True), (128, 33, 5, False), (36, 7, 3, True)])
+def test_lw_solver_2stream_matches_oracle(gpu_ctx, G, L, C, top):
+    """lw_solver_2stream (rte/kernels/mo_rte_solver_kernels.F90:426-486) and rte_lw(use_2stream=True)."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib, spectral
+    torch = _torch()
+    rng = np.random.default_rng(G + 7 * L)
+    # lw_source_2str divides the level-source difference by tau*(gamma1+gamma2) and then cancels: below tau ~ 1e-4 every fp32
+    # evaluation of the reference formula is rounding noise (oracle32 vs oracle64: 1e-2 of 6 at tau = 2e-6), so the random
+    # optical depths stay above that, plus exact zeros for the tau <= 1e-8 branch
+    tau = np.maximum(rng.gamma(0.4, 1.5, size=(C, L, G)), 1e-4).astype(np.float32); tau[0, 0, :3] = 0.0
+    ssa = rng.uniform(0.0, 0.95, size=(C, L, G)).astype(np.float32)
+    g = rng.uniform(-0.2, 0.9, size=(C, L, G)).astype(np.float32)
+    lev = np.sort(rng.uniform(0.5, 2.0, size=(C, L + 1, G)).astype(np.float32), axis=1)
+    emis = rng.uniform(0.8, 1.0, size=(C, G)).astype(np.float32)
+    ssrc = rng.uniform(0.5, 2.0, size=(C, G)).astype(np.float32)
+    inc = rng.uniform(0.0, 0.5, size=(C, G)).astype(np.float32)
+    ref = O.lw_solver_2stream(top, tau, ssa, g, lev, emis, ssrc, inc_flux=inc, want_gpt=True)
+    r64 = O.lw_solver_2stream(top, tau, ssa, g, lev, emis, ssrc, inc_flux=inc, want_gpt=True, fast="f64")
+    d = [torch.from_numpy(v).cuda() for v in (inc, tau, ssa, g, lev, emis, ssrc)]
+    P = api._ptr
+    up = torch.zeros((C, L + 1), device="cuda"); dn = torch.zeros_like(up)
+    gu = torch.zeros((C, L + 1, G), device="cuda"); gd = torch.zeros_like(gu)
+    _lib.check(_lib.lib().rrnn_lw_solver_2stream(gpu_ctx.h, G, L, C, int(top), *[P(t) for t in d], P(up), P(dn), P(gu), P(gd)))
+    for got, k in ((up, 0), (dn, 1), (gu, 2), (gd, 3)):
+        e = np.abs(got.cpu().numpy() - r64[k]).max()
+        noise = np.abs(ref[k] - r64[k]).max()
+        assert e <= max(2e-5 * max(np.abs(ref[k]).max(), 1e-3), 2.0 * noise), (k, e, noise)
+    up2 = torch.zeros_like(up); dn2 = torch.zeros_like(up)
+    _lib.check(_lib.lib().rrnn_lw_solver_2stream(gpu_ctx.h, G, L, C, int(top), *[P(t) for t in d], P(up2), P(dn2), None, None))
+    assert torch.allclose(up2, up, rtol=1e-6, atol=1e-5) and torch.allclose(dn2, dn, rtol=1e-6, atol=1e-5)
+    if G == 256:  # the host mirror: rte_lw(use_2stream=True) on a 2str atmosphere, band emissivity expanded
+        k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); kd = spectral.synthetic_kdist_lw(256); k_dist.load(kd)
+        atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(C, L, k_dist) == ""
+        atmos._kd = k_dist._kd
+        atmos.tau.copy_(d[1]); atmos.ssa.copy_(d[2]); atmos.g = d[3].clone()
+        src = api.ty_source_func_lw(); assert src.alloc(C, L, k_dist) == ""
+        src.lev_source.copy_(d[4]); src.sfc_source.copy_(d[6])
+        emis_b = rng.uniform(0.8, 1.0, size=(C, 16)).astype(np.float32)
+        fl = api.ty_fluxes_broadband(torch.zeros_like(up), torch.zeros_like(up))
+        assert api.rte_lw(atmos, top, src, emis_b, fl, use_2stream=True) == ""
+        eg = O.expand(kd["band_lims_gpt"], G, emis_b)
+        w = O.lw_solver_2stream(top, tau, ssa, g, lev, eg, ssrc)
+        w64 = O.lw_solver_2stream(top, tau, ssa, g, lev, eg, ssrc, fast="f64")
+        assert np.abs(fl.flux_up.cpu().numpy() - w64[0]).max() <= max(2e-5 * np.abs(w[0]).max(), 2.0 * np.abs(w[0] - w64[0]).max())
+        assert "Jacobian" in api.rte_lw(atmos, top, src, emis_b, fl, use_2stream=True, flux_up_Jac=torch.zeros_like(up))
+        op1 = api.ty_optical_props_1scl(); op1.alloc_1scl(C, L, k_dist); op1._kd = k_dist._kd
+        assert api.rte_lw(op1, top, src, emis_b, fl, use_2stream=True) == "rte_lw: can't use two-stream methods with only absorption optical depth"
+
+
 def test_sgemm_entry_points(gpu_ctx):
     """output_sgemm_tau / _pfrac / _lw on materialised inputs (+ compute_nn_inputs, get_col_dry, Planck source)."""
     import oracle as O
