@@ -134,22 +134,36 @@ class NC4File:
         else:
             bt, cd = layout[1], layout[2]
             cshape = tuple(cd[:-1])
-            if len(cshape) != len(shape) or any(c < s_ for c, s_ in zip(cshape, shape)):
-                raise ValueError(f"{name}: multi-chunk datasets unsupported")
+            if len(cshape) != len(shape):
+                raise ValueError(f"{name}: chunk rank differs from dataset rank")
             b = self.buf
-            if b[bt:bt + 4] != b"TREE" or b[bt + 4] != 1 or b[bt + 5] != 0:
-                raise ValueError("unsupported chunk b-tree")
-            nent = struct.unpack_from("<H", b, bt + 6)[0]
-            if nent != 1:
-                raise ValueError("multi-chunk")
-            p = bt + 8 + 16  # siblings
             nd = len(cd)
-            p += 8 + 8 * nd  # key: size(4) mask(4) offsets
-            child = struct.unpack_from("<Q", b, p)[0]
             cn = int(np.prod(cshape))
-            carr = np.frombuffer(b[child:child + cn * npdt.itemsize], dtype=npdt, count=cn).reshape(cshape)
-            carr = carr[tuple(slice(0, s_) for s_ in shape)]
-            raw = np.ascontiguousarray(carr).tobytes()
+            out = np.zeros(shape, dtype=npdt)
+
+            def walk(addr):  # version-1 B-tree of raw-data chunks: leaves (level 0) point at chunks, inner nodes at nodes
+                if b[addr:addr + 4] != b"TREE" or b[addr + 4] != 1:
+                    raise ValueError("unsupported chunk b-tree")
+                level = b[addr + 5]
+                nent = struct.unpack_from("<H", b, addr + 6)[0]
+                q = addr + 8 + 16  # siblings
+                for _ in range(nent):
+                    size, mask = struct.unpack_from("<II", b, q)
+                    offs = struct.unpack_from("<%dQ" % nd, b, q + 8)
+                    child = struct.unpack_from("<Q", b, q + 8 + 8 * nd)[0]
+                    q += 8 + 8 * nd + 8
+                    if level > 0:
+                        walk(child)
+                        continue
+                    if mask != 0 or size != cn * npdt.itemsize:
+                        raise ValueError(f"{name}: filtered chunks unsupported")
+                    carr = np.frombuffer(b[child:child + size], dtype=npdt, count=cn).reshape(cshape)
+                    dst = tuple(slice(o, min(o + c, s_)) for o, c, s_ in zip(offs, cshape, shape))
+                    src = tuple(slice(0, d.stop - d.start) for d in dst)
+                    out[dst] = carr[src]
+
+            walk(bt)
+            raw = np.ascontiguousarray(out).tobytes()
         arr = np.frombuffer(raw, dtype=npdt, count=n).reshape(shape)
         if cls != 3:
             arr = arr.astype(npdt.newbyteorder("="))

@@ -382,3 +382,15 @@ def test_lw_solver_2stream_known_answers():
     two = O.lw_solver_2stream(True, tau, z, z, lev2, em, ss, fast="f64")
     one = O.lw_solver_noscat_GaussQuad(True, 1, tau, lay2, lev2, em, ss, fast="f64")
     assert np.abs(two[0] - one[0]).max() / one[0].max() < 0.05
+
+
+def test_garand_fixture_and_chunked_reader():
+    """tests/golden/garand_atmos.npz (tools/make_garand_fixture.py; the minimal HDF5 reader walks the multi-chunk v1 B-trees
+    of examples/all-sky/garand-atmos-1.nc): a physically ordered, bottom-up, 42-layer atmosphere."""
+    z = np.load(os.path.join(H.GOLDEN, "garand_atmos.npz"))
+    assert z["p_lay"].shape == (2, 42) and z["p_lev"].shape == (2, 43)
+    assert (np.diff(z["p_lev"], axis=1) < 0).all() and z["p_lev"][0, 0] == np.float32(101320.0)
+    assert ((z["p_lay"] < z["p_lev"][:, :-1]) & (z["p_lay"] > z["p_lev"][:, 1:])).all()
+    assert 190 < z["t_lay"].min() and z["t_lay"].max() < 305 and abs(z["vmr_o2"].mean() - 0.209) < 1e-3
+    dry = z["vmr_n2"] + z["vmr_o2"]
+    assert (dry > 0.99).all() and (dry < 1.0).all()

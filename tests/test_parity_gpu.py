@@ -843,6 +843,70 @@ def test_mcica_sampling_matches_oracle(gpu_ctx):
     assert "inconsistent" in api.sampled_mask_max_ran(randoms, cf[:, :-1], bad, ctx=gpu_ctx)
 
 
+def test_driver_replicas(gpu_ctx, tmp_path):
+    """rte_rrtmgp_nn_b200.drivers: the RFMIP drivers' block loop is block-size independent and matches the
+    oracle on real RFMIP profiles; the all-sky driver on the Garand atmosphere matches the oracle chain (LUT and Pade);
+    the flux files have the drivers' structure."""
+    import oracle as O
+    from scipy.io import netcdf_file
+    from rte_rrtmgp_nn_b200 import drivers, rfmip, spectral
+    cols = np.r_[0:20, 900:912, 1795:1800]   # 37 columns from three experiments: ragged last block
+    up8, dn8 = drivers.rrtmgp_rfmip_lw(gpu_ctx, block_size=8, columns=cols)
+    up37, dn37 = drivers.rrtmgp_rfmip_lw(gpu_ctx, block_size=64, columns=cols)
+    assert np.array_equal(up8, up37) and np.array_equal(dn8, dn37)          # blocks do not matter (tests/clear_sky_regression.F90)
+    atm = rfmip.load(columns=cols)
+    kd = spectral.synthetic_kdist_lw(256)
+    ref = O.gas_optics_lw(kd, H.oracle_nets(H.LW_G256), atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"])
+    rup, rdn = O.rte_lw(kd, atm["top_at_1"], ref["tau"], ref["lay_source"], ref["lev_source"], ref["sfc_source"],
+                        np.repeat(atm["sfc_emis"][:, None], 16, 1))
+    assert np.abs(up8 - rup).max() <= H.FLUX_TOL and np.abs(dn8 - rdn).max() <= H.FLUX_TOL
+    su8, sd8 = drivers.rrtmgp_rfmip_sw(gpu_ctx, block_size=8, columns=cols)
+    su37, sd37 = drivers.rrtmgp_rfmip_sw(gpu_ctx, block_size=64, columns=cols)
+    assert np.array_equal(su8, su37) and np.array_equal(sd8, sd37)
+    assert (su8[~atm["usecol"]] == 0).all() and su8[atm["usecol"]].max() > 10
+    # files: (expt, site, level) and (lev, col)
+    p = str(tmp_path / "rlu.nc")
+    drivers.write_rfmip_fluxes(p, ("rlu", "rld"), (np.tile(up8[:1], (200, 1)), np.tile(dn8[:1], (200, 1))), 2, 100)
+    f = netcdf_file(p, "r", mmap=False)
+    assert f.variables["rlu"].shape == (2, 100, 61) and f.variables["rlu"].dimensions == ("expt", "site", "level")
+    assert np.array_equal(f.variables["rld"][1, 99], dn8[0]); f.close()
+    # all-sky on the Garand atmosphere (bottom-up, 42 layers): against the oracle chain
+    for band, pade in (("lw", False), ("sw", False), ("sw", True)):
+        ncol = 12
+        out = drivers.rrtmgp_allsky(ncol, nloops=2, band=band, ctx=gpu_ctx, use_pade=pade, out_path=str(tmp_path / f"allsky_{band}.nc"))
+        a = drivers.garand_atmosphere(ncol)
+        assert not a["top_at_1"]
+        co = drivers.api.ty_cloud_optics(gpu_ctx)
+        coef = drivers.os.path.join(drivers.ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc")
+        assert (co.load_pade(**drivers.api.load_cloud_pade_file(coef)) if pade else co.load(**drivers.api.load_cloud_lut_file(coef))) == ""
+        cl = drivers.allsky_clouds(a, co)
+        assert (cl["lwp"] > 0).any() and (cl["iwp"] > 0).any() and not cl["lwp"][2].any()   # every third column is clear
+        copt = O.cloud_optics_pade if pade else O.cloud_optics_lut
+        if band == "lw":
+            kd = spectral.synthetic_kdist_lw(256)
+            tsfc = a["tlev"][:, 0].copy()
+            r = O.gas_optics_lw(kd, H.oracle_nets(H.LW_G256), a["play"], a["plev"], a["tlay"], tsfc, a["gases"], tlev=a["tlev"])
+            tau = O.inc_1scalar_by_1scalar_bybnd(r["tau"], copt(co.tables, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], False), kd["band_lims_gpt"])
+            want = O.rte_lw(kd, False, tau, r["lay_source"], r["lev_source"], r["sfc_source"], np.full((ncol, 16), 0.98, np.float32))
+            for got, w in zip(out, want):
+                assert np.abs(got - w).max() <= H.FLUX_TOL
+        else:
+            kd = spectral.synthetic_kdist_sw(224)
+            alb = np.full((ncol, 224), 0.06, np.float32); mu0 = np.full(ncol, 0.86, np.float32)
+
+            def chain(fast):
+                r = O.gas_optics_sw(kd, H.oracle_nets(H.SW_G224), a["play"], a["plev"], a["tlay"], a["gases"], fast=fast)
+                c = O.delta_scale_2str(*copt(co.tables, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], True, fast=fast), fast=fast)
+                t, w, g = O.inc_2stream_by_2stream_bybnd(r["tau"], r["ssa"], r["g"], *c, kd["band_lims_gpt"], fast=fast)
+                return O.rte_sw(False, mu0, r["toa_src"], alb, alb, t, w, g, fast=fast)
+
+            w32, w64 = chain(False), chain("f64")
+            for got, x, y, nm in zip(out, w32, w64, ("up", "dn", "dir")):
+                H.assert_within_reference_noise(got, x, y, H.FLUX_TOL, f"all-sky driver SW flux_{nm} (pade={pade})")
+        f = netcdf_file(str(tmp_path / f"allsky_{band}.nc"), "r", mmap=False)
+        assert f.variables[f"{band}_flux_up"].shape == (43, ncol) and np.array_equal(f.variables[f"{band}_flux_up"][:].T, out[0]); f.close()
+
+
 def test_heating_rate_K_per_s(gpu_ctx):
     import oracle as O
     from rte_rrtmgp_nn_b200 import api
