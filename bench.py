@@ -234,7 +234,7 @@ def main():
     ap.add_argument("--fast-math", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--solver-buffer", type=int, default=0, help="0 auto, 1 shared memory, 2 L2-resident global scratch")
-    ap.add_argument("--sw-fast-math", type=int, default=0)
+    ap.add_argument("--sw-fast-math", type=int, default=1, help="library default: the SW solver without Newton refinements (no measurable accuracy cost, DESIGN.md section 3b)")
     ap.add_argument("--solver-variant", type=int, default=0, help="0 packed two-g-points-per-lane solvers, 1 one g-point per lane")
     ap.add_argument("--solver-scratch-mb", type=int, default=0, help="L2 budget of the packed solvers' reverse-sweep scratch (0 = default)")
     ap.add_argument("--lw-compact-source", type=int, default=1, help="1 = LW sources stay factored between gas optics and solver (default), 0 = materialised lay/lev_source")
@@ -442,7 +442,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, ncol_total),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
-        "fast_math": int(args.fast_math), "lw_compact_source": int(bool(args.lw_compact_source) and args.solver_variant == 0), "nn_variant": "tcgen05 (fp16 hi/lo split operands, fp32 accumulation in TMEM)",
+        "fast_math": int(args.fast_math), "sw_fast_math": int(args.sw_fast_math), "lw_compact_source": int(bool(args.lw_compact_source) and args.solver_variant == 0), "nn_variant": "tcgen05 (fp16 hi/lo split operands, fp32 accumulation in TMEM)",
         "solver_variant": {0: "v5 TMA-staged packed fp32x2", 2: "v4 packed fp32x2", 1: "v3 one g-point per lane"}[args.solver_variant],
     }
     emit(line)
