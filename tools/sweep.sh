@@ -1,9 +1,9 @@
 #!/bin/bash
-# Column-count sweep (BASELINE configs[4]): LW+SW at 91 layers, 1e3 ... 1e6 columns on one GPU -> profiles/<tag>_sweep_L91.jsonl
+# Column-count sweep (BASELINE configs[4]): LW+SW at 91 layers, 1e3 ... 3e6 columns on one GPU -> profiles/<tag>_sweep_L91.jsonl
 tag=${1:-r1}
 out=gpurun_out/${tag}_sweep_L91.jsonl
 : > $out
-for n in 1000 3000 10000 30000 100000 300000 1000000; do
+for n in 1000 3000 10000 30000 100000 300000 1000000 3000000; do
   timeout 300 python bench.py --columns $n --nlay 91 --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | grep '^{' >> $out
 done
 python - <<'PY' $out
