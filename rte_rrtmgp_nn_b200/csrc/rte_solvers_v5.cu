@@ -39,6 +39,12 @@ namespace v5 {
 #ifndef RRNN_V5_DISCARD
 #define RRNN_V5_DISCARD 1
 #endif
+#ifndef RRNN_V5_LW_SB
+#define RRNN_V5_LW_SB 3
+#endif
+#ifndef RRNN_V5_SW_SB
+#define RRNN_V5_SW_SB 2
+#endif
 #ifndef RRNN_V5_SW_NOB
 #define RRNN_V5_SW_NOB 2
 #endif
@@ -51,7 +57,10 @@ namespace v5 {
 constexpr int MAX_WARPS = 4;  // solvers (warps) per CTA
 constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
 constexpr int SW_OBR = (SW_U > 4) ? SW_U / RRNN_V5_SW_NOB : SW_U;
-constexpr int LW_OBR = (LW_U > 4) ? LW_U / 2 : LW_U;  // layers per store-staging tile of the SW solver
+constexpr int LW_OBR = (LW_U > 4) ? LW_U / 2 : LW_U;
+// stages of the reverse-sweep (upward) ring: the upward sweep spends only a few hundred cycles per group, less than an L2 /
+// DRAM round trip, so it prefetches as deep as the shared memory of the downward sweep (which it reuses) allows
+constexpr int LW_SB = RRNN_V5_LW_SB, SW_SB = RRNN_V5_SW_SB;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -193,14 +202,14 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
   constexpr int OBR = LW_OBR, NOB = U / OBR;                 // store staging in tiles of OBR layers (see sw_solver_v5)
   uint8_t* ob = in_ring + S * STAGE;                         // [2][OBR][512 B]
   uint8_t* bb = smem;                                        // [S][U][512 B]  (aliases in_ring / ob)
-  constexpr int FWD_BYTES = S * STAGE + 2 * OBR * 512, BWD_BYTES = S * U * 512;
+  constexpr int FWD_BYTES = S * STAGE + 2 * OBR * 512, BWD_BYTES = LW_SB * U * 512;
   float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][2][L+1]
   const int part_set = 2 * (L + 1);
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
   const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
   const uint32_t in_a = smem_u32(in_ring), ob_a = smem_u32(ob), bb_a = smem_u32(bb);
   if (lane == 0) {
-    for (int s = 0; s < 2 * S; ++s) mbar_init(bar_in + 8 * s, 1);
+    for (int s = 0; s < S + LW_SB; ++s) mbar_init(bar_in + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
       auto issue_bb = [&](int j) {  // j-th group of the upward sweep = forward group NG-1-j
         if (j < NG) {
           const int k = NG - 1 - j;
-          const uint32_t st = (n_bb + (uint32_t)j) % S;
+          const uint32_t st = (n_bb + (uint32_t)j) % LW_SB;
           const uint32_t bytes = (uint32_t)min(U, L - k * U) * 512u;
           if (elect_one()) {
             mbar_expect_tx(bar_bb + 8 * st, bytes);
@@ -423,15 +432,15 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
         }
       };
 #pragma unroll
-      for (int j = 0; j < S - 1; ++j) issue_bb(j);
+      for (int j = 0; j < LW_SB - 1; ++j) issue_bb(j);
       auto backward_group = [&](int j, auto tail_c) {
         constexpr bool TAIL = decltype(tail_c)::value;
         __syncwarp();
-        issue_bb(j + S - 1);
+        issue_bb(j + LW_SB - 1);
         const int k = NG - 1 - j;
         const uint32_t nj = n_bb + (uint32_t)j;
-        const uint32_t st = nj % S;
-        mbar_wait(bar_bb + 8 * st, (nj / S) & 1u);
+        const uint32_t st = nj % LW_SB;
+        mbar_wait(bar_bb + 8 * st, (nj / LW_SB) & 1u);
         const uint8_t* bt = bb + st * (U * 512) + lane_bf;
         const int nvalid = TAIL ? min(U, L - k * U) : U;
         discard_scratch(scratch + (size_t)k * (U * 512), (uint32_t)nvalid * 512u, lane);
@@ -643,14 +652,14 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
   constexpr int OBR = SW_OBR, NOB = U / OBR;
   uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][OBR][768 B]
   uint8_t* bb = smem;                                          // [S][U][768 B]  (aliases in_ring / ob, see lw_solver_v5)
-  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * OBR * SWROW, BWD_BYTES = S * U * SWROW;
+  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * OBR * SWROW, BWD_BYTES = SW_SB * U * SWROW;
   float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][3][L+1]
   const int part_set = 3 * (L + 1) + ((L + 1) & 1);            // keep the barriers 8-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
   const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
   const uint32_t in_a = smem_u32(in_ring), ob_a = smem_u32(ob), bb_a = smem_u32(bb);
   if (lane == 0) {
-    for (int s = 0; s < 2 * S; ++s) mbar_init(bar_in + 8 * s, 1);
+    for (int s = 0; s < S + SW_SB; ++s) mbar_init(bar_in + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -827,7 +836,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
     auto issue_bb = [&](int j) {
       if (j < NG) {
         const int k = NG - 1 - j;
-        const uint32_t st = (n_bb + (uint32_t)j) % S;
+        const uint32_t st = (n_bb + (uint32_t)j) % SW_SB;
         const uint32_t bytes = (uint32_t)min(U, L - k * U) * SWROW;
         if (elect_one()) {
           mbar_expect_tx(bar_bb + 8 * st, bytes);
@@ -837,15 +846,15 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
       }
     };
 #pragma unroll
-    for (int j = 0; j < S - 1; ++j) issue_bb(j);
+    for (int j = 0; j < SW_SB - 1; ++j) issue_bb(j);
     auto backward_group = [&](int j, auto tail_c) {
       constexpr bool TAIL = decltype(tail_c)::value;
       __syncwarp();
-      issue_bb(j + S - 1);
+      issue_bb(j + SW_SB - 1);
       const int k = NG - 1 - j;
       const uint32_t nj = n_bb + (uint32_t)j;
-      const uint32_t st = nj % S;
-      mbar_wait(bar_bb + 8 * st, (nj / S) & 1u);
+      const uint32_t st = nj % SW_SB;
+      mbar_wait(bar_bb + 8 * st, (nj / SW_SB) & 1u);
       const uint8_t* bt = bb + st * (U * SWROW);
       const int nvalid = TAIL ? min(U, L - k * U) : U;
       discard_scratch(scratch + (size_t)k * (U * SWROW), (uint32_t)nvalid * SWROW, lane);
@@ -1015,7 +1024,7 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
     tm_bl = tm_tau; tm_bv = tm_tau;
     stage = (size_t)3 * U * 256;
   }
-  const size_t smem = std::max<size_t>((size_t)S * stage + 2 * v5::LW_OBR * 512, (size_t)S * U * 512) + 4 * (size_t)(L + 1) * 4 + 2 * S * 8;
+  const size_t smem = std::max<size_t>((size_t)S * stage + 2 * v5::LW_OBR * 512, (size_t)v5::LW_SB * U * 512) + 4 * (size_t)(L + 1) * 4 + (S + v5::LW_SB) * 8;
   const size_t per_cta = (size_t)L * 512;
 #define LW5(F, T, D, C) launch_clustered(ctx, v5::lw_solver_v5<F, T, D, C>, csize, smem, per_cta, 160, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv)
 #define LW5C(F, T, D) (compact ? LW5(F, T, D, true) : LW5(F, T, D, false))
@@ -1049,8 +1058,8 @@ int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, v5::SW_U)) return rc; }
   else tm_g = tm_ssa;
   const int nin = p.g ? 3 : 2;
-  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_OBR * v5::SWROW, (size_t)v5::SW_S * v5::SW_U * v5::SWROW) +
-                      2 * (size_t)(3 * (L + 1) + 1) * 4 + 2 * v5::SW_S * 8;
+  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_OBR * v5::SWROW, (size_t)v5::SW_SB * v5::SW_U * v5::SWROW) +
+                      2 * (size_t)(3 * (L + 1) + 1) * 4 + (v5::SW_S + v5::SW_SB) * 8;
   const size_t per_cta = (size_t)L * v5::SWROW;
   const bool top = p.top_at_1 != 0;
 #define SW5(F, HG, T) launch_clustered(ctx, v5::sw_solver_v5<F, HG, T>, csize, smem, per_cta, 250, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
