@@ -141,6 +141,64 @@ module mo_rrnn_c_binding
       real(c_float)         :: flux_up(nlay+1, *), flux_dn(nlay+1, *), flux_dn_dir(nlay+1, *)
       integer(c_int)        :: rc
     end function
+    ! rte_lw for _2str clouds (re-scaled solution), lw_Ds, flux_up_Jac, g-point fluxes  (rte/mo_rte_lw.F90:60-64, 324-384);
+    ! device pointers, c_null_ptr for absent optional arguments
+    function rrnn_rte_lw_ext(ctx, kd, nlay, ncol, top_at_1, n_gauss_angles, inc_flux, tau, ssa, g, lay_source, lev_source, &
+                             sfc_source, sfc_emis, lw_Ds, sfc_source_Jac, flux_up, flux_dn, flux_up_Jac, gpt_flux_up, &
+                             gpt_flux_dn) bind(C, name="rrnn_rte_lw_ext") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, kd
+      integer(c_int), value :: nlay, ncol, top_at_1, n_gauss_angles
+      type(c_ptr),    value :: inc_flux, tau, ssa, g, lay_source, lev_source, sfc_source, sfc_emis, lw_Ds, sfc_source_Jac
+      type(c_ptr),    value :: flux_up, flux_dn, flux_up_Jac, gpt_flux_up, gpt_flux_dn
+      integer(c_int)        :: rc
+    end function
+    ! rte_lw(..., use_2stream = .true.)  (rte/mo_rte_lw.F90:346-361, lw_solver_2stream)
+    function rrnn_rte_lw_2stream(ctx, kd, nlay, ncol, top_at_1, inc_flux, tau, ssa, g, lev_source, sfc_source, sfc_emis, &
+                                 flux_up, flux_dn, gpt_flux_up, gpt_flux_dn) bind(C, name="rrnn_rte_lw_2stream") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, kd
+      integer(c_int), value :: nlay, ncol, top_at_1
+      type(c_ptr),    value :: inc_flux, tau, ssa, g, lev_source, sfc_source, sfc_emis, flux_up, flux_dn, gpt_flux_up, gpt_flux_dn
+      integer(c_int)        :: rc
+    end function
+    ! sw_solver_2stream with g-point fluxes  (rte/kernels/mo_rte_solver_kernels.F90:541-546)
+    function rrnn_sw_solver_2stream_ext(ctx, ngpt, nlay, ncol, top_at_1, inc_flux, inc_flux_dif, tau, ssa, g, mu0, sfc_alb_dir, &
+                                        sfc_alb_dif, flux_up, flux_dn, flux_dir, gpt_flux_up, gpt_flux_dn, gpt_flux_dir) &
+                                        bind(C, name="rrnn_sw_solver_2stream_ext") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx
+      integer(c_int), value :: ngpt, nlay, ncol, top_at_1
+      type(c_ptr),    value :: inc_flux, inc_flux_dif, tau, ssa, g, mu0, sfc_alb_dir, sfc_alb_dif
+      type(c_ptr),    value :: flux_up, flux_dn, flux_dir, gpt_flux_up, gpt_flux_dn, gpt_flux_dir
+      integer(c_int)        :: rc
+    end function
+    ! cloud_optics (LUT or Pade handle)  (extensions/cloud_optics/mo_cloud_optics.F90:354-535)
+    function rrnn_cloud_optics(ctx, lut, ncol, nlay, clwp, ciwp, reliq, reice, tau, ssa, g) bind(C, name="rrnn_cloud_optics") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, lut
+      integer(c_int), value :: ncol, nlay
+      type(c_ptr),    value :: clwp, ciwp, reliq, reice, tau, ssa, g
+      integer(c_int)        :: rc
+    end function
+    ! sampled_mask_max_ran / sampled_mask_exp_ran (overlap_param = c_null_ptr: maximum-random), draw_samples
+    ! (extensions/cloud_optics/mo_cloud_sampling.F90:38-286); the mask is one byte per element, (ngpt,nlay,ncol)
+    function rrnn_sampled_mask(ctx, ngpt, nlay, ncol, randoms, cloud_frac, overlap_param, cloud_mask) &
+                               bind(C, name="rrnn_sampled_mask") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx
+      integer(c_int), value :: ngpt, nlay, ncol
+      type(c_ptr),    value :: randoms, cloud_frac, overlap_param, cloud_mask
+      integer(c_int)        :: rc
+    end function
+    function rrnn_draw_samples(ctx, kd, nlay, ncol, cloud_mask, tau_bnd, ssa_bnd, g_bnd, tau_gpt, ssa_gpt, g_gpt) &
+                               bind(C, name="rrnn_draw_samples") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, kd
+      integer(c_int), value :: nlay, ncol
+      type(c_ptr),    value :: cloud_mask, tau_bnd, ssa_bnd, g_bnd, tau_gpt, ssa_gpt, g_gpt
+      integer(c_int)        :: rc
+    end function
     ! compute_heating_rate  (extensions/mo_heating_rates.F90:26-54)
     function rrnn_heating_rate(ctx, ncol, nlay, flux_up, flux_dn, plev, heating_rate) bind(C, name="rrnn_heating_rate") result(rc)
       import :: c_int, c_ptr
