@@ -25,6 +25,12 @@ LW_NETS = ("lw-g256-2018-12-04_absorption_58_58.nc", "lw-g256-2018-12-04_planck_
 SW_NETS = ("sw-g224-2018-12-04-absorption_16_16.nc", "sw-g224-2018-12-04-rayleigh_16_16.nc")
 
 
+def _ok(error_msg):
+    """stop_on_err of the reference drivers (mo_rrtmgp_clr_all_sky / the drivers' own copies): an error message aborts."""
+    if error_msg != "":
+        raise RuntimeError(error_msg)
+
+
 def _nets(ctx, files):
     return [api.rrtmgp_network_type(ctx).load_netcdf(os.path.join(NN_DIR, f)) for f in files]
 
@@ -139,38 +145,37 @@ def rrtmgp_allsky(ncol, nloops=1, band="lw", ctx=None, use_pade=False, out_path=
     nets = _nets(ctx, LW_NETS if lw else SW_NETS)
     coef = os.path.join(ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc")
     co = api.ty_cloud_optics(ctx)
-    err = co.load_pade(**api.load_cloud_pade_file(coef)) if use_pade else co.load(**api.load_cloud_lut_file(coef))
-    assert err == "", err
+    _ok(co.load_pade(**api.load_cloud_pade_file(coef)) if use_pade else co.load(**api.load_cloud_lut_file(coef)))
     cl = allsky_clouds(atm, co)
     gc = api.ty_gas_concs()
     for k, v in atm["gases"].items():
         gc.set_vmr(k, v)
     mk = lambda: torch.zeros((ncol, nlay + 1), device="cuda")
     if lw:
-        atmos = api.ty_optical_props_1scl(); assert atmos.alloc_1scl(ncol, nlay, k_dist) == ""
-        clouds = api.ty_optical_props_1scl(); assert clouds.alloc_1scl(ncol, nlay, k_dist, by_band=True) == ""
-        src = api.ty_source_func_lw(); assert src.alloc(ncol, nlay, k_dist) == ""
+        atmos = api.ty_optical_props_1scl(); _ok(atmos.alloc_1scl(ncol, nlay, k_dist))
+        clouds = api.ty_optical_props_1scl(); _ok(clouds.alloc_1scl(ncol, nlay, k_dist, by_band=True))
+        src = api.ty_source_func_lw(); _ok(src.alloc(ncol, nlay, k_dist))
         t_sfc = atm["tlev"][:, nlay if atm["top_at_1"] else 0].copy()
         emis = np.full((ncol, k_dist.nband), 0.98, np.float32)
         fl = api.ty_fluxes_broadband(mk(), mk())
     else:
-        atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(ncol, nlay, k_dist) == ""
-        clouds = api.ty_optical_props_2str(); assert clouds.alloc_2str(ncol, nlay, k_dist, by_band=True) == ""
+        atmos = api.ty_optical_props_2str(); _ok(atmos.alloc_2str(ncol, nlay, k_dist))
+        clouds = api.ty_optical_props_2str(); _ok(clouds.alloc_2str(ncol, nlay, k_dist, by_band=True))
         toa = torch.empty((ncol, k_dist.ngpt), device="cuda")
         alb = np.full((ncol, k_dist.ngpt), 0.06, np.float32)
         mu0 = np.full(ncol, 0.86, np.float32)
         fl = api.ty_fluxes_broadband(mk(), mk(), None, mk())
     for _ in range(nloops):  # :366-446
-        assert co.cloud_optics(cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], clouds) == ""
+        _ok(co.cloud_optics(cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], clouds))
         if lw:
-            assert k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], t_sfc, gc, atmos, src, tlev=atm["tlev"], neural_nets=nets) == ""
-            assert clouds.increment(atmos) == ""
-            assert api.rte_lw(atmos, atm["top_at_1"], src, emis, fl) == ""
+            _ok(k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], t_sfc, gc, atmos, src, tlev=atm["tlev"], neural_nets=nets))
+            _ok(clouds.increment(atmos))
+            _ok(api.rte_lw(atmos, atm["top_at_1"], src, emis, fl))
         else:
-            assert k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], gc, atmos, toa, neural_nets=nets) == ""
-            assert clouds.delta_scale() == ""
-            assert clouds.increment(atmos) == ""
-            assert api.rte_sw(atmos, atm["top_at_1"], mu0, toa, alb, alb, fl) == ""
+            _ok(k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], gc, atmos, toa, neural_nets=nets))
+            _ok(clouds.delta_scale())
+            _ok(clouds.increment(atmos))
+            _ok(api.rte_sw(atmos, atm["top_at_1"], mu0, toa, alb, alb, fl))
     out = [fl.flux_up.cpu().numpy(), fl.flux_dn.cpu().numpy()] + ([] if lw else [fl.flux_dn_dir.cpu().numpy()])
     if out_path:
         write_allsky_fluxes(out_path, ("lw_flux_up", "lw_flux_dn") if lw else ("sw_flux_up", "sw_flux_dn", "sw_flux_dir"), out)
