@@ -73,6 +73,62 @@ module mo_rrnn_c_binding
       real(c_float), value :: tsi
       integer(c_int)       :: rc
     end function
+    ! load_ext's solar tables (rrtmgp/mo_gas_optics_rrtmgp.F90:1317-1325) and set_solar_variability (:1058-1095)
+    function rrnn_kdist_set_solar_tables(kd, solar_quiet, solar_facular, solar_sunspot) &
+                                         bind(C, name="rrnn_kdist_set_solar_tables") result(rc)
+      import :: c_int, c_ptr, c_float
+      type(c_ptr),   value :: kd
+      real(c_float)        :: solar_quiet(*), solar_facular(*), solar_sunspot(*)
+      integer(c_int)       :: rc
+    end function
+    function rrnn_kdist_set_solar_variability(kd, mg_index, sb_index, have_tsi, tsi) &
+                                              bind(C, name="rrnn_kdist_set_solar_variability") result(rc)
+      import :: c_int, c_ptr, c_float
+      type(c_ptr),    value :: kd
+      real(c_float),  value :: mg_index, sb_index, tsi
+      integer(c_int), value :: have_tsi
+      integer(c_int)        :: rc
+    end function
+    function rrnn_kdist_get_solar_source(kd, solar_source) bind(C, name="rrnn_kdist_get_solar_source") result(rc)
+      import :: c_int, c_ptr, c_float
+      type(c_ptr),   value :: kd
+      real(c_float)        :: solar_source(*)
+      integer(c_int)       :: rc
+    end function
+    ! optimal_angle_fit(2,nbnd) of load (:1163, 1210) and compute_optimal_angles (:1712-1758); device pointers
+    function rrnn_kdist_set_optimal_angle_fit(kd, optimal_angle_fit) bind(C, name="rrnn_kdist_set_optimal_angle_fit") result(rc)
+      import :: c_int, c_ptr, c_float
+      type(c_ptr),   value :: kd
+      real(c_float)        :: optimal_angle_fit(2,*)
+      integer(c_int)       :: rc
+    end function
+    function rrnn_compute_optimal_angles(ctx, kd, nlay, ncol, tau, optimal_angles) &
+                                         bind(C, name="rrnn_compute_optimal_angles") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, kd, tau, optimal_angles
+      integer(c_int), value :: nlay, ncol
+      integer(c_int)        :: rc
+    end function
+    ! ty_fluxes_byband%reduce (extensions/mo_fluxes_byband.F90:41-131): sum_byband, net_byband_full, net_*_precalc
+    function rrnn_sum_byband(ctx, kd, nlev, ncol, gpt_flux, bnd_flux) bind(C, name="rrnn_sum_byband") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, kd, gpt_flux, bnd_flux
+      integer(c_int), value :: nlev, ncol
+      integer(c_int)        :: rc
+    end function
+    function rrnn_net_byband(ctx, kd, nlev, ncol, gpt_flux_dn, gpt_flux_up, bnd_flux_net) &
+                             bind(C, name="rrnn_net_byband") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr),    value :: ctx, kd, gpt_flux_dn, gpt_flux_up, bnd_flux_net
+      integer(c_int), value :: nlev, ncol
+      integer(c_int)        :: rc
+    end function
+    function rrnn_net_flux(ctx, n, flux_dn, flux_up, flux_net) bind(C, name="rrnn_net_flux") result(rc)
+      import :: c_int, c_ptr, c_size_t
+      type(c_ptr),       value :: ctx, flux_dn, flux_up, flux_net
+      integer(c_size_t), value :: n
+      integer(c_int)           :: rc
+    end function
     ! gas_optics (LW), neural_nets present  (rrtmgp/mo_gas_optics_rrtmgp.F90:239-243, NN branch :368-411)
     function rrnn_gas_optics_lw(ctx, kd, models, nmodels, ncol, nlay, play, plev, tlay, tsfc, gases, ngas, tlev, &
                                 tau, lay_source, lev_source, sfc_source, sfc_source_Jac) &

@@ -101,6 +101,22 @@ RRNN_API int rrnn_kdist_create(rrnn_ctx_t* ctx, int nbnd, int ngpt, const int* b
 RRNN_API int rrnn_kdist_destroy(rrnn_kdist_t* kd);
 /* ty_gas_optics_rrtmgp%set_tsi, rrtmgp/mo_gas_optics_rrtmgp.F90:1097-1120 */
 RRNN_API int rrnn_kdist_set_tsi(rrnn_kdist_t* kd, float tsi);
+/* The optional solar tables of ty_gas_optics_rrtmgp%load (load_ext, rrtmgp/mo_gas_optics_rrtmgp.F90:1317-1325):
+ * solar_source_quiet / _facular / _sunspot, HOST arrays of ngpt entries. */
+RRNN_API int rrnn_kdist_set_solar_tables(rrnn_kdist_t* kd, const float* solar_quiet, const float* solar_facular,
+                                         const float* solar_sunspot);
+/* ty_gas_optics_rrtmgp%set_solar_variability, rrtmgp/mo_gas_optics_rrtmgp.F90:1058-1095: solar_source = quiet +
+ * (mg_index - 0.1495954) facular + (sb_index - 0.00066696) sunspot, then set_tsi(tsi) when have_tsi != 0. */
+RRNN_API int rrnn_kdist_set_solar_variability(rrnn_kdist_t* kd, float mg_index, float sb_index, int have_tsi, float tsi);
+/* Host copy of the current solar source (ngpt). */
+RRNN_API int rrnn_kdist_get_solar_source(const rrnn_kdist_t* kd, float* solar_source_out);
+/* optimal_angle_fit (2,nbnd) of ty_gas_optics_rrtmgp%load (:1163, 1210), a HOST array == C [nbnd][2]. */
+RRNN_API int rrnn_kdist_set_optimal_angle_fit(rrnn_kdist_t* kd, const float* optimal_angle_fit);
+/* ty_gas_optics_rrtmgp%compute_optimal_angles, rrtmgp/mo_gas_optics_rrtmgp.F90:1712-1758: secant per column and g-point
+ * from the column transmissivity, fit(1,bnd) exp(-sum_lay tau) + fit(2,bnd).  tau_d (ngpt,nlay,ncol); optimal_angles_d
+ * (ngpt,ncol) -- the layout rte_lw's lw_Ds takes here (the reference declares (ncol,ngpt), a stale upstream order). */
+RRNN_API int rrnn_compute_optimal_angles(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, const float* tau_d,
+                                         float* optimal_angles_d);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* Gas optics building blocks (device pointers)                                                       */
@@ -269,6 +285,17 @@ RRNN_API int rrnn_heating_rate(rrnn_ctx_t* ctx, int ncol, int nlay, const float*
                                const float* plev_d, float* heating_rate_d);
 RRNN_API int rrnn_calc_heating_rate(rrnn_ctx_t* ctx, int ncol, int nlay, const float* flux_up_d, const float* flux_dn_d,
                                     const float* plev_d, float* hr_K_day_d);
+
+/* ty_fluxes_byband%reduce, extensions/mo_fluxes_byband.F90:41-131.  sum_byband (mo_fluxes_byband_kernels.F90:33-51):
+ * g-point fluxes (ngpt,nlev,ncol) -> by-band (nbnd,nlev,ncol), summed in g-point order; net_byband_full (:56-78):
+ * by-band sum of (down - up).  Band limits from kd.  This fork's layout (g-point / band fastest). */
+RRNN_API int rrnn_sum_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlev, int ncol, const float* gpt_flux_d,
+                             float* bnd_flux_d);
+RRNN_API int rrnn_net_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlev, int ncol, const float* gpt_flux_dn_d,
+                             const float* gpt_flux_up_d, float* bnd_flux_net_d);
+/* net = down - up over n elements: net_byband_precalc (mo_fluxes_byband_kernels.F90:80-86) and the broadband flux_net of
+ * ty_fluxes_broadband%reduce (rte/mo_fluxes.F90, net_broadband_precalc). */
+RRNN_API int rrnn_net_flux(rrnn_ctx_t* ctx, size_t n, const float* flux_dn_d, const float* flux_up_d, float* flux_net_d);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* Whole-path drivers with HOST buffers: what one iteration of the reference drivers' block loop does

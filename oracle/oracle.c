@@ -1164,3 +1164,69 @@ ORC_API void orc_calc_heating_rate(int ncol, int nlay, const float* flux_up, con
       hr_K_day[(size_t)icol * nlay + l] = scaling * dF / dP;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * By-band fluxes: extensions/mo_fluxes_byband_kernels.F90.  Restated in this fork's layout (g-point / band
+ * fastest: gpt_flux [ncol][nlev][ngpt] -> bnd_flux [ncol][nlev][nbnd]); the module itself still declares the
+ * upstream (ncol,nlev,ngpt) order.  band_lims is (2,nbnd), 1-based inclusive.
+ *  orc_sum_byband      : sum_byband :33-51 (first g-point, then += in g-point order)
+ *  orc_net_byband_full : net_byband_full :56-78 (net = net + dn - up, left to right)
+ *  orc_net_flux        : net_byband_precalc :80-86 and net_broadband_precalc (flux_net = flux_dn - flux_up)
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_sum_byband(int ncol, int nlev, int ngpt, int nbnd, const int* band_lims, const float* spectral_flux,
+                            float* byband_flux) {
+  for (size_t r = 0; r < (size_t)ncol * nlev; ++r)
+    for (int ibnd = 0; ibnd < nbnd; ++ibnd) {
+      float acc = spectral_flux[r * ngpt + band_lims[2 * ibnd] - 1];
+      for (int igpt = band_lims[2 * ibnd]; igpt <= band_lims[2 * ibnd + 1] - 1; ++igpt) acc = acc + spectral_flux[r * ngpt + igpt];
+      byband_flux[r * nbnd + ibnd] = acc;
+    }
+}
+
+ORC_API void orc_net_byband_full(int ncol, int nlev, int ngpt, int nbnd, const int* band_lims, const float* spectral_flux_dn,
+                                 const float* spectral_flux_up, float* byband_flux_net) {
+  for (size_t r = 0; r < (size_t)ncol * nlev; ++r)
+    for (int ibnd = 0; ibnd < nbnd; ++ibnd) {
+      int igpt = band_lims[2 * ibnd] - 1;
+      float acc = spectral_flux_dn[r * ngpt + igpt] - spectral_flux_up[r * ngpt + igpt];
+      for (igpt = band_lims[2 * ibnd]; igpt <= band_lims[2 * ibnd + 1] - 1; ++igpt)
+        acc = acc + spectral_flux_dn[r * ngpt + igpt] - spectral_flux_up[r * ngpt + igpt];
+      byband_flux_net[r * nbnd + ibnd] = acc;
+    }
+}
+
+ORC_API void orc_net_flux(size_t n, const float* flux_dn, const float* flux_up, float* flux_net) {
+  for (size_t i = 0; i < n; ++i) flux_net[i] = flux_dn[i] - flux_up[i];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * compute_optimal_angles: rrtmgp/mo_gas_optics_rrtmgp.F90:1712-1758.  tau [ncol][nlay][ngpt], gpt2band 0-based,
+ * optimal_angle_fit (2,nbnd) == C [nbnd][2]; output [ncol][ngpt] (the layout rte_lw's lw_Ds takes in this fork).
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_compute_optimal_angles(int ncol, int nlay, int ngpt, const int* gpt2band, const float* optimal_angle_fit,
+                                        const float* tau, float* optimal_angles) {
+  for (int icol = 0; icol < ncol; ++icol)
+    for (int igpt = 0; igpt < ngpt; ++igpt) {
+      float t = 0.0f;
+      for (int ilay = 0; ilay < nlay; ++ilay) t = t + tau[((size_t)icol * nlay + ilay) * ngpt + igpt];
+      const float trans_total = expf(-t);
+      const int bnd = gpt2band[igpt];
+      optimal_angles[(size_t)icol * ngpt + igpt] = optimal_angle_fit[2 * bnd] * trans_total + optimal_angle_fit[2 * bnd + 1];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * set_solar_variability: rrtmgp/mo_gas_optics_rrtmgp.F90:1058-1095, followed by set_tsi :1097-1120 when have_tsi.
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_set_solar_variability(int ngpt, const float* solar_quiet, const float* solar_facular, const float* solar_sunspot,
+                                       float mg_index, float sb_index, int have_tsi, float tsi, float* solar_source) {
+  const float a_offset = 0.1495954f, b_offset = 0.00066696f;
+  for (int igpt = 0; igpt < ngpt; ++igpt)
+    solar_source[igpt] = solar_quiet[igpt] + (mg_index - a_offset) * solar_facular[igpt] + (sb_index - b_offset) * solar_sunspot[igpt];
+  if (have_tsi) {
+    float sum = 0.0f;
+    for (int igpt = 0; igpt < ngpt; ++igpt) sum += solar_source[igpt];
+    const float norm = 1.0f / sum;
+    for (int igpt = 0; igpt < ngpt; ++igpt) solar_source[igpt] = solar_source[igpt] * tsi * norm;
+  }
+}

@@ -457,5 +457,53 @@ def calc_heating_rate(flux_up, flux_dn, plev, fast=False):
     return out
 
 
+def sum_byband(gpt_flux, band_lims, fast=False):
+    """sum_byband (extensions/mo_fluxes_byband_kernels.F90:33-51): (ncol, nlev, ngpt) -> (ncol, nlev, nbnd)."""
+    ncol, nlev, ngpt = np.shape(gpt_flux)
+    f = _a(gpt_flux, fast); bl = np.ascontiguousarray(band_lims, np.int32)
+    out = np.empty((ncol, nlev, len(bl)), _dt(fast))
+    lib(fast).orc_sum_byband(ncol, nlev, ngpt, len(bl), _ip(bl), _p(f), _p(out))
+    return out
+
+
+def net_byband_full(gpt_flux_dn, gpt_flux_up, band_lims, fast=False):
+    """net_byband_full (extensions/mo_fluxes_byband_kernels.F90:56-78)."""
+    ncol, nlev, ngpt = np.shape(gpt_flux_dn)
+    d, u = _a(gpt_flux_dn, fast), _a(gpt_flux_up, fast); bl = np.ascontiguousarray(band_lims, np.int32)
+    out = np.empty((ncol, nlev, len(bl)), _dt(fast))
+    lib(fast).orc_net_byband_full(ncol, nlev, ngpt, len(bl), _ip(bl), _p(d), _p(u), _p(out))
+    return out
+
+
+def net_flux(flux_dn, flux_up, fast=False):
+    """net_byband_precalc / net_broadband_precalc: down - up."""
+    d, u = _a(flux_dn, fast), _a(flux_up, fast)
+    out = np.empty_like(d)
+    lib(fast).orc_net_flux(C.c_size_t(d.size), _p(d), _p(u), _p(out))
+    return out
+
+
+def compute_optimal_angles(tau, band_lims, optimal_angle_fit, fast=False):
+    """compute_optimal_angles (rrtmgp/mo_gas_optics_rrtmgp.F90:1712-1758): tau (ncol, nlay, ngpt), optimal_angle_fit
+    (nbnd, 2) [== Fortran (2, nbnd)] -> (ncol, ngpt)."""
+    ncol, nlay, ngpt = np.shape(tau)
+    t, fit = _a(tau, fast), _a(optimal_angle_fit, fast)
+    g2b = np.zeros(ngpt, np.int32)
+    for b, (s, e) in enumerate(np.asarray(band_lims)):
+        g2b[s - 1:e] = b
+    out = np.empty((ncol, ngpt), _dt(fast))
+    lib(fast).orc_compute_optimal_angles(ncol, nlay, ngpt, _ip(g2b), _p(fit), _p(t), _p(out))
+    return out
+
+
+def set_solar_variability(solar_quiet, solar_facular, solar_sunspot, mg_index, sb_index, tsi=None, fast=False):
+    """set_solar_variability (+ set_tsi when tsi is given), rrtmgp/mo_gas_optics_rrtmgp.F90:1058-1120."""
+    q, f, s = _a(solar_quiet, fast), _a(solar_facular, fast), _a(solar_sunspot, fast)
+    out = np.empty_like(q)
+    lib(fast).orc_set_solar_variability(len(q), _p(q), _p(f), _p(s), _sc(mg_index, fast), _sc(sb_index, fast),
+                                        int(tsi is not None), _sc(0.0 if tsi is None else tsi, fast), _p(out))
+    return out
+
+
 def num_threads(fast=True):
     return int(lib(fast).orc_num_threads())

@@ -66,6 +66,14 @@ _SIGS = {
                                     C.POINTER(vp)]),
     "rrnn_kdist_destroy": (C.c_int, [vp]),
     "rrnn_kdist_set_tsi": (C.c_int, [vp, C.c_float]),
+    "rrnn_kdist_set_solar_tables": (C.c_int, [vp, c_float_p, c_float_p, c_float_p]),
+    "rrnn_kdist_set_solar_variability": (C.c_int, [vp, C.c_float, C.c_float, C.c_int, C.c_float]),
+    "rrnn_kdist_get_solar_source": (C.c_int, [vp, c_float_p]),
+    "rrnn_kdist_set_optimal_angle_fit": (C.c_int, [vp, c_float_p]),
+    "rrnn_compute_optimal_angles": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
+    "rrnn_sum_byband": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),
+    "rrnn_net_byband": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),
+    "rrnn_net_flux": (C.c_int, [vp, C.c_size_t, vp, vp, vp]),
     "rrnn_get_col_dry": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
     "rrnn_interp_tlev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "rrnn_compute_nn_inputs": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.POINTER(rrnn_gas_t), C.c_int, vp]),

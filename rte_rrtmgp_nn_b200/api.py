@@ -261,6 +261,15 @@ class _kdist_handle:
         _lib.check(_lib.lib().rrnn_kdist_create(ctx.h, int(kd["nbnd"]), int(kd["ngpt"]), bl.ctypes.data_as(_lib.c_int_p), ntemp,
                                                 fp(tot_a), float(kd.get("temp_ref_min", 0.0)), float(kd.get("totplnk_delta", 1.0)),
                                                 fp(sol_a), C.byref(self.h)))
+        tabs = [kd.get(k) for k in ("solar_source_quiet", "solar_source_facular", "solar_source_sunspot")]
+        if all(t is not None for t in tabs):   # load_ext, rrtmgp/mo_gas_optics_rrtmgp.F90:1317-1325
+            arrs = [np.ascontiguousarray(t, np.float32) for t in tabs]
+            _lib.check(_lib.lib().rrnn_kdist_set_solar_tables(self.h, *[fp(a) for a in arrs]))
+        if kd.get("optimal_angle_fit") is not None:   # (nbnd, 2) == Fortran optimal_angle_fit(2, nbnd), :1163, 1210
+            fit = np.ascontiguousarray(kd["optimal_angle_fit"], np.float32)
+            if fit.shape != (int(kd["nbnd"]), 2):
+                raise RRNNError("gas_optics%load: optimal_angle_fit must be (nbnd, 2)")
+            _lib.check(_lib.lib().rrnn_kdist_set_optimal_angle_fit(self.h, fp(fit)))
 
     def __del__(self):
         try:
@@ -428,6 +437,112 @@ class ty_fluxes_flexible(ty_fluxes_broadband):
         self.gpt_flux_up, self.gpt_flux_dn, self.gpt_flux_dn_dir = gpt_flux_up, gpt_flux_dn, gpt_flux_dn_dir
 
 
+class ty_fluxes_byband(ty_fluxes_broadband):
+    """ty_fluxes_byband (extensions/mo_fluxes_byband.F90:31-40): broadband fluxes plus, when associated, the by-band fluxes
+    bnd_flux_up / bnd_flux_dn / bnd_flux_net / bnd_flux_dn_dir, (ncol, nlay+1, nband) in this fork's band-fastest layout."""
+
+    def __init__(self, flux_up=None, flux_dn=None, flux_net=None, flux_dn_dir=None, bnd_flux_up=None, bnd_flux_dn=None,
+                 bnd_flux_net=None, bnd_flux_dn_dir=None):
+        super().__init__(flux_up, flux_dn, flux_net, flux_dn_dir)
+        self.bnd_flux_up, self.bnd_flux_dn, self.bnd_flux_net, self.bnd_flux_dn_dir = bnd_flux_up, bnd_flux_dn, bnd_flux_net, bnd_flux_dn_dir
+
+    def _bnd_desired(self):
+        return any(v is not None for v in (self.bnd_flux_up, self.bnd_flux_dn, self.bnd_flux_net, self.bnd_flux_dn_dir))
+
+    def are_desired(self):
+        return self._bnd_desired() or super().are_desired()
+
+    def reduce(self, gpt_flux_up, gpt_flux_dn, spectral_disc, top_at_1, gpt_flux_dn_dir=None):
+        """reduce_byband (:41-131), by-band part: g-point fluxes (ncol, nlay+1, ngpt) on the device -> the associated by-band
+        arrays.  (The broadband part of reduce is done inside the solvers' fused broadband sums.)"""
+        ncol, nlev, ngpt = tuple(gpt_flux_up.shape)
+        nbnd = spectral_disc.get_nband()
+        if tuple(gpt_flux_dn.shape) != (ncol, nlev, ngpt):
+            return "reduce: gpt_flux_dn array incorrectly sized"
+        if gpt_flux_dn_dir is not None and tuple(gpt_flux_dn_dir.shape) != (ncol, nlev, ngpt):
+            return "reduce: gpt_flux_dn_dir array incorrectly sized"
+        if ngpt != spectral_disc.get_ngpt():
+            return "reduce: spectral discretization and g-point flux arrays have differing number of g-points"
+        err = ""
+        for nm in ("bnd_flux_up", "bnd_flux_dn"):
+            v = getattr(self, nm)
+            if v is not None and tuple(v.shape) != (ncol, nlev, nbnd):
+                err = f"reduce: {nm} array incorrectly sized (can't compute net flux either)"
+        if self.bnd_flux_dn_dir is not None and tuple(self.bnd_flux_dn_dir.shape) != (ncol, nlev, nbnd):
+            err = "reduce: bnd_flux_dn_dir array incorrectly sized"
+        if self.bnd_flux_net is not None and tuple(self.bnd_flux_net.shape) != (ncol, nlev, nbnd):
+            err = "reduce: bnd_flux_net array incorrectly sized (can't compute net flux either)"
+        if err:
+            return err
+        if self.bnd_flux_dn_dir is not None and gpt_flux_dn_dir is None:
+            return "reduce: requesting bnd_flux_dn_dir but direct flux hasn't been supplied"
+        kd = getattr(spectral_disc, "_kd", None)
+        if kd is None:
+            return "reduce: spectral discretization carries no band limits"
+        ctx = getattr(spectral_disc, "ctx", None) or default_context()
+        lib = _lib.lib()
+        try:
+            for out, src in ((self.bnd_flux_up, gpt_flux_up), (self.bnd_flux_dn, gpt_flux_dn), (self.bnd_flux_dn_dir, gpt_flux_dn_dir)):
+                if out is not None:
+                    _lib.check(lib.rrnn_sum_byband(ctx.h, kd.h, nlev, ncol, _ptr(src), _ptr(out)))
+            if self.bnd_flux_net is not None:
+                if self.bnd_flux_dn is not None and self.bnd_flux_up is not None:   # net_byband_precalc
+                    _lib.check(lib.rrnn_net_flux(ctx.h, ncol * nlev * nbnd, _ptr(self.bnd_flux_dn), _ptr(self.bnd_flux_up),
+                                                 _ptr(self.bnd_flux_net)))
+                else:                                                               # net_byband_full
+                    _lib.check(lib.rrnn_net_byband(ctx.h, kd.h, nlev, ncol, _ptr(gpt_flux_dn), _ptr(gpt_flux_up),
+                                                   _ptr(self.bnd_flux_net)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+
+def _solve_and_reduce(core, fluxes, optical_props, sw):
+    """Wraps a solver call for the flux types whose outputs the fused broadband kernels do not produce themselves: flux_net
+    (ty_fluxes_broadband%reduce, rte/mo_fluxes.F90: net_broadband_precalc) and ty_fluxes_byband's by-band arrays, which need
+    the g-point fluxes (general kernels) reduced by band afterwards."""
+    byband = isinstance(fluxes, ty_fluxes_byband) and fluxes._bnd_desired()
+    if not byband and fluxes.flux_net is None:
+        return core(fluxes)
+    torch = _torch()
+    ctx = optical_props.ctx
+    ncol, nlev, ngpt = optical_props.get_ncol(), optical_props.get_nlay() + 1, optical_props.ngpt
+    dev = optical_props.tau.device
+
+    def new(*shape):   # temporaries belong to the context's stream (the caching allocator re-uses them in stream order)
+        with torch.cuda.stream(ctx.torch_stream()):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+
+    for nm in ("flux_up", "flux_dn", "flux_net", "flux_dn_dir"):
+        v = getattr(fluxes, nm)
+        if v is not None and tuple(v.shape) != (ncol, nlev):
+            return f"reduce: {nm} array incorrectly sized"
+    pick = lambda v: v if v is not None else new(ncol, nlev)
+    inner = ty_fluxes_flexible(pick(fluxes.flux_up), pick(fluxes.flux_dn), None,
+                               pick(fluxes.flux_dn_dir) if sw else None,
+                               getattr(fluxes, "gpt_flux_up", None), getattr(fluxes, "gpt_flux_dn", None),
+                               getattr(fluxes, "gpt_flux_dn_dir", None))
+    if byband:
+        if inner.gpt_flux_up is None: inner.gpt_flux_up = new(ncol, nlev, ngpt)
+        if inner.gpt_flux_dn is None: inner.gpt_flux_dn = new(ncol, nlev, ngpt)
+        if sw and inner.gpt_flux_dn_dir is None: inner.gpt_flux_dn_dir = new(ncol, nlev, ngpt)
+        if not sw and fluxes.bnd_flux_dn_dir is not None:
+            return "reduce: requesting bnd_flux_dn_dir but direct flux hasn't been supplied"
+    err = core(inner)
+    if err:
+        return err
+    if byband:
+        err = fluxes.reduce(inner.gpt_flux_up, inner.gpt_flux_dn, optical_props, None, inner.gpt_flux_dn_dir if sw else None)
+        if err:
+            return err
+    if fluxes.flux_net is not None:
+        try:
+            _lib.check(_lib.lib().rrnn_net_flux(ctx.h, ncol * nlev, _ptr(inner.flux_dn), _ptr(inner.flux_up), _ptr(fluxes.flux_net)))
+        except RRNNError as e:
+            return str(e)
+    return ""
+
+
 class ty_gas_optics_rrtmgp(ty_optical_props):
     """The NN path of the RRTMGP gas optics.  `load` takes the spectral tables of the k-distribution
     (rte_rrtmgp_nn_b200.spectral.make_kdist / synthetic_kdist_*)."""
@@ -458,6 +573,39 @@ class ty_gas_optics_rrtmgp(ty_optical_props):
     def set_tsi(self, tsi):
         try:
             _lib.check(_lib.lib().rrnn_kdist_set_tsi(self._kd.h, float(tsi)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+    def set_solar_variability(self, mg_index, sb_index, tsi=None):
+        """set_solar_variability (rrtmgp/mo_gas_optics_rrtmgp.F90:1058-1095); needs solar_source_quiet / _facular / _sunspot
+        among the tables given to load()."""
+        try:
+            _lib.check(_lib.lib().rrnn_kdist_set_solar_variability(self._kd.h, float(mg_index), float(sb_index),
+                                                                   int(tsi is not None), float(0.0 if tsi is None else tsi)))
+        except RRNNError as e:
+            return str(e)
+        return ""
+
+    def get_solar_source(self):
+        out = np.empty(self.ngpt, np.float32)
+        _lib.check(_lib.lib().rrnn_kdist_get_solar_source(self._kd.h, out.ctypes.data_as(_lib.c_float_p)))
+        return out
+
+    def gpoints_are_equal(self, other):
+        return self.ngpt == other.get_ngpt() and np.array_equal(self.band2gpt, other.get_band_lims_gpoint())
+
+    def compute_optimal_angles(self, optical_props, optimal_angles):
+        """compute_optimal_angles (rrtmgp/mo_gas_optics_rrtmgp.F90:1712-1758): optimal_angles is a device tensor (ncol, ngpt),
+        the layout rte_lw's lw_Ds takes."""
+        if not self.gpoints_are_equal(optical_props):
+            return "gas_optics%compute_optimal_angles: optical_props has different spectral discretization than gas_optics"
+        ncol, nlay = optical_props.get_ncol(), optical_props.get_nlay()
+        if tuple(optimal_angles.shape) != (ncol, self.ngpt):
+            return "gas_optics%compute_optimal_angles: optimal_angles different dimension (ncol)"
+        try:
+            _lib.check(_lib.lib().rrnn_compute_optimal_angles(self.ctx.h, self._kd.h, nlay, ncol, _ptr(optical_props.tau),
+                                                              _ptr(optimal_angles)))
         except RRNNError as e:
             return str(e)
         return ""
@@ -531,6 +679,9 @@ def rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes, inc_flux=None, n_
     re-scaled solution (:363-384), or lw_solver_2stream with use_2stream=True (:346-361)."""
     if not fluxes.are_desired():
         return "rte_lw: no space allocated for fluxes"
+    if fluxes.flux_net is not None or (isinstance(fluxes, ty_fluxes_byband) and fluxes._bnd_desired()):
+        return _solve_and_reduce(lambda f: rte_lw(optical_props, top_at_1, sources, sfc_emis, f, inc_flux, n_gauss_angles, use_2stream,
+                                                  lw_Ds, flux_up_Jac, flux_dn_Jac), fluxes, optical_props, sw=False)
     two = isinstance(optical_props, ty_optical_props_2str)
     if not two and not isinstance(optical_props, ty_optical_props_1scl):
         return "rte_lw: lw_solver(...ty_optical_props_nstr...) not yet implemented"
@@ -616,6 +767,9 @@ def rte_sw(atmos, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, flu
         return "rte_sw: no space allocated for fluxes"
     if not isinstance(atmos, ty_optical_props_2str):
         return "rte_sw: only ty_optical_props_2str (two-stream) is implemented"
+    if fluxes.flux_net is not None or (isinstance(fluxes, ty_fluxes_byband) and fluxes._bnd_desired()):
+        return _solve_and_reduce(lambda f: rte_sw(atmos, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, f, inc_flux_dif),
+                                 fluxes, atmos, sw=True)
     ctx = atmos.ctx
     ncol, nlay, ngpt = atmos.get_ncol(), atmos.get_nlay(), atmos.ngpt
     mu0, inc_flux = _dev(mu0, ctx), _dev(inc_flux, ctx)

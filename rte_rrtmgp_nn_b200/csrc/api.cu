@@ -593,7 +593,7 @@ extern "C" int rrnn_kdist_create(rrnn_ctx_t* ctx, int nbnd, int ngpt, const int*
 extern "C" int rrnn_kdist_destroy(rrnn_kdist_t* k) {
   if (!k) return 0;
   cudaSetDevice(k->device);
-  cudaFree(k->d_band_lims_gpt); cudaFree(k->d_gpt2band); cudaFree(k->d_totplnk); cudaFree(k->d_solar_source);
+  cudaFree(k->d_band_lims_gpt); cudaFree(k->d_gpt2band); cudaFree(k->d_totplnk); cudaFree(k->d_solar_source); cudaFree(k->d_optimal_angle_fit);
   delete k;
   return 0;
 }

@@ -123,11 +123,14 @@ struct rrnn_kdist {
   std::vector<int> band_lims_gpt;  // [nbnd][2], 1-based inclusive
   std::vector<int> gpt2band;       // [ngpt], 0-based band
   std::vector<float> totplnk, solar_source;
+  std::vector<float> solar_quiet, solar_facular, solar_sunspot;  // set_solar_variability tables (optional)
+  std::vector<float> optimal_angle_fit;                          // (2,nbnd) (optional)
   int device = 0;
   int* d_band_lims_gpt = nullptr;
   int* d_gpt2band = nullptr;
   float* d_totplnk = nullptr;
   float* d_solar_source = nullptr;
+  float* d_optimal_angle_fit = nullptr;
 };
 
 struct rrnn_cloud_lut {

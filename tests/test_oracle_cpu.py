@@ -219,6 +219,34 @@ def test_heating_rates_formulas():
     assert np.allclose(O.heating_rate(up, dn, plev), want_s, rtol=1e-4, atol=1e-8)
 
 
+def test_byband_optimal_angle_and_solar_variability_restatements():
+    """The small reductions either side of the solvers against independent float64 numpy evaluations, plus their defining
+    properties (bands partition the g-points; a transparent column gets fit(1)+fit(2); set_tsi fixes the integral)."""
+    rng = np.random.default_rng(21)
+    bl = np.array([[1, 1], [2, 7], [8, 11], [12, 27]], np.int32)
+    up = rng.uniform(0, 30, size=(3, 6, 27)).astype(np.float32); dn = rng.uniform(0, 30, size=(3, 6, 27)).astype(np.float32)
+    seg = lambda a: np.stack([a[..., s - 1:e].astype(np.float64).sum(-1) for s, e in bl], axis=-1)
+    assert np.allclose(O.sum_byband(up, bl), seg(up), rtol=1e-6)
+    assert np.allclose(O.sum_byband(up, bl, fast="f64"), seg(up), rtol=1e-13)
+    assert np.allclose(O.net_byband_full(dn, up, bl), seg(dn) - seg(up), rtol=0, atol=2e-4)
+    assert np.array_equal(O.net_flux(dn, up), dn - up)
+    assert np.allclose(O.sum_byband(up, bl).sum(-1), up.sum(-1), rtol=1e-6)
+    assert np.array_equal(O.sum_byband(up, bl)[..., 0], up[..., 0])          # a one-g-point band is a copy
+    fit = np.stack([rng.uniform(0.1, 0.4, 4), rng.uniform(1.5, 1.7, 4)], axis=1).astype(np.float32)
+    tau = rng.gamma(0.3, 0.2, size=(3, 9, 27)).astype(np.float32); tau[1] = 0.0
+    g2b = np.concatenate([[b] * (e - s + 1) for b, (s, e) in enumerate(bl)])
+    want = fit[g2b, 0].astype(np.float64) * np.exp(-tau.astype(np.float64).sum(1)) + fit[g2b, 1]
+    assert np.allclose(O.compute_optimal_angles(tau, bl, fit), want, rtol=3e-7)
+    assert np.allclose(O.compute_optimal_angles(tau, bl, fit)[1], fit[g2b, 0] + fit[g2b, 1], rtol=1e-7)
+    q = rng.uniform(1, 9, 27).astype(np.float32); fa = (0.03 * q).astype(np.float32); sp = (-0.2 * q).astype(np.float32)
+    s = O.set_solar_variability(q, fa, sp, 0.1495954, 0.00066696)
+    assert np.allclose(s, q, rtol=1e-7)                                        # the offsets are the quiet sun
+    want = q.astype(np.float64) + (0.16 - 0.1495954) * fa + (0.002 - 0.00066696) * sp
+    assert np.allclose(O.set_solar_variability(q, fa, sp, 0.16, 0.002), want, rtol=3e-7)
+    s = O.set_solar_variability(q, fa, sp, 0.16, 0.002, tsi=1361.0)
+    assert abs(float(s.sum(dtype=np.float64)) - 1361.0) < 1e-2 and np.allclose(s / s.sum(), want / want.sum(), rtol=1e-6)
+
+
 def test_gas_missing_and_profile_modes(cfg):
     """compute_nn_inputs: scalar / per-layer / full concentrations; a missing minor gas counts as zero (:757-759)."""
     atm = synth.make_atmosphere(3, 60, seed=10)

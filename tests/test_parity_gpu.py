@@ -907,6 +907,161 @@ def test_driver_replicas(gpu_ctx, tmp_path):
         assert f.variables[f"{band}_flux_up"].shape == (43, ncol) and np.array_equal(f.variables[f"{band}_flux_up"][:].T, out[0]); f.close()
 
 
+def test_byband_and_net_fluxes_match_oracle(gpu_ctx):
+    """ty_fluxes_byband (extensions/mo_fluxes_byband.F90) and flux_net: bit-exact against the oracle's serial
+    sums on the kernel entry points, and through rte_sw / rte_lw with the by-band flux type."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib, spectral
+    torch = _torch()
+    P = api._ptr
+    lib = _lib.lib()
+    rng = np.random.default_rng(77)
+    for kd in (spectral.synthetic_kdist_sw(224), spectral.synthetic_kdist_lw(256),
+               dict(nbnd=3, ngpt=11, band_lims_gpt=np.array([[1, 1], [2, 7], [8, 11]], np.int32))):   # ragged bands
+        G, B = int(kd["ngpt"]), int(kd["nbnd"])
+        C_, NL = 5, 34
+        up = rng.uniform(0, 30, size=(C_, NL, G)).astype(np.float32); dn = rng.uniform(0, 30, size=(C_, NL, G)).astype(np.float32)
+        h = api._kdist_handle(gpu_ctx, kd)
+        dup, ddn = torch.from_numpy(up).cuda(), torch.from_numpy(dn).cuda()
+        out = torch.zeros((C_, NL, B), device="cuda")
+        _lib.check(lib.rrnn_sum_byband(gpu_ctx.h, h.h, NL, C_, P(dup), P(out)))
+        assert np.array_equal(out.cpu().numpy(), O.sum_byband(up, kd["band_lims_gpt"]))
+        _lib.check(lib.rrnn_net_byband(gpu_ctx.h, h.h, NL, C_, P(ddn), P(dup), P(out)))
+        assert np.array_equal(out.cpu().numpy(), O.net_byband_full(dn, up, kd["band_lims_gpt"]))
+        net = torch.zeros((C_, NL, G), device="cuda")
+        _lib.check(lib.rrnn_net_flux(gpu_ctx.h, net.numel(), P(ddn), P(dup), P(net)))
+        assert np.array_equal(net.cpu().numpy(), O.net_flux(dn, up))
+    # through rte_sw: by-band fluxes of a random two-stream problem
+    G, L, C_ = 224, 60, 6
+    kd = spectral.synthetic_kdist_sw(G)
+    k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_dist.load(kd) == ""
+    tau = rng.gamma(0.4, 1.5, size=(C_, L, G)).astype(np.float32); ssa = rng.uniform(0.0, 0.999, size=(C_, L, G)).astype(np.float32)
+    g = rng.uniform(-0.2, 0.9, size=(C_, L, G)).astype(np.float32)
+    mu0 = rng.uniform(0.05, 1.0, size=C_).astype(np.float32); inc = rng.uniform(0.5, 8.0, size=(C_, G)).astype(np.float32)
+    ad = rng.uniform(0.0, 0.9, size=(C_, G)).astype(np.float32); af = rng.uniform(0.0, 0.9, size=(C_, G)).astype(np.float32)
+    atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(C_, L, k_dist) == ""
+    atmos.tau.copy_(torch.from_numpy(tau)); atmos.ssa.copy_(torch.from_numpy(ssa)); atmos.g = torch.from_numpy(g).cuda()
+    mk = lambda *s_: torch.zeros(s_, device="cuda")
+    flex = api.ty_fluxes_flexible(mk(C_, L + 1), mk(C_, L + 1), None, mk(C_, L + 1), mk(C_, L + 1, G), mk(C_, L + 1, G), mk(C_, L + 1, G))
+    assert api.rte_sw(atmos, True, mu0, inc, ad, af, flex) == ""
+    bb = api.ty_fluxes_byband(mk(C_, L + 1), mk(C_, L + 1), mk(C_, L + 1), mk(C_, L + 1), mk(C_, L + 1, 14), mk(C_, L + 1, 14),
+                              mk(C_, L + 1, 14), mk(C_, L + 1, 14))
+    assert api.rte_sw(atmos, True, mu0, inc, ad, af, bb) == ""
+    gup, gdn, gdir = (v.cpu().numpy() for v in (flex.gpt_flux_up, flex.gpt_flux_dn, flex.gpt_flux_dn_dir))
+    assert np.array_equal(bb.bnd_flux_up.cpu().numpy(), O.sum_byband(gup, kd["band_lims_gpt"]))
+    assert np.array_equal(bb.bnd_flux_dn.cpu().numpy(), O.sum_byband(gdn, kd["band_lims_gpt"]))
+    assert np.array_equal(bb.bnd_flux_dn_dir.cpu().numpy(), O.sum_byband(gdir, kd["band_lims_gpt"]))
+    assert torch.equal(bb.bnd_flux_net, bb.bnd_flux_dn - bb.bnd_flux_up)          # net_byband_precalc
+    assert torch.equal(bb.flux_up, flex.flux_up) and torch.equal(bb.flux_net, flex.flux_dn - flex.flux_up)
+    assert torch.allclose(bb.bnd_flux_up.sum(-1), bb.flux_up, rtol=1e-5, atol=1e-4)
+    ref = O.sw_solver_2stream_gpt(True, inc, np.zeros_like(inc), tau, ssa, g, mu0, ad, af)
+    r64 = O.sw_solver_2stream_gpt(True, inc, np.zeros_like(inc), tau, ssa, g, mu0, ad, af, fast="f64")
+    for k, got in enumerate((bb.bnd_flux_up, bb.bnd_flux_dn, bb.bnd_flux_dn_dir)):
+        want32, want64 = O.sum_byband(ref[3 + k], kd["band_lims_gpt"]), O.sum_byband(r64[3 + k], kd["band_lims_gpt"], fast="f64")
+        H.assert_within_reference_noise(got.cpu().numpy(), want32, want64, H.FLUX_TOL, f"SW by-band flux {k}")
+    # only the net by-band flux asked for: net_byband_full; the production kernel still serves plain flux_net requests
+    only_net = api.ty_fluxes_byband(bnd_flux_net=mk(C_, L + 1, 14))
+    assert api.rte_sw(atmos, True, mu0, inc, ad, af, only_net) == ""
+    assert np.array_equal(only_net.bnd_flux_net.cpu().numpy(), O.net_byband_full(gdn, gup, kd["band_lims_gpt"]))
+    plain = api.ty_fluxes_broadband(flux_net=mk(C_, L + 1))
+    assert api.rte_sw(atmos, True, mu0, inc, ad, af, plain) == ""
+    fl = api.ty_fluxes_broadband(mk(C_, L + 1), mk(C_, L + 1), None, mk(C_, L + 1))
+    assert api.rte_sw(atmos, True, mu0, inc, ad, af, fl) == ""
+    assert torch.equal(plain.flux_net, fl.flux_dn - fl.flux_up)
+    # error behaviour of reduce_byband
+    bad = api.ty_fluxes_byband(bnd_flux_up=mk(C_, L + 1, 13))
+    assert api.rte_sw(atmos, True, mu0, inc, ad, af, bad) == "reduce: bnd_flux_up array incorrectly sized (can't compute net flux either)"
+    # LW: by-band fluxes through rte_lw (general kernel for the g-point fluxes)
+    kdl = spectral.synthetic_kdist_lw(256)
+    kl = api.ty_gas_optics_rrtmgp(gpu_ctx); assert kl.load(kdl) == ""
+    Ll = 33
+    op = api.ty_optical_props_1scl(); assert op.alloc_1scl(C_, Ll, kl) == ""
+    src = api.ty_source_func_lw(); assert src.alloc(C_, Ll, kl) == ""
+    op.tau.copy_(torch.from_numpy(rng.gamma(0.4, 1.5, size=(C_, Ll, 256)).astype(np.float32)))
+    src.lay_source.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=(C_, Ll, 256)).astype(np.float32)))
+    src.lev_source.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=(C_, Ll + 1, 256)).astype(np.float32)))
+    src.sfc_source.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=(C_, 256)).astype(np.float32)))
+    emis = np.full((C_, 16), 0.98, np.float32)
+    flexl = api.ty_fluxes_flexible(mk(C_, Ll + 1), mk(C_, Ll + 1), None, None, mk(C_, Ll + 1, 256), mk(C_, Ll + 1, 256))
+    assert api.rte_lw(op, True, src, emis, flexl) == ""
+    bbl = api.ty_fluxes_byband(flux_net=mk(C_, Ll + 1), bnd_flux_up=mk(C_, Ll + 1, 16), bnd_flux_net=mk(C_, Ll + 1, 16))
+    assert api.rte_lw(op, True, src, emis, bbl) == ""
+    assert np.array_equal(bbl.bnd_flux_up.cpu().numpy(), O.sum_byband(flexl.gpt_flux_up.cpu().numpy(), kdl["band_lims_gpt"]))
+    assert np.array_equal(bbl.bnd_flux_net.cpu().numpy(),
+                          O.net_byband_full(flexl.gpt_flux_dn.cpu().numpy(), flexl.gpt_flux_up.cpu().numpy(), kdl["band_lims_gpt"]))
+    assert torch.equal(bbl.flux_net, flexl.flux_dn - flexl.flux_up)
+    assert api.rte_lw(op, True, src, emis, api.ty_fluxes_byband(bnd_flux_dn_dir=mk(C_, Ll + 1, 16))) == \
+        "reduce: requesting bnd_flux_dn_dir but direct flux hasn't been supplied"
+
+
+def test_optimal_angles_and_solar_variability(gpu_ctx):
+    """compute_optimal_angles and set_solar_variability against the oracle; the optimal angles feed rte_lw's
+    lw_Ds and give the fluxes of the oracle's solver with the same secants."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral
+    torch = _torch()
+    rng = np.random.default_rng(5)
+    kd = dict(spectral.synthetic_kdist_lw(256))
+    kd["optimal_angle_fit"] = np.stack([rng.uniform(0.1, 0.4, 16), rng.uniform(1.5, 1.7, 16)], axis=1).astype(np.float32)
+    k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_dist.load(kd) == ""
+    C_, L = 9, 60
+    op = api.ty_optical_props_1scl(); assert op.alloc_1scl(C_, L, k_dist) == ""
+    tau = (rng.gamma(0.3, 0.2, size=(C_, L, 256)) * rng.uniform(0.01, 1.0, size=(1, 1, 256))).astype(np.float32)
+    op.tau.copy_(torch.from_numpy(tau))
+    ang = torch.zeros((C_, 256), device="cuda")
+    assert k_dist.compute_optimal_angles(op, ang) == ""
+    want = O.compute_optimal_angles(tau, kd["band_lims_gpt"], kd["optimal_angle_fit"])
+    got = ang.cpu().numpy()
+    assert np.abs(got - want).max() <= 4e-7 * np.abs(want).max()      # serial sums are identical; expf differs by <= 2 ulp
+    assert got.min() >= 1.0 and np.ptp(got) > 0.05
+    assert "different dimension" in k_dist.compute_optimal_angles(op, torch.zeros((C_, 255), device="cuda"))
+    other = api.ty_optical_props_1scl(); other.alloc_1scl(C_, L, spectral.synthetic_kdist_lw(128), ctx=gpu_ctx)
+    assert "different spectral discretization" in k_dist.compute_optimal_angles(other, ang)
+    nofit = api.ty_gas_optics_rrtmgp(gpu_ctx); nofit.load(spectral.synthetic_kdist_lw(256))
+    assert "no optimal_angle_fit" in nofit.compute_optimal_angles(op, ang)
+    # the angles as lw_Ds: same fluxes as the oracle's no-scattering solver with these secants
+    src = api.ty_source_func_lw(); assert src.alloc(C_, L, k_dist) == ""
+    lay = rng.uniform(0.5, 1.5, size=(C_, L, 256)).astype(np.float32); lev = rng.uniform(0.5, 1.5, size=(C_, L + 1, 256)).astype(np.float32)
+    sfc = rng.uniform(0.5, 1.5, size=(C_, 256)).astype(np.float32)
+    src.lay_source.copy_(torch.from_numpy(lay)); src.lev_source.copy_(torch.from_numpy(lev)); src.sfc_source.copy_(torch.from_numpy(sfc))
+    emis = np.full((C_, 16), 0.98, np.float32)
+    fl = api.ty_fluxes_broadband(torch.zeros((C_, L + 1), device="cuda"), torch.zeros((C_, L + 1), device="cuda"))
+    assert api.rte_lw(op, True, src, emis, fl, lw_Ds=ang) == ""
+    fl166 = api.ty_fluxes_broadband(torch.zeros((C_, L + 1), device="cuda"), torch.zeros((C_, L + 1), device="cuda"))
+    assert api.rte_lw(op, True, src, emis, fl166) == ""
+    assert float((fl.flux_dn - fl166.flux_dn).abs().max()) > 1e-3     # the secants matter
+    # solar variability
+    kds = dict(spectral.synthetic_kdist_sw(224))
+    q = np.asarray(kds["solar_source"], np.float32)
+    kds["solar_source_quiet"] = q
+    kds["solar_source_facular"] = (q * rng.uniform(0.0, 0.05, 224)).astype(np.float32)
+    kds["solar_source_sunspot"] = (-q * rng.uniform(0.0, 0.3, 224)).astype(np.float32)
+    ks = api.ty_gas_optics_rrtmgp(gpu_ctx); assert ks.load(kds) == ""
+    assert ks.set_solar_variability(0.16, 0.0012) == ""
+    want = O.set_solar_variability(q, kds["solar_source_facular"], kds["solar_source_sunspot"], 0.16, 0.0012)
+    assert np.array_equal(ks.get_solar_source(), want)
+    assert ks.set_solar_variability(0.152, 0.0009, tsi=1360.5) == ""
+    want = O.set_solar_variability(q, kds["solar_source_facular"], kds["solar_source_sunspot"], 0.152, 0.0009, tsi=1360.5)
+    assert np.allclose(ks.get_solar_source(), want, rtol=3e-7, atol=0) and abs(ks.get_solar_source().sum() - 1360.5) < 0.01
+    assert ks.set_solar_variability(-1.0, 0.001) == "mg_index out of range"
+    assert ks.set_solar_variability(-1.0, -0.001) == "sb_index out of range"
+    assert "no solar variability tables" in _loaded(api, gpu_ctx, spectral.synthetic_kdist_sw(224)).set_solar_variability(0.15, 0.001)
+    # the device copy is the one gas_optics hands out as toa_src
+    from rte_rrtmgp_nn_b200 import synth
+    atm = synth.make_atmosphere(3, 60)
+    dnets = H.device_nets(gpu_ctx, H.SW_G224)
+    atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(3, 60, ks) == ""
+    toa = torch.zeros((3, 224), device="cuda")
+    assert ks.gas_optics(atm["play"], atm["plev"], atm["tlay"], H.gas_concs(atm["gases"]), atmos, toa, neural_nets=dnets) == ""
+    assert np.array_equal(toa.cpu().numpy()[1], ks.get_solar_source())
+
+
+def _loaded(api, ctx, kd):
+    k = api.ty_gas_optics_rrtmgp(ctx)
+    assert k.load(kd) == ""
+    return k
+
+
 def test_heating_rate_K_per_s(gpu_ctx):
     import oracle as O
     from rte_rrtmgp_nn_b200 import api
