@@ -9,7 +9,7 @@ C ABI on inputs tiled from a few thousand distinct columns.  Every column is an 
   * the first n0 columns must equal a separate n0-column call bit for bit;
   * a sample of the base columns is checked against the oracle within the stated flux tolerance;
   * boundary conditions hold at every column: no LW flux down at the top, SW flux down at the top = mu0 x sum of the
-    solar source = the direct flux there, direct <= total, night columns zero, everything finite.
+    solar source = the direct flux there, direct <= total, flux_up / flux_dn of night columns zero, everything finite.
 """
 import numpy as np
 import pytest
@@ -90,13 +90,13 @@ def test_clear_sky_lw_sw_at_1M_columns_137_layers(gpu_ctx):
     night = big["mu0"] <= 0
     assert bool((full["lw_dn"][:, 0] == 0).all())
     assert bool((full["lw_up"] > 0).all()) and bool((full["lw_dn"][:, 1:] > 0).all())
-    for k in ("sw_up", "sw_dn", "sw_dir"):
+    for k in ("sw_up", "sw_dn"):   # the drivers zero flux_up / flux_dn of night columns only (rrtmgp_rfmip_sw.F90:458-463)
         assert bool((full[k][night] == 0).all()), k
     day = ~night
     tsi = float(np.asarray(kds["solar_source"], np.float64).sum())
     assert torch.equal(full["sw_dn"][day][:, 0], full["sw_dir"][day][:, 0])
     assert torch.allclose(full["sw_dn"][day][:, 0], big["mu0"][day] * tsi, rtol=2e-5, atol=0)
-    assert bool((full["sw_dir"] <= full["sw_dn"] + 1e-3).all()) and bool((full["sw_up"] >= 0).all())
+    assert bool((full["sw_dir"][day] <= full["sw_dn"][day] + 1e-3).all()) and bool((full["sw_up"] >= 0).all())
     # a sample of the base columns against the oracle (the 1M-column results are these, replicated)
     idx = np.arange(0, n0, n0 // 24)[:24]
     sub = {k: np.ascontiguousarray(v[idx]) for k, v in base.items() if isinstance(v, np.ndarray)}
@@ -113,7 +113,7 @@ def test_clear_sky_lw_sw_at_1M_columns_137_layers(gpu_ctx):
     for fast in (False, "f64"):
         r = O.gas_optics_sw(kds, ons, sub["play"], sub["plev"], sub["tlay"], gases, fast=fast)
         f = [np.array(a) for a in O.rte_sw(True, mu0e, r["toa_src"], alb, alb, r["tau"], r["ssa"], r["g"], fast=fast)]
-        for a in f:
+        for a in f[:2]:
             a[mu0 <= 0] = 0
         outs.append(f)
     for k, w32, w64 in zip(("sw_up", "sw_dn", "sw_dir"), outs[0], outs[1]):
