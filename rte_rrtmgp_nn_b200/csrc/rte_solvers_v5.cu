@@ -57,7 +57,16 @@ namespace v5 {
 constexpr int MAX_WARPS = 4;  // solvers (warps) per CTA
 constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
 constexpr int SW_OBR = (SW_U > 4) ? SW_U / RRNN_V5_SW_NOB : SW_U;
-constexpr int LW_OBR = (LW_U > 4) ? LW_U / 2 : LW_U;
+// layers per store-staging tile of the SW kernel (<= SW_OBR, which stays the batch of the two-stream coefficients)
+#ifndef RRNN_V5_SW_STL
+#define RRNN_V5_SW_STL SW_OBR
+#endif
+constexpr int SW_STL = RRNN_V5_SW_STL;
+static_assert(SW_OBR % SW_STL == 0, "staging tile must divide the coefficient batch");
+#ifndef RRNN_V5_LW_NOB
+#define RRNN_V5_LW_NOB 2
+#endif
+constexpr int LW_OBR = (LW_U > 4) ? LW_U / RRNN_V5_LW_NOB : LW_U;
 // stages of the reverse-sweep (upward) ring: the upward sweep spends only a few hundred cycles per group, less than an L2 /
 // DRAM round trip, so it prefetches as deep as the shared memory of the downward sweep (which it reuses) allows
 constexpr int LW_SB = RRNN_V5_LW_SB, SW_SB = RRNN_V5_SW_SB;
@@ -649,10 +658,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
   uint8_t* in_ring = smem;                                     // [S][NIN][U][256 B]: tau, ssa (, g)
   // store staging: two tiles of OBR layers (groups of 8 layers are staged and stored in two halves: 6 KB less per solver)
-  constexpr int OBR = SW_OBR, NOB = U / OBR;
-  uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][OBR][768 B]
+  constexpr int OBR = SW_OBR, NOB = U / OBR, STL = SW_STL, NST = OBR / STL;
+  uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][STL][768 B]
   uint8_t* bb = smem;                                          // [S][U][768 B]  (aliases in_ring / ob, see lw_solver_v5)
-  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * OBR * SWROW, BWD_BYTES = SW_SB * U * SWROW;
+  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * STL * SWROW, BWD_BYTES = SW_SB * U * SWROW;
   float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][3][L+1]
   const int part_set = 3 * (L + 1) + ((L + 1) & 1);            // keep the barriers 8-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
@@ -777,38 +786,43 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
         }
         f2 Rdif[OBR], Tdif[OBR], Rdir[OBR], Tdir[OBR], Tnos[OBR];
         two_stream2_batch<FAST, HAS_G, OBR>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
-        // staging tile (k*NOB + h) & 1: free once the bulk store issued two tiles ago has read it
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
-        const int slot = (k * NOB + h) & 1;
-        uint8_t* ot = ob + slot * (OBR * SWROW);
+        // staging tiles of STL layers, alternating between two slots: a slot is free once the bulk store issued two tiles
+        // ago has read it
 #pragma unroll
-        for (int uu = 0; uu < OBR; ++uu) {
-          const int u = h * OBR + uu;
-          if (!TAIL || u < nvalid) {  // warp-uniform
-            const f2 s_up = Rdir[uu] * dir;
-            const f2 s_dn = Tdir[uu] * dir;
-            dir = Tnos[uu] * dir;
-            const f2 d = rcp2<FAST>(fnma2(Rdif[uu], alpha, splat2(1.0f)));
-            const f2 e = d * Tdif[uu];
-            const f2 f = d * fma2(Rdif[uu], beta, s_up);
-            sts2(ot + uu * SWROW + lane_al, alpha);  // reflectance of the atmosphere ABOVE this layer: what sweep 2 needs
-            sts22(ot + uu * SWROW + lane_ef, e, f);
-            beta = fma2(e, fma2(alpha, s_up, beta), s_dn);
-            alpha = fma2(Tdif[uu] * e, alpha, Rdif[uu]);
+        for (int t = 0; t < NST; ++t) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const int slot = ((k * NOB + h) * NST + t) & 1;
+          uint8_t* ot = ob + slot * (STL * SWROW);
+#pragma unroll
+          for (int ss = 0; ss < STL; ++ss) {
+            const int uu = t * STL + ss;
+            const int u = h * OBR + uu;
+            if (!TAIL || u < nvalid) {  // warp-uniform
+              const f2 s_up = Rdir[uu] * dir;
+              const f2 s_dn = Tdir[uu] * dir;
+              dir = Tnos[uu] * dir;
+              const f2 d = rcp2<FAST>(fnma2(Rdif[uu], alpha, splat2(1.0f)));
+              const f2 e = d * Tdif[uu];
+              const f2 f = d * fma2(Rdif[uu], beta, s_up);
+              sts2(ot + ss * SWROW + lane_al, alpha);  // reflectance of the atmosphere ABOVE this layer: what sweep 2 needs
+              sts22(ot + ss * SWROW + lane_ef, e, f);
+              beta = fma2(e, fma2(alpha, s_up, beta), s_dn);
+              alpha = fma2(Tdif[uu] * e, alpha, Rdif[uu]);
+            }
+            red[u] = hsum2(dir);
+            red[U + u] = hsum2(beta + dir);
           }
-          red[u] = hsum2(dir);
-          red[U + u] = hsum2(beta + dir);
+          fence_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            const int nrows = min(max(nvalid - (h * OBR + t * STL), 0), STL);
+            if (nrows > 0)
+              bulk_store(scratch + ((size_t)k * U + h * OBR + t * STL) * SWROW, ob_a + slot * (STL * SWROW), (uint32_t)nrows * SWROW, pol_buf);
+            bulk_commit();
+          }
+          __syncwarp();
         }
-        fence_async_smem();
-        __syncwarp();
-        if (elect_one()) {
-          const int nrows = min(max(nvalid - h * OBR, 0), OBR);
-          if (nrows > 0)
-            bulk_store(scratch + ((size_t)k * U + h * OBR) * SWROW, ob_a + slot * (OBR * SWROW), (uint32_t)nrows * SWROW, pol_buf);
-          bulk_commit();
-        }
-        __syncwarp();
       }
 #pragma unroll
       for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
@@ -1058,7 +1072,7 @@ int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, v5::SW_U)) return rc; }
   else tm_g = tm_ssa;
   const int nin = p.g ? 3 : 2;
-  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_OBR * v5::SWROW, (size_t)v5::SW_SB * v5::SW_U * v5::SWROW) +
+  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_STL * v5::SWROW, (size_t)v5::SW_SB * v5::SW_U * v5::SWROW) +
                       2 * (size_t)(3 * (L + 1) + 1) * 4 + (v5::SW_S + v5::SW_SB) * 8;
   const size_t per_cta = (size_t)L * v5::SWROW;
   const bool top = p.top_at_1 != 0;
