@@ -12,9 +12,19 @@
 
 namespace rrnn {
 
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  // not volatile: the arrays are read-only here, so the compiler may hoist the loads of an unrolled loop ahead of the serial sums
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // one thread per (column-level row, band).  The 16 (or so) g-points of a band are 64 contiguous bytes: a warp covers
 // 32 consecutive bands = 2 KB of the row-major g-point array, every fetched sector is used.
-template <bool NET>
+// VEC: every band starts at a multiple of 4 g-points and holds a multiple of 4 (checked on the host, with ngpt % 4 == 0 and
+// 16-byte aligned arrays): 16-byte loads, a quarter of the load instructions and L1 wavefronts.  The additions keep the
+// g-point order either way.
+template <bool NET, bool VEC>
 __global__ void __launch_bounds__(256) byband_kernel(size_t nrow, int ngpt, int nbnd, const int* __restrict__ band_lims,
                                                      const float* __restrict__ a, const float* __restrict__ b,
                                                      float* __restrict__ out) {
@@ -24,22 +34,50 @@ __global__ void __launch_bounds__(256) byband_kernel(size_t nrow, int ngpt, int 
   const int bnd = (int)(i - row * nbnd);
   const int g0 = band_lims[2 * bnd] - 1, g1 = band_lims[2 * bnd + 1] - 1;
   const float* pa = a + row * ngpt;
-  if (NET) {
-    const float* pb = b + row * ngpt;  // a = down, b = up
-    float acc = __fsub_rn(pa[g0], pb[g0]);
-    for (int g = g0 + 1; g <= g1; ++g) acc = __fsub_rn(__fadd_rn(acc, pa[g]), pb[g]);  // (net + dn) - up, :70-72
-    out[i] = acc;
+  const float* pb = NET ? b + row * ngpt : nullptr;  // a = down, b = up
+  float acc;
+  if (VEC) {
+    float4 x = ld_stream4(pa + g0);
+    if (NET) {
+      float4 y = ld_stream4(pb + g0);
+      acc = __fsub_rn(x.x, y.x);                       // (net + dn) - up, :70-72
+      acc = __fsub_rn(__fadd_rn(acc, x.y), y.y); acc = __fsub_rn(__fadd_rn(acc, x.z), y.z); acc = __fsub_rn(__fadd_rn(acc, x.w), y.w);
+#pragma unroll 4
+      for (int g = g0 + 4; g <= g1; g += 4) {
+        x = ld_stream4(pa + g); y = ld_stream4(pb + g);
+        acc = __fsub_rn(__fadd_rn(acc, x.x), y.x); acc = __fsub_rn(__fadd_rn(acc, x.y), y.y);
+        acc = __fsub_rn(__fadd_rn(acc, x.z), y.z); acc = __fsub_rn(__fadd_rn(acc, x.w), y.w);
+      }
+    } else {
+      acc = __fadd_rn(__fadd_rn(__fadd_rn(x.x, x.y), x.z), x.w);
+#pragma unroll 4
+      for (int g = g0 + 4; g <= g1; g += 4) {
+        x = ld_stream4(pa + g);
+        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, x.x), x.y), x.z), x.w);
+      }
+    }
+  } else if (NET) {
+    acc = __fsub_rn(pa[g0], pb[g0]);
+    for (int g = g0 + 1; g <= g1; ++g) acc = __fsub_rn(__fadd_rn(acc, pa[g]), pb[g]);
   } else {
-    float acc = pa[g0];
+    acc = pa[g0];
     for (int g = g0 + 1; g <= g1; ++g) acc = __fadd_rn(acc, pa[g]);
-    out[i] = acc;
   }
+  out[i] = acc;
 }
 
 __global__ void __launch_bounds__(256) net_flux_kernel(size_t n, const float* __restrict__ dn, const float* __restrict__ up,
                                                        float* __restrict__ net) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) net[i] = dn[i] - up[i];
+}
+
+__global__ void __launch_bounds__(256) net_flux4_kernel(size_t n4, const float* __restrict__ dn, const float* __restrict__ up,
+                                                        float* __restrict__ net) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 d = ld_stream4(dn + 4 * i), u = ld_stream4(up + 4 * i);
+  reinterpret_cast<float4*>(net)[i] = make_float4(d.x - u.x, d.y - u.y, d.z - u.z, d.w - u.w);
 }
 
 // one thread per (column, g-point); consecutive lanes = consecutive g-points, so every layer is one coalesced row.
@@ -60,6 +98,18 @@ __global__ void __launch_bounds__(256) optimal_angles_kernel(int ncol, int nlay,
 
 static inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// 16-byte loads are possible when every band is a whole number of aligned 4-g-point groups
+static bool bands_vectorise(const rrnn_kdist_t* kd) {
+  if (kd->ngpt & 3) return false;
+  for (int b = 0; b < kd->nbnd; ++b) {
+    const int s0 = kd->band_lims_gpt[2 * b] - 1, n = kd->band_lims_gpt[2 * b + 1] - s0;
+    if ((s0 & 3) || (n & 3)) return false;
+  }
+  return true;
+}
+
 }  // namespace rrnn
 using namespace rrnn;
 
@@ -70,8 +120,12 @@ extern "C" int rrnn_sum_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlev
   if (ncol <= 0 || nlev <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const size_t nrow = (size_t)ncol * nlev;
-  byband_kernel<false><<<nblk(nrow * kd->nbnd), 256, 0, ctx->stream>>>(nrow, kd->ngpt, kd->nbnd, kd->d_band_lims_gpt, gpt_flux_d,
-                                                                      nullptr, bnd_flux_d);
+  if (bands_vectorise(kd) && aligned16(gpt_flux_d))
+    byband_kernel<false, true><<<nblk(nrow * kd->nbnd), 256, 0, ctx->stream>>>(nrow, kd->ngpt, kd->nbnd, kd->d_band_lims_gpt,
+                                                                              gpt_flux_d, nullptr, bnd_flux_d);
+  else
+    byband_kernel<false, false><<<nblk(nrow * kd->nbnd), 256, 0, ctx->stream>>>(nrow, kd->ngpt, kd->nbnd, kd->d_band_lims_gpt,
+                                                                               gpt_flux_d, nullptr, bnd_flux_d);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -83,8 +137,12 @@ extern "C" int rrnn_net_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlev
   if (ncol <= 0 || nlev <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const size_t nrow = (size_t)ncol * nlev;
-  byband_kernel<true><<<nblk(nrow * kd->nbnd), 256, 0, ctx->stream>>>(nrow, kd->ngpt, kd->nbnd, kd->d_band_lims_gpt, gpt_flux_dn_d,
-                                                                     gpt_flux_up_d, bnd_flux_net_d);
+  if (bands_vectorise(kd) && aligned16(gpt_flux_dn_d) && aligned16(gpt_flux_up_d))
+    byband_kernel<true, true><<<nblk(nrow * kd->nbnd), 256, 0, ctx->stream>>>(nrow, kd->ngpt, kd->nbnd, kd->d_band_lims_gpt,
+                                                                             gpt_flux_dn_d, gpt_flux_up_d, bnd_flux_net_d);
+  else
+    byband_kernel<true, false><<<nblk(nrow * kd->nbnd), 256, 0, ctx->stream>>>(nrow, kd->ngpt, kd->nbnd, kd->d_band_lims_gpt,
+                                                                              gpt_flux_dn_d, gpt_flux_up_d, bnd_flux_net_d);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -94,7 +152,10 @@ extern "C" int rrnn_net_flux(rrnn_ctx_t* ctx, size_t n, const float* flux_dn_d, 
   RRNN_CHECK(flux_dn_d && flux_up_d && flux_net_d, "reduce: null array");
   if (n == 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
-  net_flux_kernel<<<nblk(n), 256, 0, ctx->stream>>>(n, flux_dn_d, flux_up_d, flux_net_d);
+  if (!(n & 3) && aligned16(flux_dn_d) && aligned16(flux_up_d) && aligned16(flux_net_d))
+    net_flux4_kernel<<<nblk(n / 4), 256, 0, ctx->stream>>>(n / 4, flux_dn_d, flux_up_d, flux_net_d);
+  else
+    net_flux_kernel<<<nblk(n), 256, 0, ctx->stream>>>(n, flux_dn_d, flux_up_d, flux_net_d);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }
