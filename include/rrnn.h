@@ -4,7 +4,7 @@
  * Drop-in boundary for the reference's NN gas optics + RTE flux solvers.  Every entry point cites the
  * reference interface it replaces (paths relative to the reference tree).  The reference's own C seam
  * is the bind(C) kernel layer (rte/kernels/mo_rte_solver_kernels.F90:125,546,1530); the type-bound
- * Fortran procedures above it are mirrored by fortran/*.F90 (ISO_C_BINDING veneer) and by the Python
+ * Fortran procedures above it are mirrored by the .F90 files under fortran/ (ISO_C_BINDING veneer), by the C++ mirror rrnn.hpp and by the Python
  * host mirror in rte_rrtmgp_nn_b200/.
  *
  * Conventions
