@@ -556,7 +556,10 @@ class ty_gas_optics_rrtmgp(ty_optical_props):
     def load(self, kd):
         self.kd = dict(kd)
         self.init(kd, "ty_gas_optics_rrtmgp")
-        self._kd = _kdist_handle(self.ctx, self.kd)
+        try:
+            self._kd = _kdist_handle(self.ctx, self.kd)
+        except RRNNError as e:
+            return str(e)
         return ""
 
     def source_is_internal(self):
