@@ -8,7 +8,9 @@
 //   ty_optical_props[_1scl|_2str]  rte/mo_optical_props.F90:62-190           (alloc_1scl / alloc_2str, get_ncol ...)
 //   ty_source_func_lw          rte/mo_source_functions.F90:27-80             (alloc)
 //   ty_fluxes_broadband        rte/mo_fluxes.F90:36-50                        (caller-associated outputs)
-//   ty_gas_optics_rrtmgp       rrtmgp/mo_gas_optics_rrtmgp.F90:239-243, 433-438, 1097-1120 (gas_optics with neural_nets, set_tsi)
+//   ty_fluxes_byband           extensions/mo_fluxes_byband.F90:31-131         (reduce: by-band sums of g-point fluxes)
+//   ty_gas_optics_rrtmgp       rrtmgp/mo_gas_optics_rrtmgp.F90:239-243, 433-438, 1058-1120, 1712-1758 (gas_optics with neural_nets,
+//                              set_tsi, set_solar_variability, compute_optimal_angles)
 //   rte_lw / rte_sw            rte/mo_rte_lw.F90:60-64, rte/mo_rte_sw.F90:48-52
 //
 // Arrays live on the device (dev_array: cudaMalloc'd float storage with host <-> device copies); layouts are the
@@ -188,6 +190,33 @@ struct ty_fluxes_broadband {
   bool are_desired() const { return flux_up || flux_dn || flux_net || flux_dn_dir; }
 };
 
+// ty_fluxes_byband (extensions/mo_fluxes_byband.F90:31-131): by-band outputs (nbnd,nlay+1,ncol) the caller associates
+struct ty_fluxes_byband : ty_fluxes_broadband {
+  float* bnd_flux_up = nullptr;
+  float* bnd_flux_dn = nullptr;
+  float* bnd_flux_net = nullptr;
+  float* bnd_flux_dn_dir = nullptr;
+  bool are_desired() const { return bnd_flux_up || bnd_flux_dn || bnd_flux_net || bnd_flux_dn_dir || ty_fluxes_broadband::are_desired(); }
+  // reduce_byband, by-band part: g-point fluxes (ngpt,nlev,ncol) on the device -> the associated by-band arrays
+  std::string reduce(const context& ctx, const float* gpt_flux_up_d, const float* gpt_flux_dn_d, const ty_optical_props& spectral_disc,
+                     int ncol, int nlev, const float* gpt_flux_dn_dir_d = nullptr) const {
+    if (bnd_flux_dn_dir && !gpt_flux_dn_dir_d) return "reduce: requesting bnd_flux_dn_dir but direct flux hasn't been supplied";
+    const rrnn_kdist_t* kd = spectral_disc.kd();
+    if (!kd) return "reduce: spectral discretization carries no band limits";
+    int rc = 0;
+    if (bnd_flux_up) rc = rrnn_sum_byband(ctx.h(), kd, nlev, ncol, gpt_flux_up_d, bnd_flux_up);
+    if (!rc && bnd_flux_dn) rc = rrnn_sum_byband(ctx.h(), kd, nlev, ncol, gpt_flux_dn_d, bnd_flux_dn);
+    if (!rc && bnd_flux_dn_dir) rc = rrnn_sum_byband(ctx.h(), kd, nlev, ncol, gpt_flux_dn_dir_d, bnd_flux_dn_dir);
+    if (!rc && bnd_flux_net) {
+      if (bnd_flux_dn && bnd_flux_up)  // net_byband_precalc
+        rc = rrnn_net_flux(ctx.h(), static_cast<size_t>(ncol) * nlev * spectral_disc.get_nband(), bnd_flux_dn, bnd_flux_up, bnd_flux_net);
+      else                             // net_byband_full
+        rc = rrnn_net_byband(ctx.h(), kd, nlev, ncol, gpt_flux_dn_d, gpt_flux_up_d, bnd_flux_net);
+    }
+    return err(rc);
+  }
+};
+
 class ty_gas_optics_rrtmgp : public ty_optical_props {
  public:
   // load: the spectral tables the NN path needs (rrtmgp/mo_gas_optics_rrtmgp.F90:1130-1326): band -> g-point limits,
@@ -207,6 +236,24 @@ class ty_gas_optics_rrtmgp : public ty_optical_props {
   bool source_is_internal() const { return internal_; }
   bool source_is_external() const { return !internal_; }
   std::string set_tsi(float tsi) { return err(rrnn_kdist_set_tsi(kd_.get(), tsi)); }
+  // the optional tables of load (:1163, 1210, 1317-1325): solar_source_quiet / _facular / _sunspot (ngpt), optimal_angle_fit (2,nbnd)
+  std::string load_solar_tables(const float* solar_quiet, const float* solar_facular, const float* solar_sunspot) {
+    return err(rrnn_kdist_set_solar_tables(kd_.get(), solar_quiet, solar_facular, solar_sunspot));
+  }
+  std::string load_optimal_angle_fit(const float* optimal_angle_fit) { return err(rrnn_kdist_set_optimal_angle_fit(kd_.get(), optimal_angle_fit)); }
+  // set_solar_variability(mg_index, sb_index [, tsi]), :1058-1095
+  std::string set_solar_variability(float mg_index, float sb_index) { return err(rrnn_kdist_set_solar_variability(kd_.get(), mg_index, sb_index, 0, 0.f)); }
+  std::string set_solar_variability(float mg_index, float sb_index, float tsi) {
+    return err(rrnn_kdist_set_solar_variability(kd_.get(), mg_index, sb_index, 1, tsi));
+  }
+  std::vector<float> get_solar_source() const {
+    std::vector<float> v(static_cast<size_t>(ngpt_));
+    if (rrnn_kdist_get_solar_source(kd_.get(), v.data())) v.clear();
+    return v;
+  }
+  bool gpoints_are_equal(const ty_optical_props& other) const { return ngpt_ == other.get_ngpt() && band_lims_ == other.get_band_lims_gpoint(); }
+  // compute_optimal_angles(optical_props, optimal_angles), :1712-1758; optimal_angles is (ngpt,ncol), what rte_lw's lw_Ds takes
+  std::string compute_optimal_angles(const ty_optical_props_1scl& optical_props, dev_array& optimal_angles) const;
 
   // longwave: gas_optics(play, plev, tlay, tsfc, gas_desc, optical_props, sources, tlev=, neural_nets=)
   std::string gas_optics(const float* play_d, const float* plev_d, const float* tlay_d, const float* tsfc_d, const ty_gas_concs& gas_desc,
@@ -241,6 +288,15 @@ class ty_gas_optics_rrtmgp : public ty_optical_props {
   const context* ctx_ = nullptr;
   bool internal_ = false;
 };
+
+inline std::string ty_gas_optics_rrtmgp::compute_optimal_angles(const ty_optical_props_1scl& optical_props, dev_array& optimal_angles) const {
+  if (!gpoints_are_equal(optical_props))
+    return "gas_optics%compute_optimal_angles: optical_props has different spectral discretization than gas_optics";
+  if (optimal_angles.size() != static_cast<size_t>(optical_props.get_ncol()) * ngpt_)
+    return "gas_optics%compute_optimal_angles: optimal_angles different dimension (ncol)";
+  return err(rrnn_compute_optimal_angles(ctx_->h(), kd_.get(), optical_props.get_nlay(), optical_props.get_ncol(), optical_props.tau.data(),
+                                         optimal_angles.data()));
+}
 
 // rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes [, inc_flux] [, n_gauss_angles]); sfc_emis_d is (nbnd,ncol)
 inline std::string rte_lw(const context& ctx, const ty_optical_props_1scl& optical_props, bool top_at_1, const ty_source_func_lw& sources,

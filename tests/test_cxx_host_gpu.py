@@ -11,11 +11,12 @@ import helpers as H
 
 CXX_DIR = os.path.join(H.ROOT, "examples", "cxx")
 EXE = os.path.join(CXX_DIR, "rfmip_driver")
+API_CHECK = os.path.join(CXX_DIR, "api_check")
 
 
 def _build():
     subprocess.check_call(["make", "-C", CXX_DIR, "-s"])
-    assert os.path.exists(EXE)
+    assert os.path.exists(EXE) and os.path.exists(API_CHECK)
 
 
 def _write_case(d, band, atm, kd, block_size, n_quad_angles=1):
@@ -55,6 +56,17 @@ def test_cxx_driver_fails_loudly_without_a_gpu(tmp_path):
     (tmp_path / "meta.txt").write_text("ncol 1\nnlay 1\nblock_size 1\nnbnd 1\nngpt 1\ntop_at_1 1\n")
     r = subprocess.run([EXE, "lw", str(tmp_path), "a.nc", "b.nc"], capture_output=True, text=True)
     assert r.returncode == 1 and "no CUDA device available (this library has no CPU fallback)" in r.stderr
+    r = subprocess.run([API_CHECK], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device available (this library has no CPU fallback)" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cxx_mirror_self_check(gpu_ctx):
+    """examples/cxx/api_check.cpp: by-band / net fluxes, optimal angles, solar variability and the reference's error strings
+    through the C++ mirror, against exact expectations (small integers, a transparent column, the quiet-sun offsets)."""
+    _build()
+    r = subprocess.run([API_CHECK], capture_output=True, text=True)
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.gpu
