@@ -70,6 +70,13 @@ RRNN_API int rrnn_ctx_profile(rrnn_ctx_t* ctx, int enable);
 RRNN_API int rrnn_ctx_profile_read(rrnn_ctx_t* ctx, int kind, double* total_ms, int* nlaunches);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 RRNN_API long long rrnn_ctx_launch_count(rrnn_ctx_t* ctx);
+/* Which MLP kernel served the most recent NN gas-optics call on this context (the reference has ONE code path per model
+ * set, predict_nn_{lw,sw}_blas_sp, rrtmgp/kernels/mo_gas_optics_kernels.F90:690-774, 869-953; here the tcgen05 kernel takes
+ * every shipped model set and the fp32 FFMA kernel is the nn_tensor_cores = 0 variant and the fallback for anything else):
+ * 0 none yet, RRNN_NN_KERNEL_FFMA, RRNN_NN_KERNEL_TCGEN05.  The counts are launches since the context was created. */
+enum { RRNN_NN_KERNEL_NONE = 0, RRNN_NN_KERNEL_FFMA = 1, RRNN_NN_KERNEL_TCGEN05 = 2 };
+RRNN_API int rrnn_ctx_last_nn_kernel(rrnn_ctx_t* ctx);
+RRNN_API int rrnn_ctx_nn_kernel_counts(rrnn_ctx_t* ctx, long long* n_tcgen05, long long* n_ffma);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* NN models: rrtmgp_network_type%load_netcdf, neural/mod_network_rrtmgp.F90:58-122                   */

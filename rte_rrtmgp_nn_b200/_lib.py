@@ -48,6 +48,8 @@ _SIGS = {
     "rrnn_ctx_synchronize": (C.c_int, [vp]),
     "rrnn_ctx_set_flag": (C.c_int, [vp, C.c_char_p, C.c_int]),
     "rrnn_ctx_launch_count": (C.c_longlong, [vp]),
+    "rrnn_ctx_last_nn_kernel": (C.c_int, [vp]),
+    "rrnn_ctx_nn_kernel_counts": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "rrnn_ctx_profile": (C.c_int, [vp, C.c_int]),
     "rrnn_ctx_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), c_int_p]),
     "rrnn_ctx_set_chunk_columns": (C.c_int, [vp, C.c_int]),

@@ -68,6 +68,20 @@ class Context:
     def launch_count(self):
         return int(_lib.lib().rrnn_ctx_launch_count(self.h))
 
+    NN_KERNELS = {0: "none", 1: "ffma", 2: "tcgen05"}
+
+    @property
+    def last_nn_kernel(self):
+        """Which MLP kernel served the most recent NN gas-optics call: "none", "ffma" or "tcgen05"."""
+        return self.NN_KERNELS[int(_lib.lib().rrnn_ctx_last_nn_kernel(self.h))]
+
+    @property
+    def nn_kernel_counts(self):
+        """(tcgen05 launches, fp32 FFMA launches) of the NN gas optics since the context was created."""
+        a = C.c_longlong(0); b = C.c_longlong(0)
+        _lib.check(_lib.lib().rrnn_ctx_nn_kernel_counts(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def torch_stream(self):
         torch = _torch()
         if not self.stream:  # legacy default stream == torch's default stream

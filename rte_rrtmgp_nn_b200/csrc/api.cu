@@ -419,6 +419,13 @@ extern "C" int rrnn_ctx_synchronize(rrnn_ctx_t* c) {
   return 0;
 }
 extern "C" long long rrnn_ctx_launch_count(rrnn_ctx_t* c) { return c ? c->launches : 0; }
+extern "C" int rrnn_ctx_last_nn_kernel(rrnn_ctx_t* c) { return c ? c->last_nn_kernel : 0; }
+extern "C" int rrnn_ctx_nn_kernel_counts(rrnn_ctx_t* c, long long* n_tc, long long* n_ffma) {
+  RRNN_CHECK(c, "rrnn_ctx_nn_kernel_counts: null context");
+  if (n_tc) *n_tc = c->nn_tc_launches;
+  if (n_ffma) *n_ffma = c->nn_ffma_launches;
+  return 0;
+}
 extern "C" int rrnn_ctx_set_chunk_columns(rrnn_ctx_t* c, int n) {
   RRNN_CHECK(c && n >= 0, "rrnn_ctx_set_chunk_columns: bad argument");
   c->chunk_columns = n;

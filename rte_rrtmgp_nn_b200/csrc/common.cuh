@@ -47,6 +47,8 @@ struct rrnn_ctx {
   int num_sms = 148;
   size_t smem_optin = 0;
   long long launches = 0;
+  int last_nn_kernel = 0;                        // RRNN_NN_KERNEL_* of the most recent NN gas-optics launch
+  long long nn_tc_launches = 0, nn_ffma_launches = 0;
   // flags (rte/mo_rte_rrtmgp_config.F90:23-40 + this library's own)
   int lw_source_bug_compat = 1;
   int fast_math = 0;       // solver transcendental variant: 0 = IEEE-accurate libdevice, 1 = ex2/rcp/rsqrt approx

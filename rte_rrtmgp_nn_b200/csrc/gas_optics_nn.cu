@@ -575,6 +575,10 @@ static int launch_go(rrnn_ctx_t* ctx, const GoParams& p, int nout_max, int prof_
   }
   if (prof_kind >= 0) prof_end(ctx, prof_kind, ps);
   RRNN_LAUNCH_CHECK(ctx);
+  if (prof_kind >= 0) {  // a gas_optics() call (the stand-alone output_sgemm_* entry points are FFMA by definition)
+    ctx->last_nn_kernel = RRNN_NN_KERNEL_FFMA;
+    ctx->nn_ffma_launches++;
+  }
   return 0;
 }
 
@@ -617,7 +621,7 @@ int map_gases(const rrnn_model_t* m, const rrnn_gas_t* gases, int ngas, GoParams
 
 using namespace rrnn;
 
-int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol, int nlay,
+int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int ncol, int nlay,
                        const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
                        const rrnn_gas_t* gases, int ngas, float* out0, float* out1, float* out2, float* sfc_source,
                        float* sfc_jac, int prof_kind, float* planck_lay = nullptr,
@@ -653,8 +657,8 @@ extern "C" int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
   p.temp_ref_min = kd->temp_ref_min; p.totplnk_delta = kd->totplnk_delta;
   p.out0 = tau_d; p.out1 = lay_source_d; p.out2 = lev_source_d; p.sfc_source = sfc_source_d; p.sfc_jac = sfc_source_Jac_d;
   int rc = -1;
-  if (nmodels == 2 && ctx->nn_tensor_cores) {
-    rc = rrnn_gas_optics_tc(ctx, 0, kd, models, ncol, nlay, play_d, plev_d, tlay_d, p.tlev, tsfc_d, gases, ngas, tau_d,
+  if (ctx->nn_tensor_cores) {
+    rc = rrnn_gas_optics_tc(ctx, 0, kd, models, nmodels, ncol, nlay, play_d, plev_d, tlay_d, p.tlev, tsfc_d, gases, ngas, tau_d,
                             lay_source_d, lev_source_d, sfc_source_d, sfc_source_Jac_d, K_GAS_LW);
   }
   if (rc >= 0) {
@@ -683,7 +687,7 @@ extern "C" int rrnn_gas_optics_lw_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* k
                                           float* tau_d, float* pfrac_d, float* planck_lay_d, float* planck_lev_d,
                                           float* sfc_source_d, float* sfc_source_Jac_d) {
   RRNN_CHECK(ctx && kd && models, "gas_optics(): null handle");
-  RRNN_CHECK(nmodels == 2, "gas_optics (compact sources): needs the absorption and the Planck-fraction network");
+  RRNN_CHECK(nmodels == 1 || nmodels == 2, "gas_optics(): neural_nets must hold 1 or 2 networks for the longwave");
   RRNN_CHECK(kd->d_totplnk, "gas_optics(): k-distribution has no Planck table (not a longwave k-distribution)");
   RRNN_CHECK(nlay >= 2 && ncol >= 0, "gas_optics(): bad extents");
   RRNN_CHECK(tau_d && pfrac_d && planck_lay_d && planck_lev_d && sfc_source_d && sfc_source_Jac_d, "gas_optics (compact sources): null output");
@@ -695,7 +699,7 @@ extern "C" int rrnn_gas_optics_lw_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* k
     RRNN_CUDA(cudaMallocAsync((void**)&tlev_tmp, (size_t)ncol * (nlay + 1) * sizeof(float), ctx->stream));
     if (int rc = rrnn_interp_tlev(ctx, ncol, nlay, play_d, plev_d, tlay_d, tlev_tmp)) return rc;
   }
-  const int rc = rrnn_gas_optics_tc(ctx, 0, kd, models, ncol, nlay, play_d, plev_d, tlay_d, tlev_d ? tlev_d : tlev_tmp, tsfc_d, gases,
+  const int rc = rrnn_gas_optics_tc(ctx, 0, kd, models, nmodels, ncol, nlay, play_d, plev_d, tlay_d, tlev_d ? tlev_d : tlev_tmp, tsfc_d, gases,
                                     ngas, tau_d, pfrac_d, nullptr, sfc_source_d, sfc_source_Jac_d, K_GAS_LW, planck_lay_d, planck_lev_d);
   if (tlev_tmp) RRNN_CUDA(cudaFreeAsync(tlev_tmp, ctx->stream));
   if (rc < 0) return fail("gas_optics (compact sources): configuration not supported by the tensor-core kernel");
@@ -728,7 +732,7 @@ extern "C" int rrnn_gas_optics_sw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
   p.out0 = tau_d; p.out1 = ssa_d; p.out2 = g_d;
   int rc = -1;
   if (two_stream && ctx->nn_tensor_cores)
-    rc = rrnn_gas_optics_tc(ctx, 1, kd, models, ncol, nlay, play_d, plev_d, tlay_d, nullptr, nullptr, gases, ngas, tau_d, ssa_d,
+    rc = rrnn_gas_optics_tc(ctx, 1, kd, models, 2, ncol, nlay, play_d, plev_d, tlay_d, nullptr, nullptr, gases, ngas, tau_d, ssa_d,
                             g_d, nullptr, nullptr, K_GAS_SW);
   if (rc < 0) rc = launch_go<EPI_SW>(ctx, p, kd->ngpt, K_GAS_SW);
   if (rc) return rc;

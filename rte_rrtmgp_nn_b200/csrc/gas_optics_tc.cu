@@ -22,9 +22,13 @@
 //   ystd*(z+b)+ymean is folded into the last layer's weights (times 2^10 so that the fp16 lo parts stay normal; the
 //   2^-80 comes back with N_dry) and, where the padded K has a spare column, the bias rides on a column of ones.
 //
-// Supported: two networks with 2 hidden layers of equal width <= 64, linear output, <= 32 inputs, ngpt a multiple of
-// 32 and <= 256, nbnd <= 16 (all g256 / g224 / g128 two-network models of the reference with hidden width <= 64);
-// anything else returns -1 and the caller uses the fp32 FFMA kernel.
+// Supported: every model generation the reference ships (neural/data): two networks (absorption + Planck fraction,
+// absorption + Rayleigh) with 2 hidden layers each, widths up to 80 and different per network (58/16, 64/24, 72/24,
+// 80/32, 32/16, 32/32 ...), or ONE longwave network with 2*ngpt outputs (the "both" models,
+// rrtmgp/kernels/mo_gas_optics_kernels.F90:745-767: two output heads on one hidden stack); linear output, <= 32
+// inputs, ngpt a multiple of 16 and <= 256 (256, 224, 128, 112: a ragged last job of 16 g-points is padded with zero
+// weight rows and clipped by the TMA store), nbnd <= 16.  Anything else returns -1 and the caller uses the fp32 FFMA
+// kernel.
 #include "common.cuh"
 #include "f32x2.cuh"
 #include <cuda.h>
@@ -43,7 +47,9 @@ constexpr int NSLOT = 6;         // ring of output accumulators: 6 jobs of 32 g-
                                  // 3 pairs of 128 columns [net 0: 64 | net 1: 64] so that ONE N = 64 MMA per network and k-step
                                  // feeds two jobs (an SS-mode MMA re-reads its 4 KB A operand from shared memory whatever N is:
                                  // measured ~60 cycles per N = 32 MMA against a 16-cycle tensor floor)
-constexpr int RING_COL0 = 128;   // TMEM columns 0..63 / 64..127: hidden accumulators of net 0 / 1
+constexpr int RING_COL0 = 128;   // TMEM columns 0..127: hidden accumulators (net 0 at column 0, net 1 at NetP::hid_col)
+constexpr int HMAX = 80;         // widest hidden layer (padded to a multiple of 16)
+constexpr int REC_F = 6;         // floats per row record
 constexpr int STAGE_BYTES = 4096;  // one staged output tile: 32 rows x 32 g-points
 constexpr float OUT_SCALE = 1024.0f;            // folded into the last layer of the tau-type networks
 constexpr float OUT_UNSCALE = 8.271806125530277e-25f;  // 2^-80 = OUT_SCALE^-8
@@ -52,6 +58,7 @@ enum { BAR_AIN = 0, BAR_HID = 1, BAR_ACT = 3, BAR_ACTFREE = 5, BAR_SLOT_FULL = 7
 
 struct NetP {
   int H, K3, Hraw, fold, act0, act1, ntot;
+  int hid_col;               // TMEM column of this network's hidden accumulator
   uint32_t w[3][2];          // shared-memory byte offsets of W{1,2,3}{hi,lo} (canonical K-major layout, fp16)
   uint32_t b[3];             // byte offsets of b1[H], b2[H], b3''[N] (fp32)
   uint32_t act_hi, act_lo;   // activation operand (A of layers 2 and 3)
@@ -66,6 +73,8 @@ struct Params {
   int ncol, nlay, ngpt, nx, kin, nbnd, ntemp, period, nchunks;
   int nstage;  // staging tiles per epilogue warp (2 when shared memory allows, else 1)
   int nrec;  // depth of the per-row record ring (how many tiles the front warps may run ahead of the output epilogue)
+  int nhid;  // hidden stacks: 2 = two networks, 1 = one network with two output heads ("both" models; net[1] shares net[0]'s activations)
+  int totplnk_global;  // 1: the Planck table is read from global memory (shared memory is short), 0: from the image in shared memory
   unsigned nrows;
   const float *play, *plev, *tlay, *tlev, *tsfc;
   GasIn gas[KIN_MAX];
@@ -374,7 +383,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     for (uint32_t i = tid; i < p.blob_bytes / 16; i += THREADS) dst[i] = __ldg(src + i);
     // activation operands start from zero (padding k-units are never written again); a folded bias that lives in an
     // extension k-unit (Hraw == H) gets its column of ones here, once
-    for (int n = 0; n < 2; ++n) {
+    for (int n = 0; n < p.nhid; ++n) {
       const NetP& nt = p.net[n];
       uint4* a = reinterpret_cast<uint4*>(smem + nt.act_hi);
       const uint32_t units = (uint32_t)(2 * TM * nt.K3 * 2) / 16;  // hi and lo are contiguous
@@ -384,7 +393,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     for (uint32_t i = tid; i < (uint32_t)(2 * TM * p.kin * 2) / 16; i += THREADS) ain[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  for (int n = 0; n < 2; ++n) {
+  for (int n = 0; n < p.nhid; ++n) {
     const NetP& nt = p.net[n];
     if (nt.fold && nt.Hraw >= nt.H && tid < TM) {
       __half* a = reinterpret_cast<__half*>(smem + nt.act_hi + unit_off(TM, tid, nt.Hraw >> 3));
@@ -491,7 +500,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
       // ---- per-row record for the output epilogue of this tile (a ring of nrec tiles; ordered by the
       //      AIN -> ... -> SLOT_FULL barrier chain): N_dry * 2^-80 and where T_lay, T_lev, T_sfc fall in the Planck table
       {
-        float* rec = reinterpret_cast<float*>(smem + p.off_rec) + (it % p.nrec) * (8 * TM) + r;
+        float* rec = reinterpret_cast<float*>(smem + p.off_rec) + (it % p.nrec) * (REC_F * TM) + r;
         float cdp = 0.0f;
         if (valid) {
           const float h = p.xvar[2] ? cur.x2 : p.h2o_const;
@@ -516,7 +525,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 #pragma unroll 1
       for (int l = 0; l < 2; ++l) {
 #pragma unroll 1
-        for (int n = 0; n < 2; ++n) {
+        for (int n = 0; n < p.nhid; ++n) {
           const NetP& nt = p.net[n];
           uint8_t* act_hi = smem + nt.act_hi;
           uint8_t* act_lo = smem + nt.act_lo;
@@ -531,7 +540,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
           const bool ones = (l == 1) && nt.fold && nt.Hraw < nt.H;
           for (int c0 = 0; c0 < nt.H; c0 += 16) {
             float v[16];
-            tmem_ld16(tmem_row + 64u * n + c0, v);
+            tmem_ld16(tmem_row + (uint32_t)(nt.hid_col + c0), v);
             const bool has_one = ones && (nt.Hraw >> 4) == (c0 >> 4);
             if (act == RRNN_ACT_SOFTSIGN && !has_one) {
               // the common case, in packed arithmetic: bias, softsign, fp16 hi/lo split of two columns at a time
@@ -589,7 +598,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         wstep12[n] = 2u * (uint32_t)nt.H;  // two k-units of H rows x 16 B, in 16-byte units
         idesc_h[n] = make_idesc(TM, nt.H);
       }
-      const uint32_t wstep3 = 2u * (uint32_t)p.ngpt;
+      const uint32_t wstep3 = 2u * (uint32_t)p.net[0].ntot;  // both heads are packed with the same (padded) number of rows
       const uint32_t idesc_o = make_idesc(TM, 32), idesc_o2 = make_idesc(TM, 64);
       const int nch_pad = (p.nchunks + 1) & ~1;
       int mit = 0;
@@ -601,26 +610,31 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         if (elect_one()) {
 #pragma unroll
           for (int n = 0; n < 2; ++n) {
-            issue_gemm(tmem_base + 64u * n, d_ain, d_w[n][0], wstep12[n], p.kin >> 4, idesc_h[n]);
-            mma_commit(BAR(BAR_HID + n));
+            if (n < p.nhid) {
+              issue_gemm(tmem_base + (uint32_t)p.net[n].hid_col, d_ain, d_w[n][0], wstep12[n], p.kin >> 4, idesc_h[n]);
+              mma_commit(BAR(BAR_HID + n));
+            }
           }
         }
         __syncwarp();
         if (lane == 0) dbg_ts(p.dbg, mit, 22);
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
+          if (n >= p.nhid) continue;  // warp-uniform
           mbar_wait(BAR(BAR_ACT + n), ph_act[n]); ph_act[n] ^= 1u;
           fence_after();
           if (lane == 0) dbg_ts(p.dbg, mit, 23 + 2 * n);
           if (elect_one()) {
-            issue_gemm(tmem_base + 64u * n, d_act[n], d_w[n][1], wstep12[n], p.net[n].H >> 4, idesc_h[n]);
+            issue_gemm(tmem_base + (uint32_t)p.net[n].hid_col, d_act[n], d_w[n][1], wstep12[n], p.net[n].H >> 4, idesc_h[n]);
             mma_commit(BAR(BAR_HID + n));
           }
           __syncwarp();
           if (lane == 0) dbg_ts(p.dbg, mit, 24 + 2 * n);
         }
 #pragma unroll
-        for (int n = 0; n < 2; ++n) { mbar_wait(BAR(BAR_ACT + n), ph_act[n]); ph_act[n] ^= 1u; }
+        for (int n = 0; n < 2; ++n) {
+          if (n < p.nhid) { mbar_wait(BAR(BAR_ACT + n), ph_act[n]); ph_act[n] ^= 1u; }
+        }
         fence_after();
         if (lane == 0) dbg_ts(p.dbg, mit, 27);
         // two jobs (64 g-points) per set of MMAs; an odd last job (ngpt = 224) is padded with an empty one so that job
@@ -649,7 +663,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         if (elect_one()) {
           mma_commit(BAR(BAR_ACTFREE + 0));
-          mma_commit(BAR(BAR_ACTFREE + 1));
+          if (p.nhid > 1) mma_commit(BAR(BAR_ACTFREE + 1));
         }
         __syncwarp();
       }
@@ -665,7 +679,8 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
     uint8_t* stage = smem + p.off_stage + (uint32_t)(warp - 4) * (uint32_t)(p.nstage * STAGE_BYTES);
     const uint32_t stage_a = smem_u32(stage);
     const int* band4_s = reinterpret_cast<const int*>(smem + p.off_band4);  // band of each group of 4 g-points
-    const float* tp_s = reinterpret_cast<const float*>(smem + p.off_totplnk);  // totplnk [band][ntemp]
+    // totplnk [band][ntemp]: in the shared-memory image, or (wide networks, shared memory short) in global memory / L1
+    const float* tp_s = p.totplnk_global ? p.totplnk : reinterpret_cast<const float*>(smem + p.off_totplnk);
     const float* b3_0 = reinterpret_cast<const float*>(smem + p.net[0].b[2]);
     const float* b3_1 = reinterpret_cast<const float*>(smem + p.net[1].b[2]);
     const bool fold0 = p.net[0].fold != 0, fold1 = p.net[1].fold != 0;
@@ -700,7 +715,8 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (dest < nrows_arr && !(p.dbg_flags & 2)) tma_store_2d(tm, stage_a + sbuf * (STAGE_BYTES / 2), g0 + 16 * hf, (int)dest);
+            // (a half tile that starts past the last g-point -- ngpt = 112 -- is not stored; one that starts inside is clipped)
+            if (dest < nrows_arr && g0 + 16 * hf < G && !(p.dbg_flags & 2)) tma_store_2d(tm, stage_a + sbuf * (STAGE_BYTES / 2), g0 + 16 * hf, (int)dest);
             bulk_commit();
           }
           sbuf ^= 1;
@@ -749,7 +765,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         dest_lay = w0 - wcol;
       }
       const bool is_sfc = (MODE == 0) && valid && lev == sfc_lev;
-      const float* rec = reinterpret_cast<const float*>(smem + p.off_rec) + (it % p.nrec) * (8 * TM) + r;
+      const float* rec = reinterpret_cast<const float*>(smem + p.off_rec) + (it % p.nrec) * (REC_F * TM) + r;
       float cdp = 0.0f, frac_l = 0.0f, frac_v = 0.0f;
       const float *tp_l = tp_s, *tp_v = tp_s;   // &totplnk[0][idx-1] for T_lay and T_lev of this row
       PlanckPos ps0{1, 0.0f}, ps1{1, 0.0f};      // T_sfc, T_sfc + 1 (surface row only)
@@ -885,8 +901,10 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
                 b0 = u0 + ps0.frac * (t[ps0.idx] - u0);
                 bj = (u1 + ps1.frac * (t[ps1.idx] - u1)) - b0;
               }
-              *reinterpret_cast<float4*>(ss + 4 * j4) = make_float4(z[32 + 4 * j4] * b0, z[33 + 4 * j4] * b0, z[34 + 4 * j4] * b0, z[35 + 4 * j4] * b0);
-              *reinterpret_cast<float4*>(sj + 4 * j4) = make_float4(z[32 + 4 * j4] * bj, z[33 + 4 * j4] * bj, z[34 + 4 * j4] * bj, z[35 + 4 * j4] * bj);
+              if (g0 + 4 * j4 < G) {  // (the padding g-points of a ragged last job are not part of the arrays)
+                *reinterpret_cast<float4*>(ss + 4 * j4) = make_float4(z[32 + 4 * j4] * b0, z[33 + 4 * j4] * b0, z[34 + 4 * j4] * b0, z[35 + 4 * j4] * b0);
+                *reinterpret_cast<float4*>(sj + 4 * j4) = make_float4(z[32 + 4 * j4] * bj, z[33 + 4 * j4] * bj, z[34 + 4 * j4] * bj, z[35 + 4 * j4] * bj);
+              }
             }
           }
         } else {
@@ -923,9 +941,10 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// pack one layer W (row-major [K][O] fp32, scaled per output) into the canonical K-major layout of the B operand:
-// rows = outputs (padded to OP), K padded to KP; hi block then lo block.  bias_k >= 0 puts bias[o] on that k.
-static void pack_layer(const float* W, int K, int O, int KP, int OP, const double* oscale, int bias_k, const double* bias,
+// pack O output columns of one layer W (row-major [K][ldw] fp32, scaled per output) into the canonical K-major layout of
+// the B operand: rows = outputs (padded to OP with zeros), K padded to KP; hi block then lo block.  bias_k >= 0 puts
+// bias[o] on that k.
+static void pack_layer(const float* W, int K, int O, int ldw, int KP, int OP, const double* oscale, int bias_k, const double* bias,
                        std::vector<uint8_t>& out, uint32_t& off_hi, uint32_t& off_lo) {
   const size_t base = out.size();
   out.resize(base + (size_t)2 * OP * KP * 2, 0);
@@ -936,7 +955,7 @@ static void pack_layer(const float* W, int K, int O, int KP, int OP, const doubl
   for (int o = 0; o < OP; ++o)
     for (int k = 0; k < KP; ++k) {
       double wd = 0.0;
-      if (o < O && k < K) wd = (double)W[(size_t)k * O + o] * (oscale ? oscale[o] : 1.0);
+      if (o < O && k < K) wd = (double)W[(size_t)k * ldw + o] * (oscale ? oscale[o] : 1.0);
       else if (o < O && k == bias_k) wd = bias[o];
       const float w = (float)wd;
       const __half h = __float2half_rn(w);
@@ -987,27 +1006,34 @@ static int make_map(CUtensorMap* tm, float* base, int G, unsigned long long rows
 using namespace rrnn;
 
 static int pad16(int n) { return (n + 15) & ~15; }
+static int pad32(int n) { return (n + 31) & ~31; }
 
-// Is this pair of networks supported by the tensor-core kernel?
-static bool tc_supported(const rrnn_model_t* const* models, const rrnn_kdist_t* kd, int mode) {
+// Is this set of networks supported by the tensor-core kernel?  nmodels = 2: two networks with ngpt outputs each;
+// nmodels = 1 (longwave only): one network with 2*ngpt outputs (tau head, Planck-fraction head).
+static bool tc_supported(const rrnn_model_t* const* models, int nmodels, const rrnn_kdist_t* kd, int mode) {
   const int ngpt = kd->ngpt;
-  if (ngpt % 32 != 0 || ngpt > 256) return false;
+  if (ngpt % 16 != 0 || ngpt > 256 || ngpt < 32) return false;
   if (mode == 0 && (kd->nbnd > 16 || kd->nbnd < 1)) return false;
-  for (int n = 0; n < 2; ++n) {
+  if (nmodels != 2 && !(nmodels == 1 && mode == 0)) return false;
+  int hsum = 0;
+  for (int n = 0; n < nmodels; ++n) {
     const rrnn_model_t* m = models[n];
     if (!m || m->nlayers != 3) return false;
-    if (m->dims[0] > tc::KIN_MAX || m->dims[0] < 4 || m->dims[1] > 64 || m->dims[2] != m->dims[1] || m->dims[3] != ngpt) return false;
+    if (m->dims[0] > tc::KIN_MAX || m->dims[0] < 4 || m->dims[1] > tc::HMAX || m->dims[2] != m->dims[1]) return false;
+    if (m->dims[3] != (nmodels == 1 ? 2 * ngpt : ngpt)) return false;
     if (m->act[2] != RRNN_ACT_LINEAR) return false;
+    hsum += pad16(m->dims[1]);
   }
-  if (models[0]->dims[0] != models[1]->dims[0]) return false;
-  if (models[0]->ymean.empty() || models[0]->ystd.empty()) return false;
+  if (hsum > tc::RING_COL0) return false;  // the hidden accumulators share TMEM columns 0..127
+  if (nmodels == 2 && models[0]->dims[0] != models[1]->dims[0]) return false;
+  if ((int)models[0]->ymean.size() < ngpt || (int)models[0]->ystd.size() < ngpt) return false;
   if (mode == 1 && (models[1]->ymean.empty() || models[1]->ystd.empty())) return false;
   return true;
 }
 
-// Build the shared-memory image (weights, biases, band tables) and the layout; cached per (model pair, kdist, mode).
+// Build the shared-memory image (weights, biases, band tables) and the layout; cached per (model set, kdist, mode).
 struct TcCache {
-  unsigned long long m0 = 0, m1 = 0, kd = 0;  // uids
+  unsigned long long m0 = 0, m1 = 0, kd = 0;  // uids (m1 = 0: one network with two heads)
   int mode = -1, device = -1;
   tc::Params p{};
   size_t smem = 0;
@@ -1016,33 +1042,46 @@ struct TcCache {
 static std::vector<TcCache> g_tc_cache;
 static std::mutex g_tc_mutex;
 
-// returns 0 and a copy of the plan, -1 if the pair does not fit the kernel's shared-memory design, > 0 on error
-static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, TcCache* out) {
+// returns 0 and a copy of the plan, -1 if the networks do not fit the kernel's shared-memory design, > 0 on error
+static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, TcCache* out) {
   std::lock_guard<std::mutex> lock(g_tc_mutex);
+  const unsigned long long uid1 = nmodels == 2 ? models[1]->uid : 0ull;
   for (auto& c : g_tc_cache)
-    if (c.m0 == models[0]->uid && c.m1 == models[1]->uid && c.kd == kd->uid && c.mode == mode && c.device == ctx->device) { *out = c; return 0; }
-  const int G = kd->ngpt;
+    if (c.m0 == models[0]->uid && c.m1 == uid1 && c.kd == kd->uid && c.mode == mode && c.device == ctx->device) { *out = c; return 0; }
+  const int G = kd->ngpt, Gp = pad32(G);
   const int nx = models[0]->dims[0];
   const int kin = pad16(nx);
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  const bool both = nmodels == 1;
+  // Shared memory is what limits the wide networks.  Attempts, cheapest concession first:
+  //   0: output bias folded into the last layer even if that costs one more k-step; Planck table in shared memory
+  //   1: bias folded only where the padded K has a spare column (else added in the epilogue)
+  //   2: like 1, and the Planck table is read from global memory (L1-resident: 12.5 KB for 16 bands)
+  for (int attempt = 0; attempt < 3; ++attempt) {
     TcCache c;
-    c.m0 = models[0]->uid; c.m1 = models[1]->uid; c.kd = kd->uid; c.mode = mode; c.device = ctx->device;
+    c.m0 = models[0]->uid; c.m1 = uid1; c.kd = kd->uid; c.mode = mode; c.device = ctx->device;
     tc::Params& p = c.p;
+    p.nhid = both ? 1 : 2;
+    p.totplnk_global = (attempt == 2 && mode == 0) ? 1 : 0;
     std::vector<uint8_t> blob;
+    int hid_col = 0;
     for (int n = 0; n < 2; ++n) {
-      const rrnn_model_t* m = models[n];
+      const rrnn_model_t* m = models[both ? 0 : n];
       tc::NetP& nt = p.net[n];
       const int Hraw = m->dims[1];
-      nt.Hraw = Hraw; nt.H = pad16(Hraw); nt.ntot = G;
+      const int O = m->dims[3];            // outputs of the network: G, or 2G for a two-headed one
+      const int o0 = (both && n == 1) ? G : 0;  // first output of this head
+      nt.Hraw = Hraw; nt.H = pad16(Hraw); nt.ntot = Gp;
       nt.act0 = m->act[0]; nt.act1 = m->act[1];
+      nt.hid_col = hid_col;
+      if (!(both && n == 1)) hid_col += nt.H;
       // bias of the output layer on a column of ones: free when the padded K has a spare column, otherwise one more
-      // k-step (first attempt) or not at all (second attempt, when shared memory is short)
+      // k-step (first attempt) or not at all (later attempts, when shared memory is short)
       nt.fold = (Hraw < nt.H) ? 1 : (attempt == 0 ? 1 : 0);
       nt.K3 = (nt.fold && Hraw >= nt.H) ? nt.H + 16 : nt.H;
       const bool tau_type = (mode == 1) || (n == 0);
-      std::vector<double> oscale(G, 1.0), bias(G, 0.0);
+      std::vector<double> oscale(Gp, 1.0), bias(Gp, 0.0);
       for (int o = 0; o < G; ++o) {
-        const double b3 = m->bpack[m->b_off[2] + o];
+        const double b3 = m->bpack[m->b_off[2] + o0 + o];
         if (tau_type) {
           oscale[o] = (double)m->ystd[o] * tc::OUT_SCALE;
           bias[o] = ((double)m->ystd[o] * b3 + (double)m->ymean[o]) * tc::OUT_SCALE;
@@ -1050,34 +1089,43 @@ static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn
           bias[o] = b3;
         }
       }
-      tc::pack_layer(m->wpack.data() + m->w_off[0], nx, Hraw, kin, nt.H, nullptr, -1, nullptr, blob, nt.w[0][0], nt.w[0][1]);
-      tc::pack_layer(m->wpack.data() + m->w_off[1], Hraw, Hraw, nt.H, nt.H, nullptr, -1, nullptr, blob, nt.w[1][0], nt.w[1][1]);
-      tc::pack_layer(m->wpack.data() + m->w_off[2], Hraw, G, nt.K3, G, oscale.data(), nt.fold ? Hraw : -1, bias.data(), blob,
+      if (both && n == 1) {
+        // second head: same hidden stack and activation operand as head 0
+        nt.w[0][0] = p.net[0].w[0][0]; nt.w[0][1] = p.net[0].w[0][1];
+        nt.w[1][0] = p.net[0].w[1][0]; nt.w[1][1] = p.net[0].w[1][1];
+      } else {
+        tc::pack_layer(m->wpack.data() + m->w_off[0], nx, Hraw, Hraw, kin, nt.H, nullptr, -1, nullptr, blob, nt.w[0][0], nt.w[0][1]);
+        tc::pack_layer(m->wpack.data() + m->w_off[1], Hraw, Hraw, Hraw, nt.H, nt.H, nullptr, -1, nullptr, blob, nt.w[1][0], nt.w[1][1]);
+      }
+      // output layer of this head: columns o0 .. o0+G-1 of the (Hraw, O) matrix, rows padded to Gp with zeros
+      tc::pack_layer(m->wpack.data() + m->w_off[2] + o0, Hraw, G, O, nt.K3, Gp, oscale.data(), nt.fold ? Hraw : -1, bias.data(), blob,
                      nt.w[2][0], nt.w[2][1]);
-      // fp32 biases: b1[H], b2[H], b3''[G]
+      // fp32 biases: b1[H], b2[H], b3''[Gp]
       const size_t fb = blob.size();
-      blob.resize(fb + (size_t)(2 * nt.H + G) * 4, 0);
+      blob.resize(fb + (size_t)(2 * nt.H + Gp) * 4, 0);
       float* f = reinterpret_cast<float*>(blob.data() + fb);
       for (int i = 0; i < Hraw; ++i) { f[i] = m->bpack[m->b_off[0] + i]; f[nt.H + i] = m->bpack[m->b_off[1] + i]; }
       for (int o = 0; o < G; ++o) f[2 * nt.H + o] = (float)bias[o];
       nt.b[0] = (uint32_t)fb; nt.b[1] = (uint32_t)(fb + nt.H * 4); nt.b[2] = (uint32_t)(fb + 2 * nt.H * 4);
     }
-    // band of every group of 4 g-points (the kernel multiplies 4 g-points by one Planck value: mixed groups -> fallback)
+    // band of every group of 4 g-points (the kernel multiplies 4 g-points by one Planck value: mixed groups -> fallback);
+    // the padding groups of a ragged last job repeat the last band
     p.off_band4 = (uint32_t)blob.size();
     blob.resize(blob.size() + 64 * 4, 0);
     {
       int* band4 = reinterpret_cast<int*>(blob.data() + p.off_band4);
-      for (int g4 = 0; g4 < G / 4; ++g4) {
-        const int b = kd->gpt2band.empty() ? 0 : kd->gpt2band[4 * g4];
+      for (int g4 = 0; g4 < Gp / 4; ++g4) {
+        const int gq = std::min(4 * g4, G - 4);
+        const int b = kd->gpt2band.empty() ? 0 : kd->gpt2band[gq];
         if (mode == 0)
           for (int e = 1; e < 4; ++e)
-            if (kd->gpt2band[4 * g4 + e] != b) return -1;
+            if (kd->gpt2band[gq + e] != b) return -1;
         band4[g4] = b;
       }
     }
-    // LW: the Planck table totplnk [band][ntemp] rides in the image too
+    // LW: the Planck table totplnk [band][ntemp] rides in the image too (unless shared memory is short)
     p.off_totplnk = (uint32_t)blob.size();
-    if (mode == 0) {
+    if (mode == 0 && !p.totplnk_global) {
       blob.resize(blob.size() + (((size_t)kd->nbnd * kd->ntemp * 4 + 15) & ~(size_t)15), 0);
       memcpy(blob.data() + p.off_totplnk, kd->totplnk.data(), (size_t)kd->nbnd * kd->ntemp * 4);
     }
@@ -1085,10 +1133,11 @@ static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn
     uint32_t off = (p.blob_bytes + 127u) & ~127u;
     p.off_ain_hi = off; off += tc::TM * kin * 2;
     p.off_ain_lo = off; off += tc::TM * kin * 2;
-    for (int n = 0; n < 2; ++n) {
+    for (int n = 0; n < p.nhid; ++n) {
       p.net[n].act_hi = off; off += tc::TM * p.net[n].K3 * 2;
       p.net[n].act_lo = off; off += tc::TM * p.net[n].K3 * 2;
     }
+    if (both) { p.net[1].act_hi = p.net[0].act_hi; p.net[1].act_lo = p.net[0].act_lo; }
     off = (off + 1023u) & ~1023u;
     p.off_stage = off;
     const uint32_t off_stage_end2 = off + 8 * 2 * tc::STAGE_BYTES;  // 8 epilogue warps x 2 staging tiles, if they fit
@@ -1096,20 +1145,17 @@ static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn
     // Per-row records, a ring over tiles.  The front warps start tile t+2 only after every output-layer MMA of tile t
     // has been issued, i.e. when the epilogue (either group) is at most NSLOT jobs short of the end of tile t, which is
     // at most ceil(NSLOT/nchunks) tiles back.
-    const int nchunks = G / 32;
+    const int nchunks = Gp / 32;
     p.nrec = (tc::NSLOT + nchunks - 1) / nchunks + 2;  // (the padded job count of the kernel is >= nchunks: this stays an upper bound)
-    p.off_rec = off; off += (uint32_t)p.nrec * 8 * tc::TM * 4;
+    p.off_rec = off; off += (uint32_t)p.nrec * tc::REC_F * tc::TM * 4;
     p.off_bar = off; off += tc::NBAR * 8 + 16;
     c.smem = (size_t)off + 1024;  // alignment slack
     if (c.smem > ctx->smem_optin) {  // one staging tile per warp instead of two
       const uint32_t shrink = 8 * tc::STAGE_BYTES;
       p.nstage = 1; p.off_rec -= shrink; p.off_bar -= shrink; c.smem -= shrink;
     }
-    if (c.smem > ctx->smem_optin) {
-      if (attempt == 0) continue;
-      return -1;
-    }
-    p.kin = kin; p.nx = nx; p.ngpt = G; p.nchunks = G / 32;
+    if (c.smem > ctx->smem_optin) continue;
+    p.kin = kin; p.nx = nx; p.ngpt = G; p.nchunks = nchunks;
     p.nbnd = kd->nbnd; p.ntemp = kd->ntemp;
     RRNN_CUDA(cudaMalloc((void**)&c.d_blob, blob.size()));
     RRNN_CUDA(cudaMemcpy(c.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -1128,19 +1174,19 @@ static int tc_plan(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn
 // Does the tensor-core kernel take this configuration?  (pipeline.cu decides the workspace layout with it)
 bool rrnn_gas_optics_tc_can(const rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int nlay,
                             bool compact) {
-  if (!ctx->nn_tensor_cores || nmodels != 2 || !models[0] || !models[1]) return false;
-  if (!tc_supported(models, kd, mode)) return false;
+  if (!ctx->nn_tensor_cores || nmodels < 1 || nmodels > 2 || !models[0] || (nmodels == 2 && !models[1])) return false;
+  if (!tc_supported(models, nmodels, kd, mode)) return false;
   if (mode == 0 && nlay < 31) return false;
   if (compact && (mode != 0 || kd->nbnd > 16)) return false;
   return true;
 }
 
 // Launch the tensor-core gas optics; returns -1 if the configuration is not supported (caller falls back).
-int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol, int nlay,
+int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int ncol, int nlay,
                        const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
                        const rrnn_gas_t* gases, int ngas, float* out0, float* out1, float* out2, float* sfc_source,
                        float* sfc_jac, int prof_kind, float* planck_lay, float* planck_lev) {
-  if (!tc_supported(models, kd, mode)) return -1;
+  if (nmodels < 1 || nmodels > 2 || !tc_supported(models, nmodels, kd, mode)) return -1;
   const bool compact = planck_lay != nullptr;  // LW only: out1 receives the Planck fraction, out2 is not written
   if (compact && (mode != 0 || !planck_lev || kd->nbnd > 16)) return -1;
   const int period = (mode == 0) ? nlay + 1 : nlay;
@@ -1148,7 +1194,7 @@ int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const 
   if ((long long)ncol * period >= (1LL << 31) - tc::TM) return -1;
   TcCache cache;
   {
-    const int rc = tc_plan(ctx, mode, kd, models, &cache);
+    const int rc = tc_plan(ctx, mode, kd, models, nmodels, &cache);
     if (rc != 0) return rc;
   }
   tc::Params p = cache.p;
@@ -1231,6 +1277,8 @@ int rrnn_gas_optics_tc(rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const 
   }
   prof_end(ctx, prof_kind, ps);
   RRNN_LAUNCH_CHECK(ctx);
+  ctx->last_nn_kernel = RRNN_NN_KERNEL_TCGEN05;
+  ctx->nn_tc_launches++;
   if (dbg_flags) {
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     fprintf(stderr, "[tc debug] mode %d ncol %d nlay %d grid %u smem %zu -> %s | front %08x mma %08x epi %08x store %08x | wd %08x bar %08x par %u blk %u | init %08x\n",

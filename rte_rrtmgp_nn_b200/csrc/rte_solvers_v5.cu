@@ -249,8 +249,6 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
     float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
     float* fdn = fup + (L + 1);
     for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
-    // the previous column's discards (generic proxy) are ordered before this column's bulk stores (async proxy) to the same lines
-    if (RRNN_V5_DISCARD) asm volatile("fence.proxy.async.global;" ::: "memory");
     const size_t gc_off = (size_t)col * G + gs;
     const f2 emis = ldg2(p.sfc_emis + gc_off);
     const f2 ssrc = ldg2(p.sfc_source + gc_off);
@@ -269,6 +267,9 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
     __syncwarp();
 
     for (int imu = 0; imu < p.nmus; ++imu) {
+      // the discards of the previous upward sweep (previous column, or previous angle of this one; generic proxy) are ordered
+      // before this sweep's bulk stores (async proxy) to the same scratch lines
+      if (RRNN_V5_DISCARD) asm volatile("fence.proxy.async.global;" ::: "memory");
       const f2 D = splat2(p.Ds[imu]);
       const f2 fac = splat2(2.0f * kPi * p.wts[imu] * live);
       const float rad_norm = 2.0f * kPi * p.wts[imu];
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
 #pragma unroll
         for (int h = 0; h < NOB; ++h) {
           // reverse-buffer staging tile (k*NOB + h) & 1 (OBR layers): free once the bulk store issued two tiles ago has read it
-          if (lane == 0) bulk_wait_read<1>();
+          if (elect_one()) bulk_wait_read<1>();
           __syncwarp();
           const int slot = (k * NOB + h) & 1;
           uint8_t* ot = ob + slot * (OBR * 512) + lane_bf;
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_cons
         if (lane == 0) fup[TOP ? L : 0] += s;
       }
       // ---------------- upward sweep (reverse order) from the scratch ring ----------------
-      if (lane == 0) bulk_wait_all();  // all reverse-buffer stores have landed
+      if (elect_one()) bulk_wait_all();  // all reverse-buffer stores have landed (bulk groups are per thread: the electing lane issued them)
       __syncwarp();
       auto issue_bb = [&](int j) {  // j-th group of the upward sweep = forward group NG-1-j
         if (j < NG) {
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
         // ago has read it
 #pragma unroll
         for (int t = 0; t < NST; ++t) {
-          if (lane == 0) bulk_wait_read<1>();
+          if (elect_one()) bulk_wait_read<1>();
           __syncwarp();
           const int slot = ((k * NOB + h) * NST + t) & 1;
           uint8_t* ot = ob + slot * (STL * SWROW);
@@ -845,7 +846,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
       if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
     }
     // ---------------- sweep 2: surface -> top (back substitution) ----------------
-    if (lane == 0) bulk_wait_all();
+    if (elect_one()) bulk_wait_all();
     __syncwarp();
     auto issue_bb = [&](int j) {
       if (j < NG) {

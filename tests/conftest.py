@@ -25,11 +25,19 @@ def gpu_ctx():
 @pytest.fixture(params=[1, 0], ids=["tensor_cores", "fp32_ffma"])
 def nn_variant(request, gpu_ctx):
     """Both MLP variants of the NN gas optics: tcgen05 tensor cores (the default) and the fp32 FFMA kernel, each with
-    the tau tolerance stated for it (helpers.TAU_RTOL_*)."""
+    the tau tolerance stated for it (helpers.TAU_RTOL_*).  The fixture checks WHICH kernel served the test's gas-optics
+    calls (rrnn_ctx_nn_kernel_counts): a "tensor_cores" id fails if the FFMA kernel ran, and the other way round."""
     import helpers as H
     gpu_ctx.set_flag("nn_tensor_cores", request.param)
+    tc0, ff0 = gpu_ctx.nn_kernel_counts
     yield (H.TAU_RTOL_TC if request.param else H.TAU_RTOL_FP32)
+    tc1, ff1 = gpu_ctx.nn_kernel_counts
     gpu_ctx.set_flag("nn_tensor_cores", 1)
+    if request.param:
+        assert ff1 == ff0, f"a tensor_cores test ran the fp32 FFMA kernel {ff1 - ff0} time(s) (silent fallback)"
+        assert tc1 > tc0, "a tensor_cores test never launched the tcgen05 kernel"
+    else:
+        assert tc1 == tc0, f"an fp32_ffma test ran the tcgen05 kernel {tc1 - tc0} time(s)"
 
 
 @pytest.fixture(params=[0, 2, 1], ids=["v5_tma_packed", "v4_packed", "v3_scalar"])

@@ -13,6 +13,13 @@ LW_G128 = ("lw-g128-210809_absorption_BEST.nc", "lw-g128-210809_planck_frac_BEST
 LW_G128_BOTH = ("lw-g128-210809_both_BEST.nc",)
 LW_G128_NWP = ("rrtmgp-data-lw-g128-210809_NN_GCM_NWP_absorption.nc", "rrtmgp-data-lw-g128-210809_NN_GCM_NWP_planck_frac.nc")
 SW_G112 = ("sw-g112-210809_absorption_BEST.nc", "sw-g112-210809_rayleigh_BEST.nc")
+# further shipped generations: 64-wide absorption net (hidden width == its padding: the folded output bias needs one more
+# k-step), 58-wide g128, the 56- and 72-wide two-headed nets, the 16-wide g112 Rayleigh net
+LW_G128_64 = ("lw-g128-210809_absorption_64_64_HR_1.12e+00_FRC_9.82e-01.nc", "lw-g128-210809_planck_frac_24_24.nc")
+LW_G128_58 = ("lw-g128-210809_absorption_58_58_HR_1.46e+00_FRC_1.56e+00.nc", "lw-g128-210809_planck_frac_24_24_HR_1.15e+00_FRC_7.06e-01.nc")
+LW_G128_BOTH56 = ("lw-g128-210809_both_56_56_HR_1.11e+00_FRC_7.57e-01.nc",)
+LW_G128_BOTH72 = ("lw-g128-210809_both_72_72_HR_1.01e+00_FRC_1.83e+00.nc",)
+SW_G112_16 = ("sw-g112-210809_absorption_32_32_HR_9.48e-01_FRC_6.07e-01.nc", "sw-g112-210809_rayleigh_16_16_HR_1.11e+00_FRC_4.93e+01.nc")
 
 # tolerances stated by BASELINE.json north_star
 FLUX_TOL = 0.01      # W m-2, every level

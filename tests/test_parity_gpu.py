@@ -39,7 +39,9 @@ def _run_lw_gas_optics(ctx, k_dist, dnets, atm, use_tlev=True):
 
 
 @pytest.mark.parametrize("files,ngpt,nlay,ncol", [(H.LW_G256, 256, 60, 50), (H.LW_G128, 128, 33, 37),
-                                                  (H.LW_G128_NWP, 128, 137, 9), (H.LW_G128_BOTH, 128, 60, 21)])
+                                                  (H.LW_G128_NWP, 128, 137, 9), (H.LW_G128_BOTH, 128, 60, 21),
+                                                  (H.LW_G128_64, 128, 91, 13), (H.LW_G128_58, 128, 60, 8),
+                                                  (H.LW_G128_BOTH56, 128, 47, 11), (H.LW_G128_BOTH72, 128, 137, 5)])
 def test_lw_gas_optics_matches_oracle(gpu_ctx, nn_variant, files, ngpt, nlay, ncol):
     import oracle as O
     kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, files, ngpt, ncol, nlay)
@@ -64,7 +66,9 @@ def test_lw_gas_optics_without_tlev(gpu_ctx):
 
 
 @pytest.mark.parametrize("files,ngpt,nlay,ncol,flip,nang", [(H.LW_G256, 256, 60, 40, False, 1), (H.LW_G256, 256, 60, 13, True, 1),
-                                                           (H.LW_G128, 128, 91, 17, False, 3), (H.LW_G128, 128, 137, 6, False, 1)])
+                                                           (H.LW_G128, 128, 91, 17, False, 3), (H.LW_G128, 128, 137, 6, False, 1),
+                                                           (H.LW_G128_NWP, 128, 60, 12, False, 1), (H.LW_G128_BOTH, 128, 91, 10, True, 2),
+                                                           (H.LW_G128_BOTH72, 128, 60, 7, False, 1)])
 def test_lw_fluxes_match_oracle(gpu_ctx, nn_variant, files, ngpt, nlay, ncol, flip, nang):
     import oracle as O
     from rte_rrtmgp_nn_b200 import api
@@ -155,6 +159,36 @@ def test_lw_solver_alone_random_inputs(gpu_ctx, solver_variant):
         assert np.abs(dn.cpu().numpy() - rdn).max() <= 2e-5 * scale
 
 
+def test_lw_solver_three_angles_many_columns(gpu_ctx):
+    """n_gauss_angles = 3 at 137 layers with many more columns than resident clusters: every angle's downward sweep
+    rewrites the scratch rows the previous angle's upward sweep has just discarded from the L2 (the proxy fence between
+    the two sits inside the angle loop).  Every column against the oracle, and twice for run-to-run bit identity."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    rng = np.random.default_rng(21)
+    G, L, C = 128, 137, 4000
+    tau = rng.gamma(0.3, 2.0, size=(C, L, G)).astype(np.float32)
+    lay = rng.uniform(0.1, 2.0, size=(C, L, G)).astype(np.float32)
+    lev = rng.uniform(0.1, 2.0, size=(C, L + 1, G)).astype(np.float32)
+    emis = rng.uniform(0.8, 1.0, size=(C, G)).astype(np.float32)
+    ssrc = rng.uniform(0.1, 2.0, size=(C, G)).astype(np.float32)
+    rup, rdn = O.lw_solver_noscat_GaussQuad(True, 3, tau, lay, lev, emis, ssrc)
+    d = [torch.from_numpy(a).cuda() for a in (tau, lay, lev, emis, ssrc)]
+    Ds = np.array([1.09719858, 1.69338507, 4.70941630], np.float32)
+    w = np.array([0.2009319137, 0.2292411064, 0.0698269799], np.float32)
+    outs = []
+    for _ in range(2):
+        up = torch.empty((C, L + 1), device="cuda"); dn = torch.empty_like(up)
+        _lib.check(_lib.lib().rrnn_lw_solver_noscat(gpu_ctx.h, G, L, C, 1, 3, Ds.ctypes.data_as(_lib.c_float_p),
+                                                    w.ctypes.data_as(_lib.c_float_p), None, *[api._ptr(t) for t in d],
+                                                    api._ptr(up), api._ptr(dn)))
+        outs.append((up.cpu().numpy(), dn.cpu().numpy()))
+    scale = max(np.abs(rup).max(), 1.0)
+    assert np.abs(outs[0][0] - rup).max() <= 2e-5 * scale and np.abs(outs[0][1] - rdn).max() <= 2e-5 * scale
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def _sw_setup(ctx, files, ngpt, ncol, nlay, seed=2, flip=False):
     from rte_rrtmgp_nn_b200 import api, spectral, synth
     kd = spectral.synthetic_kdist_sw(ngpt=ngpt)
@@ -167,7 +201,7 @@ def _sw_setup(ctx, files, ngpt, ncol, nlay, seed=2, flip=False):
 
 
 @pytest.mark.parametrize("files,ngpt,nlay,ncol,flip", [(H.SW_G224, 224, 60, 45, False), (H.SW_G112, 112, 91, 14, False),
-                                                      (H.SW_G224, 224, 137, 5, True)])
+                                                      (H.SW_G224, 224, 137, 5, True), (H.SW_G112_16, 112, 60, 9, True)])
 def test_sw_gas_optics_and_fluxes_match_oracle(gpu_ctx, nn_variant, files, ngpt, nlay, ncol, flip):
     import oracle as O
     from rte_rrtmgp_nn_b200 import api
