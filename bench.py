@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--solver-scratch-mb", type=int, default=0, help="L2 budget of the packed solvers' reverse-sweep scratch (0 = default)")
     ap.add_argument("--lw-compact-source", type=int, default=1, help="1 = LW sources stay factored between gas optics and solver (default), 0 = materialised lay/lev_source")
     ap.add_argument("--solver-warps", type=int, default=0, help="solvers (warps) per CTA in the v5 solver kernels (0 = default)")
+    ap.add_argument("--lw-solver-gen", type=int, default=0, help="generation of the packed LW solver: 0 default, 5 staged scratch, 6 direct scratch")
+    ap.add_argument("--sw-solver-gen", type=int, default=0, help="the same for the SW solver")
     args = ap.parse_args()
     NLAY = args.nlay
     args.steps = max(1, args.steps)
@@ -279,6 +281,8 @@ def main():
     ctx.set_flag("solver_variant", args.solver_variant)
     ctx.set_flag("solver_scratch_mb", args.solver_scratch_mb)
     ctx.set_flag("solver_warps", args.solver_warps)
+    ctx.set_flag("lw_solver_gen", args.lw_solver_gen)
+    ctx.set_flag("sw_solver_gen", args.sw_solver_gen)
     ctx.set_flag("lw_compact_source", args.lw_compact_source)
     if args.chunk:
         ctx.set_chunk_columns(args.chunk)
@@ -457,7 +461,8 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, ncol_total),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "fast_math": int(args.fast_math), "sw_fast_math": int(args.sw_fast_math), "lw_compact_source": int(bool(args.lw_compact_source) and args.solver_variant == 0), "nn_variant": "tcgen05 (fp16 hi/lo split operands, fp32 accumulation in TMEM)",
-        "solver_variant": {0: "v5 TMA-staged packed fp32x2", 2: "v4 packed fp32x2", 1: "v3 one g-point per lane"}[args.solver_variant],
+        "solver_variant": {0: "v6 TMA-staged packed fp32x2, direct reverse-sweep scratch", 5: "v5 TMA-staged packed fp32x2 (staged scratch)",
+                           1: "v3 one g-point per lane"}.get(args.solver_variant, str(args.solver_variant)),
     }
     emit(line)
     if world > 1:

@@ -461,6 +461,8 @@ extern "C" int rrnn_ctx_set_flag(rrnn_ctx_t* c, const char* name, int value) {
   else if (s == "nn_tensor_cores") c->nn_tensor_cores = value ? 1 : 0;
   else if (s == "lw_compact_source") c->lw_compact_source = value ? 1 : 0;
   else if (s == "solver_variant") c->solver_variant = value;
+  else if (s == "lw_solver_gen") c->lw_solver_gen = value;
+  else if (s == "sw_solver_gen") c->sw_solver_gen = value;
   else if (s == "solver_scratch_mb") c->solver_scratch_mb = value;
   else if (s == "solver_warps") c->solver_warps = value;
   else return fail("rrnn_ctx_set_flag: unknown flag " + s);

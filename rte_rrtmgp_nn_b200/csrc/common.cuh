@@ -57,7 +57,8 @@ struct rrnn_ctx {
                            // 9.1e-3 both, strict fp32 oracle 6.4e-2 / 9.4e-3 at 200 x 137): the two-stream formulas' own conditioning
                            // sets the error, not 1-ulp differences of rcp / sqrt / exp; the solver is 11 % faster without them
   int solver_buffer = 0;   // reverse-sweep buffer: 0 auto, 1 shared memory, 2 L2-resident global scratch
-  int solver_variant = 0;  // 0 = TMA-staged packed kernels (rte_solvers_v5.cu), 2 = packed with per-lane loads (v4), 1 = one g-point per lane (rte_solvers.cu)
+  int solver_variant = 0;  // 0 = TMA-staged packed kernels (rte_solvers_v5.cu), 1 = one g-point per lane (rte_solvers.cu)
+  int lw_solver_gen = 0, sw_solver_gen = 0;  // generation of the TMA-staged packed kernel per solver: 0 = default, 5 = staged scratch (v5), 6 = direct scratch (v6)
   int solver_scratch_mb = 0;  // L2 budget of the packed kernels' reverse-sweep scratch (0 = default)
   int solver_warps = 0;       // solvers per CTA in the v5 kernels (0 = default)
   void* scratch = nullptr;

@@ -396,8 +396,10 @@ using namespace rrnn;
 
 namespace rrnn {
 int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v5.cu (TMA-staged, packed); -1 = shape not supported
+int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p);           // its direct-scratch generation (default)
 int launch_lw_v4(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v4.cu (packed, per-lane loads)
 int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast);
+int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast);  // direct-scratch generation of the TMA-staged packed kernel (default)
 int launch_sw_v4(rrnn_ctx_t* ctx, SwParams& p, bool fast);
 }
 
@@ -440,7 +442,7 @@ extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int nc
   const int ps = prof_begin(ctx, K_LW_SOLVER);
   int rc4 = -1;
   if (ctx->solver_variant == 0) {
-    rc4 = launch_lw_v5(ctx, p);
+    rc4 = ctx->lw_solver_gen == 5 ? launch_lw_v5(ctx, p) : launch_lw_v6(ctx, p);
     if (rc4 > 0) return rc4;
   }
   if (rc4 < 0 && (ctx->solver_variant == 0 || ctx->solver_variant == 2)) {
@@ -498,7 +500,7 @@ int lw_solver_noscat_compact(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int 
   p.tau = tau_d; p.lay_source = pfrac_d; p.planck_lay = planck_lay_d; p.planck_lev = planck_lev_d; p.gpt2band = gpt2band_d;
   p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
   const int ps = prof_begin(ctx, K_LW_SOLVER);
-  const int rc = launch_lw_v5(ctx, p);
+  const int rc = ctx->lw_solver_gen == 5 ? launch_lw_v5(ctx, p) : launch_lw_v6(ctx, p);
   if (rc < 0) return fail("lw_solver (compact sources): shape not supported by the packed kernel");
   if (rc > 0) return rc;
   prof_end(ctx, K_LW_SOLVER, ps);
@@ -543,7 +545,7 @@ extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
   const int ps = prof_begin(ctx, K_SW_SOLVER);
   int rc4 = -1;
   if (ctx->solver_variant == 0) {
-    rc4 = launch_sw_v5(ctx, p, fast);
+    rc4 = ctx->sw_solver_gen == 5 ? launch_sw_v5(ctx, p, fast) : launch_sw_v6(ctx, p, fast);
     if (rc4 > 0) return rc4;
   }
   if (rc4 < 0 && (ctx->solver_variant == 0 || ctx->solver_variant == 2)) {

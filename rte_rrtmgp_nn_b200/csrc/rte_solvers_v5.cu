@@ -918,6 +918,619 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_cons
   cluster.sync();
 }
 
+// ==================================================================================================== v6
+// Second generation of the TMA-staged packed solvers.  What ncu and three ablation builds of sw_solver_v5 showed
+// (profiles/r2_sw_solver_ablation.md): the kernel is latency-bound -- its time is inversely proportional to the resident
+// warps (7.7 / 11.5 warps per SM: 6.2 / 4.45 ms) and indifferent to the L2 spill of the scratch (60 against 137 layers at
+// equal work: no faster) --, the butterfly reductions cost 12 % although they are 7 % of the instructions, and 2.4 of
+// 4.45 ms remain with all arithmetic removed: the per-group machinery (staging tiles, proxy fences, MEMBAR, elect / bulk
+// store sequences, mbarrier waits of the upward sweep) is what a column trip waits for.  So here
+//   * the reverse-sweep rows go to the L2-resident scratch with plain per-lane 8-byte stores at immediate offsets
+//     (three coalesced 256-byte segments per layer: e | f | alpha_above) and come back by per-lane loads issued one group
+//     of 8 layers ahead into registers: no staging tiles, no fences, no bulk-copy issue, no mbarrier on the way up;
+//   * the shared memory that frees (6 KB of 17.7 per solver) is what lets 8 instead of 6 CTAs = 16 instead of 11.5 solver
+//     warps reside per SM (the kernels stay at <= 128 registers);
+//   * the per-level broadband sums are a transposition through 2.3 KB of shared memory (each lane stores its 16 values,
+//     16 lanes x 2 halves each add one value over 16 lanes with four 16-byte loads, one shuffle joins the halves):
+//     42 instead of ~100 instructions per group and direction, and no selects;
+//   * a ragged last group only computes the halves it needs (137 = 17 x 8 + 1 used to cost a whole group).
+// Arithmetic, orientation handling, the cluster combine and every interface are those of v5.
+__device__ __forceinline__ void stg_scr(uint8_t* p, f2 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v.v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ f2 ldg_scr(const uint8_t* p, uint64_t pol) {
+  f2 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v.v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+#ifndef RRNN_V6_SW_S
+#define RRNN_V6_SW_S 3  // stages of the input ring (groups of 8 layers in flight ahead of the downward sweep)
+#endif
+#ifndef RRNN_V6_LW_MINB
+#define RRNN_V6_LW_MINB 4  // 4 CTAs of 128 threads = 16 warps per SM: at most 128 registers per thread
+#endif
+#ifndef RRNN_V6_MINB
+#define RRNN_V6_MINB 3  // 3 CTAs of 128 threads = 12 warps per SM: at most 168 registers per thread
+#endif
+constexpr int TR_PITCH = 36;  // floats per row of the transposition buffer (32 lanes + 4: conflict-free 16-byte reads)
+// All-lane sums of N (8 or 16) values per lane through shared memory: on return lane l holds the sum of v[l % N].
+// Fixed summation order (deterministic).  tr: [N][TR_PITCH] floats owned by the warp.
+template <int N>
+__device__ __forceinline__ float tr_reduce(const float (&v)[N], float* tr, int lane) {
+  static_assert(N == 8 || N == 16, "tr_reduce: 8 or 16 values");
+  constexpr int PER = 32 / (32 / N) / 1;  // lanes summed by one reader = N ... readers per value = 32 / N
+  constexpr int NRD = 32 / N;             // readers per value (2 or 4), each over 32 / NRD = N lanes
+  (void)PER;
+  __syncwarp();  // the readers of the previous call are done with tr
+#pragma unroll
+  for (int i = 0; i < N; ++i) tr[i * TR_PITCH + lane] = v[i];
+  __syncwarp();
+  const int idx = lane & (N - 1), part = lane / N;
+  const float4* src = reinterpret_cast<const float4*>(tr + idx * TR_PITCH + part * N);
+  float4 q[N / 4];
+#pragma unroll
+  for (int j = 0; j < N / 4; ++j) q[j] = src[j];
+  float s[N / 4];
+#pragma unroll
+  for (int j = 0; j < N / 4; ++j) s[j] = (q[j].x + q[j].y) + (q[j].z + q[j].w);
+  float t = (N == 16) ? (s[0] + s[1]) + (s[2] + s[N / 4 - 1]) : s[0] + s[1];
+  if (NRD == 4) t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return t;
+}
+
+// rows of the reverse-sweep scratch: three 256-byte segments (32 lanes x 8 B) per layer
+constexpr int SW6_ROW = 768, SW6_F = 256, SW6_A = 512;
+
+template <bool FAST, bool HAS_G, bool TOP>
+__global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
+                                                   const __grid_constant__ CUtensorMap tm_ssa, const __grid_constant__ CUtensorMap tm_g) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int U = 8, S = HAS_G ? 2 : RRNN_V6_SW_S, SB = 2, H = 4, NH = U / H;  // groups of 8 layers (one TMA box), coefficients in halves of 4
+  static_assert(SB * U * SW6_ROW <= S * (HAS_G ? 3 : 2) * U * 256, "the upward sweep's stages live in the input ring");
+  const SwParams& p = pp.b;
+  constexpr int NIN = HAS_G ? 3 : 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
+  const int G = p.ngpt, L = p.nlay;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t pol_buf = policy_evict_last();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int chunk = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
+  uint8_t* in_ring = smem;                                                   // [S][NIN][U][256 B]: tau, ssa (, g)
+  float* tr = reinterpret_cast<float*>(in_ring + S * NIN * U * 256);         // [16][TR_PITCH]
+  float* part = tr + 16 * TR_PITCH;                                          // [2 sets][3][L+1]
+  const int part_set = 3 * (L + 1) + ((L + 1) & 1);                          // keeps the barriers 8-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
+  const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
+  const uint32_t in_a = smem_u32(in_ring);
+  if (lane == 0) {
+    for (int s = 0; s < S + SB; ++s) mbar_init(bar_in + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t n_in = 0, n_bb = 0;
+
+  const int g = chunk * 64 + 2 * lane;
+  const bool act = g < G;
+  const int gs = act ? g : chunk * 64;
+  const f2 live = splat2(act ? 1.0f : 0.0f);
+  const int NG = pp.ngroups;
+  const int NGF = L / U;
+  // this lane's 8-byte slot in the e-segment of scratch row 0 of this solver
+  uint8_t* const srow = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * SW6_ROW + (size_t)lane * 8u;
+  const uint32_t lane_in = (uint32_t)lane * 8u;
+  const int top_level = TOP ? 0 : L;
+  // which of the 16 reduced values of a group this lane ends up with: lanes 0-7 / 16-23 quantity A of layer u = lane & 7,
+  // lanes 8-15 / 24-31 quantity B; only lanes < 16 write
+  const int ru = lane & 7;
+  const bool rB = (lane & 8) != 0, rW = lane < 16;
+
+  int ncols_done = 0;
+  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
+    const bool owner = cb + warp < p.ncol;
+    const int col = owner ? cb + warp : p.ncol - 1;
+    float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [3][L+1]
+    float* fdn = fup + (L + 1);
+    float* fdr = fdn + (L + 1);
+    for (int i = lane; i < 3 * (L + 1); i += 32) fup[i] = 0.0f;
+    const size_t gc_off = (size_t)col * G + gs;
+    const float mu0 = __ldg(p.mu0 + col);
+    const float mu0_inv = 1.0f / mu0;
+    const int lay0 = col * L + (TOP ? 0 : L - 1);
+    f2 dir = (live * ldg2(p.inc_flux + gc_off)) * splat2(mu0);                        // :589
+    f2 beta = p.inc_flux_dif ? live * ldg2(p.inc_flux_dif + gc_off) : splat2(0.0f);   // :590
+    f2 alpha = splat2(0.0f);
+    const f2 a_s = ldg2(p.alb_dif + gc_off);
+    const f2 a_d = ldg2(p.alb_dir + gc_off);
+    __syncwarp();
+    {
+      const float sd = warp_sum(hsum2(dir)), sb = warp_sum(hsum2(beta + dir));
+      if (lane == 0) { fdr[top_level] += sd; fdn[top_level] += sb; }
+    }
+    auto issue_in = [&](int k) {
+      if (k < NG) {
+        const uint32_t st = (n_in + (uint32_t)k) % S;
+        int sh;
+        const int rl = box_start<TOP, U>(lay0, k, sh);
+        if (elect_one()) {
+          const uint32_t bar = bar_in + 8 * st;
+          const uint32_t dst = in_a + st * (NIN * U * 256);
+          mbar_expect_tx(bar, NIN * U * 256);
+          tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
+          tma_load_2d(dst + U * 256, &tm_ssa, chunk * 64, rl, bar, pol_in);
+          if (HAS_G) tma_load_2d(dst + 2 * U * 256, &tm_g, chunk * 64, rl, bar, pol_in);
+        }
+        __syncwarp();
+      }
+    };
+#pragma unroll
+    for (int k = 0; k < S - 1; ++k) issue_in(k);
+    // per-level broadband sums of a group: reduced one group later (their latency then overlaps the next group's arithmetic)
+    float pend[2 * U];
+#pragma unroll
+    for (int u = 0; u < 2 * U; ++u) pend[u] = 0.0f;
+    int pend_k = -1;
+    auto flush_fwd = [&]() {  // pend[u] = dir, pend[U + u] = diffuse + dir at the bottom of sweep layer pend_k * U + u
+      const float t = tr_reduce<2 * U>(pend, tr, lane);
+      const int i = pend_k * U + ru;
+      if (rW && pend_k >= 0 && i < L) {
+        float* dst = (rB ? fdn : fdr) + (TOP ? i + 1 : L - 1 - i);
+        *dst += t;
+      }
+    };
+    auto flush_bwd = [&]() {  // pend[u] = up, pend[U + u] = alpha_above * up at the top of sweep layer pend_k * U + (U - 1 - u)
+      const float t = tr_reduce<2 * U>(pend, tr, lane);
+      const int i = pend_k * U + (U - 1 - ru);
+      if (rW && pend_k >= 0 && i < L) {
+        float* dst = (rB ? fdn : fup) + (TOP ? i : L - i);
+        *dst += t;
+      }
+    };
+    // ---------------- sweep 1: top -> surface ----------------
+    auto forward_group = [&](int k, auto tail_c) {
+      constexpr bool TAIL = decltype(tail_c)::value;
+      __syncwarp();
+      issue_in(k + S - 1);
+      const uint32_t nk = n_in + (uint32_t)k;
+      const uint32_t st = nk % S;
+      mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
+      const uint8_t* base = in_ring + st * (NIN * U * 256) + lane_in;
+      int shl = 0, nvalid = U;
+      if (TAIL) {
+        box_start<TOP, U>(lay0, k, shl);
+        nvalid = min(U, L - k * U);
+      }
+      flush_fwd();
+      uint8_t* const sg = srow + (size_t)k * (U * SW6_ROW);
+      float red[2 * U];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        if (TAIL && h * H >= nvalid) {  // warp-uniform: nothing of this half belongs to the column
+#pragma unroll
+          for (int uu = 0; uu < H; ++uu) { red[h * H + uu] = 0.0f; red[U + h * H + uu] = 0.0f; }
+          continue;
+        }
+        f2 tau[H], w0[H], gg[H];
+#pragma unroll
+        for (int uu = 0; uu < H; ++uu) {
+          const int u = h * H + uu;
+          const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
+          tau[uu] = lds2(base + rl * 256);
+          w0[uu] = lds2(base + U * 256 + rl * 256);
+          gg[uu] = HAS_G ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
+        }
+        f2 Rdif[H], Tdif[H], Rdir[H], Tdir[H], Tnos[H];
+        two_stream2_batch<FAST, HAS_G, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+#pragma unroll
+        for (int uu = 0; uu < H; ++uu) {
+          const int u = h * H + uu;
+          if (!TAIL || u < nvalid) {  // warp-uniform
+            const f2 s_up = Rdir[uu] * dir;
+            const f2 s_dn = Tdir[uu] * dir;
+            dir = Tnos[uu] * dir;
+            const f2 d = rcp2<FAST>(fnma2(Rdif[uu], alpha, splat2(1.0f)));
+            const f2 e = d * Tdif[uu];
+            const f2 f = d * fma2(Rdif[uu], beta, s_up);
+            stg_scr(sg + u * SW6_ROW, e, pol_buf);
+            stg_scr(sg + u * SW6_ROW + SW6_F, f, pol_buf);
+            stg_scr(sg + u * SW6_ROW + SW6_A, alpha, pol_buf);  // reflectance of the atmosphere ABOVE this layer: what sweep 2 needs
+            beta = fma2(e, fma2(alpha, s_up, beta), s_dn);
+            alpha = fma2(Tdif[uu] * e, alpha, Rdif[uu]);
+          }
+          red[u] = hsum2(dir);
+          red[U + u] = hsum2(beta + dir);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
+      pend_k = k;
+    };
+    {
+      const int nfast = (TOP || col > 0) ? NGF : max(NGF - 1, 0);
+      for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
+      for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
+    }
+    flush_fwd();
+    pend_k = -1;
+    n_in += (uint32_t)NG;
+    // ---------------- surface ----------------
+    const f2 S_s = dir * a_d;  // source_sfc :1477
+    f2 Uu = div2<FAST>(fma2(a_s, beta, S_s), fnma2(a_s, alpha, splat2(1.0f))) * live;
+    {
+      const int sfc = TOP ? L : 0;
+      const float su = warp_sum(hsum2(Uu)), sa = warp_sum(hsum2(alpha * Uu));
+      if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
+    }
+    // ---------------- sweep 2: surface -> top (back substitution) ----------------
+    // The rows of a group come back with ONE bulk copy into the (now idle) input ring (SB stages), SB - 1 groups ahead of
+    // their use; a group is pulled into registers in one go, which frees its stage for the copy of the group SB further up.
+    asm volatile("fence.proxy.async.global;" ::: "memory");  // this lane's row stores (generic proxy) before the bulk loads (async proxy)
+    __syncwarp();
+    auto issue_bb = [&](int j) {  // j-th group of the upward sweep = forward group NG-1-j -> stage (n_bb + j) % SB
+      if (j < NG) {
+        const int k = NG - 1 - j;
+        const uint32_t st = (n_bb + (uint32_t)j) % SB;
+        const uint32_t bytes = (uint32_t)min(U, L - k * U) * SW6_ROW;
+        if (elect_one()) {
+          mbar_expect_tx(bar_bb + 8 * st, bytes);
+          bulk_load(in_a + st * (U * SW6_ROW), srow - (size_t)lane * 8u + (size_t)k * (U * SW6_ROW), bytes, bar_bb + 8 * st, pol_buf);
+        }
+        __syncwarp();
+      }
+    };
+#pragma unroll
+    for (int j = 0; j < SB - 1; ++j) issue_bb(j);
+    auto backward_group = [&](int j, auto tail_c) {
+      constexpr bool TAIL = decltype(tail_c)::value;
+      const int k = NG - 1 - j;
+      const int nvalid = TAIL ? min(U, L - k * U) : U;
+      __syncwarp();  // every lane has pulled the previous group into registers: its stage may be refilled
+      issue_bb(j + SB - 1);
+      const uint32_t nj = n_bb + (uint32_t)j;
+      const uint32_t st = nj % SB;
+      mbar_wait(bar_bb + 8 * st, (nj / SB) & 1u);
+      f2 e[U], f[U], a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint8_t* row = in_ring + st * (U * SW6_ROW) + (TAIL ? min(u, nvalid - 1) : u) * SW6_ROW + lane_in;
+        e[u] = lds2(row);
+        f[u] = lds2(row + SW6_F);
+        a[u] = lds2(row + SW6_A);
+      }
+      flush_bwd();
+      float red[2 * U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
+        const int uu = U - 1 - u;
+        if (!TAIL || uu < nvalid) Uu = fma2(e[uu], Uu, f[uu]);
+        red[u] = hsum2(Uu);               // upward flux at the level on top of that layer
+        red[U + u] = hsum2(a[uu] * Uu);   // diffuse downward flux there: alpha_above * U (+ beta, added in sweep 1)
+      }
+      // the rows are in registers: their L2 lines are dead (no write-back; the next column rewrites them in full)
+      discard_scratch(srow - (size_t)lane * 8u + (size_t)k * (U * SW6_ROW), (uint32_t)nvalid * SW6_ROW, lane);
+#pragma unroll
+      for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
+      pend_k = k;
+    };
+    {
+      int j = 0;
+      if (NG > NGF) backward_group(j++, std::true_type{});  // the ragged group comes first on the way up
+      for (; j < NG; ++j) backward_group(j, std::false_type{});
+    }
+    n_bb += (uint32_t)NG;
+    flush_bwd();
+    pend_k = -1;
+    __syncwarp();
+    // ---- combine the chunks of this column (see lw_solver_v5)
+    cluster.sync();
+    {
+      float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1), p.flux_dir + (size_t)col * (L + 1)};
+      const int n = 3 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
+      for (int i = lo + lane; i < hi && owner; i += 32) {
+        float sacc = 0.0f;
+        for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
+        const int a = i / (L + 1);
+        gout[a][i - a * (L + 1)] = sacc;
+      }
+    }
+  }
+  cluster.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------- LW, v6
+// lw_solver_v5 with the v6 machinery (see sw_solver_v6): reverse-sweep rows (t | source_up: two 256-byte segments per
+// layer) stored per lane at immediate offsets, brought back by one bulk copy per group into the idle input ring and pulled
+// into registers; per-level sums by transposition through shared memory; a ragged last group computes only its layers.
+constexpr int LW6_ROW = 512, LW6_S = 256;
+
+template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT>
+__global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
+                                                   const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev,
+                                                   const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int U = 8, S = 2, SB = 2;
+  // one stage of the input ring.  Materialised: tau | lay_source | lev_source(ext rows), U rows of 256 B each.
+  // COMPACT: tau (U rows) | pfrac (PFR rows: top-down sweeps also need the next layer's) | B_lay | B_lev(ext) (U rows of 64 B)
+  constexpr int PFR = COMPACT ? (TOP ? U + 1 : U) : U;
+  constexpr int OFF_PF = U * 256, OFF_3 = OFF_PF + PFR * 256, OFF_BV = OFF_3 + U * 64;
+  constexpr int STAGE = COMPACT ? OFF_BV + U * 64 : 3 * U * 256;
+  static_assert(SB * U * LW6_ROW <= S * STAGE, "the upward sweep's stages live in the input ring");
+  const LwParams& p = pp.b;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
+  const int G = p.ngpt, L = p.nlay;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t pol_buf = policy_evict_last();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int chunk = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
+  uint8_t* in_ring = smem;                                            // [S][STAGE]
+  float* tr = reinterpret_cast<float*>(in_ring + S * STAGE);          // [8][TR_PITCH]
+  float* part = tr + 8 * TR_PITCH;                                    // [2 sets][2][L+1]
+  const int part_set = 2 * (L + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
+  const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
+  const uint32_t in_a = smem_u32(in_ring);
+  if (lane == 0) {
+    for (int s = 0; s < S + SB; ++s) mbar_init(bar_in + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t n_in = 0, n_bb = 0;  // groups consumed so far from each ring (stage = n % S, parity = (n / S) & 1)
+
+  const float tau_thresh = 3.4526698e-4f;  // sqrt(epsilon(1._sp)), mo_rte_solver_kernels.F90:754
+  const int g = chunk * 64 + 2 * lane;
+  const bool act = g < G;                // ngpt is even: a pair is live or not as a whole
+  const int gs = act ? g : chunk * 64;   // idle lanes shadow the chunk's first pair and contribute zero
+  const float live = act ? 1.0f : 0.0f;
+  const int NG = pp.ngroups;
+  const int NGF = L / U;                 // full groups; the ragged one (if any) is group NGF
+  // this lane's 8-byte slot in the t-segment of scratch row 0 of this solver
+  uint8_t* const srow = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * LW6_ROW + (size_t)lane * 8u;
+  const uint32_t lane_in = (uint32_t)lane * 8u;   // byte offset of this lane's pair in a 256-byte row
+  // COMPACT: byte offsets of the bands of this lane's two g-points in a 64-byte row of the Planck tables
+  uint32_t bo0 = 0, bo1 = 0;
+  if (COMPACT) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
+  auto band_pair = [&](const uint8_t* row) { return mk2(*reinterpret_cast<const float*>(row + bo0), *reinterpret_cast<const float*>(row + bo1)); };
+  const int ru = lane & 7;      // the reduced value (layer within its group) this lane ends up with; lanes < 8 write
+  const bool rW = lane < 8;
+
+  int ncols_done = 0;
+  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
+    const bool owner = cb + warp < p.ncol;
+    const int col = owner ? cb + warp : p.ncol - 1;
+    float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
+    float* fdn = fup + (L + 1);
+    for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
+    const size_t gc_off = (size_t)col * G + gs;
+    const f2 emis = ldg2(p.sfc_emis + gc_off);
+    const f2 ssrc = ldg2(p.sfc_source + gc_off);
+    const f2 inc = p.inc_flux ? ldg2(p.inc_flux + gc_off) : splat2(0.0f);
+    // tensor rows of sweep layer 0: layers (tau, lay_source) and the level towards the surface (lev_source)
+    const int lay0 = col * L + (TOP ? 0 : L - 1);
+    const int ext0 = col * (L + 1) + (TOP ? 1 : L - 1);
+    // lev_source at the level where the sweep enters the atmosphere
+    f2 ent0;
+    if (COMPACT) {
+      const float* bv0 = p.planck_lev + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * 16;
+      ent0 = ldg2(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs) * mk2(__ldg(bv0 + (bo0 >> 2)), __ldg(bv0 + (bo1 >> 2)));
+    } else {
+      ent0 = ldg2(p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs);
+    }
+    __syncwarp();
+
+    for (int imu = 0; imu < p.nmus; ++imu) {
+      const f2 D = splat2(p.Ds[imu]);
+      const f2 fac = splat2(2.0f * kPi * p.wts[imu] * live);
+      const float rad_norm = 2.0f * kPi * p.wts[imu];
+      f2 I = map2(inc, [&](float v) { return v / rad_norm; });  // radn_dn(top) = inc_flux/(2 pi w), :196-201
+      {
+        const float s = warp_sum(hsum2(fac * I));
+        if (lane == 0) fdn[TOP ? 0 : L] += s;
+      }
+      // one elected lane feeds the input ring: group k -> stage (n_in + k) % S
+      auto issue_in = [&](int k) {
+        if (k < NG) {
+          const uint32_t st = (n_in + (uint32_t)k) % S;
+          int sh;
+          const int rl = box_start<TOP, U>(lay0, k, sh), rv = box_start<TOP, U>(ext0, k, sh);
+          if (elect_one()) {
+            const uint32_t bar = bar_in + 8 * st;
+            const uint32_t dst = in_a + st * STAGE;
+            mbar_expect_tx(bar, STAGE);
+            tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
+            tma_load_2d(dst + OFF_PF, &tm_lay, chunk * 64, rl, bar, pol_in);
+            if (COMPACT) {
+              tma_load_2d(dst + OFF_3, &tm_bl, 0, rl, bar, pol_in);
+              tma_load_2d(dst + OFF_BV, &tm_bv, 0, rv, bar, pol_in);
+            } else {
+              tma_load_2d(dst + OFF_3, &tm_lev, chunk * 64, rv, bar, pol_in);
+            }
+          }
+          __syncwarp();
+        }
+      };
+      f2 carry = ent0;  // ent(0)
+      // (the upward sweep of the previous angle / column read its last rows from the ring: refill it only now)
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < S - 1; ++k) issue_in(k);
+      // per-level broadband sums of a group: reduced one group later (their latency overlaps the next group's arithmetic)
+      float pend[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) pend[u] = 0.0f;
+      int pend_k = -1;
+      auto flush_dn = [&]() {
+        const float t = tr_reduce<U>(pend, tr, lane);
+        const int i = pend_k * U + ru;
+        if (rW && pend_k >= 0 && i < L) fdn[TOP ? i + 1 : L - 1 - i] += t;
+      };
+      auto flush_up = [&]() {
+        const float t = tr_reduce<U>(pend, tr, lane);
+        const int i = pend_k * U + (U - 1 - ru);
+        if (rW && pend_k >= 0 && i < L) fup[TOP ? i : L - i] += t;
+      };
+      // ---------------- downward sweep: one group of U layers ----------------
+      // TAIL = false: a full group whose boxes sit where box_start put them (immediate shared-memory offsets);
+      // TAIL = true: the ragged last group (nvalid < U) and/or a box that was moved (column 0, bottom-up)
+      auto forward_group = [&](int k, auto tail_c) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        __syncwarp();                 // every lane is done with the stage that group k+S-1 overwrites
+        issue_in(k + S - 1);
+        const uint32_t nk = n_in + (uint32_t)k;
+        const uint32_t st = nk % S;
+        mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
+        const uint8_t* stg = in_ring + st * STAGE;
+        const uint8_t* base = stg + lane_in;
+        int shl = 0, shv = 0, nvalid = U;
+        if (TAIL) {
+          box_start<TOP, U>(lay0, k, shl);
+          box_start<TOP, U>(ext0, k, shv);
+          nvalid = min(U, L - k * U);
+        }
+        f2 tau[U], lay[U], ext[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (TAIL && u >= nvalid) { tau[u] = splat2(1.0f); lay[u] = splat2(0.0f); ext[u] = splat2(0.0f); continue; }  // warp-uniform
+          const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
+          const int rv = TAIL ? box_row<TOP, U>(u, shv) : (TOP ? u : U - 1 - u);
+          tau[u] = lds2(base + rl * 256);
+          if (COMPACT) {
+            const f2 pf = lds2(base + OFF_PF + rl * 256);
+            lay[u] = pf * band_pair(stg + OFF_3 + rl * 64);
+            // the level below the bottom layer takes that layer's fraction (:667-669); bottom-up sweeps leave through
+            // the layer's own level
+            const f2 pfx = (TOP && k * U + u != L - 1) ? lds2(base + OFF_PF + (rl + 1) * 256) : pf;
+            ext[u] = pfx * band_pair(stg + OFF_BV + rv * 64);
+          } else {
+            lay[u] = lds2(base + OFF_PF + rl * 256);
+            ext[u] = lds2(base + OFF_3 + rv * 256);
+          }
+        }
+        flush_dn();
+        uint8_t* const sg = srow + (size_t)k * (U * LW6_ROW);
+        float red[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (TAIL && u >= nvalid) { red[u] = 0.0f; continue; }  // warp-uniform: this layer is not part of the column
+          const f2 ent = (u == 0) ? carry : ext[u - 1];
+          const f2 tl = tau[u] * D;
+          f2 t, omt;
+          exp_and_complement2<FAST>(tl, t, omt);
+          // fact = (1-t)/tau' - t, or its series where tau' is tiny (:757-768)
+          const f2 fa = div2<true>(omt, tl) - t;
+          const f2 fb = tl * fnma2(tl, splat2(1.0f / 3.0f), splat2(0.5f));
+          float tx, ty;
+          unpack2(tl, tx, ty);
+          const f2 fact = sel2(tx > tau_thresh, ty > tau_thresh, fa, fb);
+          const f2 f2x = fact + fact;
+          // lw_source_noscat (:770-773): source_dn from lev(l+1), source_up from lev(l) whatever the orientation (quirk Q1)
+          const f2 lev_dn = DN_EXT ? ext[u] : ent;
+          const f2 lev_up = DN_EXT ? ent : ext[u];
+          const f2 sdn = fma2(f2x, lay[u] - lev_dn, omt * lev_dn);
+          const f2 sup = fma2(f2x, lay[u] - lev_up, omt * lev_up);
+          stg_scr(sg + u * LW6_ROW, t, pol_buf);
+          stg_scr(sg + u * LW6_ROW + LW6_S, sup, pol_buf);
+          I = fma2(t, I, sdn);
+          red[u] = hsum2(fac * I);
+        }
+        carry = ext[U - 1];  // (a ragged group is the last one of its sweep: its carry is not used)
+#pragma unroll
+        for (int u = 0; u < U; ++u) pend[u] = red[u];
+        pend_k = k;
+      };
+      {
+        // bottom-up, column 0: the boxes of the last groups may have been moved -> generic path for those
+        const int nfast = (TOP || col > 0) ? NGF : max(NGF - 1, 0);
+        for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
+        for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
+      }
+      flush_dn();
+      pend_k = -1;
+      n_in += (uint32_t)NG;
+      // ---------------- surface ----------------
+      f2 Uu = fma2(I, splat2(1.0f) - emis, emis * ssrc);  // :269
+      {
+        const float s = warp_sum(hsum2(fac * Uu));
+        if (lane == 0) fup[TOP ? L : 0] += s;
+      }
+      // ---------------- upward sweep (reverse order): rows back by bulk copies into the idle input ring ----------------
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // this lane's row stores (generic proxy) before the bulk loads (async proxy)
+      __syncwarp();
+      auto issue_bb = [&](int j) {  // j-th group of the upward sweep = forward group NG-1-j
+        if (j < NG) {
+          const int k = NG - 1 - j;
+          const uint32_t st = (n_bb + (uint32_t)j) % SB;
+          const uint32_t bytes = (uint32_t)min(U, L - k * U) * LW6_ROW;
+          if (elect_one()) {
+            mbar_expect_tx(bar_bb + 8 * st, bytes);
+            bulk_load(in_a + st * (U * LW6_ROW), srow - (size_t)lane * 8u + (size_t)k * (U * LW6_ROW), bytes, bar_bb + 8 * st, pol_buf);
+          }
+          __syncwarp();
+        }
+      };
+#pragma unroll
+      for (int j = 0; j < SB - 1; ++j) issue_bb(j);
+      auto backward_group = [&](int j, auto tail_c) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        const int k = NG - 1 - j;
+        const int nvalid = TAIL ? min(U, L - k * U) : U;
+        __syncwarp();  // every lane has pulled the previous group into registers: its stage may be refilled
+        issue_bb(j + SB - 1);
+        const uint32_t nj = n_bb + (uint32_t)j;
+        const uint32_t st = nj % SB;
+        mbar_wait(bar_bb + 8 * st, (nj / SB) & 1u);
+        f2 t[U], s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint8_t* row = in_ring + st * (U * LW6_ROW) + (TAIL ? min(u, nvalid - 1) : u) * LW6_ROW + lane_in;
+          t[u] = lds2(row);
+          s[u] = lds2(row + LW6_S);
+        }
+        flush_up();
+        float red[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
+          const int uu = U - 1 - u;
+          if (!TAIL || uu < nvalid) Uu = fma2(t[uu], Uu, s[uu]);
+          red[u] = hsum2(fac * Uu);
+        }
+        // the rows are in registers: their L2 lines are dead (no write-back; the next sweep rewrites them in full)
+        discard_scratch(srow - (size_t)lane * 8u + (size_t)k * (U * LW6_ROW), (uint32_t)nvalid * LW6_ROW, lane);
+#pragma unroll
+        for (int u = 0; u < U; ++u) pend[u] = red[u];
+        pend_k = k;
+      };
+      {
+        int j = 0;
+        if (NG > NGF) backward_group(j++, std::true_type{});  // the ragged group comes first on the way up
+        for (; j < NG; ++j) backward_group(j, std::false_type{});
+      }
+      flush_up();
+      pend_k = -1;
+      n_bb += (uint32_t)NG;
+      __syncwarp();
+    }
+    // ---- combine the chunks of this column (see lw_solver_v5)
+    cluster.sync();
+    {
+      float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
+      const int n = 2 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
+      for (int i = lo + lane; i < hi && owner; i += 32) {
+        float sacc = 0.0f;
+        for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
+        const int a = i / (L + 1);
+        gout[a][i - a * (L + 1)] = sacc;
+      }
+    }
+  }
+  cluster.sync();  // nobody leaves while another rank may still read its shared memory
+}
+
 // ---------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1054,6 +1667,54 @@ int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
 }
 
 
+// v6: the default (see lw_solver_v6); returns -1 when the shape does not fit
+int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
+  const int G = p.ngpt, L = p.nlay;
+  const int csize = (G + 63) / 64;
+  const bool compact = p.planck_lay != nullptr;
+  constexpr int U = 8, S = 2, SB = 2;
+  if (!lw_v5_supports(G, L)) return -1;
+  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source, (const void*)p.planck_lay, (const void*)p.planck_lev})
+    if ((uintptr_t)q & 15) return -1;
+  for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
+    if ((uintptr_t)q & 7) return -1;
+  v5::LwV5Params pp;
+  pp.b = p;
+  pp.ngroups = (L + U - 1) / U;
+  const long long rows_lay = (long long)p.ncol * L, rows_lev = (long long)p.ncol * (L + 1);
+  if (rows_lev >= (1LL << 31) - 8) return -1;
+  const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
+  CUtensorMap tm_tau, tm_lay, tm_lev, tm_bl, tm_bv;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, U)) return rc;
+  size_t stage;
+  if (compact) {
+    if (!p.planck_lev || !p.gpt2band) return fail("lw_solver: incomplete compact source description");
+    const int pfr = top ? U + 1 : U;
+    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, pfr)) return rc;
+    if (int rc = v5::make_map(&tm_bl, p.planck_lay, 16, rows_lay, U, 16)) return rc;
+    if (int rc = v5::make_map(&tm_bv, p.planck_lev, 16, rows_lev, U, 16)) return rc;
+    tm_lev = tm_tau;
+    stage = (size_t)U * 256 + (size_t)pfr * 256 + 2 * U * 64;
+  } else {
+    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, U)) return rc;
+    if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev, U)) return rc;
+    tm_bl = tm_tau; tm_bv = tm_tau;
+    stage = (size_t)3 * U * 256;
+  }
+  const size_t smem = (size_t)S * stage + 8 * v5::TR_PITCH * 4 + 4 * (size_t)(L + 1) * 4 + (S + SB) * 8;
+  const size_t per_cta = (size_t)L * v5::LW6_ROW;
+#define LW6(F, T, D, C) launch_clustered(ctx, v5::lw_solver_v6<F, T, D, C>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv)
+#define LW6C(F, T, D) (compact ? LW6(F, T, D, true) : LW6(F, T, D, false))
+  if (fast) {
+    if (top) return LW6C(true, true, true);
+    return dn_ext ? LW6C(true, false, true) : LW6C(true, false, false);
+  }
+  if (top) return LW6C(false, true, true);
+  return dn_ext ? LW6C(false, false, true) : LW6C(false, false, false);
+#undef LW6C
+#undef LW6
+}
+
 int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 63) / 64;
@@ -1087,4 +1748,39 @@ int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
 #undef SW5
 }
 
+
+// v6: the default (see sw_solver_v6)
+int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
+  const int G = p.ngpt, L = p.nlay;
+  const int csize = (G + 63) / 64;
+  constexpr int U = 8, SB = 2;
+  const int S = p.g ? 2 : RRNN_V6_SW_S;  // (three input arrays: two stages already hold the upward sweep's ring)
+  if ((G & 3) || csize > 8 || L < U) return -1;
+  for (const void* q : {(const void*)p.tau, (const void*)p.ssa, (const void*)p.g})
+    if ((uintptr_t)q & 15) return -1;
+  for (const void* q : {(const void*)p.inc_flux, (const void*)p.inc_flux_dif, (const void*)p.alb_dir, (const void*)p.alb_dif})
+    if ((uintptr_t)q & 7) return -1;
+  v5::SwV5Params pp;
+  pp.b = p;
+  pp.ngroups = (L + U - 1) / U;
+  const long long rows = (long long)p.ncol * L;
+  if (rows >= (1LL << 31) - 8) return -1;
+  CUtensorMap tm_tau, tm_ssa, tm_g;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows, U)) return rc;
+  if (int rc = v5::make_map(&tm_ssa, p.ssa, G, rows, U)) return rc;
+  if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, U)) return rc; }
+  else tm_g = tm_ssa;
+  const int nin = p.g ? 3 : 2;
+  const size_t smem = (size_t)S * nin * U * 256 + 16 * v5::TR_PITCH * 4 + 2 * (size_t)(3 * (L + 1) + 1) * 4 + (S + SB) * 8;
+  const size_t per_cta = (size_t)L * v5::SW6_ROW;
+  const bool top = p.top_at_1 != 0;
+#define SW6(F, HG, T) launch_clustered(ctx, v5::sw_solver_v6<F, HG, T>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
+  if (fast) {
+    if (p.g) return top ? SW6(true, true, true) : SW6(true, true, false);
+    return top ? SW6(true, false, true) : SW6(true, false, false);
+  }
+  if (p.g) return top ? SW6(false, true, true) : SW6(false, true, false);
+  return top ? SW6(false, false, true) : SW6(false, false, false);
+#undef SW6
+}
 }  // namespace rrnn
