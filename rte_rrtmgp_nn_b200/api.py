@@ -126,6 +126,22 @@ def _ptr(t):
     return vp(t.data_ptr()) if t is not None else None
 
 
+# rte/mo_rte_rrtmgp_config.F90:23-24, 52-67: run-time checks, off by default, switched by rte_rrtmgp_config_checks
+check_extents = False
+check_values = False
+
+
+def rte_rrtmgp_config_checks(extents, values=None):
+    """rte_rrtmgp_config_checks(extents, values) / rte_rrtmgp_config_checks(do_checks) (mo_rte_rrtmgp_config.F90:52-67)."""
+    global check_extents, check_values
+    check_extents = bool(extents)
+    check_values = bool(extents if values is None else values)
+
+
+def _outside(t, lo, hi):
+    return bool((t < lo).any() or (t > hi).any())
+
+
 class rrtmgp_network_type:
     """The reference's network container; `load_netcdf` reads the shipped netCDF-4 weight files."""
 
@@ -639,8 +655,30 @@ class ty_gas_optics_rrtmgp(ty_optical_props):
         ncol, nlay = play.shape
         lib = _lib.lib()
         models = (vp * 2)(*[n.h for n in neural_nets][:2])
+        lw = self.source_is_internal()
+        # mo_gas_optics_rrtmgp.F90:287-315 (LW), 474-494 (SW): the same checks, the same messages, off unless configured
+        if check_extents:
+            err = ""
+            if tuple(play.shape) != (ncol, nlay): err = "gas_optics(): array play has wrong size"
+            if tuple(tlay.shape) != (ncol, nlay): err = "gas_optics(): array tlay has wrong size"
+            if tuple(plev.shape) != (ncol, nlay + 1): err = "gas_optics(): array plev has wrong size"
+            if lw and np.shape(args[0]) != (ncol,): err = "gas_optics(): array tsfc has wrong size"
+            if lw and tlev is not None and tuple(np.shape(tlev)) != (ncol, nlay + 1): err = "gas_optics(): array tlev has wrong size"
+            if err:
+                return err
+        if check_values:
+            err = ""
+            pmin, pmax = self.kd.get("press_ref_min", 1.00518357), self.kd.get("press_ref_max", 109663.31)
+            tmin, tmax = self.kd.get("temp_ref_min", 160.0), self.kd.get("temp_ref_max", 355.0)
+            if _outside(play, pmin, pmax): err = "gas_optics(): array play has values outside range"
+            if bool((plev < 0).any()): err = "gas_optics(): array plev has values outside range"
+            if _outside(tlay, tmin, tmax): err = "gas_optics(): array tlay has values outside range"
+            if lw and _outside(_dev(args[0], ctx), tmin, tmax): err = "gas_optics(): array tsfc has values outside range"
+            if lw and tlev is not None and _outside(_dev(tlev, ctx), tmin, tmax): err = "gas_optics(): array tlev has values outside range"
+            if err:
+                return err
         try:
-            if self.source_is_internal():
+            if lw:
                 tsfc, gas_desc, optical_props, sources = args
                 tsfc = _dev(tsfc, ctx)
                 tlev_d = _dev(tlev, ctx)
@@ -1049,6 +1087,17 @@ def _hp(a):
     return None if a is None else vp(a.ctypes.data)
 
 
+def _flux_out(a, ncol, nlev, name):
+    """A caller-supplied output array is written by the library through its raw pointer: it must be float32, C-contiguous and
+    (ncol, nlay+1) -- anything else is an error, not a silent write past the buffer."""
+    if a is None:
+        return np.empty((ncol, nlev), np.float32)
+    if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"] or a.shape != (ncol, nlev) \
+            or not a.flags["WRITEABLE"]:
+        raise ValueError(f"{name}: output array must be a writeable C-contiguous float32 array of shape ({ncol}, {nlev})")
+    return a
+
+
 def lw_fluxes_host(k_dist, neural_nets, play, plev, tlay, tsfc, sfc_emis, gas_desc, tlev=None, top_at_1=True,
                    n_gauss_angles=1, flux_up=None, flux_dn=None):
     """numpy in / numpy out: gas_optics(neural_nets=) -> rte_lw for all columns (rrnn_lw_fluxes_host)."""
@@ -1056,10 +1105,8 @@ def lw_fluxes_host(k_dist, neural_nets, play, plev, tlay, tsfc, sfc_emis, gas_de
     f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
     play, plev, tlay, tlev, tsfc, sfc_emis = map(f32, (play, plev, tlay, tlev, tsfc, sfc_emis))
     ncol, nlay = play.shape
-    if flux_up is None:
-        flux_up = np.empty((ncol, nlay + 1), np.float32)
-    if flux_dn is None:
-        flux_dn = np.empty((ncol, nlay + 1), np.float32)
+    flux_up = _flux_out(flux_up, ncol, nlay + 1, "lw_fluxes_host: flux_up")
+    flux_dn = _flux_out(flux_dn, ncol, nlay + 1, "lw_fluxes_host: flux_dn")
     gases, ngas, keep = gas_desc._to_c(ctx, host=True)
     _lib.check(_lib.lib().rrnn_lw_fluxes_host(ctx.h, k_dist._kd.h, _models(neural_nets), len(neural_nets), ncol, nlay,
                                               int(bool(top_at_1)), int(n_gauss_angles), _hp(play), _hp(plev), _hp(tlay), _hp(tlev),
@@ -1073,8 +1120,9 @@ def sw_fluxes_host(k_dist, neural_nets, play, plev, tlay, mu0, sfc_alb, gas_desc
     f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
     play, plev, tlay, mu0, sfc_alb, tsi = map(f32, (play, plev, tlay, mu0, sfc_alb, tsi))
     ncol, nlay = play.shape
-    mk = lambda a: np.empty((ncol, nlay + 1), np.float32) if a is None else a
-    flux_up, flux_dn, flux_dn_dir = mk(flux_up), mk(flux_dn), mk(flux_dn_dir)
+    flux_up = _flux_out(flux_up, ncol, nlay + 1, "sw_fluxes_host: flux_up")
+    flux_dn = _flux_out(flux_dn, ncol, nlay + 1, "sw_fluxes_host: flux_dn")
+    flux_dn_dir = _flux_out(flux_dn_dir, ncol, nlay + 1, "sw_fluxes_host: flux_dn_dir")
     gases, ngas, keep = gas_desc._to_c(ctx, host=True)
     _lib.check(_lib.lib().rrnn_sw_fluxes_host(ctx.h, k_dist._kd.h, _models(neural_nets), ncol, nlay, int(bool(top_at_1)),
                                               _hp(play), _hp(plev), _hp(tlay), _hp(mu0), _hp(sfc_alb), _hp(tsi), gases, ngas,

@@ -441,13 +441,16 @@ extern "C" int rrnn_ctx_profile_read(rrnn_ctx_t* c, int kind, double* total_ms, 
   RRNN_CHECK(c && kind >= 0 && kind < 4 && total_ms && nlaunches, "rrnn_ctx_profile_read: bad argument");
   RRNN_CUDA(cudaStreamSynchronize(c->stream));
   double tot = 0.0;
+  int n = 0;
   for (size_t i = 0; i < c->prof_used[kind]; ++i) {
     float ms = 0.f;
-    RRNN_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[kind][i].first, c->prof_ev[kind][i].second));
+    // a launch that failed between its two records leaves the stop event unrecorded: skip that slot
+    if (cudaEventElapsedTime(&ms, c->prof_ev[kind][i].first, c->prof_ev[kind][i].second) != cudaSuccess) { cudaGetLastError(); continue; }
     tot += ms;
+    ++n;
   }
   *total_ms = tot;
-  *nlaunches = (int)c->prof_used[kind];
+  *nlaunches = n;
   return 0;
 }
 
@@ -461,8 +464,9 @@ extern "C" int rrnn_ctx_set_flag(rrnn_ctx_t* c, const char* name, int value) {
   else if (s == "nn_tensor_cores") c->nn_tensor_cores = value ? 1 : 0;
   else if (s == "lw_compact_source") c->lw_compact_source = value ? 1 : 0;
   else if (s == "solver_variant") c->solver_variant = value;
-  else if (s == "lw_solver_gen") c->lw_solver_gen = value;
-  else if (s == "sw_solver_gen") c->sw_solver_gen = value;
+  else if (s == "host_copy_threads") c->host_copy_threads = value;
+  else if (s == "check_extents") c->check_extents = value ? 1 : 0;
+  else if (s == "check_values") c->check_values = value ? 1 : 0;
   else if (s == "solver_scratch_mb") c->solver_scratch_mb = value;
   else if (s == "solver_warps") c->solver_warps = value;
   else return fail("rrnn_ctx_set_flag: unknown flag " + s);

@@ -57,8 +57,7 @@ struct rrnn_ctx {
                            // 9.1e-3 both, strict fp32 oracle 6.4e-2 / 9.4e-3 at 200 x 137): the two-stream formulas' own conditioning
                            // sets the error, not 1-ulp differences of rcp / sqrt / exp; the solver is 11 % faster without them
   int solver_buffer = 0;   // reverse-sweep buffer: 0 auto, 1 shared memory, 2 L2-resident global scratch
-  int solver_variant = 0;  // 0 = TMA-staged packed kernels (rte_solvers_v5.cu), 1 = one g-point per lane (rte_solvers.cu)
-  int lw_solver_gen = 0, sw_solver_gen = 0;  // generation of the TMA-staged packed kernel per solver: 0 = default, 5 = staged scratch (v5), 6 = direct scratch (v6)
+  int solver_variant = 0;  // 0 = TMA-staged packed kernels (rte_solvers_tma.cu), 1 = one g-point per lane (rte_solvers.cu)
   int solver_scratch_mb = 0;  // L2 budget of the packed kernels' reverse-sweep scratch (0 = default)
   int solver_warps = 0;       // solvers per CTA in the v5 kernels (0 = default)
   void* scratch = nullptr;
@@ -66,6 +65,8 @@ struct rrnn_ctx {
   int lw_compact_source = 1;  // fused LW path: sources stay factored between gas optics and solver (8 instead of 12 B per g-point and layer)
   int nn_tensor_cores = 1; // MLP variant: 1 = tcgen05 (fp16 hi/lo split operands, fp32 accumulation; default), 0 = fp32 FFMA
   int chunk_columns = 0;
+  int host_copy_threads = 0;  // threads that copy pageable caller memory to / from the pinned bounce ring (0 = min(8, cores))
+  int check_extents = 0, check_values = 0;  // rte/mo_rte_rrtmgp_config.F90:23-24, 52-53 (rte_config_checks); default .false. as there
   // persistent workspace for the whole-path drivers
   void* ws = nullptr;
   size_t ws_bytes = 0;

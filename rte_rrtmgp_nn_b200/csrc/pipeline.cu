@@ -6,6 +6,8 @@
 // of chunk k+1 and the D2H copy of chunk k-1 with the kernels of chunk k on three streams.
 #include "common.cuh"
 #include <algorithm>
+#include <functional>
+#include <thread>
 
 namespace rrnn {
 bool lw_v5_supports(int G, int L);  // rte_solvers_v5.cu
@@ -71,12 +73,33 @@ static size_t sw_ws_bytes(int G, int L, int nc) {
 
 static int pick_chunk(rrnn_ctx_t* ctx, int ncol, size_t bytes_per_col) {
   if (ctx->chunk_columns > 0) return std::min(ncol, ctx->chunk_columns);
-  // default: at most ~12 GiB of optical-property workspace, at least enough columns to fill the GPU
-  const size_t budget = (size_t)12 << 30;
+  // default: at most ~12 GiB of optical-property workspace and never more than half of what the device has free right
+  // now (the library may be embedded in a host model or share the GPU with a framework); at least enough columns to
+  // fill the GPU
+  size_t budget = (size_t)12 << 30, free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min(budget, (free_b + ctx->ws_bytes) / 2);
+  else cudaGetLastError();
   long long c = (long long)(budget / bytes_per_col);
   c = std::max<long long>(c, 256);
   c = std::min<long long>(c, 32768);
   return (int)std::min<long long>(c, ncol);
+}
+
+// Workspace for `chunk` columns; when the allocation fails the chunk is halved and tried again (down to 256 columns):
+// a busy device gets a smaller workspace and more passes instead of an error.  bytes_of(chunk) -> workspace bytes.
+static int ensure_ws_retry(rrnn_ctx_t* ctx, int& chunk, const std::function<size_t(int)>& bytes_of) {
+  for (;;) {
+    const size_t need = bytes_of(chunk);
+    if (ctx->ws_bytes >= need) return 0;
+    if (ctx->ws) { RRNN_CUDA(cudaStreamSynchronize(ctx->stream)); RRNN_CUDA(cudaFree(ctx->ws)); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+    const cudaError_t e = cudaMalloc(&ctx->ws, need);
+    if (e == cudaSuccess) { ctx->ws_bytes = need; return 0; }
+    cudaGetLastError();
+    ctx->ws = nullptr;
+    if (ctx->chunk_columns > 0 || chunk <= 256)
+      return fail(std::string("workspace allocation failed (") + cudaGetErrorString(e) + ") for " + std::to_string(chunk) + " columns per chunk");
+    chunk = std::max(256, chunk / 2);
+  }
 }
 
 static void offset_gases(const rrnn_gas_t* in, int ngas, size_t c0, int nlay, std::vector<rrnn_gas_t>& out) {
@@ -162,8 +185,8 @@ extern "C" int rrnn_lw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrn
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const int G = kd->ngpt, L = nlay;
   const bool compact = lw_compact(ctx, kd, models, nmodels, L);
-  const int chunk = pick_chunk(ctx, ncol, lw_ws_bytes(G, L, 1, compact));
-  if (int rc = ensure_ws(ctx, lw_ws_bytes(G, L, chunk, compact))) return rc;
+  int chunk = pick_chunk(ctx, ncol, lw_ws_bytes(G, L, 1, compact));
+  if (int rc = ensure_ws_retry(ctx, chunk, [&](int c) { return lw_ws_bytes(G, L, c, compact); })) return rc;
   std::vector<rrnn_gas_t> gs;
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int nc = std::min(chunk, ncol - c0);
@@ -186,8 +209,8 @@ extern "C" int rrnn_sw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrn
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const int G = kd->ngpt, L = nlay;
-  const int chunk = pick_chunk(ctx, ncol, sw_ws_bytes(G, L, 1));
-  if (int rc = ensure_ws(ctx, sw_ws_bytes(G, L, chunk))) return rc;
+  int chunk = pick_chunk(ctx, ncol, sw_ws_bytes(G, L, 1));
+  if (int rc = ensure_ws_retry(ctx, chunk, [&](int c) { return sw_ws_bytes(G, L, c); })) return rc;
   std::vector<rrnn_gas_t> gs;
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int nc = std::min(chunk, ncol - c0);
@@ -208,17 +231,49 @@ struct HostField {
   const float* host;   // host source (per column stride `per_col`), null = absent
   size_t per_col;      // floats per column
   float* dev[2];       // device staging (double-buffered)
+  bool pageable;       // the caller's memory is not page-locked: it goes through the pinned bounce ring
+  float* pin[2];       // this field's slots in the bounce ring
 };
 
-struct Staging {
-  std::vector<HostField> in;
-  float* out_dev[2][3];
-  float* ws_opt;
-  size_t total_bytes;
-};
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Anything else -- malloc, Fortran allocate, numpy --
+// is pageable, and a cudaMemcpyAsync from it would be staged by the driver synchronously and without overlap.
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// memcpy split over a few host threads (one thread moves ~10 GB/s; the PCIe / C2C link wants more)
+void parallel_copy(void* dst, const void* src, size_t bytes, int nthreads) {
+  if (bytes == 0) return;
+  const size_t min_per_thread = (size_t)4 << 20;
+  int nt = (int)std::min<size_t>((size_t)std::max(nthreads, 1), (bytes + min_per_thread - 1) / min_per_thread);
+  if (nt <= 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  th.reserve(nt - 1);
+  const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+  for (int t = 1; t < nt; ++t) {
+    const size_t o = std::min(bytes, per * t), e = std::min(bytes, per * (t + 1));
+    if (e > o) th.emplace_back([=]() { memcpy((char*)dst + o, (const char*)src + o, e - o); });
+  }
+  memcpy(dst, src, std::min(bytes, per));
+  for (auto& x : th) x.join();
+}
+
+int ensure_pinned(rrnn_ctx_t* ctx, size_t bytes) {
+  if (ctx->pinned_bytes >= bytes) return 0;
+  if (ctx->pinned) { RRNN_CUDA(cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+  RRNN_CUDA(cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocDefault));
+  ctx->pinned_bytes = bytes;
+  return 0;
+}
 
 }  // namespace
 
+// One pass over all columns with HOST buffers.  Three streams overlap the H2D copy of chunk k+1, the kernels of chunk k
+// and the D2H copy of chunk k-1.  Page-locked caller memory is copied from / to directly; pageable caller memory (what a
+// Fortran or C host normally passes) is staged through a persistent pinned bounce ring of the context, two slots per
+// array, filled and drained by a few host threads while the GPU works on the neighbouring chunks.
 static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
                              int ncol, int L, int top_at_1, int nang, std::vector<HostField>& fields,
                              const rrnn_gas_t* gases, int ngas, float* const* out_host, int nout) {
@@ -226,47 +281,97 @@ static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, c
   // 2-D gas fields are appended to the staged fields
   std::vector<int> gas_field(ngas, -1);
   for (int g = 0; g < ngas; ++g)
-    if (gases[g].ndims == 2) { gas_field[g] = (int)fields.size(); fields.push_back({gases[g].conc, (size_t)L, {nullptr, nullptr}}); }
+    if (gases[g].ndims == 2) { gas_field[g] = (int)fields.size(); fields.push_back({gases[g].conc, (size_t)L, {nullptr, nullptr}, false, {nullptr, nullptr}}); }
   // 1-D gas profiles: uploaded once
   std::vector<float*> gas1d(ngas, nullptr);
-  size_t in_per_col = 0;
-  for (auto& f : fields) if (f.host) in_per_col += f.per_col;
+  size_t in_per_col = 0, in_pageable_per_col = 0;
+  for (auto& f : fields)
+    if (f.host) {
+      in_per_col += f.per_col;
+      f.pageable = !is_pinned(f.host);
+      if (f.pageable) in_pageable_per_col += f.per_col;
+    }
+  bool out_pageable[3] = {false, false, false};
+  int nout_pageable = 0;
+  for (int o = 0; o < nout; ++o) { out_pageable[o] = !is_pinned(out_host[o]); nout_pageable += out_pageable[o] ? 1 : 0; }
   const size_t out_per_col = (size_t)nout * (L + 1);
   const bool compact = lw && lw_compact(ctx, kd, models, nmodels, L);
   const size_t opt_per_col = lw ? lw_ws_bytes(G, L, 1, compact) : sw_ws_bytes(G, L, 1);
-  const int chunk = pick_chunk(ctx, ncol, opt_per_col + 8 * (in_per_col + out_per_col));
-  const size_t opt_bytes = lw ? lw_ws_bytes(G, L, chunk, compact) : sw_ws_bytes(G, L, chunk);
-  size_t stage_floats = 0;
-  for (auto& f : fields) if (f.host) stage_floats += 2 * align256(f.per_col * chunk);
-  stage_floats += 2 * (size_t)nout * align256((size_t)(L + 1) * chunk);
+  int chunk = pick_chunk(ctx, ncol, opt_per_col + 8 * (in_per_col + out_per_col));
   size_t gas1d_floats = 0;
   for (int g = 0; g < ngas; ++g) if (gases[g].ndims == 1) gas1d_floats += align256((size_t)L);
-  if (int rc = ensure_ws(ctx, opt_bytes + 4 * (stage_floats + gas1d_floats))) return rc;
+  auto stage_floats_of = [&](int c) {
+    size_t n = 0;
+    for (auto& f : fields) if (f.host) n += 2 * align256(f.per_col * c);
+    n += 2 * (size_t)nout * align256((size_t)(L + 1) * c);
+    return n;
+  };
+  auto opt_bytes_of = [&](int c) { return lw ? lw_ws_bytes(G, L, c, compact) : sw_ws_bytes(G, L, c); };
+  if (int rc = ensure_ws_retry(ctx, chunk, [&](int c) { return opt_bytes_of(c) + 4 * (stage_floats_of(c) + gas1d_floats); })) return rc;
+  const size_t opt_bytes = opt_bytes_of(chunk);
   float* p = (float*)((char*)ctx->ws + opt_bytes);
   for (auto& f : fields) if (f.host) for (int b = 0; b < 2; ++b) { f.dev[b] = p; p += align256(f.per_col * chunk); }
   float* outd[2][3] = {};
   for (int b = 0; b < 2; ++b) for (int o = 0; o < nout; ++o) { outd[b][o] = p; p += align256((size_t)(L + 1) * chunk); }
+  // the pinned bounce ring (only what pageable arrays need)
+  float* outpin[2][3] = {};
+  {
+    const size_t pin_floats = 2 * (align256(in_pageable_per_col * chunk) + (size_t)fields.size() * 256) +
+                              2 * (size_t)nout_pageable * align256((size_t)(L + 1) * chunk);
+    if (in_pageable_per_col || nout_pageable) {
+      if (int rc = ensure_pinned(ctx, 4 * pin_floats)) return rc;
+      float* q = (float*)ctx->pinned;
+      for (auto& f : fields) if (f.host && f.pageable) for (int b = 0; b < 2; ++b) { f.pin[b] = q; q += align256(f.per_col * chunk); }
+      for (int b = 0; b < 2; ++b) for (int o = 0; o < nout; ++o) if (out_pageable[o]) { outpin[b][o] = q; q += align256((size_t)(L + 1) * chunk); }
+    }
+  }
+  const int nthreads = ctx->host_copy_threads > 0 ? ctx->host_copy_threads : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  cudaStream_t s_in = ctx->copy_stream, s_cmp = ctx->stream, s_out = ctx->out_stream;
+  // every exit path leaves no copy in flight on the caller's (or the ring's) memory
+  auto drain = [&]() { cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_out); cudaStreamSynchronize(s_cmp); };
+#define RRNN_PIPE(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) { drain(); return fail(std::string(#call) + ": " + cudaGetErrorString(_e)); } \
+  } while (0)
   for (int g = 0; g < ngas; ++g)
     if (gases[g].ndims == 1) {
       gas1d[g] = p; p += align256((size_t)L);
-      RRNN_CUDA(cudaMemcpyAsync(gas1d[g], gases[g].conc, L * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      RRNN_PIPE(cudaMemcpyAsync(gas1d[g], gases[g].conc, L * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     }
-  cudaStream_t s_in = ctx->copy_stream, s_cmp = ctx->stream, s_out = ctx->out_stream;
   // events: 0/1 = H2D done (per buffer), 2/3 = compute done (per buffer), 4/5 = D2H done (per buffer)
   std::vector<rrnn_gas_t> gs(gases, gases + ngas);
+  auto unstage = [&](int kk) {  // pinned ring -> the caller's pageable flux arrays, chunk kk
+    if (!nout_pageable) return cudaSuccess;
+    const int bb = kk & 1;
+    const cudaError_t e = cudaEventSynchronize(ctx->ev[4 + bb]);
+    if (e != cudaSuccess) return e;
+    const size_t cc0 = (size_t)kk * chunk;
+    const int ncc = (int)std::min<size_t>(chunk, (size_t)ncol - cc0);
+    for (int o = 0; o < nout; ++o)
+      if (out_pageable[o]) parallel_copy(out_host[o] + cc0 * (L + 1), outpin[bb][o], (size_t)(L + 1) * ncc * sizeof(float), nthreads);
+    return cudaSuccess;
+  };
   int k = 0;
   for (int c0 = 0; c0 < ncol; c0 += chunk, ++k) {
     const int nc = std::min(chunk, ncol - c0);
     const int b = k & 1;
-    // inputs of chunk k may overwrite staging buffer b once the kernels of chunk k-2 are done
-    if (k >= 2) RRNN_CUDA(cudaStreamWaitEvent(s_in, ctx->ev[2 + b], 0));
+    // inputs of chunk k may overwrite staging buffer b once the kernels of chunk k-2 are done; ring slot b once its H2D is
+    if (k >= 2) {
+      RRNN_PIPE(cudaStreamWaitEvent(s_in, ctx->ev[2 + b], 0));
+      if (in_pageable_per_col) RRNN_PIPE(cudaEventSynchronize(ctx->ev[b]));
+    }
     for (auto& f : fields)
-      if (f.host)
-        RRNN_CUDA(cudaMemcpyAsync(f.dev[b], f.host + (size_t)c0 * f.per_col, f.per_col * nc * sizeof(float), cudaMemcpyHostToDevice, s_in));
-    RRNN_CUDA(cudaEventRecord(ctx->ev[b], s_in));
-    RRNN_CUDA(cudaStreamWaitEvent(s_cmp, ctx->ev[b], 0));
+      if (f.host) {
+        const float* src = f.host + (size_t)c0 * f.per_col;
+        const size_t bytes = f.per_col * nc * sizeof(float);
+        if (f.pageable) { parallel_copy(f.pin[b], src, bytes, nthreads); src = f.pin[b]; }
+        RRNN_PIPE(cudaMemcpyAsync(f.dev[b], src, bytes, cudaMemcpyHostToDevice, s_in));
+      }
+    RRNN_PIPE(cudaEventRecord(ctx->ev[b], s_in));
+    RRNN_PIPE(cudaStreamWaitEvent(s_cmp, ctx->ev[b], 0));
     // flux staging buffer b must have been drained (D2H of chunk k-2 on s_out)
-    if (k >= 2) RRNN_CUDA(cudaStreamWaitEvent(s_cmp, ctx->ev[4 + b], 0));
+    if (k >= 2) RRNN_PIPE(cudaStreamWaitEvent(s_cmp, ctx->ev[4 + b], 0));
     for (int g = 0; g < ngas; ++g) {
       if (gas_field[g] >= 0) gs[g].conc = fields[gas_field[g]].dev[b];
       else if (gases[g].ndims == 1) gs[g].conc = gas1d[g];
@@ -281,17 +386,24 @@ static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, c
                     fields[4].dev[b], fields[5].host ? fields[5].dev[b] : nullptr, gs.data(), ngas, outd[b][0], outd[b][1],
                     outd[b][2], (float*)ctx->ws);
     }
-    if (rc) return rc;
-    RRNN_CUDA(cudaEventRecord(ctx->ev[2 + b], s_cmp));
-    // D2H of this chunk's fluxes on its own stream (overlaps the next chunk's H2D and kernels)
-    RRNN_CUDA(cudaStreamWaitEvent(s_out, ctx->ev[2 + b], 0));
-    for (int o = 0; o < nout; ++o)
-      RRNN_CUDA(cudaMemcpyAsync(out_host[o] + (size_t)c0 * (L + 1), outd[b][o], (size_t)(L + 1) * nc * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-    RRNN_CUDA(cudaEventRecord(ctx->ev[4 + b], s_out));
+    if (rc) { drain(); return rc; }
+    RRNN_PIPE(cudaEventRecord(ctx->ev[2 + b], s_cmp));
+    // D2H of this chunk's fluxes on its own stream (overlaps the next chunk's H2D and kernels).  Ring slot b was emptied
+    // by unstage(k-2) one iteration ago.
+    RRNN_PIPE(cudaStreamWaitEvent(s_out, ctx->ev[2 + b], 0));
+    for (int o = 0; o < nout; ++o) {
+      float* dst = out_pageable[o] ? outpin[b][o] : out_host[o] + (size_t)c0 * (L + 1);
+      RRNN_PIPE(cudaMemcpyAsync(dst, outd[b][o], (size_t)(L + 1) * nc * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    }
+    RRNN_PIPE(cudaEventRecord(ctx->ev[4 + b], s_out));
+    // while the GPU works on chunk k: hand chunk k-1's fluxes to the caller
+    if (k >= 1) RRNN_PIPE(unstage(k - 1));
   }
-  RRNN_CUDA(cudaStreamSynchronize(s_in));
-  RRNN_CUDA(cudaStreamSynchronize(s_out));
-  RRNN_CUDA(cudaStreamSynchronize(s_cmp));
+  if (k >= 1) RRNN_PIPE(unstage(k - 1));
+  RRNN_PIPE(cudaStreamSynchronize(s_in));
+  RRNN_PIPE(cudaStreamSynchronize(s_out));
+  RRNN_PIPE(cudaStreamSynchronize(s_cmp));
+#undef RRNN_PIPE
   return 0;
 }
 
@@ -304,7 +416,7 @@ extern "C" int rrnn_lw_fluxes_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, cons
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const size_t L = nlay;
-  std::vector<HostField> f = {{play, L, {}}, {plev, L + 1, {}}, {tlay, L, {}}, {tlev, L + 1, {}}, {tsfc, 1, {}}, {sfc_emis, 1, {}}};
+  std::vector<HostField> f = {{play, L, {}, false, {}}, {plev, L + 1, {}, false, {}}, {tlay, L, {}, false, {}}, {tlev, L + 1, {}, false, {}}, {tsfc, 1, {}, false, {}}, {sfc_emis, 1, {}, false, {}}};
   float* outs[2] = {flux_up, flux_dn};
   return run_host_pipeline(ctx, true, kd, models, nmodels, ncol, nlay, top_at_1, n_gauss_angles, f, gases, ngas, outs, 2);
 }
@@ -318,7 +430,7 @@ extern "C" int rrnn_sw_fluxes_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, cons
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const size_t L = nlay;
-  std::vector<HostField> f = {{play, L, {}}, {plev, L + 1, {}}, {tlay, L, {}}, {mu0, 1, {}}, {sfc_alb, 1, {}}, {tsi, 1, {}}};
+  std::vector<HostField> f = {{play, L, {}, false, {}}, {plev, L + 1, {}, false, {}}, {tlay, L, {}, false, {}}, {mu0, 1, {}, false, {}}, {sfc_alb, 1, {}, false, {}}, {tsi, 1, {}, false, {}}};
   float* outs[3] = {flux_up, flux_dn, flux_dn_dir};
   return run_host_pipeline(ctx, false, kd, models, 2, ncol, nlay, top_at_1, 1, f, gases, ngas, outs, 3);
 }

@@ -395,12 +395,8 @@ __global__ void expand_kernel(int nbnd, int ngpt, int ncol, const int* __restric
 using namespace rrnn;
 
 namespace rrnn {
-int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v5.cu (TMA-staged, packed); -1 = shape not supported
-int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p);           // its direct-scratch generation (default)
-int launch_lw_v4(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_v4.cu (packed, per-lane loads)
-int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast);
-int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast);  // direct-scratch generation of the TMA-staged packed kernel (default)
-int launch_sw_v4(rrnn_ctx_t* ctx, SwParams& p, bool fast);
+int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p);           // rte_solvers_tma.cu (TMA-staged, packed); -1 = shape not supported
+int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast);
 }
 
 static int pick_warps_per_block(size_t per_warp_bytes) {
@@ -442,12 +438,8 @@ extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int nc
   const int ps = prof_begin(ctx, K_LW_SOLVER);
   int rc4 = -1;
   if (ctx->solver_variant == 0) {
-    rc4 = ctx->lw_solver_gen == 5 ? launch_lw_v5(ctx, p) : launch_lw_v6(ctx, p);
-    if (rc4 > 0) return rc4;
-  }
-  if (rc4 < 0 && (ctx->solver_variant == 0 || ctx->solver_variant == 2)) {
-    rc4 = launch_lw_v4(ctx, p);
-    if (rc4 > 0) return rc4;
+    rc4 = launch_lw_v6(ctx, p);
+    if (rc4 > 0) { prof_end(ctx, K_LW_SOLVER, ps); return rc4; }
   }
   if (rc4 == 0) {
     // done by the packed kernel
@@ -500,10 +492,10 @@ int lw_solver_noscat_compact(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int 
   p.tau = tau_d; p.lay_source = pfrac_d; p.planck_lay = planck_lay_d; p.planck_lev = planck_lev_d; p.gpt2band = gpt2band_d;
   p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
   const int ps = prof_begin(ctx, K_LW_SOLVER);
-  const int rc = ctx->lw_solver_gen == 5 ? launch_lw_v5(ctx, p) : launch_lw_v6(ctx, p);
+  const int rc = launch_lw_v6(ctx, p);
+  prof_end(ctx, K_LW_SOLVER, ps);  // (paired with prof_begin on every path)
   if (rc < 0) return fail("lw_solver (compact sources): shape not supported by the packed kernel");
   if (rc > 0) return rc;
-  prof_end(ctx, K_LW_SOLVER, ps);
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -545,12 +537,8 @@ extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
   const int ps = prof_begin(ctx, K_SW_SOLVER);
   int rc4 = -1;
   if (ctx->solver_variant == 0) {
-    rc4 = ctx->sw_solver_gen == 5 ? launch_sw_v5(ctx, p, fast) : launch_sw_v6(ctx, p, fast);
-    if (rc4 > 0) return rc4;
-  }
-  if (rc4 < 0 && (ctx->solver_variant == 0 || ctx->solver_variant == 2)) {
-    rc4 = launch_sw_v4(ctx, p, fast);
-    if (rc4 > 0) return rc4;
+    rc4 = launch_sw_v6(ctx, p, fast);
+    if (rc4 > 0) { prof_end(ctx, K_SW_SOLVER, ps); return rc4; }
   }
   if (rc4 == 0) {
     // done by the packed kernel

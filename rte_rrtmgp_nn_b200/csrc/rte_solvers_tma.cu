@@ -1,21 +1,22 @@
-// RTE flux solvers, TMA-staged packed variant (the default): two g-points per lane, fp32x2 arithmetic, and every
-// global <-> on-chip transfer done by the TMA unit instead of per-lane loads and stores.
+// RTE flux solvers, TMA-staged packed kernels (the default): two g-points per lane, fp32x2 arithmetic, inputs staged by
+// the TMA unit, reverse-sweep rows through an L2-resident scratch.
 //
-//  lw_solver_v5  <- lw_solver_noscat + lw_source_noscat + lw_transport_noscat_dn/_up + inlined broadband sums
+//  lw_solver_v6  <- lw_solver_noscat + lw_source_noscat + lw_transport_noscat_dn/_up + inlined broadband sums
 //                   (rte/kernels/mo_rte_solver_kernels.F90:119-330, 742-776, 950-1009, 301-314), angle loop :332-415
-//  sw_solver_v5  <- sw_solver_2stream + sw_two_stream_source + adding (:541-692, 1366-1480, 1526-1637)
+//  sw_solver_v6  <- sw_solver_2stream + sw_two_stream_source + adding (:541-692, 1366-1480, 1526-1637)
 //
-// Why: ncu on the per-lane-load kernels (rte_solvers.cu, rte_solvers_v4.cu) shows them bound by instruction issue and
-// load latency, not by HBM -- ~40 % of the issued instructions were 64-bit address arithmetic for the loads, and with the
-// few warps the reverse-sweep buffer allows, one group of register prefetch could not cover the memory latency.  Here
-//   * one elected lane issues ONE cp.async.bulk.tensor.2d per input array per group of U layers (box 64 g-points x U rows of
-//     the [rows][ngpt] tensor) into a ring of S shared-memory stages, S-1 groups ahead, signalled by mbarriers; lanes read
-//     their two g-points with LDS.64 at immediate offsets -- no per-lane address arithmetic, no prefetch registers;
-//   * the reverse-sweep coefficients (LW: t, source_up -- 16 B per lane and layer; SW: e, f, alpha_above -- 24 B) are staged
-//     in shared memory and moved to / from an L2-resident scratch ring with 1-D bulk copies (cp.async.bulk), evict_last;
-//   * arithmetic as in rte_solvers_v4.cu (f32x2.cuh); orientation and the level-source convention are template parameters.
-// One warp per CTA, the ceil(ngpt/64) chunk-warps of a column form a cluster, partial fluxes are combined through DSMEM
-// in rank order (deterministic), clusters are persistent over columns.
+//   * one elected lane issues ONE cp.async.bulk.tensor.2d per input array per group of 8 layers (box 64 g-points x 8 rows of
+//     the [rows][ngpt] tensor) into a ring of shared-memory stages, one or two groups ahead, signalled by mbarriers; lanes
+//     read their two g-points with LDS.64 at immediate offsets -- no per-lane address arithmetic, no prefetch registers;
+//   * the reverse-sweep coefficients (LW: t, source_up -- 16 B per lane and layer; SW: e, f, alpha_above -- 24 B) go to an
+//     L2-resident scratch with per-lane 8-byte stores (evict_last) and come back by one bulk copy per group into the idle
+//     input ring (see the v6 note below);
+//   * arithmetic in f32x2.cuh; orientation and the level-source convention are template parameters.
+// One warp = one solver (a 64-g-point chunk of one column), `solver_warps` of them per CTA on adjacent columns, the
+// ceil(ngpt/64) chunk-CTAs of a column form a cluster, partial fluxes are combined through DSMEM in rank order
+// (deterministic), clusters are persistent over columns.
+// History: v3 (rte_solvers.cu, one g-point per lane, the fallback for odd shapes) -> v4 (packed, per-lane loads) -> v5 (TMA
+// inputs, staged bulk stores of the scratch) -> v6; v4 and v5 are gone from the tree (git history; profiles/r1*).
 #include "solver_common.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -27,49 +28,11 @@
 namespace rrnn {
 namespace v5 {
 
-// Layers per group (one TMA box) and stages of the input / back-sweep rings, tuned per kernel on B200 (1 M x 137):
-// LW 8 x 2 (146 -> 124 ms against 4 x 3: more independent layers per warp), SW 4 x 3 (8 x 2: 238 ms, 4 x 3: 224 ms --
-// the two-stream arithmetic already fills the registers at 4 layers).
-#ifndef RRNN_V5_LW_U
-#define RRNN_V5_LW_U 8
-#endif
-#ifndef RRNN_V5_LW_S
-#define RRNN_V5_LW_S 2
-#endif
 #ifndef RRNN_V5_DISCARD
 #define RRNN_V5_DISCARD 1
 #endif
-#ifndef RRNN_V5_LW_SB
-#define RRNN_V5_LW_SB 3
-#endif
-#ifndef RRNN_V5_SW_SB
-#define RRNN_V5_SW_SB 2
-#endif
-#ifndef RRNN_V5_SW_NOB
-#define RRNN_V5_SW_NOB 2
-#endif
-#ifndef RRNN_V5_SW_U
-#define RRNN_V5_SW_U 8
-#endif
-#ifndef RRNN_V5_SW_S
-#define RRNN_V5_SW_S 2
-#endif
 constexpr int MAX_WARPS = 4;  // solvers (warps) per CTA
-constexpr int LW_U = RRNN_V5_LW_U, LW_S = RRNN_V5_LW_S, SW_U = RRNN_V5_SW_U, SW_S = RRNN_V5_SW_S;
-constexpr int SW_OBR = (SW_U > 4) ? SW_U / RRNN_V5_SW_NOB : SW_U;
-// layers per store-staging tile of the SW kernel (<= SW_OBR, which stays the batch of the two-stream coefficients)
-#ifndef RRNN_V5_SW_STL
-#define RRNN_V5_SW_STL SW_OBR
-#endif
-constexpr int SW_STL = RRNN_V5_SW_STL;
-static_assert(SW_OBR % SW_STL == 0, "staging tile must divide the coefficient batch");
-#ifndef RRNN_V5_LW_NOB
-#define RRNN_V5_LW_NOB 2
-#endif
-constexpr int LW_OBR = (LW_U > 4) ? LW_U / RRNN_V5_LW_NOB : LW_U;
-// stages of the reverse-sweep (upward) ring: the upward sweep spends only a few hundred cycles per group, less than an L2 /
-// DRAM round trip, so it prefetches as deep as the shared memory of the downward sweep (which it reuses) allows
-constexpr int LW_SB = RRNN_V5_LW_SB, SW_SB = RRNN_V5_SW_SB;
+constexpr int LW_U = 8;       // layers per group (one TMA box)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -176,327 +139,6 @@ struct LwV5Params {
   int ngroups;
   int warp_smem;  // bytes of shared memory per warp
 };
-
-// ---------------------------------------------------------------------------------------------------- LW
-// COMPACT: the sources are not materialised per g-point.  `lay_source` holds the Planck fraction pfrac (G,L,C) and the two
-// small tables planck_lay (16,L,C) / planck_lev (16,L+1,C) the band Planck functions B_b(T_lay), B_b(T_lev); the kernel
-// forms lay_source = pfrac(l) B(T_lay(l)) and lev_source(l) = pfrac(min(l, L)) B(T_lev(l)) itself with the same single
-// fp32 multiplication compute_Planck_source_nn does (mo_gas_optics_kernels.F90:654-672): 8 instead of 12 bytes per
-// (g-point, layer) cross HBM, on both sides of the interface.
-template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT>
-__global__ void __launch_bounds__(32 * MAX_WARPS) lw_solver_v5(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
-                                                   const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev,
-                                                   const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  constexpr int U = LW_U, S = LW_S;
-  // one stage of the input ring.  Materialised: tau | lay_source | lev_source(ext rows), U rows of 256 B each.
-  // COMPACT: tau (U rows) | pfrac (PFR rows: top-down sweeps also need the next layer's) | B_lay | B_lev(ext) (U rows of 64 B)
-  constexpr int PFR = COMPACT ? (TOP ? U + 1 : U) : U;
-  constexpr int OFF_PF = U * 256, OFF_3 = OFF_PF + PFR * 256, OFF_BV = OFF_3 + U * 64;
-  constexpr int STAGE = COMPACT ? OFF_BV + U * 64 : 3 * U * 256;
-  const LwParams& p = pp.b;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
-  const int G = p.ngpt, L = p.nlay;
-  const uint64_t pol_in = policy_evict_first();
-  const uint64_t pol_buf = policy_evict_last();
-  cg::cluster_group cluster = cg::this_cluster();
-  const int chunk = (int)cluster.block_rank();
-  const int csize = (int)cluster.num_blocks();
-
-  // ---- shared memory: input ring, reverse-buffer staging (out: 2 tiles, back: S tiles), partial fluxes (2 sets), barriers
-  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
-  // The input ring and the store staging are only live during the downward sweep, the back ring only during the upward
-  // sweep (bulk_wait_all separates them): they share their shared memory, which is what bounds the CTAs per SM.
-  uint8_t* in_ring = smem;                                   // [S][STAGE]
-  constexpr int OBR = LW_OBR, NOB = U / OBR;                 // store staging in tiles of OBR layers (see sw_solver_v5)
-  uint8_t* ob = in_ring + S * STAGE;                         // [2][OBR][512 B]
-  uint8_t* bb = smem;                                        // [S][U][512 B]  (aliases in_ring / ob)
-  constexpr int FWD_BYTES = S * STAGE + 2 * OBR * 512, BWD_BYTES = LW_SB * U * 512;
-  float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][2][L+1]
-  const int part_set = 2 * (L + 1);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
-  const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
-  const uint32_t in_a = smem_u32(in_ring), ob_a = smem_u32(ob), bb_a = smem_u32(bb);
-  if (lane == 0) {
-    for (int s = 0; s < S + LW_SB; ++s) mbar_init(bar_in + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint32_t n_in = 0, n_bb = 0;  // groups consumed so far from each ring (stage = n % S, parity = (n / S) & 1)
-
-  const float tau_thresh = 3.4526698e-4f;  // sqrt(epsilon(1._sp)), mo_rte_solver_kernels.F90:754
-  const int g = chunk * 64 + 2 * lane;
-  const bool act = g < G;                // ngpt is even: a pair is live or not as a whole
-  const int gs = act ? g : chunk * 64;   // idle lanes shadow the chunk's first pair and contribute zero
-  const float live = act ? 1.0f : 0.0f;
-  const int NG = pp.ngroups;
-  const int NGF = L / U;                 // full groups; the ragged one (if any) is group NGF
-  // reverse-sweep scratch of this CTA in global memory (L2-resident): [L][32 lanes x 16 B]
-  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * 512;
-  const uint32_t lane_in = (uint32_t)lane * 8u;   // byte offset of this lane's pair in a 256-byte row
-  const uint32_t lane_bf = (uint32_t)lane * 16u;  // ... in a 512-byte reverse-buffer row
-  // COMPACT: byte offsets of the bands of this lane's two g-points in a 64-byte row of the Planck tables
-  uint32_t bo0 = 0, bo1 = 0;
-  if (COMPACT) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
-  auto band_pair = [&](const uint8_t* row) { return mk2(*reinterpret_cast<const float*>(row + bo0), *reinterpret_cast<const float*>(row + bo1)); };
-
-  int ncols_done = 0;
-  // The warps of a CTA take adjacent columns; all warps of a cluster make the same number of trips (one cluster barrier
-  // each), a warp past the last column recomputes it and does not write.
-  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
-    const bool owner = cb + warp < p.ncol;
-    const int col = owner ? cb + warp : p.ncol - 1;
-    float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
-    float* fdn = fup + (L + 1);
-    for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
-    const size_t gc_off = (size_t)col * G + gs;
-    const f2 emis = ldg2(p.sfc_emis + gc_off);
-    const f2 ssrc = ldg2(p.sfc_source + gc_off);
-    const f2 inc = p.inc_flux ? ldg2(p.inc_flux + gc_off) : splat2(0.0f);
-    // tensor rows of sweep layer 0: layers (tau, lay_source) and the level towards the surface (lev_source)
-    const int lay0 = col * L + (TOP ? 0 : L - 1);
-    const int ext0 = col * (L + 1) + (TOP ? 1 : L - 1);
-    // lev_source at the level where the sweep enters the atmosphere
-    f2 ent0;
-    if (COMPACT) {
-      const float* bv0 = p.planck_lev + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * 16;
-      ent0 = ldg2(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs) * mk2(__ldg(bv0 + (bo0 >> 2)), __ldg(bv0 + (bo1 >> 2)));
-    } else {
-      ent0 = ldg2(p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs);
-    }
-    __syncwarp();
-
-    for (int imu = 0; imu < p.nmus; ++imu) {
-      // the discards of the previous upward sweep (previous column, or previous angle of this one; generic proxy) are ordered
-      // before this sweep's bulk stores (async proxy) to the same scratch lines
-      if (RRNN_V5_DISCARD) asm volatile("fence.proxy.async.global;" ::: "memory");
-      const f2 D = splat2(p.Ds[imu]);
-      const f2 fac = splat2(2.0f * kPi * p.wts[imu] * live);
-      const float rad_norm = 2.0f * kPi * p.wts[imu];
-      f2 I = map2(inc, [&](float v) { return v / rad_norm; });  // radn_dn(top) = inc_flux/(2 pi w), :196-201
-      {
-        const float s = warp_sum(hsum2(fac * I));
-        if (lane == 0) fdn[TOP ? 0 : L] += s;
-      }
-      // one elected lane feeds the input ring: group k -> stage (n_in + k) % S
-      auto issue_in = [&](int k) {
-        if (k < NG) {
-          const uint32_t st = (n_in + (uint32_t)k) % S;
-          int sh;
-          const int rl = box_start<TOP, U>(lay0, k, sh), rv = box_start<TOP, U>(ext0, k, sh);
-          if (elect_one()) {
-            const uint32_t bar = bar_in + 8 * st;
-            const uint32_t dst = in_a + st * STAGE;
-            mbar_expect_tx(bar, STAGE);
-            tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
-            tma_load_2d(dst + OFF_PF, &tm_lay, chunk * 64, rl, bar, pol_in);
-            if (COMPACT) {
-              tma_load_2d(dst + OFF_3, &tm_bl, 0, rl, bar, pol_in);
-              tma_load_2d(dst + OFF_BV, &tm_bv, 0, rv, bar, pol_in);
-            } else {
-              tma_load_2d(dst + OFF_3, &tm_lev, chunk * 64, rv, bar, pol_in);
-            }
-          }
-          __syncwarp();
-        }
-      };
-      f2 carry = ent0;  // ent(0)
-#pragma unroll
-      for (int k = 0; k < S - 1; ++k) issue_in(k);
-      // The per-level broadband sums (butterfly shuffles: long dependent latencies, nothing downstream waits for them)
-      // are deferred by one group, so that they overlap the next group's arithmetic instead of stalling the warp.
-      float pend[U];
-      int pend_k = -1;
-      auto flush_dn = [&]() {
-        if (pend_k >= 0) {
-          multi_reduce<U>(pend, lane);
-          const int i = pend_k * U + multi_index<U>(lane);
-          if (multi_writer<U>(lane) && i < L) fdn[TOP ? i + 1 : L - 1 - i] += pend[0];
-        }
-      };
-      auto flush_up = [&]() {
-        if (pend_k >= 0) {
-          multi_reduce<U>(pend, lane);
-          const int i = pend_k * U + (U - 1 - multi_index<U>(lane));
-          if (multi_writer<U>(lane) && i < L) fup[TOP ? i : L - i] += pend[0];
-        }
-      };
-      // ---------------- downward sweep: one group of U layers ----------------
-      // TAIL = false: a full group whose boxes sit where box_start put them (immediate shared-memory offsets);
-      // TAIL = true: the ragged last group (nvalid < U) and/or a box that was moved (column 0, bottom-up)
-      auto forward_group = [&](int k, auto tail_c) {
-        constexpr bool TAIL = decltype(tail_c)::value;
-        __syncwarp();                 // every lane is done with the stage that group k+S-1 overwrites
-        issue_in(k + S - 1);
-        const uint32_t nk = n_in + (uint32_t)k;
-        const uint32_t st = nk % S;
-        mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
-        const uint8_t* stg = in_ring + st * STAGE;
-        const uint8_t* base = stg + lane_in;
-        int shl = 0, shv = 0, nvalid = U;
-        if (TAIL) {
-          box_start<TOP, U>(lay0, k, shl);
-          box_start<TOP, U>(ext0, k, shv);
-          nvalid = min(U, L - k * U);
-        }
-        f2 tau[U], lay[U], ext[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
-          const int rv = TAIL ? box_row<TOP, U>(u, shv) : (TOP ? u : U - 1 - u);
-          tau[u] = lds2(base + rl * 256);
-          if (COMPACT) {
-            const f2 pf = lds2(base + OFF_PF + rl * 256);
-            lay[u] = pf * band_pair(stg + OFF_3 + rl * 64);
-            // the level below the bottom layer takes that layer's fraction (:667-669); bottom-up sweeps leave through
-            // the layer's own level
-            const f2 pfx = (TOP && k * U + u != L - 1) ? lds2(base + OFF_PF + (rl + 1) * 256) : pf;
-            ext[u] = pfx * band_pair(stg + OFF_BV + rv * 64);
-          } else {
-            lay[u] = lds2(base + OFF_PF + rl * 256);
-            ext[u] = lds2(base + OFF_3 + rv * 256);
-          }
-        }
-        flush_dn();
-        f2 tv[U], sdn[U], sup[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const f2 ent = (u == 0) ? carry : ext[u - 1];
-          const f2 tl = tau[u] * D;
-          f2 t, omt;
-          exp_and_complement2<FAST>(tl, t, omt);
-          // fact = (1-t)/tau' - t, or its series where tau' is tiny (:757-768)
-          const f2 fa = div2<true>(omt, tl) - t;
-          const f2 fb = tl * fnma2(tl, splat2(1.0f / 3.0f), splat2(0.5f));
-          float tx, ty;
-          unpack2(tl, tx, ty);
-          const f2 fact = sel2(tx > tau_thresh, ty > tau_thresh, fa, fb);
-          const f2 f2x = fact + fact;
-          // lw_source_noscat (:770-773): source_dn from lev(l+1), source_up from lev(l) whatever the orientation (quirk Q1)
-          const f2 lev_dn = DN_EXT ? ext[u] : ent;
-          const f2 lev_up = DN_EXT ? ent : ext[u];
-          tv[u] = t;
-          sdn[u] = fma2(f2x, lay[u] - lev_dn, omt * lev_dn);
-          sup[u] = fma2(f2x, lay[u] - lev_up, omt * lev_up);
-        }
-        carry = ext[U - 1];
-        float red[U];
-#pragma unroll
-        for (int h = 0; h < NOB; ++h) {
-          // reverse-buffer staging tile (k*NOB + h) & 1 (OBR layers): free once the bulk store issued two tiles ago has read it
-          if (elect_one()) bulk_wait_read<1>();
-          __syncwarp();
-          const int slot = (k * NOB + h) & 1;
-          uint8_t* ot = ob + slot * (OBR * 512) + lane_bf;
-#pragma unroll
-          for (int uu = 0; uu < OBR; ++uu) {
-            const int u = h * OBR + uu;
-            if (!TAIL || u < nvalid) {  // warp-uniform
-              I = fma2(tv[u], I, sdn[u]);
-              sts22(ot + uu * 512, tv[u], sup[u]);
-            }
-            red[u] = hsum2(fac * I);
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (elect_one()) {
-            const int nrows = min(max(nvalid - h * OBR, 0), OBR);
-            if (nrows > 0)
-              bulk_store(scratch + ((size_t)k * U + h * OBR) * 512, ob_a + slot * (OBR * 512), (uint32_t)nrows * 512u, pol_buf);
-            bulk_commit();
-          }
-          __syncwarp();
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) pend[u] = red[u];
-        pend_k = k;
-      };
-      {
-        // bottom-up, column 0: the boxes of the last groups may have been moved -> generic path for those
-        const int nfast = (TOP || col > 0) ? NGF : max(NGF - 1, 0);
-        for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
-        for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
-      }
-      flush_dn();
-      pend_k = -1;
-      n_in += (uint32_t)NG;
-      // ---------------- surface ----------------
-      f2 Uu = fma2(I, splat2(1.0f) - emis, emis * ssrc);  // :269
-      {
-        const float s = warp_sum(hsum2(fac * Uu));
-        if (lane == 0) fup[TOP ? L : 0] += s;
-      }
-      // ---------------- upward sweep (reverse order) from the scratch ring ----------------
-      if (elect_one()) bulk_wait_all();  // all reverse-buffer stores have landed (bulk groups are per thread: the electing lane issued them)
-      __syncwarp();
-      auto issue_bb = [&](int j) {  // j-th group of the upward sweep = forward group NG-1-j
-        if (j < NG) {
-          const int k = NG - 1 - j;
-          const uint32_t st = (n_bb + (uint32_t)j) % LW_SB;
-          const uint32_t bytes = (uint32_t)min(U, L - k * U) * 512u;
-          if (elect_one()) {
-            mbar_expect_tx(bar_bb + 8 * st, bytes);
-            bulk_load(bb_a + st * (U * 512), scratch + (size_t)k * (U * 512), bytes, bar_bb + 8 * st, pol_buf);
-          }
-          __syncwarp();
-        }
-      };
-#pragma unroll
-      for (int j = 0; j < LW_SB - 1; ++j) issue_bb(j);
-      auto backward_group = [&](int j, auto tail_c) {
-        constexpr bool TAIL = decltype(tail_c)::value;
-        __syncwarp();
-        issue_bb(j + LW_SB - 1);
-        const int k = NG - 1 - j;
-        const uint32_t nj = n_bb + (uint32_t)j;
-        const uint32_t st = nj % LW_SB;
-        mbar_wait(bar_bb + 8 * st, (nj / LW_SB) & 1u);
-        const uint8_t* bt = bb + st * (U * 512) + lane_bf;
-        const int nvalid = TAIL ? min(U, L - k * U) : U;
-        discard_scratch(scratch + (size_t)k * (U * 512), (uint32_t)nvalid * 512u, lane);
-        f2 t[U], s[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) lds22(bt + (TAIL ? min(u, nvalid - 1) : u) * 512, t[u], s[u]);
-        flush_up();
-        float red[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
-          const int uu = U - 1 - u;
-          if (!TAIL || uu < nvalid) Uu = fma2(t[uu], Uu, s[uu]);
-          red[u] = hsum2(fac * Uu);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) pend[u] = red[u];
-        pend_k = k;
-      };
-      {
-        int j = 0;
-        if (NG > NGF) backward_group(j++, std::true_type{});  // the ragged group comes first on the way up
-        for (; j < NG; ++j) backward_group(j, std::false_type{});
-      }
-      flush_up();
-      pend_k = -1;
-      n_bb += (uint32_t)NG;
-      __syncwarp();
-    }
-    // ---- combine the chunks of this column: the ranks' partial sums are added in rank order through distributed
-    //      shared memory (deterministic), each rank doing its share of the levels.  Partial sums are double-buffered by column, so one cluster barrier per column
-    //      is enough: the other ranks only need it before they reuse this set, two columns later.
-    cluster.sync();
-    {
-      // every rank combines its share of the levels, adding the ranks' partial sums in rank order
-      float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
-      const int n = 2 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
-      for (int i = lo + lane; i < hi && owner; i += 32) {
-        float sacc = 0.0f;
-        for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
-        const int a = i / (L + 1);
-        gout[a][i - a * (L + 1)] = sacc;
-      }
-    }
-  }
-  cluster.sync();  // nobody leaves while another rank may still read its shared memory
-}
 
 // ---------------------------------------------------------------------------------------------------- SW
 // Two-stream coefficients of one layer for a pair of g-points (sw_two_stream_source :1405-1475; PIFM, Zdunkowski).
@@ -637,286 +279,6 @@ struct SwV5Params {
   int ngroups;
   int warp_smem;
 };
-
-// Reverse-buffer row of one layer: 32 lanes x (e, f) 16 B, then 32 lanes x alpha_above 8 B = 768 B
-constexpr int SWROW = 768;
-
-template <bool FAST, bool HAS_G, bool TOP>
-__global__ void __launch_bounds__(32 * MAX_WARPS) sw_solver_v5(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
-                                                   const __grid_constant__ CUtensorMap tm_ssa, const __grid_constant__ CUtensorMap tm_g) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  constexpr int U = SW_U, S = SW_S;
-  const SwParams& p = pp.b;
-  constexpr int NIN = HAS_G ? 3 : 2;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
-  const int G = p.ngpt, L = p.nlay;
-  const uint64_t pol_in = policy_evict_first();
-  const uint64_t pol_buf = policy_evict_last();
-  cg::cluster_group cluster = cg::this_cluster();
-  const int chunk = (int)cluster.block_rank();
-  const int csize = (int)cluster.num_blocks();
-
-  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
-  uint8_t* in_ring = smem;                                     // [S][NIN][U][256 B]: tau, ssa (, g)
-  // store staging: two tiles of OBR layers (groups of 8 layers are staged and stored in two halves: 6 KB less per solver)
-  constexpr int OBR = SW_OBR, NOB = U / OBR, STL = SW_STL, NST = OBR / STL;
-  uint8_t* ob = in_ring + S * NIN * U * 256;                   // [2][STL][768 B]
-  uint8_t* bb = smem;                                          // [S][U][768 B]  (aliases in_ring / ob, see lw_solver_v5)
-  constexpr int FWD_BYTES = S * NIN * U * 256 + 2 * STL * SWROW, BWD_BYTES = SW_SB * U * SWROW;
-  float* part = reinterpret_cast<float*>(smem + (FWD_BYTES > BWD_BYTES ? FWD_BYTES : BWD_BYTES));  // [2 sets][3][L+1]
-  const int part_set = 3 * (L + 1) + ((L + 1) & 1);            // keep the barriers 8-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
-  const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
-  const uint32_t in_a = smem_u32(in_ring), ob_a = smem_u32(ob), bb_a = smem_u32(bb);
-  if (lane == 0) {
-    for (int s = 0; s < S + SW_SB; ++s) mbar_init(bar_in + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint32_t n_in = 0, n_bb = 0;
-
-  const int g = chunk * 64 + 2 * lane;
-  const bool act = g < G;
-  const int gs = act ? g : chunk * 64;
-  const f2 live = splat2(act ? 1.0f : 0.0f);
-  const int NG = pp.ngroups;
-  const int NGF = L / U;
-  uint8_t* scratch = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * SWROW;
-  const uint32_t lane_in = (uint32_t)lane * 8u;
-  const uint32_t lane_ef = (uint32_t)lane * 16u, lane_al = 512u + (uint32_t)lane * 8u;
-  const int top_level = TOP ? 0 : L;
-
-  int ncols_done = 0;
-  // The warps of a CTA take adjacent columns; all warps of a cluster make the same number of trips (one cluster barrier
-  // each), a warp past the last column recomputes it and does not write.
-  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
-    const bool owner = cb + warp < p.ncol;
-    const int col = owner ? cb + warp : p.ncol - 1;
-    float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [3][L+1]
-    float* fdn = fup + (L + 1);
-    float* fdr = fdn + (L + 1);
-    for (int i = lane; i < 3 * (L + 1); i += 32) fup[i] = 0.0f;
-    // the previous column's discards (generic proxy) are ordered before this column's bulk stores (async proxy) to the same lines
-    if (RRNN_V5_DISCARD) asm volatile("fence.proxy.async.global;" ::: "memory");
-    const size_t gc_off = (size_t)col * G + gs;
-    const float mu0 = __ldg(p.mu0 + col);
-    const float mu0_inv = 1.0f / mu0;
-    const int lay0 = col * L + (TOP ? 0 : L - 1);
-    f2 dir = (live * ldg2(p.inc_flux + gc_off)) * splat2(mu0);                        // :589
-    f2 beta = p.inc_flux_dif ? live * ldg2(p.inc_flux_dif + gc_off) : splat2(0.0f);   // :590
-    f2 alpha = splat2(0.0f);
-    const f2 a_s = ldg2(p.alb_dif + gc_off);
-    const f2 a_d = ldg2(p.alb_dir + gc_off);
-    __syncwarp();
-    {
-      const float sd = warp_sum(hsum2(dir)), sb = warp_sum(hsum2(beta + dir));
-      if (lane == 0) { fdr[top_level] += sd; fdn[top_level] += sb; }
-    }
-    auto issue_in = [&](int k) {
-      if (k < NG) {
-        const uint32_t st = (n_in + (uint32_t)k) % S;
-        int sh;
-        const int rl = box_start<TOP, U>(lay0, k, sh);
-        if (elect_one()) {
-          const uint32_t bar = bar_in + 8 * st;
-          const uint32_t dst = in_a + st * (NIN * U * 256);
-          mbar_expect_tx(bar, NIN * U * 256);
-          tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
-          tma_load_2d(dst + U * 256, &tm_ssa, chunk * 64, rl, bar, pol_in);
-          if (HAS_G) tma_load_2d(dst + 2 * U * 256, &tm_g, chunk * 64, rl, bar, pol_in);
-        }
-        __syncwarp();
-      }
-    };
-#pragma unroll
-    for (int k = 0; k < S - 1; ++k) issue_in(k);
-    // per-level broadband sums deferred by one group (see lw_solver_v5)
-    float pend[2 * U];
-    int pend_k = -1;
-    auto flush_fwd = [&]() {
-      if (pend_k >= 0) {
-        multi_reduce<2 * U>(pend, lane);
-        const int idx = multi_index<2 * U>(lane);
-        const int i = pend_k * U + (idx & (U - 1));
-        if (multi_writer<2 * U>(lane) && i < L) {
-          const int lvl = TOP ? i + 1 : L - 1 - i;
-          if (idx < U) fdr[lvl] += pend[0]; else fdn[lvl] += pend[0];
-        }
-      }
-    };
-    auto flush_bwd = [&]() {
-      if (pend_k >= 0) {
-        multi_reduce<2 * U>(pend, lane);
-        const int idx = multi_index<2 * U>(lane);
-        const int i = pend_k * U + (U - 1 - (idx & (U - 1)));
-        if (multi_writer<2 * U>(lane) && i < L) {
-          const int lvl = TOP ? i : L - i;  // level at the top of layer i
-          if (idx < U) fup[lvl] += pend[0]; else fdn[lvl] += pend[0];
-        }
-      }
-    };
-    // ---------------- sweep 1: top -> surface ----------------
-    auto forward_group = [&](int k, auto tail_c) {
-      constexpr bool TAIL = decltype(tail_c)::value;
-      __syncwarp();
-      issue_in(k + S - 1);
-      const uint32_t nk = n_in + (uint32_t)k;
-      const uint32_t st = nk % S;
-      mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
-      const uint8_t* base = in_ring + st * (NIN * U * 256) + lane_in;
-      int shl = 0, nvalid = U;
-      if (TAIL) {
-        box_start<TOP, U>(lay0, k, shl);
-        nvalid = min(U, L - k * U);
-      }
-      flush_fwd();
-      // the sequential part: direct beam and the adding recurrences, eliminated from the top
-      float red[2 * U];
-#pragma unroll
-      for (int h = 0; h < NOB; ++h) {
-        // layer coefficients of this half: independent across its OBR layers (instruction-level parallelism); a group of
-        // 8 layers is done in two halves so that the register footprint stays that of 4 layers
-        f2 tau[OBR], w0[OBR], gg[OBR];
-#pragma unroll
-        for (int uu = 0; uu < OBR; ++uu) {
-          const int u = h * OBR + uu;
-          const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
-          tau[uu] = lds2(base + rl * 256);
-          w0[uu] = lds2(base + U * 256 + rl * 256);
-          gg[uu] = HAS_G ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
-        }
-        f2 Rdif[OBR], Tdif[OBR], Rdir[OBR], Tdir[OBR], Tnos[OBR];
-        two_stream2_batch<FAST, HAS_G, OBR>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
-        // staging tiles of STL layers, alternating between two slots: a slot is free once the bulk store issued two tiles
-        // ago has read it
-#pragma unroll
-        for (int t = 0; t < NST; ++t) {
-          if (elect_one()) bulk_wait_read<1>();
-          __syncwarp();
-          const int slot = ((k * NOB + h) * NST + t) & 1;
-          uint8_t* ot = ob + slot * (STL * SWROW);
-#pragma unroll
-          for (int ss = 0; ss < STL; ++ss) {
-            const int uu = t * STL + ss;
-            const int u = h * OBR + uu;
-            if (!TAIL || u < nvalid) {  // warp-uniform
-              const f2 s_up = Rdir[uu] * dir;
-              const f2 s_dn = Tdir[uu] * dir;
-              dir = Tnos[uu] * dir;
-              const f2 d = rcp2<FAST>(fnma2(Rdif[uu], alpha, splat2(1.0f)));
-              const f2 e = d * Tdif[uu];
-              const f2 f = d * fma2(Rdif[uu], beta, s_up);
-              sts2(ot + ss * SWROW + lane_al, alpha);  // reflectance of the atmosphere ABOVE this layer: what sweep 2 needs
-              sts22(ot + ss * SWROW + lane_ef, e, f);
-              beta = fma2(e, fma2(alpha, s_up, beta), s_dn);
-              alpha = fma2(Tdif[uu] * e, alpha, Rdif[uu]);
-            }
-            red[u] = hsum2(dir);
-            red[U + u] = hsum2(beta + dir);
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (elect_one()) {
-            const int nrows = min(max(nvalid - (h * OBR + t * STL), 0), STL);
-            if (nrows > 0)
-              bulk_store(scratch + ((size_t)k * U + h * OBR + t * STL) * SWROW, ob_a + slot * (STL * SWROW), (uint32_t)nrows * SWROW, pol_buf);
-            bulk_commit();
-          }
-          __syncwarp();
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
-      pend_k = k;
-    };
-    {
-      const int nfast = (TOP || col > 0) ? NGF : max(NGF - 1, 0);
-      for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
-      for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
-    }
-    flush_fwd();
-    pend_k = -1;
-    n_in += (uint32_t)NG;
-    // ---------------- surface ----------------
-    const f2 S_s = dir * a_d;  // source_sfc :1477
-    f2 Uu = div2<FAST>(fma2(a_s, beta, S_s), fnma2(a_s, alpha, splat2(1.0f))) * live;
-    {
-      const int sfc = TOP ? L : 0;
-      const float su = warp_sum(hsum2(Uu)), sa = warp_sum(hsum2(alpha * Uu));
-      if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
-    }
-    // ---------------- sweep 2: surface -> top (back substitution) ----------------
-    if (elect_one()) bulk_wait_all();
-    __syncwarp();
-    auto issue_bb = [&](int j) {
-      if (j < NG) {
-        const int k = NG - 1 - j;
-        const uint32_t st = (n_bb + (uint32_t)j) % SW_SB;
-        const uint32_t bytes = (uint32_t)min(U, L - k * U) * SWROW;
-        if (elect_one()) {
-          mbar_expect_tx(bar_bb + 8 * st, bytes);
-          bulk_load(bb_a + st * (U * SWROW), scratch + (size_t)k * (U * SWROW), bytes, bar_bb + 8 * st, pol_buf);
-        }
-        __syncwarp();
-      }
-    };
-#pragma unroll
-    for (int j = 0; j < SW_SB - 1; ++j) issue_bb(j);
-    auto backward_group = [&](int j, auto tail_c) {
-      constexpr bool TAIL = decltype(tail_c)::value;
-      __syncwarp();
-      issue_bb(j + SW_SB - 1);
-      const int k = NG - 1 - j;
-      const uint32_t nj = n_bb + (uint32_t)j;
-      const uint32_t st = nj % SW_SB;
-      mbar_wait(bar_bb + 8 * st, (nj / SW_SB) & 1u);
-      const uint8_t* bt = bb + st * (U * SWROW);
-      const int nvalid = TAIL ? min(U, L - k * U) : U;
-      discard_scratch(scratch + (size_t)k * (U * SWROW), (uint32_t)nvalid * SWROW, lane);
-      f2 e[U], f[U], a[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ru = TAIL ? min(u, nvalid - 1) : u;
-        lds22(bt + ru * SWROW + lane_ef, e[u], f[u]);
-        a[u] = lds2(bt + ru * SWROW + lane_al);
-      }
-      flush_bwd();
-      float red[2 * U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
-        const int uu = U - 1 - u;
-        if (!TAIL || uu < nvalid) Uu = fma2(e[uu], Uu, f[uu]);
-        red[u] = hsum2(Uu);               // upward flux at the level on top of that layer
-        red[U + u] = hsum2(a[uu] * Uu);   // diffuse downward flux there: alpha_above * U (+ beta, added in sweep 1)
-      }
-#pragma unroll
-      for (int u = 0; u < 2 * U; ++u) pend[u] = red[u];
-      pend_k = k;
-    };
-    {
-      int j = 0;
-      if (NG > NGF) backward_group(j++, std::true_type{});
-      for (; j < NG; ++j) backward_group(j, std::false_type{});
-    }
-    flush_bwd();
-    pend_k = -1;
-    n_bb += (uint32_t)NG;
-    __syncwarp();
-    // ---- combine the chunks of this column (see lw_solver_v5)
-    cluster.sync();
-    {
-      float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1), p.flux_dir + (size_t)col * (L + 1)};
-      const int n = 3 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
-      for (int i = lo + lane; i < hi && owner; i += 32) {
-        float sacc = 0.0f;
-        for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
-        const int a = i / (L + 1);
-        gout[a][i - a * (L + 1)] = sacc;
-      }
-    }
-  }
-  cluster.sync();
-}
 
 // ==================================================================================================== v6
 // Second generation of the TMA-staged packed solvers.  What ncu and three ablation builds of sw_solver_v5 showed
@@ -1618,55 +980,6 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_sm
 // The shapes the v5 kernels take (TMA: row pitch a multiple of 16 B; one cluster per column)
 bool lw_v5_supports(int G, int L) { return !(G & 3) && (G + 63) / 64 <= 8 && L >= v5::LW_U; }
 
-// returns -1 when the shape does not fit (the caller falls back to the per-lane-load kernels)
-int launch_lw_v5(rrnn_ctx_t* ctx, LwParams& p) {
-  const int G = p.ngpt, L = p.nlay;
-  const int csize = (G + 63) / 64;
-  const bool compact = p.planck_lay != nullptr;
-  if (!lw_v5_supports(G, L)) return -1;
-  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source, (const void*)p.planck_lay, (const void*)p.planck_lev})
-    if ((uintptr_t)q & 15) return -1;
-  for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
-    if ((uintptr_t)q & 7) return -1;
-  v5::LwV5Params pp;
-  pp.b = p;
-  pp.ngroups = (L + v5::LW_U - 1) / v5::LW_U;
-  const long long rows_lay = (long long)p.ncol * L, rows_lev = (long long)p.ncol * (L + 1);
-  if (rows_lev >= (1LL << 31) - 8) return -1;
-  const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
-  constexpr int U = v5::LW_U, S = v5::LW_S;
-  CUtensorMap tm_tau, tm_lay, tm_lev, tm_bl, tm_bv;
-  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, U)) return rc;
-  size_t stage;
-  if (compact) {
-    if (!p.planck_lev || !p.gpt2band) return fail("lw_solver: incomplete compact source description");
-    const int pfr = top ? U + 1 : U;
-    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, pfr)) return rc;
-    if (int rc = v5::make_map(&tm_bl, p.planck_lay, 16, rows_lay, U, 16)) return rc;
-    if (int rc = v5::make_map(&tm_bv, p.planck_lev, 16, rows_lev, U, 16)) return rc;
-    tm_lev = tm_tau;
-    stage = (size_t)U * 256 + (size_t)pfr * 256 + 2 * U * 64;
-  } else {
-    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, U)) return rc;
-    if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev, U)) return rc;
-    tm_bl = tm_tau; tm_bv = tm_tau;
-    stage = (size_t)3 * U * 256;
-  }
-  const size_t smem = std::max<size_t>((size_t)S * stage + 2 * v5::LW_OBR * 512, (size_t)v5::LW_SB * U * 512) + 4 * (size_t)(L + 1) * 4 + (S + v5::LW_SB) * 8;
-  const size_t per_cta = (size_t)L * 512;
-#define LW5(F, T, D, C) launch_clustered(ctx, v5::lw_solver_v5<F, T, D, C>, csize, smem, per_cta, 160, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv)
-#define LW5C(F, T, D) (compact ? LW5(F, T, D, true) : LW5(F, T, D, false))
-  if (fast) {
-    if (top) return LW5C(true, true, true);
-    return dn_ext ? LW5C(true, false, true) : LW5C(true, false, false);
-  }
-  if (top) return LW5C(false, true, true);
-  return dn_ext ? LW5C(false, false, true) : LW5C(false, false, false);
-#undef LW5C
-#undef LW5
-}
-
-
 // v6: the default (see lw_solver_v6); returns -1 when the shape does not fit
 int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
   const int G = p.ngpt, L = p.nlay;
@@ -1714,40 +1027,6 @@ int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
 #undef LW6C
 #undef LW6
 }
-
-int launch_sw_v5(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
-  const int G = p.ngpt, L = p.nlay;
-  const int csize = (G + 63) / 64;
-  if ((G & 3) || csize > 8 || L < v5::SW_U) return -1;
-  for (const void* q : {(const void*)p.tau, (const void*)p.ssa, (const void*)p.g})
-    if ((uintptr_t)q & 15) return -1;
-  for (const void* q : {(const void*)p.inc_flux, (const void*)p.inc_flux_dif, (const void*)p.alb_dir, (const void*)p.alb_dif})
-    if ((uintptr_t)q & 7) return -1;
-  v5::SwV5Params pp;
-  pp.b = p;
-  pp.ngroups = (L + v5::SW_U - 1) / v5::SW_U;
-  const long long rows = (long long)p.ncol * L;
-  if (rows >= (1LL << 31) - 8) return -1;
-  CUtensorMap tm_tau, tm_ssa, tm_g;
-  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows, v5::SW_U)) return rc;
-  if (int rc = v5::make_map(&tm_ssa, p.ssa, G, rows, v5::SW_U)) return rc;
-  if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, v5::SW_U)) return rc; }
-  else tm_g = tm_ssa;
-  const int nin = p.g ? 3 : 2;
-  const size_t smem = std::max<size_t>((size_t)v5::SW_S * nin * v5::SW_U * 256 + 2 * v5::SW_STL * v5::SWROW, (size_t)v5::SW_SB * v5::SW_U * v5::SWROW) +
-                      2 * (size_t)(3 * (L + 1) + 1) * 4 + (v5::SW_S + v5::SW_SB) * 8;
-  const size_t per_cta = (size_t)L * v5::SWROW;
-  const bool top = p.top_at_1 != 0;
-#define SW5(F, HG, T) launch_clustered(ctx, v5::sw_solver_v5<F, HG, T>, csize, smem, per_cta, 250, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
-  if (fast) {
-    if (p.g) return top ? SW5(true, true, true) : SW5(true, true, false);
-    return top ? SW5(true, false, true) : SW5(true, false, false);
-  }
-  if (p.g) return top ? SW5(false, true, true) : SW5(false, true, false);
-  return top ? SW5(false, false, true) : SW5(false, false, false);
-#undef SW5
-}
-
 
 // v6: the default (see sw_solver_v6)
 int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {

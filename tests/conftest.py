@@ -40,10 +40,10 @@ def nn_variant(request, gpu_ctx):
         assert tc1 == tc0, f"an fp32_ffma test ran the tcgen05 kernel {tc1 - tc0} time(s)"
 
 
-@pytest.fixture(params=[0, 2, 1], ids=["v5_tma_packed", "v4_packed", "v3_scalar"])
+@pytest.fixture(params=[0, 1], ids=["v6_tma_packed", "v3_scalar"])
 def solver_variant(request, gpu_ctx):
-    """The three generations of RTE solver kernels behind rrnn_lw_solver_noscat / rrnn_sw_solver_2stream: TMA-staged
-    packed fp32x2 (default), packed with per-lane loads, one g-point per lane."""
+    """The RTE solver kernels behind rrnn_lw_solver_noscat / rrnn_sw_solver_2stream: TMA-staged packed fp32x2 (default;
+    rte_solvers_tma.cu) and one g-point per lane (rte_solvers.cu, the fallback for shapes the packed kernels do not take)."""
     gpu_ctx.set_flag("solver_variant", request.param)
     yield request.param
     gpu_ctx.set_flag("solver_variant", 0)

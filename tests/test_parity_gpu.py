@@ -1126,3 +1126,79 @@ def test_error_behaviour(gpu_ctx):
     fl = api.ty_fluxes_broadband(torch.empty((4, 61), device="cuda"), torch.empty((4, 61), device="cuda"))
     assert "too many quadrature" in api.rte_lw(op, True, src, np.ones((4, 16), np.float32), fl, n_gauss_angles=5)
     assert "sfc_emis inconsistently sized" in api.rte_lw(op, True, src, np.ones((4, 15), np.float32), fl)
+
+
+def test_host_pipeline_pageable_equals_pinned(gpu_ctx):
+    """rrnn_{lw,sw}_fluxes_host with pageable caller memory (plain numpy: staged through the library's pinned bounce ring by
+    host threads) and with page-locked caller memory must give bit-identical fluxes, over several chunks and a ragged last one."""
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    torch = _torch()
+    ncol, nlay = 2500, 60
+    atm = synth.make_atmosphere(ncol, nlay, seed=17)
+    gc = H.gas_concs(atm["gases"])
+    k_lw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_lw.load(spectral.synthetic_kdist_lw(256)) == ""
+    k_sw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_sw.load(spectral.synthetic_kdist_sw(224)) == ""
+    nl, ns = H.device_nets(gpu_ctx, H.LW_G256), H.device_nets(gpu_ctx, H.SW_G224)
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    keep = {k: pinned(atm[k]) for k in ("play", "plev", "tlay", "tlev", "tsfc", "sfc_emis", "sfc_alb", "mu0")}
+    gp = api.ty_gas_concs()
+    for k, v in atm["gases"].items():
+        if np.ndim(v) == 2:
+            keep["gas_" + k] = pinned(v); gp.set_vmr(k, keep["gas_" + k].numpy())
+        else:
+            gp.set_vmr(k, float(v))
+    P = {k: v.numpy() for k, v in keep.items()}
+    gpu_ctx.set_chunk_columns(700)   # 4 chunks, the last one ragged
+    try:
+        for threads in (1, 3):
+            gpu_ctx.set_flag("host_copy_threads", threads)
+            a = api.lw_fluxes_host(k_lw, nl, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["sfc_emis"], gc, tlev=atm["tlev"])
+            out = [pinned(np.zeros((ncol, nlay + 1), np.float32)) for _ in range(2)]
+            b = api.lw_fluxes_host(k_lw, nl, P["play"], P["plev"], P["tlay"], P["tsfc"], P["sfc_emis"], gp, tlev=P["tlev"],
+                                   flux_up=out[0].numpy(), flux_dn=out[1].numpy())
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            a = api.sw_fluxes_host(k_sw, ns, atm["play"], atm["plev"], atm["tlay"], atm["mu0"], atm["sfc_alb"], gc)
+            b = api.sw_fluxes_host(k_sw, ns, P["play"], P["plev"], P["tlay"], P["mu0"], P["sfc_alb"], gp)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+            assert np.isfinite(a[0]).all() and a[1].max() > 100.0
+    finally:
+        gpu_ctx.set_chunk_columns(0)
+        gpu_ctx.set_flag("host_copy_threads", 0)
+    # a caller-supplied output array of the wrong kind is an error, not a write past the buffer
+    with pytest.raises(ValueError):
+        api.lw_fluxes_host(k_lw, nl, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["sfc_emis"], gc, tlev=atm["tlev"],
+                           flux_up=np.zeros((ncol, nlay + 1), np.float64))
+    with pytest.raises(ValueError):
+        api.sw_fluxes_host(k_sw, ns, atm["play"], atm["plev"], atm["tlay"], atm["mu0"], atm["sfc_alb"], gc,
+                           flux_dn=np.zeros((ncol, nlay), np.float32))
+
+
+def test_rte_rrtmgp_config_checks(gpu_ctx):
+    """check_extents / check_values (rte/mo_rte_rrtmgp_config.F90:23-24, 52-67; used at mo_gas_optics_rrtmgp.F90:287-315, 474-494):
+    off by default, the reference's messages when on."""
+    from rte_rrtmgp_nn_b200 import api
+    kd, atm, k_dist, onets, dnets = _lw_setup(gpu_ctx, H.LW_G256, 256, 6, 60, seed=4)
+    ncol, nlay = atm["play"].shape
+    op = api.ty_optical_props_1scl(); assert op.alloc_1scl(ncol, nlay, k_dist) == ""
+    src = api.ty_source_func_lw(); assert src.alloc(ncol, nlay, k_dist) == ""
+    gc = H.gas_concs(atm["gases"])
+    cold = atm["tlay"].copy(); cold[2, 5] = 120.0          # below temp_ref_min = 160 K
+    run = lambda **kw: k_dist.gas_optics(kw.get("play", atm["play"]), kw.get("plev", atm["plev"]), kw.get("tlay", atm["tlay"]),
+                                         kw.get("tsfc", atm["tsfc"]), gc, op, src, tlev=atm["tlev"], neural_nets=dnets)
+    assert run(tlay=cold) == ""                              # default: no checks, as in the reference
+    try:
+        api.rte_rrtmgp_config_checks(True)
+        assert run() == ""
+        assert run(tlay=cold) == "gas_optics(): array tlay has values outside range"
+        neg = atm["plev"].copy(); neg[0, 0] = -1.0
+        assert run(plev=neg) == "gas_optics(): array plev has values outside range"
+        assert run(tsfc=atm["tsfc"][:-1]) == "gas_optics(): array tsfc has wrong size"
+        api.rte_rrtmgp_config_checks(True, False)
+        assert run(tlay=cold) == ""
+    finally:
+        api.rte_rrtmgp_config_checks(False)
