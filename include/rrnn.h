@@ -77,6 +77,14 @@ RRNN_API long long rrnn_ctx_launch_count(rrnn_ctx_t* ctx);
 enum { RRNN_NN_KERNEL_NONE = 0, RRNN_NN_KERNEL_FFMA = 1, RRNN_NN_KERNEL_TCGEN05 = 2 };
 RRNN_API int rrnn_ctx_last_nn_kernel(rrnn_ctx_t* ctx);
 RRNN_API int rrnn_ctx_nn_kernel_counts(rrnn_ctx_t* ctx, long long* n_tcgen05, long long* n_ffma);
+/* Device memory for hosts without a CUDA binding of their own (the Fortran veneer, fortran/mo_rrnn_veneer.F90): the derived
+ * types of the reference own allocatable host arrays (tau/ssa/g, sources: rte/mo_optical_props.F90:98-192,
+ * rte/mo_source_functions.F90:26-43); here they own device buffers.  Copies are ordered on the context's stream and complete
+ * before the call returns. */
+RRNN_API int rrnn_dev_malloc(rrnn_ctx_t* ctx, size_t bytes, void** out_d);
+RRNN_API int rrnn_dev_free(rrnn_ctx_t* ctx, void* p_d);
+RRNN_API int rrnn_memcpy_h2d(rrnn_ctx_t* ctx, void* dst_d, const void* src, size_t bytes);
+RRNN_API int rrnn_memcpy_d2h(rrnn_ctx_t* ctx, void* dst, const void* src_d, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* NN models: rrtmgp_network_type%load_netcdf, neural/mod_network_rrtmgp.F90:58-122                   */
@@ -330,6 +338,35 @@ RRNN_API int rrnn_sw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_
                             float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d);
 /* Column chunk used by the drivers above (0 = automatic from free device memory). */
 RRNN_API int rrnn_ctx_set_chunk_columns(rrnn_ctx_t* ctx, int ncol_chunk);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* One process, N devices.  The reference's drivers run their column blocks under an OpenMP parallel-do with firstprivate
+ * copies of the k-distribution and the networks (examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:364-368, rrtmgp_rfmip_sw.F90:
+ * 352-356); here the "threads" are GPUs: a rrnn_multi_t holds one context per device with the spectral tables and the networks
+ * replicated on each, the columns of a call are cut into contiguous shards (sizes differing by at most one column), every
+ * shard runs rrnn_{lw,sw}_fluxes_host on its own host thread and writes its fluxes straight into its slice of the caller's
+ * HOST arrays.  No exchange step, hence no collective.  devices = NULL means devices 0 .. ndev-1; a device may be listed twice. */
+typedef struct rrnn_multi rrnn_multi_t;
+RRNN_API int rrnn_multi_create(int ndev, const int* devices, rrnn_multi_t** out);
+RRNN_API int rrnn_multi_destroy(rrnn_multi_t* m);
+RRNN_API int rrnn_multi_ndev(const rrnn_multi_t* m);
+RRNN_API rrnn_ctx_t* rrnn_multi_ctx(rrnn_multi_t* m, int i);               /* the i-th device's context (flags, profiling) */
+RRNN_API int rrnn_multi_set_flag(rrnn_multi_t* m, const char* name, int value);   /* rrnn_ctx_set_flag on every device */
+/* rrtmgp_network_type%load_netcdf (neural/mod_network_rrtmgp.F90:58-122) onto every device; returns an id for the calls below */
+RRNN_API int rrnn_multi_model_load_netcdf(rrnn_multi_t* m, const char* filename, int* model_id);
+/* rrnn_kdist_create on every device; returns an id */
+RRNN_API int rrnn_multi_kdist_create(rrnn_multi_t* m, int nbnd, int ngpt, const int* band_lims_gpt, int ntemp, const float* totplnk,
+                                     float temp_ref_min, float totplnk_delta, const float* solar_source, int* kdist_id);
+RRNN_API int rrnn_multi_kdist_set_tsi(rrnn_multi_t* m, int kdist_id, float tsi);
+/* rrnn_lw_fluxes_host / rrnn_sw_fluxes_host over all devices (same arguments, ids instead of handles) */
+RRNN_API int rrnn_multi_lw_fluxes_host(rrnn_multi_t* m, int kdist_id, const int* model_ids, int nmodels, int ncol, int nlay, int top_at_1,
+                                       int n_gauss_angles, const float* play, const float* plev, const float* tlay, const float* tlev,
+                                       const float* tsfc, const float* sfc_emis, const rrnn_gas_t* gases, int ngas, float* flux_up,
+                                       float* flux_dn);
+RRNN_API int rrnn_multi_sw_fluxes_host(rrnn_multi_t* m, int kdist_id, const int* model_ids, int ncol, int nlay, int top_at_1,
+                                       const float* play, const float* plev, const float* tlay, const float* mu0, const float* sfc_alb,
+                                       const float* tsi, const rrnn_gas_t* gases, int ngas, float* flux_up, float* flux_dn,
+                                       float* flux_dn_dir);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,10 @@ _SIGS = {
     "rrnn_ctx_launch_count": (C.c_longlong, [vp]),
     "rrnn_ctx_last_nn_kernel": (C.c_int, [vp]),
     "rrnn_ctx_nn_kernel_counts": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "rrnn_dev_malloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+    "rrnn_dev_free": (C.c_int, [vp, vp]),
+    "rrnn_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "rrnn_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "rrnn_ctx_profile": (C.c_int, [vp, C.c_int]),
     "rrnn_ctx_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), c_int_p]),
     "rrnn_ctx_set_chunk_columns": (C.c_int, [vp, C.c_int]),
@@ -117,6 +121,18 @@ _SIGS = {
                                       vp, C.POINTER(rrnn_gas_t), C.c_int, vp, vp]),
     "rrnn_sw_fluxes_host": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                       C.POINTER(rrnn_gas_t), C.c_int, vp, vp, vp]),
+    "rrnn_multi_create": (C.c_int, [C.c_int, c_int_p, C.POINTER(vp)]),
+    "rrnn_multi_destroy": (C.c_int, [vp]),
+    "rrnn_multi_ndev": (C.c_int, [vp]),
+    "rrnn_multi_ctx": (vp, [vp, C.c_int]),
+    "rrnn_multi_set_flag": (C.c_int, [vp, C.c_char_p, C.c_int]),
+    "rrnn_multi_model_load_netcdf": (C.c_int, [vp, C.c_char_p, c_int_p]),
+    "rrnn_multi_kdist_create": (C.c_int, [vp, C.c_int, C.c_int, c_int_p, C.c_int, c_float_p, C.c_float, C.c_float, c_float_p, c_int_p]),
+    "rrnn_multi_kdist_set_tsi": (C.c_int, [vp, C.c_int, C.c_float]),
+    "rrnn_multi_lw_fluxes_host": (C.c_int, [vp, C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                            C.POINTER(rrnn_gas_t), C.c_int, vp, vp]),
+    "rrnn_multi_sw_fluxes_host": (C.c_int, [vp, C.c_int, c_int_p, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
+                                            C.POINTER(rrnn_gas_t), C.c_int, vp, vp, vp]),
     "rrnn_lw_fluxes": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                  C.POINTER(rrnn_gas_t), C.c_int, vp, vp]),
     "rrnn_sw_fluxes": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,

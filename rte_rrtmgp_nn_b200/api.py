@@ -1149,3 +1149,78 @@ def sw_fluxes(k_dist, neural_nets, play, plev, tlay, mu0, sfc_alb, gas_desc, flu
     _lib.check(_lib.lib().rrnn_sw_fluxes(ctx.h, k_dist._kd.h, _models(neural_nets), ncol, nlay, int(bool(top_at_1)), _ptr(play),
                                          _ptr(plev), _ptr(tlay), _ptr(mu0), _ptr(sfc_alb), _ptr(tsi), gases, ngas,
                                          _ptr(flux_up), _ptr(flux_dn), _ptr(flux_dn_dir)))
+
+
+class MultiDevice:
+    """One process, N devices (rrnn_multi_*): contexts, spectral tables and networks replicated per device, the columns of a
+    call cut into contiguous shards, every shard's host pipeline on its own thread, fluxes written into the caller's host arrays."""
+
+    def __init__(self, devices=None, ndev=None):
+        self.h = vp()
+        if devices is None:
+            n = int(ndev or _lib.lib().rrnn_device_count())
+            _lib.check(_lib.lib().rrnn_multi_create(n, None, C.byref(self.h)))
+        else:
+            d = np.ascontiguousarray(devices, np.int32)
+            _lib.check(_lib.lib().rrnn_multi_create(len(d), d.ctypes.data_as(_lib.c_int_p), C.byref(self.h)))
+        self.ndev = int(_lib.lib().rrnn_multi_ndev(self.h))
+
+    def set_flag(self, name, value):
+        _lib.check(_lib.lib().rrnn_multi_set_flag(self.h, name.encode(), int(value)))
+
+    def load_netcdf(self, filename):
+        i = C.c_int(-1)
+        _lib.check(_lib.lib().rrnn_multi_model_load_netcdf(self.h, str(filename).encode(), C.byref(i)))
+        return int(i.value)
+
+    def load_kdist(self, kd):
+        bl = np.ascontiguousarray(kd["band_lims_gpt"], np.int32)
+        tot, sol = kd.get("totplnk"), kd.get("solar_source")
+        tot_a = None if tot is None else np.ascontiguousarray(tot, np.float32)
+        sol_a = None if sol is None else np.ascontiguousarray(sol, np.float32)
+        fp = lambda a: None if a is None else a.ctypes.data_as(_lib.c_float_p)
+        i = C.c_int(-1)
+        _lib.check(_lib.lib().rrnn_multi_kdist_create(self.h, int(kd["nbnd"]), int(kd["ngpt"]), bl.ctypes.data_as(_lib.c_int_p),
+                                                      0 if tot_a is None else tot_a.shape[1], fp(tot_a), float(kd.get("temp_ref_min", 0.0)),
+                                                      float(kd.get("totplnk_delta", 1.0)), fp(sol_a), C.byref(i)))
+        return int(i.value)
+
+    def lw_fluxes_host(self, kdist_id, model_ids, play, plev, tlay, tsfc, sfc_emis, gas_desc, tlev=None, top_at_1=True,
+                       n_gauss_angles=1, flux_up=None, flux_dn=None):
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        play, plev, tlay, tlev, tsfc, sfc_emis = map(f32, (play, plev, tlay, tlev, tsfc, sfc_emis))
+        ncol, nlay = play.shape
+        flux_up = _flux_out(flux_up, ncol, nlay + 1, "lw_fluxes_host: flux_up")
+        flux_dn = _flux_out(flux_dn, ncol, nlay + 1, "lw_fluxes_host: flux_dn")
+        gases, ngas, keep = gas_desc._to_c(None, host=True)
+        ids = np.ascontiguousarray(model_ids, np.int32)
+        _lib.check(_lib.lib().rrnn_multi_lw_fluxes_host(self.h, int(kdist_id), ids.ctypes.data_as(_lib.c_int_p), len(ids), ncol, nlay,
+                                                        int(bool(top_at_1)), int(n_gauss_angles), _hp(play), _hp(plev), _hp(tlay), _hp(tlev),
+                                                        _hp(tsfc), _hp(sfc_emis), gases, ngas, _hp(flux_up), _hp(flux_dn)))
+        return flux_up, flux_dn
+
+    def sw_fluxes_host(self, kdist_id, model_ids, play, plev, tlay, mu0, sfc_alb, gas_desc, tsi=None, top_at_1=True, flux_up=None,
+                       flux_dn=None, flux_dn_dir=None):
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        play, plev, tlay, mu0, sfc_alb, tsi = map(f32, (play, plev, tlay, mu0, sfc_alb, tsi))
+        ncol, nlay = play.shape
+        flux_up = _flux_out(flux_up, ncol, nlay + 1, "sw_fluxes_host: flux_up")
+        flux_dn = _flux_out(flux_dn, ncol, nlay + 1, "sw_fluxes_host: flux_dn")
+        flux_dn_dir = _flux_out(flux_dn_dir, ncol, nlay + 1, "sw_fluxes_host: flux_dn_dir")
+        gases, ngas, keep = gas_desc._to_c(None, host=True)
+        ids = np.ascontiguousarray(model_ids, np.int32)
+        _lib.check(_lib.lib().rrnn_multi_sw_fluxes_host(self.h, int(kdist_id), ids.ctypes.data_as(_lib.c_int_p), ncol, nlay,
+                                                        int(bool(top_at_1)), _hp(play), _hp(plev), _hp(tlay), _hp(mu0), _hp(sfc_alb),
+                                                        _hp(tsi), gases, ngas, _hp(flux_up), _hp(flux_dn), _hp(flux_dn_dir)))
+        return flux_up, flux_dn, flux_dn_dir
+
+    def close(self):
+        if self.h:
+            _lib.lib().rrnn_multi_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -419,6 +419,39 @@ extern "C" int rrnn_ctx_synchronize(rrnn_ctx_t* c) {
   return 0;
 }
 extern "C" long long rrnn_ctx_launch_count(rrnn_ctx_t* c) { return c ? c->launches : 0; }
+// Device memory for hosts that have no CUDA binding of their own (the Fortran veneer): stream-ordered on the context's stream.
+extern "C" int rrnn_dev_malloc(rrnn_ctx_t* c, size_t bytes, void** out) {
+  RRNN_CHECK(c && out, "rrnn_dev_malloc: null argument");
+  RRNN_CUDA(cudaSetDevice(c->device));
+  *out = nullptr;
+  if (bytes == 0) return 0;
+  RRNN_CUDA(cudaMalloc(out, bytes));
+  return 0;
+}
+extern "C" int rrnn_dev_free(rrnn_ctx_t* c, void* p) {
+  RRNN_CHECK(c, "rrnn_dev_free: null context");
+  if (!p) return 0;
+  RRNN_CUDA(cudaSetDevice(c->device));
+  RRNN_CUDA(cudaStreamSynchronize(c->stream));
+  RRNN_CUDA(cudaFree(p));
+  return 0;
+}
+extern "C" int rrnn_memcpy_h2d(rrnn_ctx_t* c, void* dst_d, const void* src, size_t bytes) {
+  RRNN_CHECK(c && (bytes == 0 || (dst_d && src)), "rrnn_memcpy_h2d: null argument");
+  if (bytes == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(c->device));
+  RRNN_CUDA(cudaMemcpyAsync(dst_d, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  RRNN_CUDA(cudaStreamSynchronize(c->stream));   // the caller may reuse src at once
+  return 0;
+}
+extern "C" int rrnn_memcpy_d2h(rrnn_ctx_t* c, void* dst, const void* src_d, size_t bytes) {
+  RRNN_CHECK(c && (bytes == 0 || (dst && src_d)), "rrnn_memcpy_d2h: null argument");
+  if (bytes == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(c->device));
+  RRNN_CUDA(cudaMemcpyAsync(dst, src_d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  RRNN_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
 extern "C" int rrnn_ctx_last_nn_kernel(rrnn_ctx_t* c) { return c ? c->last_nn_kernel : 0; }
 extern "C" int rrnn_ctx_nn_kernel_counts(rrnn_ctx_t* c, long long* n_tc, long long* n_ffma) {
   RRNN_CHECK(c, "rrnn_ctx_nn_kernel_counts: null context");

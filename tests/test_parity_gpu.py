@@ -1202,3 +1202,36 @@ def test_rte_rrtmgp_config_checks(gpu_ctx):
         assert run(tlay=cold) == ""
     finally:
         api.rte_rrtmgp_config_checks(False)
+
+
+def test_multi_device_driver_matches_single_context(gpu_ctx):
+    """rrnn_multi_*: one process driving N devices (here every visible device, and device 0 listed twice so that the sharding
+    is exercised on a one-GPU box too).  Shards are contiguous, every column is independent: the fluxes must be bit-identical
+    to one call on one context."""
+    import os
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    torch = _torch()
+    ncol, nlay = 1501, 60
+    atm = synth.make_atmosphere(ncol, nlay, seed=23)
+    gc = H.gas_concs(atm["gases"])
+    kd_lw, kd_sw = spectral.synthetic_kdist_lw(256), spectral.synthetic_kdist_sw(224)
+    k_lw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_lw.load(kd_lw) == ""
+    k_sw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_sw.load(kd_sw) == ""
+    one_lw = api.lw_fluxes_host(k_lw, H.device_nets(gpu_ctx, H.LW_G256), atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["sfc_emis"],
+                                gc, tlev=atm["tlev"])
+    one_sw = api.sw_fluxes_host(k_sw, H.device_nets(gpu_ctx, H.SW_G224), atm["play"], atm["plev"], atm["tlay"], atm["mu0"], atm["sfc_alb"], gc)
+    nd = torch.cuda.device_count()
+    for devices in ([0, 0, 0], list(range(nd)) if nd > 1 else [0, 0]):
+        md = api.MultiDevice(devices=devices)
+        assert md.ndev == len(devices)
+        kl, ks = md.load_kdist(kd_lw), md.load_kdist(kd_sw)
+        ml = [md.load_netcdf(os.path.join(H.NN_DIR, f)) for f in H.LW_G256]
+        ms = [md.load_netcdf(os.path.join(H.NN_DIR, f)) for f in H.SW_G224]
+        up, dn = md.lw_fluxes_host(kl, ml, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["sfc_emis"], gc, tlev=atm["tlev"])
+        assert np.array_equal(up, one_lw[0]) and np.array_equal(dn, one_lw[1]), devices
+        got = md.sw_fluxes_host(ks, ms, atm["play"], atm["plev"], atm["tlay"], atm["mu0"], atm["sfc_alb"], gc)
+        for a, b in zip(got, one_sw):
+            assert np.array_equal(a, b), devices
+        md.close()
+    with pytest.raises(Exception):
+        api.MultiDevice(devices=[nd + 7])
