@@ -1,6 +1,6 @@
 ! ISO_C_BINDING interfaces of librrnn_b200.so -- GENERATED from include/rrnn.h by tools/gen_fortran_binding.py; do not edit.
 !
-! One interface block per C entry point (85 of 85).  Scalars by value; handles, device addresses and host
+! One interface block per C entry point (94 of 94).  Scalars by value; handles, device addresses and host
 ! arrays as type(c_ptr) values (host arrays: c_loc(a)); out-arguments and small integer / double arrays by reference.
 ! The comment above each block is the one the header carries: it cites the reference interface the entry point replaces.
 ! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler, SURVEY.md section 0 F1): `make -C fortran` builds it where
@@ -1062,6 +1062,75 @@ module mo_rrnn_c_binding
       integer(c_int), value :: ncol_chunk
       integer(c_int) :: rc
     end function rrnn_ctx_set_chunk_columns
+    function rrnn_nc_open(path, out_h) bind(C, name="rrnn_nc_open") result(rc)
+      import :: c_char, c_int, c_ptr
+      character(kind=c_char) :: path(*)
+      type(c_ptr) :: out_h
+      integer(c_int) :: rc
+    end function rrnn_nc_open
+    function rrnn_nc_create(path, out_h) bind(C, name="rrnn_nc_create") result(rc)
+      import :: c_char, c_int, c_ptr
+      character(kind=c_char) :: path(*)
+      type(c_ptr) :: out_h
+      integer(c_int) :: rc
+    end function rrnn_nc_create
+    function rrnn_nc_close(f) bind(C, name="rrnn_nc_close") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: f
+      integer(c_int) :: rc
+    end function rrnn_nc_close
+    function rrnn_nc_var_exists(f, name_c) bind(C, name="rrnn_nc_var_exists") result(rc)
+      import :: c_char, c_int, c_ptr
+      type(c_ptr), value :: f
+      character(kind=c_char) :: name_c(*)
+      integer(c_int) :: rc
+    end function rrnn_nc_var_exists
+    ! 1 / 0
+    function rrnn_nc_inq_var(f, name_c, ndims, shape) bind(C, name="rrnn_nc_inq_var") result(rc)
+      import :: c_char, c_int, c_long_long, c_ptr
+      type(c_ptr), value :: f
+      character(kind=c_char) :: name_c(*)
+      integer(c_int) :: ndims(*)
+      integer(c_long_long) :: shape(*)
+      integer(c_int) :: rc
+    end function rrnn_nc_inq_var
+    ! any numeric variable, converted to float (real(wp) read_field)
+    function rrnn_nc_get_var_float(f, name_c, data_out, n) bind(C, name="rrnn_nc_get_var_float") result(rc)
+      import :: c_char, c_int, c_ptr, c_size_t
+      type(c_ptr), value :: f
+      character(kind=c_char) :: name_c(*)
+      type(c_ptr), value :: data_out
+      integer(c_size_t), value :: n
+      integer(c_int) :: rc
+    end function rrnn_nc_get_var_float
+    function rrnn_nc_get_att_text(f, var, att, buf, nbuf) bind(C, name="rrnn_nc_get_att_text") result(rc)
+      import :: c_char, c_int, c_ptr
+      type(c_ptr), value :: f
+      character(kind=c_char) :: var(*)
+      character(kind=c_char) :: att(*)
+      character(kind=c_char) :: buf(*)
+      integer(c_int), value :: nbuf
+      integer(c_int) :: rc
+    end function rrnn_nc_get_att_text
+    function rrnn_nc_def_dim(f, name_c, len_i, dimid) bind(C, name="rrnn_nc_def_dim") result(rc)
+      import :: c_char, c_int, c_long_long, c_ptr
+      type(c_ptr), value :: f
+      character(kind=c_char) :: name_c(*)
+      integer(c_long_long), value :: len_i
+      integer(c_int) :: dimid(*)
+      integer(c_int) :: rc
+    end function rrnn_nc_def_dim
+    ! create_var + write_field: a float variable over already-defined dimensions; units may be NULL
+    function rrnn_nc_put_var_float(f, name_c, ndims, dimids, data_p, units) bind(C, name="rrnn_nc_put_var_float") result(rc)
+      import :: c_char, c_int, c_ptr
+      type(c_ptr), value :: f
+      character(kind=c_char) :: name_c(*)
+      integer(c_int), value :: ndims
+      integer(c_int) :: dimids(*)
+      type(c_ptr), value :: data_p
+      character(kind=c_char) :: units(*)
+      integer(c_int) :: rc
+    end function rrnn_nc_put_var_float
     function rrnn_multi_create(ndev, devices, out_h) bind(C, name="rrnn_multi_create") result(rc)
       import :: c_int, c_ptr
       integer(c_int), value :: ndev

@@ -340,6 +340,26 @@ RRNN_API int rrnn_sw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_
 RRNN_API int rrnn_ctx_set_chunk_columns(rrnn_ctx_t* ctx, int ncol_chunk);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* netCDF-4 files on either side of the path (no libnetcdf / libhdf5 needed; csrc/nc4_io.cpp, csrc/nc4.hpp): the calls the
+ * reference's drivers make through examples/mo_simple_netcdf.F90 -- read_field :34-96, var_exists :308-318, create_dim :320-343,
+ * create_var :345-380, write_field :167-237 -- and nf90_get_att for the RFMIP `units` scaling factors (examples/rfmip-clear-sky/
+ * mo_rfmip_io.F90:560-600).  A handle is either open for reading (rrnn_nc_open) or a file being built (rrnn_nc_create; written by
+ * rrnn_nc_close).  Arrays are in file order (C order of the netCDF dimensions). */
+typedef struct rrnn_ncfile rrnn_ncfile_t;
+RRNN_API int rrnn_nc_open(const char* path, rrnn_ncfile_t** out);
+RRNN_API int rrnn_nc_create(const char* path, rrnn_ncfile_t** out);
+RRNN_API int rrnn_nc_close(rrnn_ncfile_t* f);
+RRNN_API int rrnn_nc_var_exists(const rrnn_ncfile_t* f, const char* name);   /* 1 / 0 */
+RRNN_API int rrnn_nc_inq_var(const rrnn_ncfile_t* f, const char* name, int* ndims, long long* shape /* [8] */);
+/* any numeric variable, converted to float (real(wp) read_field) */
+RRNN_API int rrnn_nc_get_var_float(const rrnn_ncfile_t* f, const char* name, float* data_out, size_t n);
+RRNN_API int rrnn_nc_get_att_text(const rrnn_ncfile_t* f, const char* var, const char* att, char* buf, int nbuf);
+RRNN_API int rrnn_nc_def_dim(rrnn_ncfile_t* f, const char* name, long long len, int* dimid);
+/* create_var + write_field: a float variable over already-defined dimensions; units may be NULL */
+RRNN_API int rrnn_nc_put_var_float(rrnn_ncfile_t* f, const char* name, int ndims, const int* dimids, const float* data,
+                                   const char* units);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* One process, N devices.  The reference's drivers run their column blocks under an OpenMP parallel-do with firstprivate
  * copies of the k-distribution and the networks (examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:364-368, rrtmgp_rfmip_sw.F90:
  * 352-356); here the "threads" are GPUs: a rrnn_multi_t holds one context per device with the spectral tables and the networks

@@ -121,6 +121,15 @@ _SIGS = {
                                       vp, C.POINTER(rrnn_gas_t), C.c_int, vp, vp]),
     "rrnn_sw_fluxes_host": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                       C.POINTER(rrnn_gas_t), C.c_int, vp, vp, vp]),
+    "rrnn_nc_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "rrnn_nc_create": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "rrnn_nc_close": (C.c_int, [vp]),
+    "rrnn_nc_var_exists": (C.c_int, [vp, C.c_char_p]),
+    "rrnn_nc_inq_var": (C.c_int, [vp, C.c_char_p, c_int_p, C.POINTER(C.c_longlong)]),
+    "rrnn_nc_get_var_float": (C.c_int, [vp, C.c_char_p, c_float_p, C.c_size_t]),
+    "rrnn_nc_get_att_text": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "rrnn_nc_def_dim": (C.c_int, [vp, C.c_char_p, C.c_longlong, c_int_p]),
+    "rrnn_nc_put_var_float": (C.c_int, [vp, C.c_char_p, C.c_int, c_int_p, c_float_p, C.c_char_p]),
     "rrnn_multi_create": (C.c_int, [C.c_int, c_int_p, C.POINTER(vp)]),
     "rrnn_multi_destroy": (C.c_int, [vp]),
     "rrnn_multi_ndev": (C.c_int, [vp]),

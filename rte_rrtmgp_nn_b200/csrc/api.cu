@@ -707,6 +707,7 @@ extern "C" int rrnn_compute_nn_inputs(rrnn_ctx_t* ctx, const rrnn_model_t* m, in
 extern "C" int rrnn_planck_source_nn(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int ncol, int nlay, const float* tlay_d,
                                      const float* tlev_d, const float* tsfc_d, int sfc_lay, float* sfc_source_d,
                                      float* sfc_source_Jac_d, float* pfrac_lay_source_d, float* lev_source_d) {
+  rrnn::NvtxRange nvtx_("compute_Planck_source_nn");
   RRNN_CHECK(ctx && kd && kd->d_totplnk, "compute_Planck_source_nn: null handle or no Planck table");
   RRNN_CHECK(sfc_lay >= 1 && sfc_lay <= nlay, "compute_Planck_source_nn: sfc_lay out of range");
   if (ncol <= 0) return 0;
@@ -794,6 +795,7 @@ extern "C" int rrnn_cloud_lut_destroy(rrnn_cloud_lut_t* l) {
 extern "C" int rrnn_cloud_optics(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, int ncol, int nlay, const float* clwp_d,
                                  const float* ciwp_d, const float* reliq_d, const float* reice_d, float* tau_d, float* ssa_d,
                                  float* g_d) {
+  rrnn::NvtxRange nvtx_("cloud_optics");
   RRNN_CHECK(ctx && lut, "cloud optics: no data has been initialized");
   RRNN_CHECK((ssa_d == nullptr) == (g_d == nullptr), "cloud optics: ssa and g must both be given or both be absent");
   if (ncol <= 0) return 0;
@@ -853,6 +855,7 @@ extern "C" int rrnn_draw_samples(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nl
 }
 
 extern "C" int rrnn_delta_scale_2str(rrnn_ctx_t* ctx, size_t n, float* tau_d, float* ssa_d, float* g_d) {
+  rrnn::NvtxRange nvtx_("clouds_deltascale_increment");
   RRNN_CHECK(ctx, "delta_scale: null context");
   if (n == 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
@@ -862,6 +865,7 @@ extern "C" int rrnn_delta_scale_2str(rrnn_ctx_t* ctx, size_t n, float* tau_d, fl
 }
 
 extern "C" int rrnn_increment_1scl_bybnd(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, float* tau1_d, const float* tau2_d) {
+  rrnn::NvtxRange nvtx_("clouds_increment");
   RRNN_CHECK(ctx && kd, "increment: null handle");
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
@@ -873,6 +877,7 @@ extern "C" int rrnn_increment_1scl_bybnd(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd
 
 extern "C" int rrnn_increment_2str_bybnd(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, float* tau1_d, float* ssa1_d,
                                          float* g1_d, const float* tau2_d, const float* ssa2_d, const float* g2_d) {
+  rrnn::NvtxRange nvtx_("clouds_deltascale_increment");
   RRNN_CHECK(ctx && kd && g1_d, "increment: null handle");
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>   // header-only; resolves the profiler's injection library at run time (no link dependency)
 #include "../../include/rrnn.h"
 
 namespace rrnn {
@@ -32,6 +33,17 @@ int fail(const std::string& msg);
     cudaError_t _e = cudaGetLastError();                                                             \
     if (_e != cudaSuccess) return ::rrnn::fail(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
   } while (0)
+
+// NVTX range carrying the reference's GPTL timer name for the same stretch of work (gptlstart / gptlstop pairs in
+// examples/rfmip-clear-sky/rrtmgp_rfmip_{lw,sw}.F90:360-446, examples/all-sky/rrtmgp_allsky.F90:361-440,
+// rte/kernels/mo_rte_solver_kernels.F90:168-300, 616-640, rrtmgp/kernels/mo_gas_optics_kernels.F90:725): a timeline of this
+// library reads like the reference's GPTL report.  A push / pop costs ~20 ns when no profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* gptl_name) { nvtxRangePushA(gptl_name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 constexpr int MAX_NN_INPUTS = 32;
 constexpr int MAX_LAYERS = 6;

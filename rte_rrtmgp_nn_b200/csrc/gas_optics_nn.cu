@@ -632,6 +632,7 @@ extern "C" int rrnn_gas_optics_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
                                   const float* tsfc_d, const rrnn_gas_t* gases, int ngas, const float* tlev_d,
                                   float* tau_d, float* lay_source_d, float* lev_source_d, float* sfc_source_d,
                                   float* sfc_source_Jac_d) {
+  rrnn::NvtxRange nvtx_("gas_optics (LW)");
   RRNN_CHECK(ctx && kd && models, "gas_optics(): null handle");
   RRNN_CHECK(nmodels == 1 || nmodels == 2, "gas_optics(): neural_nets must hold 1 or 2 networks for the longwave");
   RRNN_CHECK(kd->d_totplnk, "gas_optics(): k-distribution has no Planck table (not a longwave k-distribution)");
@@ -686,6 +687,7 @@ extern "C" int rrnn_gas_optics_lw_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t* k
                                           const float* tsfc_d, const rrnn_gas_t* gases, int ngas, const float* tlev_d,
                                           float* tau_d, float* pfrac_d, float* planck_lay_d, float* planck_lev_d,
                                           float* sfc_source_d, float* sfc_source_Jac_d) {
+  rrnn::NvtxRange nvtx_("gas_optics (LW)");
   RRNN_CHECK(ctx && kd && models, "gas_optics(): null handle");
   RRNN_CHECK(nmodels == 1 || nmodels == 2, "gas_optics(): neural_nets must hold 1 or 2 networks for the longwave");
   RRNN_CHECK(kd->d_totplnk, "gas_optics(): k-distribution has no Planck table (not a longwave k-distribution)");
@@ -710,6 +712,7 @@ extern "C" int rrnn_gas_optics_sw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const
                                   int nlay, const float* play_d, const float* plev_d, const float* tlay_d,
                                   const rrnn_gas_t* gases, int ngas, float* tau_d, float* ssa_d, float* g_d,
                                   float* toa_src_d) {
+  rrnn::NvtxRange nvtx_("gas_optics (SW)");
   RRNN_CHECK(ctx && kd && models && models[0], "gas_optics(): null handle");
   RRNN_CHECK(nlay >= 1 && ncol >= 0, "gas_optics(): bad extents");
   RRNN_CHECK(on_device(models[0]) && (!ssa_d || on_device(models[1])), "gas_optics(): network was loaded without a device context");
@@ -759,6 +762,7 @@ static int sgemm_common(rrnn_ctx_t* ctx, const rrnn_model_t* m, int nbatch, cons
 
 extern "C" int rrnn_output_sgemm_tau(rrnn_ctx_t* ctx, const rrnn_model_t* m, int nbatch, const float* x_d, const float* coldry_d,
                                      float* output_d, float* output2_d) {
+  rrnn::NvtxRange nvtx_("compute_tau");
   GoParams p{};
   if (int rc = sgemm_common(ctx, m, nbatch, x_d, coldry_d, p)) return rc;
   RRNN_CHECK(m->d_ymean && m->d_ystd, "output_sgemm_tau: NN output scaling coefficients missing");
@@ -768,6 +772,7 @@ extern "C" int rrnn_output_sgemm_tau(rrnn_ctx_t* ctx, const rrnn_model_t* m, int
 }
 
 extern "C" int rrnn_output_sgemm_pfrac(rrnn_ctx_t* ctx, const rrnn_model_t* m, int nbatch, const float* x_d, float* output_d) {
+  rrnn::NvtxRange nvtx_("first_sgemm .. last_sgemm");
   GoParams p{};
   if (int rc = sgemm_common(ctx, m, nbatch, x_d, nullptr, p)) return rc;
   if (nbatch == 0) return 0;
@@ -776,6 +781,7 @@ extern "C" int rrnn_output_sgemm_pfrac(rrnn_ctx_t* ctx, const rrnn_model_t* m, i
 }
 
 extern "C" int rrnn_output_sgemm_lw(rrnn_ctx_t* ctx, const rrnn_model_t* m, int nbatch, const float* x_d, float* output_d) {
+  rrnn::NvtxRange nvtx_("first_sgemm .. last_sgemm");
   GoParams p{};
   if (int rc = sgemm_common(ctx, m, nbatch, x_d, nullptr, p)) return rc;
   if (nbatch == 0) return 0;

@@ -15,220 +15,15 @@
 #include <string>
 #include <vector>
 #include "../../include/rrnn.h"
+#include "nc4.hpp"
 
 namespace rrnn {
 int fail(const std::string& msg);
 
 namespace {
 
-struct DsInfo {
-  std::vector<uint64_t> shape;
-  int cls = -1;      // 0 int, 1 float, 3 string
-  uint32_t size = 0;
-  bool big = false;
-  int layout = -1;   // 0 compact, 1 contiguous, 2 chunked
-  uint64_t addr = 0, nbytes = 0;
-  std::vector<uint32_t> chunk;
-  std::vector<uint8_t> compact;
-  bool filtered = false;
-};
-
-class Nc4File {
- public:
-  bool open(const std::string& path, std::string& err) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) { err = "can't find file " + path; return false; }
-    buf_.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-    static const unsigned char magic[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
-    if (buf_.size() < 64 || memcmp(buf_.data(), magic, 8) != 0) { err = path + ": not a netCDF-4/HDF5 file"; return false; }
-    return true;
-  }
-
-  bool has(const std::string& name) const { return find_ohdr(name) != UINT64_MAX; }
-
-  bool info(const std::string& name, DsInfo& d, std::string& err) const {
-    const uint64_t addr = find_ohdr(name);
-    if (addr == UINT64_MAX) { err = "variable " + name + " not found"; return false; }
-    std::vector<std::pair<int, std::pair<uint64_t, uint32_t>>> msgs;
-    if (!messages(addr, msgs, err)) return false;
-    for (auto& m : msgs) {
-      const uint8_t* b = buf_.data() + m.second.first;
-      const uint32_t len = m.second.second;
-      switch (m.first) {
-        case 0x01: {
-          if (len < 4) break;
-          const int ver = b[0], rank = b[1];
-          const int off = (ver == 1) ? 8 : 4;
-          d.shape.clear();
-          for (int k = 0; k < rank; ++k) d.shape.push_back(rd64(b + off + 8 * k));
-          break;
-        }
-        case 0x03:
-          d.cls = b[0] & 0x0F;
-          d.big = (b[1] & 1) != 0;
-          d.size = rd32(b + 4);
-          break;
-        case 0x08: {
-          if (b[0] != 3) { err = name + ": unsupported data layout message version"; return false; }
-          d.layout = b[1];
-          if (d.layout == 1) { d.addr = rd64(b + 2); d.nbytes = rd64(b + 10); }
-          else if (d.layout == 2) {
-            const int nd = b[2];
-            d.addr = rd64(b + 3);
-            d.chunk.clear();
-            for (int k = 0; k < nd; ++k) d.chunk.push_back(rd32(b + 11 + 4 * k));
-          } else if (d.layout == 0) {
-            const uint16_t sz = rd16(b + 2);
-            d.compact.assign(b + 4, b + 4 + sz);
-          }
-          break;
-        }
-        case 0x0B: d.filtered = true; break;
-        default: break;
-      }
-    }
-    if (d.cls < 0 || d.layout < 0) { err = name + ": incomplete object header"; return false; }
-    return true;
-  }
-
-  // read a numeric dataset as float (fp32 / fp64 / int32 / int64 sources)
-  bool read_float(const std::string& name, std::vector<float>& out, std::vector<uint64_t>& shape, std::string& err) const {
-    DsInfo d;
-    std::vector<uint8_t> raw;
-    if (!read_raw(name, d, raw, err)) return false;
-    shape = d.shape;
-    const size_t n = raw.size() / d.size;
-    out.resize(n);
-    for (size_t i = 0; i < n; ++i) {
-      uint8_t tmp[8];
-      memcpy(tmp, raw.data() + i * d.size, d.size);
-      if (d.big) for (uint32_t k = 0; k < d.size / 2; ++k) std::swap(tmp[k], tmp[d.size - 1 - k]);
-      if (d.cls == 1 && d.size == 4) { float v; memcpy(&v, tmp, 4); out[i] = v; }
-      else if (d.cls == 1 && d.size == 8) { double v; memcpy(&v, tmp, 8); out[i] = (float)v; }
-      else if (d.cls == 0 && d.size == 4) { int32_t v; memcpy(&v, tmp, 4); out[i] = (float)v; }
-      else if (d.cls == 0 && d.size == 8) { int64_t v; memcpy(&v, tmp, 8); out[i] = (float)v; }
-      else if (d.cls == 0 && d.size == 2) { int16_t v; memcpy(&v, tmp, 2); out[i] = (float)v; }
-      else { err = name + ": unsupported datatype"; return false; }
-    }
-    return true;
-  }
-
-  // blank-padded character matrix (nrow, width) -> trimmed strings
-  bool read_strings(const std::string& name, std::vector<std::string>& out, std::string& err) const {
-    DsInfo d;
-    std::vector<uint8_t> raw;
-    if (!read_raw(name, d, raw, err)) return false;
-    if (d.cls != 3) { err = name + ": not a character variable"; return false; }
-    size_t nrow = d.shape.empty() ? 1 : d.shape[0];
-    size_t width = raw.size() / (nrow ? nrow : 1);
-    out.clear();
-    for (size_t r = 0; r < nrow; ++r) {
-      std::string s((const char*)raw.data() + r * width, width);
-      size_t z = s.find('\0');
-      if (z != std::string::npos) s.resize(z);
-      while (!s.empty() && s.back() == ' ') s.pop_back();
-      size_t b = 0;
-      while (b < s.size() && s[b] == ' ') ++b;
-      out.push_back(s.substr(b));
-    }
-    return true;
-  }
-
- private:
-  std::vector<uint8_t> buf_;
-
-  static uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
-  static uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
-  static uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
-
-  uint64_t find_ohdr(const std::string& name) const {
-    std::string key;
-    key.push_back((char)name.size());
-    key += name;
-    const size_t n = buf_.size();
-    for (size_t i = 0; i + key.size() + 8 <= n; ++i) {
-      if (memcmp(buf_.data() + i, key.data(), key.size()) != 0) continue;
-      const uint64_t addr = rd64(buf_.data() + i + key.size());
-      if (addr + 6 <= n && memcmp(buf_.data() + addr, "OHDR", 4) == 0 && buf_[addr + 4] == 2) return addr;
-    }
-    return UINT64_MAX;
-  }
-
-  bool messages(uint64_t addr, std::vector<std::pair<int, std::pair<uint64_t, uint32_t>>>& out, std::string& err) const {
-    const uint8_t flags = buf_[addr + 5];
-    uint64_t p = addr + 6;
-    if (flags & 0x20) p += 16;
-    if (flags & 0x10) p += 4;
-    const int w = 1 << (flags & 3);
-    uint64_t size0 = 0;
-    memcpy(&size0, buf_.data() + p, w);
-    p += w;
-    const bool track = (flags & 0x04) != 0;
-    std::vector<std::pair<uint64_t, uint64_t>> blocks{{p, p + size0}};
-    for (size_t bi = 0; bi < blocks.size(); ++bi) {
-      uint64_t q = blocks[bi].first, end = blocks[bi].second;
-      if (end > buf_.size()) { err = "corrupt object header"; return false; }
-      while (q + 4 <= end) {
-        const int mtype = buf_[q];
-        const uint32_t msize = rd16(buf_.data() + q + 1);
-        q += 4;
-        if (track) q += 2;
-        if (q + msize > end) break;
-        if (mtype == 0x10) {
-          const uint64_t off = rd64(buf_.data() + q), ln = rd64(buf_.data() + q + 8);
-          if (off + ln > buf_.size() || memcmp(buf_.data() + off, "OCHK", 4) != 0) { err = "bad continuation block"; return false; }
-          blocks.push_back({off + 4, off + ln - 4});
-        } else {
-          out.push_back({mtype, {q, msize}});
-        }
-        q += msize;
-      }
-    }
-    return true;
-  }
-
-  bool read_raw(const std::string& name, DsInfo& d, std::vector<uint8_t>& raw, std::string& err) const {
-    if (!info(name, d, err)) return false;
-    if (d.filtered) { err = name + ": filtered (compressed) datasets are not supported"; return false; }
-    uint64_t n = 1;
-    for (uint64_t s : d.shape) n *= s;
-    const uint64_t nbytes = n * d.size;
-    if (d.layout == 1) {
-      if (d.addr == UINT64_MAX || d.addr + nbytes > buf_.size()) { err = name + ": no data"; return false; }
-      raw.assign(buf_.begin() + d.addr, buf_.begin() + d.addr + nbytes);
-    } else if (d.layout == 0) {
-      if (d.compact.size() < nbytes) { err = name + ": short compact data"; return false; }
-      raw.assign(d.compact.begin(), d.compact.begin() + nbytes);
-    } else {
-      const size_t nd = d.chunk.size();
-      if (nd != d.shape.size() + 1) { err = name + ": unexpected chunk rank"; return false; }
-      for (size_t k = 0; k + 1 < nd; ++k)
-        if (d.chunk[k] < d.shape[k]) { err = name + ": multi-chunk datasets are not supported"; return false; }
-      const uint64_t bt = d.addr;
-      if (bt + 8 > buf_.size() || memcmp(buf_.data() + bt, "TREE", 4) != 0 || buf_[bt + 4] != 1 || buf_[bt + 5] != 0 ||
-          rd16(buf_.data() + bt + 6) != 1) { err = name + ": unsupported chunk index"; return false; }
-      const uint64_t child = rd64(buf_.data() + bt + 8 + 16 + 8 + 8 * nd);
-      // copy the [0:shape] corner of the single chunk
-      raw.resize(nbytes);
-      std::vector<uint64_t> idx(d.shape.size(), 0);
-      const size_t rank = d.shape.size();
-      const uint64_t row = (rank ? d.shape[rank - 1] : 1) * d.size;
-      uint64_t nrows = 1;
-      for (size_t k = 0; k + 1 < rank; ++k) nrows *= d.shape[k];
-      for (uint64_t r = 0; r < nrows; ++r) {
-        uint64_t src = 0, stride = 1, rem = r;
-        // offset of row r inside the chunk
-        std::vector<uint64_t> id(rank, 0);
-        for (size_t k = rank - 1; k-- > 0;) { id[k] = rem % d.shape[k]; rem /= d.shape[k]; }
-        stride = d.size;
-        for (size_t k = rank; k-- > 0;) { src += id[k] * stride; stride *= d.chunk[k]; }
-        if (child + src + row > buf_.size()) { err = name + ": chunk out of file"; return false; }
-        memcpy(raw.data() + r * row, buf_.data() + child + src, row);
-      }
-    }
-    return true;
-  }
-};
+using nc4::DsInfo;
+using nc4::Nc4File;
 
 int act_code(const std::string& s, bool& known) {
   known = true;
@@ -292,8 +87,10 @@ extern "C" int rrnn_model_load_netcdf(rrnn_ctx_t* ctx, const char* filename, rrn
   std::vector<char> nm((size_t)nx * 32, ' ');
   for (int i = 0; i < nx; ++i) memcpy(nm.data() + 32 * i, names[i].data(), std::min<size_t>(names[i].size(), 32));
   std::vector<float> ymean, ystd;
-  const bool hm = f.has("nn_output_coeffs_mean") && f.read_float("nn_output_coeffs_mean", ymean, shp, err);
-  const bool hs = f.has("nn_output_coeffs_std") && f.read_float("nn_output_coeffs_std", ystd, shp, err);
+  // absent is fine (models without output scaling); present but unreadable is an error of its own, not "missing"
+  const bool hm = f.has("nn_output_coeffs_mean"), hs = f.has("nn_output_coeffs_std");
+  if (hm && !f.read_float("nn_output_coeffs_mean", ymean, shp, err)) return fail("mod_network_rrtmgp:load_netcdf: " + err);
+  if (hs && !f.read_float("nn_output_coeffs_std", ystd, shp, err)) return fail("mod_network_rrtmgp:load_netcdf: " + err);
   if (hm && (int)ymean.size() != dims[nlayers]) return fail("load_netcdf: output mean has unexpected length");
   if (hs && (int)ystd.size() != dims[nlayers]) return fail("load_netcdf: output std has unexpected length");
   return rrnn_model_create(ctx, nlayers, dims.data(), wpack.data(), bpack.data(), act.data(), xmin.data(), xmax.data(),

@@ -131,6 +131,7 @@ static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
     float* egpt = sjac + align256((size_t)nc * G);
     if (int rc = rrnn_gas_optics_lw_compact(ctx, kd, models, nmodels, nc, L, play, plev, tlay, tsfc, gases, ngas, tlev, tau, lay, bl, bv, ssrc, sjac))
       return rc;
+    NvtxRange nvtx_rte("rte_lw");
     bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
     RRNN_LAUNCH_CHECK(ctx);
     return rrnn_lw_solver_noscat_compact(ctx, kd, L, nc, top_at_1, nang, gauss_Ds[nang - 1], gauss_wts[nang - 1], tau, lay, bl, bv, egpt,
@@ -142,6 +143,7 @@ static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
   float* egpt = sjac + align256((size_t)nc * G);
   if (int rc = rrnn_gas_optics_lw(ctx, kd, models, nmodels, nc, L, play, plev, tlay, tsfc, gases, ngas, tlev, tau, lay, lev, ssrc, sjac))
     return rc;
+  NvtxRange nvtx_rte("rte_lw");
   bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
   RRNN_LAUNCH_CHECK(ctx);
   return rrnn_lw_solver_noscat(ctx, G, L, nc, top_at_1, nang, gauss_Ds[nang - 1], gauss_wts[nang - 1], nullptr, tau, lay, lev,
@@ -162,6 +164,7 @@ static int sw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
   float def_tsi = 0.0f;
   for (float v : kd->solar_source) def_tsi += v;  // :409-416, same for every column
   const size_t n = (size_t)G * nc;
+  NvtxRange nvtx_rte("rte_sw");
   sw_bc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, kd->d_solar_source, def_tsi, tsi, alb, mu0, toa, agpt, mu0e);
   RRNN_LAUNCH_CHECK(ctx);
   if (int rc = rrnn_sw_solver_2stream(ctx, G, L, nc, top_at_1, toa, nullptr, tau, ssa, nullptr, mu0e, agpt, agpt, fup, fdn, fdir)) return rc;
@@ -179,6 +182,7 @@ extern "C" int rrnn_lw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrn
                               int ncol, int nlay, int top_at_1, int n_gauss_angles, const float* play_d, const float* plev_d,
                               const float* tlay_d, const float* tlev_d, const float* tsfc_d, const float* sfc_emis_d,
                               const rrnn_gas_t* gases, int ngas, float* flux_up_d, float* flux_dn_d) {
+  rrnn::NvtxRange nvtx_("clear_sky_total (LW)");
   RRNN_CHECK(ctx && kd && models, "rrnn_lw_fluxes: null handle");
   RRNN_CHECK(n_gauss_angles >= 1 && n_gauss_angles <= 4, "rte_lw: n_gauss_angles must be in 1..4");
   if (ncol <= 0) return 0;
@@ -204,6 +208,7 @@ extern "C" int rrnn_sw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrn
                               int top_at_1, const float* play_d, const float* plev_d, const float* tlay_d, const float* mu0_d,
                               const float* sfc_alb_d, const float* tsi_d, const rrnn_gas_t* gases, int ngas,
                               float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d) {
+  rrnn::NvtxRange nvtx_("clear_sky_total (SW)");
   RRNN_CHECK(ctx && kd && models, "rrnn_sw_fluxes: null handle");
   RRNN_CHECK(kd->d_solar_source, "rrnn_sw_fluxes: k-distribution has no solar source");
   if (ncol <= 0) return 0;
@@ -411,6 +416,7 @@ extern "C" int rrnn_lw_fluxes_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, cons
                                    int ncol, int nlay, int top_at_1, int n_gauss_angles, const float* play, const float* plev,
                                    const float* tlay, const float* tlev, const float* tsfc, const float* sfc_emis,
                                    const rrnn_gas_t* gases, int ngas, float* flux_up, float* flux_dn) {
+  rrnn::NvtxRange nvtx_("clear_sky_total (LW)");
   RRNN_CHECK(ctx && kd && models && play && plev && tlay && tsfc && sfc_emis && flux_up && flux_dn, "rrnn_lw_fluxes_host: null argument");
   RRNN_CHECK(n_gauss_angles >= 1 && n_gauss_angles <= 4, "rte_lw: n_gauss_angles must be in 1..4");
   if (ncol <= 0) return 0;
@@ -425,6 +431,7 @@ extern "C" int rrnn_sw_fluxes_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, cons
                                    int nlay, int top_at_1, const float* play, const float* plev, const float* tlay,
                                    const float* mu0, const float* sfc_alb, const float* tsi, const rrnn_gas_t* gases,
                                    int ngas, float* flux_up, float* flux_dn, float* flux_dn_dir) {
+  rrnn::NvtxRange nvtx_("clear_sky_total (SW)");
   RRNN_CHECK(ctx && kd && models && play && plev && tlay && mu0 && sfc_alb && flux_up && flux_dn && flux_dn_dir, "rrnn_sw_fluxes_host: null argument");
   RRNN_CHECK(kd->d_solar_source, "rrnn_sw_fluxes_host: k-distribution has no solar source");
   if (ncol <= 0) return 0;

@@ -304,6 +304,7 @@ extern "C" int rrnn_lw_solver_noscat_ext(rrnn_ctx_t* ctx, int ngpt, int nlay, in
                                          const float* sfc_emis_gpt_d, const float* sfc_source_d, const float* sfc_source_Jac_d,
                                          float* flux_up_d, float* flux_dn_d, float* flux_up_Jac_d, float* gpt_flux_up_d,
                                          float* gpt_flux_dn_d) {
+  rrnn::NvtxRange nvtx_("lw_solver_noscat");
   RRNN_CHECK(ctx, "rrnn_lw_solver_noscat_ext: null context");
   RRNN_CHECK(ngpt > 0 && nlay > 0 && ncol >= 0, "rrnn_lw_solver_noscat_ext: bad extents");
   RRNN_CHECK(nmus >= 1 && nmus <= 4, "rte_lw: have to ask for between 1 and 4 quadrature points for no-scattering calculation");
@@ -343,6 +344,7 @@ extern "C" int rrnn_rte_lw_ext(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay
                                const float* lay_source_d, const float* lev_source_d, const float* sfc_source_d,
                                const float* sfc_emis_d, const float* lw_Ds_d, const float* sfc_source_Jac_d, float* flux_up_d,
                                float* flux_dn_d, float* flux_up_Jac_d, float* gpt_flux_up_d, float* gpt_flux_dn_d) {
+  rrnn::NvtxRange nvtx_("rte_lw");
   RRNN_CHECK(ctx && kd, "rte_lw: null handle");
   static const float gauss_Ds[4][4] = {{1.66f, 0.f, 0.f, 0.f},  // rte/mo_rte_lw.F90:113-125
                                        {1.18350343f, 2.81649655f, 0.f, 0.f},
@@ -377,6 +379,7 @@ extern "C" int rrnn_lw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
                                       const float* tau_d, const float* ssa_d, const float* g_d, const float* lev_source_d,
                                       const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d, float* flux_dn_d,
                                       float* gpt_flux_up_d, float* gpt_flux_dn_d) {
+  rrnn::NvtxRange nvtx_("lw_solver_2stream");
   RRNN_CHECK(ctx, "rrnn_lw_solver_2stream: null context");
   RRNN_CHECK(ngpt > 0 && nlay > 0 && ncol >= 0, "rrnn_lw_solver_2stream: bad extents");
   RRNN_CHECK(tau_d && ssa_d && g_d && lev_source_d && sfc_emis_gpt_d && sfc_source_d && flux_up_d && flux_dn_d,
@@ -407,6 +410,7 @@ extern "C" int rrnn_rte_lw_2stream(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int 
                                    const float* tau_d, const float* ssa_d, const float* g_d, const float* lev_source_d,
                                    const float* sfc_source_d, const float* sfc_emis_d, float* flux_up_d, float* flux_dn_d,
                                    float* gpt_flux_up_d, float* gpt_flux_dn_d) {
+  rrnn::NvtxRange nvtx_("rte_lw");
   RRNN_CHECK(ctx && kd, "rte_lw: null handle");
   RRNN_CHECK(flux_up_d && flux_dn_d, "rte_lw: no space allocated for fluxes");
   if (ncol == 0) return 0;

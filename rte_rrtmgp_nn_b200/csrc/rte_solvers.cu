@@ -417,6 +417,7 @@ extern "C" int rrnn_lw_solver_noscat(rrnn_ctx_t* ctx, int ngpt, int nlay, int nc
                                      const float* weights, const float* inc_flux_d, const float* tau_d,
                                      const float* lay_source_d, const float* lev_source_d, const float* sfc_emis_gpt_d,
                                      const float* sfc_source_d, float* flux_up_d, float* flux_dn_d) {
+  rrnn::NvtxRange nvtx_("lw_solver_noscat");
   RRNN_CHECK(ctx, "rrnn_lw_solver_noscat: null context");
   RRNN_CHECK(ngpt > 0 && nlay > 0 && ncol >= 0, "rrnn_lw_solver_noscat: bad extents");
   RRNN_CHECK(nmus >= 1 && nmus <= 4, "rte_lw: have to ask for between 1 and 4 quadrature points for no-scattering calculation");
@@ -505,6 +506,7 @@ extern "C" int rrnn_lw_solver_noscat_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t
                                              const float* Ds, const float* weights, const float* tau_d, const float* pfrac_d,
                                              const float* planck_lay_d, const float* planck_lev_d, const float* sfc_emis_gpt_d,
                                              const float* sfc_source_d, float* flux_up_d, float* flux_dn_d) {
+  rrnn::NvtxRange nvtx_("lw_solver_noscat");
   RRNN_CHECK(ctx && kd, "rrnn_lw_solver_noscat_compact: null handle");
   RRNN_CHECK(nlay > 0 && ncol >= 0, "rrnn_lw_solver_noscat_compact: bad extents");
   RRNN_CHECK(nmus >= 1 && nmus <= 4, "rte_lw: have to ask for between 1 and 4 quadrature points for no-scattering calculation");
@@ -518,6 +520,7 @@ extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int n
                                       const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
                                       const float* mu0_d, const float* sfc_alb_dir_d, const float* sfc_alb_dif_d,
                                       float* flux_up_d, float* flux_dn_d, float* flux_dir_d) {
+  rrnn::NvtxRange nvtx_("sw_two_stream_source + adding");
   RRNN_CHECK(ctx, "rrnn_sw_solver_2stream: null context");
   RRNN_CHECK(ngpt > 0 && nlay > 0 && ncol >= 0, "rrnn_sw_solver_2stream: bad extents");
   if (ncol == 0) return 0;
@@ -583,6 +586,7 @@ extern "C" int rrnn_rte_lw(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, in
                            const float* inc_flux_d, const float* tau_d, const float* lay_source_d,
                            const float* lev_source_d, const float* sfc_source_d, const float* sfc_emis_d,
                            float* flux_up_d, float* flux_dn_d) {
+  rrnn::NvtxRange nvtx_("rte_lw");
   RRNN_CHECK(ctx && kd, "rte_lw: null handle");
   // rte/mo_rte_lw.F90:113-125
   static const float gauss_Ds[4][4] = {{1.66f, 0.f, 0.f, 0.f},
@@ -616,6 +620,7 @@ extern "C" int rrnn_rte_sw(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int to
                            const float* inc_flux_d, const float* sfc_alb_dir_gpt_d, const float* sfc_alb_dif_gpt_d,
                            const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
                            float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d) {
+  rrnn::NvtxRange nvtx_("rte_sw");
   RRNN_CHECK(flux_up_d && flux_dn_d && flux_dn_dir_d, "rte_sw: no space allocated for fluxes");
   return rrnn_sw_solver_2stream(ctx, ngpt, nlay, ncol, top_at_1, inc_flux_d, inc_flux_dif_d, tau_d, ssa_d, g_d, mu0_d,
                                 sfc_alb_dir_gpt_d, sfc_alb_dif_gpt_d, flux_up_d, flux_dn_d, flux_dn_dir_d);

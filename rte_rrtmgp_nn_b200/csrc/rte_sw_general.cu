@@ -163,6 +163,7 @@ extern "C" int rrnn_sw_solver_2stream_ext(rrnn_ctx_t* ctx, int ngpt, int nlay, i
                                           const float* mu0_d, const float* sfc_alb_dir_d, const float* sfc_alb_dif_d, float* flux_up_d,
                                           float* flux_dn_d, float* flux_dir_d, float* gpt_flux_up_d, float* gpt_flux_dn_d,
                                           float* gpt_flux_dir_d) {
+  rrnn::NvtxRange nvtx_("sw_two_stream_source + adding");
   RRNN_CHECK(ctx, "rrnn_sw_solver_2stream_ext: null context");
   RRNN_CHECK(ngpt > 0 && nlay > 0 && ncol >= 0, "rrnn_sw_solver_2stream_ext: bad extents");
   RRNN_CHECK(inc_flux_d && tau_d && ssa_d && mu0_d && sfc_alb_dir_d && sfc_alb_dif_d && flux_up_d && flux_dn_d && flux_dir_d,

@@ -4,7 +4,7 @@ either side of the hot path.
   rrtmgp_rfmip_lw / rrtmgp_rfmip_sw   examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90, rrtmgp_rfmip_sw.F90: 100 sites x 18
                                       experiments in blocks of `block_size` columns, gas optics (NN) + rte, fluxes unblocked
                                       to (expt, site, level) and written as rlu/rld (rsu/rsd) like unblock_and_write
-                                      (mo_rfmip_io.F90:700-760) -- as classic netCDF (scipy), not netCDF-4.
+                                      (mo_rfmip_io.F90:734-870) -- netCDF-4, by the library's own writer (rfmip_io, ncio).
   rrtmgp_allsky                       examples/all-sky/rrtmgp_allsky.F90:150-446: Garand atmosphere 1 replicated ncol times,
                                       the cloud recipe of :333-350, LUT or Pade cloud optics, (delta-scaling,) increment, rte;
                                       write_lw_fluxes / write_sw_fluxes (mo_garand_atmos_io.F90:92-170).
@@ -15,12 +15,13 @@ import os
 
 import numpy as np
 
-from . import api, rfmip, spectral
+from . import api, rfmip, rfmip_io, spectral
+from .ncio import NcFile
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 NN_DIR = os.path.join(ROOT, "data", "nn")
-GARAND = os.path.join(ROOT, "tests", "golden", "garand_atmos.npz")
+GARAND = os.path.join(ROOT, "data", "garand", "garand-atmos-1.nc")
 LW_NETS = ("lw-g256-2018-12-04_absorption_58_58.nc", "lw-g256-2018-12-04_planck_frac_16_16.nc")
 SW_NETS = ("sw-g224-2018-12-04-absorption_16_16.nc", "sw-g224-2018-12-04-rayleigh_16_16.nc")
 
@@ -36,29 +37,34 @@ def _nets(ctx, files):
 
 
 def write_rfmip_fluxes(path, names, fluxes, nexp, nsite):
-    """unblock_and_write (mo_rfmip_io.F90:700-760): (ncol, nlev) column-blocked fluxes -> variables `names` with
-    dimensions (expt, site, level)."""
-    from scipy.io import netcdf_file
-    nlev = fluxes[0].shape[1]
-    f = netcdf_file(path, "w")
-    f.createDimension("expt", nexp); f.createDimension("site", nsite); f.createDimension("level", nlev)
-    for name, a in zip(names, fluxes):
-        v = f.createVariable(name, "f4", ("expt", "site", "level"))
-        v[:] = np.asarray(a, np.float32).reshape(nexp, nsite, nlev)
-        v.units = "W m-2"
-    f.close()
+    """unblock_and_write (mo_rfmip_io.F90:734-870): (ncol, nlev) column-blocked fluxes -> variables `names` with
+    dimensions (expt, site, level), netCDF-4."""
+    rfmip_io.unblock_and_write(path, names, fluxes, nexp, nsite)
 
 
 def write_allsky_fluxes(path, names, fluxes):
-    """write_lw_fluxes / write_sw_fluxes (mo_garand_atmos_io.F90:92-170): variables (lev, col)."""
-    from scipy.io import netcdf_file
+    """write_lw_fluxes / write_sw_fluxes (mo_garand_atmos_io.F90:92-170): variables (lev, col), netCDF-4 (a new file; the
+    reference adds them to its input file)."""
     ncol, nlev = fluxes[0].shape
-    f = netcdf_file(path, "w")
-    f.createDimension("col", ncol); f.createDimension("lev", nlev)
-    for name, a in zip(names, fluxes):
-        v = f.createVariable(name, "f4", ("lev", "col"))
-        v[:] = np.asarray(a, np.float32).T
-    f.close()
+    with NcFile(path, "w") as f:
+        f.create_dim("col", ncol); f.create_dim("lev", nlev)
+        for name, a in zip(names, fluxes):
+            f.write_field(name, ("lev", "col"), np.asarray(a, np.float32).T)
+
+
+def read_atmos(path=GARAND):
+    """read_atmos (mo_garand_atmos_io.F90:41-88): the file's variables are (lay|lev, col); returned as (col, lay|lev), this
+    package's layout."""
+    out = {}
+    with NcFile(path) as f:
+        rd = lambda k: np.ascontiguousarray(f.read_field(k).T)
+        for k in ("p_lay", "t_lay", "p_lev", "t_lev"):
+            out[k] = rd(k)
+        for g in ("h2o", "co2", "o3", "n2o", "co", "ch4", "o2", "n2"):
+            out["vmr_" + g] = rd("vmr_" + g)
+        if f.var_exists("col_dry"):
+            out["col_dry"] = rd("col_dry")
+    return out
 
 
 def rrtmgp_rfmip_lw(ctx=None, block_size=8, out_path=None, n_quad_angles=1, columns=None):
@@ -107,7 +113,7 @@ def rrtmgp_rfmip_sw(ctx=None, block_size=8, out_path=None, columns=None):
 
 def garand_atmosphere(ncol):
     """read_atmos + `p_lay = spread(p_lay(:,1), ...)` (rrtmgp_allsky.F90:172-195): profile 1 replicated ncol times."""
-    z = np.load(GARAND)
+    z = read_atmos()
     rep = lambda a: np.ascontiguousarray(np.repeat(a[:1], ncol, axis=0))
     atm = dict(play=rep(z["p_lay"]), plev=rep(z["p_lev"]), tlay=rep(z["t_lay"]), tlev=rep(z["t_lev"]))
     atm["gases"] = {g: rep(z["vmr_" + g]) for g in ("h2o", "co2", "o3", "n2o", "co", "ch4", "o2", "n2")}

@@ -882,8 +882,8 @@ def test_driver_replicas(gpu_ctx, tmp_path):
     oracle on real RFMIP profiles; the all-sky driver on the Garand atmosphere matches the oracle chain (LUT and Pade);
     the flux files have the drivers' structure."""
     import oracle as O
-    from scipy.io import netcdf_file
     from rte_rrtmgp_nn_b200 import drivers, rfmip, spectral
+    from rte_rrtmgp_nn_b200.ncio import NcFile
     cols = np.r_[0:20, 900:912, 1795:1800]   # 37 columns from three experiments: ragged last block
     up8, dn8 = drivers.rrtmgp_rfmip_lw(gpu_ctx, block_size=8, columns=cols)
     up37, dn37 = drivers.rrtmgp_rfmip_lw(gpu_ctx, block_size=64, columns=cols)
@@ -901,9 +901,9 @@ def test_driver_replicas(gpu_ctx, tmp_path):
     # files: (expt, site, level) and (lev, col)
     p = str(tmp_path / "rlu.nc")
     drivers.write_rfmip_fluxes(p, ("rlu", "rld"), (np.tile(up8[:1], (200, 1)), np.tile(dn8[:1], (200, 1))), 2, 100)
-    f = netcdf_file(p, "r", mmap=False)
-    assert f.variables["rlu"].shape == (2, 100, 61) and f.variables["rlu"].dimensions == ("expt", "site", "level")
-    assert np.array_equal(f.variables["rld"][1, 99], dn8[0]); f.close()
+    with NcFile(p) as f:   # netCDF-4, written and read back by the library's own writer / reader
+        assert f.shape("rlu") == (2, 100, 61) and (f.shape("expt"), f.shape("site"), f.shape("level")) == ((2,), (100,), (61,))
+        assert np.array_equal(f.read_field("rld")[1, 99], dn8[0]) and f.get_att("rlu", "units") == "W m-2"
     # all-sky on the Garand atmosphere (bottom-up, 42 layers): against the oracle chain
     for band, pade in (("lw", False), ("sw", False), ("sw", True)):
         ncol = 12
@@ -937,8 +937,8 @@ def test_driver_replicas(gpu_ctx, tmp_path):
             w32, w64 = chain(False), chain("f64")
             for got, x, y, nm in zip(out, w32, w64, ("up", "dn", "dir")):
                 H.assert_within_reference_noise(got, x, y, H.FLUX_TOL, f"all-sky driver SW flux_{nm} (pade={pade})")
-        f = netcdf_file(str(tmp_path / f"allsky_{band}.nc"), "r", mmap=False)
-        assert f.variables[f"{band}_flux_up"].shape == (43, ncol) and np.array_equal(f.variables[f"{band}_flux_up"][:].T, out[0]); f.close()
+        with NcFile(str(tmp_path / f"allsky_{band}.nc")) as f:
+            assert f.shape(f"{band}_flux_up") == (43, ncol) and np.array_equal(f.read_field(f"{band}_flux_up").T, out[0])
 
 
 def test_byband_and_net_fluxes_match_oracle(gpu_ctx):
@@ -1235,3 +1235,58 @@ def test_multi_device_driver_matches_single_context(gpu_ctx):
         md.close()
     with pytest.raises(Exception):
         api.MultiDevice(devices=[nd + 7])
+
+
+@pytest.mark.parametrize("sw_fast_math", [1, 0], ids=["raw_mufu", "newton_refined"])
+def test_sw_flux_error_distribution_2048_columns(gpu_ctx, sw_fast_math):
+    """the noise-aware SW statement with tight factors on a sample large enough to populate the tails
+    (2048 columns x 60 layers x 61 levels = 125 k flux values per direction), for BOTH arithmetic variants of the SW solver
+    (sw_fast_math = 1: MUFU results as they come, the default; 0: Newton-refined rcp / sqrt / exp).  All three evaluations
+    (CUDA, strict fp32 oracle, fp64 oracle) get the SAME fp32 tau / ssa (from the CUDA gas optics), so this isolates the
+    solver: max <= 1.5 x, rms <= 1.25 x, 99th percentile <= 1.1 x the reference arithmetic's own distance from fp64."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api
+    torch = _torch()
+    ncol, nlay, ngpt = 2048, 60, 224
+    kd, atm, k_dist, onets, dnets = _sw_setup(gpu_ctx, H.SW_G224, ngpt, ncol, nlay, seed=77)
+    op = api.ty_optical_props_2str(); assert op.alloc_2str(ncol, nlay, k_dist) == ""
+    toa = torch.empty((ncol, ngpt), device="cuda")
+    assert k_dist.gas_optics(atm["play"], atm["plev"], atm["tlay"], H.gas_concs(atm["gases"]), op, toa, neural_nets=dnets) == ""
+    tau, ssa, toa_h = op.tau.cpu().numpy(), op.ssa.cpu().numpy(), toa.cpu().numpy()
+    alb = np.repeat(atm["sfc_alb"][:, None], ngpt, 1)
+    g0 = np.zeros_like(tau)
+    r32 = O.rte_sw(atm["top_at_1"], atm["mu0"], toa_h, alb, alb, tau, ssa, g0)
+    r64 = O.rte_sw(atm["top_at_1"], atm["mu0"], toa_h, alb, alb, tau, ssa, g0, fast="f64")
+    mk = lambda: torch.empty((ncol, nlay + 1), device="cuda")
+    fl = api.ty_fluxes_broadband(mk(), mk(), None, mk())
+    gpu_ctx.set_flag("sw_fast_math", sw_fast_math)
+    try:
+        assert api.rte_sw(op, atm["top_at_1"], atm["mu0"], toa, alb, alb, fl) == ""
+    finally:
+        gpu_ctx.set_flag("sw_fast_math", 1)
+    for got, w32, w64, nm in ((fl.flux_up, r32[0], r64[0], "up"), (fl.flux_dn, r32[1], r64[1], "dn"), (fl.flux_dn_dir, r32[2], r64[2], "dir")):
+        H.assert_sw_error_distribution(got.cpu().numpy(), w32, w64, H.FLUX_TOL, f"SW flux_{nm} (sw_fast_math={sw_fast_math})")
+
+
+def test_rfmip_sw_real_profiles_match_oracle(gpu_ctx):
+    """RFMIP SW on the REAL profiles (all 1800 columns: 100 sites x 18 experiments, driver conditioning,
+    TSI renormalisation, night columns) against the oracle chain -- not only block independence and night zeros."""
+    import bench
+    from rte_rrtmgp_nn_b200 import drivers, rfmip
+    su, sd = drivers.rrtmgp_rfmip_sw(gpu_ctx, block_size=1800)
+    atm = rfmip.load()
+    atm["mu0_driver"] = np.where(atm["usecol"], atm["mu0"], -1.0).astype(np.float32)
+    idx = np.arange(0, 1800, 3)     # every third column: all 18 experiments, 600 columns
+    cfg = dict(lw=False, sw=True)
+    w32 = bench.oracle_fluxes(cfg, "g256", atm, idx)
+    assert (su[~atm["usecol"]] == 0).all() and (sd[~atm["usecol"]] == 0).all()
+    day = atm["usecol"][idx]
+    assert day.sum() > 250
+    dup, ddn = np.abs(su[idx] - w32["sw_up"]), np.abs(sd[idx] - w32["sw_dn"])
+    print(f"RFMIP SW vs oracle32: flux_up max {dup.max():.3e} rms {np.sqrt((dup ** 2).mean()):.3e}, flux_dn max {ddn.max():.3e} "
+          f"rms {np.sqrt((ddn ** 2).mean()):.3e}; fraction of values within 0.01: {(dup <= 0.01).mean():.4f} / {(ddn <= 0.01).mean():.4f}")
+    # two fp32 evaluations of the PIFM formulas: each is up to ~0.04 W m-2 from fp64 at these fluxes (helpers.assert_within_reference_noise);
+    # the bulk must meet north_star's 0.01 outright
+    assert np.percentile(dup, 95) <= H.FLUX_TOL and np.percentile(ddn, 95) <= H.FLUX_TOL
+    assert dup.max() <= 0.08 and ddn.max() <= 0.08
+    assert np.sqrt((dup ** 2).mean()) <= 0.005 and np.sqrt((ddn ** 2).mean()) <= 0.005
