@@ -447,56 +447,29 @@ def run_b200(args):
         ev_g1 = [torch.cuda.Event(enable_timing=True) for _ in bounds]
         ev_cmp_end = torch.cuda.Event(enable_timing=True)
 
-        # ---- all-sky (configs[2]): the body of examples/all-sky/rrtmgp_allsky.F90:366-446 per column chunk, on device tensors
+        # ---- all-sky (configs[2]): examples/all-sky/rrtmgp_allsky.F90:366-446 for all columns -- cloud optics (LUT) by band,
+        # gas optics, delta-scaling, increment, rte -- through the fused drivers (rrnn_{lw,sw}_fluxes_allsky[_host]): the cloud
+        # increment happens inside the solvers
         allsky = None
         if cloudy:
-            chunk = min(ncol, 16384)
-
             def lut(band):
                 return api.load_cloud_lut_file(os.path.join(ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc"))
             co_lw = api.ty_cloud_optics(ctx); assert co_lw.load(**lut("lw")) == ""
             co_sw = api.ty_cloud_optics(ctx); assert co_sw.load(**lut("sw")) == ""
-            A = dict(chunk=chunk, co_lw=co_lw, co_sw=co_sw)
-            with torch.cuda.stream(stream):
-                A["atm_lw"] = api.ty_optical_props_1scl(); assert A["atm_lw"].alloc_1scl(chunk, nlay, k_lw) == ""
-                A["cld_lw"] = api.ty_optical_props_1scl(); assert A["cld_lw"].alloc_1scl(chunk, nlay, k_lw, by_band=True) == ""
-                A["src"] = api.ty_source_func_lw(); assert A["src"].alloc(chunk, nlay, k_lw) == ""
-                A["atm_sw"] = api.ty_optical_props_2str(); assert A["atm_sw"].alloc_2str(chunk, nlay, k_sw) == ""
-                A["cld_sw"] = api.ty_optical_props_2str(); assert A["cld_sw"].alloc_2str(chunk, nlay, k_sw, by_band=True) == ""
-                A["toa"] = torch.empty((chunk, m["ngpt_sw"]), device=dev)
-                A["emis"] = d["sfc_emis"][:, None].expand(ncol, k_lw.nband).contiguous()
-                A["alb"] = d["sfc_alb"][:, None].expand(ncol, m["ngpt_sw"]).contiguous()
-            stream.synchronize()
-            allsky = A
+            allsky = dict(co_lw=co_lw, co_sw=co_sw)
 
         def ok(msg):
             if msg != "":
                 raise RuntimeError(msg)
 
         def allsky_pass(src_in, gases, cl, out):
-            """One pass over the shard in chunks; src_in / cl: device tensors of the whole shard."""
+            """One pass over the shard; src_in / cl: device tensors of the whole shard."""
             A = allsky
-            ch = A["chunk"]
             with torch.cuda.stream(stream):
-                for a in range(0, ncol, ch):
-                    b = min(a + ch, ncol)
-                    if b - a != ch:   # the carriers are sized for a full chunk: a ragged tail recomputes the last full window
-                        a = b - ch
-                    s = slice(a, b)
-                    gc = api.ty_gas_concs()
-                    for k, v in atm["gases"].items():
-                        gc.set_vmr(k, gases.get_vmr(k)[s] if np.ndim(v) == 2 else float(v))
-                    ok(A["co_lw"].cloud_optics(cl["lwp"][s], cl["iwp"][s], cl["rel"][s], cl["rei"][s], A["cld_lw"]))
-                    ok(k_lw.gas_optics(src_in["play"][s], src_in["plev"][s], src_in["tlay"][s], src_in["tsfc"][s], gc, A["atm_lw"], A["src"],
-                                       tlev=src_in["tlev"][s], neural_nets=nets_lw))
-                    ok(A["cld_lw"].increment(A["atm_lw"]))
-                    ok(api.rte_lw(A["atm_lw"], top, A["src"], A["emis"][s], api.ty_fluxes_broadband(out["lw_up"][s], out["lw_dn"][s])))
-                    ok(A["co_sw"].cloud_optics(cl["lwp"][s], cl["iwp"][s], cl["rel"][s], cl["rei"][s], A["cld_sw"]))
-                    ok(k_sw.gas_optics(src_in["play"][s], src_in["plev"][s], src_in["tlay"][s], gc, A["atm_sw"], A["toa"], neural_nets=nets_sw))
-                    ok(A["cld_sw"].delta_scale())
-                    ok(A["cld_sw"].increment(A["atm_sw"]))
-                    ok(api.rte_sw(A["atm_sw"], top, src_in["mu0"][s], A["toa"], A["alb"][s], A["alb"][s],
-                                  api.ty_fluxes_broadband(out["sw_up"][s], out["sw_dn"][s], None, out["sw_dir"][s])))
+                api.lw_fluxes_allsky(k_lw, nets_lw, A["co_lw"], src_in["play"], src_in["plev"], src_in["tlay"], src_in["tsfc"], src_in["sfc_emis"],
+                                     gases, cl, out["lw_up"], out["lw_dn"], tlev=src_in["tlev"], top_at_1=top)
+                api.sw_fluxes_allsky(k_sw, nets_sw, A["co_sw"], src_in["play"], src_in["plev"], src_in["tlay"], src_in["mu0"], src_in["sfc_alb"],
+                                     gases, cl, out["sw_up"], out["sw_dn"], out["sw_dir"], top_at_1=top)
 
         def step_device():
             if cloudy:
@@ -531,20 +504,13 @@ def run_b200(args):
 
         def step_host(src, gases, out):
             if cloudy:
-                # no host-buffer entry point takes clouds: H2D of the step's inputs from the caller's buffers, the device pass,
-                # D2H of the fluxes -- all inside the timed region
-                with torch.cuda.stream(stream):
-                    dd = {k: torch.from_numpy(as_np(src[k])).to(dev, non_blocking=True) for k in in_keys}
-                    gd = api.ty_gas_concs()
-                    for k, v in atm["gases"].items():
-                        gd.set_vmr(k, torch.from_numpy(np.asarray(gases.get_vmr(k))).to(dev, non_blocking=True) if np.ndim(v) == 2 else float(v))
-                    cd = {k: torch.from_numpy(v).to(dev, non_blocking=True) for k, v in clouds.items()}
-                    tmp = {nm: torch.empty((ncol, nlev), dtype=torch.float32, device=dev) for nm in names}
-                allsky_pass(dd, gd, cd, tmp)
-                with torch.cuda.stream(stream):
-                    for nm in names:
-                        torch.from_numpy(as_np(out[nm])).copy_(tmp[nm], non_blocking=True)
-                stream.synchronize()
+                A = allsky
+                api.lw_fluxes_allsky_host(k_lw, nets_lw, A["co_lw"], as_np(src["play"]), as_np(src["plev"]), as_np(src["tlay"]), as_np(src["tsfc"]),
+                                          as_np(src["sfc_emis"]), gases, clouds, tlev=as_np(src["tlev"]), top_at_1=top,
+                                          flux_up=as_np(out["lw_up"]), flux_dn=as_np(out["lw_dn"]))
+                api.sw_fluxes_allsky_host(k_sw, nets_sw, A["co_sw"], as_np(src["play"]), as_np(src["plev"]), as_np(src["tlay"]), as_np(src["mu0"]),
+                                          as_np(src["sfc_alb"]), gases, clouds, top_at_1=top, flux_up=as_np(out["sw_up"]),
+                                          flux_dn=as_np(out["sw_dn"]), flux_dn_dir=as_np(out["sw_dir"]))
                 return
             if do_lw:
                 api.lw_fluxes_host(k_lw, nets_lw, as_np(src["play"]), as_np(src["plev"]), as_np(src["tlay"]), as_np(src["tsfc"]),
@@ -620,13 +586,11 @@ def run_b200(args):
             per = lambda k: int(np.prod(atm[k].shape[1:]))
             gas2d_n = sum(int(np.prod(v.shape[1:])) for v in atm["gases"].values() if np.ndim(v) == 2)
             n_in = 0
-            if cloudy:
-                n_in = sum(per(k) for k in in_keys) + gas2d_n + 4 * nlay
-            else:
+            if True:
                 if do_lw:
-                    n_in += sum(per(k) for k in ("play", "plev", "tlay", "tlev", "tsfc", "sfc_emis")) + gas2d_n
+                    n_in += sum(per(k) for k in ("play", "plev", "tlay", "tlev", "tsfc", "sfc_emis")) + gas2d_n + (4 * nlay if cloudy else 0)
                 if do_sw:
-                    n_in += sum(per(k) for k in ("play", "plev", "tlay", "mu0", "sfc_alb")) + (1 if "tsi" in in_keys else 0) + gas2d_n
+                    n_in += sum(per(k) for k in ("play", "plev", "tlay", "mu0", "sfc_alb")) + (1 if "tsi" in in_keys else 0) + gas2d_n + (4 * nlay if cloudy else 0)
             res["e2e"] = {"value": ncol_total / (e2e["pageable"] * 1e-3), "unit": "columns/s",
                           "h2d_bytes_per_step": int(4 * n_in * ncol), "d2h_bytes_per_step": int(4 * nf * ncol * nlev),
                           "ms_per_step": e2e["pageable"],
@@ -687,11 +651,11 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peaks()
-    compact = bool(args.lw_compact_source) and args.solver_variant == 0 and not cloudy
+    compact = bool(args.lw_compact_source) and args.solver_variant == 0
     abytes = algorithmic_bytes_per_column(nlay, m["ngpt_lw"], m["ngpt_sw"], lw_compact=compact)
-    if cloudy:   # the API path materialises g: three arrays out of the gas optics and into the solver
-        abytes["gas_optics_sw"] = 4 * 8 * nlay + 4 * m["ngpt_sw"] * (2 * nlay)
-        abytes["sw_solver"] = 4 * m["ngpt_sw"] * (3 * nlay + 3) + 4 + 12 * (nlay + 1)
+    if cloudy:   # clouds folded into the solvers: the solvers read 64 (LW) / 192 (SW) more bytes per layer and column
+        abytes["lw_solver"] += 64 * nlay
+        abytes["sw_solver"] += 192 * nlay
     prof, ncol = res["prof"], res["ncol"]
     tot = sum(v[0] for v in prof.values()) or 1.0
     kern = {}

@@ -1,6 +1,6 @@
 ! ISO_C_BINDING interfaces of librrnn_b200.so -- GENERATED from include/rrnn.h by tools/gen_fortran_binding.py; do not edit.
 !
-! One interface block per C entry point (94 of 94).  Scalars by value; handles, device addresses and host
+! One interface block per C entry point (100 of 100).  Scalars by value; handles, device addresses and host
 ! arrays as type(c_ptr) values (host arrays: c_loc(a)); out-arguments and small integer / double arrays by reference.
 ! The comment above each block is the one the header carries: it cites the reference interface the entry point replaces.
 ! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler, SURVEY.md section 0 F1): `make -C fortran` builds it where
@@ -744,6 +744,57 @@ module mo_rrnn_c_binding
       type(c_ptr), value :: flux_dn_dir_d
       integer(c_int) :: rc
     end function rrnn_rte_sw
+    ! rte_lw / rte_sw on gas optical properties + by-band cloud optical properties (nbnd,nlay,ncol) whose
+    ! `clouds%increment(atmos)` (rte/mo_optical_props.F90:714-893 -> inc_1scalar_by_1scalar_bybnd /
+    ! inc_2stream_by_2stream_bybnd, rte/kernels/ mo_optical_props_kernels.F90:358-378, 453-485) has NOT been applied: the
+    ! increment happens inside the solver, in registers, instead of as a read-modify-write pass over tau / ssa / g. SW: for gas
+    ! properties with g == 0 (the NN gas optics); the cloud properties are taken as given (delta-scale them first if the caller
+    ! does, rrnn_delta_scale_2str on the by-band arrays). Shapes the packed solvers do not take return an error that says so.
+    function rrnn_rte_lw_clouds(ctx, kd, nlay, ncol, top_at_1, n_gauss_angles, inc_flux_d, tau_d, lay_source_d, &
+        lev_source_d, sfc_source_d, sfc_emis_d, cld_tau_bnd_d, flux_up_d, flux_dn_d) &
+        bind(C, name="rrnn_rte_lw_clouds") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      integer(c_int), value :: nlay
+      integer(c_int), value :: ncol
+      integer(c_int), value :: top_at_1
+      integer(c_int), value :: n_gauss_angles
+      type(c_ptr), value :: inc_flux_d
+      type(c_ptr), value :: tau_d
+      type(c_ptr), value :: lay_source_d
+      type(c_ptr), value :: lev_source_d
+      type(c_ptr), value :: sfc_source_d
+      type(c_ptr), value :: sfc_emis_d
+      type(c_ptr), value :: cld_tau_bnd_d
+      type(c_ptr), value :: flux_up_d
+      type(c_ptr), value :: flux_dn_d
+      integer(c_int) :: rc
+    end function rrnn_rte_lw_clouds
+    function rrnn_rte_sw_clouds(ctx, kd, nlay, ncol, top_at_1, mu0_d, inc_flux_d, sfc_alb_dir_gpt_d, sfc_alb_dif_gpt_d, &
+        inc_flux_dif_d, tau_d, ssa_d, cld_tau_bnd_d, cld_ssa_bnd_d, cld_g_bnd_d, flux_up_d, flux_dn_d, flux_dn_dir_d) &
+        bind(C, name="rrnn_rte_sw_clouds") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      integer(c_int), value :: nlay
+      integer(c_int), value :: ncol
+      integer(c_int), value :: top_at_1
+      type(c_ptr), value :: mu0_d
+      type(c_ptr), value :: inc_flux_d
+      type(c_ptr), value :: sfc_alb_dir_gpt_d
+      type(c_ptr), value :: sfc_alb_dif_gpt_d
+      type(c_ptr), value :: inc_flux_dif_d
+      type(c_ptr), value :: tau_d
+      type(c_ptr), value :: ssa_d
+      type(c_ptr), value :: cld_tau_bnd_d
+      type(c_ptr), value :: cld_ssa_bnd_d
+      type(c_ptr), value :: cld_g_bnd_d
+      type(c_ptr), value :: flux_up_d
+      type(c_ptr), value :: flux_dn_d
+      type(c_ptr), value :: flux_dn_dir_d
+      integer(c_int) :: rc
+    end function rrnn_rte_sw_clouds
     ! ------------------------------------------------------------------------------------------------ Cloud optics (LUT),
     ! delta-scaling, increments, heating rates ty_cloud_optics%load_lut, extensions/cloud_optics/mo_cloud_optics.F90:90-170:
     ! tables are (nsize,nbnd) == C [nbnd][nsize] for the chosen ice roughness.
@@ -1055,6 +1106,126 @@ module mo_rrnn_c_binding
       type(c_ptr), value :: flux_dn_dir_d
       integer(c_int) :: rc
     end function rrnn_sw_fluxes
+    ! All-sky whole-path drivers: one iteration of examples/all-sky/rrtmgp_allsky.F90:366-446 -- cloud_optics (LUT or Pade
+    ! handle, by band), gas_optics(neural_nets=), [delta_scale,] increment, rte_lw / rte_sw -- for all columns of the call. clwp
+    ! / ciwp / reliq / reice are (nlay,ncol); the other arguments are those of the clear-sky drivers above. The cloud increment
+    ! is NOT a pass over the (ngpt,nlay,ncol) arrays: the by-band cloud properties are added to the gas properties inside the
+    ! solvers.
+    function rrnn_lw_fluxes_allsky(ctx, kd, models, nmodels, cloud_optics, ncol, nlay, top_at_1, n_gauss_angles, &
+        play_d, plev_d, tlay_d, tlev_d, tsfc_d, sfc_emis_d, gases, ngas, clwp_d, ciwp_d, reliq_d, reice_d, flux_up_d, &
+        flux_dn_d) &
+        bind(C, name="rrnn_lw_fluxes_allsky") result(rc)
+      import :: c_int, c_ptr, rrnn_gas_t
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      type(c_ptr) :: models(*)
+      integer(c_int), value :: nmodels
+      type(c_ptr), value :: cloud_optics
+      integer(c_int), value :: ncol
+      integer(c_int), value :: nlay
+      integer(c_int), value :: top_at_1
+      integer(c_int), value :: n_gauss_angles
+      type(c_ptr), value :: play_d
+      type(c_ptr), value :: plev_d
+      type(c_ptr), value :: tlay_d
+      type(c_ptr), value :: tlev_d
+      type(c_ptr), value :: tsfc_d
+      type(c_ptr), value :: sfc_emis_d
+      type(rrnn_gas_t) :: gases(*)
+      integer(c_int), value :: ngas
+      type(c_ptr), value :: clwp_d
+      type(c_ptr), value :: ciwp_d
+      type(c_ptr), value :: reliq_d
+      type(c_ptr), value :: reice_d
+      type(c_ptr), value :: flux_up_d
+      type(c_ptr), value :: flux_dn_d
+      integer(c_int) :: rc
+    end function rrnn_lw_fluxes_allsky
+    function rrnn_sw_fluxes_allsky(ctx, kd, models, cloud_optics, ncol, nlay, top_at_1, play_d, plev_d, tlay_d, mu0_d, &
+        sfc_alb_d, tsi_d, gases, ngas, clwp_d, ciwp_d, reliq_d, reice_d, flux_up_d, flux_dn_d, flux_dn_dir_d) &
+        bind(C, name="rrnn_sw_fluxes_allsky") result(rc)
+      import :: c_int, c_ptr, rrnn_gas_t
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      type(c_ptr) :: models(*)
+      type(c_ptr), value :: cloud_optics
+      integer(c_int), value :: ncol
+      integer(c_int), value :: nlay
+      integer(c_int), value :: top_at_1
+      type(c_ptr), value :: play_d
+      type(c_ptr), value :: plev_d
+      type(c_ptr), value :: tlay_d
+      type(c_ptr), value :: mu0_d
+      type(c_ptr), value :: sfc_alb_d
+      type(c_ptr), value :: tsi_d
+      type(rrnn_gas_t) :: gases(*)
+      integer(c_int), value :: ngas
+      type(c_ptr), value :: clwp_d
+      type(c_ptr), value :: ciwp_d
+      type(c_ptr), value :: reliq_d
+      type(c_ptr), value :: reice_d
+      type(c_ptr), value :: flux_up_d
+      type(c_ptr), value :: flux_dn_d
+      type(c_ptr), value :: flux_dn_dir_d
+      integer(c_int) :: rc
+    end function rrnn_sw_fluxes_allsky
+    function rrnn_lw_fluxes_allsky_host(ctx, kd, models, nmodels, cloud_optics, ncol, nlay, top_at_1, n_gauss_angles, &
+        play, plev, tlay, tlev, tsfc, sfc_emis, gases, ngas, clwp, ciwp, reliq, reice, flux_up, flux_dn) &
+        bind(C, name="rrnn_lw_fluxes_allsky_host") result(rc)
+      import :: c_int, c_ptr, rrnn_gas_t
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      type(c_ptr) :: models(*)
+      integer(c_int), value :: nmodels
+      type(c_ptr), value :: cloud_optics
+      integer(c_int), value :: ncol
+      integer(c_int), value :: nlay
+      integer(c_int), value :: top_at_1
+      integer(c_int), value :: n_gauss_angles
+      type(c_ptr), value :: play
+      type(c_ptr), value :: plev
+      type(c_ptr), value :: tlay
+      type(c_ptr), value :: tlev
+      type(c_ptr), value :: tsfc
+      type(c_ptr), value :: sfc_emis
+      type(rrnn_gas_t) :: gases(*)
+      integer(c_int), value :: ngas
+      type(c_ptr), value :: clwp
+      type(c_ptr), value :: ciwp
+      type(c_ptr), value :: reliq
+      type(c_ptr), value :: reice
+      type(c_ptr), value :: flux_up
+      type(c_ptr), value :: flux_dn
+      integer(c_int) :: rc
+    end function rrnn_lw_fluxes_allsky_host
+    function rrnn_sw_fluxes_allsky_host(ctx, kd, models, cloud_optics, ncol, nlay, top_at_1, play, plev, tlay, mu0, &
+        sfc_alb, tsi, gases, ngas, clwp, ciwp, reliq, reice, flux_up, flux_dn, flux_dn_dir) &
+        bind(C, name="rrnn_sw_fluxes_allsky_host") result(rc)
+      import :: c_int, c_ptr, rrnn_gas_t
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      type(c_ptr) :: models(*)
+      type(c_ptr), value :: cloud_optics
+      integer(c_int), value :: ncol
+      integer(c_int), value :: nlay
+      integer(c_int), value :: top_at_1
+      type(c_ptr), value :: play
+      type(c_ptr), value :: plev
+      type(c_ptr), value :: tlay
+      type(c_ptr), value :: mu0
+      type(c_ptr), value :: sfc_alb
+      type(c_ptr), value :: tsi
+      type(rrnn_gas_t) :: gases(*)
+      integer(c_int), value :: ngas
+      type(c_ptr), value :: clwp
+      type(c_ptr), value :: ciwp
+      type(c_ptr), value :: reliq
+      type(c_ptr), value :: reice
+      type(c_ptr), value :: flux_up
+      type(c_ptr), value :: flux_dn
+      type(c_ptr), value :: flux_dn_dir
+      integer(c_int) :: rc
+    end function rrnn_sw_fluxes_allsky_host
     ! Column chunk used by the drivers above (0 = automatic from free device memory).
     function rrnn_ctx_set_chunk_columns(ctx, ncol_chunk) bind(C, name="rrnn_ctx_set_chunk_columns") result(rc)
       import :: c_int, c_ptr

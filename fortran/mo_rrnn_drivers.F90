@@ -13,9 +13,10 @@ module mo_rrnn_drivers
   use mo_gas_optics_rrtmgp, only: ty_gas_optics_rrtmgp
   use mod_network_rrtmgp, only: rrtmgp_network_type
   use mo_gas_concentrations, only: ty_gas_concs
+  use mo_cloud_optics, only: ty_cloud_optics
   implicit none
   private
-  public :: rrnn_lw, rrnn_sw, ty_rrnn_multi
+  public :: rrnn_lw, rrnn_sw, rrnn_lw_allsky, rrnn_sw_allsky, ty_rrnn_multi
 
   ! One process, N devices (rrnn_multi_*, include/rrnn.h)
   type :: ty_rrnn_multi
@@ -107,6 +108,65 @@ contains
                   c_loc(mu0), c_loc(sfc_alb), p_tsi, gases, int(size(gases), c_int), c_loc(flux_up), c_loc(flux_dn), &
                   c_loc(flux_dn_dir)))
   end function rrnn_sw
+
+  ! ---------------------------------------------------------------------------------------------------- all-sky
+  ! One iteration of examples/all-sky/rrtmgp_allsky.F90:366-446 for all columns: cloud_optics (by band), gas_optics(neural_nets=),
+  ! [delta_scale,] increment, rte -- the increment happens inside the solvers (no pass over the (ngpt,nlay,ncol) arrays).
+  function rrnn_lw_allsky(k_dist, neural_nets, cloud_optics, play, plev, tlay, tsfc, sfc_emis, gas_desc, clwp, ciwp, reliq, reice, &
+                          top_at_1, flux_up, flux_dn, tlev, n_gauss_angles) result(error_msg)
+    type(ty_gas_optics_rrtmgp), intent(in) :: k_dist
+    type(rrtmgp_network_type),  intent(in) :: neural_nets(:)
+    type(ty_cloud_optics),      intent(in) :: cloud_optics
+    real(wp), contiguous, target, intent(in)  :: play(:,:), plev(:,:), tlay(:,:), tsfc(:), sfc_emis(:)
+    type(ty_gas_concs), target,   intent(in)  :: gas_desc
+    real(wp), contiguous, target, intent(in)  :: clwp(:,:), ciwp(:,:), reliq(:,:), reice(:,:)            ! (nlay, ncol)
+    logical,                      intent(in)  :: top_at_1
+    real(wp), contiguous, target, intent(out) :: flux_up(:,:), flux_dn(:,:)
+    real(wp), contiguous, target, optional, intent(in) :: tlev(:,:)
+    integer,                      optional, intent(in) :: n_gauss_angles
+    character(len=128) :: error_msg
+    type(rrnn_gas_t), allocatable :: gases(:)
+    type(c_ptr) :: models(2), p_tlev
+    integer :: i, nang
+    models = c_null_ptr
+    do i = 1, min(size(neural_nets), 2)
+      models(i) = neural_nets(i)%handle
+    end do
+    p_tlev = c_null_ptr
+    if (present(tlev)) p_tlev = c_loc(tlev)
+    nang = 1
+    if (present(n_gauss_angles)) nang = n_gauss_angles
+    call host_gases(gas_desc, gases)
+    error_msg = rrnn_error_msg(rrnn_lw_fluxes_allsky_host(rrnn_ctx(), k_dist%kd, models, int(size(neural_nets), c_int), &
+                  cloud_optics%lut, int(size(play, 2), c_int), int(size(play, 1), c_int), merge(1_c_int, 0_c_int, top_at_1), &
+                  int(nang, c_int), c_loc(play), c_loc(plev), c_loc(tlay), p_tlev, c_loc(tsfc), c_loc(sfc_emis), gases, &
+                  int(size(gases), c_int), c_loc(clwp), c_loc(ciwp), c_loc(reliq), c_loc(reice), c_loc(flux_up), c_loc(flux_dn)))
+  end function rrnn_lw_allsky
+
+  function rrnn_sw_allsky(k_dist, neural_nets, cloud_optics, play, plev, tlay, mu0, sfc_alb, gas_desc, clwp, ciwp, reliq, reice, &
+                          top_at_1, flux_up, flux_dn, flux_dn_dir, tsi_scale) result(error_msg)
+    type(ty_gas_optics_rrtmgp), intent(in) :: k_dist
+    type(rrtmgp_network_type),  intent(in) :: neural_nets(2)
+    type(ty_cloud_optics),      intent(in) :: cloud_optics
+    real(wp), contiguous, target, intent(in)  :: play(:,:), plev(:,:), tlay(:,:), mu0(:), sfc_alb(:)
+    type(ty_gas_concs), target,   intent(in)  :: gas_desc
+    real(wp), contiguous, target, intent(in)  :: clwp(:,:), ciwp(:,:), reliq(:,:), reice(:,:)
+    logical,                      intent(in)  :: top_at_1
+    real(wp), contiguous, target, intent(out) :: flux_up(:,:), flux_dn(:,:), flux_dn_dir(:,:)
+    real(wp), contiguous, target, optional, intent(in) :: tsi_scale(:)
+    character(len=128) :: error_msg
+    type(rrnn_gas_t), allocatable :: gases(:)
+    type(c_ptr) :: models(2), p_tsi
+    models(1) = neural_nets(1)%handle
+    models(2) = neural_nets(2)%handle
+    p_tsi = c_null_ptr
+    if (present(tsi_scale)) p_tsi = c_loc(tsi_scale)
+    call host_gases(gas_desc, gases)
+    error_msg = rrnn_error_msg(rrnn_sw_fluxes_allsky_host(rrnn_ctx(), k_dist%kd, models, cloud_optics%lut, int(size(play, 2), c_int), &
+                  int(size(play, 1), c_int), merge(1_c_int, 0_c_int, top_at_1), c_loc(play), c_loc(plev), c_loc(tlay), c_loc(mu0), &
+                  c_loc(sfc_alb), p_tsi, gases, int(size(gases), c_int), c_loc(clwp), c_loc(ciwp), c_loc(reliq), c_loc(reice), &
+                  c_loc(flux_up), c_loc(flux_dn), c_loc(flux_dn_dir)))
+  end function rrnn_sw_allsky
 
   ! ---------------------------------------------------------------------------------------------------- N devices
   function multi_init(this, devices) result(error_msg)

@@ -254,6 +254,22 @@ RRNN_API int rrnn_rte_sw(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_
                          const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d,
                          float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d);
 
+/* rte_lw / rte_sw on gas optical properties + by-band cloud optical properties (nbnd,nlay,ncol) whose `clouds%increment(atmos)`
+ * (rte/mo_optical_props.F90:714-893 -> inc_1scalar_by_1scalar_bybnd / inc_2stream_by_2stream_bybnd, rte/kernels/
+ * mo_optical_props_kernels.F90:358-378, 453-485) has NOT been applied: the increment happens inside the solver, in registers,
+ * instead of as a read-modify-write pass over tau / ssa / g.  SW: for gas properties with g == 0 (the NN gas optics); the cloud
+ * properties are taken as given (delta-scale them first if the caller does, rrnn_delta_scale_2str on the by-band arrays).
+ * Shapes the packed solvers do not take return an error that says so. */
+RRNN_API int rrnn_rte_lw_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,
+                                const float* inc_flux_d, const float* tau_d, const float* lay_source_d, const float* lev_source_d,
+                                const float* sfc_source_d, const float* sfc_emis_d, const float* cld_tau_bnd_d, float* flux_up_d,
+                                float* flux_dn_d);
+RRNN_API int rrnn_rte_sw_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, const float* mu0_d,
+                                const float* inc_flux_d, const float* sfc_alb_dir_gpt_d, const float* sfc_alb_dif_gpt_d,
+                                const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* cld_tau_bnd_d,
+                                const float* cld_ssa_bnd_d, const float* cld_g_bnd_d, float* flux_up_d, float* flux_dn_d,
+                                float* flux_dn_dir_d);
+
 /* ------------------------------------------------------------------------------------------------ */
 /* Cloud optics (LUT), delta-scaling, increments, heating rates                                        */
 /* ty_cloud_optics%load_lut, extensions/cloud_optics/mo_cloud_optics.F90:90-170: tables are
@@ -336,6 +352,30 @@ RRNN_API int rrnn_sw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_
                             int top_at_1, const float* play_d, const float* plev_d, const float* tlay_d, const float* mu0_d,
                             const float* sfc_alb_d, const float* tsi_d, const rrnn_gas_t* gases, int ngas,
                             float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d);
+/* All-sky whole-path drivers: one iteration of examples/all-sky/rrtmgp_allsky.F90:366-446 -- cloud_optics (LUT or Pade handle, by
+ * band), gas_optics(neural_nets=), [delta_scale,] increment, rte_lw / rte_sw -- for all columns of the call.  clwp / ciwp /
+ * reliq / reice are (nlay,ncol); the other arguments are those of the clear-sky drivers above.  The cloud increment is NOT a
+ * pass over the (ngpt,nlay,ncol) arrays: the by-band cloud properties are added to the gas properties inside the solvers. */
+RRNN_API int rrnn_lw_fluxes_allsky(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                                   const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, int n_gauss_angles,
+                                   const float* play_d, const float* plev_d, const float* tlay_d, const float* tlev_d, const float* tsfc_d,
+                                   const float* sfc_emis_d, const rrnn_gas_t* gases, int ngas, const float* clwp_d, const float* ciwp_d,
+                                   const float* reliq_d, const float* reice_d, float* flux_up_d, float* flux_dn_d);
+RRNN_API int rrnn_sw_fluxes_allsky(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models,
+                                   const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, const float* play_d,
+                                   const float* plev_d, const float* tlay_d, const float* mu0_d, const float* sfc_alb_d, const float* tsi_d,
+                                   const rrnn_gas_t* gases, int ngas, const float* clwp_d, const float* ciwp_d, const float* reliq_d,
+                                   const float* reice_d, float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d);
+RRNN_API int rrnn_lw_fluxes_allsky_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                                        const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, int n_gauss_angles,
+                                        const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
+                                        const float* sfc_emis, const rrnn_gas_t* gases, int ngas, const float* clwp, const float* ciwp,
+                                        const float* reliq, const float* reice, float* flux_up, float* flux_dn);
+RRNN_API int rrnn_sw_fluxes_allsky_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models,
+                                        const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, const float* play,
+                                        const float* plev, const float* tlay, const float* mu0, const float* sfc_alb, const float* tsi,
+                                        const rrnn_gas_t* gases, int ngas, const float* clwp, const float* ciwp, const float* reliq,
+                                        const float* reice, float* flux_up, float* flux_dn, float* flux_dn_dir);
 /* Column chunk used by the drivers above (0 = automatic from free device memory). */
 RRNN_API int rrnn_ctx_set_chunk_columns(rrnn_ctx_t* ctx, int ncol_chunk);
 

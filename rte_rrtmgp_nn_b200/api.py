@@ -334,7 +334,37 @@ class ty_optical_props:
     def get_name(self): return self.name
 
 
-class ty_optical_props_1scl(ty_optical_props):
+# K5: `clouds.increment(atmos)` with by-band clouds is DEFERRED -- the small by-band arrays are copied and
+# remembered on `atmos`; rte_lw / rte_sw then hand them to solvers that add them to the gas optical properties in registers
+# (rrnn_rte_lw_clouds / rrnn_rte_sw_clouds), and anything else that looks at atmos.tau / .ssa / .g first applies the increment the
+# ordinary way.  Same results either way (tests); FUSE_CLOUD_INCREMENT = False restores the eager pass over (ngpt,nlay,ncol).
+FUSE_CLOUD_INCREMENT = True
+
+
+class _deferred_increment:
+    """Mixin for the array carriers: `tau` (and `ssa`) are properties that apply a pending cloud increment before they are seen."""
+    _tau = None
+    _pending = None
+
+    @property
+    def tau(self):
+        self._apply_pending()
+        return self._tau
+
+    @tau.setter
+    def tau(self, v):
+        self._pending = None
+        self._tau = v
+
+    def _apply_pending(self):
+        pend, self._pending = self._pending, None
+        if pend is not None:
+            msg = pend._increment_now(self)
+            if msg != "":
+                raise RRNNError(msg)
+
+
+class ty_optical_props_1scl(_deferred_increment, ty_optical_props):
     def __init__(self):
         super().__init__()
         self.tau = None
@@ -349,14 +379,26 @@ class ty_optical_props_1scl(ty_optical_props):
         self.tau = torch.empty((ncol, nlay, n), dtype=torch.float32, device=torch.device("cuda", self.ctx.device))
         return ""
 
-    def get_ncol(self): return self.tau.shape[0]
-    def get_nlay(self): return self.tau.shape[1]
+    def get_ncol(self): return self._tau.shape[0]
+    def get_nlay(self): return self._tau.shape[1]
 
     def increment(self, op_io):
-        """op_io := op_io + self, self given by band (inc_1scalar_by_1scalar_bybnd)."""
+        """op_io := op_io + self, self given by band (inc_1scalar_by_1scalar_bybnd); deferred into rte_lw where possible."""
         if not getattr(self, "by_band", False):
             op_io.tau += self.tau
             return ""
+        if (FUSE_CLOUD_INCREMENT and isinstance(op_io, ty_optical_props_1scl) and not getattr(op_io, "by_band", False)
+                and tuple(op_io._tau.shape[:2]) == tuple(self.tau.shape[:2])):
+            op_io._apply_pending()
+            snap = ty_optical_props_1scl()
+            snap.by_band, snap.ctx = True, self.ctx
+            with _torch().cuda.stream(op_io.ctx.torch_stream()):
+                snap._tau = self.tau.clone()
+            op_io._pending = snap
+            return ""
+        return self._increment_now(op_io)
+
+    def _increment_now(self, op_io):
         try:
             _lib.check(_lib.lib().rrnn_increment_1scl_bybnd(op_io.ctx.h, op_io._kd.h, op_io.get_nlay(), op_io.get_ncol(),
                                                             _ptr(op_io.tau), _ptr(self.tau)))
@@ -365,13 +407,24 @@ class ty_optical_props_1scl(ty_optical_props):
         return ""
 
 
-class ty_optical_props_2str(ty_optical_props):
+class ty_optical_props_2str(_deferred_increment, ty_optical_props):
+    _ssa = None
+
     def __init__(self):
         super().__init__()
         self.tau = None
         self.ssa = None
         self._g = None
         self.g_is_zero = False
+
+    @property
+    def ssa(self):
+        self._apply_pending()
+        return self._ssa
+
+    @ssa.setter
+    def ssa(self, v):
+        self._ssa = v
 
     def alloc_2str(self, ncol, nlay, spectral=None, name="", by_band=False, ctx=None):
         torch = _torch()
@@ -391,6 +444,7 @@ class ty_optical_props_2str(ty_optical_props):
     def g(self):
         """Asymmetry parameter; materialised on first use (gas optics leaves it as an implicit zero)."""
         torch = _torch()
+        self._apply_pending()
         if self._g is None:
             with torch.cuda.stream(self.ctx.torch_stream()):
                 self._g = (torch.zeros_like(self.tau) if self.g_is_zero else torch.empty_like(self.tau))
@@ -401,8 +455,8 @@ class ty_optical_props_2str(ty_optical_props):
         self._g = v
         self.g_is_zero = False
 
-    def get_ncol(self): return self.tau.shape[0]
-    def get_nlay(self): return self.tau.shape[1]
+    def get_ncol(self): return self._tau.shape[0]
+    def get_nlay(self): return self._tau.shape[1]
 
     def delta_scale(self):
         try:
@@ -413,7 +467,20 @@ class ty_optical_props_2str(ty_optical_props):
         return ""
 
     def increment(self, op_io):
-        """op_io := op_io + self, self given by band (inc_2stream_by_2stream_bybnd)."""
+        """op_io := op_io + self, self given by band (inc_2stream_by_2stream_bybnd); deferred into rte_sw where possible (gas
+        optical properties whose g is still the implicit zero of the NN gas optics)."""
+        if (FUSE_CLOUD_INCREMENT and getattr(self, "by_band", False) and isinstance(op_io, ty_optical_props_2str)
+                and not getattr(op_io, "by_band", False) and op_io._pending is None and op_io.g_is_zero and op_io._g is None
+                and tuple(op_io._tau.shape[:2]) == tuple(self.tau.shape[:2])):
+            snap = ty_optical_props_2str()
+            snap.by_band, snap.ctx = True, self.ctx
+            with _torch().cuda.stream(op_io.ctx.torch_stream()):
+                snap._tau, snap._ssa, snap._g = self.tau.clone(), self.ssa.clone(), self.g.clone()
+            op_io._pending = snap
+            return ""
+        return self._increment_now(op_io)
+
+    def _increment_now(self, op_io):
         try:
             g1 = op_io.g  # materialises zeros if needed
             _lib.check(_lib.lib().rrnn_increment_2str_bybnd(op_io.ctx.h, op_io._kd.h, op_io.get_nlay(), op_io.get_ncol(),
@@ -686,6 +753,7 @@ class ty_gas_optics_rrtmgp(ty_optical_props):
                 if sources.get_ncol() != ncol or sources.get_nlay() != nlay or sources.ngpt != self.ngpt:
                     return "gas_optics%gas_optics: source function arrays inconsistently sized"
                 optical_props._kd = self._kd
+                optical_props._pending = None      # everything in optical_props is overwritten
                 _lib.check(lib.rrnn_gas_optics_lw(ctx.h, self._kd.h, models, len(neural_nets), ncol, nlay, _ptr(play), _ptr(plev),
                                                   _ptr(tlay), _ptr(tsfc), gases, ngas, _ptr(tlev_d), _ptr(optical_props.tau),
                                                   _ptr(sources.lay_source), _ptr(sources.lev_source), _ptr(sources.sfc_source),
@@ -694,6 +762,7 @@ class ty_gas_optics_rrtmgp(ty_optical_props):
                 gas_desc, optical_props, toa_src = args
                 gases, ngas, keep = gas_desc._to_c(ctx)
                 optical_props._kd = self._kd
+                optical_props._pending = None      # everything in optical_props is overwritten
                 if isinstance(optical_props, ty_optical_props_2str):
                     optical_props._g = None
                     optical_props.g_is_zero = True   # g(:,:,:) = 0, mo_gas_optics_rrtmgp.F90:560-567 (kept implicit)
@@ -807,6 +876,17 @@ def rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes, inc_flux=None, n_
     if tuple(sfc_emis.shape) != (ncol, optical_props.nband):
         return "rte_lw: sfc_emis inconsistently sized"
     inc = _dev(inc_flux, ctx)
+    pend = optical_props._pending
+    if pend is not None:     # clouds whose increment is still pending: added to tau inside the solver (K5)
+        try:
+            _lib.check(_lib.lib().rrnn_rte_lw_clouds(ctx.h, optical_props._kd.h, nlay, ncol, int(bool(top_at_1)), nang, _ptr(inc),
+                                                     _ptr(optical_props._tau), _ptr(sources.lay_source), _ptr(sources.lev_source),
+                                                     _ptr(sources.sfc_source), _ptr(sfc_emis), _ptr(pend._tau), _ptr(fluxes.flux_up),
+                                                     _ptr(fluxes.flux_dn)))
+            return ""
+        except RRNNError as e:
+            if "not taken by the packed solver" not in str(e):
+                return str(e)         # (otherwise: apply the increment the ordinary way -- optical_props.tau does -- and go on)
     try:
         _lib.check(_lib.lib().rrnn_rte_lw(ctx.h, optical_props._kd.h, nlay, ncol, int(bool(top_at_1)), nang, _ptr(inc),
                                           _ptr(optical_props.tau), _ptr(sources.lay_source), _ptr(sources.lev_source),
@@ -837,8 +917,19 @@ def rte_sw(atmos, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, flu
         return "rte_sw: sfc_alb_dir inconsistently sized"
     if tuple(a_dif.shape) != (ncol, ngpt):
         return "rte_sw: sfc_alb_dif inconsistently sized"
-    g_p = None if atmos.g_is_zero and atmos._g is None else _ptr(atmos.g)
     gpt = [getattr(fluxes, k, None) for k in ("gpt_flux_up", "gpt_flux_dn", "gpt_flux_dn_dir")]
+    pend = atmos._pending
+    if pend is not None and all(v is None for v in gpt):   # clouds whose increment is still pending: folded into the solver (K5)
+        try:
+            _lib.check(_lib.lib().rrnn_rte_sw_clouds(ctx.h, atmos._kd.h, nlay, ncol, int(bool(top_at_1)), _ptr(mu0), _ptr(inc_flux),
+                                                     _ptr(a_dir), _ptr(a_dif), _ptr(_dev(inc_flux_dif, ctx)), _ptr(atmos._tau),
+                                                     _ptr(atmos._ssa), _ptr(pend._tau), _ptr(pend._ssa), _ptr(pend._g),
+                                                     _ptr(fluxes.flux_up), _ptr(fluxes.flux_dn), _ptr(fluxes.flux_dn_dir)))
+            return ""
+        except RRNNError as e:
+            if "not taken by the packed solver" not in str(e):
+                return str(e)
+    g_p = None if atmos.g_is_zero and atmos._g is None and atmos._pending is None else _ptr(atmos.g)
     if any(v is not None for v in gpt):  # ty_fluxes_flexible with g-point fluxes: the general kernel
         if any(v is None for v in gpt):
             return "rte_sw: gpt_flux_up, gpt_flux_dn and gpt_flux_dn_dir must all be associated"
@@ -1149,6 +1240,68 @@ def sw_fluxes(k_dist, neural_nets, play, plev, tlay, mu0, sfc_alb, gas_desc, flu
     _lib.check(_lib.lib().rrnn_sw_fluxes(ctx.h, k_dist._kd.h, _models(neural_nets), ncol, nlay, int(bool(top_at_1)), _ptr(play),
                                          _ptr(plev), _ptr(tlay), _ptr(mu0), _ptr(sfc_alb), _ptr(tsi), gases, ngas,
                                          _ptr(flux_up), _ptr(flux_dn), _ptr(flux_dn_dir)))
+
+
+def _cloud_args(cl, conv):
+    """clwp, ciwp, reliq, reice of a dict with the keys of synth.make_clouds / drivers.allsky_clouds"""
+    return [conv(cl[k]) for k in ("lwp", "iwp", "rel", "rei")]
+
+
+def lw_fluxes_allsky(k_dist, neural_nets, cloud_optics, play, plev, tlay, tsfc, sfc_emis, gas_desc, clouds, flux_up, flux_dn, tlev=None,
+                     top_at_1=True, n_gauss_angles=1):
+    """Device tensors in / out: cloud_optics + gas_optics(neural_nets=) + increment + rte_lw for all columns (rrnn_lw_fluxes_allsky);
+    cloud_optics is a loaded ty_cloud_optics, clouds a dict lwp / iwp / rel / rei of (ncol, nlay) tensors."""
+    ctx = k_dist.ctx
+    ncol, nlay = play.shape
+    gases, ngas, keep = gas_desc._to_c(ctx)
+    _lib.check(_lib.lib().rrnn_lw_fluxes_allsky(ctx.h, k_dist._kd.h, _models(neural_nets), len(neural_nets), cloud_optics.h, ncol, nlay,
+                                                int(bool(top_at_1)), int(n_gauss_angles), _ptr(play), _ptr(plev), _ptr(tlay), _ptr(tlev),
+                                                _ptr(tsfc), _ptr(sfc_emis), gases, ngas, *_cloud_args(clouds, _ptr), _ptr(flux_up),
+                                                _ptr(flux_dn)))
+
+
+def sw_fluxes_allsky(k_dist, neural_nets, cloud_optics, play, plev, tlay, mu0, sfc_alb, gas_desc, clouds, flux_up, flux_dn, flux_dn_dir,
+                     tsi=None, top_at_1=True):
+    ctx = k_dist.ctx
+    ncol, nlay = play.shape
+    gases, ngas, keep = gas_desc._to_c(ctx)
+    _lib.check(_lib.lib().rrnn_sw_fluxes_allsky(ctx.h, k_dist._kd.h, _models(neural_nets), cloud_optics.h, ncol, nlay, int(bool(top_at_1)),
+                                                _ptr(play), _ptr(plev), _ptr(tlay), _ptr(mu0), _ptr(sfc_alb), _ptr(tsi), gases, ngas,
+                                                *_cloud_args(clouds, _ptr), _ptr(flux_up), _ptr(flux_dn), _ptr(flux_dn_dir)))
+
+
+def lw_fluxes_allsky_host(k_dist, neural_nets, cloud_optics, play, plev, tlay, tsfc, sfc_emis, gas_desc, clouds, tlev=None, top_at_1=True,
+                          n_gauss_angles=1, flux_up=None, flux_dn=None):
+    """numpy in / numpy out (rrnn_lw_fluxes_allsky_host)."""
+    ctx = k_dist.ctx
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    play, plev, tlay, tlev, tsfc, sfc_emis = map(f32, (play, plev, tlay, tlev, tsfc, sfc_emis))
+    cl = _cloud_args(clouds, f32)
+    ncol, nlay = play.shape
+    flux_up = _flux_out(flux_up, ncol, nlay + 1, "lw_fluxes_allsky_host: flux_up")
+    flux_dn = _flux_out(flux_dn, ncol, nlay + 1, "lw_fluxes_allsky_host: flux_dn")
+    gases, ngas, keep = gas_desc._to_c(ctx, host=True)
+    _lib.check(_lib.lib().rrnn_lw_fluxes_allsky_host(ctx.h, k_dist._kd.h, _models(neural_nets), len(neural_nets), cloud_optics.h, ncol, nlay,
+                                                     int(bool(top_at_1)), int(n_gauss_angles), _hp(play), _hp(plev), _hp(tlay), _hp(tlev),
+                                                     _hp(tsfc), _hp(sfc_emis), gases, ngas, *[_hp(a) for a in cl], _hp(flux_up), _hp(flux_dn)))
+    return flux_up, flux_dn
+
+
+def sw_fluxes_allsky_host(k_dist, neural_nets, cloud_optics, play, plev, tlay, mu0, sfc_alb, gas_desc, clouds, tsi=None, top_at_1=True,
+                          flux_up=None, flux_dn=None, flux_dn_dir=None):
+    ctx = k_dist.ctx
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    play, plev, tlay, mu0, sfc_alb, tsi = map(f32, (play, plev, tlay, mu0, sfc_alb, tsi))
+    cl = _cloud_args(clouds, f32)
+    ncol, nlay = play.shape
+    flux_up = _flux_out(flux_up, ncol, nlay + 1, "sw_fluxes_allsky_host: flux_up")
+    flux_dn = _flux_out(flux_dn, ncol, nlay + 1, "sw_fluxes_allsky_host: flux_dn")
+    flux_dn_dir = _flux_out(flux_dn_dir, ncol, nlay + 1, "sw_fluxes_allsky_host: flux_dn_dir")
+    gases, ngas, keep = gas_desc._to_c(ctx, host=True)
+    _lib.check(_lib.lib().rrnn_sw_fluxes_allsky_host(ctx.h, k_dist._kd.h, _models(neural_nets), cloud_optics.h, ncol, nlay,
+                                                     int(bool(top_at_1)), _hp(play), _hp(plev), _hp(tlay), _hp(mu0), _hp(sfc_alb), _hp(tsi),
+                                                     gases, ngas, *[_hp(a) for a in cl], _hp(flux_up), _hp(flux_dn), _hp(flux_dn_dir)))
+    return flux_up, flux_dn, flux_dn_dir
 
 
 class MultiDevice:

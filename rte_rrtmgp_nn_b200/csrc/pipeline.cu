@@ -10,7 +10,17 @@
 #include <thread>
 
 namespace rrnn {
-bool lw_v5_supports(int G, int L);  // rte_solvers_v5.cu
+bool lw_v5_supports(int G, int L);  // rte_solvers_tma.cu
+// rte_solvers.cu: clouds folded into the packed solvers (-1 = shape not taken)
+int cloud_rows_lw(rrnn_ctx_t* ctx, size_t nsmp, int nbnd, const float* tau_bnd_d, float* rows_d);
+int cloud_rows_sw(rrnn_ctx_t* ctx, size_t nsmp, int nbnd, const float* tau_bnd_d, const float* ssa_bnd_d, const float* g_bnd_d, float* rows_d);
+int lw_solver_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int nmus, const float* Ds, const float* weights,
+                     const float* inc_flux_d, const float* tau_d, const float* lay_d, const float* lev_d, const float* planck_lay_d,
+                     const float* planck_lev_d, const float* sfc_emis_gpt_d, const float* sfc_source_d, const float* cld_rows_d,
+                     float* flux_up_d, float* flux_dn_d);
+int sw_solver_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, const float* inc_flux_d, const float* inc_flux_dif_d,
+                     const float* tau_d, const float* ssa_d, const float* cld_rows_d, const float* mu0_d, const float* alb_dir_d,
+                     const float* alb_dif_d, float* flux_up_d, float* flux_dn_d, float* flux_dir_d);
 }
 bool rrnn_gas_optics_tc_can(const rrnn_ctx_t* ctx, int mode, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int nlay,
                             bool compact);  // gas_optics_tc.cu
@@ -71,6 +81,16 @@ static size_t sw_ws_bytes(int G, int L, int nc) {
   return 4 * (align256((size_t)nc * L * G) * 2 + 2 * align256((size_t)nc * G) + align256((size_t)nc));
 }
 
+// all-sky: the chunk's cloud physical properties on the device and where their optical properties come from
+struct CloudIn {
+  const rrnn_cloud_lut_t* lut = nullptr;   // LUT or Pade handle (rrnn_cloud_lut_create / rrnn_cloud_pade_create)
+  const float *clwp = nullptr, *ciwp = nullptr, *reliq = nullptr, *reice = nullptr;   // (nlay,ncol)
+};
+// by-band cloud optical properties (1 LW / 3 SW arrays of (16,nlay,ncol) at most) + the table rows the solver reads
+static size_t cld_ws_bytes(int L, int nc, bool sw) {
+  return 4 * ((sw ? 3 : 1) * align256((size_t)nc * L * 16) + align256((size_t)nc * L * (sw ? 48 : 16)));
+}
+
 static int pick_chunk(rrnn_ctx_t* ctx, int ncol, size_t bytes_per_col) {
   if (ctx->chunk_columns > 0) return std::min(ncol, ctx->chunk_columns);
   // default: at most ~12 GiB of optical-property workspace and never more than half of what the device has free right
@@ -110,7 +130,8 @@ static void offset_gases(const rrnn_gas_t* in, int ngas, size_t c0, int nlay, st
 
 static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int nc, int L,
                     int top_at_1, int nang, const float* play, const float* plev, const float* tlay, const float* tlev,
-                    const float* tsfc, const float* emis, const rrnn_gas_t* gases, int ngas, float* fup, float* fdn, float* ws) {
+                    const float* tsfc, const float* emis, const rrnn_gas_t* gases, int ngas, float* fup, float* fdn, float* ws,
+                    const CloudIn* cl = nullptr) {
   static const float gauss_Ds[4][4] = {{1.66f, 0.f, 0.f, 0.f},
                                        {1.18350343f, 2.81649655f, 0.f, 0.f},
                                        {1.09719858f, 1.69338507f, 4.70941630f, 0.f},
@@ -131,6 +152,18 @@ static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
     float* egpt = sjac + align256((size_t)nc * G);
     if (int rc = rrnn_gas_optics_lw_compact(ctx, kd, models, nmodels, nc, L, play, plev, tlay, tsfc, gases, ngas, tlev, tau, lay, bl, bv, ssrc, sjac))
       return rc;
+    if (cl) {   // all-sky (rrtmgp_allsky.F90:369-400): cloud optics by band, increment folded into the solver
+      float* ctau = egpt + align256((size_t)nc * G);
+      float* rows = ctau + align256((size_t)nc * L * 16);
+      if (int rc = rrnn_cloud_optics(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, ctau, nullptr, nullptr)) return rc;
+      if (int rc = cloud_rows_lw(ctx, (size_t)nc * L, kd->nbnd, ctau, rows)) return rc;
+      NvtxRange nvtx_rte("rte_lw");
+      bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
+      RRNN_LAUNCH_CHECK(ctx);
+      const int rc = lw_solver_clouds(ctx, kd, L, nc, top_at_1, nang, gauss_Ds[nang - 1], gauss_wts[nang - 1], nullptr, tau, lay, nullptr, bl, bv,
+                                      egpt, ssrc, rows, fup, fdn);
+      return rc < 0 ? fail("rrnn_lw_fluxes_allsky: shape not taken by the packed solver") : rc;
+    }
     NvtxRange nvtx_rte("rte_lw");
     bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
     RRNN_LAUNCH_CHECK(ctx);
@@ -143,6 +176,21 @@ static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
   float* egpt = sjac + align256((size_t)nc * G);
   if (int rc = rrnn_gas_optics_lw(ctx, kd, models, nmodels, nc, L, play, plev, tlay, tsfc, gases, ngas, tlev, tau, lay, lev, ssrc, sjac))
     return rc;
+  if (cl) {
+    float* ctau = egpt + align256((size_t)nc * G);
+    float* rows = ctau + align256((size_t)nc * L * 16);
+    if (int rc = rrnn_cloud_optics(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, ctau, nullptr, nullptr)) return rc;
+    if (int rc = cloud_rows_lw(ctx, (size_t)nc * L, kd->nbnd, ctau, rows)) return rc;
+    NvtxRange nvtx_rte("rte_lw");
+    bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
+    RRNN_LAUNCH_CHECK(ctx);
+    int rc = lw_solver_clouds(ctx, kd, L, nc, top_at_1, nang, gauss_Ds[nang - 1], gauss_wts[nang - 1], nullptr, tau, lay, lev, nullptr, nullptr,
+                              egpt, ssrc, rows, fup, fdn);
+    if (rc >= 0) return rc;
+    // shapes the packed solver does not take: the increment as a pass over tau, then the plain solver
+    if ((rc = rrnn_increment_1scl_bybnd(ctx, kd, L, nc, tau, ctau))) return rc;
+    return rrnn_lw_solver_noscat(ctx, G, L, nc, top_at_1, nang, gauss_Ds[nang - 1], gauss_wts[nang - 1], nullptr, tau, lay, lev, egpt, ssrc, fup, fdn);
+  }
   NvtxRange nvtx_rte("rte_lw");
   bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
   RRNN_LAUNCH_CHECK(ctx);
@@ -152,7 +200,8 @@ static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
 
 static int sw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nc, int L, int top_at_1,
                     const float* play, const float* plev, const float* tlay, const float* mu0, const float* alb,
-                    const float* tsi, const rrnn_gas_t* gases, int ngas, float* fup, float* fdn, float* fdir, float* ws) {
+                    const float* tsi, const rrnn_gas_t* gases, int ngas, float* fup, float* fdn, float* fdir, float* ws,
+                    const CloudIn* cl = nullptr) {
   const int G = kd->ngpt;
   float* tau = ws;
   float* ssa = tau + align256((size_t)nc * L * G);
@@ -167,7 +216,19 @@ static int sw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
   NvtxRange nvtx_rte("rte_sw");
   sw_bc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, kd->d_solar_source, def_tsi, tsi, alb, mu0, toa, agpt, mu0e);
   RRNN_LAUNCH_CHECK(ctx);
-  if (int rc = rrnn_sw_solver_2stream(ctx, G, L, nc, top_at_1, toa, nullptr, tau, ssa, nullptr, mu0e, agpt, agpt, fup, fdn, fdir)) return rc;
+  if (cl) {   // all-sky (rrtmgp_allsky.F90:369-431): cloud optics by band, delta-scaling by band, increment folded into the solver
+    float* ctau = mu0e + align256((size_t)nc);
+    float* cssa = ctau + align256((size_t)nc * L * 16);
+    float* cg = cssa + align256((size_t)nc * L * 16);
+    float* rows = cg + align256((size_t)nc * L * 16);
+    if (int rc = rrnn_cloud_optics(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, ctau, cssa, cg)) return rc;
+    if (int rc = rrnn_delta_scale_2str(ctx, (size_t)nc * L * kd->nbnd, ctau, cssa, cg)) return rc;
+    if (int rc = cloud_rows_sw(ctx, (size_t)nc * L, kd->nbnd, ctau, cssa, cg, rows)) return rc;
+    const int rc = sw_solver_clouds(ctx, kd, L, nc, top_at_1, toa, nullptr, tau, ssa, rows, mu0e, agpt, agpt, fup, fdn, fdir);
+    if (rc) return rc < 0 ? fail("rrnn_sw_fluxes_allsky: shape not taken by the packed solver") : rc;
+  } else if (int rc = rrnn_sw_solver_2stream(ctx, G, L, nc, top_at_1, toa, nullptr, tau, ssa, nullptr, mu0e, agpt, agpt, fup, fdn, fdir)) {
+    return rc;
+  }
   const size_t nf = (size_t)(L + 1) * nc;
   sw_night_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, ctx->stream>>>(L + 1, nc, mu0, fup, fdn);
   RRNN_LAUNCH_CHECK(ctx);
@@ -178,27 +239,78 @@ static int sw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
 
 using namespace rrnn;
 
-extern "C" int rrnn_lw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
-                              int ncol, int nlay, int top_at_1, int n_gauss_angles, const float* play_d, const float* plev_d,
-                              const float* tlay_d, const float* tlev_d, const float* tsfc_d, const float* sfc_emis_d,
-                              const rrnn_gas_t* gases, int ngas, float* flux_up_d, float* flux_dn_d) {
-  rrnn::NvtxRange nvtx_("clear_sky_total (LW)");
+static int lw_fluxes_dev(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int ncol, int nlay,
+                         int top_at_1, int n_gauss_angles, const float* play_d, const float* plev_d, const float* tlay_d, const float* tlev_d,
+                         const float* tsfc_d, const float* sfc_emis_d, const rrnn_gas_t* gases, int ngas, float* flux_up_d, float* flux_dn_d,
+                         const CloudIn* cl) {
   RRNN_CHECK(ctx && kd && models, "rrnn_lw_fluxes: null handle");
   RRNN_CHECK(n_gauss_angles >= 1 && n_gauss_angles <= 4, "rte_lw: n_gauss_angles must be in 1..4");
   if (ncol <= 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
   const int G = kd->ngpt, L = nlay;
   const bool compact = lw_compact(ctx, kd, models, nmodels, L);
-  int chunk = pick_chunk(ctx, ncol, lw_ws_bytes(G, L, 1, compact));
-  if (int rc = ensure_ws_retry(ctx, chunk, [&](int c) { return lw_ws_bytes(G, L, c, compact); })) return rc;
+  auto bytes_of = [&](int c) { return lw_ws_bytes(G, L, c, compact) + (cl ? cld_ws_bytes(L, c, false) : 0); };
+  int chunk = pick_chunk(ctx, ncol, bytes_of(1));
+  if (int rc = ensure_ws_retry(ctx, chunk, bytes_of)) return rc;
   std::vector<rrnn_gas_t> gs;
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
     const int nc = std::min(chunk, ncol - c0);
     offset_gases(gases, ngas, (size_t)c0, L, gs);
+    CloudIn c1;
+    if (cl) { c1 = *cl; c1.clwp += (size_t)c0 * L; c1.ciwp += (size_t)c0 * L; c1.reliq += (size_t)c0 * L; c1.reice += (size_t)c0 * L; }
     if (int rc = lw_chunk(ctx, kd, models, nmodels, nc, L, top_at_1, n_gauss_angles, play_d + (size_t)c0 * L,
                           plev_d + (size_t)c0 * (L + 1), tlay_d + (size_t)c0 * L, tlev_d ? tlev_d + (size_t)c0 * (L + 1) : nullptr,
                           tsfc_d + c0, sfc_emis_d + c0, gs.data(), ngas, flux_up_d + (size_t)c0 * (L + 1),
-                          flux_dn_d + (size_t)c0 * (L + 1), (float*)ctx->ws))
+                          flux_dn_d + (size_t)c0 * (L + 1), (float*)ctx->ws, cl ? &c1 : nullptr))
+      return rc;
+  }
+  return 0;
+}
+
+extern "C" int rrnn_lw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                              int ncol, int nlay, int top_at_1, int n_gauss_angles, const float* play_d, const float* plev_d,
+                              const float* tlay_d, const float* tlev_d, const float* tsfc_d, const float* sfc_emis_d,
+                              const rrnn_gas_t* gases, int ngas, float* flux_up_d, float* flux_dn_d) {
+  rrnn::NvtxRange nvtx_("clear_sky_total (LW)");
+  return lw_fluxes_dev(ctx, kd, models, nmodels, ncol, nlay, top_at_1, n_gauss_angles, play_d, plev_d, tlay_d, tlev_d, tsfc_d, sfc_emis_d, gases,
+                       ngas, flux_up_d, flux_dn_d, nullptr);
+}
+
+extern "C" int rrnn_lw_fluxes_allsky(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                                     const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, int n_gauss_angles,
+                                     const float* play_d, const float* plev_d, const float* tlay_d, const float* tlev_d, const float* tsfc_d,
+                                     const float* sfc_emis_d, const rrnn_gas_t* gases, int ngas, const float* clwp_d, const float* ciwp_d,
+                                     const float* reliq_d, const float* reice_d, float* flux_up_d, float* flux_dn_d) {
+  rrnn::NvtxRange nvtx_("cloudy_sky_total");
+  RRNN_CHECK(cloud_optics && clwp_d && ciwp_d && reliq_d && reice_d, "cloud optics: no data has been initialized");
+  CloudIn cl;
+  cl.lut = cloud_optics; cl.clwp = clwp_d; cl.ciwp = ciwp_d; cl.reliq = reliq_d; cl.reice = reice_d;
+  return lw_fluxes_dev(ctx, kd, models, nmodels, ncol, nlay, top_at_1, n_gauss_angles, play_d, plev_d, tlay_d, tlev_d, tsfc_d, sfc_emis_d, gases,
+                       ngas, flux_up_d, flux_dn_d, &cl);
+}
+
+static int sw_fluxes_dev(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int ncol, int nlay, int top_at_1,
+                         const float* play_d, const float* plev_d, const float* tlay_d, const float* mu0_d, const float* sfc_alb_d,
+                         const float* tsi_d, const rrnn_gas_t* gases, int ngas, float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d,
+                         const CloudIn* cl) {
+  RRNN_CHECK(ctx && kd && models, "rrnn_sw_fluxes: null handle");
+  RRNN_CHECK(kd->d_solar_source, "rrnn_sw_fluxes: k-distribution has no solar source");
+  if (ncol <= 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const int G = kd->ngpt, L = nlay;
+  auto bytes_of = [&](int c) { return sw_ws_bytes(G, L, c) + (cl ? cld_ws_bytes(L, c, true) : 0); };
+  int chunk = pick_chunk(ctx, ncol, bytes_of(1));
+  if (int rc = ensure_ws_retry(ctx, chunk, bytes_of)) return rc;
+  std::vector<rrnn_gas_t> gs;
+  for (int c0 = 0; c0 < ncol; c0 += chunk) {
+    const int nc = std::min(chunk, ncol - c0);
+    offset_gases(gases, ngas, (size_t)c0, L, gs);
+    CloudIn c1;
+    if (cl) { c1 = *cl; c1.clwp += (size_t)c0 * L; c1.ciwp += (size_t)c0 * L; c1.reliq += (size_t)c0 * L; c1.reice += (size_t)c0 * L; }
+    if (int rc = sw_chunk(ctx, kd, models, nc, L, top_at_1, play_d + (size_t)c0 * L, plev_d + (size_t)c0 * (L + 1),
+                          tlay_d + (size_t)c0 * L, mu0_d + c0, sfc_alb_d + c0, tsi_d ? tsi_d + c0 : nullptr, gs.data(), ngas,
+                          flux_up_d + (size_t)c0 * (L + 1), flux_dn_d + (size_t)c0 * (L + 1),
+                          flux_dn_dir_d + (size_t)c0 * (L + 1), (float*)ctx->ws, cl ? &c1 : nullptr))
       return rc;
   }
   return 0;
@@ -209,24 +321,21 @@ extern "C" int rrnn_sw_fluxes(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrn
                               const float* sfc_alb_d, const float* tsi_d, const rrnn_gas_t* gases, int ngas,
                               float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d) {
   rrnn::NvtxRange nvtx_("clear_sky_total (SW)");
-  RRNN_CHECK(ctx && kd && models, "rrnn_sw_fluxes: null handle");
-  RRNN_CHECK(kd->d_solar_source, "rrnn_sw_fluxes: k-distribution has no solar source");
-  if (ncol <= 0) return 0;
-  RRNN_CUDA(cudaSetDevice(ctx->device));
-  const int G = kd->ngpt, L = nlay;
-  int chunk = pick_chunk(ctx, ncol, sw_ws_bytes(G, L, 1));
-  if (int rc = ensure_ws_retry(ctx, chunk, [&](int c) { return sw_ws_bytes(G, L, c); })) return rc;
-  std::vector<rrnn_gas_t> gs;
-  for (int c0 = 0; c0 < ncol; c0 += chunk) {
-    const int nc = std::min(chunk, ncol - c0);
-    offset_gases(gases, ngas, (size_t)c0, L, gs);
-    if (int rc = sw_chunk(ctx, kd, models, nc, L, top_at_1, play_d + (size_t)c0 * L, plev_d + (size_t)c0 * (L + 1),
-                          tlay_d + (size_t)c0 * L, mu0_d + c0, sfc_alb_d + c0, tsi_d ? tsi_d + c0 : nullptr, gs.data(), ngas,
-                          flux_up_d + (size_t)c0 * (L + 1), flux_dn_d + (size_t)c0 * (L + 1),
-                          flux_dn_dir_d + (size_t)c0 * (L + 1), (float*)ctx->ws))
-      return rc;
-  }
-  return 0;
+  return sw_fluxes_dev(ctx, kd, models, ncol, nlay, top_at_1, play_d, plev_d, tlay_d, mu0_d, sfc_alb_d, tsi_d, gases, ngas, flux_up_d, flux_dn_d,
+                       flux_dn_dir_d, nullptr);
+}
+
+extern "C" int rrnn_sw_fluxes_allsky(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models,
+                                     const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, const float* play_d,
+                                     const float* plev_d, const float* tlay_d, const float* mu0_d, const float* sfc_alb_d, const float* tsi_d,
+                                     const rrnn_gas_t* gases, int ngas, const float* clwp_d, const float* ciwp_d, const float* reliq_d,
+                                     const float* reice_d, float* flux_up_d, float* flux_dn_d, float* flux_dn_dir_d) {
+  rrnn::NvtxRange nvtx_("cloudy_sky_total");
+  RRNN_CHECK(cloud_optics && clwp_d && ciwp_d && reliq_d && reice_d, "cloud optics: no data has been initialized");
+  CloudIn cl;
+  cl.lut = cloud_optics; cl.clwp = clwp_d; cl.ciwp = ciwp_d; cl.reliq = reliq_d; cl.reice = reice_d;
+  return sw_fluxes_dev(ctx, kd, models, ncol, nlay, top_at_1, play_d, plev_d, tlay_d, mu0_d, sfc_alb_d, tsi_d, gases, ngas, flux_up_d, flux_dn_d,
+                       flux_dn_dir_d, &cl);
 }
 
 // ---- host-buffer drivers ---------------------------------------------------------------------------
@@ -281,7 +390,8 @@ int ensure_pinned(rrnn_ctx_t* ctx, size_t bytes) {
 // array, filled and drained by a few host threads while the GPU works on the neighbouring chunks.
 static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
                              int ncol, int L, int top_at_1, int nang, std::vector<HostField>& fields,
-                             const rrnn_gas_t* gases, int ngas, float* const* out_host, int nout) {
+                             const rrnn_gas_t* gases, int ngas, float* const* out_host, int nout,
+                             const rrnn_cloud_lut_t* cloud_optics = nullptr) {   // all-sky: fields[6..9] = clwp, ciwp, reliq, reice
   const int G = kd->ngpt;
   // 2-D gas fields are appended to the staged fields
   std::vector<int> gas_field(ngas, -1);
@@ -301,7 +411,7 @@ static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, c
   for (int o = 0; o < nout; ++o) { out_pageable[o] = !is_pinned(out_host[o]); nout_pageable += out_pageable[o] ? 1 : 0; }
   const size_t out_per_col = (size_t)nout * (L + 1);
   const bool compact = lw && lw_compact(ctx, kd, models, nmodels, L);
-  const size_t opt_per_col = lw ? lw_ws_bytes(G, L, 1, compact) : sw_ws_bytes(G, L, 1);
+  const size_t opt_per_col = (lw ? lw_ws_bytes(G, L, 1, compact) : sw_ws_bytes(G, L, 1)) + (cloud_optics ? cld_ws_bytes(L, 1, !lw) : 0);
   int chunk = pick_chunk(ctx, ncol, opt_per_col + 8 * (in_per_col + out_per_col));
   size_t gas1d_floats = 0;
   for (int g = 0; g < ngas; ++g) if (gases[g].ndims == 1) gas1d_floats += align256((size_t)L);
@@ -311,7 +421,7 @@ static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, c
     n += 2 * (size_t)nout * align256((size_t)(L + 1) * c);
     return n;
   };
-  auto opt_bytes_of = [&](int c) { return lw ? lw_ws_bytes(G, L, c, compact) : sw_ws_bytes(G, L, c); };
+  auto opt_bytes_of = [&](int c) { return (lw ? lw_ws_bytes(G, L, c, compact) : sw_ws_bytes(G, L, c)) + (cloud_optics ? cld_ws_bytes(L, c, !lw) : 0); };
   if (int rc = ensure_ws_retry(ctx, chunk, [&](int c) { return opt_bytes_of(c) + 4 * (stage_floats_of(c) + gas1d_floats); })) return rc;
   const size_t opt_bytes = opt_bytes_of(chunk);
   float* p = (float*)((char*)ctx->ws + opt_bytes);
@@ -382,14 +492,16 @@ static int run_host_pipeline(rrnn_ctx_t* ctx, bool lw, const rrnn_kdist_t* kd, c
       else if (gases[g].ndims == 1) gs[g].conc = gas1d[g];
     }
     int rc;
+    CloudIn cl;
+    if (cloud_optics) { cl.lut = cloud_optics; cl.clwp = fields[6].dev[b]; cl.ciwp = fields[7].dev[b]; cl.reliq = fields[8].dev[b]; cl.reice = fields[9].dev[b]; }
     if (lw) {
       rc = lw_chunk(ctx, kd, models, nmodels, nc, L, top_at_1, nang, fields[0].dev[b], fields[1].dev[b], fields[2].dev[b],
                     fields[3].host ? fields[3].dev[b] : nullptr, fields[4].dev[b], fields[5].dev[b], gs.data(), ngas, outd[b][0],
-                    outd[b][1], (float*)ctx->ws);
+                    outd[b][1], (float*)ctx->ws, cloud_optics ? &cl : nullptr);
     } else {
       rc = sw_chunk(ctx, kd, models, nc, L, top_at_1, fields[0].dev[b], fields[1].dev[b], fields[2].dev[b], fields[3].dev[b],
                     fields[4].dev[b], fields[5].host ? fields[5].dev[b] : nullptr, gs.data(), ngas, outd[b][0], outd[b][1],
-                    outd[b][2], (float*)ctx->ws);
+                    outd[b][2], (float*)ctx->ws, cloud_optics ? &cl : nullptr);
     }
     if (rc) { drain(); return rc; }
     RRNN_PIPE(cudaEventRecord(ctx->ev[2 + b], s_cmp));
@@ -440,4 +552,45 @@ extern "C" int rrnn_sw_fluxes_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, cons
   std::vector<HostField> f = {{play, L, {}, false, {}}, {plev, L + 1, {}, false, {}}, {tlay, L, {}, false, {}}, {mu0, 1, {}, false, {}}, {sfc_alb, 1, {}, false, {}}, {tsi, 1, {}, false, {}}};
   float* outs[3] = {flux_up, flux_dn, flux_dn_dir};
   return run_host_pipeline(ctx, false, kd, models, 2, ncol, nlay, top_at_1, 1, f, gases, ngas, outs, 3);
+}
+
+// The all-sky pass with HOST buffers (examples/all-sky/rrtmgp_allsky.F90:366-446 for all columns at once): the clear-sky pipeline
+// above with four more staged fields -- cloud liquid / ice water path and effective radii, (nlay,ncol) -- cloud optics by band
+// on the device and the increment folded into the solvers.
+extern "C" int rrnn_lw_fluxes_allsky_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels,
+                                          const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, int n_gauss_angles,
+                                          const float* play, const float* plev, const float* tlay, const float* tlev, const float* tsfc,
+                                          const float* sfc_emis, const rrnn_gas_t* gases, int ngas, const float* clwp, const float* ciwp,
+                                          const float* reliq, const float* reice, float* flux_up, float* flux_dn) {
+  rrnn::NvtxRange nvtx_("cloudy_sky_total");
+  RRNN_CHECK(ctx && kd && models && play && plev && tlay && tsfc && sfc_emis && flux_up && flux_dn, "rrnn_lw_fluxes_allsky_host: null argument");
+  RRNN_CHECK(cloud_optics && clwp && ciwp && reliq && reice, "cloud optics: no data has been initialized");
+  RRNN_CHECK(n_gauss_angles >= 1 && n_gauss_angles <= 4, "rte_lw: n_gauss_angles must be in 1..4");
+  if (ncol <= 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const size_t L = nlay;
+  std::vector<HostField> f = {{play, L, {}, false, {}}, {plev, L + 1, {}, false, {}}, {tlay, L, {}, false, {}}, {tlev, L + 1, {}, false, {}},
+                              {tsfc, 1, {}, false, {}}, {sfc_emis, 1, {}, false, {}}, {clwp, L, {}, false, {}}, {ciwp, L, {}, false, {}},
+                              {reliq, L, {}, false, {}}, {reice, L, {}, false, {}}};
+  float* outs[2] = {flux_up, flux_dn};
+  return run_host_pipeline(ctx, true, kd, models, nmodels, ncol, nlay, top_at_1, n_gauss_angles, f, gases, ngas, outs, 2, cloud_optics);
+}
+
+extern "C" int rrnn_sw_fluxes_allsky_host(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models,
+                                          const rrnn_cloud_lut_t* cloud_optics, int ncol, int nlay, int top_at_1, const float* play,
+                                          const float* plev, const float* tlay, const float* mu0, const float* sfc_alb, const float* tsi,
+                                          const rrnn_gas_t* gases, int ngas, const float* clwp, const float* ciwp, const float* reliq,
+                                          const float* reice, float* flux_up, float* flux_dn, float* flux_dn_dir) {
+  rrnn::NvtxRange nvtx_("cloudy_sky_total");
+  RRNN_CHECK(ctx && kd && models && play && plev && tlay && mu0 && sfc_alb && flux_up && flux_dn && flux_dn_dir, "rrnn_sw_fluxes_allsky_host: null argument");
+  RRNN_CHECK(cloud_optics && clwp && ciwp && reliq && reice, "cloud optics: no data has been initialized");
+  RRNN_CHECK(kd->d_solar_source, "rrnn_sw_fluxes_allsky_host: k-distribution has no solar source");
+  if (ncol <= 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const size_t L = nlay;
+  std::vector<HostField> f = {{play, L, {}, false, {}}, {plev, L + 1, {}, false, {}}, {tlay, L, {}, false, {}}, {mu0, 1, {}, false, {}},
+                              {sfc_alb, 1, {}, false, {}}, {tsi, 1, {}, false, {}}, {clwp, L, {}, false, {}}, {ciwp, L, {}, false, {}},
+                              {reliq, L, {}, false, {}}, {reice, L, {}, false, {}}};
+  float* outs[3] = {flux_up, flux_dn, flux_dn_dir};
+  return run_host_pipeline(ctx, false, kd, models, 2, ncol, nlay, top_at_1, 1, f, gases, ngas, outs, 3, cloud_optics);
 }

@@ -625,3 +625,161 @@ extern "C" int rrnn_rte_sw(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int to
   return rrnn_sw_solver_2stream(ctx, ngpt, nlay, ncol, top_at_1, inc_flux_d, inc_flux_dif_d, tau_d, ssa_d, g_d, mu0_d,
                                 sfc_alb_dir_gpt_d, sfc_alb_dif_gpt_d, flux_up_d, flux_dn_d, flux_dn_dir_d);
 }
+
+// ---------------------------------------------------------------------------------------------------- clouds folded into the solvers
+// `clouds%increment(atmos)` (and, for the shortwave, the delta-scaled by-band properties it adds) is not
+// a pass over the (ngpt,nlay,ncol) arrays here.  A small kernel turns the by-band cloud properties (16 times fewer numbers) into
+// padded table rows, and the packed solvers add them to the gas optical properties in registers (lw_solver_v6<.., CLD>,
+// sw_solver_v6<.., GM = 2>): the all-sky path reads what the clear-sky path reads plus 64 / 192 bytes per layer and column.
+namespace rrnn {
+
+// LW: tau_c (nbnd,nlay,ncol) -> rows of 16 floats (bands beyond nbnd zero)
+__global__ void cloud_rows_lw_kernel(size_t nsmp, int nbnd, const float* __restrict__ tau, float* __restrict__ rows) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsmp * 16) return;
+  const size_t s = i >> 4;
+  const int b = (int)(i & 15);
+  rows[i] = b < nbnd ? tau[s * nbnd + b] : 0.0f;
+}
+// SW: (tau_c, ssa_c, g_c) (nbnd,nlay,ncol) -> rows of 48 floats: t2 = tau_c | s2 = tau_c*ssa_c | sg2 = tau_c*ssa_c*g_c, the operands
+// of inc_2stream_by_2stream_bybnd (rte/kernels/mo_optical_props_kernels.F90:470-478) that do not depend on the g-point
+__global__ void cloud_rows_sw_kernel(size_t nsmp, int nbnd, const float* __restrict__ tau, const float* __restrict__ ssa,
+                                     const float* __restrict__ g, float* __restrict__ rows) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nsmp * 16) return;
+  const size_t s = i >> 4;
+  const int b = (int)(i & 15);
+  float t2 = 0.0f, s2 = 0.0f, sg2 = 0.0f;
+  if (b < nbnd) {
+    t2 = tau[s * nbnd + b];
+    s2 = __fmul_rn(t2, ssa[s * nbnd + b]);
+    sg2 = __fmul_rn(s2, g[s * nbnd + b]);
+  }
+  rows[s * 48 + b] = t2;
+  rows[s * 48 + 16 + b] = s2;
+  rows[s * 48 + 32 + b] = sg2;
+}
+
+int cloud_rows_lw(rrnn_ctx_t* ctx, size_t nsmp, int nbnd, const float* tau_bnd_d, float* rows_d) {
+  RRNN_CHECK(nbnd >= 1 && nbnd <= 16, "clouds: the packed solvers take at most 16 bands");
+  cloud_rows_lw_kernel<<<(unsigned)((nsmp * 16 + 255) / 256), 256, 0, ctx->stream>>>(nsmp, nbnd, tau_bnd_d, rows_d);
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+int cloud_rows_sw(rrnn_ctx_t* ctx, size_t nsmp, int nbnd, const float* tau_bnd_d, const float* ssa_bnd_d, const float* g_bnd_d, float* rows_d) {
+  RRNN_CHECK(nbnd >= 1 && nbnd <= 16, "clouds: the packed solvers take at most 16 bands");
+  cloud_rows_sw_kernel<<<(unsigned)((nsmp * 16 + 255) / 256), 256, 0, ctx->stream>>>(nsmp, nbnd, tau_bnd_d, ssa_bnd_d, g_bnd_d, rows_d);
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// lw_solver_noscat on (tau + clouds), sources materialised (planck_* null) or factored; -1 (no message) = the packed kernel does
+// not take this call
+int lw_solver_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int nmus, const float* Ds, const float* weights,
+                     const float* inc_flux_d, const float* tau_d, const float* lay_d, const float* lev_d, const float* planck_lay_d,
+                     const float* planck_lev_d, const float* sfc_emis_gpt_d, const float* sfc_source_d, const float* cld_rows_d,
+                     float* flux_up_d, float* flux_dn_d) {
+  if (ncol == 0) return 0;
+  if (ctx->solver_variant != 0) return -1;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  LwParams p{};
+  p.ngpt = kd->ngpt; p.nlay = nlay; p.ncol = ncol; p.top_at_1 = top_at_1 ? 1 : 0; p.nmus = nmus;
+  p.bug_compat = ctx->lw_source_bug_compat;
+  p.nchunks = (kd->ngpt + 31) / 32;
+  for (int i = 0; i < nmus; ++i) { p.Ds[i] = Ds[i]; p.wts[i] = weights[i]; }
+  p.inc_flux = inc_flux_d; p.tau = tau_d; p.lay_source = lay_d; p.lev_source = lev_d; p.planck_lay = planck_lay_d; p.planck_lev = planck_lev_d;
+  p.gpt2band = kd->d_gpt2band; p.cld_tau = cld_rows_d;
+  p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
+  const int ps = prof_begin(ctx, K_LW_SOLVER);
+  const int rc = launch_lw_v6(ctx, p);
+  prof_end(ctx, K_LW_SOLVER, ps);
+  if (rc != 0) return rc;
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+int sw_solver_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, const float* inc_flux_d, const float* inc_flux_dif_d,
+                     const float* tau_d, const float* ssa_d, const float* cld_rows_d, const float* mu0_d, const float* alb_dir_d,
+                     const float* alb_dif_d, float* flux_up_d, float* flux_dn_d, float* flux_dir_d) {
+  if (ncol == 0) return 0;
+  if (ctx->solver_variant != 0) return -1;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  SwParams p{};
+  p.ngpt = kd->ngpt; p.nlay = nlay; p.ncol = ncol; p.top_at_1 = top_at_1 ? 1 : 0;
+  p.nchunks = (kd->ngpt + 31) / 32;
+  p.inc_flux = inc_flux_d; p.inc_flux_dif = inc_flux_dif_d; p.tau = tau_d; p.ssa = ssa_d; p.g = nullptr; p.mu0 = mu0_d;
+  p.cld = cld_rows_d; p.gpt2band = kd->d_gpt2band;
+  p.alb_dir = alb_dir_d; p.alb_dif = alb_dif_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d; p.flux_dir = flux_dir_d;
+  const int ps = prof_begin(ctx, K_SW_SOLVER);
+  const int rc = launch_sw_v6(ctx, p, ctx->fast_math || ctx->sw_fast_math);
+  prof_end(ctx, K_SW_SOLVER, ps);
+  if (rc != 0) return rc;
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace rrnn
+
+static const char* kCloudShapeMsg =
+    ": this shape is not taken by the packed solver (ngpt a multiple of 4 and <= 512, nlay >= 8, 16-byte aligned arrays, default "
+    "solver_variant / fast_math); apply increment() and call the plain entry point";
+
+// rte_lw(atmos, ...) with `clouds%increment(atmos)` still pending: cld_tau_bnd_d is the by-band cloud optical depth (nbnd,nlay,ncol)
+extern "C" int rrnn_rte_lw_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,
+                                  const float* inc_flux_d, const float* tau_d, const float* lay_source_d, const float* lev_source_d,
+                                  const float* sfc_source_d, const float* sfc_emis_d, const float* cld_tau_bnd_d, float* flux_up_d,
+                                  float* flux_dn_d) {
+  rrnn::NvtxRange nvtx_("rte_lw");
+  RRNN_CHECK(ctx && kd && tau_d && lay_source_d && lev_source_d && sfc_source_d && sfc_emis_d && cld_tau_bnd_d && flux_up_d && flux_dn_d,
+             "rte_lw: null argument");
+  static const float gauss_Ds[4][4] = {{1.66f, 0.f, 0.f, 0.f},
+                                       {1.18350343f, 2.81649655f, 0.f, 0.f},
+                                       {1.09719858f, 1.69338507f, 4.70941630f, 0.f},
+                                       {1.06056257f, 1.38282560f, 2.40148179f, 7.15513024f}};
+  static const float gauss_wts[4][4] = {{0.5f, 0.f, 0.f, 0.f},
+                                        {0.3180413817f, 0.1819586183f, 0.f, 0.f},
+                                        {0.2009319137f, 0.2292411064f, 0.0698269799f, 0.f},
+                                        {0.1355069134f, 0.2034645680f, 0.1298475476f, 0.0311809710f}};
+  RRNN_CHECK(n_gauss_angles <= 4, "rte_lw: asking for too many quadrature points for no-scattering calculation");
+  RRNN_CHECK(n_gauss_angles >= 1, "rte_lw: have to ask for at least one quadrature point for no-scattering calculation");
+  if (ncol == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const int ngpt = kd->ngpt;
+  const size_t n = (size_t)ngpt * ncol, nsmp = (size_t)ncol * nlay;
+  float* tmp = nullptr;   // sfc_emis by g-point, then the cloud rows
+  RRNN_CUDA(cudaMallocAsync((void**)&tmp, (((n + 63) & ~(size_t)63) + nsmp * 16) * sizeof(float), ctx->stream));
+  float* rows = tmp + ((n + 63) & ~(size_t)63);
+  expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(kd->nbnd, ngpt, ncol, kd->d_gpt2band, sfc_emis_d, tmp);
+  int rc = cloud_rows_lw(ctx, nsmp, kd->nbnd, cld_tau_bnd_d, rows);
+  if (rc == 0)
+    rc = lw_solver_clouds(ctx, kd, nlay, ncol, top_at_1, n_gauss_angles, gauss_Ds[n_gauss_angles - 1], gauss_wts[n_gauss_angles - 1], inc_flux_d,
+                          tau_d, lay_source_d, lev_source_d, nullptr, nullptr, tmp, sfc_source_d, rows, flux_up_d, flux_dn_d);
+  cudaFreeAsync(tmp, ctx->stream);
+  if (rc < 0) return fail(std::string("rte_lw (clouds)") + kCloudShapeMsg);
+  return rc;
+}
+
+// rte_sw(atmos, ...) with `clouds%increment(atmos)` still pending on gas optical properties whose g is 0 (the NN gas optics):
+// cld_*_bnd_d are the (delta-scaled, if the caller wants that) by-band cloud properties (nbnd,nlay,ncol)
+extern "C" int rrnn_rte_sw_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, const float* mu0_d,
+                                  const float* inc_flux_d, const float* sfc_alb_dir_gpt_d, const float* sfc_alb_dif_gpt_d,
+                                  const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* cld_tau_bnd_d,
+                                  const float* cld_ssa_bnd_d, const float* cld_g_bnd_d, float* flux_up_d, float* flux_dn_d,
+                                  float* flux_dn_dir_d) {
+  rrnn::NvtxRange nvtx_("rte_sw");
+  RRNN_CHECK(ctx && kd && mu0_d && inc_flux_d && sfc_alb_dir_gpt_d && sfc_alb_dif_gpt_d && tau_d && ssa_d && cld_tau_bnd_d && cld_ssa_bnd_d &&
+                 cld_g_bnd_d, "rte_sw: null argument");
+  RRNN_CHECK(flux_up_d && flux_dn_d && flux_dn_dir_d, "rte_sw: no space allocated for fluxes");
+  if (ncol == 0) return 0;
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const size_t nsmp = (size_t)ncol * nlay;
+  float* rows = nullptr;
+  RRNN_CUDA(cudaMallocAsync((void**)&rows, nsmp * 48 * sizeof(float), ctx->stream));
+  int rc = cloud_rows_sw(ctx, nsmp, kd->nbnd, cld_tau_bnd_d, cld_ssa_bnd_d, cld_g_bnd_d, rows);
+  if (rc == 0)
+    rc = sw_solver_clouds(ctx, kd, nlay, ncol, top_at_1, inc_flux_d, inc_flux_dif_d, tau_d, ssa_d, rows, mu0_d, sfc_alb_dir_gpt_d,
+                          sfc_alb_dif_gpt_d, flux_up_d, flux_dn_d, flux_dn_dir_d);
+  cudaFreeAsync(rows, ctx->stream);
+  if (rc < 0) return fail(std::string("rte_sw (clouds)") + kCloudShapeMsg);
+  return rc;
+}

@@ -305,6 +305,12 @@ __device__ __forceinline__ f2 ldg_scr(const uint8_t* p, uint64_t pol) {
   asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v.v) : "l"(p), "l"(pol) : "memory");
   return v;
 }
+#ifndef RRNN_SW_CLD_SKIP
+// all-sky SW, what a half group (4 layers x 64 g-points) that sees no cloud does: 0 = the increment like everybody else; 1 = skips it
+// and takes the g == 0 coefficient formulas (a second copy of the two-stream batch: 9.4 ms per 100 000 x 60 columns of the all-sky
+// benchmark -- the loop body outgrows the instruction cache); 2 = skips the increment only (7.9 ms; 8.2 ms for 0).  A/B on one B200.
+#define RRNN_SW_CLD_SKIP 2
+#endif
 #ifndef RRNN_V6_SW_S
 #define RRNN_V6_SW_S 3  // stages of the input ring (groups of 8 layers in flight ahead of the downward sweep)
 #endif
@@ -344,14 +350,23 @@ __device__ __forceinline__ float tr_reduce(const float (&v)[N], float* tr, int l
 // rows of the reverse-sweep scratch: three 256-byte segments (32 lanes x 8 B) per layer
 constexpr int SW6_ROW = 768, SW6_F = 256, SW6_A = 512;
 
-template <bool FAST, bool HAS_G, bool TOP>
+// GM: where the asymmetry parameter comes from.  0: g == 0 (the NN gas optics; nothing read), 1: a (ngpt,nlay,ncol) array,
+// 2: CLOUDS -- by-band cloud properties whose increment has not been applied (SwParams::cld: t2 | s2 | sg2, one 192-byte row per
+// layer): inc_2stream_by_2stream_bybnd (mo_optical_props_kernels.F90:453-485) on gas properties with g == 0 runs in registers,
+//   tau = tau1 + t2,  ssa = (tau1 ssa1 + s2) / max(eps, tau),  g = sg2 / max(eps, tau1 ssa1 + s2),
+// so the all-sky path neither rewrites tau / ssa nor materialises g.
+template <bool FAST, int GM, bool TOP>
 __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_ssa, const __grid_constant__ CUtensorMap tm_g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  constexpr int U = 8, S = HAS_G ? 2 : RRNN_V6_SW_S, SB = 2, H = 4, NH = U / H;  // groups of 8 layers (one TMA box), coefficients in halves of 4
-  static_assert(SB * U * SW6_ROW <= S * (HAS_G ? 3 : 2) * U * 256, "the upward sweep's stages live in the input ring");
+  constexpr bool HAS_G = GM != 0;
+  constexpr int NIN = GM == 1 ? 3 : 2;
+  // GM == 2: tau | ssa | the cloud rows (8 x 192 B), padded so that two stages hold the upward sweep's ring like the GM == 1 layout
+  constexpr int STAGE = GM == 2 ? 3 * 8 * 256 : NIN * 8 * 256;
+  constexpr int STAGE_TX = NIN * 8 * 256 + (GM == 2 ? 8 * 192 : 0);   // bytes the TMA unit delivers per stage
+  constexpr int U = 8, S = GM == 0 ? RRNN_V6_SW_S : 2, SB = 2, H = 4, NH = U / H;  // groups of 8 layers (one TMA box), coefficients in halves of 4
+  static_assert(SB * U * SW6_ROW <= S * STAGE, "the upward sweep's stages live in the input ring");
   const SwParams& p = pp.b;
-  constexpr int NIN = HAS_G ? 3 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
   const int G = p.ngpt, L = p.nlay;
   const uint64_t pol_in = policy_evict_first();
@@ -361,8 +376,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
   const int csize = (int)cluster.num_blocks();
 
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
-  uint8_t* in_ring = smem;                                                   // [S][NIN][U][256 B]: tau, ssa (, g)
-  float* tr = reinterpret_cast<float*>(in_ring + S * NIN * U * 256);         // [16][TR_PITCH]
+  uint8_t* in_ring = smem;                                                   // [S][STAGE]: tau, ssa (, g | cloud rows), U rows each
+  float* tr = reinterpret_cast<float*>(in_ring + S * STAGE);                 // [16][TR_PITCH]
   float* part = tr + 16 * TR_PITCH;                                          // [2 sets][3][L+1]
   const int part_set = 3 * (L + 1) + ((L + 1) & 1);                          // keeps the barriers 8-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
@@ -389,6 +404,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
   // lanes 8-15 / 24-31 quantity B; only lanes < 16 write
   const int ru = lane & 7;
   const bool rB = (lane & 8) != 0, rW = lane < 16;
+  // GM == 2: byte offsets of the bands of this lane's two g-points in a 64-byte table segment
+  uint32_t bo0 = 0, bo1 = 0;
+  if (GM == 2) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
+  auto band_pair = [&](const uint8_t* seg) { return mk2(*reinterpret_cast<const float*>(seg + bo0), *reinterpret_cast<const float*>(seg + bo1)); };
 
   int ncols_done = 0;
   for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
@@ -419,11 +438,12 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
         const int rl = box_start<TOP, U>(lay0, k, sh);
         if (elect_one()) {
           const uint32_t bar = bar_in + 8 * st;
-          const uint32_t dst = in_a + st * (NIN * U * 256);
-          mbar_expect_tx(bar, NIN * U * 256);
+          const uint32_t dst = in_a + st * STAGE;
+          mbar_expect_tx(bar, STAGE_TX);
           tma_load_2d(dst, &tm_tau, chunk * 64, rl, bar, pol_in);
           tma_load_2d(dst + U * 256, &tm_ssa, chunk * 64, rl, bar, pol_in);
-          if (HAS_G) tma_load_2d(dst + 2 * U * 256, &tm_g, chunk * 64, rl, bar, pol_in);
+          if (GM == 1) tma_load_2d(dst + 2 * U * 256, &tm_g, chunk * 64, rl, bar, pol_in);
+          if (GM == 2) tma_load_2d(dst + 2 * U * 256, &tm_g, 0, rl, bar, pol_in);   // (tm_g maps the (48,nlay,ncol) cloud rows)
         }
         __syncwarp();
       }
@@ -459,7 +479,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
       const uint32_t nk = n_in + (uint32_t)k;
       const uint32_t st = nk % S;
       mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
-      const uint8_t* base = in_ring + st * (NIN * U * 256) + lane_in;
+      const uint8_t* stg = in_ring + st * STAGE;
+      const uint8_t* base = stg + lane_in;
       int shl = 0, nvalid = U;
       if (TAIL) {
         box_start<TOP, U>(lay0, k, shl);
@@ -475,17 +496,43 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
           for (int uu = 0; uu < H; ++uu) { red[h * H + uu] = 0.0f; red[U + h * H + uu] = 0.0f; }
           continue;
         }
-        f2 tau[H], w0[H], gg[H];
+        f2 tau[H], w0[H], gg[H], t2[H];
+        bool cloud_here = false;
 #pragma unroll
         for (int uu = 0; uu < H; ++uu) {
           const int u = h * H + uu;
           const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
           tau[uu] = lds2(base + rl * 256);
           w0[uu] = lds2(base + U * 256 + rl * 256);
-          gg[uu] = HAS_G ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
+          gg[uu] = GM == 1 ? lds2(base + 2 * U * 256 + rl * 256) : splat2(0.0f);
+          if (GM == 2) {
+            t2[uu] = band_pair(stg + 2 * U * 256 + rl * 192);
+            cloud_here = cloud_here || lo2(t2[uu]) != 0.0f || hi2(t2[uu]) != 0.0f;
+          }
         }
         f2 Rdif[H], Tdif[H], Rdir[H], Tdir[H], Tnos[H];
-        two_stream2_batch<FAST, HAS_G, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+        // Clouds sit in a few contiguous layers of some columns: a half group none of whose 64 g-points x 4 layers sees cloud
+        // (warp-uniform) keeps the gas properties as they are -- tau + 0, ssa = (tau ssa) / tau up to its last bit, g = 0
+        const bool cloudy = GM == 2 && (RRNN_SW_CLD_SKIP == 0 || __any_sync(0xffffffffu, cloud_here));
+        if (GM == 2 && RRNN_SW_CLD_SKIP == 1 && !cloudy) {
+          two_stream2_batch<FAST, false, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+        } else {
+          if (GM == 2 && cloudy) {   // inc_2stream_by_2stream_bybnd with g1 == 0, same operation order (products first, then the sum)
+            const f2 eps = splat2(3.0f * 1.17549435e-38f);
+#pragma unroll
+            for (int uu = 0; uu < H; ++uu) {
+              const int u = h * H + uu;
+              const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
+              const uint8_t* crow = stg + 2 * U * 256 + rl * 192;
+              const f2 tau12 = tau[uu] + t2[uu];
+              const f2 scat = tau[uu] * w0[uu] + band_pair(crow + 64);
+              gg[uu] = div2<FAST>(band_pair(crow + 128), max2(eps, scat));
+              w0[uu] = div2<FAST>(scat, max2(eps, tau12));
+              tau[uu] = tau12;
+            }
+          }
+          two_stream2_batch<FAST, HAS_G, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+        }
 #pragma unroll
         for (int uu = 0; uu < H; ++uu) {
           const int u = h * H + uu;
@@ -608,17 +655,21 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
 // into registers; per-level sums by transposition through shared memory; a ragged last group computes only its layers.
 constexpr int LW6_ROW = 512, LW6_S = 256;
 
-template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT>
+// CLD: by-band cloud optical depths whose increment has not been applied (LwParams::cld_tau) ride along as one more 64-byte
+// table row per layer and are added to tau in registers -- the all-sky path never rewrites the (ngpt,nlay,ncol) array.
+template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT, bool CLD>
 __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev,
-                                                   const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv) {
+                                                   const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv,
+                                                   const __grid_constant__ CUtensorMap tm_cld) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int U = 8, S = 2, SB = 2;
   // one stage of the input ring.  Materialised: tau | lay_source | lev_source(ext rows), U rows of 256 B each.
   // COMPACT: tau (U rows) | pfrac (PFR rows: top-down sweeps also need the next layer's) | B_lay | B_lev(ext) (U rows of 64 B)
   constexpr int PFR = COMPACT ? (TOP ? U + 1 : U) : U;
   constexpr int OFF_PF = U * 256, OFF_3 = OFF_PF + PFR * 256, OFF_BV = OFF_3 + U * 64;
-  constexpr int STAGE = COMPACT ? OFF_BV + U * 64 : 3 * U * 256;
+  constexpr int OFF_CLD = COMPACT ? OFF_BV + U * 64 : 3 * U * 256;   // CLD: by-band cloud optical depth (U rows of 64 B)
+  constexpr int STAGE = OFF_CLD + (CLD ? U * 64 : 0);
   static_assert(SB * U * LW6_ROW <= S * STAGE, "the upward sweep's stages live in the input ring");
   const LwParams& p = pp.b;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
@@ -656,7 +707,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
   const uint32_t lane_in = (uint32_t)lane * 8u;   // byte offset of this lane's pair in a 256-byte row
   // COMPACT: byte offsets of the bands of this lane's two g-points in a 64-byte row of the Planck tables
   uint32_t bo0 = 0, bo1 = 0;
-  if (COMPACT) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
+  if (COMPACT || CLD) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
   auto band_pair = [&](const uint8_t* row) { return mk2(*reinterpret_cast<const float*>(row + bo0), *reinterpret_cast<const float*>(row + bo1)); };
   const int ru = lane & 7;      // the reduced value (layer within its group) this lane ends up with; lanes < 8 write
   const bool rW = lane < 8;
@@ -712,6 +763,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
             } else {
               tma_load_2d(dst + OFF_3, &tm_lev, chunk * 64, rv, bar, pol_in);
             }
+            if (CLD) tma_load_2d(dst + OFF_CLD, &tm_cld, 0, rl, bar, pol_in);
           }
           __syncwarp();
         }
@@ -761,6 +813,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
           const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
           const int rv = TAIL ? box_row<TOP, U>(u, shv) : (TOP ? u : U - 1 - u);
           tau[u] = lds2(base + rl * 256);
+          if (CLD) tau[u] = tau[u] + band_pair(stg + OFF_CLD + rl * 64);   // inc_1scalar_by_1scalar_bybnd
           if (COMPACT) {
             const f2 pf = lds2(base + OFF_PF + rl * 256);
             lay[u] = pf * band_pair(stg + OFF_3 + rl * 64);
@@ -987,8 +1040,11 @@ int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
   const bool compact = p.planck_lay != nullptr;
   constexpr int U = 8, S = 2, SB = 2;
   if (!lw_v5_supports(G, L)) return -1;
-  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source, (const void*)p.planck_lay, (const void*)p.planck_lev})
+  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source, (const void*)p.planck_lay, (const void*)p.planck_lev,
+                        (const void*)p.cld_tau})
     if ((uintptr_t)q & 15) return -1;
+  const bool cld = p.cld_tau != nullptr;
+  if (cld && (!p.gpt2band || ctx->fast_math)) return -1;   // (the cloud variants are built for the default arithmetic only)
   for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
     if ((uintptr_t)q & 7) return -1;
   v5::LwV5Params pp;
@@ -997,8 +1053,10 @@ int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
   const long long rows_lay = (long long)p.ncol * L, rows_lev = (long long)p.ncol * (L + 1);
   if (rows_lev >= (1LL << 31) - 8) return -1;
   const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
-  CUtensorMap tm_tau, tm_lay, tm_lev, tm_bl, tm_bv;
+  CUtensorMap tm_tau, tm_lay, tm_lev, tm_bl, tm_bv, tm_cld;
   if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, U)) return rc;
+  tm_cld = tm_tau;
+  if (cld) { if (int rc = v5::make_map(&tm_cld, p.cld_tau, 16, rows_lay, U, 16)) return rc; }
   size_t stage;
   if (compact) {
     if (!p.planck_lev || !p.gpt2band) return fail("lw_solver: incomplete compact source description");
@@ -1014,16 +1072,21 @@ int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
     tm_bl = tm_tau; tm_bv = tm_tau;
     stage = (size_t)3 * U * 256;
   }
+  if (cld) stage += (size_t)U * 64;
   const size_t smem = (size_t)S * stage + 8 * v5::TR_PITCH * 4 + 4 * (size_t)(L + 1) * 4 + (S + SB) * 8;
   const size_t per_cta = (size_t)L * v5::LW6_ROW;
-#define LW6(F, T, D, C) launch_clustered(ctx, v5::lw_solver_v6<F, T, D, C>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv)
-#define LW6C(F, T, D) (compact ? LW6(F, T, D, true) : LW6(F, T, D, false))
-  if (fast) {
-    if (top) return LW6C(true, true, true);
-    return dn_ext ? LW6C(true, false, true) : LW6C(true, false, false);
+#define LW6(F, T, D, C, CL) launch_clustered(ctx, v5::lw_solver_v6<F, T, D, C, CL>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv, tm_cld)
+#define LW6C(F, T, D, CL) (compact ? LW6(F, T, D, true, CL) : LW6(F, T, D, false, CL))
+  if (cld) {
+    if (top) return LW6C(false, true, true, true);
+    return dn_ext ? LW6C(false, false, true, true) : LW6C(false, false, false, true);
   }
-  if (top) return LW6C(false, true, true);
-  return dn_ext ? LW6C(false, false, true) : LW6C(false, false, false);
+  if (fast) {
+    if (top) return LW6C(true, true, true, false);
+    return dn_ext ? LW6C(true, false, true, false) : LW6C(true, false, false, false);
+  }
+  if (top) return LW6C(false, true, true, false);
+  return dn_ext ? LW6C(false, false, true, false) : LW6C(false, false, false, false);
 #undef LW6C
 #undef LW6
 }
@@ -1033,9 +1096,11 @@ int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 63) / 64;
   constexpr int U = 8, SB = 2;
-  const int S = p.g ? 2 : RRNN_V6_SW_S;  // (three input arrays: two stages already hold the upward sweep's ring)
+  const int gm = p.cld ? 2 : (p.g ? 1 : 0);
+  if (p.cld && (p.g || !p.gpt2band)) return -1;   // clouds are folded in on top of gas properties with g == 0 only
+  const int S = gm == 0 ? RRNN_V6_SW_S : 2;  // (three input arrays / two + cloud rows: two stages already hold the upward sweep's ring)
   if ((G & 3) || csize > 8 || L < U) return -1;
-  for (const void* q : {(const void*)p.tau, (const void*)p.ssa, (const void*)p.g})
+  for (const void* q : {(const void*)p.tau, (const void*)p.ssa, (const void*)p.g, (const void*)p.cld})
     if ((uintptr_t)q & 15) return -1;
   for (const void* q : {(const void*)p.inc_flux, (const void*)p.inc_flux_dif, (const void*)p.alb_dir, (const void*)p.alb_dif})
     if ((uintptr_t)q & 7) return -1;
@@ -1047,19 +1112,18 @@ int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   CUtensorMap tm_tau, tm_ssa, tm_g;
   if (int rc = v5::make_map(&tm_tau, p.tau, G, rows, U)) return rc;
   if (int rc = v5::make_map(&tm_ssa, p.ssa, G, rows, U)) return rc;
-  if (p.g) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, U)) return rc; }
+  if (gm == 1) { if (int rc = v5::make_map(&tm_g, p.g, G, rows, U)) return rc; }
+  else if (gm == 2) { if (int rc = v5::make_map(&tm_g, p.cld, 48, rows, U, 48)) return rc; }
   else tm_g = tm_ssa;
-  const int nin = p.g ? 3 : 2;
-  const size_t smem = (size_t)S * nin * U * 256 + 16 * v5::TR_PITCH * 4 + 2 * (size_t)(3 * (L + 1) + 1) * 4 + (S + SB) * 8;
+  const size_t stage = (size_t)(gm == 0 ? 2 : 3) * U * 256;
+  const size_t smem = (size_t)S * stage + 16 * v5::TR_PITCH * 4 + 2 * (size_t)(3 * (L + 1) + 1) * 4 + (S + SB) * 8;
   const size_t per_cta = (size_t)L * v5::SW6_ROW;
   const bool top = p.top_at_1 != 0;
-#define SW6(F, HG, T) launch_clustered(ctx, v5::sw_solver_v6<F, HG, T>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
-  if (fast) {
-    if (p.g) return top ? SW6(true, true, true) : SW6(true, true, false);
-    return top ? SW6(true, false, true) : SW6(true, false, false);
-  }
-  if (p.g) return top ? SW6(false, true, true) : SW6(false, true, false);
-  return top ? SW6(false, false, true) : SW6(false, false, false);
+#define SW6(F, GMODE, T) launch_clustered(ctx, v5::sw_solver_v6<F, GMODE, T>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
+#define SW6T(F, GMODE) (top ? SW6(F, GMODE, true) : SW6(F, GMODE, false))
+  if (fast) return gm == 2 ? SW6T(true, 2) : (gm == 1 ? SW6T(true, 1) : SW6T(true, 0));
+  return gm == 2 ? SW6T(false, 2) : (gm == 1 ? SW6T(false, 1) : SW6T(false, 0));
+#undef SW6T
 #undef SW6
 }
 }  // namespace rrnn

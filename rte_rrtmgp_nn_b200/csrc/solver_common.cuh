@@ -142,6 +142,9 @@ struct LwParams {
   const float* planck_lay = nullptr;  // (16,nlay,ncol)   band Planck function at T_lay
   const float* planck_lev = nullptr;  // (16,nlay+1,ncol) ... at T_lev
   const int* gpt2band = nullptr;      // (ngpt) 0-based band of each g-point
+  // clouds whose increment has not been applied to tau (packed kernel only; null otherwise): tau += cld_tau(band(g)) happens in
+  // the solver's registers (inc_1scalar_by_1scalar_bybnd, rte/kernels/mo_optical_props_kernels.F90:358-378); needs gpt2band
+  const float* cld_tau = nullptr;     // (16,nlay,ncol) by-band cloud optical depth, rows padded to 16 bands
 };
 
 
@@ -159,6 +162,11 @@ struct SwParams {
   float* flux_dn;
   float* flux_dir;
   float* scratch;  // GBUF: nCTA * 3 * L * 32 floats
+  // clouds whose increment has not been applied (packed kernel only; null otherwise; requires g == null, i.e. gas g = 0):
+  // inc_2stream_by_2stream_bybnd (rte/kernels/mo_optical_props_kernels.F90:453-485) happens in the solver's registers from the
+  // by-band products t2 = tau_c | s2 = tau_c ssa_c | sg2 = tau_c ssa_c g_c, three 16-band segments per (layer, column) row
+  const float* cld = nullptr;         // (48,nlay,ncol)
+  const int* gpt2band = nullptr;      // (ngpt) 0-based band of each g-point
 };
 
 

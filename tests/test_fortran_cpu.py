@@ -165,7 +165,7 @@ def looks_like(actual, decl, is_array):
 def test_fortran_callers_match_the_binding():
     blocks = binding_blocks()
     helper = {"rrnn_error_msg": 1, "rrnn_ctx": 0, "rrnn_select_device": 1, "rrnn_shutdown": 0, "rrnn_fill_zero": 1}
-    own = {"rrnn_lw", "rrnn_sw", "rrnn_lw_multi", "rrnn_sw_multi"}
+    own = {"rrnn_lw", "rrnn_sw", "rrnn_lw_multi", "rrnn_sw_multi", "rrnn_lw_allsky", "rrnn_sw_allsky"}
     ncalls = 0
     for f in CALLERS:
         for st in logical_lines(os.path.join(FORTRAN, f)):

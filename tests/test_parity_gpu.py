@@ -722,7 +722,17 @@ def test_cloud_optics_increment_delta_scale(gpu_ctx):
                 assert np.allclose(got.cpu().numpy(), w, rtol=2e-5, atol=1e-7)
 
 
-def test_all_sky_fluxes_match_oracle(gpu_ctx):
+@pytest.fixture(params=[True, False], ids=["increment_in_solver", "increment_eager"])
+def fuse_clouds(request):
+    """clouds%increment(atmos) deferred into the solvers (the default) or applied at once as a pass over
+    (ngpt,nlay,ncol): the reference's API and results either way."""
+    from rte_rrtmgp_nn_b200 import api
+    api.FUSE_CLOUD_INCREMENT = request.param
+    yield request.param
+    api.FUSE_CLOUD_INCREMENT = True
+
+
+def test_all_sky_fluxes_match_oracle(gpu_ctx, fuse_clouds):
     """BASELINE config 3 at test size, the body of examples/all-sky/rrtmgp_allsky.F90:366-446: NN gas optics -> LUT cloud
     optics (-> delta_scale, SW) -> clouds%increment(atmos) -> rte_lw / rte_sw (g != 0 in cloudy layers) -> broadband fluxes,
     against the same chain of oracle functions."""
@@ -751,9 +761,17 @@ def test_all_sky_fluxes_match_oracle(gpu_ctx):
     emis = np.repeat(atm["sfc_emis"][:, None], 16, 1)
     fl = api.ty_fluxes_broadband(mk(), mk())
     assert api.rte_lw(atmos, atm["top_at_1"], src, emis, fl) == ""
+    assert (atmos._pending is not None) == fuse_clouds      # fused: tau was never rewritten, the solver added the clouds itself
     ref = O.gas_optics_lw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["gases"], tlev=atm["tlev"])
     ctau = O.cloud_optics_lut(co.tables, cl["lwp"], cl["iwp"], cl["rel"], cl["rei"], False)
     tau = O.inc_1scalar_by_1scalar_bybnd(ref["tau"], ctau, kd["band_lims_gpt"])
+    if fuse_clouds:   # looking at atmos.tau applies the pending increment the ordinary way: the reference's state after increment()
+        gas_tau = atmos._tau.clone()
+        assert np.abs(atmos.tau.cpu().numpy() - tau).max() <= 4e-4 * np.abs(tau).max() and atmos._pending is None
+        assert not torch.equal(gas_tau, atmos.tau)
+        fl2 = api.ty_fluxes_broadband(mk(), mk())
+        assert api.rte_lw(atmos, atm["top_at_1"], src, emis, fl2) == ""          # the plain solver on the materialised sum
+        assert torch.equal(fl2.flux_up, fl.flux_up) and torch.equal(fl2.flux_dn, fl.flux_dn)   # same additions, same order
     rup, rdn = O.rte_lw(kd, atm["top_at_1"], tau, ref["lay_source"], ref["lev_source"], ref["sfc_source"], emis)
     assert np.abs(fl.flux_up.cpu().numpy() - rup).max() <= H.FLUX_TOL
     assert np.abs(fl.flux_dn.cpu().numpy() - rdn).max() <= H.FLUX_TOL
@@ -774,6 +792,7 @@ def test_all_sky_fluxes_match_oracle(gpu_ctx):
     alb = np.repeat(atm["sfc_alb"][:, None], 224, 1)
     fl = api.ty_fluxes_broadband(mk(), mk(), None, mk())
     assert api.rte_sw(atmos, atm["top_at_1"], atm["mu0"], toa, alb, alb, fl) == ""
+    assert (atmos._pending is not None) == fuse_clouds and (atmos._g is None) == fuse_clouds   # fused: g never materialised
 
     def chain(fast):
         r = O.gas_optics_sw(kd, onets, atm["play"], atm["plev"], atm["tlay"], atm["gases"], fast=fast)
@@ -785,6 +804,88 @@ def test_all_sky_fluxes_match_oracle(gpu_ctx):
     want, w64 = chain(False), chain("f64")
     for got, a, b, nm in zip((fl.flux_up, fl.flux_dn, fl.flux_dn_dir), want, w64, ("up", "dn", "dir")):
         H.assert_within_reference_noise(got.cpu().numpy(), a, b, H.FLUX_TOL, "all-sky SW flux_" + nm)
+    if fuse_clouds:   # materialise (atmos.g does) and solve again with the plain kernel: the same fluxes up to the divisions' last bit
+        _ = atmos.g
+        assert atmos._pending is None and float(atmos.g.abs().max()) > 0.1
+        fl2 = api.ty_fluxes_broadband(mk(), mk(), None, mk())
+        assert api.rte_sw(atmos, atm["top_at_1"], atm["mu0"], toa, alb, alb, fl2) == ""
+        for a, b in ((fl.flux_up, fl2.flux_up), (fl.flux_dn, fl2.flux_dn), (fl.flux_dn_dir, fl2.flux_dn_dir)):
+            assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("flip", [False, True], ids=["top_at_1", "bottom_up"])
+def test_fused_all_sky_drivers(gpu_ctx, flip):
+    """rrnn_{lw,sw}_fluxes_allsky[_host] (cloud optics + gas optics + delta-scaling + increment + rte for all columns in one call,
+    the increment inside the solvers) against the type-level API chain with the eager increment and against the oracle; host
+    buffers (pageable numpy) give the same bits as device buffers; several chunks give the same bits as one."""
+    import os
+    import bench
+    from rte_rrtmgp_nn_b200 import api, spectral, synth
+    torch = _torch()
+    ncol, nlay = 700, 60
+    atm = synth.make_atmosphere(ncol, nlay, seed=41)
+    cl = synth.make_clouds(atm)
+    if flip:
+        atm = synth.flip_vertical(atm)
+        cl = {k: np.ascontiguousarray(v[:, ::-1]) for k, v in cl.items()}
+    top = atm["top_at_1"]
+    lut = lambda band: api.load_cloud_lut_file(os.path.join(H.ROOT, "data", "cloud_optics", f"rrtmgp-cloud-optics-coeffs-{band}.nc"))
+    k_lw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_lw.load(spectral.synthetic_kdist_lw(256)) == ""
+    k_sw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_sw.load(spectral.synthetic_kdist_sw(224)) == ""
+    nl, ns = H.device_nets(gpu_ctx, H.LW_G256), H.device_nets(gpu_ctx, H.SW_G224)
+    co_lw = api.ty_cloud_optics(gpu_ctx); assert co_lw.load(**lut("lw")) == ""
+    co_sw = api.ty_cloud_optics(gpu_ctx); assert co_sw.load(**lut("sw")) == ""
+    gc = H.gas_concs(atm["gases"])
+    d = {k: torch.from_numpy(np.ascontiguousarray(atm[k])).cuda() for k in ("play", "plev", "tlay", "tlev", "tsfc", "sfc_emis", "sfc_alb", "mu0")}
+    gd = api.ty_gas_concs()
+    for k, v in atm["gases"].items():
+        gd.set_vmr(k, torch.from_numpy(np.ascontiguousarray(v)).cuda() if np.ndim(v) == 2 else float(v))
+    cd = {k: torch.from_numpy(v).cuda() for k, v in cl.items()}
+    mk = lambda: torch.empty((ncol, nlay + 1), device="cuda")
+    out = [mk() for _ in range(5)]
+
+    def fused():
+        api.lw_fluxes_allsky(k_lw, nl, co_lw, d["play"], d["plev"], d["tlay"], d["tsfc"], d["sfc_emis"], gd, cd, out[0], out[1], tlev=d["tlev"],
+                             top_at_1=top)
+        api.sw_fluxes_allsky(k_sw, ns, co_sw, d["play"], d["plev"], d["tlay"], d["mu0"], d["sfc_alb"], gd, cd, out[2], out[3], out[4], top_at_1=top)
+        return [o.cpu().numpy() for o in out]
+    one = fused()
+    gpu_ctx.set_chunk_columns(256)        # three chunks, the last one ragged
+    try:
+        three = fused()
+        host_lw = api.lw_fluxes_allsky_host(k_lw, nl, co_lw, atm["play"], atm["plev"], atm["tlay"], atm["tsfc"], atm["sfc_emis"], gc, cl,
+                                            tlev=atm["tlev"], top_at_1=top)
+        host_sw = api.sw_fluxes_allsky_host(k_sw, ns, co_sw, atm["play"], atm["plev"], atm["tlay"], atm["mu0"], atm["sfc_alb"], gc, cl, top_at_1=top)
+    finally:
+        gpu_ctx.set_chunk_columns(0)
+    for a, b, c in zip(one, three, list(host_lw) + list(host_sw)):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    # the oracle chain on a sample of the columns (bench.oracle_fluxes: the checker of the benchmark's all-sky line)
+    idx = np.arange(0, ncol, 29)
+    cfg = dict(lw=True, sw=True)
+    want = bench.oracle_fluxes(cfg, "g256", atm, idx, cl, {"lw": co_lw.tables, "sw": co_sw.tables})
+    names = ("lw_up", "lw_dn", "sw_up", "sw_dn", "sw_dir")
+    for nm, a in zip(names, one):
+        tol = H.FLUX_TOL if nm.startswith("lw") else 0.05     # SW: two fp32 evaluations (helpers.assert_within_reference_noise)
+        assert np.abs(a[idx] - want[nm]).max() <= tol, nm
+    assert np.abs(one[0][idx] - want["lw_up"]).max() <= H.FLUX_TOL
+    # the type-level API chain with the EAGER increment (the unfused kernels): same physics, different kernels
+    api.FUSE_CLOUD_INCREMENT = False
+    try:
+        atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(ncol, nlay, k_sw) == ""
+        clouds = api.ty_optical_props_2str(); assert clouds.alloc_2str(ncol, nlay, k_sw, by_band=True) == ""
+        toa = torch.empty((ncol, 224), device="cuda")
+        assert k_sw.gas_optics(d["play"], d["plev"], d["tlay"], gd, atmos, toa, neural_nets=ns) == ""
+        assert co_sw.cloud_optics(cd["lwp"], cd["iwp"], cd["rel"], cd["rei"], clouds) == ""
+        assert clouds.delta_scale() == "" and clouds.increment(atmos) == ""
+        alb = d["sfc_alb"][:, None].expand(ncol, 224).contiguous()
+        fl = api.ty_fluxes_broadband(mk(), mk(), None, mk())
+        assert api.rte_sw(atmos, top, d["mu0"], toa, alb, alb, fl) == ""
+    finally:
+        api.FUSE_CLOUD_INCREMENT = True
+    for a, b in zip(one[2:], (fl.flux_up, fl.flux_dn, fl.flux_dn_dir)):
+        b = b.cpu().numpy()
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
 
 
 def test_cloud_optics_pade_matches_oracle(gpu_ctx):
