@@ -94,26 +94,58 @@ def rfmip_inputs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  ONE long-lived `nvidia-smi -lms` process is started
+    when the sampler is constructed (before the warm-up): forking a helper from a process that holds gigabytes of pinned memory
+    inside the timed region stalls the launching thread for milliseconds (measured: 5 - 12 ms lost per step at 100 000 columns
+    whenever the fork fell into the region).  start() / stop_flag only mark which of the samples count."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=100):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
+        self.all = []          # (time, fields) of every line the helper printed
         self.stop_flag = False
+        self.t0 = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index),
+                                          "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.reader = threading.Thread(target=self._read, daemon=True)
+            self.reader.start()
+            t_end = time.perf_counter() + 5.0      # the helper's NVML start-up (~0.5 s) contends for driver locks: wait it out here
+            while not self.all and time.perf_counter() < t_end and self.proc.poll() is None:
+                time.sleep(0.02)
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        try:
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
+                if len(f) >= 7:
+                    self.all.append((time.perf_counter(), f))
+        except Exception:
+            pass
 
     def run(self):
+        self.t0 = time.perf_counter()
         while not self.stop_flag:
+            time.sleep(0.005)
+        t1 = time.perf_counter()
+        inside = [f for t, f in list(self.all) if self.t0 <= t <= t1 + 0.05]
+        if not inside and self.all:    # a timed region shorter than the sampling period: the sample nearest to it
+            inside = [min(list(self.all), key=lambda tf: abs(tf[0] - 0.5 * (self.t0 + t1)))[1]]
+        self.samples = inside
+        self.close()
+
+    def close(self):
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.proc.kill()
             except Exception:
                 pass
-            time.sleep(0.2)
+            self.proc = None
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
@@ -356,13 +388,28 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # The flux gather overlaps the next piece's kernels (below).  Optional cap on NCCL's CTAs (an experiment that lost; the
+        # solvers instead tolerate a co-running kernel by taking their columns dynamically, rte_solvers_tma.cu: NextColumns).
+        opts = None
+        if args.nccl_max_ctas > 0:
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(args.nccl_max_ctas)
+                opts.config.min_ctas = 1
+            except Exception:
+                opts = None
+        if opts is not None:
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
 
     stream = torch.cuda.Stream(device=dev)
     side = torch.cuda.Stream(device=dev)
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
     for k in ("fast_math", "solver_buffer", "sw_fast_math", "solver_variant", "solver_scratch_mb", "solver_warps", "lw_compact_source"):
         ctx.set_flag(k, getattr(args, k))
+    if world > 1:   # the ranks of one node share its host cores: the threads that stage pageable caller memory are divided among them
+        ctx.set_flag("host_copy_threads", max(2, min(8, (os.cpu_count() or 16) // world)))
     if args.chunk:
         ctx.set_chunk_columns(args.chunk)
     k_lw = api.ty_gas_optics_rrtmgp(ctx); k_lw.load(spectral.synthetic_kdist_lw(m["ngpt_lw"]))
@@ -442,6 +489,34 @@ def run_b200(args):
             for k, v in atm["gases"].items():
                 gc.set_vmr(k, gas_dev.get_vmr(k)[a:b] if np.ndim(v) == 2 else float(v))
             gas_piece.append(gc)
+        # The gather itself.  "nccl" (default): in-place all_gather_into_tensor per piece on a side stream, NCCL held to
+        # --nccl-max-ctas CTAs so that its kernel leaves the SMs to the persistent solver clusters of the next piece.
+        # "p2p" (experiment, kept): every rank pushes its slot of a piece into every peer's gather buffer with device-to-device copies
+        # through CUDA IPC peer mappings (copy engines, no SM at all; one 4-byte all_reduce after the last piece as the completion
+        # signal).  Correct, and the solvers run undisturbed -- but torch's cross-process copy reached only 26 GB/s on the 2-GPU box
+        # (345 MB per piece in 13 ms; profiles/r2o_n2_p2p.json), so the last piece's copies are exposed: 217 against 208 ms per pass.
+        peer = None
+        gather_mode = args.gather if world > 1 else "none"
+        if gather_mode == "p2p":
+            try:
+                from torch.multiprocessing.reductions import reduce_tensor
+                mine = [reduce_tensor(g) for g in gbuf]
+                everyone = [None] * world
+                dist.all_gather_object(everyone, mine)
+                peer = [[g if r == rank else fn(*a) for g, (fn, a) in zip(gbuf, everyone[r])] for r in range(world)]
+                for r in range(world):     # first touch of every peer mapping outside the timed region
+                    if r != rank:
+                        peer[r][0][rank, 0, :1].copy_(gbuf[0][rank, 0, :1])
+                torch.cuda.synchronize()
+                dist.barrier()
+            except Exception as e:   # no peer access / IPC on this box: NCCL does it
+                print(f"[bench] rank {rank}: p2p gather unavailable ({e}); using NCCL all_gather", file=sys.stderr)
+                peer, gather_mode = None, "nccl"
+            flag = torch.ones(1, dtype=torch.float32, device=dev)
+            modes = [None] * world
+            dist.all_gather_object(modes, gather_mode)
+            if any(mm != "p2p" for mm in modes):
+                peer, gather_mode = None, "nccl"
         ev_piece = [torch.cuda.Event() for _ in bounds]
         ev_g0 = [torch.cuda.Event(enable_timing=True) for _ in bounds]
         ev_g1 = [torch.cuda.Event(enable_timing=True) for _ in bounds]
@@ -488,7 +563,14 @@ def run_b200(args):
                     with torch.cuda.stream(side):
                         side.wait_event(ev_piece[i])
                         ev_g0[i].record(side)
-                        dist.all_gather_into_tensor(gbuf[i].view(world * nf, nmaxp[i], nlev), gbuf[i][rank])   # in place
+                        if peer is not None:
+                            for k in range(1, world):          # staggered targets: no two ranks push to the same peer at once
+                                r = (rank + k) % world
+                                peer[r][i][rank].copy_(gbuf[i][rank], non_blocking=True)
+                            if i == npiece - 1:
+                                dist.all_reduce(flag)           # ordered after this rank's pushes: completion = everybody's have landed
+                        else:
+                            dist.all_gather_into_tensor(gbuf[i].view(world * nf, nmaxp[i], nlev), gbuf[i][rank])   # in place
                         ev_g1[i].record(side)
             if world > 1:
                 ev_cmp_end.record(stream)
@@ -544,28 +626,31 @@ def run_b200(args):
             return float(t.item())
 
         # ---- warm-up, then the timed device-resident steps ----
+        sampler = ClockSampler(local_rank) if rank == 0 else None      # (its helper process is forked here, outside the timed region)
         for _ in range(args.warmup):
             step_device()
         barrier()
         launches0 = ctx.launch_count
         tc0, ff0 = ctx.nn_kernel_counts
         ctx.profile(True)
-        sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
         ms_dev = timed(step_device, args.steps)
         if rank == 0:
             sampler.stop_flag = True
+            sampler.join(timeout=2.0)
         prof = ctx.profile_read()
         ctx.profile(False)
         launches = ctx.launch_count - launches0
         tc1, ff1 = ctx.nn_kernel_counts
         ms_dev = max_over_ranks(ms_dev)
         res = dict(ncol=ncol, ncol_total=ncol_total, ms_dev=ms_dev, value=ncol_total / (ms_dev * 1e-3), prof=prof, launches=launches,
-                   clocks=sampler.summary(), nn_kernels={"tcgen05": tc1 - tc0, "fp32_ffma": ff1 - ff0})
+                   clocks=sampler.summary() if sampler is not None else None, nn_kernels={"tcgen05": tc1 - tc0, "fp32_ffma": ff1 - ff0})
         if world > 1:
-            res["nccl"] = {"collectives_per_step": npiece,
-                           "op": "all_gather_into_tensor (in place) of the rank's flux slots, per piece of the shard, on a side stream",
+            res["nccl"] = {"collectives_per_step": npiece if peer is None else 1, "gather": gather_mode,
+                           "op": ("all_gather_into_tensor (in place) of the rank's flux slots, per piece of the shard, on a side stream" if peer is None else
+                                  "per piece of the shard: device-to-device copies of the rank's flux slots into every peer's gather buffer (CUDA IPC "
+                                  "peer memory over NVLink, copy engines, side stream); one 4-byte NCCL all_reduce after the last piece as the completion signal"),
                            "bytes_received_per_rank_per_step": int(sum(4 * (world - 1) * nf * n * nlev for n in nmaxp)),
                            "ms_sum_of_collectives": float(sum(a.elapsed_time(b) for a, b in zip(ev_g0, ev_g1))),
                            "ms_exposed_after_last_kernel": float(max(0.0, ev_cmp_end.elapsed_time(ev_g1[-1]))),
@@ -591,10 +676,13 @@ def run_b200(args):
                     n_in += sum(per(k) for k in ("play", "plev", "tlay", "tlev", "tsfc", "sfc_emis")) + gas2d_n + (4 * nlay if cloudy else 0)
                 if do_sw:
                     n_in += sum(per(k) for k in ("play", "plev", "tlay", "mu0", "sfc_alb")) + (1 if "tsi" in in_keys else 0) + gas2d_n + (4 * nlay if cloudy else 0)
-            res["e2e"] = {"value": ncol_total / (e2e["pageable"] * 1e-3), "unit": "columns/s",
+            res["e2e"] = {"value": ncol_total / (e2e["pinned"] * 1e-3), "unit": "columns/s",
                           "h2d_bytes_per_step": int(4 * n_in * ncol), "d2h_bytes_per_step": int(4 * nf * ncol * nlev),
-                          "ms_per_step": e2e["pageable"],
-                          "host_memory": "pageable (plain numpy arrays; the library stages them through its pinned bounce ring)",
+                          "ms_per_step": e2e["pinned"],
+                          "host_memory": "pinned (page-locked caller buffers, the base contract's definition); pageable_value: the same calls on "
+                                         "plain numpy arrays -- what a Fortran host's allocate()d arrays are -- which the library stages through "
+                                         "its pinned bounce ring with a few host threads (bounded by host memory bandwidth when 8 ranks share a node)",
+                          "pageable_value": ncol_total / (e2e["pageable"] * 1e-3), "pageable_ms_per_step": e2e["pageable"],
                           "pinned_value": ncol_total / (e2e["pinned"] * 1e-3), "pinned_ms_per_step": e2e["pinned"],
                           "note": "per-rank bytes; wall clock around the synchronous host-buffer calls"}
 
@@ -717,6 +805,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["p2p", "nccl"], help="N > 1: how the flux slots reach the other ranks (see run_b200)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="N > 1: cap on the CTAs NCCL may use for the overlapped flux gather (0 = NCCL's default, which measured best: at 8 GPUs "
+                         "a cap of 4 / 2 CTAs stretched the gathers from 15 to 41 / 63 ms per pass, profiles/r2p_n8_ctas*.json)")
     ap.add_argument("--gather-pieces", type=int, default=4, help="N > 1: pieces of the rank's shard whose flux gathers overlap the next piece's kernels")
     ap.add_argument("--device-inputs", action="store_true",
                     help="tile the NUNIQUE distinct columns on the device instead of on the host (1e7-column runs: no 40 GB of pinned "

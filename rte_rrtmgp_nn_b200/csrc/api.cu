@@ -396,6 +396,7 @@ extern "C" int rrnn_ctx_destroy(rrnn_ctx_t* c) {
   cudaStreamSynchronize(c->stream);
   if (c->ws) cudaFree(c->ws);
   if (c->scratch) cudaFree(c->scratch);
+  if (c->col_counter) cudaFree(c->col_counter);
   if (c->pinned) cudaFreeHost(c->pinned);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& v : c->prof_ev) for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

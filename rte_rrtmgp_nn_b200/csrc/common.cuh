@@ -74,6 +74,7 @@ struct rrnn_ctx {
   int solver_warps = 0;       // solvers per CTA in the v5 kernels (0 = default)
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  int* col_counter = nullptr;  // the packed solvers' dynamic column assignment (one int, zeroed before every launch)
   int lw_compact_source = 1;  // fused LW path: sources stay factored between gas optics and solver (8 instead of 12 B per g-point and layer)
   int nn_tensor_cores = 1; // MLP variant: 1 = tcgen05 (fp16 hi/lo split operands, fp32 accumulation; default), 0 = fp32 FFMA
   int chunk_columns = 0;

@@ -68,10 +68,11 @@ __device__ __forceinline__ f2 rcp2(f2 x) {
   if (FAST) return r;
   return fma2(fnma2(x, r, splat2(1.0f)), r, r);
 }
-// a/b: q = a*r refined with one residual step (within ~1 ulp)
+// a/b: q = a*r with the raw MUFU reciprocal (relative error e ~ 2^-23), refined with one residual step: the corrected quotient
+// carries e^2 plus the rounding of its own FMA, i.e. it is within ~1 ulp whether or not r was refined first -- so r is not
 template <bool FAST>
 __device__ __forceinline__ f2 div2(f2 a, f2 b) {
-  const f2 r = rcp2<FAST>(b);
+  const f2 r = rcp2<true>(b);
   const f2 q = a * r;
   if (FAST) return q;
   return fma2(fnma2(b, q, a), r, q);

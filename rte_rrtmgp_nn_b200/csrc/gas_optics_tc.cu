@@ -4,17 +4,17 @@
 // epilogues; every output float written exactly once, neural/mod_network_rrtmgp.F90:125-317,
 // rrtmgp/kernels/mo_gas_optics_kernels.F90:615-683) as a warp-specialised, persistent, software-pipelined kernel:
 //
-//   one CTA per SM, 288 threads, walking tiles of 128 rows (= the 128 TMEM lanes);
+//   one CTA per SM, 416 threads, walking tiles of 128 rows (= the 128 TMEM lanes);
 //     warps 0-3  FRONT     thread = row: scaled inputs (log p, h2o^1/4, o3^1/4, min-max scaling) -> A operand of
 //                          layer 1; hidden epilogues (tcgen05.ld, bias, softsign, fp16 hi/lo split) -> A operand of
 //                          the next layer.  Runs about one tile ahead of the output epilogue.
-//     warps 4-7  EPILOGUE  thread = row: tcgen05.ld of 32 g-points of both networks at a time from a ring of TMEM
+//     warps 4-11 EPILOGUE  two groups of four warps on alternate jobs; thread = row: tcgen05.ld of 32 g-points of both networks at a time from a ring of TMEM
 //                          slots; (.)^8 * N_dry | pfrac^2 * Planck(T_lay), Planck(T_lev) | tau_abs+tau_ray, ssa in
 //                          registers; rows are staged in 128B-swizzled shared memory and written with TMA tensor stores
 //                          (cp.async.bulk.tensor.3d): no load/store instruction is spent on the 3 KB/row of output,
 //                          column boundaries inside a tile are handled by the tensor map's bounds (negative start
 //                          coordinates and rows beyond nlay are clipped by the TMA unit).
-//     warp 8     MMA       one thread issues every tcgen05.mma and commits to mbarriers.
+//     warp 12    MMA       one elected thread issues every tcgen05.mma and commits to mbarriers.
 //   LW rows run over (level, column) with nlay+1 rows per column: the extra row repeats the bottom layer and produces
 //   lev_source(nlay+1) (and the surface source when the surface is at layer nlay), so lev_source needs no special case.
 //   precision: every fp32 operand v is split v = hi + lo, hi = fp16(v), lo = fp16(v - hi) (22 mantissa bits) and each

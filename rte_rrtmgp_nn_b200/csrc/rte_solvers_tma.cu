@@ -99,7 +99,7 @@ __device__ __forceinline__ void exp_and_complement2(f2 x, f2& t, f2& omt) {
   unpack2(x, xx, xy);
   const bool sx = xx < 0.35f, sy = xy < 0.35f;
   omt = sel2(sx, sy, neg2(em1), splat2(1.0f) - e);
-  t = sel2(sx, sy, splat2(1.0f) + em1, e);
+  t = e;   // (exp2x is within ~1 ulp everywhere; only the complement needs the series)
 }
 
 // The reverse-sweep scratch is dead once the upward sweep has pulled a group back into shared memory: discarding its L2
@@ -138,6 +138,7 @@ struct LwV5Params {
   LwParams b;
   int ngroups;
   int warp_smem;  // bytes of shared memory per warp
+  int* next_col;  // dynamic column assignment (see next_columns)
 };
 
 // ---------------------------------------------------------------------------------------------------- SW
@@ -278,6 +279,7 @@ struct SwV5Params {
   SwParams b;
   int ngroups;
   int warp_smem;
+  int* next_col;
 };
 
 // ==================================================================================================== v6
@@ -347,6 +349,28 @@ __device__ __forceinline__ float tr_reduce(const float (&v)[N], float* tr, int l
   return t;
 }
 
+// Dynamic column assignment.  The clusters are persistent, but which columns a cluster solves is NOT fixed by its index: each
+// takes its first block of `nwarps` adjacent columns by index and every further one from a global counter.  With a static stride a
+// cluster that becomes resident late -- because another kernel holds some SMs when the solver is launched: the NCCL gather of the
+// previous piece of the shard does (bench.py, N > 1) -- still owes its full share of the columns and finishes long after the
+// others (measured at 8 GPUs: lw_solver 14.4 -> 18.1 ms per 125 000-column shard).  The leader thread of the cluster fetches the
+// next block at the START of a column trip (the atomic's latency hides under the sweeps) and hands it to every rank through
+// distributed shared memory just before the cluster barrier the trip ends with anyway: no extra rendezvous.  Which cluster
+// solves a column does not change its fluxes (every column is reduced in rank order), so results stay bit-identical.
+struct NextColumns {
+  int* slot;   // [2] in this CTA's shared memory, double-buffered by trip parity
+  int fetched;
+  bool leader;
+  __device__ __forceinline__ void begin(int* counter, int nwarps, int first_dynamic) {
+    if (leader) fetched = atomicAdd(counter, nwarps) + first_dynamic;
+  }
+  __device__ __forceinline__ void publish(cg::cluster_group& cluster, int csize, int trip) {   // call right before cluster.sync()
+    if (leader)
+      for (int r = 0; r < csize; ++r) *cluster.map_shared_rank(slot + ((trip + 1) & 1), r) = fetched;
+  }
+  __device__ __forceinline__ int next(int trip) const { return slot[(trip + 1) & 1]; }   // after that cluster.sync()
+};
+
 // rows of the reverse-sweep scratch: three 256-byte segments (32 lanes x 8 B) per layer
 constexpr int SW6_ROW = 768, SW6_F = 256, SW6_A = 512;
 
@@ -409,8 +433,13 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
   if (GM == 2) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
   auto band_pair = [&](const uint8_t* seg) { return mk2(*reinterpret_cast<const float*>(seg + bo0), *reinterpret_cast<const float*>(seg + bo1)); };
 
+  NextColumns nx;
+  nx.slot = reinterpret_cast<int*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)nwarps * pp.warp_smem);
+  nx.leader = chunk == 0 && threadIdx.x == 0;
+  nx.fetched = 0;
   int ncols_done = 0;
-  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
+  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; ++ncols_done) {
+    nx.begin(pp.next_col, nwarps, (int)(gridDim.x / csize) * nwarps);
     const bool owner = cb + warp < p.ncol;
     const int col = owner ? cb + warp : p.ncol - 1;
     float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [3][L+1]
@@ -634,6 +663,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
     pend_k = -1;
     __syncwarp();
     // ---- combine the chunks of this column (see lw_solver_v5)
+    nx.publish(cluster, csize, ncols_done);
     cluster.sync();
     {
       float* const gout[3] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1), p.flux_dir + (size_t)col * (L + 1)};
@@ -645,6 +675,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
         gout[a][i - a * (L + 1)] = sacc;
       }
     }
+    cb = nx.next(ncols_done);
   }
   cluster.sync();
 }
@@ -712,8 +743,13 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
   const int ru = lane & 7;      // the reduced value (layer within its group) this lane ends up with; lanes < 8 write
   const bool rW = lane < 8;
 
+  NextColumns nx;
+  nx.slot = reinterpret_cast<int*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)nwarps * pp.warp_smem);
+  nx.leader = chunk == 0 && threadIdx.x == 0;
+  nx.fetched = 0;
   int ncols_done = 0;
-  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; cb += (gridDim.x / csize) * nwarps, ++ncols_done) {
+  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; ++ncols_done) {
+    nx.begin(pp.next_col, nwarps, (int)(gridDim.x / csize) * nwarps);
     const bool owner = cb + warp < p.ncol;
     const int col = owner ? cb + warp : p.ncol - 1;
     float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
@@ -738,12 +774,14 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
 
     for (int imu = 0; imu < p.nmus; ++imu) {
       const f2 D = splat2(p.Ds[imu]);
-      const f2 fac = splat2(2.0f * kPi * p.wts[imu] * live);
+      // Idle lanes (ngpt not a multiple of 64: the ragged last chunk) read the zero fill of the TMA boxes beyond ngpt: tau = 0,
+      // sources = 0, so their radiances stay exactly zero once the two places that feed them shadow data -- the incident flux and
+      // the surface emission -- are masked.  No per-layer masking.
       const float rad_norm = 2.0f * kPi * p.wts[imu];
-      f2 I = map2(inc, [&](float v) { return v / rad_norm; });  // radn_dn(top) = inc_flux/(2 pi w), :196-201
+      f2 I = map2(inc, [&](float v) { return v / rad_norm; }) * splat2(live);  // radn_dn(top) = inc_flux/(2 pi w), :196-201
       {
-        const float s = warp_sum(hsum2(fac * I));
-        if (lane == 0) fdn[TOP ? 0 : L] += s;
+        const float s = warp_sum(hsum2(I));
+        if (lane == 0) fdn[TOP ? 0 : L] += rad_norm * s;
       }
       // one elected lane feeds the input ring: group k -> stage (n_in + k) % S
       auto issue_in = [&](int k) {
@@ -778,15 +816,16 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
 #pragma unroll
       for (int u = 0; u < U; ++u) pend[u] = 0.0f;
       int pend_k = -1;
+      // (the quadrature factor 2 pi w multiplies the REDUCED sums: one multiply per level instead of one per lane and layer)
       auto flush_dn = [&]() {
         const float t = tr_reduce<U>(pend, tr, lane);
         const int i = pend_k * U + ru;
-        if (rW && pend_k >= 0 && i < L) fdn[TOP ? i + 1 : L - 1 - i] += t;
+        if (rW && pend_k >= 0 && i < L) fdn[TOP ? i + 1 : L - 1 - i] += rad_norm * t;
       };
       auto flush_up = [&]() {
         const float t = tr_reduce<U>(pend, tr, lane);
         const int i = pend_k * U + (U - 1 - ru);
-        if (rW && pend_k >= 0 && i < L) fup[TOP ? i : L - i] += t;
+        if (rW && pend_k >= 0 && i < L) fup[TOP ? i : L - i] += rad_norm * t;
       };
       // ---------------- downward sweep: one group of U layers ----------------
       // TAIL = false: a full group whose boxes sit where box_start put them (immediate shared-memory offsets);
@@ -851,7 +890,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
           stg_scr(sg + u * LW6_ROW, t, pol_buf);
           stg_scr(sg + u * LW6_ROW + LW6_S, sup, pol_buf);
           I = fma2(t, I, sdn);
-          red[u] = hsum2(fac * I);
+          red[u] = hsum2(I);
         }
         carry = ext[U - 1];  // (a ragged group is the last one of its sweep: its carry is not used)
 #pragma unroll
@@ -868,10 +907,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
       pend_k = -1;
       n_in += (uint32_t)NG;
       // ---------------- surface ----------------
-      f2 Uu = fma2(I, splat2(1.0f) - emis, emis * ssrc);  // :269
+      f2 Uu = fma2(I, splat2(1.0f) - emis, emis * ssrc) * splat2(live);  // :269
       {
-        const float s = warp_sum(hsum2(fac * Uu));
-        if (lane == 0) fup[TOP ? L : 0] += s;
+        const float s = warp_sum(hsum2(Uu));
+        if (lane == 0) fup[TOP ? L : 0] += rad_norm * s;
       }
       // ---------------- upward sweep (reverse order): rows back by bulk copies into the idle input ring ----------------
       asm volatile("fence.proxy.async.global;" ::: "memory");  // this lane's row stores (generic proxy) before the bulk loads (async proxy)
@@ -912,7 +951,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
         for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
           const int uu = U - 1 - u;
           if (!TAIL || uu < nvalid) Uu = fma2(t[uu], Uu, s[uu]);
-          red[u] = hsum2(fac * Uu);
+          red[u] = hsum2(Uu);
         }
         // the rows are in registers: their L2 lines are dead (no write-back; the next sweep rewrites them in full)
         discard_scratch(srow - (size_t)lane * 8u + (size_t)k * (U * LW6_ROW), (uint32_t)nvalid * LW6_ROW, lane);
@@ -931,6 +970,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
       __syncwarp();
     }
     // ---- combine the chunks of this column (see lw_solver_v5)
+    nx.publish(cluster, csize, ncols_done);
     cluster.sync();
     {
       float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
@@ -942,6 +982,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
         gout[a][i - a * (L + 1)] = sacc;
       }
     }
+    cb = nx.next(ncols_done);
   }
   cluster.sync();  // nobody leaves while another rank may still read its shared memory
 }
@@ -1009,7 +1050,7 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_sm
   int occ = 0, ncl = 1;
   size_t smem = 0;
   for (;; --W) {
-    smem = 128 + (size_t)W * warp_smem;
+    smem = 128 + (size_t)W * warp_smem + 16;   // (+ the two slots of the dynamic column assignment)
     RRNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cfg.gridDim = dim3((unsigned)csize);
     cfg.blockDim = dim3(32u * (unsigned)W);
@@ -1026,6 +1067,9 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_sm
   cfg.gridDim = dim3((unsigned)ncta);
   if (int rc = ensure_scratch(ctx, (size_t)ncta * W * warp_scratch)) return rc;
   *scratch_slot = (float*)ctx->scratch;
+  if (!ctx->col_counter) RRNN_CUDA(cudaMalloc((void**)&ctx->col_counter, 256));
+  RRNN_CUDA(cudaMemsetAsync(ctx->col_counter, 0, sizeof(int), ctx->stream));
+  pp.next_col = ctx->col_counter;
   RRNN_CUDA(cudaLaunchKernelEx(&cfg, kernel, pp, maps...));
   return 0;
 }
