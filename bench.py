@@ -22,7 +22,7 @@ One step = one pass of the hot path over all columns of the rank:
           bounce ring), `pinned_value` from page-locked caller memory.
   roofline     : the dominant kernel (largest share of device time), timed live with CUDA events inside the library.
   cpu_baseline : oracle/bench_cpu.c -- compiled C, OpenMP over column blocks, blocked SGEMM over a block's samples, block sizes
-                 8 / 36 / 128 / 1800, best of 3, gas-optics / solver split -- on a bounded column sample.
+                 8 / 36 / 128 / 1800, best of 5, gas-optics / solver split -- on a bounded column sample.
   check        : max |flux - oracle| on 24 sampled columns of the device leg, the e2e leg and (N>1) the gathered buffer.
 """
 import argparse
@@ -222,7 +222,7 @@ def cpu_problem(ncol_sample, nlay, models="g256", data="synthetic"):
     return bench_cpu.Problem(spectral.synthetic_kdist_lw(m["ngpt_lw"]), spectral.synthetic_kdist_sw(m["ngpt_sw"]), lw, sw, atm)
 
 
-def cpu_baseline(ncol_sample, nlay, models="g256", lw=True, sw=True, repeats=3, data="synthetic", blocks=(8, 36, 128, 1800)):
+def cpu_baseline(ncol_sample, nlay, models="g256", lw=True, sw=True, repeats=5, data="synthetic", blocks=(8, 36, 128, 1800)):
     """block sizes 8 / 36 / 128 / 1800, best of `repeats`, OpenMP over blocks, gas-optics / solver split."""
     P = cpu_problem(ncol_sample, nlay, models, data)
     t0 = time.perf_counter()
@@ -769,7 +769,7 @@ def run_b200(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         ncs = 1800 if cfg["data"] == "rfmip" else min(args.cpu_columns, cfg["ncol"])
-        cpu, _ = cpu_baseline(ncs, nlay, args.models, do_lw, do_sw, repeats=3, data=cfg["data"])
+        cpu, _ = cpu_baseline(ncs, nlay, args.models, do_lw, do_sw, repeats=5, data=cfg["data"])
 
     line = {
         "metric": metric_name(cfg), "value": res["value"], "unit": "columns/s", "n_gpus": world,

@@ -1,6 +1,6 @@
 ! ISO_C_BINDING interfaces of librrnn_b200.so -- GENERATED from include/rrnn.h by tools/gen_fortran_binding.py; do not edit.
 !
-! One interface block per C entry point (100 of 100).  Scalars by value; handles, device addresses and host
+! One interface block per C entry point (102 of 102).  Scalars by value; handles, device addresses and host
 ! arrays as type(c_ptr) values (host arrays: c_loc(a)); out-arguments and small integer / double arrays by reference.
 ! The comment above each block is the one the header carries: it cites the reference interface the entry point replaces.
 ! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler, SURVEY.md section 0 F1): `make -C fortran` builds it where
@@ -993,6 +993,61 @@ module mo_rrnn_c_binding
       type(c_ptr), value :: bnd_flux_net_d
       integer(c_int) :: rc
     end function rrnn_net_byband
+    ! rte_lw / rte_sw with ty_fluxes_byband (extensions/mo_fluxes_byband.F90:41-131) WITHOUT g-point fluxes: broadband and
+    ! by-band fluxes (nbnd,nlay+1,ncol) both come out of the tuned solver, whose per-level sums pass through the band sums
+    ! anyway. Needs bands of 16 aligned g-points (every RRTMGP k-distribution) and a shape the packed solver takes; otherwise an
+    ! error that says so, and the general path (g-point fluxes + rrnn_sum_byband) is the one to use. Summation order differs
+    ! from sum_byband's (in g-point order), so these agree with it to rounding, not bit for bit. LW with ONE quadrature angle:
+    ! the by-band values are sums of the reference's un-scaled g-point radiances, as there (quirk Q3,
+    ! rte/kernels/mo_rte_solver_kernels.F90:284-291); the broadband fluxes are fluxes.
+    function rrnn_rte_lw_byband(ctx, kd, nlay, ncol, top_at_1, n_gauss_angles, inc_flux_d, tau_d, lay_source_d, &
+        lev_source_d, sfc_source_d, sfc_emis_d, flux_up_d, flux_dn_d, bnd_flux_up_d, bnd_flux_dn_d) &
+        bind(C, name="rrnn_rte_lw_byband") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      integer(c_int), value :: nlay
+      integer(c_int), value :: ncol
+      integer(c_int), value :: top_at_1
+      integer(c_int), value :: n_gauss_angles
+      type(c_ptr), value :: inc_flux_d
+      type(c_ptr), value :: tau_d
+      type(c_ptr), value :: lay_source_d
+      type(c_ptr), value :: lev_source_d
+      type(c_ptr), value :: sfc_source_d
+      type(c_ptr), value :: sfc_emis_d
+      type(c_ptr), value :: flux_up_d
+      type(c_ptr), value :: flux_dn_d
+      type(c_ptr), value :: bnd_flux_up_d
+      type(c_ptr), value :: bnd_flux_dn_d
+      integer(c_int) :: rc
+    end function rrnn_rte_lw_byband
+    function rrnn_rte_sw_byband(ctx, kd, nlay, ncol, top_at_1, mu0_d, inc_flux_d, sfc_alb_dir_gpt_d, sfc_alb_dif_gpt_d, &
+        inc_flux_dif_d, tau_d, ssa_d, g_d, flux_up_d, flux_dn_d, flux_dn_dir_d, bnd_flux_up_d, bnd_flux_dn_d, &
+        bnd_flux_dn_dir_d) &
+        bind(C, name="rrnn_rte_sw_byband") result(rc)
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), value :: kd
+      integer(c_int), value :: nlay
+      integer(c_int), value :: ncol
+      integer(c_int), value :: top_at_1
+      type(c_ptr), value :: mu0_d
+      type(c_ptr), value :: inc_flux_d
+      type(c_ptr), value :: sfc_alb_dir_gpt_d
+      type(c_ptr), value :: sfc_alb_dif_gpt_d
+      type(c_ptr), value :: inc_flux_dif_d
+      type(c_ptr), value :: tau_d
+      type(c_ptr), value :: ssa_d
+      type(c_ptr), value :: g_d
+      type(c_ptr), value :: flux_up_d
+      type(c_ptr), value :: flux_dn_d
+      type(c_ptr), value :: flux_dn_dir_d
+      type(c_ptr), value :: bnd_flux_up_d
+      type(c_ptr), value :: bnd_flux_dn_d
+      type(c_ptr), value :: bnd_flux_dn_dir_d
+      integer(c_int) :: rc
+    end function rrnn_rte_sw_byband
     ! net = down - up over n elements: net_byband_precalc (mo_fluxes_byband_kernels.F90:80-86) and the broadband flux_net of
     ! ty_fluxes_broadband%reduce (rte/mo_fluxes.F90, net_broadband_precalc).
     function rrnn_net_flux(ctx, n, flux_dn_d, flux_up_d, flux_net_d) bind(C, name="rrnn_net_flux") result(rc)

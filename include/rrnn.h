@@ -324,6 +324,21 @@ RRNN_API int rrnn_sum_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlev, 
                              float* bnd_flux_d);
 RRNN_API int rrnn_net_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlev, int ncol, const float* gpt_flux_dn_d,
                              const float* gpt_flux_up_d, float* bnd_flux_net_d);
+/* rte_lw / rte_sw with ty_fluxes_byband (extensions/mo_fluxes_byband.F90:41-131) WITHOUT g-point fluxes: broadband and by-band fluxes
+ * (nbnd,nlay+1,ncol) both come out of the tuned solver, whose per-level sums pass through the band sums anyway.  Needs bands of 16
+ * aligned g-points (every RRTMGP k-distribution) and a shape the packed solver takes; otherwise an error that says so, and the
+ * general path (g-point fluxes + rrnn_sum_byband) is the one to use.  Summation order differs from sum_byband's (in g-point order),
+ * so these agree with it to rounding, not bit for bit.  LW with ONE quadrature angle: the by-band values are sums of the reference's
+ * un-scaled g-point radiances, as there (quirk Q3, rte/kernels/mo_rte_solver_kernels.F90:284-291); the broadband fluxes are fluxes. */
+RRNN_API int rrnn_rte_lw_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,
+                                const float* inc_flux_d, const float* tau_d, const float* lay_source_d, const float* lev_source_d,
+                                const float* sfc_source_d, const float* sfc_emis_d, float* flux_up_d, float* flux_dn_d,
+                                float* bnd_flux_up_d, float* bnd_flux_dn_d);
+RRNN_API int rrnn_rte_sw_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, const float* mu0_d,
+                                const float* inc_flux_d, const float* sfc_alb_dir_gpt_d, const float* sfc_alb_dif_gpt_d,
+                                const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d, float* flux_up_d,
+                                float* flux_dn_d, float* flux_dn_dir_d, float* bnd_flux_up_d, float* bnd_flux_dn_d,
+                                float* bnd_flux_dn_dir_d);
 /* net = down - up over n elements: net_byband_precalc (mo_fluxes_byband_kernels.F90:80-86) and the broadband flux_net of
  * ty_fluxes_broadband%reduce (rte/mo_fluxes.F90, net_broadband_precalc). */
 RRNN_API int rrnn_net_flux(rrnn_ctx_t* ctx, size_t n, const float* flux_dn_d, const float* flux_up_d, float* flux_net_d);

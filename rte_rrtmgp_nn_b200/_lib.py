@@ -121,6 +121,8 @@ _SIGS = {
                                       vp, C.POINTER(rrnn_gas_t), C.c_int, vp, vp]),
     "rrnn_sw_fluxes_host": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,
                                       C.POINTER(rrnn_gas_t), C.c_int, vp, vp, vp]),
+    "rrnn_rte_lw_byband": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rrnn_rte_sw_byband": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_rte_lw_clouds": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_rte_sw_clouds": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rrnn_lw_fluxes_allsky": (C.c_int, [vp, vp, C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp,

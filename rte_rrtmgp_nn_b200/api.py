@@ -594,6 +594,57 @@ class ty_fluxes_byband(ty_fluxes_broadband):
         return ""
 
 
+# ty_fluxes_byband from the tuned solvers (True, default) or the reference's own route -- g-point fluxes from the general kernels, then
+# sum_byband in g-point order, bit-exact against the oracle's serial sums (False)
+BYBAND_FROM_SOLVER = True
+
+
+def _byband_from_solver(fluxes, optical_props, sw, call):
+    """ty_fluxes_byband straight from the tuned solvers (rrnn_rte_{lw,sw}_byband: the per-level sums stop at a band on their way to
+    the broadband sum) -- no g-point fluxes, no general kernel.  `call(up, dn, dir, bnd_up, bnd_dn, bnd_dir)` runs the C entry point.
+    Returns None when the packed solver does not take the case (the caller then goes the general way), else the error message."""
+    torch = _torch()
+    ctx = optical_props.ctx
+    ncol, nlev, nbnd = optical_props.get_ncol(), optical_props.get_nlay() + 1, optical_props.nband
+    dev = optical_props.tau.device
+    if not BYBAND_FROM_SOLVER:
+        return None
+    for nm in ("flux_up", "flux_dn", "flux_net", "flux_dn_dir"):
+        v = getattr(fluxes, nm)
+        if v is not None and tuple(v.shape) != (ncol, nlev):
+            return f"reduce: {nm} array incorrectly sized"
+    for nm, msg in (("bnd_flux_up", "reduce: bnd_flux_up array incorrectly sized (can't compute net flux either)"),
+                    ("bnd_flux_dn", "reduce: bnd_flux_dn array incorrectly sized (can't compute net flux either)"),
+                    ("bnd_flux_dn_dir", "reduce: bnd_flux_dn_dir array incorrectly sized"),
+                    ("bnd_flux_net", "reduce: bnd_flux_net array incorrectly sized (can't compute net flux either)")):
+        v = getattr(fluxes, nm)
+        if v is not None and tuple(v.shape) != (ncol, nlev, nbnd):
+            return msg
+    if not sw and fluxes.bnd_flux_dn_dir is not None:
+        return "reduce: requesting bnd_flux_dn_dir but direct flux hasn't been supplied"
+
+    def pick(v, *shape):
+        if v is not None:
+            return v
+        with torch.cuda.stream(ctx.torch_stream()):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+    up, dn = pick(fluxes.flux_up, ncol, nlev), pick(fluxes.flux_dn, ncol, nlev)
+    dr = pick(fluxes.flux_dn_dir, ncol, nlev) if sw else None
+    bup, bdn = pick(fluxes.bnd_flux_up, ncol, nlev, nbnd), pick(fluxes.bnd_flux_dn, ncol, nlev, nbnd)
+    bdr = pick(fluxes.bnd_flux_dn_dir, ncol, nlev, nbnd) if sw else None
+    try:
+        call(up, dn, dr, bup, bdn, bdr)
+        if fluxes.flux_net is not None:
+            _lib.check(_lib.lib().rrnn_net_flux(ctx.h, ncol * nlev, _ptr(dn), _ptr(up), _ptr(fluxes.flux_net)))
+        if fluxes.bnd_flux_net is not None:
+            _lib.check(_lib.lib().rrnn_net_flux(ctx.h, ncol * nlev * nbnd, _ptr(bdn), _ptr(bup), _ptr(fluxes.bnd_flux_net)))
+    except RRNNError as e:
+        if "by-band fluxes from the packed solver need" in str(e):
+            return None
+        return str(e)
+    return ""
+
+
 def _solve_and_reduce(core, fluxes, optical_props, sw):
     """Wraps a solver call for the flux types whose outputs the fused broadband kernels do not produce themselves: flux_net
     (ty_fluxes_broadband%reduce, rte/mo_fluxes.F90: net_broadband_precalc) and ty_fluxes_byband's by-band arrays, which need
@@ -804,6 +855,21 @@ def rte_lw(optical_props, top_at_1, sources, sfc_emis, fluxes, inc_flux=None, n_
     if not fluxes.are_desired():
         return "rte_lw: no space allocated for fluxes"
     if fluxes.flux_net is not None or (isinstance(fluxes, ty_fluxes_byband) and fluxes._bnd_desired()):
+        if (isinstance(fluxes, ty_fluxes_byband) and fluxes._bnd_desired() and isinstance(optical_props, ty_optical_props_1scl)
+                and not use_2stream and lw_Ds is None and flux_up_Jac is None and flux_dn_Jac is None
+                and (n_gauss_angles is None or 1 <= int(n_gauss_angles) <= 4)):
+            ctx = optical_props.ctx
+            ncol, nlay = optical_props.get_ncol(), optical_props.get_nlay()
+            emis_d = _dev(sfc_emis, ctx)
+            if tuple(emis_d.shape) != (ncol, optical_props.nband):
+                return "rte_lw: sfc_emis inconsistently sized"
+            inc_d = _dev(inc_flux, ctx)
+            nang = 1 if n_gauss_angles is None else int(n_gauss_angles)
+            err = _byband_from_solver(fluxes, optical_props, False, lambda up, dn, dr, bup, bdn, bdr: _lib.check(_lib.lib().rrnn_rte_lw_byband(
+                ctx.h, optical_props._kd.h, nlay, ncol, int(bool(top_at_1)), nang, _ptr(inc_d), _ptr(optical_props.tau), _ptr(sources.lay_source),
+                _ptr(sources.lev_source), _ptr(sources.sfc_source), _ptr(emis_d), _ptr(up), _ptr(dn), _ptr(bup), _ptr(bdn))))
+            if err is not None:
+                return err
         return _solve_and_reduce(lambda f: rte_lw(optical_props, top_at_1, sources, sfc_emis, f, inc_flux, n_gauss_angles, use_2stream,
                                                   lw_Ds, flux_up_Jac, flux_dn_Jac), fluxes, optical_props, sw=False)
     two = isinstance(optical_props, ty_optical_props_2str)
@@ -903,6 +969,18 @@ def rte_sw(atmos, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, flu
     if not isinstance(atmos, ty_optical_props_2str):
         return "rte_sw: only ty_optical_props_2str (two-stream) is implemented"
     if fluxes.flux_net is not None or (isinstance(fluxes, ty_fluxes_byband) and fluxes._bnd_desired()):
+        if isinstance(fluxes, ty_fluxes_byband) and fluxes._bnd_desired():
+            ctx = atmos.ctx
+            ncol, nlay, ngpt = atmos.get_ncol(), atmos.get_nlay(), atmos.ngpt
+            d = [_dev(v, ctx) for v in (mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt)]
+            if tuple(d[0].shape) == (ncol,) and all(tuple(v.shape) == (ncol, ngpt) for v in d[1:]):
+                g_p = None if atmos.g_is_zero and atmos._g is None and atmos._pending is None else _ptr(atmos.g)
+                dif = _dev(inc_flux_dif, ctx)
+                err = _byband_from_solver(fluxes, atmos, True, lambda up, dn, dr, bup, bdn, bdr: _lib.check(_lib.lib().rrnn_rte_sw_byband(
+                    ctx.h, atmos._kd.h, nlay, ncol, int(bool(top_at_1)), _ptr(d[0]), _ptr(d[1]), _ptr(d[2]), _ptr(d[3]), _ptr(dif), _ptr(atmos.tau),
+                    _ptr(atmos.ssa), g_p, _ptr(up), _ptr(dn), _ptr(dr), _ptr(bup), _ptr(bdn), _ptr(bdr))))
+                if err is not None:
+                    return err
         return _solve_and_reduce(lambda f: rte_sw(atmos, top_at_1, mu0, inc_flux, sfc_alb_dir_gpt, sfc_alb_dif_gpt, f, inc_flux_dif),
                                  fluxes, atmos, sw=True)
     ctx = atmos.ctx

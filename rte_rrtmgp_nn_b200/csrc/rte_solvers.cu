@@ -783,3 +783,88 @@ extern "C" int rrnn_rte_sw_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int n
   if (rc < 0) return fail(std::string("rte_sw (clouds)") + kCloudShapeMsg);
   return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------- by-band fluxes from the packed solvers
+// ty_fluxes_byband (extensions/mo_fluxes_byband.F90:41-131) without g-point fluxes: the packed kernels' per-level sums pass through
+// sums over 8 lanes = 16 g-points on their way to the broadband sum, which IS a band sum when every band is 16 consecutive g-points
+// starting at a multiple of 16 (all of RRTMGP's k-distributions: 16 x 16 longwave, 14 x 16 shortwave).  The by-band arrays
+// (nbnd,nlay+1,ncol) then cost a few stores per group of 8 layers; the general kernels + rrnn_sum_byband remain the path for
+// anything else.
+static bool bands_of_16(const rrnn_kdist_t* kd) {
+  if (kd->nbnd < 1 || kd->nbnd > 32 || kd->ngpt != 16 * kd->nbnd) return false;
+  for (int b = 0; b < kd->nbnd; ++b)
+    if (kd->band_lims_gpt[2 * b] != 16 * b + 1 || kd->band_lims_gpt[2 * b + 1] != 16 * b + 16) return false;
+  return true;
+}
+static const char* kBybandMsg =
+    ": by-band fluxes from the packed solver need bands of 16 aligned g-points and a shape the packed solver takes (ngpt <= 512, "
+    "nlay >= 8, 16-byte aligned arrays, default solver_variant); use the g-point fluxes and rrnn_sum_byband";
+
+extern "C" int rrnn_rte_lw_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int n_gauss_angles,
+                                  const float* inc_flux_d, const float* tau_d, const float* lay_source_d, const float* lev_source_d,
+                                  const float* sfc_source_d, const float* sfc_emis_d, float* flux_up_d, float* flux_dn_d,
+                                  float* bnd_flux_up_d, float* bnd_flux_dn_d) {
+  rrnn::NvtxRange nvtx_("rte_lw");
+  RRNN_CHECK(ctx && kd && tau_d && lay_source_d && lev_source_d && sfc_source_d && sfc_emis_d && flux_up_d && flux_dn_d && bnd_flux_up_d &&
+                 bnd_flux_dn_d, "rte_lw: null argument");
+  static const float gauss_Ds[4][4] = {{1.66f, 0.f, 0.f, 0.f},
+                                       {1.18350343f, 2.81649655f, 0.f, 0.f},
+                                       {1.09719858f, 1.69338507f, 4.70941630f, 0.f},
+                                       {1.06056257f, 1.38282560f, 2.40148179f, 7.15513024f}};
+  static const float gauss_wts[4][4] = {{0.5f, 0.f, 0.f, 0.f},
+                                        {0.3180413817f, 0.1819586183f, 0.f, 0.f},
+                                        {0.2009319137f, 0.2292411064f, 0.0698269799f, 0.f},
+                                        {0.1355069134f, 0.2034645680f, 0.1298475476f, 0.0311809710f}};
+  RRNN_CHECK(n_gauss_angles <= 4, "rte_lw: asking for too many quadrature points for no-scattering calculation");
+  RRNN_CHECK(n_gauss_angles >= 1, "rte_lw: have to ask for at least one quadrature point for no-scattering calculation");
+  if (ncol == 0) return 0;
+  if (!bands_of_16(kd) || ctx->solver_variant != 0) return fail(std::string("rte_lw (by band)") + kBybandMsg);
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  const int ngpt = kd->ngpt;
+  const size_t n = (size_t)ngpt * ncol;
+  float* emis_gpt = nullptr;
+  RRNN_CUDA(cudaMallocAsync((void**)&emis_gpt, n * sizeof(float), ctx->stream));
+  expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(kd->nbnd, ngpt, ncol, kd->d_gpt2band, sfc_emis_d, emis_gpt);
+  LwParams p{};
+  p.ngpt = ngpt; p.nlay = nlay; p.ncol = ncol; p.top_at_1 = top_at_1 ? 1 : 0; p.nmus = n_gauss_angles;
+  p.bug_compat = ctx->lw_source_bug_compat;
+  p.nchunks = (ngpt + 31) / 32;
+  for (int i = 0; i < n_gauss_angles; ++i) { p.Ds[i] = gauss_Ds[n_gauss_angles - 1][i]; p.wts[i] = gauss_wts[n_gauss_angles - 1][i]; }
+  p.inc_flux = inc_flux_d; p.tau = tau_d; p.lay_source = lay_source_d; p.lev_source = lev_source_d;
+  p.sfc_emis = emis_gpt; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
+  p.bnd_up = bnd_flux_up_d; p.bnd_dn = bnd_flux_dn_d; p.nbnd = kd->nbnd;
+  const int ps = prof_begin(ctx, K_LW_SOLVER);
+  const int rc = launch_lw_v6(ctx, p);
+  prof_end(ctx, K_LW_SOLVER, ps);
+  cudaFreeAsync(emis_gpt, ctx->stream);
+  if (rc < 0) return fail(std::string("rte_lw (by band)") + kBybandMsg);
+  if (rc > 0) return rc;
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int rrnn_rte_sw_byband(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, const float* mu0_d,
+                                  const float* inc_flux_d, const float* sfc_alb_dir_gpt_d, const float* sfc_alb_dif_gpt_d,
+                                  const float* inc_flux_dif_d, const float* tau_d, const float* ssa_d, const float* g_d, float* flux_up_d,
+                                  float* flux_dn_d, float* flux_dn_dir_d, float* bnd_flux_up_d, float* bnd_flux_dn_d,
+                                  float* bnd_flux_dn_dir_d) {
+  rrnn::NvtxRange nvtx_("rte_sw");
+  RRNN_CHECK(ctx && kd && mu0_d && inc_flux_d && sfc_alb_dir_gpt_d && sfc_alb_dif_gpt_d && tau_d && ssa_d, "rte_sw: null argument");
+  RRNN_CHECK(flux_up_d && flux_dn_d && flux_dn_dir_d && bnd_flux_up_d && bnd_flux_dn_d && bnd_flux_dn_dir_d, "rte_sw: no space allocated for fluxes");
+  if (ncol == 0) return 0;
+  if (!bands_of_16(kd) || ctx->solver_variant != 0) return fail(std::string("rte_sw (by band)") + kBybandMsg);
+  RRNN_CUDA(cudaSetDevice(ctx->device));
+  SwParams p{};
+  p.ngpt = kd->ngpt; p.nlay = nlay; p.ncol = ncol; p.top_at_1 = top_at_1 ? 1 : 0;
+  p.nchunks = (kd->ngpt + 31) / 32;
+  p.inc_flux = inc_flux_d; p.inc_flux_dif = inc_flux_dif_d; p.tau = tau_d; p.ssa = ssa_d; p.g = g_d; p.mu0 = mu0_d;
+  p.alb_dir = sfc_alb_dir_gpt_d; p.alb_dif = sfc_alb_dif_gpt_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d; p.flux_dir = flux_dn_dir_d;
+  p.bnd_up = bnd_flux_up_d; p.bnd_dn = bnd_flux_dn_d; p.bnd_dir = bnd_flux_dn_dir_d; p.nbnd = kd->nbnd;
+  const int ps = prof_begin(ctx, K_SW_SOLVER);
+  const int rc = launch_sw_v6(ctx, p, ctx->fast_math || ctx->sw_fast_math);
+  prof_end(ctx, K_SW_SOLVER, ps);
+  if (rc < 0) return fail(std::string("rte_sw (by band)") + kBybandMsg);
+  if (rc > 0) return rc;
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}

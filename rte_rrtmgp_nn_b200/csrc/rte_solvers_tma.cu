@@ -39,11 +39,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef RRNN_MBAR_SUSPEND_NS
+#define RRNN_MBAR_SUSPEND_NS 1000   // suspend-time hint of mbarrier.try_wait: how long the hardware may park the thread per attempt
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   unsigned spins = 0;
   while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)RRNN_MBAR_SUSPEND_NS) : "memory");
     if (!ok && ++spins > (1u << 26)) __trap();  // a wait of seconds is a protocol bug: fail the launch instead of hanging
   }
 }
@@ -348,6 +351,39 @@ __device__ __forceinline__ float tr_reduce(const float (&v)[N], float* tr, int l
   t += __shfl_xor_sync(0xffffffffu, t, 16);
   return t;
 }
+// The same sums, and on the way the sums over the 8 lanes = 16 g-points = ONE BAND that each reader adds up anyway: lane l ends up
+// with the total of v[l % N] (as tr_reduce, same association, same bits) and with the partial sums of the bands its quarter of the
+// row covers -- N = 16: bands 2 (l / 16) and 2 (l / 16) + 1 of the warp's four; N = 8: band l / 8 (bB unused).
+template <int N>
+__device__ __forceinline__ float tr_reduce_bands(const float (&v)[N], float* tr, int lane, float& bA, float& bB) {
+  static_assert(N == 8 || N == 16, "tr_reduce: 8 or 16 values");
+  constexpr int NRD = 32 / N;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < N; ++i) tr[i * TR_PITCH + lane] = v[i];
+  __syncwarp();
+  const int idx = lane & (N - 1), part = lane / N;
+  const float4* src = reinterpret_cast<const float4*>(tr + idx * TR_PITCH + part * N);
+  float4 q[N / 4];
+#pragma unroll
+  for (int j = 0; j < N / 4; ++j) q[j] = src[j];
+  float s[N / 4];
+#pragma unroll
+  for (int j = 0; j < N / 4; ++j) s[j] = (q[j].x + q[j].y) + (q[j].z + q[j].w);
+  bA = s[0] + s[1];
+  bB = (N == 16) ? s[2] + s[N / 4 - 1] : 0.0f;
+  float t = (N == 16) ? bA + bB : bA;
+  if (NRD == 4) t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return t;
+}
+// sum over each group of 8 lanes (one band): every lane of the group gets it
+__device__ __forceinline__ float band_sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
 
 // Dynamic column assignment.  The clusters are persistent, but which columns a cluster solves is NOT fixed by its index: each
 // takes its first block of `nwarps` adjacent columns by index and every further one from a global counter.  With a static stride a
@@ -379,7 +415,9 @@ constexpr int SW6_ROW = 768, SW6_F = 256, SW6_A = 512;
 // layer): inc_2stream_by_2stream_bybnd (mo_optical_props_kernels.F90:453-485) on gas properties with g == 0 runs in registers,
 //   tau = tau1 + t2,  ssa = (tau1 ssa1 + s2) / max(eps, tau),  g = sg2 / max(eps, tau1 ssa1 + s2),
 // so the all-sky path neither rewrites tau / ssa nor materialises g.
-template <bool FAST, int GM, bool TOP>
+// BND: by-band fluxes as well (SwParams::bnd_*): the per-level sums stop at a band on their way to the broadband sum.  A template
+// parameter, not a run-time flag: the flag's tests and the second copy of the reduction cost the broadband-only kernel 5 %.
+template <bool FAST, int GM, bool TOP, bool BND = false>
 __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(const __grid_constant__ SwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_ssa, const __grid_constant__ CUtensorMap tm_g) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -460,6 +498,17 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
       const float sd = warp_sum(hsum2(dir)), sb = warp_sum(hsum2(beta + dir));
       if (lane == 0) { fdr[top_level] += sd; fdn[top_level] += sb; }
     }
+    // by-band outputs (warp-uniform): this lane's band = chunk * 4 + lane / 8; rows (nbnd) of level `lev` of this column
+    constexpr bool bands = BND;
+    const int my_band = chunk * 4 + (lane >> 3);
+    const size_t bcol = (size_t)col * (L + 1) * (size_t)p.nbnd;
+    if (bands) {
+      const float bd = band_sum8(hsum2(dir)), bb = band_sum8(hsum2(beta + dir));
+      if (owner && (lane & 7) == 0 && my_band < p.nbnd) {
+        p.bnd_dir[bcol + (size_t)top_level * p.nbnd + my_band] = bd;
+        p.bnd_dn[bcol + (size_t)top_level * p.nbnd + my_band] = bb;
+      }
+    }
     auto issue_in = [&](int k) {
       if (k < NG) {
         const uint32_t st = (n_in + (uint32_t)k) % S;
@@ -484,20 +533,39 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
 #pragma unroll
     for (int u = 0; u < 2 * U; ++u) pend[u] = 0.0f;
     int pend_k = -1;
+    // by-band: lane l holds quantity (l & 8 ? B : A) of layer l & 7 for the bands 2 (l / 16), 2 (l / 16) + 1 of this chunk
+    auto put_bands = [&](float* arr, int lev, float bA, float bB, bool add) {
+      const int b0 = chunk * 4 + 2 * (lane >> 4);
+      float* q = arr + bcol + (size_t)lev * p.nbnd + b0;
+      if (b0 < p.nbnd) q[0] = add ? q[0] + bA : bA;
+      if (b0 + 1 < p.nbnd) q[1] = add ? q[1] + bB : bB;
+    };
     auto flush_fwd = [&]() {  // pend[u] = dir, pend[U + u] = diffuse + dir at the bottom of sweep layer pend_k * U + u
-      const float t = tr_reduce<2 * U>(pend, tr, lane);
+      float bA = 0.0f, bB = 0.0f;
+      const float t = bands ? tr_reduce_bands<2 * U>(pend, tr, lane, bA, bB) : tr_reduce<2 * U>(pend, tr, lane);
       const int i = pend_k * U + ru;
-      if (rW && pend_k >= 0 && i < L) {
-        float* dst = (rB ? fdn : fdr) + (TOP ? i + 1 : L - 1 - i);
-        *dst += t;
+      if (pend_k >= 0 && i < L) {
+        const int lev = TOP ? i + 1 : L - 1 - i;
+        if (rW) {
+          float* dst = (rB ? fdn : fdr) + lev;
+          *dst += t;
+        }
+        if (bands && owner) put_bands(rB ? p.bnd_dn : p.bnd_dir, lev, bA, bB, false);
       }
     };
     auto flush_bwd = [&]() {  // pend[u] = up, pend[U + u] = alpha_above * up at the top of sweep layer pend_k * U + (U - 1 - u)
-      const float t = tr_reduce<2 * U>(pend, tr, lane);
+      float bA = 0.0f, bB = 0.0f;
+      const float t = bands ? tr_reduce_bands<2 * U>(pend, tr, lane, bA, bB) : tr_reduce<2 * U>(pend, tr, lane);
       const int i = pend_k * U + (U - 1 - ru);
-      if (rW && pend_k >= 0 && i < L) {
-        float* dst = (rB ? fdn : fup) + (TOP ? i : L - i);
-        *dst += t;
+      if (pend_k >= 0 && i < L) {
+        const int lev = TOP ? i : L - i;
+        if (rW) {
+          float* dst = (rB ? fdn : fup) + lev;
+          *dst += t;
+        }
+        // the downward by-band flux gets its second part here (alpha_above * U on top of the beta + dir of sweep 1, written by
+        // another lane of this warp before the surface: ordered by the __syncwarp()s in between)
+        if (bands && owner) put_bands(rB ? p.bnd_dn : p.bnd_up, lev, bA, bB, rB);
       }
     };
     // ---------------- sweep 1: top -> surface ----------------
@@ -601,6 +669,14 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
       const int sfc = TOP ? L : 0;
       const float su = warp_sum(hsum2(Uu)), sa = warp_sum(hsum2(alpha * Uu));
       if (lane == 0) { fup[sfc] += su; fdn[sfc] += sa; }
+      if (bands) {
+        __syncwarp();   // (the forward sweep's last by-band rows, written by other lanes, are complete)
+        const float bu = band_sum8(hsum2(Uu)), ba = band_sum8(hsum2(alpha * Uu));
+        if (owner && (lane & 7) == 0 && my_band < p.nbnd) {
+          p.bnd_up[bcol + (size_t)sfc * p.nbnd + my_band] = bu;
+          p.bnd_dn[bcol + (size_t)sfc * p.nbnd + my_band] += ba;
+        }
+      }
     }
     // ---------------- sweep 2: surface -> top (back substitution) ----------------
     // The rows of a group come back with ONE bulk copy into the (now idle) input ring (SB stages), SB - 1 groups ahead of
@@ -688,7 +764,8 @@ constexpr int LW6_ROW = 512, LW6_S = 256;
 
 // CLD: by-band cloud optical depths whose increment has not been applied (LwParams::cld_tau) ride along as one more 64-byte
 // table row per layer and are added to tau in registers -- the all-sky path never rewrites the (ngpt,nlay,ncol) array.
-template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT, bool CLD>
+// BND: by-band fluxes as well (LwParams::bnd_*; a template parameter for the reason given at sw_solver_v6).
+template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT, bool CLD, bool BND = false>
 __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
                                                    const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev,
                                                    const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv,
@@ -783,6 +860,23 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
         const float s = warp_sum(hsum2(I));
         if (lane == 0) fdn[TOP ? 0 : L] += rad_norm * s;
       }
+      // by-band outputs (warp-uniform): this lane's band = chunk * 4 + lane / 8; later quadrature angles add to the first one's
+      const bool bands = p.bnd_up != nullptr;
+      const int my_band = chunk * 4 + (lane >> 3);
+      const size_t bcol = (size_t)col * (L + 1) * (size_t)p.nbnd;
+      // quirk Q3 (mo_rte_solver_kernels.F90:284-291): with ONE quadrature angle the reference leaves its g-point "fluxes" as radiances,
+      // un-multiplied by 2 pi w (only the inlined broadband sum is scaled), and ty_fluxes_byband reduces exactly those
+      const float band_norm = p.nmus == 1 ? 1.0f : rad_norm;
+      auto put_band = [&](float* arr, int lev, float b) {
+        if (owner && my_band < p.nbnd) {
+          float* q = arr + bcol + (size_t)lev * p.nbnd + my_band;
+          *q = imu == 0 ? band_norm * b : *q + band_norm * b;
+        }
+      };
+      if (bands) {
+        const float b = band_sum8(hsum2(I));
+        if ((lane & 7) == 0) put_band(p.bnd_dn, TOP ? 0 : L, b);
+      }
       // one elected lane feeds the input ring: group k -> stage (n_in + k) % S
       auto issue_in = [&](int k) {
         if (k < NG) {
@@ -817,15 +911,23 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
       for (int u = 0; u < U; ++u) pend[u] = 0.0f;
       int pend_k = -1;
       // (the quadrature factor 2 pi w multiplies the REDUCED sums: one multiply per level instead of one per lane and layer)
-      auto flush_dn = [&]() {
-        const float t = tr_reduce<U>(pend, tr, lane);
+      auto flush_dn = [&]() {   // by-band: lane l holds layer l & 7 of band l / 8 of this chunk
+        float bA = 0.0f, bB = 0.0f;
+        const float t = bands ? tr_reduce_bands<U>(pend, tr, lane, bA, bB) : tr_reduce<U>(pend, tr, lane);
         const int i = pend_k * U + ru;
-        if (rW && pend_k >= 0 && i < L) fdn[TOP ? i + 1 : L - 1 - i] += rad_norm * t;
+        if (pend_k >= 0 && i < L) {
+          if (rW) fdn[TOP ? i + 1 : L - 1 - i] += rad_norm * t;
+          if (bands) put_band(p.bnd_dn, TOP ? i + 1 : L - 1 - i, bA);
+        }
       };
       auto flush_up = [&]() {
-        const float t = tr_reduce<U>(pend, tr, lane);
+        float bA = 0.0f, bB = 0.0f;
+        const float t = bands ? tr_reduce_bands<U>(pend, tr, lane, bA, bB) : tr_reduce<U>(pend, tr, lane);
         const int i = pend_k * U + (U - 1 - ru);
-        if (rW && pend_k >= 0 && i < L) fup[TOP ? i : L - i] += rad_norm * t;
+        if (pend_k >= 0 && i < L) {
+          if (rW) fup[TOP ? i : L - i] += rad_norm * t;
+          if (bands) put_band(p.bnd_up, TOP ? i : L - i, bA);
+        }
       };
       // ---------------- downward sweep: one group of U layers ----------------
       // TAIL = false: a full group whose boxes sit where box_start put them (immediate shared-memory offsets);
@@ -911,6 +1013,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
       {
         const float s = warp_sum(hsum2(Uu));
         if (lane == 0) fup[TOP ? L : 0] += rad_norm * s;
+        if (bands) {
+          const float b = band_sum8(hsum2(Uu));
+          if ((lane & 7) == 0) put_band(p.bnd_up, TOP ? L : 0, b);
+        }
       }
       // ---------------- upward sweep (reverse order): rows back by bulk copies into the idle input ring ----------------
       asm volatile("fence.proxy.async.global;" ::: "memory");  // this lane's row stores (generic proxy) before the bulk loads (async proxy)
@@ -1121,6 +1227,13 @@ int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
   const size_t per_cta = (size_t)L * v5::LW6_ROW;
 #define LW6(F, T, D, C, CL) launch_clustered(ctx, v5::lw_solver_v6<F, T, D, C, CL>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv, tm_cld)
 #define LW6C(F, T, D, CL) (compact ? LW6(F, T, D, true, CL) : LW6(F, T, D, false, CL))
+  if (p.bnd_up) {   // by-band outputs: materialised sources, no clouds, default arithmetic (what rrnn_rte_lw_byband passes)
+    if (compact || cld || fast || !p.bnd_dn || p.nbnd * 16 != G) return -1;
+#define LW6B(T, D) launch_clustered(ctx, v5::lw_solver_v6<false, T, D, false, false, true>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv, tm_cld)
+    if (top) return LW6B(true, true);
+    return dn_ext ? LW6B(false, true) : LW6B(false, false);
+#undef LW6B
+  }
   if (cld) {
     if (top) return LW6C(false, true, true, true);
     return dn_ext ? LW6C(false, false, true, true) : LW6C(false, false, false, true);
@@ -1165,6 +1278,14 @@ int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   const bool top = p.top_at_1 != 0;
 #define SW6(F, GMODE, T) launch_clustered(ctx, v5::sw_solver_v6<F, GMODE, T>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
 #define SW6T(F, GMODE) (top ? SW6(F, GMODE, true) : SW6(F, GMODE, false))
+  if (p.bnd_up) {   // by-band outputs (rrnn_rte_sw_byband): g == 0 or a g array, no pending clouds
+    if (gm == 2 || !p.bnd_dn || !p.bnd_dir || p.nbnd * 16 != G) return -1;
+#define SW6B(F, GMODE) (top ? launch_clustered(ctx, v5::sw_solver_v6<F, GMODE, true, true>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g) \
+                            : launch_clustered(ctx, v5::sw_solver_v6<F, GMODE, false, true>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g))
+    if (fast) return gm == 1 ? SW6B(true, 1) : SW6B(true, 0);
+    return gm == 1 ? SW6B(false, 1) : SW6B(false, 0);
+#undef SW6B
+  }
   if (fast) return gm == 2 ? SW6T(true, 2) : (gm == 1 ? SW6T(true, 1) : SW6T(true, 0));
   return gm == 2 ? SW6T(false, 2) : (gm == 1 ? SW6T(false, 1) : SW6T(false, 0));
 #undef SW6T

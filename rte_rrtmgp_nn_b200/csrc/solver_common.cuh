@@ -145,6 +145,11 @@ struct LwParams {
   // clouds whose increment has not been applied to tau (packed kernel only; null otherwise): tau += cld_tau(band(g)) happens in
   // the solver's registers (inc_1scalar_by_1scalar_bybnd, rte/kernels/mo_optical_props_kernels.F90:358-378); needs gpt2band
   const float* cld_tau = nullptr;     // (16,nlay,ncol) by-band cloud optical depth, rows padded to 16 bands
+  // by-band fluxes (nbnd,nlay+1,ncol) straight from the packed kernel (null otherwise): the per-level sums stop at a band (every
+  // band = 16 consecutive g-points starting at a multiple of 16; checked by the caller) -- ty_fluxes_byband without g-point fluxes
+  float* bnd_up = nullptr;
+  float* bnd_dn = nullptr;
+  int nbnd = 0;
 };
 
 
@@ -167,6 +172,11 @@ struct SwParams {
   // by-band products t2 = tau_c | s2 = tau_c ssa_c | sg2 = tau_c ssa_c g_c, three 16-band segments per (layer, column) row
   const float* cld = nullptr;         // (48,nlay,ncol)
   const int* gpt2band = nullptr;      // (ngpt) 0-based band of each g-point
+  // by-band fluxes (nbnd,nlay+1,ncol) straight from the packed kernel (null otherwise; see LwParams)
+  float* bnd_up = nullptr;
+  float* bnd_dn = nullptr;
+  float* bnd_dir = nullptr;
+  int nbnd = 0;
 };
 
 

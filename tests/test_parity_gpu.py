@@ -1042,9 +1042,90 @@ def test_driver_replicas(gpu_ctx, tmp_path):
             assert f.shape(f"{band}_flux_up") == (43, ncol) and np.array_equal(f.read_field(f"{band}_flux_up").T, out[0])
 
 
-def test_byband_and_net_fluxes_match_oracle(gpu_ctx):
+@pytest.fixture
+def byband_general_route():
+    """ty_fluxes_byband the reference's way: g-point fluxes from the general kernels, then sum_byband (bit-exact sums in g-point order)."""
+    from rte_rrtmgp_nn_b200 import api
+    api.BYBAND_FROM_SOLVER = False
+    yield
+    api.BYBAND_FROM_SOLVER = True
+
+
+def test_byband_fluxes_from_the_tuned_solvers(gpu_ctx):
+    """rrnn_rte_{lw,sw}_byband: ty_fluxes_byband straight from the packed solvers (their per-level sums stop at a band on the way to
+    the broadband sum; no g-point fluxes, no general kernel).  Against the general route (g-point fluxes + sum_byband) and the oracle,
+    both orientations, g = 0 and g != 0, three quadrature angles, ragged last layer group; the broadband fluxes are the tuned
+    kernel's own, bit for bit."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api, spectral
+    torch = _torch()
+    rng = np.random.default_rng(78)
+    mk = lambda *s_: torch.zeros(s_, device="cuda")
+    for top in (True, False):
+        # ---- SW
+        G, L, C_ = 224, 61, 300       # 61 = 7 groups of 8 + a ragged group of 5
+        kd = spectral.synthetic_kdist_sw(G)
+        k_dist = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_dist.load(kd) == ""
+        tau = rng.gamma(0.4, 1.5, size=(C_, L, G)).astype(np.float32); ssa = rng.uniform(0.0, 0.999, size=(C_, L, G)).astype(np.float32)
+        mu0 = rng.uniform(0.05, 1.0, size=C_).astype(np.float32); inc = rng.uniform(0.5, 8.0, size=(C_, G)).astype(np.float32)
+        ad = rng.uniform(0.0, 0.9, size=(C_, G)).astype(np.float32); af = rng.uniform(0.0, 0.9, size=(C_, G)).astype(np.float32)
+        atmos = api.ty_optical_props_2str(); assert atmos.alloc_2str(C_, L, k_dist) == ""
+        atmos.tau.copy_(torch.from_numpy(tau)); atmos.ssa.copy_(torch.from_numpy(ssa))
+        for with_g in (False, True):
+            g = rng.uniform(-0.2, 0.9, size=(C_, L, G)).astype(np.float32) if with_g else np.zeros_like(tau)
+            if with_g:
+                atmos.g = torch.from_numpy(g).cuda()
+            else:
+                atmos._g, atmos.g_is_zero = None, True
+            bb = api.ty_fluxes_byband(mk(C_, L + 1), mk(C_, L + 1), mk(C_, L + 1), mk(C_, L + 1), mk(C_, L + 1, 14), mk(C_, L + 1, 14),
+                                      mk(C_, L + 1, 14), mk(C_, L + 1, 14))
+            n0 = gpu_ctx.launch_count
+            assert api.rte_sw(atmos, top, mu0, inc, ad, af, bb) == ""
+            assert gpu_ctx.launch_count - n0 <= 3      # the solver + two elementwise differences; no general kernel, no sum_byband
+            fl = api.ty_fluxes_broadband(mk(C_, L + 1), mk(C_, L + 1), None, mk(C_, L + 1))
+            assert api.rte_sw(atmos, top, mu0, inc, ad, af, fl) == ""
+            assert torch.equal(bb.flux_up, fl.flux_up) and torch.equal(bb.flux_dn, fl.flux_dn) and torch.equal(bb.flux_dn_dir, fl.flux_dn_dir)
+            assert torch.equal(bb.flux_net, fl.flux_dn - fl.flux_up) and torch.equal(bb.bnd_flux_net, bb.bnd_flux_dn - bb.bnd_flux_up)
+            for b, f in ((bb.bnd_flux_up, fl.flux_up), (bb.bnd_flux_dn, fl.flux_dn), (bb.bnd_flux_dn_dir, fl.flux_dn_dir)):
+                assert float((b.sum(-1) - f).abs().max()) <= 2e-6 * float(f.abs().max())     # the bands add up to the broadband flux
+            ref = O.sw_solver_2stream_gpt(top, inc, np.zeros_like(inc), tau, ssa, g, mu0, ad, af)
+            r64 = O.sw_solver_2stream_gpt(top, inc, np.zeros_like(inc), tau, ssa, g, mu0, ad, af, fast="f64")
+            for k, got in enumerate((bb.bnd_flux_up, bb.bnd_flux_dn, bb.bnd_flux_dn_dir)):
+                want32, want64 = O.sum_byband(ref[3 + k], kd["band_lims_gpt"]), O.sum_byband(r64[3 + k], kd["band_lims_gpt"], fast="f64")
+                H.assert_within_reference_noise(got.cpu().numpy(), want32, want64, H.FLUX_TOL, f"SW by-band flux {k} (top_at_1={top}, g={with_g})")
+        # ---- LW, one and three angles
+        kdl = spectral.synthetic_kdist_lw(256)
+        kl = api.ty_gas_optics_rrtmgp(gpu_ctx); assert kl.load(kdl) == ""
+        Ll = 61
+        op = api.ty_optical_props_1scl(); assert op.alloc_1scl(C_, Ll, kl) == ""
+        src = api.ty_source_func_lw(); assert src.alloc(C_, Ll, kl) == ""
+        op.tau.copy_(torch.from_numpy(rng.gamma(0.4, 1.5, size=(C_, Ll, 256)).astype(np.float32)))
+        src.lay_source.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=(C_, Ll, 256)).astype(np.float32)))
+        src.lev_source.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=(C_, Ll + 1, 256)).astype(np.float32)))
+        src.sfc_source.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, size=(C_, 256)).astype(np.float32)))
+        emis = np.full((C_, 16), 0.98, np.float32)
+        for nang in (1, 3):
+            bbl = api.ty_fluxes_byband(mk(C_, Ll + 1), mk(C_, Ll + 1), mk(C_, Ll + 1), None, mk(C_, Ll + 1, 16), mk(C_, Ll + 1, 16), mk(C_, Ll + 1, 16))
+            assert api.rte_lw(op, top, src, emis, bbl, n_gauss_angles=nang) == ""
+            fll = api.ty_fluxes_broadband(mk(C_, Ll + 1), mk(C_, Ll + 1))
+            assert api.rte_lw(op, top, src, emis, fll, n_gauss_angles=nang) == ""
+            assert torch.equal(bbl.flux_up, fll.flux_up) and torch.equal(bbl.flux_dn, fll.flux_dn)
+            assert torch.equal(bbl.bnd_flux_net, bbl.bnd_flux_dn - bbl.bnd_flux_up)
+            api.BYBAND_FROM_SOLVER = False
+            try:      # the general route: g-point fluxes (general kernel) summed by band in g-point order
+                gen = api.ty_fluxes_byband(mk(C_, Ll + 1), mk(C_, Ll + 1), None, None, mk(C_, Ll + 1, 16), mk(C_, Ll + 1, 16))
+                assert api.rte_lw(op, top, src, emis, gen, n_gauss_angles=nang) == ""
+            finally:
+                api.BYBAND_FROM_SOLVER = True
+            for a, b in ((bbl.bnd_flux_up, gen.bnd_flux_up), (bbl.bnd_flux_dn, gen.bnd_flux_dn)):
+                assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+                assert float((a.sum(-1) - b.sum(-1)).abs().max()) <= 2e-5 * float(b.sum(-1).abs().max())
+
+
+def test_byband_and_net_fluxes_match_oracle(gpu_ctx, byband_general_route):
     """ty_fluxes_byband (extensions/mo_fluxes_byband.F90) and flux_net: bit-exact against the oracle's serial
-    sums on the kernel entry points, and through rte_sw / rte_lw with the by-band flux type."""
+    sums on the kernel entry points, and through rte_sw / rte_lw with the by-band flux type (the general route: g-point fluxes from
+    the general kernels + sum_byband; the tuned-solver route has its own test above)."""
     import oracle as O
     from rte_rrtmgp_nn_b200 import api, _lib, spectral
     torch = _torch()

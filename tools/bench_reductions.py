@@ -65,5 +65,5 @@ wnet = api.ty_fluxes_broadband(z(ncol, L + 1), z(ncol, L + 1), z(ncol, L + 1), z
 line("rte_sw broadband + flux_net", timed(lambda: api.rte_sw(atmos, True, mu0, inc, alb, alb, wnet)), gb_in)
 bb = api.ty_fluxes_byband(z(ncol, L + 1), z(ncol, L + 1), z(ncol, L + 1), z(ncol, L + 1), z(ncol, L + 1, 14), z(ncol, L + 1, 14),
                           z(ncol, L + 1, 14), z(ncol, L + 1, 14))
-line("rte_sw with ty_fluxes_byband (general kernel + g-point temporaries + reductions)",
+line("rte_sw with ty_fluxes_byband (by-band sums inside the tuned solver; was: general kernel + g-point temporaries + reductions)",
      timed(lambda: api.rte_sw(atmos, True, mu0, inc, alb, alb, bb), reps=5, trials=2), gb_in + 3 * 2 * 4e-9 * ncol * (L + 1) * G)

@@ -1,6 +1,6 @@
 """Executed warp instructions and stall samples per CUDA SOURCE LINE of one kernel of an ncu report.
 
-    python tools/ncu_by_line.py report.ncu-rep <mangled-kernel-substring> <units> [top N] [file.cu]
+    [NCU_KERNEL="<demangled substring>"] python tools/ncu_by_line.py report.ncu-rep <mangled-kernel-substring> <units> [top N] [file.cu]
 
 ncu's CSV source page lists SASS only; nvdisasm -g of the shipped library carries the line table.  Both list the kernel's
 instructions in address order, so they are joined by index.  `units` divides the counts (e.g. columns x layers x chunks), so the
@@ -40,7 +40,9 @@ blk, cur = None, None
 for r in rows:
     if r and r[0] == "Kernel Name":
         cur = {"name": r[1], "hdr": None, "rows": []}
-        if blk is None and re.sub(r"[^A-Za-z0-9_]", "", sub.split("ILb")[0][-16:]) in re.sub(r"[^A-Za-z0-9_]", "", r[1]):
+        want = os.environ.get("NCU_KERNEL")    # substring of the DEMANGLED name in the report (default: derived from the mangled one)
+        hit = (want in r[1]) if want else (re.sub(r"[^A-Za-z0-9_]", "", re.split(r"I[LN]", sub)[0][-16:]) in re.sub(r"[^A-Za-z0-9_]", "", r[1]))
+        if blk is None and hit:
             blk = cur
     elif cur is not None and r and r[0] == "Address":
         cur["hdr"] = r
