@@ -74,8 +74,11 @@ static size_t lw_ws_bytes(int G, int L, int nc, bool compact) {
 // rrnn_lw_fluxes keeps the sources factored between its two kernels when both take that form (gas_optics_tc.cu,
 // rte_solvers_v5.cu); the fluxes are bit-identical either way (tested).
 static bool lw_compact(const rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t* const* models, int nmodels, int L) {
-  return ctx->lw_compact_source && ctx->solver_variant == 0 && lw_v5_supports(kd->ngpt, L) &&
-         rrnn_gas_optics_tc_can(ctx, 0, kd, models, nmodels, L, true);
+  if (!(ctx->lw_compact_source && ctx->solver_variant == 0 && lw_v5_supports(kd->ngpt, L))) return false;
+  if (kd->ngpt & 1) return false;
+  for (int g = 0; g + 1 < kd->ngpt; g += 2)   // the packed solver looks a band value up once per pair of g-points
+    if (kd->gpt2band[g] != kd->gpt2band[g + 1]) return false;
+  return rrnn_gas_optics_tc_can(ctx, 0, kd, models, nmodels, L, true);
 }
 static size_t sw_ws_bytes(int G, int L, int nc) {
   return 4 * (align256((size_t)nc * L * G) * 2 + 2 * align256((size_t)nc * G) + align256((size_t)nc));

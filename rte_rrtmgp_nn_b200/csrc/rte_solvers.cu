@@ -481,7 +481,7 @@ namespace rrnn {
 // lev_source = pfrac * planck_lev are formed inside lw_solver_v5 (see there).  Only the default solver variant has it.
 int lw_solver_noscat_compact(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, int nmus, const float* Ds, const float* weights,
                              const float* tau_d, const float* pfrac_d, const float* planck_lay_d, const float* planck_lev_d,
-                             const int* gpt2band_d, const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d,
+                             const int* gpt2band_d, int pairs_in_band, const float* sfc_emis_gpt_d, const float* sfc_source_d, float* flux_up_d,
                              float* flux_dn_d) {
   if (ncol == 0) return 0;
   RRNN_CUDA(cudaSetDevice(ctx->device));
@@ -491,6 +491,7 @@ int lw_solver_noscat_compact(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int 
   p.nchunks = (ngpt + 31) / 32;
   for (int i = 0; i < nmus; ++i) { p.Ds[i] = Ds[i]; p.wts[i] = weights[i]; }
   p.tau = tau_d; p.lay_source = pfrac_d; p.planck_lay = planck_lay_d; p.planck_lev = planck_lev_d; p.gpt2band = gpt2band_d;
+  p.pairs_in_band = pairs_in_band;
   p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
   const int ps = prof_begin(ctx, K_LW_SOLVER);
   const int rc = launch_lw_v6(ctx, p);
@@ -513,7 +514,7 @@ extern "C" int rrnn_lw_solver_noscat_compact(rrnn_ctx_t* ctx, const rrnn_kdist_t
   RRNN_CHECK(tau_d && pfrac_d && planck_lay_d && planck_lev_d && sfc_emis_gpt_d && sfc_source_d && flux_up_d && flux_dn_d,
              "rrnn_lw_solver_noscat_compact: null argument");
   return lw_solver_noscat_compact(ctx, kd->ngpt, nlay, ncol, top_at_1, nmus, Ds, weights, tau_d, pfrac_d, planck_lay_d, planck_lev_d,
-                                  kd->d_gpt2band, sfc_emis_gpt_d, sfc_source_d, flux_up_d, flux_dn_d);
+                                  kd->d_gpt2band, kd_pairs_in_band(kd), sfc_emis_gpt_d, sfc_source_d, flux_up_d, flux_dn_d);
 }
 
 extern "C" int rrnn_sw_solver_2stream(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, int top_at_1, const float* inc_flux_d,
@@ -688,7 +689,7 @@ int lw_solver_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol
   p.nchunks = (kd->ngpt + 31) / 32;
   for (int i = 0; i < nmus; ++i) { p.Ds[i] = Ds[i]; p.wts[i] = weights[i]; }
   p.inc_flux = inc_flux_d; p.tau = tau_d; p.lay_source = lay_d; p.lev_source = lev_d; p.planck_lay = planck_lay_d; p.planck_lev = planck_lev_d;
-  p.gpt2band = kd->d_gpt2band; p.cld_tau = cld_rows_d;
+  p.gpt2band = kd->d_gpt2band; p.cld_tau = cld_rows_d; p.pairs_in_band = kd_pairs_in_band(kd);
   p.sfc_emis = sfc_emis_gpt_d; p.sfc_source = sfc_source_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d;
   const int ps = prof_begin(ctx, K_LW_SOLVER);
   const int rc = launch_lw_v6(ctx, p);
@@ -708,7 +709,7 @@ int sw_solver_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol
   p.ngpt = kd->ngpt; p.nlay = nlay; p.ncol = ncol; p.top_at_1 = top_at_1 ? 1 : 0;
   p.nchunks = (kd->ngpt + 31) / 32;
   p.inc_flux = inc_flux_d; p.inc_flux_dif = inc_flux_dif_d; p.tau = tau_d; p.ssa = ssa_d; p.g = nullptr; p.mu0 = mu0_d;
-  p.cld = cld_rows_d; p.gpt2band = kd->d_gpt2band;
+  p.cld = cld_rows_d; p.gpt2band = kd->d_gpt2band; p.pairs_in_band = kd_pairs_in_band(kd);
   p.alb_dir = alb_dir_d; p.alb_dif = alb_dif_d; p.flux_up = flux_up_d; p.flux_dn = flux_dn_d; p.flux_dir = flux_dir_d;
   const int ps = prof_begin(ctx, K_SW_SOLVER);
   const int rc = launch_sw_v6(ctx, p, ctx->fast_math || ctx->sw_fast_math);

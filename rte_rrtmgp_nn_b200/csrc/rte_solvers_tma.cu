@@ -42,13 +42,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 #ifndef RRNN_MBAR_SUSPEND_NS
 #define RRNN_MBAR_SUSPEND_NS 1000   // suspend-time hint of mbarrier.try_wait: how long the hardware may park the thread per attempt
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)RRNN_MBAR_SUSPEND_NS) : "memory");
+  return ok;
+}
+// the phase has not completed at the first attempt: poll (kept out of line: the hot loops only carry the first attempt)
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   unsigned spins = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)RRNN_MBAR_SUSPEND_NS) : "memory");
-    if (!ok && ++spins > (1u << 26)) __trap();  // a wait of seconds is a protocol bug: fail the launch instead of hanging
-  }
+  while (!mbar_try(bar, parity))
+    if (++spins > (1u << 26)) __trap();  // a wait of seconds is a protocol bug: fail the launch instead of hanging
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint64_t pol) {
@@ -109,8 +115,11 @@ __device__ __forceinline__ void exp_and_complement2(f2 x, f2& t, f2& omt) {
 // lines (no write-back; the contents become undefined until the next column's downward sweep rewrites them in full) saves
 // the DRAM write of every line that was still resident -- the L2 only writes dirty lines back when it evicts them.
 __device__ __forceinline__ void discard_scratch(const uint8_t* base, uint32_t bytes, int lane) {
-  if (RRNN_V5_DISCARD)
-    for (uint32_t o = (uint32_t)lane * 128u; o < bytes; o += 32u * 128u) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + o) : "memory");
+  if (RRNN_V5_DISCARD) {   // at most 8 rows of 768 B = 48 lines: two rounds of the 32 lanes, no loop
+    const uint32_t o = (uint32_t)lane * 128u;
+    if (o < bytes) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + o) : "memory");
+    if (o + 4096u < bytes) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + o + 4096u) : "memory");
+  }
 }
 
 // one lane of a converged warp (elect.sync): ptxas then issues the uniform-datapath TMA instructions straight, without
@@ -467,9 +476,9 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
   const int ru = lane & 7;
   const bool rB = (lane & 8) != 0, rW = lane < 16;
   // GM == 2: byte offsets of the bands of this lane's two g-points in a 64-byte table segment
-  uint32_t bo0 = 0, bo1 = 0;
-  if (GM == 2) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
-  auto band_pair = [&](const uint8_t* seg) { return mk2(*reinterpret_cast<const float*>(seg + bo0), *reinterpret_cast<const float*>(seg + bo1)); };
+  uint32_t bo0 = 0;   // (both g-points of a lane lie in one band: SwParams::pairs_in_band, checked by the launcher)
+  if (GM == 2) bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs);
+  auto band_pair = [&](const uint8_t* seg) { return splat2(*reinterpret_cast<const float*>(seg + bo0)); };
 
   NextColumns nx;
   nx.slot = reinterpret_cast<int*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)nwarps * pp.warp_smem);
@@ -814,9 +823,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
   uint8_t* const srow = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * LW6_ROW + (size_t)lane * 8u;
   const uint32_t lane_in = (uint32_t)lane * 8u;   // byte offset of this lane's pair in a 256-byte row
   // COMPACT: byte offsets of the bands of this lane's two g-points in a 64-byte row of the Planck tables
-  uint32_t bo0 = 0, bo1 = 0;
-  if (COMPACT || CLD) { bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs); bo1 = 4u * (uint32_t)__ldg(p.gpt2band + gs + 1); }
-  auto band_pair = [&](const uint8_t* row) { return mk2(*reinterpret_cast<const float*>(row + bo0), *reinterpret_cast<const float*>(row + bo1)); };
+  // (both g-points of a lane lie in one band -- LwParams::pairs_in_band, checked by the launcher -- so one look-up serves the pair)
+  uint32_t bo0 = 0;
+  if (COMPACT || CLD) bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs);
+  auto band_pair = [&](const uint8_t* row) { return splat2(*reinterpret_cast<const float*>(row + bo0)); };
   const int ru = lane & 7;      // the reduced value (layer within its group) this lane ends up with; lanes < 8 write
   const bool rW = lane < 8;
 
@@ -843,7 +853,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
     f2 ent0;
     if (COMPACT) {
       const float* bv0 = p.planck_lev + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * 16;
-      ent0 = ldg2(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs) * mk2(__ldg(bv0 + (bo0 >> 2)), __ldg(bv0 + (bo1 >> 2)));
+      ent0 = ldg2(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs) * splat2(__ldg(bv0 + (bo0 >> 2)));
     } else {
       ent0 = ldg2(p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs);
     }
@@ -1195,6 +1205,7 @@ int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
     if ((uintptr_t)q & 15) return -1;
   const bool cld = p.cld_tau != nullptr;
   if (cld && (!p.gpt2band || ctx->fast_math)) return -1;   // (the cloud variants are built for the default arithmetic only)
+  if ((cld || compact) && !p.pairs_in_band) return -1;     // a lane's two g-points share their band look-ups
   for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
     if ((uintptr_t)q & 7) return -1;
   v5::LwV5Params pp;
@@ -1254,7 +1265,7 @@ int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   const int csize = (G + 63) / 64;
   constexpr int U = 8, SB = 2;
   const int gm = p.cld ? 2 : (p.g ? 1 : 0);
-  if (p.cld && (p.g || !p.gpt2band)) return -1;   // clouds are folded in on top of gas properties with g == 0 only
+  if (p.cld && (p.g || !p.gpt2band || !p.pairs_in_band)) return -1;   // clouds are folded in on top of gas properties with g == 0 only
   const int S = gm == 0 ? RRNN_V6_SW_S : 2;  // (three input arrays / two + cloud rows: two stages already hold the upward sweep's ring)
   if ((G & 3) || csize > 8 || L < U) return -1;
   for (const void* q : {(const void*)p.tau, (const void*)p.ssa, (const void*)p.g, (const void*)p.cld})

@@ -142,6 +142,7 @@ struct LwParams {
   const float* planck_lay = nullptr;  // (16,nlay,ncol)   band Planck function at T_lay
   const float* planck_lev = nullptr;  // (16,nlay+1,ncol) ... at T_lev
   const int* gpt2band = nullptr;      // (ngpt) 0-based band of each g-point
+  int pairs_in_band = 0;              // every pair of g-points (2i, 2i+1) lies in ONE band (required by the table look-ups below)
   // clouds whose increment has not been applied to tau (packed kernel only; null otherwise): tau += cld_tau(band(g)) happens in
   // the solver's registers (inc_1scalar_by_1scalar_bybnd, rte/kernels/mo_optical_props_kernels.F90:358-378); needs gpt2band
   const float* cld_tau = nullptr;     // (16,nlay,ncol) by-band cloud optical depth, rows padded to 16 bands
@@ -172,6 +173,7 @@ struct SwParams {
   // by-band products t2 = tau_c | s2 = tau_c ssa_c | sg2 = tau_c ssa_c g_c, three 16-band segments per (layer, column) row
   const float* cld = nullptr;         // (48,nlay,ncol)
   const int* gpt2band = nullptr;      // (ngpt) 0-based band of each g-point
+  int pairs_in_band = 0;              // every pair of g-points (2i, 2i+1) lies in ONE band (required with cld)
   // by-band fluxes (nbnd,nlay+1,ncol) straight from the packed kernel (null otherwise; see LwParams)
   float* bnd_up = nullptr;
   float* bnd_dn = nullptr;
@@ -181,6 +183,15 @@ struct SwParams {
 
 
 }  // namespace rrnn
+
+// every pair of g-points (2i, 2i+1) in one band?  (all of RRTMGP's k-distributions: bands of 16.)  The packed solvers carry a pair per
+// lane and look a band value up ONCE per pair.
+inline int kd_pairs_in_band(const rrnn_kdist_t* kd) {
+  if (kd->ngpt & 1) return 0;
+  for (int g = 0; g + 1 < kd->ngpt; g += 2)
+    if (kd->gpt2band[g] != kd->gpt2band[g + 1]) return 0;
+  return 1;
+}
 
 // ---- host-side launch helpers
 inline int ensure_scratch(rrnn_ctx_t* ctx, size_t bytes) {
