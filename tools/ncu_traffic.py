@@ -9,7 +9,8 @@ ix = {k: i for i, k in enumerate(hdr)}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 def val(r, k):
     return float(r[ix[k]].replace(",", "")) * scale[units[ix[k]]]
-names = {"gas_optics_lw": ("gas_optics_tc_kernel<0>", "gas_optics_lw"), "gas_optics_sw": ("gas_optics_tc_kernel<1>", "gas_optics_sw"),
+names = {"gas_optics_lw": ("gas_optics_tc_kernel<0>", "gas_optics_tc_kernel<0,", "gas_optics_lw"),
+         "gas_optics_sw": ("gas_optics_tc_kernel<1>", "gas_optics_tc_kernel<1,", "gas_optics_sw"),
          "lw_solver": ("lw_solver",), "sw_solver": ("sw_solver",)}
 res = {}
 for r in rows[2:]:
