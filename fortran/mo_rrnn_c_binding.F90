@@ -69,7 +69,9 @@ module mo_rrnn_c_binding
     end function rrnn_ctx_synchronize
     ! Run-time flags of rte/mo_rte_rrtmgp_config.F90:23-40. lw_source_bug_compat = 1 (default) reproduces lw_source_noscat
     ! ignoring top_at_1 (rte/kernels/mo_rte_solver_kernels.F90:770-773); 0 orients the level sources physically for top_at_1 =
-    ! false.
+    ! false. solver_wide = 1 (default): the LW no-scattering solver carries four g-points per lane where the shape fits
+    ! (lw_solver_v7: ngpt >= 128 and a multiple of 4, nlay >= 8); 0: two per lane (lw_solver_v6). The two differ in the order of
+    ! the sum over g-points only (<= 3e-7 of the flux).
     function rrnn_ctx_set_flag(ctx, name_c, val) bind(C, name="rrnn_ctx_set_flag") result(rc)
       import :: c_char, c_int, c_ptr
       type(c_ptr), value :: ctx

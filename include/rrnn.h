@@ -61,7 +61,9 @@ RRNN_API void* rrnn_ctx_stream(rrnn_ctx_t* ctx);
 RRNN_API int rrnn_ctx_synchronize(rrnn_ctx_t* ctx);
 /* Run-time flags of rte/mo_rte_rrtmgp_config.F90:23-40.  lw_source_bug_compat = 1 (default) reproduces
  * lw_source_noscat ignoring top_at_1 (rte/kernels/mo_rte_solver_kernels.F90:770-773); 0 orients the
- * level sources physically for top_at_1 = false. */
+ * level sources physically for top_at_1 = false.  solver_wide = 1 (default): the LW no-scattering solver carries four g-points
+ * per lane where the shape fits (lw_solver_v7: ngpt >= 128 and a multiple of 4, nlay >= 8); 0: two per lane (lw_solver_v6).
+ * The two differ in the order of the sum over g-points only (<= 3e-7 of the flux). */
 RRNN_API int rrnn_ctx_set_flag(rrnn_ctx_t* ctx, const char* name, int value);
 /* Per-kernel device timing with CUDA events on the context's stream.  rrnn_ctx_profile(ctx, 1) enables and
  * resets; rrnn_ctx_profile_read synchronises and returns the summed duration and launch count of kernel

@@ -386,6 +386,7 @@ extern "C" int rrnn_ctx_create(int device, void* stream, rrnn_ctx_t** out) {
   if (const char* e = getenv("RRNN_SW_FAST_MATH")) c->sw_fast_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("RRNN_SOLVER_BUFFER")) c->solver_buffer = atoi(e);
   if (const char* e = getenv("RRNN_NN_TENSOR_CORES")) c->nn_tensor_cores = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("RRNN_SOLVER_WIDE")) c->solver_wide = atoi(e) ? 1 : 0;
   *out = c;
   return 0;
 }
@@ -503,6 +504,7 @@ extern "C" int rrnn_ctx_set_flag(rrnn_ctx_t* c, const char* name, int value) {
   else if (s == "check_values") c->check_values = value ? 1 : 0;
   else if (s == "solver_scratch_mb") c->solver_scratch_mb = value;
   else if (s == "solver_warps") c->solver_warps = value;
+  else if (s == "solver_wide") c->solver_wide = value;
   else return fail("rrnn_ctx_set_flag: unknown flag " + s);
   return 0;
 }

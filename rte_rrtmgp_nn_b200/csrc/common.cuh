@@ -72,6 +72,7 @@ struct rrnn_ctx {
   int solver_variant = 0;  // 0 = TMA-staged packed kernels (rte_solvers_tma.cu), 1 = one g-point per lane (rte_solvers.cu)
   int solver_scratch_mb = 0;  // L2 budget of the packed kernels' reverse-sweep scratch (0 = default)
   int solver_warps = 0;       // solvers per CTA in the v5 kernels (0 = default)
+  int solver_wide = 1;        // 1: four g-points per lane in the LW solver where the shape fits (lw_solver_v7); 0: lw_solver_v6
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   int* col_counter = nullptr;  // the packed solvers' dynamic column assignment (one int, zeroed before every launch)

@@ -59,6 +59,8 @@ __device__ __forceinline__ f2 exp2x(f2 y) {
   const f2 r = fma2(y, L2E, mk2(-tx, -ty));  // y*L2E - t
   return fma2(e0, r * splat2(0.6931471805599453f), e0);
 }
+// 2^t per component, the bare MUFU
+__device__ __forceinline__ f2 ex2_raw(f2 t) { float x, y; unpack2(t, x, y); return mk2(mufu_ex2(x), mufu_ex2(y)); }
 // 1/x: MUFU seed (+ one Newton step unless FAST): within ~1 ulp, branch-free
 template <bool FAST>
 __device__ __forceinline__ f2 rcp2(f2 x) {

@@ -197,6 +197,13 @@ __device__ __forceinline__ void mul2(float& a0, float& a1, float b0, float b1) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(r));
 }
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {  // (a0,a1) += (b0,b1), each lane IEEE like FADD
+  uint64_t a, b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(r));
+}
 __device__ __forceinline__ void mul2to(float& d0, float& d1, float a0, float a1, float b) {  // (d0,d1) = (a0,a1) * b
   uint64_t a, bb, r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
@@ -705,7 +712,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         // refilled while the TMA store of the other is still reading -- no blocking wait, twice the stores.
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          if (lane == 0) bulk_wait_read<1>();  // the store issued two halves ago has read this half
+          if (elect_one()) bulk_wait_read<1>();  // the store issued two halves ago has read this half
           __syncwarp();
           if (slot_row >= 0) {
             uint8_t* row = stage + sbuf * (STAGE_BYTES / 2) + slot_row * 64;
@@ -717,7 +724,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {   // (bulk async-groups are per thread: elect.sync picks the same lane every time, waits included)
             // (a half tile that starts past the last g-point -- ngpt = 112 -- is not stored; one that starts inside is clipped)
             if (dest < nrows_arr && g0 + 16 * hf < G && !(p.dbg_flags & 2)) tma_store_2d(tm, stage_a + sbuf * (STAGE_BYTES / 2), g0 + 16 * hf, (int)dest);
             bulk_commit();
@@ -726,7 +733,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
         return;
       }
-      if (lane == 0) bulk_wait_read<1>();  // the staging tile about to be overwritten has been read by its TMA store
+      if (elect_one()) bulk_wait_read<1>();  // the staging tile about to be overwritten has been read by its TMA store
       __syncwarp();
       if (slot_row >= 0) {
         uint8_t* row = stage + sbuf * STAGE_BYTES + slot_row * 128;
@@ -737,7 +744,7 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         // a box that starts inside the tensor may hang over its end: those rows are clipped by the TMA unit
         if (dest < nrows_arr && !(p.dbg_flags & 2)) tma_store_2d(tm, stage_a + sbuf * STAGE_BYTES, g0, (int)dest);
         bulk_commit();
@@ -813,14 +820,14 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3_0 + g0 + 4 * j4);
-            z[4 * j4] += b.x; z[4 * j4 + 1] += b.y; z[4 * j4 + 2] += b.z; z[4 * j4 + 3] += b.w;
+            add2(z[4 * j4], z[4 * j4 + 1], b.x, b.y); add2(z[4 * j4 + 2], z[4 * j4 + 3], b.z, b.w);
           }
         }
         if (!fold1) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(b3_1 + g0 + 4 * j4);
-            z[32 + 4 * j4] += b.x; z[32 + 4 * j4 + 1] += b.y; z[32 + 4 * j4 + 2] += b.z; z[32 + 4 * j4 + 3] += b.w;
+            add2(z[32 + 4 * j4], z[32 + 4 * j4 + 1], b.x, b.y); add2(z[32 + 4 * j4 + 2], z[32 + 4 * j4 + 3], b.z, b.w);
           }
         }
         float o[32];
@@ -937,7 +944,8 @@ gas_optics_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
         }
       }
     }
-    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+    if (elect_one()) bulk_wait_all();
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");

@@ -90,6 +90,14 @@ __device__ __forceinline__ f2 sel2(bool mx, bool my, f2 a, f2 b) {
   return mk2(mx ? ax : bx, my ? ay : by);
 }
 
+// a * b as an instruction of its own.  ptxas contracts a single-use mul.rn.f32x2 into the add.rn / sub.rn.f32x2 that consumes it
+// (seen in SASS: FMUL2 + FADD2 -> FFMA2; the explicit .rn does not stop it for the packed forms), which changes the last bit of
+// the factored Planck sources pfrac * B(T) against the materialised arrays.  An FMA with a -0 addend is the same product, rounded
+// once -- but ptxas folds a LITERAL -0 addend back into a multiply and contracts that (lw_solver_v7, bottom-up: 32 FADD2 became
+// FFMA2).  So the -0 comes from the kernel parameters (LwV5Params::neg_zero, set by the launchers): a value the compiler cannot
+// see through, an FFMA2 that stays one, no extra instruction.
+__device__ __forceinline__ f2 mul_keep(f2 a, f2 b, f2 nz) { return fma2(a, b, nz); }
+
 // exp(-x) and 1 - exp(-x) for x >= 0 without the cancellation of the literal 1 - exp(-x) at small x (common.cuh,
 // exp_and_complement): degree-7 Taylor polynomial of expm1 below 0.35, the literal form above.
 template <bool FAST>
@@ -151,6 +159,7 @@ struct LwV5Params {
   int ngroups;
   int warp_smem;  // bytes of shared memory per warp
   int* next_col;  // dynamic column assignment (see next_columns)
+  float neg_zero = -0.0f;  // see mul_keep
 };
 
 // ---------------------------------------------------------------------------------------------------- SW
@@ -231,6 +240,8 @@ __device__ __forceinline__ void two_stream2_batch(const f2 (&tau)[U], const f2 (
       alpha2[u] = fma2(gamma1[u], gamma3[u], gamma2[u] * gamma4[u]);
     } else {
       // g = 0 (always, on the NN path): gamma3 = gamma4 = 1/2 exactly, alpha1 = alpha2 = (gamma1 + gamma2)/2
+      // (not w0 * 0.75: ptxas contracts a single multiply into the sums below and the bits leave the reference's; the trailing
+      // exact * 0.25 is harmless when contracted)
       gamma1[u] = fnma2(w0[u], splat2(5.0f), splat2(8.0f)) * quarter;
       gamma2[u] = (splat2(3.0f) * w0[u]) * quarter;
       gamma3[u] = half;
@@ -383,6 +394,23 @@ __device__ __forceinline__ float tr_reduce_bands(const float (&v)[N], float* tr,
   bB = (N == 16) ? s[2] + s[N / 4 - 1] : 0.0f;
   float t = (N == 16) ? bA + bB : bA;
   if (NRD == 4) t += __shfl_xor_sync(0xffffffffu, t, 8);
+  t += __shfl_xor_sync(0xffffffffu, t, 16);
+  return t;
+}
+// tr_reduce<8> for the wide kernels (four g-points per lane): the 8 lanes a reader adds are 32 g-points = TWO bands, its two float4
+// partial sums; same association as tr_reduce<8>, so the broadband sum keeps its bits
+__device__ __forceinline__ float tr_reduce_bands_wide(const float (&v)[8], float* tr, int lane, float& bA, float& bB) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tr[i * TR_PITCH + lane] = v[i];
+  __syncwarp();
+  const int idx = lane & 7, part = lane >> 3;
+  const float4* src = reinterpret_cast<const float4*>(tr + idx * TR_PITCH + part * 8);
+  const float4 q0 = src[0], q1 = src[1];
+  bA = (q0.x + q0.y) + (q0.z + q0.w);
+  bB = (q1.x + q1.y) + (q1.z + q1.w);
+  float t = bA + bB;
+  t += __shfl_xor_sync(0xffffffffu, t, 8);
   t += __shfl_xor_sync(0xffffffffu, t, 16);
   return t;
 }
@@ -789,6 +817,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
   constexpr int STAGE = OFF_CLD + (CLD ? U * 64 : 0);
   static_assert(SB * U * LW6_ROW <= S * STAGE, "the upward sweep's stages live in the input ring");
   const LwParams& p = pp.b;
+  const f2 NZ = splat2(pp.neg_zero);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
   const int G = p.ngpt, L = p.nlay;
   const uint64_t pol_in = policy_evict_first();
@@ -853,7 +882,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
     f2 ent0;
     if (COMPACT) {
       const float* bv0 = p.planck_lev + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * 16;
-      ent0 = ldg2(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs) * splat2(__ldg(bv0 + (bo0 >> 2)));
+      ent0 = mul_keep(ldg2(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs), splat2(__ldg(bv0 + (bo0 >> 2))), NZ);
     } else {
       ent0 = ldg2(p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs);
     }
@@ -967,11 +996,11 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
           if (CLD) tau[u] = tau[u] + band_pair(stg + OFF_CLD + rl * 64);   // inc_1scalar_by_1scalar_bybnd
           if (COMPACT) {
             const f2 pf = lds2(base + OFF_PF + rl * 256);
-            lay[u] = pf * band_pair(stg + OFF_3 + rl * 64);
+            lay[u] = mul_keep(pf, band_pair(stg + OFF_3 + rl * 64), NZ);
             // the level below the bottom layer takes that layer's fraction (:667-669); bottom-up sweeps leave through
             // the layer's own level
             const f2 pfx = (TOP && k * U + u != L - 1) ? lds2(base + OFF_PF + (rl + 1) * 256) : pf;
-            ext[u] = pfx * band_pair(stg + OFF_BV + rv * 64);
+            ext[u] = mul_keep(pfx, band_pair(stg + OFF_BV + rv * 64), NZ);
           } else {
             lay[u] = lds2(base + OFF_PF + rl * 256);
             ext[u] = lds2(base + OFF_3 + rv * 256);
@@ -1103,6 +1132,384 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_LW_MINB) lw_solver_v6(
   cluster.sync();  // nobody leaves while another rank may still read its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------------- LW, v7 ("wide")
+// lw_solver_v6 with FOUR ADJACENT g-points per lane: one warp solves 128 g-points of a column, the ceil(ngpt/128) chunk-CTAs of a
+// column form the cluster.  Why: lw_solver_v6 issues ~100 warp instructions per (layer, 64 g-points) of which ~43 are the
+// arithmetic (profiles/r2y_lw_solver_by_source_line.txt); the rest -- TMA issue, mbarrier waits, loop control, the transposition
+// sums, shared-memory loads, scratch stores -- is per WARP and layer, not per g-point.  With four g-points per lane that
+// machinery is spent once per 128 g-points, loads / stores are 16 bytes wide (LDS.128, STG.128: half the memory instructions),
+// one band look-up serves four g-points, and every lane carries two independent packed chains (the latency hiding that
+// v6 gets from a second resident warp).  The per-g-point arithmetic is v6's, instruction for instruction; only the summation
+// order over g-points differs (in-lane (a + b) packed, then the same transposition; two cluster ranks instead of four).
+// Plain clear-sky kernel: clouds and by-band outputs stay on v6.
+struct f4 { f2 a, b; };
+__device__ __forceinline__ f4 lds4(const void* p) { f4 v; lds22(p, v.a, v.b); return v; }
+__device__ __forceinline__ f4 ldg4(const float* p) {
+  f4 v;
+  asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(v.a.v), "=l"(v.b.v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_scr4(uint8_t* p, f4 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.b64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(v.a.v), "l"(v.b.v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ f4 splat4(float x) { f4 v; v.a = splat2(x); v.b = v.a; return v; }
+__device__ __forceinline__ f4 mul4(f4 x, f2 s, f2 nz) { f4 v; v.a = mul_keep(x.a, s, nz); v.b = mul_keep(x.b, s, nz); return v; }   // (the factored sources: see mul_keep)
+__device__ __forceinline__ float hsum4(f4 x) { return hsum2(x.a + x.b); }
+
+// one layer of the downward sweep for a pair of g-points (lw_source_noscat + lw_transport_noscat_dn, :742-776, 950-965):
+// the arithmetic of lw_solver_v6's forward loop, unchanged
+template <bool FAST, bool DN_EXT>
+__device__ __forceinline__ void lw_layer_dn2(f2 tau, f2 lay, f2 ext, f2 ent, f2 D, f2& I, f2& t, f2& sup) {
+  const float tau_thresh = 3.4526698e-4f;  // sqrt(epsilon(1._sp)), mo_rte_solver_kernels.F90:754
+  const f2 tl = tau * D;
+  f2 omt;
+  exp_and_complement2<FAST>(tl, t, omt);
+  const f2 fa = div2<true>(omt, tl) - t;
+  const f2 fb = tl * fnma2(tl, splat2(1.0f / 3.0f), splat2(0.5f));
+  float tx, ty;
+  unpack2(tl, tx, ty);
+  const f2 fact = sel2(tx > tau_thresh, ty > tau_thresh, fa, fb);
+  const f2 f2x = fact + fact;
+  const f2 lev_dn = DN_EXT ? ext : ent;
+  const f2 lev_up = DN_EXT ? ent : ext;
+  const f2 sdn = fma2(f2x, lay - lev_dn, omt * lev_dn);
+  sup = fma2(f2x, lay - lev_up, omt * lev_up);
+  I = fma2(t, I, sdn);
+}
+
+constexpr int LW7_ROW = 1024, LW7_S = 512;   // reverse-sweep row of one layer: t | source_up, 32 lanes x 16 B each
+#ifndef RRNN_V7_LW_S
+#define RRNN_V7_LW_S 2      // stages of the input ring
+#endif
+#ifndef RRNN_V7_LW_MINB
+#define RRNN_V7_LW_MINB 2   // 2 CTAs of 128 threads: the shared memory (23 KB per solver) allows 8 - 9 solver warps per SM
+#endif
+
+// CLD / BND: as in lw_solver_v6 (pending by-band cloud optical depths added in registers; by-band fluxes on the way to the broadband
+// sums -- here a reader of the transposition adds 8 lanes = 32 g-points = TWO bands, so it hands out both halves).
+template <bool FAST, bool TOP, bool DN_EXT, bool COMPACT, bool CLD = false, bool BND = false>
+__global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V7_LW_MINB) lw_solver_v7(const __grid_constant__ LwV5Params pp, const __grid_constant__ CUtensorMap tm_tau,
+                                                   const __grid_constant__ CUtensorMap tm_lay, const __grid_constant__ CUtensorMap tm_lev,
+                                                   const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv,
+                                                   const __grid_constant__ CUtensorMap tm_cld) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int U = 8, S = RRNN_V7_LW_S, SB = 2, H = 4, NH = U / H, RB = 512;   // groups of 8 layers (one TMA box, rows of 128 g-points), computed in halves of 4
+  constexpr int PFR = COMPACT ? (TOP ? U + 1 : U) : U;
+  constexpr int OFF_PF = U * RB, OFF_3 = OFF_PF + PFR * RB, OFF_BV = OFF_3 + U * 64;
+  constexpr int OFF_CLD = COMPACT ? OFF_BV + U * 64 : 3 * U * RB;   // CLD: by-band cloud optical depth (U rows of 64 B)
+  constexpr int STAGE = OFF_CLD + (CLD ? U * 64 : 0);
+  static_assert(SB * U * LW7_ROW <= S * STAGE, "the upward sweep's stages live in the input ring");
+  const LwParams& p = pp.b;
+  const f2 NZ = splat2(pp.neg_zero);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;  // every warp is its own solver
+  const int G = p.ngpt, L = p.nlay;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t pol_buf = policy_evict_last();
+  cg::cluster_group cluster = cg::this_cluster();
+  const int chunk = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)warp * pp.warp_smem;
+  uint8_t* in_ring = smem;                                            // [S][STAGE]
+  float* tr = reinterpret_cast<float*>(in_ring + S * STAGE);          // [8][TR_PITCH]
+  float* part = tr + 8 * TR_PITCH;                                    // [2 sets][2][L+1]
+  const int part_set = 2 * (L + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * part_set);
+  const uint32_t bar_in = smem_u32(bars), bar_bb = smem_u32(bars + S);
+  const uint32_t in_a = smem_u32(in_ring);
+  if (lane == 0) {
+    for (int s = 0; s < S + SB; ++s) mbar_init(bar_in + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t n_in = 0, n_bb = 0;  // groups consumed so far from each ring (stage = n % S, parity = (n / S) & 1)
+
+  const int g = chunk * 128 + 4 * lane;
+  const bool act = g < G;                 // ngpt is a multiple of 4: a lane's four g-points are live or not as a whole
+  const int gs = act ? g : chunk * 128;   // idle lanes shadow the chunk's first quad and contribute zero
+  const float live = act ? 1.0f : 0.0f;
+  const int NG = pp.ngroups;
+  const int NGF = L / U;                  // full groups; the ragged one (if any) is group NGF
+  // this lane's 16-byte slot in the t-segment of scratch row 0 of this solver
+  uint8_t* const srow = reinterpret_cast<uint8_t*>(p.scratch) + ((size_t)blockIdx.x * nwarps + warp) * L * LW7_ROW + (size_t)lane * 16u;
+  const uint32_t lane_in = (uint32_t)lane * 16u;   // byte offset of this lane's four g-points in a 512-byte row
+  // COMPACT: byte offset of the band of this lane's g-points in a 64-byte row of the Planck tables (all four lie in one band:
+  // LwParams::pairs_in_band == 2, checked by the launcher)
+  uint32_t bo0 = 0;
+  if (COMPACT || CLD) bo0 = 4u * (uint32_t)__ldg(p.gpt2band + gs);
+  auto band_val = [&](const uint8_t* row) { return splat2(*reinterpret_cast<const float*>(row + bo0)); };
+  const int ru = lane & 7;      // the reduced value (layer within its group) this lane ends up with; lanes < 8 write
+  const bool rW = lane < 8;
+
+  NextColumns nx;
+  nx.slot = reinterpret_cast<int*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u) + (size_t)nwarps * pp.warp_smem);
+  nx.leader = chunk == 0 && threadIdx.x == 0;
+  nx.fetched = 0;
+  int ncols_done = 0;
+  for (int cb = (blockIdx.x / csize) * nwarps; cb < p.ncol; ++ncols_done) {
+    nx.begin(pp.next_col, nwarps, (int)(gridDim.x / csize) * nwarps);
+    const bool owner = cb + warp < p.ncol;
+    const int col = owner ? cb + warp : p.ncol - 1;
+    float* fup = part + (ncols_done & 1) * part_set;  // this column's partial fluxes [2][L+1]
+    float* fdn = fup + (L + 1);
+    for (int i = lane; i < 2 * (L + 1); i += 32) fup[i] = 0.0f;
+    const size_t gc_off = (size_t)col * G + gs;
+    // (the per-column arrays need only be 8-byte aligned, as for lw_solver_v6: two 8-byte loads)
+    auto ldg4u = [](const float* q) { f4 v; v.a = ldg2(q); v.b = ldg2(q + 2); return v; };
+    const f4 emis = ldg4u(p.sfc_emis + gc_off);
+    const f4 ssrc = ldg4u(p.sfc_source + gc_off);
+    const f4 inc = p.inc_flux ? ldg4u(p.inc_flux + gc_off) : splat4(0.0f);
+    // tensor rows of sweep layer 0: layers (tau, lay_source) and the level towards the surface (lev_source)
+    const int lay0 = col * L + (TOP ? 0 : L - 1);
+    const int ext0 = col * (L + 1) + (TOP ? 1 : L - 1);
+    // lev_source at the level where the sweep enters the atmosphere
+    f4 ent0;
+    if (COMPACT) {
+      const float* bv0 = p.planck_lev + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * 16;
+      ent0 = mul4(ldg4(p.lay_source + ((size_t)col * L + (TOP ? 0 : L - 1)) * G + gs), splat2(__ldg(bv0 + (bo0 >> 2))), NZ);
+    } else {
+      ent0 = ldg4(p.lev_source + ((size_t)col * (L + 1) + (TOP ? 0 : L)) * G + gs);
+    }
+    __syncwarp();
+
+    for (int imu = 0; imu < p.nmus; ++imu) {
+      const f2 D = splat2(p.Ds[imu]);
+      // (idle lanes of a ragged chunk read the zero fill of the TMA boxes beyond ngpt and stay exactly zero: see lw_solver_v6)
+      const float rad_norm = 2.0f * kPi * p.wts[imu];
+      f4 I;   // radn_dn(top) = inc_flux/(2 pi w), :196-201
+      I.a = map2(inc.a, [&](float v) { return v / rad_norm; }) * splat2(live);
+      I.b = map2(inc.b, [&](float v) { return v / rad_norm; }) * splat2(live);
+      {
+        const float s = warp_sum(hsum4(I));
+        if (lane == 0) fdn[TOP ? 0 : L] += rad_norm * s;
+      }
+      // by-band outputs: a band = 16 g-points = 4 lanes; later quadrature angles add to the first one's; quirk Q3 as in lw_solver_v6
+      const size_t bcol = (size_t)col * (L + 1) * (size_t)p.nbnd;
+      const float band_norm = p.nmus == 1 ? 1.0f : rad_norm;
+      auto put_band = [&](float* arr, int lev, int band, float b) {
+        if (owner && band < p.nbnd) {
+          float* q = arr + bcol + (size_t)lev * p.nbnd + band;
+          *q = imu == 0 ? band_norm * b : *q + band_norm * b;
+        }
+      };
+      auto band_sum4 = [&](float v) { v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); return v; };
+      if (BND) {
+        const float b = band_sum4(hsum4(I));
+        if ((lane & 3) == 0) put_band(p.bnd_dn, TOP ? 0 : L, chunk * 8 + (lane >> 2), b);
+      }
+      // one elected lane feeds the input ring: group k -> stage (n_in + k) % S
+      auto issue_in = [&](int k) {
+        if (k < NG) {
+          const uint32_t st = (n_in + (uint32_t)k) % S;
+          int sh;
+          const int rl = box_start<TOP, U>(lay0, k, sh), rv = box_start<TOP, U>(ext0, k, sh);
+          if (elect_one()) {
+            const uint32_t bar = bar_in + 8 * st;
+            const uint32_t dst = in_a + st * STAGE;
+            mbar_expect_tx(bar, STAGE);
+            if (CLD) tma_load_2d(dst + OFF_CLD, &tm_cld, 0, rl, bar, pol_in);
+            tma_load_2d(dst, &tm_tau, chunk * 128, rl, bar, pol_in);
+            tma_load_2d(dst + OFF_PF, &tm_lay, chunk * 128, rl, bar, pol_in);
+            if (COMPACT) {
+              tma_load_2d(dst + OFF_3, &tm_bl, 0, rl, bar, pol_in);
+              tma_load_2d(dst + OFF_BV, &tm_bv, 0, rv, bar, pol_in);
+            } else {
+              tma_load_2d(dst + OFF_3, &tm_lev, chunk * 128, rv, bar, pol_in);
+            }
+          }
+          __syncwarp();
+        }
+      };
+      f4 carry = ent0;  // ent(0)
+      // (the upward sweep of the previous angle / column read its last rows from the ring: refill it only now)
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < S - 1; ++k) issue_in(k);
+      // per-level broadband sums of a group: reduced one group later (their latency overlaps the next group's arithmetic)
+      float pend[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) pend[u] = 0.0f;
+      int pend_k = -1;
+      // by-band: lane l holds layer l & 7 of the bands chunk * 8 + 2 (l / 8) and + 1
+      auto flush_dn = [&]() {
+        float bA = 0.0f, bB = 0.0f;
+        const float t = BND ? tr_reduce_bands_wide(pend, tr, lane, bA, bB) : tr_reduce<U>(pend, tr, lane);
+        const int i = pend_k * U + ru;
+        if (pend_k >= 0 && i < L) {
+          if (rW) fdn[TOP ? i + 1 : L - 1 - i] += rad_norm * t;
+          if (BND) { put_band(p.bnd_dn, TOP ? i + 1 : L - 1 - i, chunk * 8 + 2 * (lane >> 3), bA); put_band(p.bnd_dn, TOP ? i + 1 : L - 1 - i, chunk * 8 + 2 * (lane >> 3) + 1, bB); }
+        }
+      };
+      auto flush_up = [&]() {
+        float bA = 0.0f, bB = 0.0f;
+        const float t = BND ? tr_reduce_bands_wide(pend, tr, lane, bA, bB) : tr_reduce<U>(pend, tr, lane);
+        const int i = pend_k * U + (U - 1 - ru);
+        if (pend_k >= 0 && i < L) {
+          if (rW) fup[TOP ? i : L - i] += rad_norm * t;
+          if (BND) { put_band(p.bnd_up, TOP ? i : L - i, chunk * 8 + 2 * (lane >> 3), bA); put_band(p.bnd_up, TOP ? i : L - i, chunk * 8 + 2 * (lane >> 3) + 1, bB); }
+        }
+      };
+      // ---------------- downward sweep: one group of U layers, in halves of H ----------------
+      auto forward_group = [&](int k, auto tail_c) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        __syncwarp();                 // every lane is done with the stage that group k+S-1 overwrites
+        issue_in(k + S - 1);
+        const uint32_t nk = n_in + (uint32_t)k;
+        const uint32_t st = nk % S;
+        mbar_wait(bar_in + 8 * st, (nk / S) & 1u);
+        const uint8_t* stg = in_ring + st * STAGE;
+        const uint8_t* base = stg + lane_in;
+        int shl = 0, shv = 0, nvalid = U;
+        if (TAIL) {
+          box_start<TOP, U>(lay0, k, shl);
+          box_start<TOP, U>(ext0, k, shv);
+          nvalid = min(U, L - k * U);
+        }
+        flush_dn();
+        uint8_t* const sg = srow + (size_t)k * (U * LW7_ROW);
+        float red[U];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          if (TAIL && h * H >= nvalid) {   // warp-uniform: nothing of this half belongs to the column
+#pragma unroll
+            for (int uu = 0; uu < H; ++uu) red[h * H + uu] = 0.0f;
+            continue;
+          }
+          f4 tau[H], lay[H], ext[H];
+#pragma unroll
+          for (int uu = 0; uu < H; ++uu) {
+            const int u = h * H + uu;
+            if (TAIL && u >= nvalid) { tau[uu] = splat4(1.0f); lay[uu] = splat4(0.0f); ext[uu] = splat4(0.0f); continue; }  // warp-uniform
+            const int rl = TAIL ? box_row<TOP, U>(u, shl) : (TOP ? u : U - 1 - u);
+            const int rv = TAIL ? box_row<TOP, U>(u, shv) : (TOP ? u : U - 1 - u);
+            tau[uu] = lds4(base + rl * RB);
+            if (CLD) { const f2 tc = band_val(stg + OFF_CLD + rl * 64); tau[uu].a = tau[uu].a + tc; tau[uu].b = tau[uu].b + tc; }   // inc_1scalar_by_1scalar_bybnd
+            if (COMPACT) {
+              const f4 pf = lds4(base + OFF_PF + rl * RB);
+              lay[uu] = mul4(pf, band_val(stg + OFF_3 + rl * 64), NZ);
+              // the level below the bottom layer takes that layer's fraction (:667-669); bottom-up sweeps leave through
+              // the layer's own level
+              const f4 pfx = (TOP && k * U + u != L - 1) ? lds4(base + OFF_PF + (rl + 1) * RB) : pf;
+              ext[uu] = mul4(pfx, band_val(stg + OFF_BV + rv * 64), NZ);
+            } else {
+              lay[uu] = lds4(base + OFF_PF + rl * RB);
+              ext[uu] = lds4(base + OFF_3 + rv * RB);
+            }
+          }
+#pragma unroll
+          for (int uu = 0; uu < H; ++uu) {
+            const int u = h * H + uu;
+            if (TAIL && u >= nvalid) { red[u] = 0.0f; continue; }  // warp-uniform: this layer is not part of the column
+            const f4 ent = (uu == 0) ? carry : ext[uu - 1];
+            f4 t, sup;
+            lw_layer_dn2<FAST, DN_EXT>(tau[uu].a, lay[uu].a, ext[uu].a, ent.a, D, I.a, t.a, sup.a);
+            lw_layer_dn2<FAST, DN_EXT>(tau[uu].b, lay[uu].b, ext[uu].b, ent.b, D, I.b, t.b, sup.b);
+            stg_scr4(sg + u * LW7_ROW, t, pol_buf);
+            stg_scr4(sg + u * LW7_ROW + LW7_S, sup, pol_buf);
+            red[u] = hsum4(I);
+          }
+          carry = ext[H - 1];  // (a ragged half is the last one of its sweep: its carry is not used)
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) pend[u] = red[u];
+        pend_k = k;
+      };
+      {
+        // bottom-up, column 0: the boxes of the last groups may have been moved -> generic path for those
+        const int nfast = (TOP || col > 0) ? NGF : max(NGF - 1, 0);
+        for (int k = 0; k < nfast; ++k) forward_group(k, std::false_type{});
+        for (int k = nfast; k < NG; ++k) forward_group(k, std::true_type{});
+      }
+      flush_dn();
+      pend_k = -1;
+      n_in += (uint32_t)NG;
+      // ---------------- surface ----------------
+      f4 Uu;   // :269
+      Uu.a = fma2(I.a, splat2(1.0f) - emis.a, emis.a * ssrc.a) * splat2(live);
+      Uu.b = fma2(I.b, splat2(1.0f) - emis.b, emis.b * ssrc.b) * splat2(live);
+      {
+        const float s = warp_sum(hsum4(Uu));
+        if (lane == 0) fup[TOP ? L : 0] += rad_norm * s;
+        if (BND) {
+          const float b = band_sum4(hsum4(Uu));
+          if ((lane & 3) == 0) put_band(p.bnd_up, TOP ? L : 0, chunk * 8 + (lane >> 2), b);
+        }
+      }
+      // ---------------- upward sweep (reverse order): rows back by bulk copies into the idle input ring ----------------
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // this lane's row stores (generic proxy) before the bulk loads (async proxy)
+      __syncwarp();
+      auto issue_bb = [&](int j) {  // j-th group of the upward sweep = forward group NG-1-j
+        if (j < NG) {
+          const int k = NG - 1 - j;
+          const uint32_t st = (n_bb + (uint32_t)j) % SB;
+          const uint32_t bytes = (uint32_t)min(U, L - k * U) * LW7_ROW;
+          if (elect_one()) {
+            mbar_expect_tx(bar_bb + 8 * st, bytes);
+            bulk_load(in_a + st * (U * LW7_ROW), srow - (size_t)lane * 16u + (size_t)k * (U * LW7_ROW), bytes, bar_bb + 8 * st, pol_buf);
+          }
+          __syncwarp();
+        }
+      };
+#pragma unroll
+      for (int j = 0; j < SB - 1; ++j) issue_bb(j);
+      auto backward_group = [&](int j, auto tail_c) {
+        constexpr bool TAIL = decltype(tail_c)::value;
+        const int k = NG - 1 - j;
+        const int nvalid = TAIL ? min(U, L - k * U) : U;
+        __syncwarp();  // every lane has pulled the previous group into registers: its stage may be refilled
+        issue_bb(j + SB - 1);
+        const uint32_t nj = n_bb + (uint32_t)j;
+        const uint32_t st = nj % SB;
+        mbar_wait(bar_bb + 8 * st, (nj / SB) & 1u);
+        f4 t[U], s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint8_t* row = in_ring + st * (U * LW7_ROW) + (TAIL ? min(u, nvalid - 1) : u) * LW7_ROW + lane_in;
+          t[u] = lds4(row);
+          s[u] = lds4(row + LW7_S);
+        }
+        flush_up();
+        float red[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // sweep layers k*U + (U-1-u): upwards
+          const int uu = U - 1 - u;
+          if (!TAIL || uu < nvalid) { Uu.a = fma2(t[uu].a, Uu.a, s[uu].a); Uu.b = fma2(t[uu].b, Uu.b, s[uu].b); }
+          red[u] = hsum4(Uu);
+        }
+        // the rows are in registers: their L2 lines are dead (no write-back; the next sweep rewrites them in full)
+        discard_scratch(srow - (size_t)lane * 16u + (size_t)k * (U * LW7_ROW), (uint32_t)nvalid * LW7_ROW, lane);
+#pragma unroll
+        for (int u = 0; u < U; ++u) pend[u] = red[u];
+        pend_k = k;
+      };
+      {
+        int j = 0;
+        if (NG > NGF) backward_group(j++, std::true_type{});  // the ragged group comes first on the way up
+        for (; j < NG; ++j) backward_group(j, std::false_type{});
+      }
+      flush_up();
+      pend_k = -1;
+      n_bb += (uint32_t)NG;
+      __syncwarp();
+    }
+    // ---- combine the chunks of this column (see lw_solver_v6)
+    nx.publish(cluster, csize, ncols_done);
+    cluster.sync();
+    {
+      float* const gout[2] = {p.flux_up + (size_t)col * (L + 1), p.flux_dn + (size_t)col * (L + 1)};
+      const int n = 2 * (L + 1), lo = chunk * n / csize, hi = (chunk + 1) * n / csize;
+      for (int i = lo + lane; i < hi && owner; i += 32) {
+        float sacc = 0.0f;
+        for (int r = 0; r < csize; ++r) sacc += *cluster.map_shared_rank(fup + i, r);
+        const int a = i / (L + 1);
+        gout[a][i - a * (L + 1)] = sacc;
+      }
+    }
+    cb = nx.next(ncols_done);
+  }
+  cluster.sync();  // nobody leaves while another rank may still read its shared memory
+}
+
 // ---------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1193,8 +1600,78 @@ static int launch_clustered(rrnn_ctx_t* ctx, K kernel, int csize, size_t warp_sm
 // The shapes the v5 kernels take (TMA: row pitch a multiple of 16 B; one cluster per column)
 bool lw_v5_supports(int G, int L) { return !(G & 3) && (G + 63) / 64 <= 8 && L >= v5::LW_U; }
 
+// v7: four g-points per lane, 128 per warp (see lw_solver_v7) -- the default where the shape fits; -1 otherwise
+static int launch_lw_v7(rrnn_ctx_t* ctx, LwParams& p) {
+  const int G = p.ngpt, L = p.nlay;
+  const int csize = (G + 127) / 128;
+  const bool compact = p.planck_lay != nullptr, cld = p.cld_tau != nullptr, bnd = p.bnd_up != nullptr;
+  constexpr int U = 8, S = RRNN_V7_LW_S, SB = 2;
+  if ((G & 3) || G < 128 || csize > 8 || L < U) return -1;
+  if ((compact || cld) && (p.pairs_in_band < 2 || !p.gpt2band)) return -1;   // a lane's four g-points share their band look-ups
+  if (compact && !p.planck_lev) return -1;
+  if (cld && ctx->fast_math) return -1;                                    // (the cloud / by-band variants are built for the default arithmetic only)
+  if (bnd && (compact || cld || ctx->fast_math || !p.bnd_dn || p.nbnd * 16 != G)) return -1;
+  for (const void* q : {(const void*)p.tau, (const void*)p.lay_source, (const void*)p.lev_source, (const void*)p.planck_lay, (const void*)p.planck_lev,
+                        (const void*)p.cld_tau})
+    if ((uintptr_t)q & 15) return -1;
+  for (const void* q : {(const void*)p.sfc_emis, (const void*)p.sfc_source, (const void*)p.inc_flux})
+    if ((uintptr_t)q & 7) return -1;
+  v5::LwV5Params pp;
+  pp.b = p;
+  pp.ngroups = (L + U - 1) / U;
+  const long long rows_lay = (long long)p.ncol * L, rows_lev = (long long)p.ncol * (L + 1);
+  if (rows_lev >= (1LL << 31) - 8) return -1;
+  const bool top = p.top_at_1 != 0, dn_ext = top || !p.bug_compat, fast = ctx->fast_math != 0;
+  CUtensorMap tm_tau, tm_lay, tm_lev, tm_bl, tm_bv, tm_cld;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows_lay, U, 128)) return rc;
+  tm_cld = tm_tau;
+  if (cld) { if (int rc = v5::make_map(&tm_cld, p.cld_tau, 16, rows_lay, U, 16)) return rc; }
+  size_t stage;
+  if (compact) {
+    const int pfr = top ? U + 1 : U;
+    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, pfr, 128)) return rc;
+    if (int rc = v5::make_map(&tm_bl, p.planck_lay, 16, rows_lay, U, 16)) return rc;
+    if (int rc = v5::make_map(&tm_bv, p.planck_lev, 16, rows_lev, U, 16)) return rc;
+    tm_lev = tm_tau;
+    stage = (size_t)U * 512 + (size_t)pfr * 512 + 2 * U * 64;
+  } else {
+    if (int rc = v5::make_map(&tm_lay, p.lay_source, G, rows_lay, U, 128)) return rc;
+    if (int rc = v5::make_map(&tm_lev, p.lev_source, G, rows_lev, U, 128)) return rc;
+    tm_bl = tm_tau; tm_bv = tm_tau;
+    stage = (size_t)3 * U * 512;
+  }
+  if (cld) stage += (size_t)U * 64;
+  const size_t smem = (size_t)S * stage + 8 * v5::TR_PITCH * 4 + 4 * (size_t)(L + 1) * 4 + (S + SB) * 8;
+  const size_t per_cta = (size_t)L * v5::LW7_ROW;
+  // scratch budget: measured optimum at 137 layers (125 ... 145 MB = 6.3 ... 7.3 of the 8 solver warps per SM the shared memory allows:
+  // 2.54 - 2.62 ms per 30 000 columns against 2.80 - 2.85 uncapped and 2.75 for lw_solver_v6)
+  constexpr int kScratchMb = 140;
+#define LW7(F, T, D, C, CL, B) launch_clustered(ctx, v5::lw_solver_v7<F, T, D, C, CL, B>, csize, smem, per_cta, kScratchMb, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv, tm_cld)
+#define LW7C(F, T, D, CL) (compact ? LW7(F, T, D, true, CL, false) : LW7(F, T, D, false, CL, false))
+  if (bnd) {
+    if (top) return LW7(false, true, true, false, false, true);
+    return dn_ext ? LW7(false, false, true, false, false, true) : LW7(false, false, false, false, false, true);
+  }
+  if (cld) {
+    if (top) return LW7C(false, true, true, true);
+    return dn_ext ? LW7C(false, false, true, true) : LW7C(false, false, false, true);
+  }
+  if (fast) {
+    if (top) return LW7C(true, true, true, false);
+    return dn_ext ? LW7C(true, false, true, false) : LW7C(true, false, false, false);
+  }
+  if (top) return LW7C(false, true, true, false);
+  return dn_ext ? LW7C(false, false, true, false) : LW7C(false, false, false, false);
+#undef LW7C
+#undef LW7
+}
+
 // v6: the default (see lw_solver_v6); returns -1 when the shape does not fit
 int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
+  if (ctx->solver_wide) {
+    const int rc = launch_lw_v7(ctx, p);
+    if (rc >= 0) return rc;
+  }
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 63) / 64;
   const bool compact = p.planck_lay != nullptr;

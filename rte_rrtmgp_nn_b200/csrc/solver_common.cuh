@@ -185,12 +185,16 @@ struct SwParams {
 }  // namespace rrnn
 
 // every pair of g-points (2i, 2i+1) in one band?  (all of RRTMGP's k-distributions: bands of 16.)  The packed solvers carry a pair per
-// lane and look a band value up ONCE per pair.
+// lane and look a band value up ONCE per pair.  Returns 2 when every aligned group of FOUR g-points lies in one band as well (the
+// wide kernels carry four per lane), 1 for pairs only, 0 otherwise.
 inline int kd_pairs_in_band(const rrnn_kdist_t* kd) {
   if (kd->ngpt & 1) return 0;
   for (int g = 0; g + 1 < kd->ngpt; g += 2)
     if (kd->gpt2band[g] != kd->gpt2band[g + 1]) return 0;
-  return 1;
+  if (kd->ngpt & 3) return 1;
+  for (int g = 0; g + 3 < kd->ngpt; g += 4)
+    if (kd->gpt2band[g] != kd->gpt2band[g + 3]) return 1;
+  return 2;
 }
 
 // ---- host-side launch helpers

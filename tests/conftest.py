@@ -40,10 +40,13 @@ def nn_variant(request, gpu_ctx):
         assert tc1 == tc0, f"an fp32_ffma test ran the tcgen05 kernel {tc1 - tc0} time(s)"
 
 
-@pytest.fixture(params=[0, 1], ids=["v6_tma_packed", "v3_scalar"])
+@pytest.fixture(params=[(0, 1), (0, 0), (1, 0)], ids=["v7_wide_lw", "v6_tma_packed", "v3_scalar"])
 def solver_variant(request, gpu_ctx):
-    """The RTE solver kernels behind rrnn_lw_solver_noscat / rrnn_sw_solver_2stream: TMA-staged packed fp32x2 (default;
-    rte_solvers_tma.cu) and one g-point per lane (rte_solvers.cu, the fallback for shapes the packed kernels do not take)."""
-    gpu_ctx.set_flag("solver_variant", request.param)
-    yield request.param
+    """The RTE solver kernels behind rrnn_lw_solver_noscat / rrnn_sw_solver_2stream: TMA-staged packed fp32x2 (rte_solvers_tma.cu;
+    the default, with four g-points per lane in the LW solver where the shape fits -- lw_solver_v7 -- and with two -- lw_solver_v6)
+    and one g-point per lane (rte_solvers.cu, the fallback for shapes the packed kernels do not take)."""
+    gpu_ctx.set_flag("solver_variant", request.param[0])
+    gpu_ctx.set_flag("solver_wide", request.param[1])
+    yield request.param[0]
     gpu_ctx.set_flag("solver_variant", 0)
+    gpu_ctx.set_flag("solver_wide", 1)
