@@ -5,12 +5,17 @@
  * rte_rrtmgp_nn_b200/csrc.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it; the product never does.
  *
- * PARITY UNPINNED: the reference (Fortran) cannot be compiled in this image (no Fortran compiler,
- * no netCDF, k-distribution files missing -- SURVEY.md section 0 F1/F2/F4) and its own tests hold no
- * golden vector for the NN + solver path.  Every function below therefore restates
+ * PARITY PINNED IN PART.  Pinned -- against outputs of the reference's OWN PYTHON, imported unmodified and run in the build
+ * container on the reference's RFMIP profiles (tools/make_ref_python_golden.py -> tests/golden/ref_python_golden.npz;
+ * tests/test_oracle_cpu.py::test_oracle_pinned_by_the_references_own_python): orc_get_col_dry, orc_compute_nn_inputs, the
+ * (ystd z + ymean)^8 N_dry output transform of orc_output_sgemm_tau (network outputs z from a float64 numpy evaluation of the
+ * shipped weights: the reference evaluates them with Keras, absent here), orc_calc_heating_rate, and the scaling constants
+ * read from the 2018 weight files.  PARITY UNPINNED for the rest -- Planck sources, rte_lw / rte_sw and their solvers, cloud
+ * optics: that part of the reference exists only in Fortran, which cannot be compiled in this image (no Fortran compiler,
+ * no netCDF, k-distribution files missing -- SURVEY.md section 0 F1/F2/F4), and the reference's own tests hold no
+ * golden vector for it.  Every function below restates
  * the reference loops line by line in fp32 (wp = sp, rte/mo_rte_kind.F90:29-33) and cites the
- * file:line it follows under /root/reference.  Pins that do exist: the shipped NN weight files and
- * the source itself.
+ * file:line it follows under /root/reference.
  *
  * Array layout is the reference's: g-point fastest, then layer, then column --
  * Fortran (ngpt,nlay,ncol) == C [ncol][nlay][ngpt]; profiles (nlay,ncol) == C [ncol][nlay].

@@ -1,7 +1,8 @@
 """ctypes front end of the CPU oracle (oracle.c).  TEST INFRASTRUCTURE ONLY.
 
 May be imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs.  "PARITY UNPINNED" (see oracle.c header): the reference Fortran cannot be built in this image.
+legs.  Parity pinned IN PART (see oracle.c header): the gas-optics pre- and post-processing against the reference's own Python
+(tests/golden/ref_python_golden.npz); "PARITY UNPINNED" for the solvers -- the reference Fortran cannot be built in this image.
 
 The orchestration functions at the bottom restate the reference's callers:
   gas_optics_lw  <- rrtmgp/mo_gas_optics_rrtmgp.F90:239-428 (NN branch :368-411)

@@ -422,3 +422,51 @@ def test_garand_fixture_and_chunked_reader():
     assert 190 < z["t_lay"].min() and z["t_lay"].max() < 305 and abs(z["vmr_o2"].mean() - 0.209) < 1e-3
     dry = z["vmr_n2"] + z["vmr_o2"]
     assert (dry > 0.99).all() and (dry < 1.0).all()
+
+
+def _ref_python_case():
+    """The inputs of tools/make_ref_python_golden.py: RFMIP profiles (every 50th column), gases as the models name them."""
+    gold = np.load(os.path.join(H.GOLDEN, "ref_python_golden.npz"))
+    d = np.load(os.path.join(H.GOLDEN, "rfmip_inputs.npz"))
+    cols = gold["columns"]
+    gases = {k[3:]: d[k][cols] for k in d.files if k.startswith("gm_")}
+    ncol, nlay = d["p_lay"][cols].shape
+    gases = {k: np.ascontiguousarray(np.broadcast_to(v[:, None], (ncol, nlay))) for k, v in gases.items()}
+    gases["h2o"], gases["o3"] = d["h2o"][cols], d["o3"][cols]
+    return gold, dict(play=d["p_lay"][cols], plev=d["p_lev"][cols], tlay=d["t_lay"][cols], gases=gases)
+
+
+REF_PY_MODELS = dict(sw_abs=H.SW_G224[0], sw_ray=H.SW_G224[1], lw_abs=H.LW_G256[0])
+
+
+def test_oracle_pinned_by_the_references_own_python():
+    """The PIN of the oracle's gas-optics restatement: tests/golden/ref_python_golden.npz holds what the REFERENCE'S OWN Python
+    (examples/rrtmgp-nn-training/ml_load_save_preproc.py, ml_scaling_coefficients.py, ml_eval_funcs.py -- imported unmodified by
+    tools/make_ref_python_golden.py) computes on the reference's RFMIP profiles: get_col_dry, the NN input pre-processing, the
+    (ystd z + ymean)^8 N_dry output transform, the K/day heating rates, and the scaling constants of the 2018 models."""
+    import nc4min
+    gold, a = _ref_python_case()
+    # SURVEY 8a row a3: get_col_dry (ml_load_save_preproc.py:283-293)
+    cd = O.get_col_dry(a["gases"]["h2o"], a["plev"])
+    assert np.abs(cd / gold["col_dry"] - 1).max() <= 5e-7
+    for tag, fn in REF_PY_MODELS.items():
+        m = nc4min.load_nn_model(os.path.join(H.NN_DIR, fn))
+        net = O.Net(m)
+        # a-W: the constants the weight files carry are the reference's (ml_scaling_coefficients.py), to the bit
+        assert np.array_equal(m["ymean"], gold[tag + "_ymean"].astype(np.float32))
+        assert np.array_equal(m["ystd"], gold[tag + "_ysigma"].astype(np.float32))
+        # a2: compute_nn_inputs against preproc_minmax_inputs_rrtmgp (:416-435): values in [0, 1], fp32 log / fourth root
+        x = O.compute_nn_inputs(net, a["play"], a["tlay"], a["gases"])
+        assert np.abs(x - gold[tag + "_nn_inputs"]).max() <= 1e-6
+        # a5: output_sgemm_tau = (ystd z + ymean)^8 N_dry against preproc_pow_standardization_reverse (:329-340) on the float64
+        # network outputs: the tau statement of DESIGN.md section 4 (1e-4 of max(tau, 1e-4 x largest tau of the sample))
+        tau = O.output_sgemm_tau(net, x, cd).reshape(gold[tag + "_tau"].shape)
+        assert H.tau_rel_err(tau, gold[tag + "_tau"]).max() <= H.TAU_RTOL_FP32, tag
+        big = gold[tag + "_tau"] >= 1e-2 * gold[tag + "_tau"].max(-1, keepdims=True)
+        assert np.abs(tau[big] / gold[tag + "_tau"][big] - 1).max() <= 2.5e-5, tag
+        tau64 = O.output_sgemm_tau(net, x, cd, fast="f64").reshape(tau.shape)
+        assert H.tau_rel_err(tau64, gold[tag + "_tau"]).max() <= 5e-6, tag   # the fp64 build: what is left is the rounding of the fp32 inputs (measured 1.6e-6)
+    # a18: K/day heating rates (ml_eval_funcs.py:23-34; g = 9.81 there and grav = 9.80665 in the Fortran twin that the oracle
+    # restates, rrtmgp_lw_eval_nn_rfmip.F90:623-651: the ratio of the two is exact to fp32 rounding)
+    hr = O.calc_heating_rate(gold["hr_flux_up"], gold["hr_flux_dn"], a["plev"])
+    assert np.abs(hr * (9.81 / 9.80665) - gold["hr_K_day"]).max() <= 2e-4 * np.abs(gold["hr_K_day"]).max()

@@ -1472,3 +1472,50 @@ def test_rfmip_sw_real_profiles_match_oracle(gpu_ctx):
     assert np.percentile(dup, 95) <= H.FLUX_TOL and np.percentile(ddn, 95) <= H.FLUX_TOL
     assert dup.max() <= 0.08 and ddn.max() <= 0.08
     assert np.sqrt((dup ** 2).mean()) <= 0.005 and np.sqrt((ddn ** 2).mean()) <= 0.005
+
+
+def test_cuda_path_against_the_references_own_python(gpu_ctx, nn_variant):
+    """The CUDA gas optics against what the REFERENCE'S OWN Python computes on the reference's RFMIP profiles
+    (tests/golden/ref_python_golden.npz, made by tools/make_ref_python_golden.py from ml_load_save_preproc.py / ml_scaling_coefficients.py
+    imported unmodified): get_col_dry, the NN input pre-processing, and tau = (ystd z + ymean)^8 N_dry -- LW absorption and the SW
+    absorption + Rayleigh pair -- through ty_gas_optics_rrtmgp%gas_optics on both MLP kernels.  No oracle in between."""
+    from test_oracle_cpu import _ref_python_case
+    from rte_rrtmgp_nn_b200 import api, _lib, spectral
+    torch = _torch()
+    gold, a = _ref_python_case()
+    ncol, nlay = a["play"].shape
+    P = api._ptr
+    lib = _lib.lib()
+    # get_col_dry, compute_nn_inputs (materialised entry points)
+    plev = torch.from_numpy(a["plev"]).cuda(); play = torch.from_numpy(a["play"]).cuda(); tlay = torch.from_numpy(a["tlay"]).cuda()
+    d_h2o = torch.from_numpy(a["gases"]["h2o"]).cuda()
+    cd = torch.empty((ncol, nlay), device="cuda")
+    _lib.check(lib.rrnn_get_col_dry(gpu_ctx.h, ncol, nlay, P(d_h2o), P(plev), P(cd)))
+    assert np.abs(cd.cpu().numpy() / gold["col_dry"] - 1).max() <= 1e-6
+    lw_nets, sw_nets = H.device_nets(gpu_ctx, H.LW_G256), H.device_nets(gpu_ctx, H.SW_G224)
+    gases, ngas, keep = H.gas_concs(a["gases"])._to_c(gpu_ctx)
+    for net, tag, nx in ((lw_nets[0], "lw_abs", 18), (sw_nets[0], "sw_abs", 7)):
+        x = torch.empty((ncol, nlay, nx), device="cuda")
+        _lib.check(lib.rrnn_compute_nn_inputs(gpu_ctx.h, net.h, ncol, nlay, P(play), P(tlay), gases, ngas, P(x)))
+        assert np.abs(x.cpu().numpy() - gold[tag + "_nn_inputs"]).max() <= 2e-6, tag
+    # LW: tau of the absorption network through the type-level call
+    k_lw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_lw.load(spectral.synthetic_kdist_lw(ngpt=256)) == ""
+    op = api.ty_optical_props_1scl(); assert op.alloc_1scl(ncol, nlay, k_lw) == ""
+    src = api.ty_source_func_lw(); assert src.alloc(ncol, nlay, k_lw) == ""
+    tsfc = np.ascontiguousarray(a["tlay"][:, -1])
+    assert k_lw.gas_optics(a["play"], a["plev"], a["tlay"], tsfc, H.gas_concs(a["gases"]), op, src, neural_nets=lw_nets) == ""
+    e = H.tau_rel_err(op.tau.cpu().numpy(), gold["lw_abs_tau"]).max()
+    bulk = H.tau_rel_err(op.tau.cpu().numpy(), gold["lw_abs_tau"], floor=1e-2).max()
+    print(f"LW tau vs the reference's Python: {e:.2e} (bulk {bulk:.2e})")
+    assert e <= nn_variant and bulk <= 0.25 * nn_variant
+    # SW: tau = tau_abs + tau_ray, ssa = tau_ray / tau (mo_gas_optics_rrtmgp.F90:529-573)
+    k_sw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_sw.load(spectral.synthetic_kdist_sw(ngpt=224)) == ""
+    op2 = api.ty_optical_props_2str(); assert op2.alloc_2str(ncol, nlay, k_sw) == ""
+    toa = torch.empty((ncol, 224), device="cuda")
+    assert k_sw.gas_optics(a["play"], a["plev"], a["tlay"], H.gas_concs(a["gases"]), op2, toa, neural_nets=sw_nets) == ""
+    t_abs, t_ray = gold["sw_abs_tau"].astype(np.float64), gold["sw_ray_tau"].astype(np.float64)
+    e = H.tau_rel_err(op2.tau.cpu().numpy(), t_abs + t_ray).max()
+    bulk = H.tau_rel_err(op2.tau.cpu().numpy(), t_abs + t_ray, floor=1e-2).max()
+    print(f"SW tau vs the reference's Python: {e:.2e} (bulk {bulk:.2e})")
+    assert e <= nn_variant and bulk <= 0.25 * nn_variant
+    assert np.abs(op2.ssa.cpu().numpy() - t_ray / (t_abs + t_ray)).max() <= 5e-5
