@@ -387,6 +387,8 @@ extern "C" int rrnn_ctx_create(int device, void* stream, rrnn_ctx_t** out) {
   if (const char* e = getenv("RRNN_SOLVER_BUFFER")) c->solver_buffer = atoi(e);
   if (const char* e = getenv("RRNN_NN_TENSOR_CORES")) c->nn_tensor_cores = atoi(e) ? 1 : 0;
   if (const char* e = getenv("RRNN_SOLVER_WIDE")) c->solver_wide = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("RRNN_SOLVER_WIDE_SW")) c->solver_wide_sw = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("RRNN_SW_WIDE_SCRATCH_MB")) c->solver_scratch_mb_sw_wide = atoi(e);
   *out = c;
   return 0;
 }
@@ -505,6 +507,8 @@ extern "C" int rrnn_ctx_set_flag(rrnn_ctx_t* c, const char* name, int value) {
   else if (s == "solver_scratch_mb") c->solver_scratch_mb = value;
   else if (s == "solver_warps") c->solver_warps = value;
   else if (s == "solver_wide") c->solver_wide = value;
+  else if (s == "solver_wide_sw") c->solver_wide_sw = value;
+  else if (s == "solver_scratch_mb_sw_wide") c->solver_scratch_mb_sw_wide = value;
   else return fail("rrnn_ctx_set_flag: unknown flag " + s);
   return 0;
 }

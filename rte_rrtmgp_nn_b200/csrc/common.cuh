@@ -73,6 +73,8 @@ struct rrnn_ctx {
   int solver_scratch_mb = 0;  // L2 budget of the packed kernels' reverse-sweep scratch (0 = default)
   int solver_warps = 0;       // solvers per CTA in the v5 kernels (0 = default)
   int solver_wide = 1;        // 1: four g-points per lane in the LW solver where the shape fits (lw_solver_v7); 0: lw_solver_v6
+  int solver_wide_sw = 0;     // (builds with -DRRNN_EXPERIMENT_SW_WIDE only) 1: four g-points per lane in the clear-sky SW solver too (sw_solver_v7, measured slower)
+  int solver_scratch_mb_sw_wide = 0;   // scratch budget of sw_solver_v7 (0: its default)
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   int* col_counter = nullptr;  // the packed solvers' dynamic column assignment (one int, zeroed before every launch)

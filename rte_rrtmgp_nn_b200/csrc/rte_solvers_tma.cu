@@ -1510,6 +1510,13 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V7_LW_MINB) lw_solver_v7(
   cluster.sync();  // nobody leaves while another rank may still read its shared memory
 }
 
+// sw_solver_v7 (four g-points per lane, as lw_solver_v7): correct (2.3e-7 of the largest flux from sw_solver_v6) but SLOWER -- 4.20 (6 solver
+// warps per SM) / 3.95 ms (7) against 3.78 ms per 30 000 x 137 x 224 on one box -- so it is an opt-in experiment:
+// make EXTRA=-DRRNN_EXPERIMENT_SW_WIDE, context flag solver_wide_sw = 1, tools/check_wide_sw.py.
+#ifdef RRNN_EXPERIMENT_SW_WIDE
+#include "experiments/rte_solvers_sw_wide.cuh"
+#endif
+
 // ---------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1736,8 +1743,46 @@ int launch_lw_v6(rrnn_ctx_t* ctx, LwParams& p) {
 #undef LW6
 }
 
+#ifdef RRNN_EXPERIMENT_SW_WIDE
+// v7: four g-points per lane, 128 per warp (see sw_solver_v7): clear-sky broadband only; -1 where the shape does not fit
+static int launch_sw_v7(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
+  const int G = p.ngpt, L = p.nlay;
+  const int csize = (G + 127) / 128;
+  constexpr int U = 8, S = RRNN_V7_SW_S, SB = 2;
+  if (p.cld || p.g || p.bnd_up) return -1;
+  if ((G & 3) || G < 112 || csize > 8 || L < U) return -1;
+  for (const void* q : {(const void*)p.tau, (const void*)p.ssa})
+    if ((uintptr_t)q & 15) return -1;
+  for (const void* q : {(const void*)p.inc_flux, (const void*)p.inc_flux_dif, (const void*)p.alb_dir, (const void*)p.alb_dif})
+    if ((uintptr_t)q & 7) return -1;
+  v5::SwV5Params pp;
+  pp.b = p;
+  pp.ngroups = (L + U - 1) / U;
+  const long long rows = (long long)p.ncol * L;
+  if (rows >= (1LL << 31) - 8) return -1;
+  CUtensorMap tm_tau, tm_ssa;
+  if (int rc = v5::make_map(&tm_tau, p.tau, G, rows, U, 128)) return rc;
+  if (int rc = v5::make_map(&tm_ssa, p.ssa, G, rows, U, 128)) return rc;
+  const size_t stage = (size_t)2 * U * 512;
+  const size_t smem = (size_t)S * stage + 16 * v5::TR_PITCH * 4 + 2 * (size_t)(3 * (L + 1) + 1) * 4 + (S + SB) * 8;
+  const size_t per_cta = (size_t)L * v5::SW7_ROW;
+  const int mb = ctx->solver_scratch_mb_sw_wide > 0 ? ctx->solver_scratch_mb_sw_wide : 400;
+  const bool top = p.top_at_1 != 0;
+#define SW7(F, T) launch_clustered(ctx, v5::sw_solver_v7<F, T>, csize, smem, per_cta, mb, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa)
+  if (fast) return top ? SW7(true, true) : SW7(true, false);
+  return top ? SW7(false, true) : SW7(false, false);
+#undef SW7
+}
+#endif
+
 // v6: the default (see sw_solver_v6)
 int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
+#ifdef RRNN_EXPERIMENT_SW_WIDE
+  if (ctx->solver_wide_sw) {
+    const int rc = launch_sw_v7(ctx, p, fast);
+    if (rc >= 0) return rc;
+  }
+#endif
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 63) / 64;
   constexpr int U = 8, SB = 2;

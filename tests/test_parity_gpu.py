@@ -1519,3 +1519,71 @@ def test_cuda_path_against_the_references_own_python(gpu_ctx, nn_variant):
     print(f"SW tau vs the reference's Python: {e:.2e} (bulk {bulk:.2e})")
     assert e <= nn_variant and bulk <= 0.25 * nn_variant
     assert np.abs(op2.ssa.cpu().numpy() - t_ray / (t_abs + t_ray)).max() <= 5e-5
+
+
+def test_cuda_solvers_analytic_known_answers(gpu_ctx, solver_variant):
+    """The CUDA solvers against closed-form answers -- no oracle in between (the solver part of the path is what no reference output pins):
+      LW, isothermal column over a black surface: flux_up = pi sum_g B_g at every level, flux_dn(l) = pi sum_g B_g (1 - prod exp(-1.66 tau));
+      SW, pure absorption (ssa = 0): direct = mu0 inc exp(-sum tau / mu0), no diffuse flux down, the surface's diffuse reflection decays as
+          exp(-2 tau) (PIFM: gamma1 = k = 2, R = 0);
+      SW, conservative scattering (ssa = 1, g = 0 and g != 0) over any surface: nothing is absorbed in the atmosphere, so the net flux
+          flux_dn - flux_up is the same at every level (two-stream + adding conserve energy layer by layer) up to the scheme's own k^2 >= k_min
+          = 1e-4 floor, which absorbs ~1e-4 tau^2 per layer: thin layers (tau ~ 0.06) keep that at 7e-5 of the incident flux (fp64 evaluation
+          of the reference formulas) and the fp32 evaluation at 1 - 2.5e-4 -- the test allows 5e-4.
+    Shapes include ragged layer groups, idle lanes, both orientations and more columns than resident clusters."""
+    from rte_rrtmgp_nn_b200 import api, _lib
+    torch = _torch()
+    P = api._ptr
+    lib = _lib.lib()
+    rng = np.random.default_rng(11)
+    Ds = np.array([1.66], np.float32); w = np.array([0.5], np.float32)
+    for (G, L, C, top) in [(256, 137, 700, True), (128, 60, 33, False), (224, 61, 5, True), (36, 9, 3, False)]:
+        flip = (lambda a: a) if top else (lambda a: np.ascontiguousarray(a[:, ::-1]))
+        # ---- LW isothermal
+        tau = rng.gamma(0.5, 1.0, size=(C, L, G)).astype(np.float32)
+        B = rng.uniform(0.5, 2.0, size=(C, 1, G)).astype(np.float32)
+        lay = np.broadcast_to(B, (C, L, G)).copy(); lev = np.broadcast_to(B, (C, L + 1, G)).copy()
+        emis = np.ones((C, G), np.float32); ssrc = B[:, 0].copy()
+        d = [torch.from_numpy(a).cuda() for a in (flip(tau), lay, lev, emis, ssrc)]
+        up = torch.empty((C, L + 1), device="cuda"); dn = torch.empty_like(up)
+        _lib.check(lib.rrnn_lw_solver_noscat(gpu_ctx.h, G, L, C, int(top), 1, Ds.ctypes.data_as(_lib.c_float_p), w.ctypes.data_as(_lib.c_float_p),
+                                             None, *[P(t) for t in d], P(up), P(dn)))
+        up, dn = flip(up.cpu().numpy()), flip(dn.cpu().numpy())
+        want_up = np.pi * B[:, 0].sum(-1, dtype=np.float64)
+        assert np.abs(up / want_up[:, None] - 1).max() <= 4e-6, ("LW up", G, L, C, top)
+        trans = np.exp(-1.66 * np.cumsum(tau.astype(np.float64), axis=1))
+        want_dn = np.pi * (B.astype(np.float64) * (1 - trans)).sum(-1)
+        assert np.abs(dn[:, 1:] / want_dn - 1).max() <= 1e-5 and np.all(dn[:, 0] == 0), ("LW dn", G, L, C, top)
+        # ---- SW pure absorption
+        tau = rng.gamma(0.5, 0.4, size=(C, L, G)).astype(np.float32)
+        mu0 = rng.uniform(0.2, 1.0, size=C).astype(np.float32)
+        inc = rng.uniform(1, 5, size=(C, G)).astype(np.float32)
+        alb = rng.uniform(0.1, 0.8, size=(C, G)).astype(np.float32)
+
+        def run_sw(tau, ssa, g, alb_dir, alb_dif):
+            t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dict(inc=inc, tau=flip(tau), ssa=flip(ssa), mu0=mu0, ad=alb_dir, af=alb_dif).items()}
+            tg = None if g is None else torch.from_numpy(flip(g)).cuda()
+            out = [torch.empty((C, L + 1), device="cuda") for _ in range(3)]
+            _lib.check(lib.rrnn_sw_solver_2stream(gpu_ctx.h, G, L, C, int(top), P(t["inc"]), None, P(t["tau"]), P(t["ssa"]), None if tg is None else P(tg),
+                                                  P(t["mu0"]), P(t["ad"]), P(t["af"]), *[P(o) for o in out]))
+            return [flip(o.cpu().numpy()).astype(np.float64) for o in out]
+
+        up, dn, dr = run_sw(tau, np.zeros_like(tau), None, alb, alb)
+        t64 = tau.astype(np.float64)
+        cum = np.concatenate([np.zeros((C, 1, G)), np.cumsum(t64, axis=1)], axis=1)
+        dir64 = inc[:, None] * mu0[:, None, None] * np.exp(-cum / mu0[:, None, None])
+        assert np.abs(dr / dir64.sum(-1) - 1).max() <= 2e-5, ("SW dir", G, L, C, top)
+        assert np.abs(dn - dr).max() <= 1e-5 * dr.max()
+        below = cum[:, -1:, :] - cum
+        up64 = (dir64[:, -1:, :] * alb[:, None] * np.exp(-2.0 * below)).sum(-1)
+        assert np.abs(up - up64).max() <= 5e-5 * up64.max(), ("SW up", G, L, C, top)
+        # ---- SW conservative scattering: flux_dn - flux_up constant with height
+        tau = rng.gamma(0.6, 0.1, size=(C, L, G)).astype(np.float32)
+        one = np.ones_like(tau)
+        alb2 = rng.uniform(0.0, 0.9, size=(C, G)).astype(np.float32)
+        for g in (None, rng.uniform(-0.1, 0.85, size=(C, L, G)).astype(np.float32)):
+            up, dn, dr = run_sw(tau, one, g, alb, alb2)
+            net = dn - up
+            scale = dn[:, 0:1]
+            assert np.abs(net - net[:, :1]).max() <= 5e-4 * scale.max(), ("SW conservation", G, L, C, top, g is not None, np.abs(net - net[:, :1]).max() / scale.max())
+            assert np.all(net[:, -1] >= -1e-4 * scale[:, 0]) and np.all(dr <= dn + 1e-4 * scale)
