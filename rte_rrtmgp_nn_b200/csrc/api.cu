@@ -170,6 +170,58 @@ __global__ void cloud_optics_kernel(const CloudParams p) {
   }
 }
 
+// The all-sky drivers' cloud preparation in ONE pass (LUT cloud optics -> [SW: delta_scale_2str_k] -> the packed solvers' table rows):
+// compute_all_from_table + combine (above), rte/kernels/mo_optical_props_kernels.F90:72-93 and cloud_rows_{lw,sw}_kernel
+// (rte_solvers.cu) with the by-band arrays kept in registers -- they are never written.  One thread per (sample, 4 bands): the size
+// index and its fraction are per sample, the rows go out as 16-byte stores.  Same expressions in the same order as the three
+// separate kernels (the stage API still runs those).
+template <bool TWO_STREAM>
+__global__ void cloud_rows_fused_kernel(const CloudParams p, float* __restrict__ rows) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nsmp = (size_t)p.ncol * p.nlay;
+  if (i >= nsmp * 4) return;
+  const size_t s = i >> 2;
+  const int q = (int)(i & 3);
+  const float lw = p.clwp[s], iw = p.ciwp[s], rl = p.reliq[s], ri = p.reice[s];
+  float t2[4], s2[4], sg2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = 4 * q + j;
+    t2[j] = 0.0f; s2[j] = 0.0f; sg2[j] = 0.0f;
+    if (b >= p.nbnd) continue;
+    float lt, lts, ltsg, it, its, itsg;
+    table3(lw, rl, p.liq_off, p.liq_step, p.nliq, p.extliq + (size_t)b * p.nliq, p.ssaliq + (size_t)b * p.nliq, p.asyliq + (size_t)b * p.nliq,
+           lw > 0.f, lt, lts, ltsg);
+    table3(iw, ri, p.ice_off, p.ice_step, p.nice, p.extice + (size_t)b * p.nice, p.ssaice + (size_t)b * p.nice, p.asyice + (size_t)b * p.nice,
+           iw > 0.f, it, its, itsg);
+    if (!TWO_STREAM) {
+      t2[j] = (lt - lts) + (it - its);
+    } else {
+      const float t = lt + it, ts = lts + its;
+      const float gv = (ltsg + itsg) / fmaxf(FLT_EPSILON, ts);
+      const float w = ts / fmaxf(FLT_EPSILON, t);
+      // delta_scale_2str_k
+      const float eps = 3.0f * FLT_MIN;
+      const float f = gv * gv;
+      const float wf = w * f;
+      const float tau = (1.0f - wf) * t;
+      const float ssa = (w - wf) / fmaxf(eps, 1.0f - wf);
+      const float g = (gv - f) / fmaxf(eps, 1.0f - f);
+      t2[j] = tau;
+      s2[j] = __fmul_rn(tau, ssa);
+      sg2[j] = __fmul_rn(s2[j], g);
+    }
+  }
+  if (!TWO_STREAM) {
+    reinterpret_cast<float4*>(rows)[s * 4 + q] = make_float4(t2[0], t2[1], t2[2], t2[3]);
+  } else {
+    float4* r = reinterpret_cast<float4*>(rows) + s * 12 + q;
+    r[0] = make_float4(t2[0], t2[1], t2[2], t2[3]);
+    r[4] = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    r[8] = make_float4(sg2[0], sg2[1], sg2[2], sg2[3]);
+  }
+}
+
 // compute_all_from_pade + pade_eval_1 + combine, extensions/cloud_optics/mo_cloud_optics.F90:650-714, 757-781, 500-528:
 // orders [2/3] (extinction) and [2/2] (co-albedo, asymmetry), three size regimes (:476-493)
 struct PadeParams {
@@ -831,6 +883,29 @@ extern "C" int rrnn_cloud_optics(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, i
   RRNN_LAUNCH_CHECK(ctx);
   return 0;
 }
+
+// see cloud_rows_fused_kernel: rows_d holds 16 (LW: tau) or 48 (SW: t2 | s2 | sg2 after delta-scaling) floats per (layer, column);
+// -1 (no message): Pade coefficients or more than 16 bands -- the caller runs the three separate kernels
+namespace rrnn {
+int cloud_rows_fused(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, int ncol, int nlay, const float* clwp_d, const float* ciwp_d,
+                     const float* reliq_d, const float* reice_d, bool two_stream, float* rows_d) {
+  if (!lut || lut->is_pade || lut->nbnd > 16 || ((uintptr_t)rows_d & 15)) return -1;
+  if (ncol <= 0) return 0;
+  NvtxRange nvtx_("cloud_optics");
+  CloudParams p{};
+  p.ncol = ncol; p.nlay = nlay; p.nbnd = lut->nbnd; p.nliq = lut->nsize_liq; p.nice = lut->nsize_ice;
+  p.two_stream = two_stream ? 1 : 0;
+  p.liq_step = lut->liq_step; p.liq_off = lut->radliq_lwr; p.ice_step = lut->ice_step; p.ice_off = lut->radice_lwr;
+  p.extliq = lut->d_tables + lut->off[0]; p.ssaliq = lut->d_tables + lut->off[1]; p.asyliq = lut->d_tables + lut->off[2];
+  p.extice = lut->d_tables + lut->off[3]; p.ssaice = lut->d_tables + lut->off[4]; p.asyice = lut->d_tables + lut->off[5];
+  p.clwp = clwp_d; p.ciwp = ciwp_d; p.reliq = reliq_d; p.reice = reice_d;
+  const size_t n = (size_t)ncol * nlay * 4;
+  if (two_stream) cloud_rows_fused_kernel<true><<<nblk(n), 256, 0, ctx->stream>>>(p, rows_d);
+  else cloud_rows_fused_kernel<false><<<nblk(n), 256, 0, ctx->stream>>>(p, rows_d);
+  RRNN_LAUNCH_CHECK(ctx);
+  return 0;
+}
+}  // namespace rrnn
 
 extern "C" int rrnn_sampled_mask(rrnn_ctx_t* ctx, int ngpt, int nlay, int ncol, const float* randoms_d, const float* cloud_frac_d,
                                  const float* overlap_param_d, unsigned char* cloud_mask_d) {

@@ -14,6 +14,8 @@ bool lw_v5_supports(int G, int L);  // rte_solvers_tma.cu
 // rte_solvers.cu: clouds folded into the packed solvers (-1 = shape not taken)
 int cloud_rows_lw(rrnn_ctx_t* ctx, size_t nsmp, int nbnd, const float* tau_bnd_d, float* rows_d);
 int cloud_rows_sw(rrnn_ctx_t* ctx, size_t nsmp, int nbnd, const float* tau_bnd_d, const float* ssa_bnd_d, const float* g_bnd_d, float* rows_d);
+int cloud_rows_fused(rrnn_ctx_t* ctx, const rrnn_cloud_lut_t* lut, int ncol, int nlay, const float* clwp_d, const float* ciwp_d,
+                     const float* reliq_d, const float* reice_d, bool two_stream, float* rows_d);   // api.cu; -1: not taken
 int lw_solver_clouds(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, int nlay, int ncol, int top_at_1, int nmus, const float* Ds, const float* weights,
                      const float* inc_flux_d, const float* tau_d, const float* lay_d, const float* lev_d, const float* planck_lay_d,
                      const float* planck_lev_d, const float* sfc_emis_gpt_d, const float* sfc_source_d, const float* cld_rows_d,
@@ -158,8 +160,11 @@ static int lw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
     if (cl) {   // all-sky (rrtmgp_allsky.F90:369-400): cloud optics by band, increment folded into the solver
       float* ctau = egpt + align256((size_t)nc * G);
       float* rows = ctau + align256((size_t)nc * L * 16);
-      if (int rc = rrnn_cloud_optics(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, ctau, nullptr, nullptr)) return rc;
-      if (int rc = cloud_rows_lw(ctx, (size_t)nc * L, kd->nbnd, ctau, rows)) return rc;
+      if (int rf = cloud_rows_fused(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, false, rows)) {
+        if (rf > 0) return rf;
+        if (int rc = rrnn_cloud_optics(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, ctau, nullptr, nullptr)) return rc;
+        if (int rc = cloud_rows_lw(ctx, (size_t)nc * L, kd->nbnd, ctau, rows)) return rc;
+      }
       NvtxRange nvtx_rte("rte_lw");
       bcast_col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G, nc, emis, egpt);
       RRNN_LAUNCH_CHECK(ctx);
@@ -224,9 +229,12 @@ static int sw_chunk(rrnn_ctx_t* ctx, const rrnn_kdist_t* kd, const rrnn_model_t*
     float* cssa = ctau + align256((size_t)nc * L * 16);
     float* cg = cssa + align256((size_t)nc * L * 16);
     float* rows = cg + align256((size_t)nc * L * 16);
-    if (int rc = rrnn_cloud_optics(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, ctau, cssa, cg)) return rc;
-    if (int rc = rrnn_delta_scale_2str(ctx, (size_t)nc * L * kd->nbnd, ctau, cssa, cg)) return rc;
-    if (int rc = cloud_rows_sw(ctx, (size_t)nc * L, kd->nbnd, ctau, cssa, cg, rows)) return rc;
+    if (int rf = cloud_rows_fused(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, true, rows)) {
+      if (rf > 0) return rf;
+      if (int rc = rrnn_cloud_optics(ctx, cl->lut, nc, L, cl->clwp, cl->ciwp, cl->reliq, cl->reice, ctau, cssa, cg)) return rc;
+      if (int rc = rrnn_delta_scale_2str(ctx, (size_t)nc * L * kd->nbnd, ctau, cssa, cg)) return rc;
+      if (int rc = cloud_rows_sw(ctx, (size_t)nc * L, kd->nbnd, ctau, cssa, cg, rows)) return rc;
+    }
     const int rc = sw_solver_clouds(ctx, kd, L, nc, top_at_1, toa, nullptr, tau, ssa, rows, mu0e, agpt, agpt, fup, fdn, fdir);
     if (rc) return rc < 0 ? fail("rrnn_sw_fluxes_allsky: shape not taken by the packed solver") : rc;
   } else if (int rc = rrnn_sw_solver_2stream(ctx, G, L, nc, top_at_1, toa, nullptr, tau, ssa, nullptr, mu0e, agpt, agpt, fup, fdn, fdir)) {

@@ -1572,7 +1572,9 @@ def test_cuda_solvers_analytic_known_answers(gpu_ctx, solver_variant):
         t64 = tau.astype(np.float64)
         cum = np.concatenate([np.zeros((C, 1, G)), np.cumsum(t64, axis=1)], axis=1)
         dir64 = inc[:, None] * mu0[:, None, None] * np.exp(-cum / mu0[:, None, None])
-        assert np.abs(dr / dir64.sum(-1) - 1).max() <= 2e-5, ("SW dir", G, L, C, top)
+        # (a product of up to L exponentials, each within ~1e-6 relative: the beam is followed down to 1e-36 of its incident value)
+        assert np.abs(dr / dir64.sum(-1) - 1).max() <= 1.5e-6 * (L + 10), ("SW dir", G, L, C, top)
+        assert np.abs(dr - dir64.sum(-1)).max() <= 2e-6 * dir64.sum(-1).max()
         assert np.abs(dn - dr).max() <= 1e-5 * dr.max()
         below = cum[:, -1:, :] - cum
         up64 = (dir64[:, -1:, :] * alb[:, None] * np.exp(-2.0 * below)).sum(-1)
