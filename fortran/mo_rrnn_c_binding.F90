@@ -1,6 +1,6 @@
 ! ISO_C_BINDING interfaces of librrnn_b200.so -- GENERATED from include/rrnn.h by tools/gen_fortran_binding.py; do not edit.
 !
-! One interface block per C entry point (102 of 102).  Scalars by value; handles, device addresses and host
+! One interface block per C entry point (103 of 103).  Scalars by value; handles, device addresses and host
 ! arrays as type(c_ptr) values (host arrays: c_loc(a)); out-arguments and small integer / double arrays by reference.
 ! The comment above each block is the one the header carries: it cites the reference interface the entry point replaces.
 ! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler, SURVEY.md section 0 F1): `make -C fortran` builds it where
@@ -286,6 +286,20 @@ module mo_rrnn_c_binding
       real(c_float), value :: tsi
       integer(c_int) :: rc
     end function rrnn_kdist_set_solar_variability
+    ! ty_solar_var%solar_var_ind_interp, extensions/solar_variability/mo_solar_variability.F90:91-183: facular (mg) and sunspot
+    ! (sb) indices of the mean solar cycle interpolated to the cycle fraction solcycfrac in [0, 1] -- what set_solar_variability
+    ! takes. avgcyc_ind is the table ty_solar_var%load keeps (:45-69), Fortran (nsolarterms = 2, nsolarfrac) == C
+    ! [nsolarfrac][2], a HOST array; a host-only routine in the reference and here (no context, no device).
+    function rrnn_solar_var_ind_interp(avgcyc_ind, nsolarfrac, solcycfrac, mg_index_out, sb_index_out) &
+        bind(C, name="rrnn_solar_var_ind_interp") result(rc)
+      import :: c_float, c_int, c_ptr
+      type(c_ptr), value :: avgcyc_ind
+      integer(c_int), value :: nsolarfrac
+      real(c_float), value :: solcycfrac
+      type(c_ptr), value :: mg_index_out
+      type(c_ptr), value :: sb_index_out
+      integer(c_int) :: rc
+    end function rrnn_solar_var_ind_interp
     ! Host copy of the current solar source (ngpt).
     function rrnn_kdist_get_solar_source(kd, solar_source_out) bind(C, name="rrnn_kdist_get_solar_source") result(rc)
       import :: c_int, c_ptr

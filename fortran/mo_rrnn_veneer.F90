@@ -1617,3 +1617,55 @@ contains
   end subroutine cloud_optics_finalize
 
 end module mo_cloud_optics
+
+! =====================================================================================================================
+! extensions/solar_variability/mo_solar_variability.F90:20-183 -- ty_solar_var: the mean-solar-cycle table of the facular
+! (mg) and sunspot (sb) indices and its interpolation to a cycle fraction; the pair feeds set_solar_variability.
+module mo_solar_variability
+  use, intrinsic :: iso_c_binding
+  use mo_rte_kind, only: wp
+  use mo_rrnn_c_binding
+  implicit none
+  private
+
+  type, public :: ty_solar_var
+    real(wp), dimension(:,:), allocatable :: avgcyc_ind      ! (nsolarterms, nsolarfrac) -> (2,134)
+  contains
+    procedure, public :: solar_var_ind_interp
+    procedure, public :: load
+    procedure, public :: finalize
+  end type ty_solar_var
+
+contains
+
+  function load(this, avgcyc_ind) result(error_msg)      ! :45-69
+    class(ty_solar_var),      intent(inout) :: this
+    real(wp), dimension(:,:), intent(in   ) :: avgcyc_ind
+    character(len=128)    :: error_msg
+    error_msg = ""
+    if (allocated(this%avgcyc_ind)) deallocate(this%avgcyc_ind)
+    allocate(this%avgcyc_ind(size(avgcyc_ind, dim=1), size(avgcyc_ind, dim=2)))
+    this%avgcyc_ind = avgcyc_ind
+  end function load
+
+  subroutine finalize(this)      ! :75-83
+    class(ty_solar_var), intent(inout) :: this
+    if (allocated(this%avgcyc_ind)) deallocate(this%avgcyc_ind)
+  end subroutine finalize
+
+  function solar_var_ind_interp(this, solcycfrac, mg_index, sb_index) result(error_msg)      ! :91-183
+    class(ty_solar_var), target, intent(in   ) :: this
+    real(wp),            intent(in   ) :: solcycfrac
+    real(wp), target,    intent(out  ) :: mg_index
+    real(wp), target,    intent(out  ) :: sb_index
+    character(len=128)                 :: error_msg
+    error_msg = ""
+    if (solcycfrac .lt. 0._wp .or. solcycfrac .gt. 1._wp) error_msg = 'solar_var_ind_interp: solcycfrac out of range'
+    if (error_msg /= '') return
+    if (allocated(this%avgcyc_ind)) then      ! (2, nsolarfrac) in memory == C [nsolarfrac][2]
+      error_msg = rrnn_error_msg(rrnn_solar_var_ind_interp(c_loc(this%avgcyc_ind), int(size(this%avgcyc_ind, 2), c_int), solcycfrac, &
+                                                           c_loc(mg_index), c_loc(sb_index)))
+    end if
+  end function solar_var_ind_interp
+
+end module mo_solar_variability

@@ -125,6 +125,11 @@ RRNN_API int rrnn_kdist_set_solar_tables(rrnn_kdist_t* kd, const float* solar_qu
 /* ty_gas_optics_rrtmgp%set_solar_variability, rrtmgp/mo_gas_optics_rrtmgp.F90:1058-1095: solar_source = quiet +
  * (mg_index - 0.1495954) facular + (sb_index - 0.00066696) sunspot, then set_tsi(tsi) when have_tsi != 0. */
 RRNN_API int rrnn_kdist_set_solar_variability(rrnn_kdist_t* kd, float mg_index, float sb_index, int have_tsi, float tsi);
+/* ty_solar_var%solar_var_ind_interp, extensions/solar_variability/mo_solar_variability.F90:91-183: facular (mg) and sunspot (sb)
+ * indices of the mean solar cycle interpolated to the cycle fraction solcycfrac in [0, 1] -- what set_solar_variability takes.
+ * avgcyc_ind is the table ty_solar_var%load keeps (:45-69), Fortran (nsolarterms = 2, nsolarfrac) == C [nsolarfrac][2], a HOST
+ * array; a host-only routine in the reference and here (no context, no device). */
+RRNN_API int rrnn_solar_var_ind_interp(const float* avgcyc_ind, int nsolarfrac, float solcycfrac, float* mg_index_out, float* sb_index_out);
 /* Host copy of the current solar source (ngpt). */
 RRNN_API int rrnn_kdist_get_solar_source(const rrnn_kdist_t* kd, float* solar_source_out);
 /* optimal_angle_fit (2,nbnd) of ty_gas_optics_rrtmgp%load (:1163, 1210), a HOST array == C [nbnd][2]. */

@@ -12,6 +12,7 @@
 //   ty_gas_optics_rrtmgp       rrtmgp/mo_gas_optics_rrtmgp.F90:239-243, 433-438, 1058-1120, 1712-1758 (gas_optics with neural_nets,
 //                              set_tsi, set_solar_variability, compute_optimal_angles)
 //   rte_lw / rte_sw            rte/mo_rte_lw.F90:60-64, rte/mo_rte_sw.F90:48-52
+//   ty_solar_var               extensions/solar_variability/mo_solar_variability.F90:20-183 (load, solar_var_ind_interp)
 //
 // Arrays live on the device (dev_array: cudaMalloc'd float storage with host <-> device copies); layouts are the
 // reference's (g-point fastest): tau (ngpt,nlay,ncol) == C [ncol][nlay][ngpt], profiles (nlay,ncol) == C [ncol][nlay].
@@ -215,6 +216,23 @@ struct ty_fluxes_byband : ty_fluxes_broadband {
     }
     return err(rc);
   }
+};
+
+// ty_solar_var, extensions/solar_variability/mo_solar_variability.F90:20-183: load(avgcyc_ind) keeps the mean-solar-cycle table of the
+// facular and sunspot indices ((2, nsolarfrac) in the reference == [nsolarfrac][2] here), solar_var_ind_interp interpolates it to a cycle
+// fraction in [0, 1]; the pair is what ty_gas_optics_rrtmgp::set_solar_variability takes.  Host-only, as in the reference.
+class ty_solar_var {
+ public:
+  std::string load(const float* avgcyc_ind, int nsolarfrac) { avgcyc_ind_.assign(avgcyc_ind, avgcyc_ind + 2 * static_cast<size_t>(nsolarfrac)); return std::string(); }
+  void finalize() { avgcyc_ind_.clear(); }
+  std::string solar_var_ind_interp(float solcycfrac, float& mg_index, float& sb_index) const {
+    if (solcycfrac < 0.f || solcycfrac > 1.f) return "solar_var_ind_interp: solcycfrac out of range";
+    if (avgcyc_ind_.empty()) return std::string();      // as the reference: nothing is computed without a table
+    return err(rrnn_solar_var_ind_interp(avgcyc_ind_.data(), static_cast<int>(avgcyc_ind_.size() / 2), solcycfrac, &mg_index, &sb_index));
+  }
+
+ private:
+  std::vector<float> avgcyc_ind_;
 };
 
 class ty_gas_optics_rrtmgp : public ty_optical_props {

@@ -506,5 +506,34 @@ def set_solar_variability(solar_quiet, solar_facular, solar_sunspot, mg_index, s
     return out
 
 
+def solar_var_ind_interp(avgcyc_ind, solcycfrac):
+    """ty_solar_var%solar_var_ind_interp, extensions/solar_variability/mo_solar_variability.F90:91-183, restated step by step in
+    fp32 (wp = sp).  avgcyc_ind: (nsolarfrac, 2) == the reference's (2, nsolarfrac).  -> (error_msg, mg_index, sb_index)."""
+    f = np.float32
+    a = np.asarray(avgcyc_ind, f)
+    x = f(solcycfrac)
+    if x < 0 or x > 1:                                                    # :122-124
+        return "solar_var_ind_interp: solcycfrac out of range", None, None
+    n = a.shape[0]
+    if x == 0:                                                            # :139-141
+        return "", a[0, 0], a[0, 1]
+    if x == 1:                                                            # :143-145
+        return "", a[n - 1, 0], a[n - 1, 1]
+    intrvl_len = f(1) / f(n - 2)                                          # :148-149
+    hf = f(0.5) * intrvl_len
+    if x <= hf:                                                           # :153-157
+        sfid, fraclo, frachi = 1, f(0), hf
+    if x > hf and x < f(1) - hf:                                          # :160-164
+        sfid = int(np.floor(f(x - hf) * f(n - 2))) + 2
+        fraclo = f(f(sfid - 2) * intrvl_len) + hf
+        frachi = fraclo + intrvl_len
+    if x >= f(1) - hf:                                                    # :168-172
+        sfid, fraclo, frachi = n - 1, f(1) - hf, f(1)
+    intfrac = f(x - fraclo) / f(frachi - fraclo)                          # :175-179 (sfid is 1-based)
+    mg = a[sfid - 1, 0] + f(intfrac * f(a[sfid, 0] - a[sfid - 1, 0]))
+    sb = a[sfid - 1, 1] + f(intfrac * f(a[sfid, 1] - a[sfid - 1, 1]))
+    return "", f(mg), f(sb)
+
+
 def num_threads(fast=True):
     return int(lib(fast).orc_num_threads())

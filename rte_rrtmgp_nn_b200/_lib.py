@@ -74,6 +74,7 @@ _SIGS = {
     "rrnn_kdist_set_tsi": (C.c_int, [vp, C.c_float]),
     "rrnn_kdist_set_solar_tables": (C.c_int, [vp, c_float_p, c_float_p, c_float_p]),
     "rrnn_kdist_set_solar_variability": (C.c_int, [vp, C.c_float, C.c_float, C.c_int, C.c_float]),
+    "rrnn_solar_var_ind_interp": (C.c_int, [c_float_p, C.c_int, C.c_float, c_float_p, c_float_p]),
     "rrnn_kdist_get_solar_source": (C.c_int, [vp, c_float_p]),
     "rrnn_kdist_set_optimal_angle_fit": (C.c_int, [vp, c_float_p]),
     "rrnn_compute_optimal_angles": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp]),

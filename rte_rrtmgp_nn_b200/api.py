@@ -1126,6 +1126,49 @@ class ty_cloud_optics(ty_optical_props):
             pass
 
 
+class ty_solar_var:
+    """ty_solar_var (extensions/solar_variability/mo_solar_variability.F90:20-183): the mean-solar-cycle table of the facular
+    and sunspot indices and its interpolation to a cycle fraction; feeds ty_gas_optics_rrtmgp%set_solar_variability.  Host-only,
+    as in the reference."""
+
+    def __init__(self):
+        self.avgcyc_ind = None
+
+    def load(self, avgcyc_ind):
+        """load(avgcyc_ind), :45-69: avgcyc_ind is (nsolarterms = 2, nsolarfrac) in the reference == (nsolarfrac, 2) here."""
+        a = np.ascontiguousarray(avgcyc_ind, np.float32)
+        if a.ndim != 2 or a.shape[1] != 2:
+            return "ty_solar_var%load: avgcyc_ind must be (nsolarfrac, 2)"
+        self.avgcyc_ind = a
+        return ""
+
+    def finalize(self):
+        self.avgcyc_ind = None
+
+    def solar_var_ind_interp(self, solcycfrac):
+        """-> (error_msg, mg_index, sb_index), :91-183.  As in the reference nothing is computed when no table is loaded."""
+        if self.avgcyc_ind is None:
+            return "", None, None
+        out = np.zeros(2, np.float32)
+        try:
+            _lib.check(_lib.lib().rrnn_solar_var_ind_interp(self.avgcyc_ind.ctypes.data_as(_lib.c_float_p), int(self.avgcyc_ind.shape[0]),
+                                                            float(solcycfrac), out[0:1].ctypes.data_as(_lib.c_float_p),
+                                                            out[1:2].ctypes.data_as(_lib.c_float_p)))
+        except RRNNError as e:
+            return str(e), None, None
+        return "", float(out[0]), float(out[1])
+
+
+def load_solar_var_file(path):
+    """Read extensions/solar_variability/rrtmgp-solar-var-tables.nc (classic netCDF): solar_var_avgcyc (n_solar_frac = 134,
+    n_solar_terms = 2), the avgcyc_ind of ty_solar_var.load."""
+    from scipy.io import netcdf_file
+    f = netcdf_file(path, "r", mmap=False)
+    a = np.array(f.variables["solar_var_avgcyc"][:], np.float32)
+    f.close()
+    return a if a.shape[1] == 2 else np.ascontiguousarray(a.T)
+
+
 def load_cloud_lut_file(path):
     """Read a cloud-optics coefficient file (classic netCDF) -> kwargs of ty_cloud_optics.load
     (examples/all-sky/mo_load_cloud_coefficients.F90:23-110)."""

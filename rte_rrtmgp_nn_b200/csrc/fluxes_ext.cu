@@ -9,6 +9,7 @@
 // still declares the upstream (ncol,nlev,ngpt) order.  Sums run serially in g-point order, as the reference loops do,
 // so the results are bit-identical to the restatement in oracle/.
 #include "common.cuh"
+#include <cmath>
 
 namespace rrnn {
 
@@ -205,6 +206,40 @@ extern "C" int rrnn_kdist_set_solar_variability(rrnn_kdist_t* k, float mg_index,
   if (have_tsi) return rrnn_kdist_set_tsi(k, tsi);
   RRNN_CUDA(cudaSetDevice(k->device));
   RRNN_CUDA(cudaMemcpy(k->d_solar_source, k->solar_source.data(), k->solar_source.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// solar_var_ind_interp, extensions/solar_variability/mo_solar_variability.F90:91-183 (host arithmetic, as in the reference)
+extern "C" int rrnn_solar_var_ind_interp(const float* avgcyc_ind, int nsolarfrac, float solcycfrac, float* mg_index_out, float* sb_index_out) {
+  RRNN_CHECK(avgcyc_ind && mg_index_out && sb_index_out && nsolarfrac >= 3, "solar_var_ind_interp: no index table loaded");
+  RRNN_CHECK(solcycfrac >= 0.f && solcycfrac <= 1.f, "solar_var_ind_interp: solcycfrac out of range");
+  auto mg = [&](int i) { return avgcyc_ind[2 * (i - 1)]; };       // avgcyc_ind(1, i), 1-based like the reference
+  auto sb = [&](int i) { return avgcyc_ind[2 * (i - 1) + 1]; };   // avgcyc_ind(2, i)
+  if (solcycfrac == 0.f) { *mg_index_out = mg(1); *sb_index_out = sb(1); return 0; }
+  if (solcycfrac == 1.f) { *mg_index_out = mg(nsolarfrac); *sb_index_out = sb(nsolarfrac); return 0; }
+  volatile float intrvl_len = 1.0f / (float)(nsolarfrac - 2);     // volatile: every step rounded to fp32, no contraction
+  volatile float intrvl_len_hf = 0.5f * intrvl_len;
+  int sfid = 1;
+  volatile float fraclo = 0.f, frachi = intrvl_len_hf;            // the first half month of the cycle
+  volatile float hi_edge = 1.0f - intrvl_len_hf;
+  if (solcycfrac > intrvl_len_hf && solcycfrac < hi_edge) {       // month centres
+    volatile float x = (solcycfrac - intrvl_len_hf) * (float)(nsolarfrac - 2);
+    sfid = (int)std::floor(x) + 2;
+    volatile float lo = (float)(sfid - 2) * intrvl_len;
+    fraclo = lo + intrvl_len_hf;
+    frachi = fraclo + intrvl_len;
+  }
+  if (solcycfrac >= hi_edge) {                                    // the last half month
+    sfid = nsolarfrac - 1;
+    fraclo = hi_edge;
+    frachi = 1.0f;
+  }
+  volatile float num = solcycfrac - fraclo, den = frachi - fraclo;
+  volatile float intfrac = num / den;
+  volatile float dm = mg(sfid + 1) - mg(sfid), ds = sb(sfid + 1) - sb(sfid);
+  volatile float pm = intfrac * dm, ps = intfrac * ds;
+  *mg_index_out = mg(sfid) + pm;
+  *sb_index_out = sb(sfid) + ps;
   return 0;
 }
 

@@ -108,3 +108,31 @@ def test_gas_concs_and_spectral_tables():
     assert abs(np.pi * kd["totplnk"][:, 128].sum() / (5.670374e-8 * T ** 4) - 1) < 2e-3
     ks = spectral.synthetic_kdist_sw(224)
     assert abs(ks["solar_source"].sum() - 1361.0) < 1e-2
+
+
+def test_solar_var_ind_interp_host_routine():
+    """ty_solar_var (extensions/solar_variability/mo_solar_variability.F90:20-183), a HOST-only routine in the reference and here:
+    the library / Python mirror against the oracle's step-by-step restatement (bit for bit) and against an independent formulation
+    (piecewise-linear through the end points and the month centres) on the reference's own table."""
+    import oracle as O
+    from rte_rrtmgp_nn_b200 import api
+    tab = api.load_solar_var_file(os.path.join(H.ROOT, "data", "solar_variability", "rrtmgp-solar-var-tables.nc"))
+    assert tab.shape == (134, 2)
+    sv = api.ty_solar_var()
+    assert sv.solar_var_ind_interp(0.3) == ("", None, None)          # no table loaded: nothing computed, no message (as the reference)
+    assert sv.load(tab) == ""
+    n = tab.shape[0]
+    xs = np.concatenate([[0.0, 1.0], 0.5 / (n - 2) * np.array([0.5, 1.0, 1.5]), 1 - 0.5 / (n - 2) * np.array([0.5, 1.0, 1.5]),
+                         np.random.default_rng(3).uniform(0, 1, 200)]).astype(np.float32)
+    knots = np.concatenate([[0.0], (np.arange(n - 2) + 0.5) / (n - 2), [1.0]])
+    for x in xs:
+        err, mg, sb = sv.solar_var_ind_interp(float(x))
+        oerr, omg, osb = O.solar_var_ind_interp(tab, x)
+        assert err == oerr == ""
+        assert np.float32(mg) == omg and np.float32(sb) == osb, (x, mg, omg, sb, osb)
+        assert abs(mg - np.interp(float(x), knots, tab[:, 0].astype(np.float64))) <= 2e-6 * abs(tab[:, 0]).max()
+        assert abs(sb - np.interp(float(x), knots, tab[:, 1].astype(np.float64))) <= 2e-6 * abs(tab[:, 1]).max() + 1e-9
+    for bad in (-0.01, 1.01):
+        assert sv.solar_var_ind_interp(bad)[0] == "solar_var_ind_interp: solcycfrac out of range" == O.solar_var_ind_interp(tab, bad)[0]
+    sv.finalize()
+    assert sv.avgcyc_ind is None

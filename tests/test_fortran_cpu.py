@@ -207,12 +207,14 @@ REFERENCE_SIGNATURES = {
     "set_solar_variability": "this mg_index sb_index tsi",
     "rte_rrtmgp_config_checks_each": "extents values",
     "rte_rrtmgp_config_checks_all": "do_checks",
+    "solar_var_ind_interp": "this solcycfrac mg_index sb_index",
 }
 REFERENCE_FILES = {
     "gas_optics_int": "rrtmgp/mo_gas_optics_rrtmgp.F90", "gas_optics_ext": "rrtmgp/mo_gas_optics_rrtmgp.F90", "rte_lw": "rte/mo_rte_lw.F90",
     "rte_sw": "rte/mo_rte_sw.F90", "compute_heating_rate": "extensions/mo_heating_rates.F90", "load_netcdf": "neural/mod_network_rrtmgp.F90",
     "set_tsi": "rrtmgp/mo_gas_optics_rrtmgp.F90", "set_solar_variability": "rrtmgp/mo_gas_optics_rrtmgp.F90",
     "rte_rrtmgp_config_checks_each": "rte/mo_rte_rrtmgp_config.F90", "rte_rrtmgp_config_checks_all": "rte/mo_rte_rrtmgp_config.F90",
+    "solar_var_ind_interp": "extensions/solar_variability/mo_solar_variability.F90",
 }
 
 
@@ -239,11 +241,11 @@ def test_public_procedures_keep_the_reference_argument_lists():
 def test_veneer_declares_the_reference_modules_and_types():
     src = "\n".join(re.sub(r"[ \t]+", " ", st) for st in logical_lines(os.path.join(FORTRAN, "mo_rrnn_veneer.F90"))).lower()
     for mod in ("mo_rte_kind", "mod_network_rrtmgp", "mo_gas_concentrations", "mo_optical_props", "mo_source_functions", "mo_fluxes",
-                "mo_gas_optics_rrtmgp", "mo_rte_lw", "mo_rte_sw", "mo_heating_rates", "mo_cloud_optics"):
+                "mo_gas_optics_rrtmgp", "mo_rte_lw", "mo_rte_sw", "mo_heating_rates", "mo_cloud_optics", "mo_solar_variability"):
         assert re.search(rf"^module {mod}$", src, re.M), mod
         assert re.search(rf"^end module {mod}$", src, re.M), mod
     for ty in ("rrtmgp_network_type", "ty_gas_concs", "ty_optical_props_1scl", "ty_optical_props_2str", "ty_source_func_lw",
-               "ty_fluxes_broadband", "ty_fluxes_flexible", "ty_gas_optics_rrtmgp", "ty_cloud_optics"):
+               "ty_fluxes_broadband", "ty_fluxes_flexible", "ty_gas_optics_rrtmgp", "ty_cloud_optics", "ty_solar_var"):
         assert re.search(rf"^type(, [^:]*)? :: {ty}$", src, re.M), ty
     assert re.search(r"generic, public :: gas_optics => gas_optics_int, gas_optics_ext", src)
     # balanced program units

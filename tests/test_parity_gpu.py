@@ -1259,6 +1259,13 @@ def test_optimal_angles_and_solar_variability(gpu_ctx):
     assert ks.set_solar_variability(0.152, 0.0009, tsi=1360.5) == ""
     want = O.set_solar_variability(q, kds["solar_source_facular"], kds["solar_source_sunspot"], 0.152, 0.0009, tsi=1360.5)
     assert np.allclose(ks.get_solar_source(), want, rtol=3e-7, atol=0) and abs(ks.get_solar_source().sum() - 1360.5) < 0.01
+    # the indices of a point of the mean solar cycle (ty_solar_var%solar_var_ind_interp on the reference's table) into the same call
+    import os
+    sv = api.ty_solar_var(); assert sv.load(api.load_solar_var_file(os.path.join(H.ROOT, "data", "solar_variability", "rrtmgp-solar-var-tables.nc"))) == ""
+    err, mg, sb = sv.solar_var_ind_interp(0.37)
+    assert err == "" and ks.set_solar_variability(mg, sb) == ""
+    _, omg, osb = O.solar_var_ind_interp(sv.avgcyc_ind, 0.37)
+    assert np.array_equal(ks.get_solar_source(), O.set_solar_variability(q, kds["solar_source_facular"], kds["solar_source_sunspot"], omg, osb))
     assert ks.set_solar_variability(-1.0, 0.001) == "mg_index out of range"
     assert ks.set_solar_variability(-1.0, -0.001) == "sb_index out of range"
     assert "no solar variability tables" in _loaded(api, gpu_ctx, spectral.synthetic_kdist_sw(224)).set_solar_variability(0.15, 0.001)
