@@ -74,6 +74,20 @@ int main() {
   double sum = 0;
   for (float v : k_sw.get_solar_source()) sum += v;
   CHECK(std::fabs(sum - 100.0) < 1e-3);
+  {  // ty_solar_var: a four-point mean cycle (end points + two month centres at 0.25 and 0.75) -- exact expectations
+    const float tab[8] = {1.f, 10.f, 2.f, 20.f, 4.f, 40.f, 8.f, 80.f};   // [nsolarfrac][2]: mg, sb
+    rrtmgp_nn::ty_solar_var sv;
+    float mg = -1.f, sb = -1.f;
+    CHECK(sv.solar_var_ind_interp(0.5f, mg, sb).empty() && mg == -1.f);   // no table: nothing computed, no message
+    CHECK(sv.load(tab, 4).empty());
+    CHECK(sv.solar_var_ind_interp(0.f, mg, sb).empty() && mg == 1.f && sb == 10.f);
+    CHECK(sv.solar_var_ind_interp(1.f, mg, sb).empty() && mg == 8.f && sb == 80.f);
+    CHECK(sv.solar_var_ind_interp(0.125f, mg, sb).empty() && mg == 1.5f && sb == 15.f);   // half way through the first half interval
+    CHECK(sv.solar_var_ind_interp(0.5f, mg, sb).empty() && mg == 3.f && sb == 30.f);      // half way between the month centres
+    CHECK(sv.solar_var_ind_interp(0.875f, mg, sb).empty() && mg == 6.f && sb == 60.f);
+    CHECK(sv.solar_var_ind_interp(1.5f, mg, sb) == "solar_var_ind_interp: solcycfrac out of range");
+    CHECK(sv.solar_var_ind_interp(0.5f, mg, sb).empty() && k_sw.set_solar_variability(mg, sb * 1e-4f).empty());
+  }
   CHECK(k_sw.set_solar_variability(-1.f, 0.001f) == "mg_index out of range");
   CHECK(k_sw.set_solar_variability(-1.f, -0.001f) == "sb_index out of range");
   CHECK(k_sw.set_tsi(-5.f) == "tsi out of range");
