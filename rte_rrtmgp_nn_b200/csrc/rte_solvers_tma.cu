@@ -1181,6 +1181,9 @@ constexpr int LW7_ROW = 1024, LW7_S = 512;   // reverse-sweep row of one layer: 
 #ifndef RRNN_V7_LW_S
 #define RRNN_V7_LW_S 2      // stages of the input ring
 #endif
+#ifndef RRNN_V7_LW_SB
+#define RRNN_V7_LW_SB 2     // stages of the upward sweep's ring (bulk copies of reverse-sweep rows in flight ahead of their use)
+#endif
 #ifndef RRNN_V7_LW_MINB
 #define RRNN_V7_LW_MINB 2   // 2 CTAs of 128 threads: the shared memory (23 KB per solver) allows 8 - 9 solver warps per SM
 #endif
@@ -1193,7 +1196,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V7_LW_MINB) lw_solver_v7(
                                                    const __grid_constant__ CUtensorMap tm_bl, const __grid_constant__ CUtensorMap tm_bv,
                                                    const __grid_constant__ CUtensorMap tm_cld) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  constexpr int U = 8, S = RRNN_V7_LW_S, SB = 2, H = 4, NH = U / H, RB = 512;   // groups of 8 layers (one TMA box, rows of 128 g-points), computed in halves of 4
+  constexpr int U = 8, S = RRNN_V7_LW_S, SB = RRNN_V7_LW_SB, H = 4, NH = U / H, RB = 512;   // groups of 8 layers (one TMA box, rows of 128 g-points), computed in halves of 4
   constexpr int PFR = COMPACT ? (TOP ? U + 1 : U) : U;
   constexpr int OFF_PF = U * RB, OFF_3 = OFF_PF + PFR * RB, OFF_BV = OFF_3 + U * 64;
   constexpr int OFF_CLD = COMPACT ? OFF_BV + U * 64 : 3 * U * RB;   // CLD: by-band cloud optical depth (U rows of 64 B)
@@ -1612,7 +1615,7 @@ static int launch_lw_v7(rrnn_ctx_t* ctx, LwParams& p) {
   const int G = p.ngpt, L = p.nlay;
   const int csize = (G + 127) / 128;
   const bool compact = p.planck_lay != nullptr, cld = p.cld_tau != nullptr, bnd = p.bnd_up != nullptr;
-  constexpr int U = 8, S = RRNN_V7_LW_S, SB = 2;
+  constexpr int U = 8, S = RRNN_V7_LW_S, SB = RRNN_V7_LW_SB;
   if ((G & 3) || G < 128 || csize > 8 || L < U) return -1;
   if ((compact || cld) && (p.pairs_in_band < 2 || !p.gpt2band)) return -1;   // a lane's four g-points share their band look-ups
   if (compact && !p.planck_lev) return -1;
