@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V7_SW_MINB) sw_solver_v7(
           gg[2 * uu + 1] = splat2(0.0f);
         }
         f2 Rdif[2 * H], Tdif[2 * H], Rdir[2 * H], Tdir[2 * H], Tnos[2 * H];
-        two_stream2_batch<FAST, false, 2 * H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+        two_stream2_batch<FAST, false, 2 * H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos, splat2(pp.neg_zero));
 #pragma unroll
         for (int uu = 0; uu < H; ++uu) {
           const int u = h * H + uu;

@@ -219,16 +219,24 @@ __device__ __forceinline__ void two_stream2(f2 tau, f2 w0, f2 gg, float mu0, flo
 // The same coefficients for U layers at once, written step by step across the layers: the U evaluations are independent,
 // and presenting them to the compiler already interleaved is what lets one warp cover its own MUFU / FMA latencies
 // (each warp runs alone on its scheduler slot most of the time).
+// nz: -0.0 from the kernel parameters (see mul_keep): gamma2 = 0.75 w0 as ONE instruction that ptxas cannot contract into the sums
+// gamma1 +- gamma2 (the reference rounds gamma2 before it adds).
 template <bool FAST, bool HAS_G, int U>
 __device__ __forceinline__ void two_stream2_batch(const f2 (&tau)[U], const f2 (&w0)[U], const f2 (&gg)[U], float mu0, float mu0_inv,
-                                                  f2 (&Rdif)[U], f2 (&Tdif)[U], f2 (&Rdir)[U], f2 (&Tdir)[U], f2 (&Tnos)[U]) {
+                                                  f2 (&Rdif)[U], f2 (&Tdif)[U], f2 (&Rdir)[U], f2 (&Tdir)[U], f2 (&Tnos)[U],
+                                                  f2 nz = splat2(-0.0f)) {
   const float k_min = 1.e-4f;       // mo_rte_solver_kernels.F90:76-82 (single precision)
   const float eps = 1.1920929e-7f;  // epsilon(1._sp)
   const f2 one = splat2(1.0f), quarter = splat2(0.25f), half = splat2(0.5f);
   const f2 mu = splat2(mu0), nmi = splat2(-mu0_inv);
   f2 gamma1[U], gamma2[U], gamma3[U], gamma4[U], alpha1[U], alpha2[U], k[U], ekt[U];
+  // FAST: both exponentials are bare ex2 of tau * (-log2 e) * {1/mu0, k}: the scaled optical depth is formed once
+  f2 tl[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) Tnos[u] = tau[u] * nmi;
+  for (int u = 0; u < U; ++u) {
+    if (FAST) { tl[u] = tau[u] * splat2(-1.4426950408889634f); Tnos[u] = tl[u] * splat2(mu0_inv); }
+    else Tnos[u] = tau[u] * nmi;
+  }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (HAS_G) {
@@ -242,8 +250,10 @@ __device__ __forceinline__ void two_stream2_batch(const f2 (&tau)[U], const f2 (
       // g = 0 (always, on the NN path): gamma3 = gamma4 = 1/2 exactly, alpha1 = alpha2 = (gamma1 + gamma2)/2
       // (not w0 * 0.75: ptxas contracts a single multiply into the sums below and the bits leave the reference's; the trailing
       // exact * 0.25 is harmless when contracted)
-      gamma1[u] = fnma2(w0[u], splat2(5.0f), splat2(8.0f)) * quarter;
-      gamma2[u] = (splat2(3.0f) * w0[u]) * quarter;
+      // one instruction each, same bits: RN(8 - 5 w) / 4 == RN(2 - 1.25 w) and RN(3 w) / 4 == RN(0.75 w) (a power of two
+      // commutes with the rounding)
+      gamma1[u] = fma2(w0[u], splat2(-1.25f), splat2(2.0f));
+      gamma2[u] = fma2(w0[u], splat2(0.75f), nz);
       gamma3[u] = half;
       gamma4[u] = half;
       alpha1[u] = (gamma1[u] + gamma2[u]) * half;
@@ -251,13 +261,13 @@ __device__ __forceinline__ void two_stream2_batch(const f2 (&tau)[U], const f2 (
     }
   }
 #pragma unroll
-  for (int u = 0; u < U; ++u) Tnos[u] = exp2x<FAST>(Tnos[u]);
+  for (int u = 0; u < U; ++u) Tnos[u] = FAST ? ex2_raw(Tnos[u]) : exp2x<FAST>(Tnos[u]);
 #pragma unroll
   for (int u = 0; u < U; ++u) k[u] = max2((gamma1[u] - gamma2[u]) * (gamma1[u] + gamma2[u]), splat2(k_min));
 #pragma unroll
   for (int u = 0; u < U; ++u) k[u] = sqrt2<FAST>(k[u]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) ekt[u] = exp2x<FAST>(neg2(tau[u]) * k[u]);
+  for (int u = 0; u < U; ++u) ekt[u] = FAST ? ex2_raw(tl[u] * k[u]) : exp2x<FAST>(neg2(tau[u]) * k[u]);
   f2 e2kt[U], k2e[U], ome2[U], RT[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -303,6 +313,7 @@ struct SwV5Params {
   int ngroups;
   int warp_smem;
   int* next_col;
+  float neg_zero = -0.0f;  // see mul_keep / two_stream2_batch
 };
 
 // ==================================================================================================== v6
@@ -649,7 +660,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
         // (warp-uniform) keeps the gas properties as they are -- tau + 0, ssa = (tau ssa) / tau up to its last bit, g = 0
         const bool cloudy = GM == 2 && (RRNN_SW_CLD_SKIP == 0 || __any_sync(0xffffffffu, cloud_here));
         if (GM == 2 && RRNN_SW_CLD_SKIP == 1 && !cloudy) {
-          two_stream2_batch<FAST, false, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+          two_stream2_batch<FAST, false, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos, splat2(pp.neg_zero));
         } else {
           if (GM == 2 && cloudy) {   // inc_2stream_by_2stream_bybnd with g1 == 0, same operation order (products first, then the sum)
             const f2 eps = splat2(3.0f * 1.17549435e-38f);
@@ -665,7 +676,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS, RRNN_V6_MINB) sw_solver_v6(con
               tau[uu] = tau12;
             }
           }
-          two_stream2_batch<FAST, HAS_G, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos);
+          two_stream2_batch<FAST, HAS_G, H>(tau, w0, gg, mu0, mu0_inv, Rdif, Tdif, Rdir, Tdir, Tnos, splat2(pp.neg_zero));
         }
 #pragma unroll
         for (int uu = 0; uu < H; ++uu) {
