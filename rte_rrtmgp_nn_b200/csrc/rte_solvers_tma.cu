@@ -230,13 +230,8 @@ __device__ __forceinline__ void two_stream2_batch(const f2 (&tau)[U], const f2 (
   const f2 one = splat2(1.0f), quarter = splat2(0.25f), half = splat2(0.5f);
   const f2 mu = splat2(mu0), nmi = splat2(-mu0_inv);
   f2 gamma1[U], gamma2[U], gamma3[U], gamma4[U], alpha1[U], alpha2[U], k[U], ekt[U];
-  // FAST: both exponentials are bare ex2 of tau * (-log2 e) * {1/mu0, k}: the scaled optical depth is formed once
-  f2 tl[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    if (FAST) { tl[u] = tau[u] * splat2(-1.4426950408889634f); Tnos[u] = tl[u] * splat2(mu0_inv); }
-    else Tnos[u] = tau[u] * nmi;
-  }
+  for (int u = 0; u < U; ++u) Tnos[u] = tau[u] * nmi;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (HAS_G) {
@@ -261,13 +256,13 @@ __device__ __forceinline__ void two_stream2_batch(const f2 (&tau)[U], const f2 (
     }
   }
 #pragma unroll
-  for (int u = 0; u < U; ++u) Tnos[u] = FAST ? ex2_raw(Tnos[u]) : exp2x<FAST>(Tnos[u]);
+  for (int u = 0; u < U; ++u) Tnos[u] = exp2x<FAST>(Tnos[u]);
 #pragma unroll
   for (int u = 0; u < U; ++u) k[u] = max2((gamma1[u] - gamma2[u]) * (gamma1[u] + gamma2[u]), splat2(k_min));
 #pragma unroll
   for (int u = 0; u < U; ++u) k[u] = sqrt2<FAST>(k[u]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) ekt[u] = FAST ? ex2_raw(tl[u] * k[u]) : exp2x<FAST>(neg2(tau[u]) * k[u]);
+  for (int u = 0; u < U; ++u) ekt[u] = exp2x<FAST>(neg2(tau[u]) * k[u]);
   f2 e2kt[U], k2e[U], ome2[U], RT[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
