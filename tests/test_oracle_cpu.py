@@ -436,7 +436,7 @@ def _ref_python_case():
     return gold, dict(play=d["p_lay"][cols], plev=d["p_lev"][cols], tlay=d["t_lay"][cols], gases=gases)
 
 
-REF_PY_MODELS = dict(sw_abs=H.SW_G224[0], sw_ray=H.SW_G224[1], lw_abs=H.LW_G256[0])
+REF_PY_MODELS = dict(sw_abs=H.SW_G224[0], sw_ray=H.SW_G224[1], lw_abs=H.LW_G256[0], lw128_abs=H.LW_G128[0])
 
 
 def test_oracle_pinned_by_the_references_own_python():
@@ -453,8 +453,11 @@ def test_oracle_pinned_by_the_references_own_python():
         m = nc4min.load_nn_model(os.path.join(H.NN_DIR, fn))
         net = O.Net(m)
         # a-W: the constants the weight files carry are the reference's (ml_scaling_coefficients.py), to the bit
-        assert np.array_equal(m["ymean"], gold[tag + "_ymean"].astype(np.float32))
-        assert np.array_equal(m["ystd"], gold[tag + "_ysigma"].astype(np.float32))
+        if tag + "_ymean" in gold.files:
+            assert np.array_equal(m["ymean"], gold[tag + "_ymean"].astype(np.float32))
+            assert np.array_equal(m["ystd"], gold[tag + "_ysigma"].astype(np.float32))
+        else:   # the 2021 generation: the INPUT scaling is the reference's xmin_all / xmax_all (:14-28)
+            assert np.array_equal(m["xmin"], gold[tag + "_xmin"]) and np.array_equal(m["xmax"], gold[tag + "_xmax"])
         # a2: compute_nn_inputs against preproc_minmax_inputs_rrtmgp (:416-435): values in [0, 1], fp32 log / fourth root
         x = O.compute_nn_inputs(net, a["play"], a["tlay"], a["gases"])
         assert np.abs(x - gold[tag + "_nn_inputs"]).max() <= 1e-6

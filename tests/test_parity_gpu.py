@@ -1515,6 +1515,19 @@ def test_cuda_path_against_the_references_own_python(gpu_ctx, nn_variant):
     bulk = H.tau_rel_err(op.tau.cpu().numpy(), gold["lw_abs_tau"], floor=1e-2).max()
     print(f"LW tau vs the reference's Python: {e:.2e} (bulk {bulk:.2e})")
     assert e <= nn_variant and bulk <= 0.25 * nn_variant
+    # the 2021 generation (g128; input scaling = the reference's xmin_all / xmax_all): inputs and LW tau
+    lw128 = H.device_nets(gpu_ctx, H.LW_G128)
+    x = torch.empty((ncol, nlay, 18), device="cuda")
+    _lib.check(lib.rrnn_compute_nn_inputs(gpu_ctx.h, lw128[0].h, ncol, nlay, P(play), P(tlay), gases, ngas, P(x)))
+    assert np.abs(x.cpu().numpy() - gold["lw128_abs_nn_inputs"]).max() <= 2e-6
+    k128 = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k128.load(spectral.synthetic_kdist_lw(ngpt=128)) == ""
+    op128 = api.ty_optical_props_1scl(); assert op128.alloc_1scl(ncol, nlay, k128) == ""
+    src128 = api.ty_source_func_lw(); assert src128.alloc(ncol, nlay, k128) == ""
+    assert k128.gas_optics(a["play"], a["plev"], a["tlay"], tsfc, H.gas_concs(a["gases"]), op128, src128, neural_nets=lw128) == ""
+    e = H.tau_rel_err(op128.tau.cpu().numpy(), gold["lw128_abs_tau"]).max()
+    bulk = H.tau_rel_err(op128.tau.cpu().numpy(), gold["lw128_abs_tau"], floor=1e-2).max()
+    print(f"LW g128 tau vs the reference's Python: {e:.2e} (bulk {bulk:.2e})")
+    assert e <= nn_variant and bulk <= 0.25 * nn_variant
     # SW: tau = tau_abs + tau_ray, ssa = tau_ray / tau (mo_gas_optics_rrtmgp.F90:529-573)
     k_sw = api.ty_gas_optics_rrtmgp(gpu_ctx); assert k_sw.load(spectral.synthetic_kdist_sw(ngpt=224)) == ""
     op2 = api.ty_optical_props_2str(); assert op2.alloc_2str(ncol, nlay, k_sw) == ""

@@ -49,6 +49,9 @@ MODELS = {  # tag -> (file under data/nn, the reference's constants for it)
     "sw_abs": ("sw-g224-2018-12-04-absorption_16_16.nc", "ymeans_sw_absorption_224", "ysigma_sw_absorption_224"),
     "sw_ray": ("sw-g224-2018-12-04-rayleigh_16_16.nc", "ymeans_sw_ray_224", "ysigma_sw_ray_224"),
     "lw_abs": ("lw-g256-2018-12-04_absorption_58_58.nc", "ymeans_lw_absorption_256", "ysigma_lw_absorption_256"),
+    # the 2021 generation: its INPUT scaling is the reference's xmin_all / xmax_all (ml_scaling_coefficients.py:14-28), which the 16 shipped
+    # lw-g128 files carry to the bit; its output scaling exists in the weight file only (None: taken from the file)
+    "lw128_abs": ("lw-g128-210809_absorption_BEST.nc", None, None),
 }
 
 
@@ -65,8 +68,15 @@ def main():
     for tag, (fn, ym_name, ys_name) in MODELS.items():
         m = load_nn_model(os.path.join(ROOT, "data", "nn", fn))
         names = m["input_names"]
-        out[tag + "_ymean"] = np.asarray(getattr(SC, ym_name))
-        out[tag + "_ysigma"] = np.asarray(getattr(SC, ys_name))
+        if ym_name is None:
+            ymean, ysigma = m["ymean"].astype(np.float64), m["ystd"].astype(np.float64)
+            xco = tuple(np.asarray(c, np.float32)[[SC.input_names_all.index(n) for n in names]] for c in SC.xcoeffs_all)
+            out[tag + "_xmin"], out[tag + "_xmax"] = xco
+        else:
+            ymean, ysigma = getattr(SC, ym_name).astype(np.float64), getattr(SC, ys_name).astype(np.float64)
+            out[tag + "_ymean"] = np.asarray(getattr(SC, ym_name))
+            out[tag + "_ysigma"] = np.asarray(getattr(SC, ys_name))
+            xco = (m["xmin"], m["xmax"])
         # the raw inputs, one row per (column, layer), in the order of the model's own input names
         x_raw = np.empty((ncol * nlay, len(names)), np.float32)
         for i, n in enumerate(names):
@@ -76,14 +86,14 @@ def main():
             elif n == "o3": v = o3
             else: v = np.broadcast_to(d["gm_" + n][cols][:, None], (ncol, nlay))
             x_raw[:, i] = np.asarray(v, np.float32).reshape(-1)
-        x = P.preproc_minmax_inputs_rrtmgp(x_raw, (m["xmin"], m["xmax"]))
+        x = P.preproc_minmax_inputs_rrtmgp(x_raw, xco)
         out[tag + "_nn_inputs"] = x.reshape(ncol, nlay, -1)
         a = x.astype(np.float64)
         for l in range(3):
             a = a @ m["W"][l].astype(np.float64) + m["b"][l].astype(np.float64)
             if l < 2:
                 a = a / (np.abs(a) + 1)
-        y = P.preproc_pow_standardization_reverse(a, 8, getattr(SC, ym_name).astype(np.float64), getattr(SC, ys_name).astype(np.float64))
+        y = P.preproc_pow_standardization_reverse(a, 8, ymean, ysigma)
         out[tag + "_tau"] = (y * col_dry.reshape(-1, 1).astype(np.float64)).reshape(ncol, nlay, -1).astype(np.float32)   # (stored rounded to fp32)
     # heating rates of a smooth synthetic flux profile on the RFMIP pressure levels
     rng = np.random.default_rng(7)
