@@ -1661,7 +1661,8 @@ static int launch_lw_v7(rrnn_ctx_t* ctx, LwParams& p) {
   const size_t per_cta = (size_t)L * v5::LW7_ROW;
   // scratch budget: measured optimum at 137 layers (125 ... 145 MB = 6.3 ... 7.3 of the 8 solver warps per SM the shared memory allows:
   // 2.54 - 2.62 ms per 30 000 columns against 2.80 - 2.85 uncapped and 2.75 for lw_solver_v6)
-  constexpr int kScratchMb = 140;
+  constexpr int kScratchMbDefault = 140;
+  static const int kScratchMb = getenv("RRNN_LW_SCRATCH_MB") ? atoi(getenv("RRNN_LW_SCRATCH_MB")) : kScratchMbDefault;   // (A/B knob)
 #define LW7(F, T, D, C, CL, B) launch_clustered(ctx, v5::lw_solver_v7<F, T, D, C, CL, B>, csize, smem, per_cta, kScratchMb, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_lay, tm_lev, tm_bl, tm_bv, tm_cld)
 #define LW7C(F, T, D, CL) (compact ? LW7(F, T, D, true, CL, false) : LW7(F, T, D, false, CL, false))
   if (bnd) {
@@ -1818,7 +1819,8 @@ int launch_sw_v6(rrnn_ctx_t* ctx, SwParams& p, bool fast) {
   const size_t smem = (size_t)S * stage + 16 * v5::TR_PITCH * 4 + 2 * (size_t)(3 * (L + 1) + 1) * 4 + (S + SB) * 8;
   const size_t per_cta = (size_t)L * v5::SW6_ROW;
   const bool top = p.top_at_1 != 0;
-#define SW6(F, GMODE, T) launch_clustered(ctx, v5::sw_solver_v6<F, GMODE, T>, csize, smem, per_cta, 400, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
+  static const int kSwScratchMb = getenv("RRNN_SW_SCRATCH_MB") ? atoi(getenv("RRNN_SW_SCRATCH_MB")) : 400;   // (A/B knob; 400 = no cap at 137 layers)
+#define SW6(F, GMODE, T) launch_clustered(ctx, v5::sw_solver_v6<F, GMODE, T>, csize, smem, per_cta, kSwScratchMb, 2, p.ncol, pp, &pp.b.scratch, tm_tau, tm_ssa, tm_g)
 #define SW6T(F, GMODE) (top ? SW6(F, GMODE, true) : SW6(F, GMODE, false))
   if (p.bnd_up) {   // by-band outputs (rrnn_rte_sw_byband): g == 0 or a g array, no pending clouds
     if (gm == 2 || !p.bnd_dn || !p.bnd_dir || p.nbnd * 16 != G) return -1;
